@@ -1,0 +1,200 @@
+"""Generate ``tests/golden/*.npz`` by running the UNMODIFIED reference in this container.
+
+Test infrastructure only.  Usage (from the repo root, build container only — needs
+``/root/reference``):
+
+    python -m oracle.make_golden            # all cases
+    python -m oracle.make_golden c1_singlet # some cases
+
+For every case in ``tests/scenes.py::CASES`` the script
+  1. builds the scene from the reference's own classes and samples a seeded bundle with
+     the reference's own ``Bundle.sample``;
+  2. runs the reference trace (``SequentialScene.simulate`` — scene/sequential.py:12 — or
+     the ``Scene.step`` bounce loop — scene/base.py:129-235) in fp32 and again in fp64;
+  3. for the gradient cases, back-propagates a scalar loss through the reference with
+     torch autograd and stores d loss / d parameter and d loss / d input rays;
+  4. compiles the *reference objects* with this repo's scene compiler and stores the
+     surface table, so tests can check that this repo's mirror classes compile to the very
+     same table without the reference being present.
+The fixtures are small (N_RAYS rays per case) and committed.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle.ref_loader import load_reference          # noqa: E402
+from raytracetorch_b200.table import compile_elements  # noqa: E402
+import scenes                                          # noqa: E402
+
+N_RAYS = 3000
+NBOUNCES = 8
+OUT = os.path.join(ROOT, "tests", "golden")
+SEED = 1234
+
+
+def ref_namespace():
+    R = load_reference()
+    return types.SimpleNamespace(elements=R.elements, geom=R.geom, phys=R.phys, rays=R.rays, scene=R.scene,
+                                 optim=R.optim, render=R.render)
+
+
+def _run_seq(ns, elements, rays):
+    scene = ns.scene.SequentialScene(elements)
+    out = scene.simulate(rays)
+    return out
+
+
+def _run_nonseq(ns, elements, rays, nb=NBOUNCES):
+    scene = ns.scene.Scene()
+    for e in elements:
+        scene.add_element(e)
+    scene.rays = rays
+    scene.Nbounces = nb
+    scene._build_index_maps()
+    # bounce loop of Scene.simulate (scene/base.py:139-142) with a per-bounce winner log
+    seq = torch.full((rays.pos.shape[0], nb), -1, dtype=torch.long)
+    for b in range(nb):
+        if not (scene.rays.intensity > 0).any():
+            break
+        res = scene.ray_cast(scene.rays)
+        if res is not None:
+            hit_mask, we, ws = res
+            active = hit_mask & (scene.rays.intensity > 0)
+            # flat row index = position in (map_to_element, map_to_surface)
+            starts = torch.tensor([0] + [len(e.shape) for e in elements]).cumsum(0)[:-1]
+            seq[active, b] = (starts[we] + ws)[active]
+        scene.step()
+    return scene.rays, seq
+
+
+def _sensor_dump(elements, dtype):
+    out = {}
+    slot = 0
+    for e in elements:
+        if type(e).__name__ == "Sensor":
+            if e.hitLocs:
+                locs, w, _ = e.getHitsTensors()
+            else:
+                locs, w = torch.zeros(0, 3, dtype=dtype), torch.zeros(0, dtype=dtype)
+            out[f"sensor{slot}_loc"] = locs.detach().numpy()
+            out[f"sensor{slot}_w"] = w.detach().numpy()
+            slot += 1
+    return out
+
+
+def _cast_rays(ns, rays, dtype):
+    c = lambda t: t.detach().clone().to(dtype)
+    return ns.rays.Rays(pos=c(rays.pos), dir=c(rays.dir), intensity=c(rays.intensity),
+                        id=rays.id, wavelength=c(rays.wavelength), batch_size=rays.batch_size)
+
+
+def gen_forward_case(ns, name):
+    builder, kw, mode, bspec = scenes.CASES[name]
+    data = {}
+    rays0 = scenes.make_bundle(ns, bspec, N_RAYS, SEED)
+    data["in_pos"], data["in_dir"] = rays0.pos.numpy().copy(), rays0.dir.numpy().copy()
+    data["in_intensity"] = rays0.intensity.numpy().copy()
+    for tag, dtype in (("f32", torch.float32), ("f64", torch.float64)):
+        elements = builder(ns, **kw)
+        if dtype == torch.float64:
+            for e in elements:
+                e.double()
+        rays = _cast_rays(ns, rays0, dtype)
+        with torch.no_grad():
+            if mode == "seq":
+                out = _run_seq(ns, elements, rays)
+            else:
+                out, seq = _run_nonseq(ns, elements, rays)
+                data[f"{tag}_seq"] = seq.numpy()
+        data[f"{tag}_pos"], data[f"{tag}_dir"] = out.pos.numpy(), out.dir.numpy()
+        data[f"{tag}_intensity"] = out.intensity.numpy()
+        for k, v in _sensor_dump(elements, dtype).items():
+            data[f"{tag}_{k}"] = v
+        if dtype == torch.float32:
+            tab = compile_elements(builder(ns, **kw))
+            data["table_f"], data["table_i"] = tab.f.detach().numpy(), tab.i.numpy()
+    data["mode"] = np.array(mode)
+    data["nbounces"] = np.array(NBOUNCES)
+    return data
+
+
+GRAD_CASES = {
+    # name: (builder, kwargs, bundle spec) — sequential scenes with trainable parameters
+    "grad_c3_singlet": (scenes.c1_singlet, {"physical": True, "grads": True}, ("coll", 5.0, -10.0, None)),
+    "grad_c3_singlet_ref_order": (scenes.c1_singlet, {"grads": True}, ("coll", 5.0, -10.0, None)),
+    "grad_c2_cylindrical": (scenes.c2_cylindrical, {"grads": True}, ("coll", 8.0, -10.0, [0.01, 0.02, 0.0])),
+    "grad_c4_camera_lens": (scenes.c4_camera_lens, {"grads": True}, ("coll", 7.0, -10.0, [0.02, 0.03, 0.0])),
+    "grad_x2_tilted": (scenes.x2_tilted_lenses, {"grads": True}, ("coll", 7.0, -12.0, [0.02, 0.03, 0.0])),
+}
+
+
+def golden_loss(pos, dir_, intensity):
+    """Scalar used by every gradient fixture: touches positions, directions and intensity."""
+    return (intensity * (pos[:, 0] ** 2 + pos[:, 1] ** 2)).mean() \
+        + 0.25 * (intensity * dir_[:, 2]).mean() + 0.1 * (dir_[:, 0] * pos[:, 1]).mean()
+
+
+def gen_grad_case(ns, name):
+    builder, kw, bspec = GRAD_CASES[name]
+    data = {}
+    rays0 = scenes.make_bundle(ns, bspec, N_RAYS, SEED)
+    data["in_pos"], data["in_dir"] = rays0.pos.numpy().copy(), rays0.dir.numpy().copy()
+    data["in_intensity"] = rays0.intensity.numpy().copy()
+    for tag, dtype in (("f32", torch.float32), ("f64", torch.float64)):
+        elements = builder(ns, **kw)
+        if dtype == torch.float64:
+            for e in elements:
+                e.double()
+        rays = _cast_rays(ns, rays0, dtype)
+        rays.pos.requires_grad_(True)
+        rays.dir.requires_grad_(True)
+        rays.intensity.requires_grad_(True)
+        leaf_pos, leaf_dir, leaf_int = rays.pos, rays.dir, rays.intensity
+        out = _run_seq(ns, elements, rays)
+        loss = golden_loss(out.pos, out.dir, out.intensity)
+        loss.backward()
+        data[f"{tag}_loss"] = np.array(loss.item())
+        data[f"{tag}_g_pos"] = leaf_pos.grad.numpy()
+        data[f"{tag}_g_dir"] = leaf_dir.grad.numpy()
+        data[f"{tag}_g_intensity"] = leaf_int.grad.numpy()
+        scene = ns.scene.SequentialScene(elements)
+        for pname, p in scene.named_parameters():
+            if p.requires_grad:
+                g = p.grad if p.grad is not None else torch.zeros_like(p)
+                data[f"{tag}_gp::{pname}"] = g.detach().numpy()
+    return data
+
+
+def main(argv):
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_namespace()
+    wanted = set(argv)
+    for name in scenes.CASES:
+        if wanted and name not in wanted:
+            continue
+        d = gen_forward_case(ns, name)
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **d)
+        alive = (d["f32_intensity"] > 0).mean()
+        print(f"{name:28s} rows={d['table_f'].shape[0]:2d} alive={alive:.3f} "
+              f"sensor_hits={d.get('f32_sensor0_w', np.zeros(0)).shape[0]}")
+    for name in GRAD_CASES:
+        if wanted and name not in wanted:
+            continue
+        d = gen_grad_case(ns, name)
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **d)
+        keys = [k for k in d if k.startswith("f32_gp::")]
+        print(f"{name:28s} loss={float(d['f32_loss']):.6f} params={len(keys)}")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    main(sys.argv[1:])

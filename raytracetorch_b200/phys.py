@@ -1,0 +1,64 @@
+"""Surface interaction descriptors (mirror of the reference's ``phys`` package).
+
+Like ``geom.py`` these are parameter holders: the arithmetic of each interaction
+(``phys/std.py:97-108`` Reflect, ``:123-145`` RefractSnell, ``:227-235`` Transmit,
+``:243-254`` Block, ``phys/filter.py:24-33`` ApertureFilter) lives in the CUDA kernels;
+``PHYS`` is the code the scene compiler writes into the surface table.
+
+Not provided: ``RefractFresnel`` (stochastic, RNG-dependent — no parity definition),
+``Fuzzy`` (arbitrary Python callable), ``Linear`` (ideal elements; listed "next").
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import torch
+import torch.nn as nn
+
+from . import codes as C
+
+
+class SurfaceFunction(nn.Module):
+    PHYS = C.PHYS_TRANSMIT
+
+    def forward(self, local_intersect, ray_dir, normal, **kwargs):
+        """(new_dir [N,3], intensity_mod [N]) — evaluated by the CUDA physics op."""
+        from .ops import physics_apply
+        return physics_apply(self, local_intersect, ray_dir, normal)
+
+
+class Transmit(SurfaceFunction):
+    PHYS = C.PHYS_TRANSMIT
+
+
+class Reflect(SurfaceFunction):
+    PHYS = C.PHYS_REFLECT
+
+
+class Block(SurfaceFunction):
+    PHYS = C.PHYS_BLOCK
+
+
+class RefractSnell(SurfaceFunction):
+    """ior_in: medium on the -normal side, ior_out: medium on the +normal side
+    (phys/std.py:126-132).  Lenses rebind these attributes to shared Parameters."""
+
+    PHYS = C.PHYS_SNELL
+
+    def __init__(self, ior_in, ior_out, ior_in_grad: bool = False, ior_out_grad: bool = False):
+        super().__init__()
+        self.ior_in = nn.Parameter(torch.as_tensor(float(ior_in)), requires_grad=ior_in_grad)
+        self.ior_out = nn.Parameter(torch.as_tensor(float(ior_out)), requires_grad=ior_out_grad)
+
+
+class ApertureFilter(Transmit):
+    """Passes rays whose local hit lies inside the (non-inverted) bound of the surface
+    it was built from, zeroes direction and intensity otherwise (phys/filter.py:10-33)."""
+
+    PHYS = C.PHYS_APERTURE
+
+    def __init__(self, inBounds: Callable):
+        super().__init__()
+        self._inBounds = inBounds
+        # the bounded surface whose rule the kernels evaluate (not registered as a submodule)
+        object.__setattr__(self, "_bound_surface", getattr(inBounds, "__self__", None))
