@@ -1,0 +1,178 @@
+/*
+ * rtt_b200 — C ABI of the B200 (sm_100a) ray-propagation kernels.
+ *
+ * This is the drop-in boundary for the batched ray-trace hot path of RayTraceTorch.
+ * The reference is pure Python/PyTorch and has no FFI of its own; each entry point below
+ * replaces one Python seam of the reference (file:line under /root/reference) and is what
+ * a binding written by the reference's maintainer (ctypes) calls.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says
+ *     "host"; all float arrays are contiguous fp32, int arrays int32, masks uint64/uint8
+ *   - the caller owns every buffer; the library allocates nothing that outlives a call
+ *     and keeps no global state (the surface table is read from device memory and staged
+ *     in shared memory by every thread block), so calls are re-entrant
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *     synchronises
+ *   - return value: 0 on success, a cudaError_t (>0) from the launch, or a negative
+ *     RTT_E_* code for argument errors; rtt_error_string() explains any of them
+ *   - there is NO CPU path: without a CUDA device every compute entry returns an error
+ *
+ * Surface table (built by raytracetorch_b200/table.py from the live nn.Parameters):
+ *   table_f [n_rows, RTT_ROW_F] fp32, table_i [n_rows, RTT_ROW_I] int32; one row per
+ *   (element, surface index) in the reference's flattening order
+ *   (scene/base.py:116-123, scene/sequential.py:17-19).  Layout: see the enums below and
+ *   raytracetorch_b200/codes.py (rtt_layout_query() lets a binding verify both agree).
+ */
+#ifndef RTT_B200_H
+#define RTT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- row layout (floats) ---- */
+enum {
+    RTT_ROW_F = 48, RTT_F_RE = 0, RTT_F_TE = 9, RTT_F_RS = 12, RTT_F_TS = 21,
+    RTT_F_C = 24, RTT_F_K = 25, RTT_F_RADIUS = 26, RTT_F_IOR_IN = 27, RTT_F_IOR_OUT = 28,
+    RTT_N_DIFF = 29, RTT_F_SB = 29, RTT_F_HB = 33, RTT_ROW_G = 48
+};
+/* ---- row layout (ints) ---- */
+enum {
+    RTT_ROW_I = 16, RTT_I_SURF = 0, RTT_I_BOUND = 1, RTT_I_INVERT = 2, RTT_I_SHAPE = 3,
+    RTT_I_PHYS = 4, RTT_I_SENSOR = 5, RTT_I_POLY_FIRST = 6, RTT_I_POLY_COUNT = 7,
+    RTT_I_ELEM = 8, RTT_I_SIDX = 9, RTT_I_FLAGS = 10
+};
+enum { RTT_SURF_PLANE = 0, RTT_SURF_QUADRIC, RTT_SURF_QUADRIC_ZY, RTT_SURF_CYLINDER, RTT_SURF_SPHERE };
+enum { RTT_BOUND_NONE = 0, RTT_BOUND_DISK, RTT_BOUND_RECT, RTT_BOUND_ELLIPSE, RTT_BOUND_HALF, RTT_BOUND_HALF_DISK };
+enum { RTT_SHAPE_NONE = 0, RTT_SHAPE_SPHERIC_FACE, RTT_SHAPE_SPHERIC_EDGE, RTT_SHAPE_CYL_FACE,
+       RTT_SHAPE_CYL_EDGE, RTT_SHAPE_POLY, RTT_SHAPE_OPEN };
+enum { RTT_PHYS_TRANSMIT = 0, RTT_PHYS_SNELL, RTT_PHYS_REFLECT, RTT_PHYS_BLOCK, RTT_PHYS_APERTURE };
+enum { RTT_FLAG_GRAD_POSE_E = 1, RTT_FLAG_GRAD_POSE_S = 2, RTT_FLAG_GRAD_CK = 4,
+       RTT_FLAG_GRAD_RADIUS = 8, RTT_FLAG_GRAD_IOR = 16 };
+enum { RTT_MAX_ROWS = 64, RTT_MAX_SENSORS = 4, RTT_MAX_WAVELENGTHS = 8, RTT_MAX_BOUNCES = 255 };
+
+/* ---- error codes ---- */
+enum { RTT_OK = 0, RTT_E_ARG = -1, RTT_E_ROWS = -2, RTT_E_NO_DEVICE = -3, RTT_E_ALIGN = -4, RTT_E_SENSOR = -5 };
+
+/* arithmetic mode: FAST lets the compiler contract a*b+c into FMA and uses reciprocal
+ * multiplies; EXACT keeps every rounding step of the reference's eager fp32 ops (separately
+ * rounded mul/add, IEEE div/sqrt) — used by the parity tests to get bit-exact masks. */
+enum { RTT_MODE_FAST = 0, RTT_MODE_EXACT = 1 };
+
+/* Sensor image request for one sensor slot.  Bin rule (restating the fixed-range
+ * histogram of gui/workbench.py:615-624 in fp32):
+ *   ix = floor((x - x0) * sx), iy = floor((y - y0) * sy), kept iff 0<=ix<W and 0<=iy<H,
+ *   image[channel, iy, ix] += weight, weight = ray intensity BEFORE the sensor
+ *   (elements/sensor.py:36), channel = wavelength index (0 without a wavelength LUT). */
+typedef struct {
+    float* image;      /* [channels, height, width] fp32, accumulated into (caller zeroes), or NULL */
+    float* record;     /* [n, 4] (hit_local x,y,z, weight) written for rays that hit, or NULL      */
+    int32_t height, width, channels;
+    float x0, y0, sx, sy;
+} rtt_sensor_t;
+
+typedef struct {
+    const float* f;        /* [n_rows, RTT_ROW_F] */
+    const int32_t* i;      /* [n_rows, RTT_ROW_I] */
+    int32_t n_rows;
+    int32_t n_lut;         /* L sample wavelengths, 0 = no per-wavelength index          */
+    const float* lut;      /* [L, n_rows, 2] (ior_in, ior_out) or NULL                   */
+    const float* lut_w;    /* [L] sample wavelengths, same unit as the rays' wavelength  */
+} rtt_table_t;
+
+/* Library identity / layout handshake. which: 0 ROW_F, 1 ROW_I, 2 ROW_G, 3 MAX_ROWS,
+ * 4 N_DIFF, 5 MAX_SENSORS, 6 MAX_WAVELENGTHS, 7 MAX_BOUNCES; returns -1 for unknown. */
+int rtt_version(void);
+int rtt_layout_query(int which);
+const char* rtt_error_string(int code);
+/* Number of kernels this library has launched since load (host counter; bench.py reports it). */
+int64_t rtt_launch_count(void);
+
+/* SequentialScene.simulate(rays) -> rays          (scene/sequential.py:12-36)
+ * Every ray walks all n_rows rows once, in order, state in registers.  Rays that miss a
+ * row are left untouched; dead rays keep walking (reference behaviour).
+ *   in_*        : pos/dir [n,3], intensity [n], wavelength [n] (may be NULL iff n_lut==0)
+ *   out_*       : same shapes (may alias the inputs)
+ *   hitmask     : [n] uint64, bit r set iff the ray interacted with row r (may be NULL)
+ *   sensors     : HOST array of n_sensors requests indexed by the rows' sensor slot        */
+int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_intensity,
+                      const float* in_wavelength,
+                      float* out_pos, float* out_dir, float* out_intensity, uint64_t* hitmask,
+                      const rtt_table_t* table, const rtt_sensor_t* sensors, int32_t n_sensors,
+                      int64_t n, int32_t mode, void* stream);
+
+/* Adjoint of rtt_trace_seq_fwd (replaces torch autograd over scene/sequential.py:12-36 as
+ * driven by tests/test_optimize_singlet.py:66-116 / optim/goals.py:144-187).  Recomputes the
+ * forward per ray from the ORIGINAL inputs and the recorded hitmask, then sweeps the rows in
+ * reverse.
+ *   g_out_*     : upstream gradients of out_pos/out_dir/out_intensity ([n,3],[n,3],[n]); NULL = zero
+ *   g_record    : HOST array [n_sensors] of device pointers [n,4]: upstream gradient of each
+ *                 sensor record (d/d hit_local xyz, d/d weight); entries or the array may be NULL
+ *   g_in_*      : gradients w.r.t. the input rays (NULL to skip)
+ *   g_table     : [n_rows, RTT_ROW_G] fp32, ACCUMULATED into (caller zeroes); entries
+ *                 [0, RTT_N_DIFF) are d/d table_f; NULL to skip
+ *   g_lut       : [L, n_rows, 2] accumulated gradient of the wavelength LUT, or NULL        */
+int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float* in_intensity,
+                      const float* in_wavelength, const uint64_t* hitmask,
+                      const float* g_out_pos, const float* g_out_dir, const float* g_out_intensity,
+                      const float* const* g_record,
+                      float* g_in_pos, float* g_in_dir, float* g_in_intensity,
+                      float* g_table, float* g_lut,
+                      const rtt_table_t* table, int32_t n_sensors,
+                      int64_t n, int32_t mode, void* stream);
+
+/* Scene.simulate() / step() / ray_cast()             (scene/base.py:129-235)
+ * Per ray: up to nbounces times { stop if intensity<=0; nearest valid hit over ALL rows
+ * (first row wins ties, NaN distance anywhere = no hit); stop if none; interact }.
+ *   hit_seq     : [n, nbounces] uint8, row index per executed bounce, 255 = none (may be NULL)
+ *   n_hits      : [n] uint8 number of executed bounces (may be NULL)
+ * Sensors: every sensor interaction is accumulated into the image; `record` keeps the LAST. */
+int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* in_intensity,
+                         const float* in_wavelength,
+                         float* out_pos, float* out_dir, float* out_intensity,
+                         uint8_t* hit_seq, uint8_t* n_hits,
+                         const rtt_table_t* table, const rtt_sensor_t* sensors, int32_t n_sensors,
+                         int32_t nbounces, int64_t n, int32_t mode, void* stream);
+
+/* Adjoint of rtt_trace_nonseq_fwd: replays the recorded hit sequence (no search), then
+ * reverse sweep.  Same gradient conventions as rtt_trace_seq_bwd. */
+int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float* in_intensity,
+                         const float* in_wavelength, const uint8_t* hit_seq, int32_t nbounces,
+                         const float* g_out_pos, const float* g_out_dir, const float* g_out_intensity,
+                         float* g_in_pos, float* g_in_dir, float* g_in_intensity,
+                         float* g_table, float* g_lut,
+                         const rtt_table_t* table, int64_t n, int32_t mode, void* stream);
+
+/* Element.intersectTest(rays) -> [n, K]              (elements/parent.py:30-42,
+ * geom/shape.py:25-59, geom/primitives.py:38-57): distances of rows [row0, row0+k) with all
+ * validity rules applied, +inf (or NaN, as the reference) on a miss.  t_out is [n, k]. */
+int rtt_intersect_test(const float* in_pos, const float* in_dir, float* t_out,
+                       const rtt_table_t* table, int32_t row0, int32_t k,
+                       int64_t n, int32_t mode, void* stream);
+
+/* Element.forward(rays, surf_idx) -> (new_pos, new_dir, intensity_mult)
+ *                                                     (elements/parent.py:44-58)
+ * One row, NO shape-level validity (the reference applies it only in intersectTest,
+ * geom/shape.py:52 vs :61-87); rays that miss produce inf/NaN exactly like the reference.
+ * Optional extra outputs (NULL to skip): hit_local [n,3], t [n], normal [n,3]. */
+int rtt_surface_step_fwd(const float* in_pos, const float* in_dir, const float* in_wavelength,
+                         float* new_pos, float* new_dir, float* mod,
+                         float* hit_local, float* t_out, float* normal,
+                         const rtt_table_t* table, int32_t row,
+                         int64_t n, int32_t mode, void* stream);
+
+/* Adjoint of rtt_surface_step_fwd.  Upstream gradients may be NULL (= zero). */
+int rtt_surface_step_bwd(const float* in_pos, const float* in_dir, const float* in_wavelength,
+                         const float* g_new_pos, const float* g_new_dir, const float* g_hit_local,
+                         const float* g_t, const float* g_normal,
+                         float* g_in_pos, float* g_in_dir, float* g_table, float* g_lut,
+                         const rtt_table_t* table, int32_t row,
+                         int64_t n, int32_t mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTT_B200_H */

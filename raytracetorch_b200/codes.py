@@ -23,7 +23,7 @@ F_IOR_OUT = 28      # RefractSnell.ior_out                        phys/std.py:12
 N_DIFF = 29         # entries [0, N_DIFF) receive gradients from the adjoint kernel
 F_SB = 29           # 4 floats: surface-level bound parameters (non-differentiable selections)
 F_HB = 33           # 8 floats: shape-level bound parameters
-ROW_G = 32          # floats per row of the gradient table returned by the adjoint
+ROW_G = 48          # floats per row of the gradient table returned by the adjoint (== ROW_F)
 
 # ---- int part of a row ---------------------------------------------------------
 ROW_I = 16

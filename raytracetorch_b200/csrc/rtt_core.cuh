@@ -1,0 +1,668 @@
+// rtt_core.cuh — per-ray arithmetic of the ray-propagation path (forward and adjoint).
+//
+// Pure functions of (table row, ray state): no memory traffic policy, no launch logic —
+// that lives in rtt_kernels.inl.  Everything is RTT_HD so the same source also compiles
+// for the host in tests/hostsim (a development checker that runs the kernel arithmetic on
+// the CPU against the torch oracle; it is never loaded by the product package).
+//
+// The formulas restate the reference step by step (file:line under /root/reference are
+// given at each function) and keep its operation ORDER, because in EXACT mode (compiled
+// with -fmad=false) every fp32 rounding step of the reference's eager ops is reproduced:
+// hit masks, root selection and sensor bins then agree bit for bit on identity-rotation
+// scenes.  FAST mode is the same source with FMA contraction enabled.
+#pragma once
+
+#include <stdint.h>
+#include <math.h>
+#include "../../include/rtt_b200.h"
+
+#if defined(__CUDACC__)
+#define RTT_HD __host__ __device__ __forceinline__
+#else
+#define RTT_HD inline
+#endif
+
+namespace rtt {
+
+// ---- row record as staged in shared memory ------------------------------------------------
+// f[0..40] is the caller's table row; f[41..47] and i[11] are derived once per block.
+enum {
+    D_C1K = 41,       // c*(1+k)                 geom/primitives.py:280
+    D_MU_ENTER = 42,  // ior_out/ior_in          phys/std.py:132
+    D_MU_EXIT = 43,   // ior_in/ior_out
+    D_R2 = 44,        // radius**2               geom/primitives.py:161,214
+    D_SB0SQ = 45,     // sb[0]**2                geom/bounded.py:64,157
+    D_HB0SQ = 46,     // hb[0]**2                geom/spherics.py:44
+    DI_IDENT = 11     // bit0: Re == I, bit1: Rs == I (exact compare)
+};
+
+struct RowDev {
+    float f[RTT_ROW_F];
+    int32_t i[RTT_ROW_I];
+};
+
+struct V3 { float x, y, z; };
+
+RTT_HD V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+RTT_HD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+RTT_HD V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+RTT_HD V3 operator*(float s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+RTT_HD V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+// torch.sum(a*b, dim=1): products rounded, accumulated left to right
+RTT_HD float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+// p + t*d with t broadcast (geom/primitives.py:80-81)
+RTT_HD V3 along(V3 p, float t, V3 d) { return v3(p.x + t * d.x, p.y + t * d.y, p.z + t * d.z); }
+
+RTT_HD float rtt_inf() { return INFINITY; }
+RTT_HD float rtt_nan() { return NAN; }
+RTT_HD bool is_nan(float x) { return x != x; }
+
+// Explicit fused multiply-add (honoured in EXACT mode too).  The reference's `[N,3] @ [3,3]`
+// runs in the CPU BLAS as the chain fma(a2,R2j, fma(a1,R1j, a0*R0j)) and torch.norm over a
+// 3-vector as fma(z,z, fma(y,y, x*x)) (measured on the reference host), so
+// these two patterns are written as FMA chains in both variants.
+RTT_HD float fma3(float a0, float b0, float a1, float b1, float a2, float b2) {
+    return fmaf(a2, b2, fmaf(a1, b1, a0 * b0));
+}
+// a @ R   (row vector times matrix; geom/transform.py:92-93)
+RTT_HD V3 mul_R(V3 a, const float* R) {
+    return v3(fma3(a.x, R[0], a.y, R[3], a.z, R[6]),
+              fma3(a.x, R[1], a.y, R[4], a.z, R[7]),
+              fma3(a.x, R[2], a.y, R[5], a.z, R[8]));
+}
+// a @ R^T (geom/primitives.py:94, geom/shape.py:85)
+RTT_HD V3 mul_RT(V3 a, const float* R) {
+    return v3(fma3(a.x, R[0], a.y, R[1], a.z, R[2]),
+              fma3(a.x, R[3], a.y, R[4], a.z, R[5]),
+              fma3(a.x, R[6], a.y, R[7], a.z, R[8]));
+}
+// torch.norm / F.normalize over one 3-vector
+RTT_HD float norm3(float x, float y, float z) { return sqrtf(fma3(x, x, y, y, z, z)); }
+RTT_HD V3 ld3(const float* p) { return v3(p[0], p[1], p[2]); }
+
+// Derived per-row constants; the same fp32 operations the reference performs on 0-dim tensors.
+RTT_HD void prepare_row(RowDev& R) {
+    const float c = R.f[RTT_F_C], k = R.f[RTT_F_K];
+    R.f[D_C1K] = c * (1.0f + k);
+    R.f[D_MU_ENTER] = R.f[RTT_F_IOR_OUT] / R.f[RTT_F_IOR_IN];
+    R.f[D_MU_EXIT] = R.f[RTT_F_IOR_IN] / R.f[RTT_F_IOR_OUT];
+    R.f[D_R2] = R.f[RTT_F_RADIUS] * R.f[RTT_F_RADIUS];
+    R.f[D_SB0SQ] = R.f[RTT_F_SB] * R.f[RTT_F_SB];
+    R.f[D_HB0SQ] = R.f[RTT_F_HB] * R.f[RTT_F_HB];
+    int ident = 0;
+    const float* Re = R.f + RTT_F_RE;
+    const float* Rs = R.f + RTT_F_RS;
+    bool ie = true, is = true;
+    for (int a = 0; a < 9; ++a) {
+        const float want = (a % 4 == 0) ? 1.0f : 0.0f;
+        ie = ie && (Re[a] == want);
+        is = is && (Rs[a] == want);
+    }
+    if (ie) ident |= 1;
+    if (is) ident |= 2;
+    R.i[DI_IDENT] = ident;
+}
+
+// ---- poses ---------------------------------------------------------------------------------
+RTT_HD V3 rot_fwd(V3 a, const float* R, bool ident) { return ident ? a : mul_R(a, R); }
+RTT_HD V3 rot_bwd(V3 a, const float* R, bool ident) { return ident ? a : mul_RT(a, R); }
+
+// F.normalize(v, p=2, dim=1, eps=1e-12)  (rays/ray.py:25)
+RTT_HD V3 normalize12(V3 v, float* len_out) {
+    const float s = norm3(v.x, v.y, v.z);
+    const float den = fmaxf(s, 1e-12f);
+    *len_out = s;
+    return v3(v.x / den, v.y / den, v.z / den);
+}
+
+// ---- surface-level bounds (geom/bounded.py) ------------------------------------------------
+RTT_HD bool surface_in_bounds(const RowDev& R, V3 h) {
+    const float* sb = R.f + RTT_F_SB;
+    switch (R.i[RTT_I_BOUND]) {
+        case RTT_BOUND_DISK:                                            // :60-64
+            return (h.x * h.x + h.y * h.y) <= R.f[D_SB0SQ];
+        case RTT_BOUND_RECT:                                            // :77-82
+            return (fabsf(h.x) <= sb[0]) && (fabsf(h.y) <= sb[1]);
+        case RTT_BOUND_ELLIPSE: {                                       // :98-106
+            const float u = h.x * sb[2] - h.y * sb[3];
+            const float v = h.x * sb[3] + h.y * sb[2];
+            const float a = u / sb[0], b = v / sb[1];
+            return (a * a + b * b) <= 1.0f;
+        }
+        case RTT_BOUND_HALF:                                            // :123-127, :171-174
+            return fabsf(h.z * R.f[RTT_F_C]) < 1.000001f;
+        case RTT_BOUND_HALF_DISK:                                       // :151-159
+            return (fabsf(h.z * R.f[RTT_F_C]) < 1.000001f) && ((h.x * h.x + h.y * h.y) <= R.f[D_SB0SQ]);
+        default:
+            return true;
+    }
+}
+
+// ---- candidate roots (geom/primitives.py) --------------------------------------------------
+struct Roots {
+    float t1, t2;     // t2 unused for planes (n == 1)
+    int n;
+    // quantities the adjoint reuses
+    float A, B, C, sq;
+    bool lin;
+};
+
+RTT_HD Roots solve_roots(const RowDev& R, V3 o, V3 d) {
+    Roots q;
+    q.n = 2; q.A = q.B = q.C = q.sq = 0.0f; q.lin = false;
+    const float inf = rtt_inf();
+    switch (R.i[RTT_I_SURF]) {
+        case RTT_SURF_PLANE: {                                          // :124-136
+            const float safe = (fabsf(d.z) < 1e-6f) ? 1e-8f : d.z;
+            q.t1 = -o.z / safe; q.t2 = inf; q.n = 1; q.B = safe;
+            return q;
+        }
+        case RTT_SURF_SPHERE: {                                         // :155-184 (a == 1 assumed)
+            const float b = 2.0f * dot(o, d);
+            const float cc = dot(o, o) - R.f[D_R2];
+            const float disc = b * b - 4.0f * cc;
+            const bool ok = disc >= 0.0f;
+            const float sq = sqrtf(ok ? disc : 0.0f);
+            q.t1 = ok ? (-b - sq) / 2.0f : inf;
+            q.t2 = ok ? (-b + sq) / 2.0f : inf;
+            q.B = b; q.sq = sq;
+            return q;
+        }
+        case RTT_SURF_CYLINDER: {                                       // :201-231 (no A==0 guard)
+            const float A = d.x * d.x + d.y * d.y;
+            const float B = 2.0f * (o.x * d.x + o.y * d.y);
+            const float Cq = (o.x * o.x + o.y * o.y) - R.f[D_R2];
+            const float disc = B * B - 4.0f * A * Cq;
+            const bool ok = disc >= 0.0f;
+            const float sq = sqrtf(fabsf(disc));
+            q.t1 = ok ? (-B - sq) / (2.0f * A) : inf;
+            q.t2 = ok ? (-B + sq) / (2.0f * A) : inf;
+            q.A = A; q.B = B; q.C = Cq; q.sq = sq;
+            return q;
+        }
+        default: {                                                      // conics :266-320, :356-376
+            const float c = R.f[RTT_F_C], c1k = R.f[D_C1K];
+            const float tc = 2.0f * c, tc1k = 2.0f * c1k;
+            float A, B, Cq;
+            if (R.i[RTT_I_SURF] == RTT_SURF_QUADRIC) {
+                A = c * (d.x * d.x + d.y * d.y) + c1k * (d.z * d.z);
+                B = (tc * (o.x * d.x + o.y * d.y) + (tc1k * o.z) * d.z) - 2.0f * d.z;
+                Cq = (c * (o.x * o.x + o.y * o.y) + c1k * (o.z * o.z)) - 2.0f * o.z;
+            } else {
+                A = c * (d.y * d.y) + c1k * (d.z * d.z);
+                B = (tc * (o.y * d.y) + (tc1k * o.z) * d.z) - 2.0f * d.z;
+                Cq = (c * (o.y * o.y) + c1k * (o.z * o.z)) - 2.0f * o.z;
+            }
+            const float disc = B * B - (4.0f * A) * Cq;
+            const bool ok = disc >= 0.0f;
+            const bool lin = fabsf(A) < 1e-6f;
+            const float sq = sqrtf(fabsf(disc));
+            const float As = lin ? 1.0f : A;
+            const float den = 2.0f * As;
+            const float r1 = (-B - sq) / den, r2 = (-B + sq) / den;
+            const float Bs = (fabsf(B) < 1e-6f) ? 1e-6f : B;
+            const float tl = -Cq / Bs;
+            q.t1 = lin ? tl : (ok ? r1 : inf);
+            q.t2 = lin ? tl : (ok ? r2 : inf);
+            q.A = A; q.B = B; q.C = Cq; q.sq = sq; q.lin = lin;
+            return q;
+        }
+    }
+}
+
+// Smallest admissible root.  Unbounded: geom/primitives.py:28-36; bounded: geom/bounded.py:20-36.
+// NaN propagates like torch.min (a NaN candidate that was not masked makes the result NaN).
+// *which = index of the selected root (0/1).
+RTT_HD float select_root(const RowDev& R, const Roots& q, V3 o, V3 d, int* which) {
+    const float inf = rtt_inf();
+    float t1 = q.t1, t2 = q.t2;
+    if (R.i[RTT_I_BOUND] == RTT_BOUND_NONE) {
+        if (t1 <= 1e-6f) t1 = inf;
+        if (q.n == 2 && t2 <= 1e-6f) t2 = inf;
+    } else {
+        const bool inv = R.i[RTT_I_INVERT] != 0;
+        bool k1 = surface_in_bounds(R, along(o, t1, d));
+        if (inv) k1 = !k1;
+        if (t1 <= 1e-6f || !k1) t1 = inf;
+        if (q.n == 2) {
+            bool k2 = surface_in_bounds(R, along(o, t2, d));
+            if (inv) k2 = !k2;
+            if (t2 <= 1e-6f || !k2) t2 = inf;
+        }
+    }
+    if (q.n == 1) { *which = 0; return t1; }
+    if (is_nan(t1) || is_nan(t2)) { *which = 0; return rtt_nan(); }
+    if (t2 < t1) { *which = 1; return t2; }
+    *which = 0;
+    return t1;
+}
+
+// ---- shape-level validity (geom/shape.py:47-55) ---------------------------------------------
+RTT_HD float sag_at(float c, float h, float tz) {                       // geom/bounded.py:129-139
+    const float h2 = h * h;
+    float term = 1.0f - (c * c) * h2;
+    term = term > 0.0f ? term : 0.0f;
+    return (c * h2) / (1.0f + sqrtf(term)) + tz;
+}
+
+RTT_HD bool shape_in_bounds(const RowDev* rows, int r, V3 h) {
+    const RowDev& R = rows[r];
+    const float* hb = R.f + RTT_F_HB;
+    switch (R.i[RTT_I_SHAPE]) {
+        case RTT_SHAPE_SPHERIC_FACE:                                    // geom/spherics.py:40-46
+            return (h.x * h.x + h.y * h.y) <= R.f[D_HB0SQ];
+        case RTT_SHAPE_SPHERIC_EDGE:                                    // geom/spherics.py:34-39
+            return (h.z >= hb[0]) && (h.z <= hb[1]);
+        case RTT_SHAPE_CYL_FACE:
+        case RTT_SHAPE_CYL_EDGE: {                                      // geom/cylindrics.py:23-55
+            const bool ap = (h.x <= hb[1] + 1e-5f) && (h.x >= hb[0] - 1e-5f) &&
+                            (h.y <= hb[3] + 1e-5f) && (h.y >= hb[2] - 1e-5f);
+            if (R.i[RTT_I_SHAPE] == RTT_SHAPE_CYL_FACE) return ap;
+            const float zf = sag_at(hb[4], h.y, hb[5]);
+            const float zb = sag_at(hb[6], h.y, hb[7]);
+            return (h.z >= zf + 1e-4f) && (h.z <= zb - 1e-4f) && ap;
+        }
+        case RTT_SHAPE_POLY: {                                          // geom/shape.py:122-132
+            const int first = R.i[RTT_I_POLY_FIRST], cnt = R.i[RTT_I_POLY_COUNT];
+            bool ok = true;
+            for (int m = first; m < first + cnt; ++m) {
+                if (m == r) continue;
+                const float* Rm = rows[m].f + RTT_F_RS;                 // ROW 2 of R (reference quirk)
+                const float* Tm = rows[m].f + RTT_F_TS;
+                const float lz = (Rm[6] * (h.x - Tm[0]) + Rm[7] * (h.y - Tm[1])) + Rm[8] * (h.z - Tm[2]);
+                ok = ok && (lz < 1e-4f);
+            }
+            return ok;
+        }
+        default:
+            return true;
+    }
+}
+
+// ---- intersection of one ray with one row ---------------------------------------------------
+struct Frames {
+    V3 pe, de;     // element frame (de NOT renormalised); == global for bare surfaces
+    V3 den;        // renormalised element-frame direction
+    float len;     // |de|
+    V3 o, dd;      // surface frame
+};
+
+RTT_HD Frames to_frames(const RowDev& R, V3 p, V3 d) {
+    Frames F;
+    const int ident = R.i[DI_IDENT];
+    if (R.i[RTT_I_SHAPE] == RTT_SHAPE_NONE) {                           // geom/primitives.py:49
+        F.pe = p; F.de = d; F.den = d; F.len = 1.0f;
+    } else {                                                            // geom/shape.py:37-38
+        F.pe = rot_fwd(p - ld3(R.f + RTT_F_TE), R.f + RTT_F_RE, ident & 1);
+        F.de = rot_fwd(d, R.f + RTT_F_RE, ident & 1);
+        F.den = normalize12(F.de, &F.len);
+    }
+    F.o = rot_fwd(F.pe - ld3(R.f + RTT_F_TS), R.f + RTT_F_RS, ident & 2);
+    F.dd = rot_fwd(F.den, R.f + RTT_F_RS, ident & 2);
+    return F;
+}
+
+// Distance with every validity rule; returns true iff `t < inf` and valid.
+// WITH_SHAPE=false is the Element.forward variant (geom/shape.py:61-87: no shape-level rule).
+template <bool WITH_SHAPE>
+RTT_HD bool intersect(const RowDev* rows, int r, V3 p, V3 d, Frames& F, Roots& q, float& t, int& which) {
+    const RowDev& R = rows[r];
+    F = to_frames(R, p, d);
+    q = solve_roots(R, F.o, F.dd);
+    t = select_root(R, q, F.o, F.dd, &which);
+    bool valid = t < rtt_inf();                                         // false for NaN
+    if (WITH_SHAPE && valid && R.i[RTT_I_SHAPE] != RTT_SHAPE_NONE) {
+        valid = shape_in_bounds(rows, r, along(F.pe, t, F.de));         // un-normalised de: shape.py:47
+    }
+    return valid;
+}
+
+// ---- normals (geom/primitives.py:138-143, 186-187, 233-241, 330-343, 378-395) ---------------
+RTT_HD V3 normal_local(const RowDev& R, V3 h, float* len_out) {
+    *len_out = 1.0f;
+    switch (R.i[RTT_I_SURF]) {
+        case RTT_SURF_PLANE: return v3(0.0f, 0.0f, 1.0f);
+        case RTT_SURF_SPHERE: { const float rr = R.f[RTT_F_RADIUS]; return v3(h.x / rr, h.y / rr, h.z / rr); }
+        case RTT_SURF_CYLINDER: { const float rr = R.f[RTT_F_RADIUS]; return v3(h.x / rr, h.y / rr, 0.0f); }
+        default: {
+            const float tc = 2.0f * R.f[RTT_F_C], tc1k = 2.0f * R.f[D_C1K];
+            const float nx = (R.i[RTT_I_SURF] == RTT_SURF_QUADRIC) ? tc * h.x : 0.0f;
+            const float ny = tc * h.y;
+            const float nz = tc1k * h.z - 2.0f;
+            const float len = norm3(nx, ny, nz);
+            const float den = len + 1e-8f;
+            *len_out = len;
+            return v3(-(nx / den), -(ny / den), -(nz / den));
+        }
+    }
+}
+
+RTT_HD V3 normal_global(const RowDev& R, V3 nl) {
+    const int ident = R.i[DI_IDENT];
+    V3 n = rot_bwd(nl, R.f + RTT_F_RS, ident & 2);
+    if (R.i[RTT_I_SHAPE] != RTT_SHAPE_NONE) n = rot_bwd(n, R.f + RTT_F_RE, ident & 1);
+    return n;
+}
+
+// ---- physics (phys/std.py, phys/filter.py) --------------------------------------------------
+// mu_enter = ior_out/ior_in, mu_exit = ior_in/ior_out (per wavelength when a LUT is present).
+RTT_HD V3 physics(const RowDev& R, V3 hl, V3 d, V3 n, float mu_enter, float mu_exit, float* mod) {
+    *mod = 1.0f;
+    switch (R.i[RTT_I_PHYS]) {
+        case RTT_PHYS_BLOCK:                                            // std.py:243-254
+            *mod = 0.0f;
+            return v3(0.0f, 0.0f, 0.0f);
+        case RTT_PHYS_REFLECT: {                                        // std.py:97-108
+            const float tw = 2.0f * dot(d, n);
+            return v3(d.x - tw * n.x, d.y - tw * n.y, d.z - tw * n.z);
+        }
+        case RTT_PHYS_APERTURE: {                                       // filter.py:24-33
+            const float m = surface_in_bounds(R, hl) ? 1.0f : 0.0f;
+            *mod = m;
+            return v3(d.x * m, d.y * m, d.z * m);
+        }
+        case RTT_PHYS_SNELL: {                                          // std.py:123-145
+            const float dt = dot(d, n);
+            const bool entering = dt < 0.0f;
+            const float c1 = fabsf(dt);
+            const float mu = entering ? mu_enter : mu_exit;
+            const float term = 1.0f - (mu * mu) * (1.0f - c1 * c1);
+            if (term < 0.0f) {                                          // total internal reflection
+                const float tw = 2.0f * dt;
+                return v3(d.x - tw * n.x, d.y - tw * n.y, d.z - tw * n.z);
+            }
+            const float c2 = sqrtf(term > 0.0f ? term : 0.0f);
+            const float qf = mu * c1 - c2;
+            const V3 ne = entering ? n : -n;
+            return v3(mu * d.x + qf * ne.x, mu * d.y + qf * ne.y, mu * d.z + qf * ne.z);
+        }
+        default:                                                        // Transmit std.py:227-235
+            return d;
+    }
+}
+
+// ---- one complete interaction (Element.forward, elements/parent.py:44-58) -------------------
+struct Step {
+    V3 hit_global, hit_local, normal, new_dir;
+    float mod, t;
+};
+
+RTT_HD Step interact(const RowDev& R, const Frames& F, float t, V3 p, V3 d, float mu_enter, float mu_exit) {
+    Step s;
+    s.t = t;
+    s.hit_local = along(F.o, t, F.dd);                                  // primitives.py:81
+    float nlen;
+    s.normal = normal_global(R, normal_local(R, s.hit_local, &nlen));
+    s.hit_global = along(p, t, d);                                      // shape.py:81 / primitives.py:80
+    s.new_dir = physics(R, s.hit_local, d, s.normal, mu_enter, mu_exit, &s.mod);
+    return s;
+}
+
+// ---- sensor binning (restating gui/workbench.py:615-624 in fp32; see rtt_b200.h) ------------
+RTT_HD bool sensor_bin(float x, float y, float x0, float y0, float sx, float sy, int W, int H, int* ix, int* iy) {
+    const float fx = floorf((x - x0) * sx);
+    const float fy = floorf((y - y0) * sy);
+    if (!(fx >= 0.0f && fx < (float)W && fy >= 0.0f && fy < (float)H)) return false;
+    *ix = (int)fx; *iy = (int)fy;
+    return true;
+}
+
+// =============================================================================================
+// Adjoint
+// =============================================================================================
+// Gradient of one row's differentiable entries, in table_f order [0, RTT_N_DIFF).
+struct RowGrad {
+    float g[RTT_N_DIFF];
+};
+
+RTT_HD void zero(RowGrad& G) {
+    for (int a = 0; a < RTT_N_DIFF; ++a) G.g[a] = 0.0f;
+}
+
+// y = a @ R : ga += gy @ R^T ; gR[i][j] += a[i]*gy[j]
+RTT_HD V3 adj_mul_R(V3 a, V3 gy, const float* R, bool ident, float* gR, bool want_gR) {
+    if (want_gR) {
+        gR[0] += a.x * gy.x; gR[1] += a.x * gy.y; gR[2] += a.x * gy.z;
+        gR[3] += a.y * gy.x; gR[4] += a.y * gy.y; gR[5] += a.y * gy.z;
+        gR[6] += a.z * gy.x; gR[7] += a.z * gy.y; gR[8] += a.z * gy.z;
+    }
+    return ident ? gy : mul_RT(gy, R);
+}
+// y = a @ R^T : ga += gy @ R ; gR[j][i] += gy[j]*a[i]
+RTT_HD V3 adj_mul_RT(V3 a, V3 gy, const float* R, bool ident, float* gR, bool want_gR) {
+    if (want_gR) {
+        gR[0] += gy.x * a.x; gR[1] += gy.x * a.y; gR[2] += gy.x * a.z;
+        gR[3] += gy.y * a.x; gR[4] += gy.y * a.y; gR[5] += gy.y * a.z;
+        gR[6] += gy.z * a.x; gR[7] += gy.z * a.y; gR[8] += gy.z * a.z;
+    }
+    return ident ? gy : mul_R(gy, R);
+}
+
+// Reverse of `interact` for a ray known to have hit row R with incoming state (p, d).
+// Upstream: g_pos (d/d new_pos), g_dir (d/d new_dir), g_hl_up (d/d hit_local, sensor record),
+// g_n_up (d/d normal) and g_t_up (d/d t) for callers of the single-surface op.
+// Produces d/d p, d/d d and accumulates the row's parameter gradients into G.
+// Intensity is handled by the caller (g_I_in = g_I_out * mod; mod is returned).
+// (ni, no) are the (ior_in, ior_out) this ray used (row values, or the wavelength LUT's).
+RTT_HD void interact_adjoint(const RowDev& R, V3 p, V3 d, float ni, float no, float mu_enter, float mu_exit,
+                             V3 g_pos, V3 g_dir, V3 g_hl_up, V3 g_n_up, float g_t_up,
+                             V3& g_p, V3& g_d, float& mod_out, RowGrad& G, int want) {
+    // ---- recompute the forward pieces (same selections as the forward pass) ----
+    const Frames F = to_frames(R, p, d);
+    const Roots q = solve_roots(R, F.o, F.dd);
+    int which;
+    const float t = select_root(R, q, F.o, F.dd, &which);
+    const V3 hl = along(F.o, t, F.dd);
+    float nlen;
+    const V3 nl = normal_local(R, hl, &nlen);
+    const int ident = R.i[DI_IDENT];
+    const bool has_shape = R.i[RTT_I_SHAPE] != RTT_SHAPE_NONE;
+    const V3 n_e = rot_bwd(nl, R.f + RTT_F_RS, ident & 2);              // element-frame normal
+    const V3 n = has_shape ? rot_bwd(n_e, R.f + RTT_F_RE, ident & 1) : n_e;
+    const bool w_pose_e = (want & RTT_FLAG_GRAD_POSE_E) != 0;
+    const bool w_pose_s = (want & RTT_FLAG_GRAD_POSE_S) != 0;
+
+    g_p = g_pos;                                                        // hit_global = p + t d
+    g_d = v3(t * g_pos.x, t * g_pos.y, t * g_pos.z);
+    float g_t = dot(g_pos, d) + g_t_up;
+    V3 g_n = v3(0.0f, 0.0f, 0.0f);
+    V3 g_hl = g_hl_up;
+    float mod = 1.0f;
+
+    // ---- physics ----
+    switch (R.i[RTT_I_PHYS]) {
+        case RTT_PHYS_BLOCK:
+            mod = 0.0f;
+            break;
+        case RTT_PHYS_APERTURE: {
+            const float m = surface_in_bounds(R, hl) ? 1.0f : 0.0f;
+            mod = m;
+            g_d = g_d + m * g_dir;
+            break;
+        }
+        case RTT_PHYS_REFLECT: {
+            const float dn = dot(d, n), gn = dot(g_dir, n);
+            g_d = g_d + (g_dir - (2.0f * gn) * n);
+            g_n = -2.0f * (gn * d + dn * g_dir);
+            break;
+        }
+        case RTT_PHYS_SNELL: {
+            const float dt = dot(d, n);
+            const bool entering = dt < 0.0f;
+            const float c1 = fabsf(dt);
+            const float mu = entering ? mu_enter : mu_exit;
+            const float one_m = 1.0f - c1 * c1;
+            const float term = 1.0f - (mu * mu) * one_m;
+            if (term < 0.0f) {
+                const float gn = dot(g_dir, n);
+                g_d = g_d + (g_dir - (2.0f * gn) * n);
+                g_n = -2.0f * (gn * d + dt * g_dir);
+            } else {
+                const float c2 = sqrtf(term > 0.0f ? term : 0.0f);
+                const float sgn = entering ? 1.0f : -1.0f;
+                const float qf = mu * c1 - c2;
+                float g_mu = dot(g_dir, d);
+                const float g_q = sgn * dot(g_dir, n);
+                g_d = g_d + mu * g_dir;
+                g_n = (qf * sgn) * g_dir;
+                g_mu += c1 * g_q;
+                float g_c1 = mu * g_q;
+                const float g_term = (term > 0.0f) ? (-g_q) / (2.0f * c2) : 0.0f;
+                g_mu += g_term * (-2.0f * mu * one_m);
+                g_c1 += g_term * (2.0f * mu * mu * c1);
+                const float g_dt = (dt < 0.0f) ? -g_c1 : ((dt > 0.0f) ? g_c1 : 0.0f);
+                g_d = g_d + g_dt * n;
+                g_n = g_n + g_dt * d;
+                if (want & RTT_FLAG_GRAD_IOR) {
+                    if (entering) {                                     // mu = no/ni
+                        G.g[RTT_F_IOR_OUT] += g_mu / ni;
+                        G.g[RTT_F_IOR_IN] -= g_mu * no / (ni * ni);
+                    } else {                                            // mu = ni/no
+                        G.g[RTT_F_IOR_IN] += g_mu / no;
+                        G.g[RTT_F_IOR_OUT] -= g_mu * ni / (no * no);
+                    }
+                }
+            }
+            break;
+        }
+        default:
+            g_d = g_d + g_dir;
+            break;
+    }
+    mod_out = mod;
+    g_n = g_n + g_n_up;
+
+    // ---- normal: n = (nl @ Rs^T) @ Re^T ----
+    V3 g_ne = g_n;
+    if (has_shape) g_ne = adj_mul_RT(n_e, g_n, R.f + RTT_F_RE, ident & 1, G.g + RTT_F_RE, w_pose_e);
+    const V3 g_nl = adj_mul_RT(nl, g_ne, R.f + RTT_F_RS, ident & 2, G.g + RTT_F_RS, w_pose_s);
+
+    // ---- normal_local(hl) ----
+    switch (R.i[RTT_I_SURF]) {
+        case RTT_SURF_PLANE: break;
+        case RTT_SURF_SPHERE: {
+            const float rr = R.f[RTT_F_RADIUS];
+            g_hl = g_hl + v3(g_nl.x / rr, g_nl.y / rr, g_nl.z / rr);
+            G.g[RTT_F_RADIUS] -= dot(g_nl, hl) / (rr * rr);
+            break;
+        }
+        case RTT_SURF_CYLINDER: {
+            const float rr = R.f[RTT_F_RADIUS];
+            g_hl.x += g_nl.x / rr; g_hl.y += g_nl.y / rr;
+            G.g[RTT_F_RADIUS] -= (g_nl.x * hl.x + g_nl.y * hl.y) / (rr * rr);
+            break;
+        }
+        default: {
+            const float c = R.f[RTT_F_C], k = R.f[RTT_F_K];
+            const float tc = 2.0f * c, tc1k = 2.0f * R.f[D_C1K];
+            const bool full = R.i[RTT_I_SURF] == RTT_SURF_QUADRIC;
+            const V3 raw = v3(full ? tc * hl.x : 0.0f, tc * hl.y, tc1k * hl.z - 2.0f);
+            const float den = nlen + 1e-8f;
+            // nl = -raw/den, den = |raw| + 1e-8
+            const float rg = dot(raw, g_nl);
+            const float s = (nlen > 0.0f) ? rg / (den * den * nlen) : 0.0f;
+            const V3 g_raw = v3(-(g_nl.x / den) + raw.x * s, -(g_nl.y / den) + raw.y * s, -(g_nl.z / den) + raw.z * s);
+            float g_tc = g_raw.y * hl.y;
+            if (full) { g_hl.x += tc * g_raw.x; g_tc += g_raw.x * hl.x; }
+            g_hl.y += tc * g_raw.y;
+            g_hl.z += tc1k * g_raw.z;
+            const float g_tc1k = g_raw.z * hl.z;
+            G.g[RTT_F_C] += 2.0f * g_tc + 2.0f * (1.0f + k) * g_tc1k;
+            G.g[RTT_F_K] += 2.0f * c * g_tc1k;
+            break;
+        }
+    }
+
+    // ---- hit_local = o + t dd ----
+    V3 g_o = g_hl;
+    V3 g_dd = t * g_hl;
+    g_t += dot(g_hl, F.dd);
+
+    // ---- t = selected root ----
+    const V3 o = F.o, dd = F.dd;
+    switch (R.i[RTT_I_SURF]) {
+        case RTT_SURF_PLANE: {
+            const float safe = q.B;
+            g_o.z += -g_t / safe;
+            if (!(fabsf(dd.z) < 1e-6f)) g_dd.z += -g_t * t / safe;      // d(-oz/dz)/d dz = -t/dz
+            break;
+        }
+        case RTT_SURF_SPHERE: {
+            const float sg = which ? 1.0f : -1.0f;
+            const float b = q.B, sq = q.sq;
+            const float g_b = g_t * (-1.0f + sg * b / sq) * 0.5f;
+            const float g_cc = -g_t * sg / sq;
+            g_o = g_o + (2.0f * g_b) * dd + (2.0f * g_cc) * o;
+            g_dd = g_dd + (2.0f * g_b) * o;
+            G.g[RTT_F_RADIUS] += g_cc * (-2.0f * R.f[RTT_F_RADIUS]);
+            break;
+        }
+        case RTT_SURF_CYLINDER: {
+            const float D = 2.0f * q.A * t + q.B;
+            const float gA = -g_t * t * t / D, gB = -g_t * t / D, gC = -g_t / D;
+            g_dd.x += gA * 2.0f * dd.x + gB * 2.0f * o.x;
+            g_dd.y += gA * 2.0f * dd.y + gB * 2.0f * o.y;
+            g_o.x += gB * 2.0f * dd.x + gC * 2.0f * o.x;
+            g_o.y += gB * 2.0f * dd.y + gC * 2.0f * o.y;
+            G.g[RTT_F_RADIUS] += gC * (-2.0f * R.f[RTT_F_RADIUS]);
+            break;
+        }
+        default: {
+            const float c = R.f[RTT_F_C], k = R.f[RTT_F_K], c1k = R.f[D_C1K];
+            float gA, gB, gC;
+            if (q.lin) {
+                const float Bs = (fabsf(q.B) < 1e-6f) ? 1e-6f : q.B;
+                gA = 0.0f;
+                gC = -g_t / Bs;
+                gB = (fabsf(q.B) < 1e-6f) ? 0.0f : g_t * q.C / (Bs * Bs);
+            } else {
+                const float D = 2.0f * q.A * t + q.B;
+                gA = -g_t * t * t / D; gB = -g_t * t / D; gC = -g_t / D;
+            }
+            const bool full = R.i[RTT_I_SURF] == RTT_SURF_QUADRIC;
+            const float ox = full ? o.x : 0.0f, dx = full ? dd.x : 0.0f;
+            const float g_u = gA * (dx * dx + dd.y * dd.y) + gB * 2.0f * (ox * dx + o.y * dd.y) + gC * (ox * ox + o.y * o.y);
+            const float g_v = gA * (dd.z * dd.z) + gB * 2.0f * (o.z * dd.z) + gC * (o.z * o.z);
+            if (full) {
+                g_dd.x += gA * 2.0f * c * dx + gB * 2.0f * c * ox;
+                g_o.x += gB * 2.0f * c * dx + gC * 2.0f * c * ox;
+            }
+            g_dd.y += gA * 2.0f * c * dd.y + gB * 2.0f * c * o.y;
+            g_o.y += gB * 2.0f * c * dd.y + gC * 2.0f * c * o.y;
+            g_dd.z += gA * 2.0f * c1k * dd.z + gB * (2.0f * c1k * o.z - 2.0f);
+            g_o.z += gB * 2.0f * c1k * dd.z + gC * (2.0f * c1k * o.z - 2.0f);
+            G.g[RTT_F_C] += g_u + (1.0f + k) * g_v;
+            G.g[RTT_F_K] += c * g_v;
+            break;
+        }
+    }
+
+    // ---- surface pose: o = (pe - Ts) @ Rs ; dd = den @ Rs ----
+    const V3 pes = F.pe - ld3(R.f + RTT_F_TS);
+    const V3 g_pes = adj_mul_R(pes, g_o, R.f + RTT_F_RS, ident & 2, G.g + RTT_F_RS, w_pose_s);
+    const V3 g_den = adj_mul_R(F.den, g_dd, R.f + RTT_F_RS, ident & 2, G.g + RTT_F_RS, w_pose_s);
+    if (w_pose_s) { G.g[RTT_F_TS] -= g_pes.x; G.g[RTT_F_TS + 1] -= g_pes.y; G.g[RTT_F_TS + 2] -= g_pes.z; }
+
+    if (!has_shape) {
+        g_p = g_p + g_pes;
+        g_d = g_d + g_den;
+        return;
+    }
+    // ---- renormalisation: den = de / max(|de|, 1e-12) ----
+    V3 g_de;
+    if (F.len > 1e-12f) {
+        const float pr = dot(F.den, g_den);
+        g_de = v3((g_den.x - F.den.x * pr) / F.len, (g_den.y - F.den.y * pr) / F.len, (g_den.z - F.den.z * pr) / F.len);
+    } else {
+        g_de = v3(g_den.x / 1e-12f, g_den.y / 1e-12f, g_den.z / 1e-12f);
+    }
+    // ---- element pose: pe = (p - Te) @ Re ; de = d @ Re ----
+    const V3 pte = p - ld3(R.f + RTT_F_TE);
+    const V3 g_pte = adj_mul_R(pte, g_pes, R.f + RTT_F_RE, ident & 1, G.g + RTT_F_RE, w_pose_e);
+    const V3 g_dg = adj_mul_R(d, g_de, R.f + RTT_F_RE, ident & 1, G.g + RTT_F_RE, w_pose_e);
+    if (w_pose_e) { G.g[RTT_F_TE] -= g_pte.x; G.g[RTT_F_TE + 1] -= g_pte.y; G.g[RTT_F_TE + 2] -= g_pte.z; }
+    g_p = g_p + g_pte;
+    g_d = g_d + g_dg;
+}
+
+}  // namespace rtt

@@ -1,0 +1,563 @@
+// rtt_kernels.inl — CUDA kernels of the ray-propagation path (sm_100a).
+//
+// Included twice: rtt_kernels_fast.cu (FMA contraction on) and rtt_kernels_exact.cu
+// (-fmad=false; every rounding step of the reference's eager fp32 ops is kept).  The
+// including file defines RTT_VARIANT (fast|exact).
+//
+// Execution model
+//   * the surface table ([S,48] f32 + [S,16] i32, a few KB) is read from device memory and
+//     staged once per thread block in shared memory together with per-row derived constants;
+//     every row access afterwards is a shared-memory broadcast
+//   * one thread owns one ray at a time and keeps its state (p, d, I, hit mask) in
+//     registers through the whole surface stack; blocks are persistent and walk the bundle
+//     with a grid stride, so the staging cost is paid once per SM-resident block
+//   * sensor hits are binned in the same kernel (no hit lists unless requested)
+//   * the adjoint kernels recompute the forward per ray (checkpoints = incoming (p, d) of
+//     each interaction) and reduce parameter gradients warp -> block (shared) -> global
+#include <cuda_runtime.h>
+#include "rtt_core.cuh"
+#include "rtt_kernels_decl.h"
+
+namespace rtt {
+namespace RTT_VARIANT {
+
+constexpr int kThreads = 256;
+constexpr unsigned kFull = 0xffffffffu;
+
+
+
+// Shared-memory image of the table.
+struct SmemTable {
+    RowDev* rows;        // [S]
+    float* lut_ni;       // [L*S]
+    float* lut_no;       // [L*S]
+    float* mu_enter;     // [L*S]   no/ni
+    float* mu_exit;      // [L*S]   ni/no
+    float* lut_w;        // [L]
+};
+
+__host__ __device__ inline size_t smem_table_bytes(int S, int L) {
+    return sizeof(RowDev) * (size_t)S + sizeof(float) * ((size_t)4 * L * S + (size_t)L + 4);
+}
+
+__device__ __forceinline__ SmemTable carve(unsigned char* base, int S, int L) {
+    SmemTable T;
+    T.rows = reinterpret_cast<RowDev*>(base);
+    float* f = reinterpret_cast<float*>(base + sizeof(RowDev) * (size_t)S);
+    T.lut_ni = f; f += (size_t)L * S;
+    T.lut_no = f; f += (size_t)L * S;
+    T.mu_enter = f; f += (size_t)L * S;
+    T.mu_exit = f; f += (size_t)L * S;
+    T.lut_w = f;
+    return T;
+}
+
+// Cooperative staging: coalesced copy of the rows, then one thread per row derives constants.
+__device__ __forceinline__ void stage_table(const TableDev& tab, SmemTable& T) {
+    const int S = tab.S, L = tab.L;
+    for (int idx = threadIdx.x; idx < S * RTT_ROW_F; idx += blockDim.x)
+        T.rows[idx / RTT_ROW_F].f[idx % RTT_ROW_F] = tab.f[idx];
+    for (int idx = threadIdx.x; idx < S * RTT_ROW_I; idx += blockDim.x)
+        T.rows[idx / RTT_ROW_I].i[idx % RTT_ROW_I] = tab.i[idx];
+    for (int idx = threadIdx.x; idx < L * S; idx += blockDim.x) {
+        const float ni = tab.lut[2 * idx], no = tab.lut[2 * idx + 1];
+        T.lut_ni[idx] = ni; T.lut_no[idx] = no;
+        T.mu_enter[idx] = no / ni; T.mu_exit[idx] = ni / no;
+    }
+    for (int idx = threadIdx.x; idx < L; idx += blockDim.x) T.lut_w[idx] = tab.lut_w[idx];
+    __syncthreads();
+    for (int r = threadIdx.x; r < S; r += blockDim.x) prepare_row(T.rows[r]);
+    __syncthreads();
+}
+
+// nearest sample wavelength, first minimum (oracle: torch.argmin)
+__device__ __forceinline__ int wavelength_index(const SmemTable& T, int L, float w) {
+    int best = 0;
+    float bd = fabsf(w - T.lut_w[0]);
+    for (int l = 1; l < L; ++l) {
+        const float dd = fabsf(w - T.lut_w[l]);
+        if (dd < bd) { bd = dd; best = l; }
+    }
+    return best;
+}
+
+struct Ior { float ni, no, mu_enter, mu_exit; };
+
+__device__ __forceinline__ Ior row_ior(const SmemTable& T, int S, int L, int r, int lam) {
+    Ior q;
+    if (L > 0) {
+        const int idx = lam * S + r;
+        q.ni = T.lut_ni[idx]; q.no = T.lut_no[idx]; q.mu_enter = T.mu_enter[idx]; q.mu_exit = T.mu_exit[idx];
+    } else {
+        const RowDev& R = T.rows[r];
+        q.ni = R.f[RTT_F_IOR_IN]; q.no = R.f[RTT_F_IOR_OUT]; q.mu_enter = R.f[D_MU_ENTER]; q.mu_exit = R.f[D_MU_EXIT];
+    }
+    return q;
+}
+
+__device__ __forceinline__ V3 load3(const float* a, long long i) { return v3(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
+__device__ __forceinline__ void store3(float* a, long long i, V3 v) { a[3 * i] = v.x; a[3 * i + 1] = v.y; a[3 * i + 2] = v.z; }
+
+__device__ __forceinline__ void sensor_deposit(const SensorDev& sd, long long i, V3 hl, float w, int lam) {
+    if (sd.record) {
+        float4* rec = reinterpret_cast<float4*>(sd.record);
+        rec[i] = make_float4(hl.x, hl.y, hl.z, w);
+    }
+    if (sd.image) {
+        int ix, iy;
+        if (sensor_bin(hl.x, hl.y, sd.x0, sd.y0, sd.sx, sd.sy, sd.W, sd.H, &ix, &iy)) {
+            const int ch = (sd.C > 1) ? min(lam, sd.C - 1) : 0;
+            atomicAdd(sd.image + ((size_t)ch * sd.H + iy) * sd.W + ix, w);
+        }
+    }
+}
+
+// ============================================================================================
+// Sequential trace, forward (scene/sequential.py:12-36)
+// ============================================================================================
+
+__global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_fwd)(const __grid_constant__ SeqFwdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemTable T = carve(smem_raw, a.tab.S, a.tab.L);
+    stage_table(a.tab, T);
+    const int S = a.tab.S, L = a.tab.L;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        V3 p = load3(a.pos, i), d = load3(a.dir, i);
+        float I = a.inten[i];
+        const int lam = (L > 0) ? wavelength_index(T, L, a.wav[i]) : 0;
+        unsigned long long mask = 0ull;
+        for (int r = 0; r < S; ++r) {
+            Frames F; Roots q; float t; int which;
+            if (!intersect<true>(T.rows, r, p, d, F, q, t, which)) continue;
+            const RowDev& R = T.rows[r];
+            const Ior io = row_ior(T, S, L, r, lam);
+            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
+            const int slot = R.i[RTT_I_SENSOR];
+            if (slot >= 0 && slot < a.n_sens) sensor_deposit(a.sens[slot], i, s.hit_local, I, lam);
+            p = s.hit_global; d = s.new_dir; I = I * s.mod;
+            mask |= 1ull << r;
+        }
+        store3(a.opos, i, p); store3(a.odir, i, d);
+        a.ointen[i] = I;
+        if (a.hitmask) a.hitmask[i] = mask;
+    }
+}
+
+// ============================================================================================
+// Parameter-gradient reduction helpers (adjoint kernels)
+// ============================================================================================
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// Reduce entries [lo, hi) of G over the warp and add them to the block accumulator row.
+__device__ __forceinline__ void reduce_span(const RowGrad& G, int lo, int hi, float* acc_row) {
+    for (int e = lo; e < hi; ++e) {
+        const float s = warp_sum(G.g[e]);
+        if ((threadIdx.x & 31) == 0 && s != 0.0f) atomicAdd(acc_row + e, s);
+    }
+}
+
+__device__ __forceinline__ void reduce_row_grad(const RowGrad& G, int flags, float* acc_row) {
+    if (flags & RTT_FLAG_GRAD_POSE_E) reduce_span(G, RTT_F_RE, RTT_F_TE + 3, acc_row);
+    if (flags & RTT_FLAG_GRAD_POSE_S) reduce_span(G, RTT_F_RS, RTT_F_TS + 3, acc_row);
+    if (flags & RTT_FLAG_GRAD_CK) reduce_span(G, RTT_F_C, RTT_F_K + 1, acc_row);
+    if (flags & RTT_FLAG_GRAD_RADIUS) reduce_span(G, RTT_F_RADIUS, RTT_F_RADIUS + 1, acc_row);
+    if (flags & RTT_FLAG_GRAD_IOR) reduce_span(G, RTT_F_IOR_IN, RTT_F_IOR_OUT + 1, acc_row);
+}
+
+// Per-lane variant for divergent rows (non-sequential adjoint): shared-memory atomics.
+__device__ __forceinline__ void scatter_row_grad(const RowGrad& G, int flags, float* acc_row) {
+    auto span = [&](int lo, int hi) {
+        for (int e = lo; e < hi; ++e) if (G.g[e] != 0.0f) atomicAdd(acc_row + e, G.g[e]);
+    };
+    if (flags & RTT_FLAG_GRAD_POSE_E) span(RTT_F_RE, RTT_F_TE + 3);
+    if (flags & RTT_FLAG_GRAD_POSE_S) span(RTT_F_RS, RTT_F_TS + 3);
+    if (flags & RTT_FLAG_GRAD_CK) span(RTT_F_C, RTT_F_K + 1);
+    if (flags & RTT_FLAG_GRAD_RADIUS) span(RTT_F_RADIUS, RTT_F_RADIUS + 1);
+    if (flags & RTT_FLAG_GRAD_IOR) span(RTT_F_IOR_IN, RTT_F_IOR_OUT + 1);
+}
+
+__device__ __forceinline__ void flush_block_grads(const float* acc, int S, float* g_table,
+                                                  const float* acc_lut, int L, float* g_lut) {
+    __syncthreads();
+    if (g_table)
+        for (int idx = threadIdx.x; idx < S * RTT_ROW_G; idx += blockDim.x)
+            if (acc[idx] != 0.0f) atomicAdd(g_table + idx, acc[idx]);
+    if (g_lut)
+        for (int idx = threadIdx.x; idx < L * S * 2; idx += blockDim.x)
+            if (acc_lut[idx] != 0.0f) atomicAdd(g_lut + idx, acc_lut[idx]);
+}
+
+// ============================================================================================
+// Sequential trace, adjoint
+// ============================================================================================
+
+struct Checkpoint { V3 p, d; };
+
+__global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_bwd)(const __grid_constant__ SeqBwdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = a.tab.S, L = a.tab.L;
+    SmemTable T = carve(smem_raw, S, L);
+    float* acc = reinterpret_cast<float*>(smem_raw + ((smem_table_bytes(S, L) + 15) / 16) * 16);
+    float* acc_lut = acc + S * RTT_ROW_G;
+    for (int idx = threadIdx.x; idx < S * RTT_ROW_G + L * S * 2; idx += blockDim.x) acc[idx] = 0.0f;
+    stage_table(a.tab, T);
+
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < a.n; base += stride) {
+        const long long i = base + threadIdx.x;
+        const bool live = i < a.n;
+        unsigned long long mask = 0ull;
+        V3 p = v3(0, 0, 0), d = v3(0, 0, 1);
+        int lam = 0;
+        if (live) {
+            mask = a.hitmask[i];
+            p = load3(a.pos, i); d = load3(a.dir, i);
+            if (L > 0) lam = wavelength_index(T, L, a.wav[i]);
+        }
+        // ---- forward replay over the recorded interactions ----
+        Checkpoint ck[RTT_MAX_ROWS];
+        int nh = 0;
+        for (unsigned long long m = mask; m; m &= m - 1) {
+            const int r = __ffsll((long long)m) - 1;
+            ck[nh].p = p; ck[nh].d = d; ++nh;
+            const RowDev& R = T.rows[r];
+            const Frames F = to_frames(R, p, d);
+            const Roots q = solve_roots(R, F.o, F.dd);
+            int which;
+            const float t = select_root(R, q, F.o, F.dd, &which);
+            const Ior io = row_ior(T, S, L, r, lam);
+            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
+            p = s.hit_global; d = s.new_dir;
+        }
+        // ---- reverse sweep ----
+        V3 gp = v3(0, 0, 0), gd = v3(0, 0, 0);
+        float gI = 0.0f;
+        if (live) {
+            if (a.g_opos) gp = load3(a.g_opos, i);
+            if (a.g_odir) gd = load3(a.g_odir, i);
+            if (a.g_ointen) gI = a.g_ointen[i];
+        }
+        for (int r = S - 1; r >= 0; --r) {
+            const bool hit = (mask >> r) & 1ull;
+            if (__ballot_sync(kFull, hit) == 0u) continue;
+            const RowDev& R = T.rows[r];
+            const int flags = R.i[RTT_I_FLAGS];
+            RowGrad G;
+            zero(G);
+            if (hit) {
+                --nh;
+                const Ior io = row_ior(T, S, L, r, lam);
+                V3 g_hl = v3(0, 0, 0);
+                float g_w = 0.0f;
+                const int slot = R.i[RTT_I_SENSOR];
+                if (slot >= 0 && slot < a.n_sens && a.g_record[slot]) {
+                    const float4 gr = reinterpret_cast<const float4*>(a.g_record[slot])[i];
+                    g_hl = v3(gr.x, gr.y, gr.z); g_w = gr.w;
+                }
+                V3 ngp, ngd; float mod;
+                interact_adjoint(R, ck[nh].p, ck[nh].d, io.ni, io.no, io.mu_enter, io.mu_exit,
+                                 gp, gd, g_hl, v3(0, 0, 0), 0.0f, ngp, ngd, mod, G, flags);
+                gp = ngp; gd = ngd;
+                gI = gI * mod + g_w;
+            }
+            if (a.g_table && flags) {
+                if (L > 0 && (flags & RTT_FLAG_GRAD_IOR)) {
+                    // wavelength-resolved index gradients go to the LUT accumulator
+                    for (int l = 0; l < L; ++l) {
+                        const float s_in = warp_sum((hit && lam == l) ? G.g[RTT_F_IOR_IN] : 0.0f);
+                        const float s_out = warp_sum((hit && lam == l) ? G.g[RTT_F_IOR_OUT] : 0.0f);
+                        if ((threadIdx.x & 31) == 0) {
+                            if (s_in != 0.0f) atomicAdd(acc_lut + ((size_t)l * S + r) * 2, s_in);
+                            if (s_out != 0.0f) atomicAdd(acc_lut + ((size_t)l * S + r) * 2 + 1, s_out);
+                        }
+                    }
+                    reduce_row_grad(G, flags & ~RTT_FLAG_GRAD_IOR, acc + r * RTT_ROW_G);
+                } else {
+                    reduce_row_grad(G, flags, acc + r * RTT_ROW_G);
+                }
+            }
+        }
+        if (live) {
+            if (a.g_pos) store3(a.g_pos, i, gp);
+            if (a.g_dir) store3(a.g_dir, i, gd);
+            if (a.g_inten) a.g_inten[i] = gI;
+        }
+    }
+    flush_block_grads(acc, S, a.g_table, acc_lut, L, a.g_lut);
+}
+
+// ============================================================================================
+// Non-sequential trace, forward (scene/base.py:129-235)
+// ============================================================================================
+
+__global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const __grid_constant__ NonseqFwdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemTable T = carve(smem_raw, a.tab.S, a.tab.L);
+    stage_table(a.tab, T);
+    const int S = a.tab.S, L = a.tab.L, NB = a.nbounces;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        V3 p = load3(a.pos, i), d = load3(a.dir, i);
+        float I = a.inten[i];
+        const int lam = (L > 0) ? wavelength_index(T, L, a.wav[i]) : 0;
+        int nb = 0;
+        for (; nb < NB; ++nb) {
+            if (!(I > 0.0f)) break;                                     // base.py:140,201
+            // ray_cast (base.py:164-176): min over all rows, NaN anywhere => no hit
+            float best = rtt_inf();
+            int win = -1;
+            bool poisoned = false;
+            for (int r = 0; r < S; ++r) {
+                Frames F; Roots q; float t; int which;
+                const bool valid = intersect<true>(T.rows, r, p, d, F, q, t, which);
+                // rows of a Shape report inf when invalid; bare surfaces may report NaN
+                if (T.rows[r].i[RTT_I_SHAPE] == RTT_SHAPE_NONE && is_nan(t)) poisoned = true;
+                if (valid && t < best) { best = t; win = r; }
+            }
+            if (poisoned || win < 0) break;
+            Frames F; Roots q; float t; int which;
+            intersect<false>(T.rows, win, p, d, F, q, t, which);
+            const RowDev& R = T.rows[win];
+            const Ior io = row_ior(T, S, L, win, lam);
+            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
+            const int slot = R.i[RTT_I_SENSOR];
+            if (slot >= 0 && slot < a.n_sens) sensor_deposit(a.sens[slot], i, s.hit_local, I, lam);
+            p = s.hit_global; d = s.new_dir; I = I * s.mod;
+            if (a.hit_seq) a.hit_seq[i * NB + nb] = (unsigned char)win;
+        }
+        if (a.hit_seq) for (int b = nb; b < NB; ++b) a.hit_seq[i * NB + b] = 255;
+        if (a.n_hits) a.n_hits[i] = (unsigned char)nb;
+        store3(a.opos, i, p); store3(a.odir, i, d);
+        a.ointen[i] = I;
+    }
+}
+
+// ============================================================================================
+// Non-sequential trace, adjoint: replay the recorded hit sequence, then reverse
+// ============================================================================================
+
+constexpr int kMaxReplay = 32;   // bounces differentiated per ray (deeper tails are treated as constant)
+
+__global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_bwd)(const __grid_constant__ NonseqBwdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = a.tab.S, L = a.tab.L, NB = a.nbounces;
+    SmemTable T = carve(smem_raw, S, L);
+    float* acc = reinterpret_cast<float*>(smem_raw + ((smem_table_bytes(S, L) + 15) / 16) * 16);
+    float* acc_lut = acc + S * RTT_ROW_G;
+    for (int idx = threadIdx.x; idx < S * RTT_ROW_G + L * S * 2; idx += blockDim.x) acc[idx] = 0.0f;
+    stage_table(a.tab, T);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        V3 p = load3(a.pos, i), d = load3(a.dir, i);
+        const int lam = (L > 0) ? wavelength_index(T, L, a.wav[i]) : 0;
+        Checkpoint ck[kMaxReplay];
+        unsigned char rows_hit[kMaxReplay];
+        int nh = 0;
+        const int lim = NB < kMaxReplay ? NB : kMaxReplay;
+        for (int b = 0; b < lim; ++b) {
+            const int r = a.hit_seq[i * NB + b];
+            if (r == 255) break;
+            ck[nh].p = p; ck[nh].d = d; rows_hit[nh] = (unsigned char)r; ++nh;
+            const RowDev& R = T.rows[r];
+            const Frames F = to_frames(R, p, d);
+            const Roots q = solve_roots(R, F.o, F.dd);
+            int which;
+            const float t = select_root(R, q, F.o, F.dd, &which);
+            const Ior io = row_ior(T, S, L, r, lam);
+            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
+            p = s.hit_global; d = s.new_dir;
+        }
+        V3 gp = a.g_opos ? load3(a.g_opos, i) : v3(0, 0, 0);
+        V3 gd = a.g_odir ? load3(a.g_odir, i) : v3(0, 0, 0);
+        float gI = a.g_ointen ? a.g_ointen[i] : 0.0f;
+        while (nh > 0) {
+            --nh;
+            const int r = rows_hit[nh];
+            const RowDev& R = T.rows[r];
+            const int flags = R.i[RTT_I_FLAGS];
+            const Ior io = row_ior(T, S, L, r, lam);
+            RowGrad G;
+            zero(G);
+            V3 ngp, ngd; float mod;
+            interact_adjoint(R, ck[nh].p, ck[nh].d, io.ni, io.no, io.mu_enter, io.mu_exit,
+                             gp, gd, v3(0, 0, 0), v3(0, 0, 0), 0.0f, ngp, ngd, mod, G, flags);
+            gp = ngp; gd = ngd; gI = gI * mod;
+            if (a.g_table && flags) {
+                if (L > 0 && (flags & RTT_FLAG_GRAD_IOR)) {
+                    atomicAdd(acc_lut + ((size_t)lam * S + r) * 2, G.g[RTT_F_IOR_IN]);
+                    atomicAdd(acc_lut + ((size_t)lam * S + r) * 2 + 1, G.g[RTT_F_IOR_OUT]);
+                    scatter_row_grad(G, flags & ~RTT_FLAG_GRAD_IOR, acc + r * RTT_ROW_G);
+                } else {
+                    scatter_row_grad(G, flags, acc + r * RTT_ROW_G);
+                }
+            }
+        }
+        if (a.g_pos) store3(a.g_pos, i, gp);
+        if (a.g_dir) store3(a.g_dir, i, gd);
+        if (a.g_inten) a.g_inten[i] = gI;
+    }
+    flush_block_grads(acc, S, a.g_table, acc_lut, L, a.g_lut);
+}
+
+// ============================================================================================
+// Element.intersectTest (elements/parent.py:30-42): [n, k] distances
+// ============================================================================================
+
+__global__ void __launch_bounds__(kThreads) RTT_NAME(k_intersect_test)(const __grid_constant__ IsectArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemTable T = carve(smem_raw, a.tab.S, 0);
+    TableDev tb = a.tab; tb.L = 0;
+    stage_table(tb, T);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        const V3 p = load3(a.pos, i), d = load3(a.dir, i);
+        for (int j = 0; j < a.k; ++j) {
+            Frames F; Roots q; float t; int which;
+            const bool valid = intersect<true>(T.rows, a.row0 + j, p, d, F, q, t, which);
+            // Shape rows mask invalid hits to inf (shape.py:55); bare surfaces return t as is
+            const bool bare = T.rows[a.row0 + j].i[RTT_I_SHAPE] == RTT_SHAPE_NONE;
+            a.t_out[i * a.k + j] = bare ? t : (valid ? t : rtt_inf());
+        }
+    }
+}
+
+// ============================================================================================
+// Element.forward on one row (elements/parent.py:44-58), forward and adjoint
+// ============================================================================================
+
+__global__ void __launch_bounds__(kThreads) RTT_NAME(k_surface_step_fwd)(const __grid_constant__ StepFwdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemTable T = carve(smem_raw, a.tab.S, a.tab.L);
+    stage_table(a.tab, T);
+    const int S = a.tab.S, L = a.tab.L, r = a.row;
+    const RowDev& R = T.rows[r];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        const V3 p = load3(a.pos, i), d = load3(a.dir, i);
+        const int lam = (L > 0) ? wavelength_index(T, L, a.wav[i]) : 0;
+        const Frames F = to_frames(R, p, d);
+        const Roots q = solve_roots(R, F.o, F.dd);
+        int which;
+        const float t = select_root(R, q, F.o, F.dd, &which);
+        const Ior io = row_ior(T, S, L, r, lam);
+        const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
+        store3(a.npos, i, s.hit_global); store3(a.ndir, i, s.new_dir);
+        a.mod[i] = s.mod;
+        if (a.hit_local) store3(a.hit_local, i, s.hit_local);
+        if (a.t_out) a.t_out[i] = t;
+        if (a.normal) store3(a.normal, i, s.normal);
+    }
+}
+
+
+__global__ void __launch_bounds__(kThreads) RTT_NAME(k_surface_step_bwd)(const __grid_constant__ StepBwdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = a.tab.S, L = a.tab.L, r = a.row;
+    SmemTable T = carve(smem_raw, S, L);
+    float* acc = reinterpret_cast<float*>(smem_raw + ((smem_table_bytes(S, L) + 15) / 16) * 16);
+    float* acc_lut = acc + S * RTT_ROW_G;
+    for (int idx = threadIdx.x; idx < S * RTT_ROW_G + L * S * 2; idx += blockDim.x) acc[idx] = 0.0f;
+    stage_table(a.tab, T);
+    const RowDev& R = T.rows[r];
+    const int flags = R.i[RTT_I_FLAGS];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < a.n; base += stride) {
+        const long long i = base + threadIdx.x;
+        const bool live = i < a.n;
+        RowGrad G;
+        zero(G);
+        int lam = 0;
+        if (live) {
+            const V3 p = load3(a.pos, i), d = load3(a.dir, i);
+            if (L > 0) lam = wavelength_index(T, L, a.wav[i]);
+            const Ior io = row_ior(T, S, L, r, lam);
+            const V3 gnp = a.g_npos ? load3(a.g_npos, i) : v3(0, 0, 0);
+            const V3 gnd = a.g_ndir ? load3(a.g_ndir, i) : v3(0, 0, 0);
+            const V3 ghl = a.g_hit_local ? load3(a.g_hit_local, i) : v3(0, 0, 0);
+            const V3 gnn = a.g_normal ? load3(a.g_normal, i) : v3(0, 0, 0);
+            const float gtt = a.g_t ? a.g_t[i] : 0.0f;
+            V3 gp, gd; float mod;
+            interact_adjoint(R, p, d, io.ni, io.no, io.mu_enter, io.mu_exit, gnp, gnd, ghl, gnn, gtt,
+                             gp, gd, mod, G, flags);
+            if (a.g_pos) store3(a.g_pos, i, gp);
+            if (a.g_dir) store3(a.g_dir, i, gd);
+        }
+        if (a.g_table && flags) {
+            if (L > 0 && (flags & RTT_FLAG_GRAD_IOR)) {
+                for (int l = 0; l < L; ++l) {
+                    const float s_in = warp_sum((live && lam == l) ? G.g[RTT_F_IOR_IN] : 0.0f);
+                    const float s_out = warp_sum((live && lam == l) ? G.g[RTT_F_IOR_OUT] : 0.0f);
+                    if ((threadIdx.x & 31) == 0) {
+                        if (s_in != 0.0f) atomicAdd(acc_lut + ((size_t)l * S + r) * 2, s_in);
+                        if (s_out != 0.0f) atomicAdd(acc_lut + ((size_t)l * S + r) * 2 + 1, s_out);
+                    }
+                }
+                reduce_row_grad(G, flags & ~RTT_FLAG_GRAD_IOR, acc + r * RTT_ROW_G);
+            } else {
+                reduce_row_grad(G, flags, acc + r * RTT_ROW_G);
+            }
+        }
+    }
+    flush_block_grads(acc, S, a.g_table, acc_lut, L, a.g_lut);
+}
+
+// ============================================================================================
+// Host launchers
+// ============================================================================================
+inline int sm_count() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return sms;
+}
+
+// persistent blocks: a multiple of the SM count, never more blocks than there are ray tiles
+inline int grid_for(long long n, int blocks_per_sm) {
+    const long long tiles = (n + kThreads - 1) / kThreads;
+    long long g = (long long)sm_count() * blocks_per_sm;
+    if (g <= 0) g = 1;
+    if (tiles < g) g = tiles;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+inline size_t bwd_smem(int S, int L) {
+    return ((smem_table_bytes(S, L) + 15) / 16) * 16 + sizeof(float) * ((size_t)S * RTT_ROW_G + (size_t)L * S * 2);
+}
+
+cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
+    RTT_NAME(k_trace_seq_fwd)<<<grid_for(a.n, 8), kThreads, smem_table_bytes(a.tab.S, a.tab.L), st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t RTT_NAME(launch_seq_bwd)(const SeqBwdArgs& a, cudaStream_t st) {
+    RTT_NAME(k_trace_seq_bwd)<<<grid_for(a.n, 4), kThreads, bwd_smem(a.tab.S, a.tab.L), st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t RTT_NAME(launch_nonseq_fwd)(const NonseqFwdArgs& a, cudaStream_t st) {
+    RTT_NAME(k_trace_nonseq_fwd)<<<grid_for(a.n, 8), kThreads, smem_table_bytes(a.tab.S, a.tab.L), st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t RTT_NAME(launch_nonseq_bwd)(const NonseqBwdArgs& a, cudaStream_t st) {
+    RTT_NAME(k_trace_nonseq_bwd)<<<grid_for(a.n, 4), kThreads, bwd_smem(a.tab.S, a.tab.L), st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t RTT_NAME(launch_intersect_test)(const IsectArgs& a, cudaStream_t st) {
+    RTT_NAME(k_intersect_test)<<<grid_for(a.n, 8), kThreads, smem_table_bytes(a.tab.S, 0), st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t RTT_NAME(launch_step_fwd)(const StepFwdArgs& a, cudaStream_t st) {
+    RTT_NAME(k_surface_step_fwd)<<<grid_for(a.n, 8), kThreads, smem_table_bytes(a.tab.S, a.tab.L), st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t RTT_NAME(launch_step_bwd)(const StepBwdArgs& a, cudaStream_t st) {
+    RTT_NAME(k_surface_step_bwd)<<<grid_for(a.n, 4), kThreads, bwd_smem(a.tab.S, a.tab.L), st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace RTT_VARIANT
+}  // namespace rtt

@@ -1,0 +1,109 @@
+// rtt_kernels_decl.h — argument records and host launchers of one kernel variant.
+// Included once per variant (RTT_VARIANT = fast | exact) by rtt_kernels.inl and rtt_cabi.cu;
+// deliberately has no include guard.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/rtt_b200.h"
+
+#ifndef RTT_CAT
+#define RTT_CAT2(a, b) a##b
+#define RTT_CAT(a, b) RTT_CAT2(a, b)
+#define RTT_NAME(base) RTT_CAT(base, RTT_CAT(_, RTT_VARIANT))
+#endif
+
+namespace rtt {
+namespace RTT_VARIANT {
+
+struct SensorDev {
+    float* image;
+    float* record;
+    int H, W, C;
+    float x0, y0, sx, sy;
+};
+
+struct TableDev {
+    const float* f;
+    const int32_t* i;
+    int S, L;
+    const float* lut;
+    const float* lut_w;
+};
+
+struct SeqFwdArgs {
+    const float *pos, *dir, *inten, *wav;
+    float *opos, *odir, *ointen;
+    unsigned long long* hitmask;
+    TableDev tab;
+    SensorDev sens[RTT_MAX_SENSORS];
+    int n_sens;
+    long long n;
+};
+
+struct SeqBwdArgs {
+    const float *pos, *dir, *inten, *wav;
+    const unsigned long long* hitmask;
+    const float *g_opos, *g_odir, *g_ointen;
+    const float* g_record[RTT_MAX_SENSORS];
+    float *g_pos, *g_dir, *g_inten;
+    float *g_table, *g_lut;
+    TableDev tab;
+    int n_sens;
+    long long n;
+};
+
+struct NonseqFwdArgs {
+    const float *pos, *dir, *inten, *wav;
+    float *opos, *odir, *ointen;
+    unsigned char *hit_seq, *n_hits;
+    TableDev tab;
+    SensorDev sens[RTT_MAX_SENSORS];
+    int n_sens, nbounces;
+    long long n;
+};
+
+struct NonseqBwdArgs {
+    const float *pos, *dir, *inten, *wav;
+    const unsigned char* hit_seq;
+    const float *g_opos, *g_odir, *g_ointen;
+    float *g_pos, *g_dir, *g_inten;
+    float *g_table, *g_lut;
+    TableDev tab;
+    int nbounces;
+    long long n;
+};
+
+struct IsectArgs {
+    const float *pos, *dir;
+    float* t_out;
+    TableDev tab;
+    int row0, k;
+    long long n;
+};
+
+struct StepFwdArgs {
+    const float *pos, *dir, *wav;
+    float *npos, *ndir, *mod, *hit_local, *t_out, *normal;
+    TableDev tab;
+    int row;
+    long long n;
+};
+
+struct StepBwdArgs {
+    const float *pos, *dir, *wav;
+    const float *g_npos, *g_ndir, *g_hit_local, *g_t, *g_normal;
+    float *g_pos, *g_dir, *g_table, *g_lut;
+    TableDev tab;
+    int row;
+    long long n;
+};
+
+cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st);
+cudaError_t RTT_NAME(launch_seq_bwd)(const SeqBwdArgs& a, cudaStream_t st);
+cudaError_t RTT_NAME(launch_nonseq_fwd)(const NonseqFwdArgs& a, cudaStream_t st);
+cudaError_t RTT_NAME(launch_nonseq_bwd)(const NonseqBwdArgs& a, cudaStream_t st);
+cudaError_t RTT_NAME(launch_intersect_test)(const IsectArgs& a, cudaStream_t st);
+cudaError_t RTT_NAME(launch_step_fwd)(const StepFwdArgs& a, cudaStream_t st);
+cudaError_t RTT_NAME(launch_step_bwd)(const StepBwdArgs& a, cudaStream_t st);
+
+}  // namespace RTT_VARIANT
+}  // namespace rtt

@@ -1,0 +1,363 @@
+// hostsim.cpp — TEST INFRASTRUCTURE: runs the kernels' per-ray arithmetic on the host.
+//
+// The CUDA kernels cannot execute in the build container (no GPU).  This file compiles the
+// very same per-ray source (raytracetorch_b200/csrc/rtt_core.cuh) with g++ and drives it
+// with plain loops that mirror the kernel bodies of rtt_kernels.inl, so the CPU test-suite
+// can check the kernel arithmetic (forward AND hand-written adjoint) against the torch
+// oracle before any GPU time is spent.  It exports the same C signatures as
+// include/rtt_b200.h but with HOST pointers.  It is built into tests/hostsim/ and is never
+// loaded by the product package (raytracetorch_b200/_cabi.py only opens librtt_b200.so).
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../raytracetorch_b200/csrc/rtt_core.cuh"
+
+using namespace rtt;
+
+namespace {
+
+struct HostTable {
+    std::vector<RowDev> rows;
+    int S = 0, L = 0;
+    std::vector<float> ni, no, mu_enter, mu_exit, lut_w;
+};
+
+HostTable stage(const rtt_table_t* t) {
+    HostTable T;
+    T.S = t->n_rows; T.L = t->n_lut;
+    T.rows.resize(T.S);
+    for (int r = 0; r < T.S; ++r) {
+        std::memset(&T.rows[r], 0, sizeof(RowDev));
+        std::memcpy(T.rows[r].f, t->f + (size_t)r * RTT_ROW_F, sizeof(float) * RTT_ROW_F);
+        std::memcpy(T.rows[r].i, t->i + (size_t)r * RTT_ROW_I, sizeof(int32_t) * RTT_ROW_I);
+        prepare_row(T.rows[r]);
+    }
+    const int LS = T.L * T.S;
+    T.ni.resize(LS); T.no.resize(LS); T.mu_enter.resize(LS); T.mu_exit.resize(LS);
+    for (int idx = 0; idx < LS; ++idx) {
+        T.ni[idx] = t->lut[2 * idx]; T.no[idx] = t->lut[2 * idx + 1];
+        T.mu_enter[idx] = T.no[idx] / T.ni[idx]; T.mu_exit[idx] = T.ni[idx] / T.no[idx];
+    }
+    T.lut_w.assign(t->lut_w, t->lut_w + T.L);
+    return T;
+}
+
+int lam_index(const HostTable& T, float w) {
+    int best = 0;
+    float bd = std::fabs(w - T.lut_w[0]);
+    for (int l = 1; l < T.L; ++l) {
+        const float dd = std::fabs(w - T.lut_w[l]);
+        if (dd < bd) { bd = dd; best = l; }
+    }
+    return best;
+}
+
+struct Ior { float ni, no, mu_enter, mu_exit; };
+
+Ior row_ior(const HostTable& T, int r, int lam) {
+    Ior q;
+    if (T.L > 0) {
+        const int idx = lam * T.S + r;
+        q.ni = T.ni[idx]; q.no = T.no[idx]; q.mu_enter = T.mu_enter[idx]; q.mu_exit = T.mu_exit[idx];
+    } else {
+        const RowDev& R = T.rows[r];
+        q.ni = R.f[RTT_F_IOR_IN]; q.no = R.f[RTT_F_IOR_OUT]; q.mu_enter = R.f[D_MU_ENTER]; q.mu_exit = R.f[D_MU_EXIT];
+    }
+    return q;
+}
+
+V3 load3(const float* a, int64_t i) { return v3(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
+void store3(float* a, int64_t i, V3 v) { a[3 * i] = v.x; a[3 * i + 1] = v.y; a[3 * i + 2] = v.z; }
+
+void deposit(const rtt_sensor_t& sd, int64_t i, V3 hl, float w, int lam) {
+    if (sd.record) { float* r = sd.record + 4 * i; r[0] = hl.x; r[1] = hl.y; r[2] = hl.z; r[3] = w; }
+    if (sd.image) {
+        int ix, iy;
+        if (sensor_bin(hl.x, hl.y, sd.x0, sd.y0, sd.sx, sd.sy, sd.width, sd.height, &ix, &iy)) {
+            const int ch = (sd.channels > 1) ? (lam < sd.channels - 1 ? lam : sd.channels - 1) : 0;
+            sd.image[((size_t)ch * sd.height + iy) * sd.width + ix] += w;
+        }
+    }
+}
+
+void add_row_grad(const RowGrad& G, int flags, float* acc_row) {
+    auto span = [&](int lo, int hi) { for (int e = lo; e < hi; ++e) acc_row[e] += G.g[e]; };
+    if (flags & RTT_FLAG_GRAD_POSE_E) span(RTT_F_RE, RTT_F_TE + 3);
+    if (flags & RTT_FLAG_GRAD_POSE_S) span(RTT_F_RS, RTT_F_TS + 3);
+    if (flags & RTT_FLAG_GRAD_CK) span(RTT_F_C, RTT_F_K + 1);
+    if (flags & RTT_FLAG_GRAD_RADIUS) span(RTT_F_RADIUS, RTT_F_RADIUS + 1);
+    if (flags & RTT_FLAG_GRAD_IOR) span(RTT_F_IOR_IN, RTT_F_IOR_OUT + 1);
+}
+
+struct Ck { V3 p, d; };
+
+// shared reverse step used by both adjoint drivers
+void reverse_row(const HostTable& T, int r, int lam, const Ck& ck, V3& gp, V3& gd, float& gI,
+                 V3 g_hl, float g_w, float* g_table, float* g_lut) {
+    const RowDev& R = T.rows[r];
+    const int flags = R.i[RTT_I_FLAGS];
+    const Ior io = row_ior(T, r, lam);
+    RowGrad G;
+    zero(G);
+    V3 ngp, ngd; float mod;
+    interact_adjoint(R, ck.p, ck.d, io.ni, io.no, io.mu_enter, io.mu_exit, gp, gd, g_hl, v3(0, 0, 0), 0.0f,
+                     ngp, ngd, mod, G, flags);
+    gp = ngp; gd = ngd; gI = gI * mod + g_w;
+    if (g_table && flags) {
+        int fl = flags;
+        if (T.L > 0 && (flags & RTT_FLAG_GRAD_IOR)) {
+            if (g_lut) {
+                g_lut[((size_t)lam * T.S + r) * 2] += G.g[RTT_F_IOR_IN];
+                g_lut[((size_t)lam * T.S + r) * 2 + 1] += G.g[RTT_F_IOR_OUT];
+            }
+            fl &= ~RTT_FLAG_GRAD_IOR;
+        }
+        add_row_grad(G, fl, g_table + (size_t)r * RTT_ROW_G);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_intensity,
+                      const float* in_wavelength,
+                      float* out_pos, float* out_dir, float* out_intensity, uint64_t* hitmask,
+                      const rtt_table_t* table, const rtt_sensor_t* sensors, int32_t n_sensors,
+                      int64_t n, int32_t, void*) {
+    const HostTable T = stage(table);
+    for (int64_t i = 0; i < n; ++i) {
+        V3 p = load3(in_pos, i), d = load3(in_dir, i);
+        float I = in_intensity[i];
+        const int lam = T.L > 0 ? lam_index(T, in_wavelength[i]) : 0;
+        uint64_t mask = 0;
+        for (int r = 0; r < T.S; ++r) {
+            Frames F; Roots q; float t; int which;
+            if (!intersect<true>(T.rows.data(), r, p, d, F, q, t, which)) continue;
+            const RowDev& R = T.rows[r];
+            const Ior io = row_ior(T, r, lam);
+            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
+            const int slot = R.i[RTT_I_SENSOR];
+            if (slot >= 0 && slot < n_sensors) deposit(sensors[slot], i, s.hit_local, I, lam);
+            p = s.hit_global; d = s.new_dir; I = I * s.mod;
+            mask |= 1ull << r;
+        }
+        store3(out_pos, i, p); store3(out_dir, i, d);
+        out_intensity[i] = I;
+        if (hitmask) hitmask[i] = mask;
+    }
+    return 0;
+}
+
+int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float*,
+                      const float* in_wavelength, const uint64_t* hitmask,
+                      const float* g_out_pos, const float* g_out_dir, const float* g_out_intensity,
+                      const float* const* g_record,
+                      float* g_in_pos, float* g_in_dir, float* g_in_intensity,
+                      float* g_table, float* g_lut,
+                      const rtt_table_t* table, int32_t n_sensors,
+                      int64_t n, int32_t, void*) {
+    const HostTable T = stage(table);
+    std::vector<Ck> ck(RTT_MAX_ROWS);
+    for (int64_t i = 0; i < n; ++i) {
+        V3 p = load3(in_pos, i), d = load3(in_dir, i);
+        const int lam = T.L > 0 ? lam_index(T, in_wavelength[i]) : 0;
+        const uint64_t mask = hitmask[i];
+        int nh = 0;
+        for (int r = 0; r < T.S; ++r) {
+            if (!((mask >> r) & 1ull)) continue;
+            ck[nh].p = p; ck[nh].d = d; ++nh;
+            const RowDev& R = T.rows[r];
+            const Frames F = to_frames(R, p, d);
+            const Roots q = solve_roots(R, F.o, F.dd);
+            int which;
+            const float t = select_root(R, q, F.o, F.dd, &which);
+            const Ior io = row_ior(T, r, lam);
+            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
+            p = s.hit_global; d = s.new_dir;
+        }
+        V3 gp = g_out_pos ? load3(g_out_pos, i) : v3(0, 0, 0);
+        V3 gd = g_out_dir ? load3(g_out_dir, i) : v3(0, 0, 0);
+        float gI = g_out_intensity ? g_out_intensity[i] : 0.0f;
+        for (int r = T.S - 1; r >= 0; --r) {
+            if (!((mask >> r) & 1ull)) continue;
+            --nh;
+            V3 g_hl = v3(0, 0, 0); float g_w = 0.0f;
+            const int slot = T.rows[r].i[RTT_I_SENSOR];
+            if (slot >= 0 && slot < n_sensors && g_record && g_record[slot]) {
+                const float* gr = g_record[slot] + 4 * i;
+                g_hl = v3(gr[0], gr[1], gr[2]); g_w = gr[3];
+            }
+            reverse_row(T, r, lam, ck[nh], gp, gd, gI, g_hl, g_w, g_table, g_lut);
+        }
+        if (g_in_pos) store3(g_in_pos, i, gp);
+        if (g_in_dir) store3(g_in_dir, i, gd);
+        if (g_in_intensity) g_in_intensity[i] = gI;
+    }
+    return 0;
+}
+
+int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* in_intensity,
+                         const float* in_wavelength,
+                         float* out_pos, float* out_dir, float* out_intensity,
+                         uint8_t* hit_seq, uint8_t* n_hits,
+                         const rtt_table_t* table, const rtt_sensor_t* sensors, int32_t n_sensors,
+                         int32_t nbounces, int64_t n, int32_t, void*) {
+    const HostTable T = stage(table);
+    for (int64_t i = 0; i < n; ++i) {
+        V3 p = load3(in_pos, i), d = load3(in_dir, i);
+        float I = in_intensity[i];
+        const int lam = T.L > 0 ? lam_index(T, in_wavelength[i]) : 0;
+        int nb = 0;
+        for (; nb < nbounces; ++nb) {
+            if (!(I > 0.0f)) break;
+            float best = rtt_inf();
+            int win = -1;
+            bool poisoned = false;
+            for (int r = 0; r < T.S; ++r) {
+                Frames F; Roots q; float t; int which;
+                const bool valid = intersect<true>(T.rows.data(), r, p, d, F, q, t, which);
+                if (T.rows[r].i[RTT_I_SHAPE] == RTT_SHAPE_NONE && is_nan(t)) poisoned = true;
+                if (valid && t < best) { best = t; win = r; }
+            }
+            if (poisoned || win < 0) break;
+            Frames F; Roots q; float t; int which;
+            intersect<false>(T.rows.data(), win, p, d, F, q, t, which);
+            const RowDev& R = T.rows[win];
+            const Ior io = row_ior(T, win, lam);
+            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
+            const int slot = R.i[RTT_I_SENSOR];
+            if (slot >= 0 && slot < n_sensors) deposit(sensors[slot], i, s.hit_local, I, lam);
+            p = s.hit_global; d = s.new_dir; I = I * s.mod;
+            if (hit_seq) hit_seq[i * nbounces + nb] = (uint8_t)win;
+        }
+        if (hit_seq) for (int b = nb; b < nbounces; ++b) hit_seq[i * nbounces + b] = 255;
+        if (n_hits) n_hits[i] = (uint8_t)nb;
+        store3(out_pos, i, p); store3(out_dir, i, d);
+        out_intensity[i] = I;
+    }
+    return 0;
+}
+
+int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float*,
+                         const float* in_wavelength, const uint8_t* hit_seq, int32_t nbounces,
+                         const float* g_out_pos, const float* g_out_dir, const float* g_out_intensity,
+                         float* g_in_pos, float* g_in_dir, float* g_in_intensity,
+                         float* g_table, float* g_lut,
+                         const rtt_table_t* table, int64_t n, int32_t, void*) {
+    const HostTable T = stage(table);
+    std::vector<Ck> ck(nbounces + 1);
+    std::vector<int> rows_hit(nbounces + 1);
+    for (int64_t i = 0; i < n; ++i) {
+        V3 p = load3(in_pos, i), d = load3(in_dir, i);
+        const int lam = T.L > 0 ? lam_index(T, in_wavelength[i]) : 0;
+        int nh = 0;
+        for (int b = 0; b < nbounces && b < 32; ++b) {
+            const int r = hit_seq[i * nbounces + b];
+            if (r == 255) break;
+            ck[nh].p = p; ck[nh].d = d; rows_hit[nh] = r; ++nh;
+            const RowDev& R = T.rows[r];
+            const Frames F = to_frames(R, p, d);
+            const Roots q = solve_roots(R, F.o, F.dd);
+            int which;
+            const float t = select_root(R, q, F.o, F.dd, &which);
+            const Ior io = row_ior(T, r, lam);
+            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
+            p = s.hit_global; d = s.new_dir;
+        }
+        V3 gp = g_out_pos ? load3(g_out_pos, i) : v3(0, 0, 0);
+        V3 gd = g_out_dir ? load3(g_out_dir, i) : v3(0, 0, 0);
+        float gI = g_out_intensity ? g_out_intensity[i] : 0.0f;
+        while (nh > 0) {
+            --nh;
+            reverse_row(T, rows_hit[nh], lam, ck[nh], gp, gd, gI, v3(0, 0, 0), 0.0f, g_table, g_lut);
+        }
+        if (g_in_pos) store3(g_in_pos, i, gp);
+        if (g_in_dir) store3(g_in_dir, i, gd);
+        if (g_in_intensity) g_in_intensity[i] = gI;
+    }
+    return 0;
+}
+
+int rtt_intersect_test(const float* in_pos, const float* in_dir, float* t_out,
+                       const rtt_table_t* table, int32_t row0, int32_t k,
+                       int64_t n, int32_t, void*) {
+    rtt_table_t tb = *table; tb.n_lut = 0;
+    const HostTable T = stage(&tb);
+    for (int64_t i = 0; i < n; ++i) {
+        const V3 p = load3(in_pos, i), d = load3(in_dir, i);
+        for (int j = 0; j < k; ++j) {
+            Frames F; Roots q; float t; int which;
+            const bool valid = intersect<true>(T.rows.data(), row0 + j, p, d, F, q, t, which);
+            const bool bare = T.rows[row0 + j].i[RTT_I_SHAPE] == RTT_SHAPE_NONE;
+            t_out[i * k + j] = bare ? t : (valid ? t : rtt_inf());
+        }
+    }
+    return 0;
+}
+
+int rtt_surface_step_fwd(const float* in_pos, const float* in_dir, const float* in_wavelength,
+                         float* new_pos, float* new_dir, float* mod,
+                         float* hit_local, float* t_out, float* normal,
+                         const rtt_table_t* table, int32_t row, int64_t n, int32_t, void*) {
+    const HostTable T = stage(table);
+    const RowDev& R = T.rows[row];
+    for (int64_t i = 0; i < n; ++i) {
+        const V3 p = load3(in_pos, i), d = load3(in_dir, i);
+        const int lam = T.L > 0 ? lam_index(T, in_wavelength[i]) : 0;
+        const Frames F = to_frames(R, p, d);
+        const Roots q = solve_roots(R, F.o, F.dd);
+        int which;
+        const float t = select_root(R, q, F.o, F.dd, &which);
+        const Ior io = row_ior(T, row, lam);
+        const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
+        store3(new_pos, i, s.hit_global); store3(new_dir, i, s.new_dir);
+        mod[i] = s.mod;
+        if (hit_local) store3(hit_local, i, s.hit_local);
+        if (t_out) t_out[i] = t;
+        if (normal) store3(normal, i, s.normal);
+    }
+    return 0;
+}
+
+int rtt_surface_step_bwd(const float* in_pos, const float* in_dir, const float* in_wavelength,
+                         const float* g_new_pos, const float* g_new_dir, const float* g_hit_local,
+                         const float* g_t, const float* g_normal,
+                         float* g_in_pos, float* g_in_dir, float* g_table, float* g_lut,
+                         const rtt_table_t* table, int32_t row, int64_t n, int32_t, void*) {
+    const HostTable T = stage(table);
+    const RowDev& R = T.rows[row];
+    const int flags = R.i[RTT_I_FLAGS];
+    for (int64_t i = 0; i < n; ++i) {
+        const V3 p = load3(in_pos, i), d = load3(in_dir, i);
+        const int lam = T.L > 0 ? lam_index(T, in_wavelength[i]) : 0;
+        const Ior io = row_ior(T, row, lam);
+        RowGrad G;
+        zero(G);
+        V3 gp, gd; float mod;
+        interact_adjoint(R, p, d, io.ni, io.no, io.mu_enter, io.mu_exit,
+                         g_new_pos ? load3(g_new_pos, i) : v3(0, 0, 0),
+                         g_new_dir ? load3(g_new_dir, i) : v3(0, 0, 0),
+                         g_hit_local ? load3(g_hit_local, i) : v3(0, 0, 0),
+                         g_normal ? load3(g_normal, i) : v3(0, 0, 0), g_t ? g_t[i] : 0.0f,
+                         gp, gd, mod, G, flags);
+        if (g_in_pos) store3(g_in_pos, i, gp);
+        if (g_in_dir) store3(g_in_dir, i, gd);
+        if (g_table && flags) {
+            int fl = flags;
+            if (T.L > 0 && (flags & RTT_FLAG_GRAD_IOR)) {
+                if (g_lut) {
+                    g_lut[((size_t)lam * T.S + row) * 2] += G.g[RTT_F_IOR_IN];
+                    g_lut[((size_t)lam * T.S + row) * 2 + 1] += G.g[RTT_F_IOR_OUT];
+                }
+                fl &= ~RTT_FLAG_GRAD_IOR;
+            }
+            add_row_grad(G, fl, g_table + (size_t)row * RTT_ROW_G);
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"
