@@ -331,9 +331,50 @@ class Sensor(Element):
         super().__init__()
         self.shape = shape
         self.surface_functions.extend([P.Transmit()] * len(shape))
-        self.hitLocs, self.hitIntensity, self.hitID = [], [], []
+        self._locs, self._w, self._ids, self._pending = [], [], [], []
         self.image_spec = None      # (H, W, x0, x1, y0, y1, n_channels)
         self.image = None
+
+    # The fused scene kernels hand over (record [N,4], hit mask [N], ids [N]); compaction to the
+    # reference's per-call lists needs a boolean gather (a host sync), so it is deferred until
+    # somebody actually reads the lists.
+    def _pend(self, record, hit, ids):
+        self._pending.append((record, hit, ids))
+
+    def _flush(self):
+        for record, hit, ids in self._pending:
+            sel = record[hit]
+            self._locs.append(sel[:, :3])
+            self._w.append(sel[:, 3])
+            self._ids.append(ids[hit])
+        self._pending = []
+
+    @property
+    def hitLocs(self):
+        self._flush()
+        return self._locs
+
+    @hitLocs.setter
+    def hitLocs(self, v):
+        self._pending, self._locs = [], v
+
+    @property
+    def hitIntensity(self):
+        self._flush()
+        return self._w
+
+    @hitIntensity.setter
+    def hitIntensity(self, v):
+        self._w = v
+
+    @property
+    def hitID(self):
+        self._flush()
+        return self._ids
+
+    @hitID.setter
+    def hitID(self, v):
+        self._ids = v
 
     def set_image(self, height: int, width: int, extent=None, channels: int = 1):
         """Ask the scene kernels to accumulate an intensity image on this sensor.
@@ -360,12 +401,13 @@ class Sensor(Element):
         return new_pos, new_dir, mod
 
     def record(self, hit_local, intensity, ids):
-        self.hitLocs.append(hit_local)
-        self.hitIntensity.append(intensity)
-        self.hitID.append(ids)
+        self._flush()
+        self._locs.append(hit_local)
+        self._w.append(intensity)
+        self._ids.append(ids)
 
     def reset(self):
-        self.hitLocs, self.hitIntensity, self.hitID = [], [], []
+        self._locs, self._w, self._ids, self._pending = [], [], [], []
         self.image = None
 
     def getHitsTensors(self, ray_id=None):

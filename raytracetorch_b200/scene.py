@@ -1,0 +1,208 @@
+"""Scenes: the two trace loops of the reference, each executed by ONE fused CUDA kernel.
+
+* ``SequentialScene.simulate(rays)``  — scene/sequential.py:12-36.  The reference runs a
+  Python double loop with ~10^4 eager ops and two host syncs per surface; here the whole
+  surface stack is one launch (plus one adjoint launch in backward).
+* ``Scene.simulate()`` / ``step()`` / ``ray_cast(rays)`` — scene/base.py:129-235, the
+  non-sequential nearest-hit bounce loop.
+
+Same public attributes as the reference (``elements``, ``bundles``, ``rays``, ``Nbounces``,
+``map_to_element`` / ``map_to_surface``, ``total_surfaces``).  Sensors receive the same three
+hit lists; they are materialised lazily (``Sensor.hitLocs`` etc.) so that ``simulate`` itself
+never synchronises with the host.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import codes as C
+from . import ops
+from .rays import Bundle, Rays
+from .table import Dispersion, SceneCompiler
+
+
+class Scene(nn.Module):
+    """Non-sequential scene (scene/base.py:8-289)."""
+
+    def __init__(self):
+        super().__init__()
+        self.elements = nn.ModuleList()
+        self.bundles = nn.ModuleList()
+        self._bundle_N_rays: list[int] = []
+        self.rays: Optional[Rays] = None
+        self.Nbounces = 100
+        self.dispersion: Optional[Dispersion] = None
+        self.record_hits = True          # fill Sensor.hitLocs/hitIntensity/hitID like the reference
+        self.mode: Optional[int] = None  # None = ops default (FAST)
+        self.last_trace = None           # raw kernel outputs of the latest simulate()/step()
+        self._compiler = SceneCompiler()
+        self._build_index_maps()
+
+    # ---- population (scene/base.py:25-52) ---------------------------------------------------
+    def add_element(self, element):
+        self.elements.append(element)
+
+    def add_bundle(self, bundle: Bundle, N_rays: int = 200):
+        self.bundles.append(bundle)
+        self._bundle_N_rays.append(N_rays)
+
+    def clear_elements(self):
+        self.elements = nn.ModuleList()
+        self._build_index_maps()
+
+    def clear_bundles(self):
+        self.bundles = nn.ModuleList()
+        self._bundle_N_rays = []
+        self.rays = None
+
+    def clear_rays(self):
+        self.rays = None
+
+    def set_dispersion(self, dispersion: Optional[Dispersion]):
+        """Per-wavelength refractive indices (extension, see table.Dispersion)."""
+        self.dispersion = dispersion
+
+    # ---- ray construction (scene/base.py:57-90) ----------------------------------------------
+    def _build_rays(self):
+        if len(self.bundles) == 0:
+            self.rays = None
+            return
+        batches = [b.sample(n) for b, n in zip(self.bundles, self._bundle_N_rays)]
+        if len(batches) == 1:
+            self.rays = batches[0]
+            return
+        cat = lambda k: torch.cat([getattr(r, k) for r in batches], dim=0)
+        self.rays = Rays._wrap(pos=cat("pos"), dir=cat("dir"), intensity=cat("intensity"), id=cat("id"),
+                               wavelength=cat("wavelength"))
+
+    # ---- flattening (scene/base.py:96-123): row order == table row order -----------------------
+    def _build_index_maps(self):
+        dev = self.map_to_element.device if isinstance(getattr(self, "map_to_element", None), torch.Tensor) \
+            else torch.device("cpu")
+        e_idx, s_idx = [], []
+        for k, el in enumerate(self.elements):
+            n = len(el.shape)
+            e_idx += [k] * n
+            s_idx += list(range(n))
+        self.register_buffer("map_to_element", torch.tensor(e_idx, dtype=torch.long, device=dev))
+        self.register_buffer("map_to_surface", torch.tensor(s_idx, dtype=torch.long, device=dev))
+        self.total_surfaces = len(e_idx)
+
+    # ---- kernels --------------------------------------------------------------------------------
+    def table(self):
+        return self._compiler.table(self.elements, dispersion=self.dispersion)
+
+    def _deliver_to_sensors(self, table, records, hit_of_slot, rays_before: Rays, images):
+        for slot, sensor in enumerate(table.sensors):
+            if images[slot] is not None:
+                sensor.image = images[slot] if sensor.image is None else sensor.image + images[slot]
+            if self.record_hits and records.numel():
+                sensor._pend(records[slot], hit_of_slot(slot), rays_before.id)
+
+    def _trace(self, rays: Rays, nbounces: int):
+        table = self.table()
+        out = ops.trace_nonsequential(table, rays.pos, rays.dir, rays.intensity, nbounces, rays.wavelength,
+                                      want_record=self.record_hits, mode=self.mode)
+        self.last_trace = out
+        seq = out["hit_seq"]
+
+        def hit_of_slot(slot):
+            row = table.sensor_rows[slot]
+            return (seq == row).any(dim=1)
+
+        self._deliver_to_sensors(table, out["records"], hit_of_slot, rays, out["images"])
+        rays.pos, rays.dir, rays.intensity = out["pos"], out["dir"], out["intensity"]
+        return out
+
+    def simulate(self):
+        """Propagate ``self.rays`` for up to ``Nbounces`` bounces in one kernel (scene/base.py:129-142)."""
+        if self.rays is None:
+            self._build_rays()
+        if self.rays is None:
+            return
+        self._build_index_maps()
+        rays = self.rays.unwrap() if hasattr(self.rays, "unwrap") else self.rays
+        self._trace(rays, min(int(self.Nbounces), C.MAX_BOUNCES))
+
+    def step(self):
+        """One bounce for all active rays (scene/base.py:180-235)."""
+        if self.rays is None:
+            return
+        rays = self.rays.unwrap() if hasattr(self.rays, "unwrap") else self.rays
+        self._trace(rays, 1)
+
+    def ray_cast(self, rays):
+        """(hit_mask, winner_element_ids, winner_surf_ids) or None (scene/base.py:144-178)."""
+        if len(self.elements) == 0:
+            return None
+        raw = rays.unwrap() if hasattr(rays, "unwrap") else rays
+        table = self.table()
+        with torch.no_grad():
+            out = ops.trace_nonsequential(table, raw.pos, raw.dir, torch.ones_like(raw.intensity), 1,
+                                          raw.wavelength, want_record=False, sensor_cfg=[], mode=self.mode)
+            win = out["hit_seq"][:, 0].long()
+            hit_mask = win != 255
+            if not bool(hit_mask.any()):
+                return None
+            win = torch.where(hit_mask, win, torch.zeros_like(win))
+            if self.map_to_element.device != win.device:
+                self._build_index_maps()
+                self.map_to_element = self.map_to_element.to(win.device)
+                self.map_to_surface = self.map_to_surface.to(win.device)
+            return hit_mask, self.map_to_element[win], self.map_to_surface[win]
+
+    # ---- conversions (scene/base.py:261-289, scene/sequential.py:80-105) ------------------------
+    def to_sequential(self):
+        ordered = sorted(self.elements, key=lambda el: el.shape.transform.trans[2].item())
+        seq = SequentialScene(ordered)
+        seq.Nbounces = self.Nbounces
+        for b, n in zip(self.bundles, self._bundle_N_rays):
+            seq.add_bundle(b, n)
+        seq.rays, seq.dispersion = self.rays, self.dispersion
+        return seq
+
+
+class SequentialScene(Scene):
+    """Fixed traversal order (scene/sequential.py:7-36)."""
+
+    def __init__(self, elements):
+        super().__init__()
+        self.elements = nn.ModuleList(elements)
+        self._build_index_maps()
+
+    def simulate(self, rays: Optional[Rays] = None):
+        """Propagate ``rays`` through every surface of every element, in order; mutates and
+        returns the same ``Rays`` object.  ``rays=None`` uses ``self.rays`` (so the goals in
+        ``optim`` work with sequential scenes too — the reference's own call raises)."""
+        if rays is None:
+            if self.rays is None:
+                self._build_rays()
+            rays = self.rays
+        if rays is None:
+            return None
+        table = self.table()
+        out = ops.trace_sequential(table, rays.pos, rays.dir, rays.intensity, rays.wavelength,
+                                   want_record=self.record_hits, mode=self.mode)
+        self.last_trace = out
+        mask = out["hitmask"]
+
+        def hit_of_slot(slot):
+            return ((mask >> table.sensor_rows[slot]) & 1).bool()
+
+        self._deliver_to_sensors(table, out["records"], hit_of_slot, rays, out["images"])
+        rays.pos, rays.dir, rays.intensity = out["pos"], out["dir"], out["intensity"]
+        return rays
+
+    def to_base(self):
+        base = Scene()
+        base.Nbounces = self.Nbounces
+        for el in self.elements:
+            base.add_element(el)
+        for b, n in zip(self.bundles, self._bundle_N_rays):
+            base.add_bundle(b, n)
+        base.rays, base.dispersion = self.rays, self.dispersion
+        base._build_index_maps()
+        return base
