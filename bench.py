@@ -1,0 +1,508 @@
+#!/usr/bin/env python
+"""Benchmark of the ray-propagation hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1|c4|c5] [--rays R]
+
+Metric (BASELINE.json): ray-surface interactions / s = rays x table rows / time, forward; the
+forward+adjoint figure rides along in "fwd_bwd".  Workload at one GPU = BASELINE configs[1]
+("c2": crossed cylindrical lens pair + inverted stop + sensor, 14 rows, 1e8 rays, 3 wavelengths,
+3x1024x1024 sensor image).  One "step" = one pass of the hot path over one bundle.
+
+  value      device-resident inputs, CUDA-event timed, K steps, max over ranks
+  e2e        same metric through the public API (SequentialScene.simulate) with HOST (pinned) ray
+             buffers: H2D of the bundle + kernel + D2H of the sensor image inside the timed region
+  roofline   dominant kernel (k_trace_seq_fwd): algorithmic bytes / mean launch time vs the measured
+             HBM peak; "fp32" carries the FLOP view (this path has no dense contraction)
+  cpu_baseline  the CPU oracle (port of the reference's algorithm) on a bounded sample, host cores
+  --impl reference   the same CPU path as the timed arm (rank 0 only)
+
+N > 1: launched by torchrun, one rank per GPU; every rank traces its own shard (weak scaling, no
+data-path collective) and the sensor image is all-reduced once per step over NCCL.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "ray_surface_interactions_per_s"
+UNIT = "interactions/s"
+
+
+# ---------------------------------------------------------------------------------------------
+# workloads (scene definitions shared with the parity tests: tests/scenes.py)
+# ---------------------------------------------------------------------------------------------
+def build_workload(name: str, device):
+    import types
+    import raytracetorch_b200 as rtt
+    import scenes
+    ns = types.SimpleNamespace(elements=rtt.elements, geom=rtt.geom, phys=rtt.phys, rays=rtt.rays)
+    w = dict(name=name, dispersion=None, nonseq=False, nbounces=0, image=None)
+    if name == "c2":
+        els = scenes.c2_cylindrical(ns)
+        w["dispersion"] = rtt.Dispersion(scenes.C2_WAVELENGTHS, {
+            els[0].ior_glass: [1.5 * s for s in scenes.C2_GLASS_SCALE],
+            els[1].ior_glass: [1.6 * s for s in scenes.C2_GLASS_SCALE]})
+        els[3].set_image(1024, 1024, channels=3)
+        w.update(elements=els, sensor=els[3], source=("disk", 8.0, -10.0), wavelengths=scenes.C2_WAVELENGTHS,
+                 rays=10 ** 8, desc="C2 cylindrical pair + stop + sensor, 14 rows, 3 wavelengths, 3x1024x1024 image")
+    elif name == "c1":
+        els = scenes.c1_singlet(ns, physical=True)
+        els[1].set_image(1024, 1024, extent=(-2.0, 2.0, -2.0, 2.0))
+        w.update(elements=els, sensor=els[1], source=("disk", 5.0, -10.0), wavelengths=None, rays=10 ** 8,
+                 desc="C1 singlet + sensor, 4 rows, 1024x1024 image")
+    elif name == "c4":
+        els = scenes.c4_camera_lens(ns)
+        els[4].set_image(2160, 3840)
+        w.update(elements=els, sensor=els[4], source=("disk", 9.0, -10.0), wavelengths=None, rays=10 ** 8,
+                 desc="C4 doublet + stop + triplet + singlet + 4K sensor, 17 rows")
+    elif name == "c5":
+        els = scenes.c5_nonsequential(ns)
+        els[4].set_image(512, 512)
+        w.update(elements=els, sensor=els[4], source=("disk", 10.0, -5.0), wavelengths=None, rays=10 ** 8,
+                 nonseq=True, nbounces=8, desc="C5 non-sequential mirror/lens/box/stop/sensor, 12 rows, 8 bounces")
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return w
+
+
+def synth_bundle(w, n, device, seed):
+    """CollimatedDisk-style synthetic bundle (rays/bundle.py:40-56 sampling rule), generated on `device`."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    _kind, radius, z = w["source"]
+    th = torch.rand(n, device=device, generator=g) * (2 * np.pi)
+    r = torch.sqrt(torch.rand(n, device=device, generator=g)) * radius
+    pos = torch.stack([r * torch.cos(th), r * torch.sin(th), torch.full_like(r, z)], 1).contiguous()
+    del th, r
+    dirs = torch.zeros_like(pos)
+    dirs[:, 2] = 1.0
+    inten = torch.ones(n, device=device)
+    wav = None
+    if w["wavelengths"] is not None:
+        lam = torch.tensor(w["wavelengths"], device=device)
+        wav = lam[torch.arange(n, device=device) % len(w["wavelengths"])].contiguous()
+    return pos, dirs, inten, wav
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.proc, self.path = None, None
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            sel = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+        except Exception:
+            sel = str(device_index)
+        self.sel = sel
+
+    def start(self):
+        fd, self.path = tempfile.mkstemp(suffix=".csv")
+        os.close(fd)
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", self.sel, f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, parts[3:7]):
+                if v == "Active":
+                    reasons.add(nme)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle (port of the reference's algorithm) on a bounded sample
+# ---------------------------------------------------------------------------------------------
+def cpu_port_time(w, n_sample, repeats=1, threads=None):
+    """Seconds for one forward trace of n_sample rays by oracle/trace_oracle.py on the host cores."""
+    import raytracetorch_b200 as rtt
+    from oracle import trace_oracle as O          # checker / baseline only; never on the product path
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    els = w["elements"]
+    tab = rtt.compile_elements([e.cpu() for e in els], dispersion=w["dispersion"])
+    pos, dirs, inten, wav = synth_bundle(w, n_sample, "cpu", 1234)
+    kw = dict(wavelength=wav, lut=tab.lut, lut_w=tab.lut_wavelengths) if tab.lut is not None else {}
+
+    def run():
+        with torch.no_grad():
+            if w["nonseq"]:
+                return O.trace_nonsequential(tab.f, tab.i_host, pos, dirs, inten, w["nbounces"], **kw)
+            return O.trace_sequential(tab.f, tab.i_host, pos, dirs, inten, **kw)
+
+    small = slice(0, min(n_sample, 20000))
+    with torch.no_grad():       # warm-up on a slice (allocator, thread pool)
+        (O.trace_nonsequential(tab.f, tab.i_host, pos[small], dirs[small], inten[small], w["nbounces"])
+         if w["nonseq"] else O.trace_sequential(tab.f, tab.i_host, pos[small], dirs[small], inten[small]))
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        run()
+        best = min(best, time.perf_counter() - t0)
+    return best, tab.n_rows, threads
+
+
+def units_per_ray(w, n_rows):
+    """Interactions counted per ray: every row is tested once per sequential trace; the
+    non-sequential kernel tests every row at every executed bounce (counted by the caller)."""
+    return n_rows
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = build_workload(args.workload, "cpu")
+    n_sample = args.cpu_rays
+    times = []
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_port_time(w, n_sample)
+    rows = threads = None
+    for _ in range(args.steps):
+        t, rows, threads = cpu_port_time(w, n_sample)
+        times.append(t)
+    ms = 1e3 * float(np.mean(times))
+    per_ray = rows * (w["nbounces"] if w["nonseq"] else 1)
+    value = n_sample * per_ray / (ms / 1e3)
+    line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=dict(workload=w["desc"], rays_per_step=n_sample, rows=rows),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind="port",
+                                  sample=f"{n_sample} rays of the {args.workload} bundle per step, eager torch on "
+                                         f"{threads} host threads (oracle/trace_oracle.py restates the reference's "
+                                         f"algorithm; the Python reference itself cannot travel to the GPU box)"),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import raytracetorch_b200 as rtt
+    from raytracetorch_b200 import _cabi, dist as rdist, roofline as rf
+    import torch.distributed as tdist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; this package has no CPU path "
+                         "(use --impl reference for the CPU baseline)")
+    rank, world, local = rdist.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _cabi.load()
+    w = build_workload(args.workload, dev)
+    n = int(args.rays or w["rays"])
+    if w["nonseq"]:
+        scene = rtt.scene.Scene()
+        for e in w["elements"]:
+            scene.add_element(e)
+        scene.Nbounces = w["nbounces"]
+    else:
+        scene = rtt.scene.SequentialScene(w["elements"])
+    scene.set_dispersion(w["dispersion"])
+    scene = scene.to(dev)
+    scene.record_hits = False
+    table = scene.table()
+    S = table.n_rows
+    pos, dirs, inten, wav = synth_bundle(w, n, dev, 1000 + rank)
+    cfg = rtt.ops.sensor_cfg_of(table)
+    img_numel = sum(int(cfg[k]) * int(cfg[k + 1]) * int(cfg[k + 2]) for k in range(0, len(cfg), rtt.ops.SENSOR_CFG))
+
+    def fwd_step():
+        if w["nonseq"]:
+            out = rtt.ops.trace_nonsequential(table, pos, dirs, inten, w["nbounces"], wav, want_record=False,
+                                              sensor_cfg=cfg)
+        else:
+            out = rtt.ops.trace_sequential(table, pos, dirs, inten, wav, want_record=False, sensor_cfg=cfg)
+        if world > 1:
+            red = rdist.FlatReducer()
+            red.extend(out["images"])
+            red.reduce()
+        return out
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up -------------------------------------------------------------------------------
+    out = None
+    for _ in range(max(args.warmup, 1)):
+        out = fwd_step()
+    torch.cuda.synchronize()
+    # interactions actually counted per ray
+    if w["nonseq"]:
+        bounces = float(out["n_hits"].float().mean().item())
+        tests_per_ray = S * min(bounces + 1.0, w["nbounces"])   # the bounce that finds no hit also tests every row
+        hit_frac = None
+    else:
+        tests_per_ray = float(S)
+        hm = out["hitmask"]
+        hit_frac = [float(((hm >> r) & 1).float().mean().item()) for r in range(S)]
+    alive = float((out["intensity"] > 0).float().mean().item())
+    del out
+
+    # ---- timed: K forward steps, device-resident inputs -------------------------------------------
+    sampler = ClockSampler(local)
+    launches0 = lib.launch_count()
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        fwd_step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = lib.launch_count() - launches0
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    value = world * n * tests_per_ray / (ms_step / 1e3)
+
+    # ---- dominant kernel alone (per-launch CUDA events on the launch stream) -----------------------
+    req_mode = None
+    kt = []
+    for _ in range(args.steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        images = torch.zeros(img_numel, dtype=torch.float32, device=dev)
+        a.record()
+        if w["nonseq"]:
+            torch.ops.rtt_b200.trace_nonseq_fwd(pos, dirs, inten, wav, table.f, table.i, table.lut,
+                                                table.lut_wavelengths, cfg, False, w["nbounces"],
+                                                rtt.ops._default_mode_nonseq)
+        else:
+            torch.ops.rtt_b200.trace_seq_fwd(pos, dirs, inten, wav, table.f, table.i, table.lut,
+                                             table.lut_wavelengths, cfg, False, rtt.ops.get_default_mode())
+        b.record()
+        torch.cuda.synchronize()
+        kt.append(a.elapsed_time(b))
+        del images
+    k_ms = float(np.median(kt))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    if w["nonseq"]:
+        bytes_per_ray = 28 + 28 + w["nbounces"] + 1
+        flops_per_ray = None
+    else:
+        bytes_per_ray = rf.sequential_bytes_per_ray(wavelength=wav is not None, hitmask=True)
+        tf_host, ti_host = table.f.detach().cpu().tolist(), table.i_host
+        flops_per_ray = rf.sequential_flops_per_ray(tf_host, ti_host, hit_frac)
+    achieved = n * bytes_per_ray / (k_ms / 1e3) / 1e9
+    roof = dict(bound="hbm", achieved=achieved, peak=hbm_peak, unit="GB/s", frac=achieved / hbm_peak, traffic=None,
+                kernel="k_trace_nonseq_fwd" if w["nonseq"] else "k_trace_seq_fwd", kernel_ms=k_ms,
+                bytes_per_ray=bytes_per_ray, peak_source=peak_src)
+    props = torch.cuda.get_device_properties(dev)
+    if flops_per_ray is not None:
+        clk = clocks["sm_mhz"] or float(peaks.get("sm_max_mhz", 1965.0))
+        pk_nom = rf.fp32_peak_tflops(props.multi_processor_count, float(peaks.get("sm_max_mhz", 1965.0)))
+        pk_run = rf.fp32_peak_tflops(props.multi_processor_count, clk)
+        ach = n * flops_per_ray / (k_ms / 1e3) / 1e12
+        roof["fp32"] = dict(achieved=ach, unit="TFLOP/s", flops_per_ray=flops_per_ray, peak_nominal=pk_nom,
+                            frac_nominal=ach / pk_nom, peak_at_run_clock=pk_run, frac_at_run_clock=ach / pk_run,
+                            note="algorithmic FLOPs (raytracetorch_b200/roofline.py), FMA = 2; peak = SMs x 128 x 2 x clock")
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = roof["kernel"] + ":" + args.workload
+        if key in prof and int(prof[key].get("rays", 0)) > 0:
+            roof["traffic"] = prof[key]["dram_bytes"] / prof[key]["rays"] * n
+            roof["traffic_source"] = prof[key].get("source")
+    except Exception:
+        pass
+
+    # ---- forward + adjoint (optimisation step: loss on the final rays, grads to the lens parameters) ----
+    fb = None
+    if not w["nonseq"] and not args.no_bwd:
+        for p in scene.parameters():
+            p.requires_grad_(False)
+        trainable = []
+        for el in w["elements"]:
+            sh = el.shape
+            for s in getattr(sh, "surfaces", []):
+                if hasattr(s, "c") and isinstance(s.c, torch.nn.Parameter):
+                    s.c.requires_grad_(True)
+                    trainable.append(s.c)
+        opt_params = trainable
+
+        def fwd_bwd_step():
+            for p in opt_params:
+                p.grad = None
+            tab = scene.table()
+            o = rtt.ops.trace_sequential(tab, pos, dirs, inten, wav, want_record=False, sensor_cfg=[])
+            loss = (o["intensity"] * (o["pos"][:, 0] ** 2 + o["pos"][:, 1] ** 2)).sum()
+            loss.backward()
+            if world > 1:
+                red = rdist.FlatReducer()
+                red.extend([p.grad for p in opt_params])
+                red.reduce()
+            return loss
+
+        n_fb = n
+        for _ in range(max(args.warmup, 1)):
+            fwd_bwd_step()
+        barrier()
+        l0 = lib.launch_count()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            fwd_bwd_step()
+        f1.record()
+        barrier()
+        fb_ms = max_over_ranks(f0.elapsed_time(f1) / args.steps)
+        fb = dict(value=world * n_fb * S / (fb_ms / 1e3), unit=UNIT, ms_per_step=fb_ms,
+                  launches=lib.launch_count() - l0,
+                  note="trace forward + loss (torch elementwise) + hand-written adjoint kernel + table->Parameter "
+                       "autograd; interactions counted once per ray and row")
+        for p in opt_params:
+            p.requires_grad_(False)
+            p.grad = None
+
+    # ---- end to end through the public API with host buffers --------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = [t.cpu().pin_memory() for t in (pos, dirs, inten)] + ([wav.cpu().pin_memory()] if wav is not None else [])
+        h2d = sum(t.numel() * t.element_size() for t in host)
+        img_host = torch.empty(img_numel, dtype=torch.float32).pin_memory()
+        ids = torch.zeros(n, dtype=torch.int8, device=dev)
+        sensor = w["sensor"]
+
+        def e2e_step():
+            dv = [t.to(dev, non_blocking=True) for t in host]
+            rays = rtt.rays.Rays._wrap(pos=dv[0], dir=dv[1], intensity=dv[2], id=ids,
+                                       wavelength=dv[3] if len(dv) > 3 else dv[2])
+            sensor.reset()
+            if w["nonseq"]:
+                scene.rays = rays
+                scene.simulate()
+            else:
+                scene.simulate(rays)
+            img = sensor.image
+            if world > 1:
+                tdist.all_reduce(img)
+            img_host.copy_(img.reshape(-1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        del pos, dirs, inten
+        torch.cuda.empty_cache()
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        g1.record()
+        barrier()
+        e_ms = max_over_ranks(max(g0.elapsed_time(g1), 1e3 * (time.perf_counter() - t0)) / args.e2e_steps)
+        e2e = dict(value=world * n * tests_per_ray / (e_ms / 1e3), unit=UNIT, h2d_bytes_per_step=h2d,
+                   d2h_bytes_per_step=img_numel * 4, ms_per_step=e_ms, steps=args.e2e_steps,
+                   api="SequentialScene.simulate(rays)" if not w["nonseq"] else "Scene.simulate()")
+
+    # ---- CPU baseline on rank 0, N=1 only --------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        t, rows, threads = cpu_port_time(w, args.cpu_rays)
+        per_ray = rows * (w["nbounces"] if w["nonseq"] else 1)
+        cpu = dict(value=args.cpu_rays * per_ray / t, unit=UNIT, cores=threads, kind="port",
+                   sample=f"one forward trace of {args.cpu_rays} rays of the same bundle ({t:.1f} s), eager torch "
+                          f"oracle on {threads} host threads")
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                    data="synthetic",
+                    config=dict(workload=w["desc"], rays_per_gpu=n, rows=S, tests_per_ray=tests_per_ray,
+                                alive_fraction=alive, l2="inputs larger than L2 (>= 1 GB per array)",
+                                mode="FAST (FMA contraction)" if not w["nonseq"] else "EXACT (reference rounding)",
+                                collective="all_reduce(sensor image) per step" if world > 1 else "none"),
+                    clocks=clocks, gpu_launches=launches, roofline=roof)
+        if fb:
+            line["fwd_bwd"] = fb
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        tdist.barrier()
+        tdist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4", "c5"])
+    ap.add_argument("--rays", type=float, default=0, help="rays per GPU (default: the workload's BASELINE size)")
+    ap.add_argument("--cpu-rays", type=int, default=2_000_000, help="rays of the CPU sample")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-bwd", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.rays = int(args.rays)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

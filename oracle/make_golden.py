@@ -127,14 +127,7 @@ def gen_forward_case(ns, name):
     return data
 
 
-GRAD_CASES = {
-    # name: (builder, kwargs, bundle spec) — sequential scenes with trainable parameters
-    "grad_c3_singlet": (scenes.c1_singlet, {"physical": True, "grads": True}, ("coll", 5.0, -10.0, None)),
-    "grad_c3_singlet_ref_order": (scenes.c1_singlet, {"grads": True}, ("coll", 5.0, -10.0, None)),
-    "grad_c2_cylindrical": (scenes.c2_cylindrical, {"grads": True}, ("coll", 8.0, -10.0, [0.01, 0.02, 0.0])),
-    "grad_c4_camera_lens": (scenes.c4_camera_lens, {"grads": True}, ("coll", 7.0, -10.0, [0.02, 0.03, 0.0])),
-    "grad_x2_tilted": (scenes.x2_tilted_lenses, {"grads": True}, ("coll", 7.0, -12.0, [0.02, 0.03, 0.0])),
-}
+GRAD_CASES = scenes.GRAD_CASES
 
 
 def golden_loss(pos, dir_, intensity):

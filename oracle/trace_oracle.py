@@ -50,6 +50,7 @@ from raytracetorch_b200 import codes as C
 INF = float("inf")
 EPS_T = 1e-6      # geom/primitives.py:6
 EPS_S = 1e-6      # Surface.epsilon, geom/primitives.py:21
+EPS_HALF = 1e-6   # HalfSphere/HalfCyl bound slack (geom/bounded.py:127,174 use intersectEpsilon too)
 
 
 # torch's CPU sqrt goes through MKL VML (high-accuracy mode: < 1 ulp, NOT correctly rounded), so
@@ -148,7 +149,7 @@ def _surface_in_bounds(row: Row, h):
         v = h[:, 0] * sb[3] + h[:, 1] * sb[2]
         return ((u / sb[0]) ** 2 + (v / sb[1]) ** 2) <= 1.0
     if row.bound in (C.BOUND_HALF, C.BOUND_HALF_DISK):   # geom/bounded.py:123-127, 171-174
-        keep = torch.abs(h[:, 2] * row.c.detach()) < 1 + EPS_T
+        keep = torch.abs(h[:, 2] * row.c.detach()) < 1 + EPS_HALF
         if row.bound == C.BOUND_HALF_DISK:        # geom/bounded.py:151-159
             keep = keep & (h[:, 0] ** 2 + h[:, 1] ** 2 <= sb[0] ** 2)
         return keep

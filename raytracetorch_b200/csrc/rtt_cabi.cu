@@ -105,10 +105,10 @@ int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_
                       const rtt_table_t* table, const rtt_sensor_t* sensors, int32_t n_sensors,
                       int64_t n, int32_t mode, void* stream) {
     if (int e = check_table(table)) return e;
+    if (n == 0) return RTT_OK;   /* empty bundle: nothing to do, pointers may be NULL */
     if (n < 0 || !in_pos || !in_dir || !in_intensity || !out_pos || !out_dir || !out_intensity) return RTT_E_ARG;
     if (table->n_lut > 0 && !in_wavelength) return RTT_E_ARG;
     if (!have_device()) return RTT_E_NO_DEVICE;
-    if (n == 0) return RTT_OK;
     auto st = (cudaStream_t)stream;
 #define RTT_BODY(NS)                                                                                   \
     {                                                                                                  \
@@ -134,11 +134,11 @@ int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float* in_
                       const rtt_table_t* table, int32_t n_sensors,
                       int64_t n, int32_t mode, void* stream) {
     if (int e = check_table(table)) return e;
+    if (n == 0) return RTT_OK;   /* empty bundle: nothing to do, pointers may be NULL */
     if (n < 0 || !in_pos || !in_dir || !in_intensity || !hitmask) return RTT_E_ARG;
     if (table->n_lut > 0 && !in_wavelength) return RTT_E_ARG;
     if (n_sensors < 0 || n_sensors > RTT_MAX_SENSORS) return RTT_E_SENSOR;
     if (!have_device()) return RTT_E_NO_DEVICE;
-    if (n == 0) return RTT_OK;
     auto st = (cudaStream_t)stream;
 #define RTT_BODY(NS)                                                                                   \
     {                                                                                                  \
@@ -167,12 +167,12 @@ int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* 
                          const rtt_table_t* table, const rtt_sensor_t* sensors, int32_t n_sensors,
                          int32_t nbounces, int64_t n, int32_t mode, void* stream) {
     if (int e = check_table(table)) return e;
+    if (n == 0) return RTT_OK;   /* empty bundle: nothing to do, pointers may be NULL */
     if (n < 0 || !in_pos || !in_dir || !in_intensity || !out_pos || !out_dir || !out_intensity) return RTT_E_ARG;
     if (nbounces < 0 || (hit_seq && nbounces > RTT_MAX_BOUNCES)) return RTT_E_ARG;
     if (table->n_rows > 255) return RTT_E_ROWS;
     if (table->n_lut > 0 && !in_wavelength) return RTT_E_ARG;
     if (!have_device()) return RTT_E_NO_DEVICE;
-    if (n == 0) return RTT_OK;
     auto st = (cudaStream_t)stream;
 #define RTT_BODY(NS)                                                                                   \
     {                                                                                                  \
@@ -196,11 +196,11 @@ int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float* 
                          float* g_table, float* g_lut,
                          const rtt_table_t* table, int64_t n, int32_t mode, void* stream) {
     if (int e = check_table(table)) return e;
+    if (n == 0) return RTT_OK;   /* empty bundle: nothing to do, pointers may be NULL */
     if (n < 0 || !in_pos || !in_dir || !in_intensity || !hit_seq) return RTT_E_ARG;
     if (nbounces < 0 || nbounces > RTT_MAX_BOUNCES) return RTT_E_ARG;
     if (table->n_lut > 0 && !in_wavelength) return RTT_E_ARG;
     if (!have_device()) return RTT_E_NO_DEVICE;
-    if (n == 0) return RTT_OK;
     auto st = (cudaStream_t)stream;
 #define RTT_BODY(NS)                                                                                   \
     {                                                                                                  \
@@ -222,10 +222,10 @@ int rtt_intersect_test(const float* in_pos, const float* in_dir, float* t_out,
                        const rtt_table_t* table, int32_t row0, int32_t k,
                        int64_t n, int32_t mode, void* stream) {
     if (int e = check_table(table)) return e;
+    if (n == 0) return RTT_OK;   /* empty bundle: nothing to do, pointers may be NULL */
     if (n < 0 || !in_pos || !in_dir || !t_out) return RTT_E_ARG;
     if (row0 < 0 || k < 1 || row0 + k > table->n_rows) return RTT_E_ROWS;
     if (!have_device()) return RTT_E_NO_DEVICE;
-    if (n == 0) return RTT_OK;
     auto st = (cudaStream_t)stream;
 #define RTT_BODY(NS)                                                                                   \
     {                                                                                                  \
@@ -245,11 +245,11 @@ int rtt_surface_step_fwd(const float* in_pos, const float* in_dir, const float* 
                          const rtt_table_t* table, int32_t row,
                          int64_t n, int32_t mode, void* stream) {
     if (int e = check_table(table)) return e;
+    if (n == 0) return RTT_OK;   /* empty bundle: nothing to do, pointers may be NULL */
     if (n < 0 || !in_pos || !in_dir || !new_pos || !new_dir || !mod) return RTT_E_ARG;
     if (row < 0 || row >= table->n_rows) return RTT_E_ROWS;
     if (table->n_lut > 0 && !in_wavelength) return RTT_E_ARG;
     if (!have_device()) return RTT_E_NO_DEVICE;
-    if (n == 0) return RTT_OK;
     auto st = (cudaStream_t)stream;
 #define RTT_BODY(NS)                                                                                   \
     {                                                                                                  \
@@ -272,11 +272,11 @@ int rtt_surface_step_bwd(const float* in_pos, const float* in_dir, const float* 
                          const rtt_table_t* table, int32_t row,
                          int64_t n, int32_t mode, void* stream) {
     if (int e = check_table(table)) return e;
+    if (n == 0) return RTT_OK;   /* empty bundle: nothing to do, pointers may be NULL */
     if (n < 0 || !in_pos || !in_dir) return RTT_E_ARG;
     if (row < 0 || row >= table->n_rows) return RTT_E_ROWS;
     if (table->n_lut > 0 && !in_wavelength) return RTT_E_ARG;
     if (!have_device()) return RTT_E_NO_DEVICE;
-    if (n == 0) return RTT_OK;
     auto st = (cudaStream_t)stream;
 #define RTT_BODY(NS)                                                                                   \
     {                                                                                                  \

@@ -24,6 +24,21 @@
 
 namespace rtt {
 
+// Separately rounded multiply / subtract that the compiler may NOT contract into an FMA, in
+// either variant.  Used for the discriminant b*b - 4ac only: when a ray starts ON a surface
+// (every non-sequential bounce does) c is O(ulp) and the reference's separately rounded
+// b*b - 4ac collapses to b*b exactly, which makes the near root exactly 0 and the t > 1e-6 rule
+// (geom/primitives.py:32) reject the self-intersection.  An FMA keeps the tiny -4ac term, the
+// near root becomes ~c/b != 0, and ~20 % of otherwise stable rays re-hit the surface they are
+// leaving (measured on the c5 fixture).  Keeping this one expression un-fused costs 1 FLOP.
+#if defined(__CUDA_ARCH__)
+RTT_HD float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+RTT_HD float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+#else
+inline float mul_rn(float a, float b) { volatile float m = a * b; return m; }
+inline float sub_rn(float a, float b) { volatile float m = a - b; return m; }
+#endif
+
 // ---- row record as staged in shared memory ------------------------------------------------
 // f[0..40] is the caller's table row; f[41..47] and i[11] are derived once per block.
 enum {
@@ -51,7 +66,7 @@ RTT_HD V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
 // torch.sum(a*b, dim=1): products rounded, accumulated left to right
 RTT_HD float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 // p + t*d with t broadcast (geom/primitives.py:80-81)
-RTT_HD V3 along(V3 p, float t, V3 d) { return v3(p.x + t * d.x, p.y + t * d.y, p.z + t * d.z); }
+RTT_HD V3 along(V3 p, float t, V3 d) { return v3(p.x + mul_rn(t, d.x), p.y + mul_rn(t, d.y), p.z + mul_rn(t, d.z)); }
 
 RTT_HD float rtt_inf() { return INFINITY; }
 RTT_HD float rtt_nan() { return NAN; }
@@ -160,7 +175,7 @@ RTT_HD Roots solve_roots(const RowDev& R, V3 o, V3 d) {
         case RTT_SURF_SPHERE: {                                         // :155-184 (a == 1 assumed)
             const float b = 2.0f * dot(o, d);
             const float cc = dot(o, o) - R.f[D_R2];
-            const float disc = b * b - 4.0f * cc;
+            const float disc = sub_rn(mul_rn(b, b), mul_rn(4.0f, cc));
             const bool ok = disc >= 0.0f;
             const float sq = sqrtf(ok ? disc : 0.0f);
             q.t1 = ok ? (-b - sq) / 2.0f : inf;
@@ -172,7 +187,7 @@ RTT_HD Roots solve_roots(const RowDev& R, V3 o, V3 d) {
             const float A = d.x * d.x + d.y * d.y;
             const float B = 2.0f * (o.x * d.x + o.y * d.y);
             const float Cq = (o.x * o.x + o.y * o.y) - R.f[D_R2];
-            const float disc = B * B - 4.0f * A * Cq;
+            const float disc = sub_rn(mul_rn(B, B), mul_rn(mul_rn(4.0f, A), Cq));
             const bool ok = disc >= 0.0f;
             const float sq = sqrtf(fabsf(disc));
             q.t1 = ok ? (-B - sq) / (2.0f * A) : inf;
@@ -193,7 +208,7 @@ RTT_HD Roots solve_roots(const RowDev& R, V3 o, V3 d) {
                 B = (tc * (o.y * d.y) + (tc1k * o.z) * d.z) - 2.0f * d.z;
                 Cq = (c * (o.y * o.y) + c1k * (o.z * o.z)) - 2.0f * o.z;
             }
-            const float disc = B * B - (4.0f * A) * Cq;
+            const float disc = sub_rn(mul_rn(B, B), mul_rn(mul_rn(4.0f, A), Cq));
             const bool ok = disc >= 0.0f;
             const bool lin = fabsf(A) < 1e-6f;
             const float sq = sqrtf(fabsf(disc));

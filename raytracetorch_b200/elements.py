@@ -385,9 +385,10 @@ class Sensor(Element):
         if extent is None:
             s = self.shape
             if hasattr(s, "hx"):
-                extent = (-float(s.hx), float(s.hx), -float(s.hy), float(s.hy))
+                hx, hy = float(s.hx.detach()), float(s.hy.detach())
+                extent = (-hx, hx, -hy, hy)
             elif hasattr(s, "radius"):
-                r = float(s.radius)
+                r = float(s.radius.detach())
                 extent = (-r, r, -r, r)
             else:
                 raise ValueError("extent required for this sensor shape")

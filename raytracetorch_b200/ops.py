@@ -19,13 +19,21 @@ from . import _cabi, codes as C
 from .table import SurfaceTable, compile_elements
 
 MODE_FAST, MODE_EXACT = _cabi.MODE_FAST, _cabi.MODE_EXACT
+# Arithmetic defaults.  Sequential traces: FAST (FMA contraction; masks verified identical to
+# the reference on every fixture, points within 1e-5).  Non-sequential traces: EXACT — the
+# reference's t > 1e-6 self-intersection rule sits at the fp32 ulp of scene-scale coordinates,
+# so which surface a ray hits next depends on the reference's exact rounding sequence
+# (SURVEY 0.10); only arithmetic that rounds like the reference reproduces its hit sequences.
 _default_mode = MODE_FAST
+_default_mode_nonseq = MODE_EXACT
 
 
-def set_default_mode(mode: int):
-    """MODE_FAST (default) or MODE_EXACT (parity / validation: no FMA contraction)."""
-    global _default_mode
+def set_default_mode(mode: int, nonseq: Optional[int] = None):
+    """Set the arithmetic of the sequential/element ops (and, if given, of the non-sequential op)."""
+    global _default_mode, _default_mode_nonseq
     _default_mode = int(mode)
+    if nonseq is not None:
+        _default_mode_nonseq = int(nonseq)
 
 
 def get_default_mode() -> int:
@@ -461,7 +469,7 @@ def trace_nonsequential(table: SurfaceTable, pos, dir_, intensity, nbounces: int
     if not 0 <= nbounces <= C.MAX_BOUNCES:
         raise ValueError(f"nbounces must be in [0, {C.MAX_BOUNCES}]")
     cfg = sensor_cfg_of(table) if sensor_cfg is None else list(sensor_cfg)
-    mode = _default_mode if mode is None else mode
+    mode = _default_mode_nonseq if mode is None else mode
     opos, odir, oint, seq, nh, records, images = _TraceNonseq.apply(
         pos, dir_, intensity, wav, table.f, table.i, table.lut, table.lut_wavelengths, cfg, bool(want_record),
         int(nbounces), mode)

@@ -30,7 +30,8 @@ def build(variant: str = "exact") -> "HostSim":
     out = os.path.join(_BUILD, f"librtt_hostsim_{variant}.so")
     src = os.path.join(_HERE, "hostsim.cpp")
     core = os.path.join(_HERE, "..", "..", "raytracetorch_b200", "csrc", "rtt_core.cuh")
-    newest = max(os.path.getmtime(src), os.path.getmtime(core))
+    hdr = os.path.join(_HERE, "..", "..", "include", "rtt_b200.h")
+    newest = max(os.path.getmtime(src), os.path.getmtime(core), os.path.getmtime(hdr))
     if not os.path.exists(out) or os.path.getmtime(out) < newest:
         cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fno-fast-math", *_FLAGS[variant], src, "-o", out]
         subprocess.run(cmd, check=True)

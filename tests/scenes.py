@@ -145,6 +145,16 @@ CASES = {
 }
 
 
+GRAD_CASES = {
+    # name: (builder, kwargs, bundle spec) — sequential scenes with trainable parameters
+    "grad_c3_singlet": (c1_singlet, {"physical": True, "grads": True}, ("coll", 5.0, -10.0, None)),
+    "grad_c3_singlet_ref_order": (c1_singlet, {"grads": True}, ("coll", 5.0, -10.0, None)),
+    "grad_c2_cylindrical": (c2_cylindrical, {"grads": True}, ("coll", 8.0, -10.0, [0.01, 0.02, 0.0])),
+    "grad_c4_camera_lens": (c4_camera_lens, {"grads": True}, ("coll", 7.0, -10.0, [0.02, 0.03, 0.0])),
+    "grad_x2_tilted": (x2_tilted_lenses, {"grads": True}, ("coll", 7.0, -12.0, [0.02, 0.03, 0.0])),
+}
+
+
 def make_bundle(ns, spec, n, seed):
     if spec[0] == "coll":
         return bundle_collimated(ns, n, spec[1], spec[2], seed, tilt=spec[3])

@@ -1,0 +1,265 @@
+"""GPU tests of the drop-in Python API (Element / Scene / SequentialScene / Rays) — the calls a
+RayTraceTorch user makes — against the reference's golden fixtures and the oracle, plus
+size-independent properties at BASELINE sizes.  Everything here goes
+scene object -> torch.library op -> ctypes -> librtt_b200.so (CUDA)."""
+import numpy as np
+import pytest
+import torch
+
+import parity
+import scenes
+from oracle import trace_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda_rays(rtt, d, grads=False):
+    p, dd, inten = (t.cuda() for t in parity.inputs_t(d))
+    rays = rtt.rays.Rays._wrap(pos=p, dir=dd, intensity=inten,
+                               id=torch.zeros(p.shape[0], dtype=torch.int8, device="cuda"),
+                               wavelength=torch.zeros(p.shape[0], device="cuda"))
+    if grads:
+        for t in (rays.pos, rays.dir, rays.intensity):
+            t.requires_grad_(True)
+    return rays
+
+
+def _build(rtt_ns, name):
+    if name in scenes.CASES:
+        builder, kw, mode, _ = scenes.CASES[name]
+    else:
+        builder, kw, _ = scenes.GRAD_CASES[name]
+        mode = "seq"
+    return builder(rtt_ns, **kw), mode
+
+
+@pytest.mark.parametrize("name", parity.forward_names("seq"))
+def test_sequential_scene_simulate_matches_reference(rtt_ns, name):
+    import raytracetorch_b200 as rtt
+    d = parity.load(name)
+    els, _ = _build(rtt_ns, name)
+    scene = rtt.scene.SequentialScene(els).cuda()
+    rays = _cuda_rays(rtt, d)
+    out = scene.simulate(rays)
+    assert out is rays                                            # mutated in place, like the reference
+    parity.assert_close_noise_aware(out.pos.cpu().numpy(), out.dir.cpu().numpy(), out.intensity.cpu().numpy(), d, name)
+    # sensor hit lists: same hits, same order, weight = intensity before the sensor
+    sensors = [e for e in els if type(e).__name__ == "Sensor"]
+    if sensors and "f32_sensor0_loc" in d.files:
+        locs, w, ids = sensors[0].getHitsTensors()
+        assert locs.shape[0] == d["f32_sensor0_loc"].shape[0]
+        np.testing.assert_array_equal(w.cpu().numpy(), d["f32_sensor0_w"])
+        live = d["f32_sensor0_w"] > 0
+        e = parity.vec_rel(locs.cpu().numpy()[live], d["f32_sensor0_loc"][live])
+        noise = parity.vec_rel(d["f32_sensor0_loc"], d["f64_sensor0_loc"].astype(np.float32))[live] \
+            if d["f64_sensor0_loc"].shape == d["f32_sensor0_loc"].shape else np.zeros_like(e)
+        assert np.all(e <= np.maximum(parity.TOL_POINT, np.maximum(16 * noise, 2 * noise.max(initial=0.0))))
+
+
+@pytest.mark.parametrize("name", parity.golden_names(grads=True))
+def test_backward_through_autograd_function_matches_reference(rtt_ns, name):
+    """loss.backward() on the fused op = the reference's autograd: every trainable Parameter and the
+    input rays (tests/test_optimize_singlet.py:66-116 is this loop)."""
+    import raytracetorch_b200 as rtt
+    d = parity.load(name)
+    els, _ = _build(rtt_ns, name)
+    scene = rtt.scene.SequentialScene(els).cuda()
+    rays = _cuda_rays(rtt, d, grads=True)
+    leaf = (rays.pos, rays.dir, rays.intensity)
+    out = scene.simulate(rays)
+    loss = parity.golden_loss(out.pos, out.dir, out.intensity)
+    loss.backward()
+    assert abs(float(loss) - float(d["f32_loss"])) <= 1e-5 * abs(float(d["f32_loss"]))
+    for t, k in zip(leaf, ("g_pos", "g_dir", "g_intensity")):
+        assert parity.grad_rel(t.grad.cpu().numpy(), d["f32_" + k]) < parity.TOL_GRAD, k
+    params = dict(scene.named_parameters())
+    for k in [k[len("f32_gp::"):] for k in d.files if k.startswith("f32_gp::")]:
+        ref = d["f64_gp::" + k]
+        g = params[k].grad
+        g = np.zeros_like(ref) if g is None else g.cpu().numpy()
+        if np.linalg.norm(ref) == 0:
+            assert np.linalg.norm(g) == 0, k
+        else:
+            assert parity.grad_rel(g, ref) < parity.TOL_GRAD, (k, g, ref)
+
+
+@pytest.mark.parametrize("name", parity.forward_names("nonseq"))
+def test_nonsequential_scene_matches_reference_on_stable_rays(rtt_ns, name):
+    import raytracetorch_b200 as rtt
+    d = parity.load(name)
+    els, _ = _build(rtt_ns, name)
+    scene = rtt.scene.Scene()
+    for e in els:
+        scene.add_element(e)
+    scene = scene.cuda()
+    scene.Nbounces = int(d["nbounces"])
+    scene.rays = _cuda_rays(rtt, d)
+    scene.simulate()
+    seq = scene.last_trace["hit_seq"].cpu().numpy().astype(np.int64)
+    seq[seq == 255] = -1
+    stable = parity.stable_nonseq_rows(d) & parity.self_hit_free(d, torch.from_numpy(d["table_f"]), d["table_i"].tolist())
+    np.testing.assert_array_equal(seq[stable], d["f32_seq"][stable])
+    r = scene.rays
+    parity.assert_close_noise_aware(r.pos.cpu().numpy(), r.dir.cpu().numpy(), r.intensity.cpu().numpy(), d, name,
+                                    rows=stable)
+    # ray_cast: winners of the first bounce as (element, surface) ids
+    scene.rays = _cuda_rays(rtt, d)
+    hit_mask, we, ws = scene.ray_cast(scene.rays)
+    first = d["f32_seq"][:, 0]
+    np.testing.assert_array_equal(hit_mask.cpu().numpy(), first >= 0)
+    flat = torch.tensor(d["table_i"][:, 8:10])
+    sel = first >= 0
+    np.testing.assert_array_equal(we.cpu().numpy()[sel], flat[first[sel], 0].numpy())
+    np.testing.assert_array_equal(ws.cpu().numpy()[sel], flat[first[sel], 1].numpy())
+
+
+def test_element_forward_and_intersect_test_like_the_reference_scripts(rtt_ns):
+    """Direct lens(rays, surf_idx) calls and the projection loss of tests/test_optimize_singlet.py:80-106."""
+    import raytracetorch_b200 as rtt
+    d = parity.load("grad_c3_singlet")
+    els = scenes.c1_singlet(rtt_ns, physical=True, grads=True)
+    lens = els[0].cuda()
+    rays = _cuda_rays(rtt, d)
+    p1, d1, _ = lens(rays, 0)
+    rays.pos, rays.dir = p1, d1
+    p2, d2, _ = lens(rays, 1)
+    t = (100.0 - p2[:, 2]) / (d2[:, 2] + 1e-6)
+    x, y = p2[:, 0] + t * d2[:, 0], p2[:, 1] + t * d2[:, 1]
+    loss = (x ** 2 + y ** 2).mean()
+    loss.backward()
+    # oracle: same two element steps + same loss through torch autograd
+    els_o = scenes.c1_singlet(rtt_ns, physical=True, grads=True)
+    tab = rtt.compile_elements(els_o)
+    rows = O.make_rows(tab.f, tab.i_host)
+    p, dd, _ = parity.inputs_t(d)
+    h1, n1, *_ = O.element_step(rows, 0, p, dd)
+    h2, n2, *_ = O.element_step(rows, 1, h1, n1)
+    to = (100.0 - h2[:, 2]) / (n2[:, 2] + 1e-6)
+    lo = ((h2[:, 0] + to * n2[:, 0]) ** 2 + (h2[:, 1] + to * n2[:, 1]) ** 2).mean()
+    lo.backward()
+    assert abs(float(loss) - float(lo)) <= 1e-5 * abs(float(lo))
+    for k in (0, 1):
+        g = lens.shape.surfaces[k].c.grad.cpu().numpy()
+        go = els_o[0].shape.surfaces[k].c.grad.numpy()
+        assert parity.grad_rel(g, go) < parity.TOL_GRAD
+    tm = lens.intersectTest(_cuda_rays(rtt, d))
+    assert tm.shape == (d["in_pos"].shape[0], 3)
+    ref = torch.stack([O.intersect_row(rows, r, p, dd) for r in range(3)], 1).numpy()
+    np.testing.assert_array_equal(np.isfinite(tm.cpu().numpy()), np.isfinite(ref))
+
+
+def test_sensor_image_and_wavelength_channels(rtt_ns):
+    """C2: 3 wavelengths -> 3-channel image; equals the oracle's histogram of the reference hit list."""
+    import raytracetorch_b200 as rtt
+    n = 200_000
+    els = scenes.c2_cylindrical(rtt_ns)
+    disp = rtt.Dispersion(scenes.C2_WAVELENGTHS, {
+        els[0].ior_glass: [1.5 * s for s in scenes.C2_GLASS_SCALE],
+        els[1].ior_glass: [1.6 * s for s in scenes.C2_GLASS_SCALE]})
+    els[3].set_image(256, 256, channels=3)
+    scene = rtt.scene.SequentialScene(els)
+    scene.set_dispersion(disp)
+    scene = scene.cuda()
+    rays = scenes.make_bundle(rtt_ns, ("coll", 8.0, -10.0, None), n, 7)
+    wav = torch.tensor(scenes.C2_WAVELENGTHS)[torch.arange(n) % 3]
+    rays.wavelength = wav
+    cpu = (rays.pos.clone(), rays.dir.clone(), rays.intensity.clone())
+    rays = rays.to("cuda")
+    scene.simulate(rays)
+    img = els[3].image.cpu().numpy()
+    assert img.shape == (3, 256, 256)
+    tab = rtt.compile_elements([e.cpu() for e in els], dispersion=disp)
+    o = O.trace_sequential(tab.f, tab.i_host, *cpu, wavelength=wav, lut=tab.lut, lut_w=tab.lut_wavelengths)
+    mask, hl, w = o["sensor"][0]
+    ref = O.sensor_image(hl, w, els[3].image_spec, channel=(torch.arange(n) % 3)[mask]).numpy()
+    assert ref.sum() > 0.3 * n
+    assert parity.rel_l1(img, ref) <= parity.TOL_IMAGE_L1
+    assert abs(img.sum() - ref.sum()) <= 1e-6 * ref.sum()
+
+
+@pytest.mark.parametrize("n", [10 ** 6, 10 ** 8])
+def test_full_size_properties_sequential(rtt_ns, n):
+    """BASELINE sizes (C1: 1e6, C2: 1e8 rays): properties that need no CPU run of the same size —
+    chunking invariance (rays are independent), determinism, image = checksum of the hit list,
+    and a random sub-sample traced by the oracle."""
+    import raytracetorch_b200 as rtt
+    els = scenes.c2_cylindrical(rtt_ns)
+    els[3].set_image(1024, 1024)
+    scene = rtt.scene.SequentialScene(els).cuda()
+    scene.record_hits = False
+    g = torch.Generator(device="cuda").manual_seed(11)
+    th = torch.rand(n, device="cuda", generator=g) * (2 * np.pi)
+    r = torch.sqrt(torch.rand(n, device="cuda", generator=g)) * 8.0
+    pos = torch.stack([r * torch.cos(th), r * torch.sin(th), torch.full_like(r, -10.0)], 1)
+    del th, r
+    dirs = torch.zeros_like(pos)
+    dirs[:, 2] = 1.0
+    inten = torch.ones(n, device="cuda")
+    tab = scene.table()
+    out = rtt.ops.trace_sequential(tab, pos, dirs, inten, want_record=False)
+    img = out["images"][0]
+    # (1) determinism of per-ray outputs
+    out2 = rtt.ops.trace_sequential(tab, pos, dirs, inten, want_record=False)
+    assert torch.equal(out["pos"], out2["pos"]) and torch.equal(out["hitmask"], out2["hitmask"])
+    # (2) chunking invariance: tracing two halves == tracing the whole bundle
+    h = n // 2
+    a = rtt.ops.trace_sequential(tab, pos[:h], dirs[:h], inten[:h], want_record=False)
+    b = rtt.ops.trace_sequential(tab, pos[h:], dirs[h:], inten[h:], want_record=False)
+    assert torch.equal(torch.cat([a["pos"], b["pos"]]), out["pos"])
+    assert torch.equal(torch.cat([a["intensity"], b["intensity"]]), out["intensity"])
+    img_halves = a["images"][0] + b["images"][0]
+    assert float((img_halves - img).abs().sum() / img.sum()) < parity.TOL_IMAGE_L1
+    del a, b, out2
+    # (3) checksum: image total == total weight of rays that hit the sensor inside the extent
+    srow = tab.sensor_rows[0]
+    hit = ((out["hitmask"] >> srow) & 1).bool()
+    inside = hit & (out["pos"][:, 0].abs() < 15.0) & (out["pos"][:, 1].abs() < 15.0)
+    total = float(inten[inside].double().sum())
+    assert abs(float(img.double().sum()) - total) <= 1e-4 * total
+    # (4) oracle on a random sub-sample
+    idx = torch.randint(0, n, (20000,), device="cuda", generator=g)
+    tabc = rtt.compile_elements([e.cpu() for e in scenes.c2_cylindrical(rtt_ns)])
+    o = O.trace_sequential(tabc.f, tabc.i_host, pos[idx].cpu(), dirs[idx].cpu(), inten[idx].cpu())
+    np.testing.assert_array_equal(out["intensity"][idx].cpu().numpy(), o["intensity"].numpy())
+    live = o["intensity"].numpy() > 0
+    assert parity.vec_rel(out["pos"][idx].cpu().numpy()[live], o["pos"].numpy()[live]).max() <= parity.TOL_POINT
+    S = tabc.n_rows
+    np.testing.assert_array_equal(parity.mask_bits(out["hitmask"][idx].cpu().numpy().view(np.uint64), S),
+                                  o["hit"].numpy())
+
+
+def test_full_size_nonsequential_properties(rtt_ns):
+    """C5 at 2e7 rays: determinism, chunking invariance, first-bounce winners vs the oracle."""
+    import raytracetorch_b200 as rtt
+    n = 20_000_000
+    els = scenes.c5_nonsequential(rtt_ns)
+    scene = rtt.scene.Scene()
+    for e in els:
+        scene.add_element(e)
+    scene = scene.cuda()
+    tab = scene.table()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    th = torch.rand(n, device="cuda", generator=g) * (2 * np.pi)
+    r = torch.sqrt(torch.rand(n, device="cuda", generator=g)) * 10.0
+    pos = torch.stack([r * torch.cos(th), r * torch.sin(th), torch.full_like(r, -5.0)], 1)
+    dirs = torch.zeros_like(pos)
+    dirs[:, 2] = 1.0
+    inten = torch.ones(n, device="cuda")
+    out = rtt.ops.trace_nonsequential(tab, pos, dirs, inten, 8, want_record=False)
+    out2 = rtt.ops.trace_nonsequential(tab, pos, dirs, inten, 8, want_record=False)
+    assert torch.equal(out["hit_seq"], out2["hit_seq"]) and torch.equal(out["pos"], out2["pos"])
+    h = n // 3
+    a = rtt.ops.trace_nonsequential(tab, pos[:h], dirs[:h], inten[:h], 8, want_record=False)
+    assert torch.equal(a["hit_seq"], out["hit_seq"][:h]) and torch.equal(a["pos"], out["pos"][:h])
+    idx = torch.randint(0, n, (5000,), device="cuda", generator=g)
+    tabc = rtt.compile_elements([e.cpu() for e in scenes.c5_nonsequential(rtt_ns)])
+    O.IEEE_SQRT = True
+    try:
+        o = O.trace_nonsequential(tabc.f, tabc.i_host, pos[idx].cpu(), dirs[idx].cpu(), inten[idx].cpu(), 1)
+    finally:
+        O.IEEE_SQRT = False
+    first = out["hit_seq"][idx, 0].cpu().numpy().astype(np.int64)
+    first[first == 255] = -1
+    np.testing.assert_array_equal(first, o["seq"].numpy()[:, 0])
+    nh = out["n_hits"].cpu().numpy()
+    assert nh.max() <= 8 and (out["hit_seq"].cpu().numpy() != 255).sum(1).tolist()[:1000] == nh.tolist()[:1000]

@@ -1,0 +1,415 @@
+"""Kernel parity: every entry point of include/rtt_b200.h against the CPU oracle and the
+reference's golden fixtures.
+
+Each test runs on two back-ends (see conftest.py):
+  [host] tests/hostsim compiles the product's per-ray source (csrc/rtt_core.cuh — the exact code
+         the CUDA kernels inline) with g++ behind the same C signatures, so the CPU suite checks
+         forward AND adjoint arithmetic before any GPU time is spent;
+  [gpu]  the real CUDA kernels of librtt_b200.so through the C ABI (`-m gpu`, B200 box).
+"""
+import numpy as np
+import pytest
+import torch
+
+import parity
+import scenes
+from oracle import trace_oracle as O
+
+SEQ = parity.forward_names("seq")
+NONSEQ = parity.forward_names("nonseq")
+
+
+@pytest.fixture()
+def ieee_oracle():
+    """Oracle with a correctly rounded sqrt (what every IEEE device computes; MKL's is not)."""
+    O.IEEE_SQRT = True
+    yield O
+    O.IEEE_SQRT = False
+
+
+def _oracle_seq(d, Om=O, **kw):
+    p, dd, inten = parity.inputs_t(d)
+    return Om.trace_sequential(torch.from_numpy(d["table_f"]), d["table_i"].tolist(), p, dd, inten, **kw)
+
+
+# ---------------------------------------------------------------------------------------------
+# sequential forward
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", SEQ)
+def test_seq_exact_is_bit_identical_to_oracle(run_exact, ieee_oracle, name):
+    d = parity.load(name)
+    o = _oracle_seq(d, ieee_oracle)
+    h = run_exact.trace_seq(d["table_f"], d["table_i"], d["in_pos"], d["in_dir"], d["in_intensity"],
+                                sensor_specs=[None])
+    for k in ("pos", "dir", "intensity"):
+        np.testing.assert_array_equal(h[k], o[k].numpy(), err_msg=f"{name}:{k}")
+    S = d["table_f"].shape[0]
+    np.testing.assert_array_equal(parity.mask_bits(h["hitmask"], S), o["hit"].numpy())
+    if 0 in o["sensor"]:
+        mask, hl, w = o["sensor"][0]
+        rec = h["sensors"][0][0]
+        np.testing.assert_array_equal(rec[mask.numpy(), :3], hl.numpy())
+        np.testing.assert_array_equal(rec[mask.numpy(), 3], w.numpy())
+
+
+@pytest.mark.parametrize("variant", ["exact", "fast"])
+@pytest.mark.parametrize("name", SEQ)
+def test_seq_matches_reference_within_tolerance(runner_of, name, variant):
+    d = parity.load(name)
+    h = runner_of(variant).trace_seq(d["table_f"], d["table_i"], d["in_pos"], d["in_dir"], d["in_intensity"])
+    _assert_close_noise_aware(h, d, name)
+
+
+def _assert_close_noise_aware(h, d, name, rows=None):
+    parity.assert_close_noise_aware(h["pos"], h["dir"], h["intensity"], d, name, rows)
+
+
+# ---------------------------------------------------------------------------------------------
+# non-sequential forward
+# ---------------------------------------------------------------------------------------------
+def _self_hit_free(d, tf, ti):
+    return parity.self_hit_free(d, tf, ti)
+
+
+@pytest.mark.parametrize("name", NONSEQ)
+def test_nonseq_exact_matches_oracle(run_exact, ieee_oracle, name):
+    d = parity.load(name)
+    tf, ti = torch.from_numpy(d["table_f"]), d["table_i"].tolist()
+    nb = int(d["nbounces"])
+    p, dd, inten = parity.inputs_t(d)
+    o = ieee_oracle.trace_nonsequential(tf, ti, p, dd, inten, nb)
+    h = run_exact.trace_nonseq(d["table_f"], d["table_i"], d["in_pos"], d["in_dir"], d["in_intensity"], nb)
+    hseq = h["seq"].astype(np.int64)
+    hseq[hseq == 255] = -1
+    clean = _self_hit_free(d, tf, ti)
+    assert clean.mean() > 0.1      # most c5 rays re-hit the surface they just left
+    np.testing.assert_array_equal(hseq[clean], o["seq"].numpy()[clean])
+    np.testing.assert_array_equal(h["nb"][clean], o["nb"].numpy()[clean])
+    np.testing.assert_array_equal(h["intensity"][clean], o["intensity"].numpy()[clean])
+    assert parity.vec_rel(h["pos"][clean], o["pos"].numpy()[clean]).max() <= parity.TOL_POINT
+    # all rays, including the noise-dominated ones: sequences still agree almost everywhere
+    assert (hseq == o["seq"].numpy()).all(axis=1).mean() > 0.995
+
+
+@pytest.mark.parametrize("name", NONSEQ)
+def test_nonseq_exact_matches_reference_on_stable_rays(run_exact, name):
+    """EXACT arithmetic (the default of the non-sequential ops) reproduces the reference's hit
+    sequences on every ray whose path is not decided by fp32 noise in the reference itself."""
+    d = parity.load(name)
+    nb = int(d["nbounces"])
+    h = run_exact.trace_nonseq(d["table_f"], d["table_i"], d["in_pos"], d["in_dir"], d["in_intensity"], nb)
+    hseq = h["seq"].astype(np.int64)
+    hseq[hseq == 255] = -1
+    stable = parity.stable_nonseq_rows(d) & _self_hit_free(d, torch.from_numpy(d["table_f"]), d["table_i"].tolist())
+    assert stable.sum() > 100
+    np.testing.assert_array_equal(hseq[stable], d["f32_seq"][stable])
+    _assert_close_noise_aware(h, d, name, rows=stable)
+
+
+@pytest.mark.parametrize("name", NONSEQ)
+def test_nonseq_fast_is_statistically_equivalent(run_fast, name):
+    """FAST arithmetic (FMA contraction) cannot reproduce the rounding coincidences that decide
+    whether a ray re-hits the surface it is leaving (t > 1e-6 rule at fp32 ulp ~2e-6): paths of
+    individual rays differ, like the reference's own fp32 and fp64 runs differ.
+    What must hold: first-bounce winners identical, and the energy budget equal within 2 %."""
+    d = parity.load(name)
+    nb = int(d["nbounces"])
+    h = run_fast.trace_nonseq(d["table_f"], d["table_i"], d["in_pos"], d["in_dir"], d["in_intensity"], nb)
+    hseq = h["seq"].astype(np.int64)
+    hseq[hseq == 255] = -1
+    np.testing.assert_array_equal(hseq[:, 0], d["f32_seq"][:, 0])
+    ref_disagree = (d["f32_seq"] != d["f64_seq"]).any(axis=1).mean()
+    ours_disagree = (hseq != d["f32_seq"]).any(axis=1).mean()
+    assert ours_disagree <= max(0.05, 1.5 * ref_disagree), (ours_disagree, ref_disagree)
+    alive_ref, alive_got = (d["f32_intensity"] > 0).mean(), (h["intensity"] > 0).mean()
+    assert abs(alive_ref - alive_got) <= 0.02 + 0.5 * abs(alive_ref - (d["f64_intensity"] > 0).mean())
+
+
+@pytest.mark.parametrize("name", NONSEQ)
+def test_single_bounce_parity_from_identical_states(run_exact, ieee_oracle, name):
+    """One ray_cast + step from the same input state."""
+    d = parity.load(name)
+    tf, ti = torch.from_numpy(d["table_f"]), d["table_i"].tolist()
+    p, dd, inten = parity.inputs_t(d)
+    for _b in range(3):
+        o = ieee_oracle.trace_nonsequential(tf, ti, p, dd, inten, 1)
+        h = run_exact.trace_nonseq(d["table_f"], d["table_i"], p.numpy(), dd.numpy(), inten.numpy(), 1)
+        hseq = h["seq"].astype(np.int64)
+        hseq[hseq == 255] = -1
+        np.testing.assert_array_equal(hseq, o["seq"].numpy())
+        np.testing.assert_array_equal(h["intensity"], o["intensity"].numpy())
+        # identical winners; arithmetic of the step is identical except for BLAS batch effects
+        assert parity.vec_rel(h["pos"], o["pos"].numpy()).max() <= 1e-6
+        assert parity.vec_rel(h["dir"], o["dir"].numpy()).max() <= 1e-6
+        p, dd, inten = o["pos"], o["dir"], o["intensity"]
+
+
+# ---------------------------------------------------------------------------------------------
+# element-level ops
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c1_singlet_wide", "c2_cylindrical_tilt", "c5_nonsequential", "x1_mirrors",
+                                  "x2_tilted_lenses"])
+def test_intersect_test_matches_oracle(run_exact, ieee_oracle, name):
+    d = parity.load(name)
+    tf, ti = torch.from_numpy(d["table_f"]), d["table_i"].tolist()
+    rows = ieee_oracle.make_rows(tf, ti)
+    p, dd, _ = parity.inputs_t(d)
+    S = len(rows)
+    t = run_exact.intersect_test(d["table_f"], d["table_i"], d["in_pos"], d["in_dir"], 0, S)
+    for r in range(S):
+        ref = ieee_oracle.intersect_row(rows, r, p, dd).numpy()
+        np.testing.assert_array_equal(np.nan_to_num(t[:, r], nan=-1.0), np.nan_to_num(ref, nan=-1.0),
+                                      err_msg=f"{name} row {r}")
+
+
+@pytest.mark.parametrize("name", ["c1_singlet_physical", "c2_cylindrical", "x1_mirrors", "x2_tilted_lenses"])
+def test_surface_step_matches_oracle(run_exact, ieee_oracle, name):
+    """Element.forward(rays, surf_idx): every row, on the rays that reach it (no shape-level rule)."""
+    d = parity.load(name)
+    tf, ti = torch.from_numpy(d["table_f"]), d["table_i"].tolist()
+    rows = ieee_oracle.make_rows(tf, ti)
+    p, dd, _ = parity.inputs_t(d)
+    for r in range(len(rows)):
+        hit, nd, mod, hl, t, n = ieee_oracle.element_step(rows, r, p, dd)
+        h = run_exact.surface_step(d["table_f"], d["table_i"], d["in_pos"], d["in_dir"], r)
+        ok = np.isfinite(t.numpy())
+        np.testing.assert_array_equal(np.isfinite(h["t"]), ok)
+        for a, b in ((h["pos"], hit), (h["dir"], nd), (h["hit_local"], hl), (h["normal"], n)):
+            np.testing.assert_array_equal(a[ok], b.numpy()[ok], err_msg=f"{name} row {r}")
+        np.testing.assert_array_equal(h["mod"][ok], mod.numpy()[ok])
+
+
+# ---------------------------------------------------------------------------------------------
+# sensor image
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,spec", [
+    ("c1_singlet_physical", (64, 64, -2.0, 2.0, -2.0, 2.0, 1)),
+    ("c2_cylindrical", (96, 128, -15.0, 15.0, -15.0, 15.0, 1)),
+    ("c4_camera_lens_field", (54, 96, -12.0, 12.0, -6.75, 6.75, 1)),
+])
+def test_sensor_image_matches_histogram_oracle(run_fast, name, spec):
+    d = parity.load(name)
+    o = _oracle_seq(d)
+    h = run_fast.trace_seq(d["table_f"], d["table_i"], d["in_pos"], d["in_dir"], d["in_intensity"],
+                               sensor_specs=[spec])
+    mask, hl, w = o["sensor"][0]
+    img = O.sensor_image(hl, w, spec).numpy()
+    got = h["sensors"][0][1]
+    assert got.sum() > 0
+    assert parity.rel_l1(got, img) <= parity.TOL_IMAGE_L1
+    # bin indices bit-exact away from ties: recompute bins from the kernel's own records
+    rec = h["sensors"][0][0][mask.numpy()]
+    iy, ix, inside = O.sensor_bins(torch.from_numpy(rec[:, :3]), spec)
+    iy0, ix0, inside0 = O.sensor_bins(hl, spec)
+    H, W, x0, x1, y0, y1 = spec[:6]
+    fx = (hl[:, 0].double().numpy() - x0) / (x1 - x0) * W
+    fy = (hl[:, 1].double().numpy() - y0) / (y1 - y0) * H
+    away = (np.abs(fx - np.round(fx)) > 1e-3) & (np.abs(fy - np.round(fy)) > 1e-3)
+    np.testing.assert_array_equal(ix.numpy()[away], ix0.numpy()[away])
+    np.testing.assert_array_equal(iy.numpy()[away], iy0.numpy()[away])
+    np.testing.assert_array_equal(inside.numpy()[away], inside0.numpy()[away])
+
+
+def test_wavelength_lut_equals_scalar_reference(run_exact, ieee_oracle, rtt_ns):
+    """Per-wavelength index (extension): tracing wavelength l through the LUT must equal
+    the scalar-ior trace with the glass index set to values[l]."""
+    import raytracetorch_b200 as rtt
+    d = parity.load("c2_cylindrical")
+    els = scenes.c2_cylindrical(rtt_ns)
+    disp = rtt.Dispersion(scenes.C2_WAVELENGTHS, {
+        els[0].ior_glass: [1.5 * s for s in scenes.C2_GLASS_SCALE],
+        els[1].ior_glass: [1.6 * s for s in scenes.C2_GLASS_SCALE]})
+    tab = rtt.compile_elements(els, dispersion=disp)
+    n = d["in_pos"].shape[0]
+    wav = np.asarray(scenes.C2_WAVELENGTHS, np.float32)[np.arange(n) % 3]
+    h = run_exact.trace_seq(tab.f.detach().numpy(), tab.i.numpy(), d["in_pos"], d["in_dir"], d["in_intensity"],
+                                wav=wav, lut=tab.lut.numpy(), lut_w=tab.lut_wavelengths.numpy())
+    for l in range(3):
+        els_l = scenes.c2_cylindrical(rtt_ns)
+        with torch.no_grad():
+            els_l[0].ior_glass.fill_(1.5 * scenes.C2_GLASS_SCALE[l])
+            els_l[1].ior_glass.fill_(1.6 * scenes.C2_GLASS_SCALE[l])
+        tab_l = rtt.compile_elements(els_l)
+        sel = np.arange(n) % 3 == l
+        p, dd, inten = (torch.from_numpy(d[k][sel]) for k in ("in_pos", "in_dir", "in_intensity"))
+        o = ieee_oracle.trace_sequential(tab_l.f, tab_l.i_host, p, dd, inten)
+        np.testing.assert_array_equal(h["pos"][sel], o["pos"].numpy())
+        np.testing.assert_array_equal(h["dir"][sel], o["dir"].numpy())
+        np.testing.assert_array_equal(h["intensity"][sel], o["intensity"].numpy())
+
+
+# ---------------------------------------------------------------------------------------------
+# adjoint
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", ["exact", "fast"])
+@pytest.mark.parametrize("name", parity.golden_names(grads=True))
+def test_seq_adjoint_matches_reference_autograd(runner_of, rtt_ns, name, variant):
+    """Hand-written adjoint (recompute + reverse sweep) vs the reference's autograd: input-ray
+    gradients per ray and every trainable Parameter, within 1e-3 relative."""
+    import raytracetorch_b200 as rtt
+    hs = runner_of(variant)
+    builder, kw, _ = scenes.GRAD_CASES[name]
+    d = parity.load(name)
+    els = builder(rtt_ns, **kw)
+    holder = torch.nn.Module()
+    holder.elements = torch.nn.ModuleList(els)
+    tab = rtt.compile_elements(els)
+    tf, ti = tab.f.detach().numpy(), tab.i.numpy()
+    fwd = hs.trace_seq(tf, ti, d["in_pos"], d["in_dir"], d["in_intensity"])
+    gp, gd, gi = parity.golden_loss_grads(fwd["pos"], fwd["dir"], fwd["intensity"])
+    bwd = hs.trace_seq_bwd(tf, ti, d["in_pos"], d["in_dir"], d["in_intensity"], fwd["hitmask"], gp, gd, gi)
+    assert parity.grad_rel(bwd["g_pos"], d["f32_g_pos"]) < parity.TOL_GRAD
+    assert parity.grad_rel(bwd["g_dir"], d["f32_g_dir"]) < parity.TOL_GRAD
+    assert parity.grad_rel(bwd["g_intensity"], d["f32_g_intensity"]) < parity.TOL_GRAD
+    # chain d loss / d table through the table-building graph to the Parameters
+    tab.f.backward(torch.from_numpy(bwd["g_table"]))
+    params = dict(holder.named_parameters())
+    for k in [k[len("f32_gp::"):] for k in d.files if k.startswith("f32_gp::")]:
+        ref = d["f64_gp::" + k]
+        g = params[k].grad
+        g = np.zeros_like(ref) if g is None else g.numpy()
+        if np.linalg.norm(ref) == 0:
+            assert np.linalg.norm(g) == 0, k
+        else:
+            assert parity.grad_rel(g, ref) < parity.TOL_GRAD, (k, g, ref)
+            assert parity.grad_rel(g, d["f32_gp::" + k]) < parity.TOL_GRAD, k
+
+
+def test_sensor_record_adjoint(rtt_ns, run_exact):
+    """Gradient flowing in through the sensor record (hit_local, weight) — what SpotSizeLoss uses
+    (optim/goals.py:165-187) — against oracle autograd."""
+    import raytracetorch_b200 as rtt
+    d = parity.load("grad_c3_singlet")
+    els = scenes.c1_singlet(rtt_ns, physical=True, grads=True)
+    tab = rtt.compile_elements(els)
+    p, dd, inten = parity.inputs_t(d)
+    for t in (p, dd, inten):
+        t.requires_grad_(True)
+    o = O.trace_sequential(tab.f, tab.i_host, p, dd, inten)
+    mask, hl, w = o["sensor"][0]
+    loss = (w * (hl[:, 0] ** 2 + hl[:, 1] ** 2)).sum() / w.sum()
+    loss.backward()
+    ref_c = [els[0].shape.surfaces[k].c.grad.clone() for k in (0, 1)]
+    ref_gpos = p.grad.numpy().copy()
+    for k in (0, 1):
+        els[0].shape.surfaces[k].c.grad = None
+    tab = rtt.compile_elements(els)
+    tf, ti = tab.f.detach().numpy(), tab.i.numpy()
+    fwd = run_exact.trace_seq(tf, ti, d["in_pos"], d["in_dir"], d["in_intensity"], sensor_specs=[None])
+    rec = torch.from_numpy(fwd["sensors"][0][0]).requires_grad_(True)
+    m = torch.from_numpy(parity.mask_bits(fwd["hitmask"], tf.shape[0])[:, tab.sensor_rows[0]])
+    ww = rec[:, 3] * m
+    ((ww * (rec[:, 0] ** 2 + rec[:, 1] ** 2)).sum() / ww.sum()).backward()
+    bwd = run_exact.trace_seq_bwd(tf, ti, d["in_pos"], d["in_dir"], d["in_intensity"], fwd["hitmask"],
+                                      None, None, None, g_records=[rec.grad.numpy()])
+    tab.f.backward(torch.from_numpy(bwd["g_table"]))
+    for k in (0, 1):
+        assert parity.grad_rel(els[0].shape.surfaces[k].c.grad.numpy(), ref_c[k].numpy()) < parity.TOL_GRAD
+    assert parity.grad_rel(bwd["g_pos"], ref_gpos) < parity.TOL_GRAD
+
+
+def test_nonseq_adjoint_matches_oracle_autograd(rtt_ns, run_exact, ieee_oracle):
+    import raytracetorch_b200 as rtt
+    d = parity.load("x2_nonsequential")
+    els = scenes.x2_tilted_lenses(rtt_ns, grads=True)
+    holder = torch.nn.Module()
+    holder.elements = torch.nn.ModuleList(els)
+    tab = rtt.compile_elements(els)
+    nb = 6
+    p, dd, inten = parity.inputs_t(d)
+    for t in (p, dd, inten):
+        t.requires_grad_(True)
+    o = O.trace_nonsequential(tab.f, tab.i_host, p, dd, inten, nb)
+    parity.golden_loss(o["pos"], o["dir"], o["intensity"]).backward()
+    ref = {k: v.grad.clone() for k, v in holder.named_parameters() if v.grad is not None}
+    for v in holder.parameters():
+        v.grad = None
+    tab = rtt.compile_elements(els)
+    tf, ti = tab.f.detach().numpy(), tab.i.numpy()
+    fwd = run_exact.trace_nonseq(tf, ti, d["in_pos"], d["in_dir"], d["in_intensity"], nb)
+    same = (np.where(fwd["seq"] == 255, -1, fwd["seq"].astype(np.int64)) == o["seq"].numpy()).all(1)
+    assert same.mean() > 0.97
+    gp, gd, gi = parity.golden_loss_grads(fwd["pos"], fwd["dir"], fwd["intensity"])
+    bwd = run_exact.trace_nonseq_bwd(tf, ti, d["in_pos"], d["in_dir"], d["in_intensity"], fwd["seq"], gp, gd, gi)
+    assert parity.grad_rel(bwd["g_pos"][same], p.grad.numpy()[same]) < parity.TOL_GRAD
+    assert parity.grad_rel(bwd["g_dir"][same], dd.grad.numpy()[same]) < parity.TOL_GRAD
+    tab.f.backward(torch.from_numpy(bwd["g_table"]))
+    checked = 0
+    for k, v in holder.named_parameters():
+        if k in ref and float(ref[k].norm()) > 0:
+            # a handful of noise-dominated rays take another path: looser than the sequential bar
+            assert parity.grad_rel(v.grad.numpy(), ref[k].numpy()) < 2e-2, k
+            checked += 1
+    assert checked >= 5
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------------------
+def test_empty_single_and_degenerate_bundles(run_exact, ieee_oracle):
+    d = parity.load("c1_singlet_physical")
+    tf, ti = d["table_f"], d["table_i"]
+    z3, z1 = np.zeros((0, 3), np.float32), np.zeros(0, np.float32)
+    h = run_exact.trace_seq(tf, ti, z3, z3, z1)
+    assert h["pos"].shape == (0, 3)
+    # one ray; a ray that misses everything; a dead ray; a NaN ray; an axis ray (edge cylinder A=B=0 -> NaN -> miss)
+    pos = np.array([[0, 1, -10], [100, 100, -10], [0, 2, -10], [np.nan, 0, -10], [0, 0, -10]], np.float32)
+    dr = np.array([[0, 0, 1], [0, 0, 1], [0, 0, 1], [0, 0, 1], [0, 0, 1]], np.float32)
+    inten = np.array([1, 1, 0, 1, 1], np.float32)
+    h = run_exact.trace_seq(tf, ti, pos, dr, inten)
+    o = ieee_oracle.trace_sequential(torch.from_numpy(tf), ti.tolist(), torch.from_numpy(pos), torch.from_numpy(dr),
+                                     torch.from_numpy(inten))
+    np.testing.assert_array_equal(h["pos"], o["pos"].numpy())
+    np.testing.assert_array_equal(h["dir"], o["dir"].numpy())
+    np.testing.assert_array_equal(h["intensity"], o["intensity"].numpy())
+    np.testing.assert_array_equal(h["pos"][1], pos[1])          # miss => untouched (scene/sequential.py:23-34)
+    assert h["hitmask"][1] == 0 and h["hitmask"][3] == 0
+    for n in (1, 2, 31, 33):
+        hh = run_exact.trace_seq(tf, ti, pos[:1].repeat(n, 0), dr[:1].repeat(n, 0), inten[:1].repeat(n))
+        np.testing.assert_array_equal(hh["pos"], h["pos"][:1].repeat(n, 0))
+
+
+def test_known_answers_of_reference_tests(run_exact, rtt_ns):
+    """The analytic known answers the reference's own tests hold for this path
+    (tests/test_primitive.py:121-128 parabola heights, :84-94 sphere, :166-242 plane hit (0,5,5) and
+    dL/dT=(0,0,2), :244-307 quadric dL/dTz=1)."""
+    import raytracetorch_b200 as rtt
+    G = rtt.geom
+    holder = rtt.ops._Holder
+
+    def table_of(surface):
+        return rtt.compile_elements([holder(surface, [rtt.phys.Transmit()])])
+
+    # parabola c=0.1, k=-1: z(y=2)=0.2, z(y=5)=1.25
+    tab = table_of(G.Quadric(c=0.1, k=-1.0))
+    pos = np.array([[0, 2, -10], [0, 5, -10]], np.float32)
+    dr = np.array([[0, 0, 1], [0, 0, 1]], np.float32)
+    s = run_exact.surface_step(tab.f.detach().numpy(), tab.i.numpy(), pos, dr, 0)
+    np.testing.assert_allclose(s["pos"][:, 2], [0.2, 1.25], atol=1e-5)
+    np.testing.assert_allclose(s["pos"], pos + s["t"][:, None] * dr, atol=1e-6)
+    # sphere R=10 from outside: hit radius is R; a far ray misses
+    tab = table_of(G.Sphere(10.0))
+    pos = np.array([[0, 0, -20], [0, 20, -20]], np.float32)
+    s = run_exact.surface_step(tab.f.detach().numpy(), tab.i.numpy(), pos, dr, 0)
+    assert abs(np.linalg.norm(s["pos"][0]) - 10.0) < 1e-4 and not np.isfinite(s["t"][1])
+    # plane at z=5, ray (0,1,1)/sqrt2 from the origin: hit (0,5,5); d(sum hit)/dT = (0,0,2)
+    tr = G.RayTransform(translation=[0.0, 0.0, 5.0], trans_grad=True, rot_grad=False)
+    plane = G.Plane(transform=tr)
+    tab = table_of(plane)
+    pos = np.zeros((1, 3), np.float32)
+    dr = (np.array([[0, 1, 1]], np.float32) / np.sqrt(np.float32(2))).astype(np.float32)
+    tf, ti = tab.f.detach().numpy(), tab.i.numpy()
+    s = run_exact.surface_step(tf, ti, pos, dr, 0)
+    np.testing.assert_allclose(s["pos"][0], [0, 5, 5], atol=1e-5)
+    b = run_exact.surface_step_bwd(tf, ti, pos, dr, 0, g_npos=np.ones((1, 3), np.float32))
+    tab.f.backward(torch.from_numpy(b["g_table"]))
+    np.testing.assert_allclose(tr.trans.grad.numpy(), [0, 0, 2], atol=1e-5)
+    # quadric c=0.01 at z=5, axial ray at x=5: d(sum hit)/dTz = 1
+    tr = G.RayTransform(translation=[0.0, 0.0, 5.0], trans_grad=True, rot_grad=False)
+    tab = table_of(G.Quadric(c=0.01, k=0.0, c_grad=True, transform=tr))
+    pos = np.array([[5, 0, 0]], np.float32)
+    dr = np.array([[0, 0, 1]], np.float32)
+    tf, ti = tab.f.detach().numpy(), tab.i.numpy()
+    b = run_exact.surface_step_bwd(tf, ti, pos, dr, 0, g_npos=np.ones((1, 3), np.float32))
+    tab.f.backward(torch.from_numpy(b["g_table"]))
+    np.testing.assert_allclose(tr.trans.grad.numpy()[2], 1.0, atol=1e-5)
