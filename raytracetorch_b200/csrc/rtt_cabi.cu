@@ -48,6 +48,7 @@ int fill_sensors(SD* dst, const rtt_sensor_t* src, int n) {
         std::memset(&q, 0, sizeof(q));
         if (s < n) {
             if (src[s].image && (src[s].height < 1 || src[s].width < 1 || src[s].channels < 1)) return RTT_E_SENSOR;
+            if (src[s].image && (long long)src[s].height * src[s].width * src[s].channels >= (1ll << 28)) return RTT_E_SENSOR;
             if (src[s].record && (reinterpret_cast<uintptr_t>(src[s].record) & 15)) return RTT_E_ALIGN;
             q.image = src[s].image; q.record = src[s].record;
             q.H = src[s].height; q.W = src[s].width; q.C = src[s].channels;

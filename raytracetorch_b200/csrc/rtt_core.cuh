@@ -39,6 +39,24 @@ inline float mul_rn(float a, float b) { volatile float m = a * b; return m; }
 inline float sub_rn(float a, float b) { volatile float m = a - b; return m; }
 #endif
 
+// Division / square root.  EXACT: IEEE (div.rn / sqrt.rn), like the reference's eager ops.  FAST
+// (RTT_APPROX, device only): MUFU approximations (rcp / sqrt .approx.ftz, <= 2 ulp), one reciprocal
+// shared by the three components of a vector; IEEE fp32 division costs ~10 issue slots plus a
+// slow-path CALL for zero / inf / denormal operands, which dead rays (dir == 0) and missed roots
+// (t == inf) hit all the time: ~40 % of the forward kernel's instructions in the first profile
+// (profiles/r1_c2_seq_fwd_baseline.md).  Special values behave like IEEE where the algorithm
+// relies on them: x*rcp(0) = inf or NaN (0*inf), which keeps "axis-parallel ray on a cylinder edge
+// => NaN => miss" (geom/primitives.py:212-231).
+#if defined(RTT_APPROX) && defined(__CUDA_ARCH__)
+RTT_HD float rcp_(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+RTT_HD float sqrt_(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+RTT_HD float div_(float a, float b) { return a * rcp_(b); }
+#else
+RTT_HD float rcp_(float x) { return 1.0f / x; }
+RTT_HD float sqrt_(float x) { return sqrtf(x); }
+RTT_HD float div_(float a, float b) { return a / b; }
+#endif
+
 // ---- row record as staged in shared memory ------------------------------------------------
 // f[0..40] is the caller's table row; f[41..47] and i[11] are derived once per block.
 enum {
@@ -92,8 +110,17 @@ RTT_HD V3 mul_RT(V3 a, const float* R) {
               fma3(a.x, R[6], a.y, R[7], a.z, R[8]));
 }
 // torch.norm / F.normalize over one 3-vector
-RTT_HD float norm3(float x, float y, float z) { return sqrtf(fma3(x, x, y, y, z, z)); }
+RTT_HD float norm3(float x, float y, float z) { return sqrt_(fma3(x, x, y, y, z, z)); }
 RTT_HD V3 ld3(const float* p) { return v3(p[0], p[1], p[2]); }
+// v / s, component-wise (one reciprocal in FAST mode)
+RTT_HD V3 div3(V3 v, float s) {
+#if defined(RTT_APPROX) && defined(__CUDA_ARCH__)
+    const float r = rcp_(s);
+    return v3(v.x * r, v.y * r, v.z * r);
+#else
+    return v3(v.x / s, v.y / s, v.z / s);
+#endif
+}
 
 // Derived per-row constants; the same fp32 operations the reference performs on 0-dim tensors.
 RTT_HD void prepare_row(RowDev& R) {
@@ -127,7 +154,7 @@ RTT_HD V3 normalize12(V3 v, float* len_out) {
     const float s = norm3(v.x, v.y, v.z);
     const float den = fmaxf(s, 1e-12f);
     *len_out = s;
-    return v3(v.x / den, v.y / den, v.z / den);
+    return div3(v, den);
 }
 
 // ---- surface-level bounds (geom/bounded.py) ------------------------------------------------
@@ -141,7 +168,7 @@ RTT_HD bool surface_in_bounds(const RowDev& R, V3 h) {
         case RTT_BOUND_ELLIPSE: {                                       // :98-106
             const float u = h.x * sb[2] - h.y * sb[3];
             const float v = h.x * sb[3] + h.y * sb[2];
-            const float a = u / sb[0], b = v / sb[1];
+            const float a = div_(u, sb[0]), b = div_(v, sb[1]);
             return (a * a + b * b) <= 1.0f;
         }
         case RTT_BOUND_HALF:                                            // :123-127, :171-174
@@ -169,7 +196,7 @@ RTT_HD Roots solve_roots(const RowDev& R, V3 o, V3 d) {
     switch (R.i[RTT_I_SURF]) {
         case RTT_SURF_PLANE: {                                          // :124-136
             const float safe = (fabsf(d.z) < 1e-6f) ? 1e-8f : d.z;
-            q.t1 = -o.z / safe; q.t2 = inf; q.n = 1; q.B = safe;
+            q.t1 = div_(-o.z, safe); q.t2 = inf; q.n = 1; q.B = safe;
             return q;
         }
         case RTT_SURF_SPHERE: {                                         // :155-184 (a == 1 assumed)
@@ -177,9 +204,9 @@ RTT_HD Roots solve_roots(const RowDev& R, V3 o, V3 d) {
             const float cc = dot(o, o) - R.f[D_R2];
             const float disc = sub_rn(mul_rn(b, b), mul_rn(4.0f, cc));
             const bool ok = disc >= 0.0f;
-            const float sq = sqrtf(ok ? disc : 0.0f);
-            q.t1 = ok ? (-b - sq) / 2.0f : inf;
-            q.t2 = ok ? (-b + sq) / 2.0f : inf;
+            const float sq = sqrt_(ok ? disc : 0.0f);
+            q.t1 = ok ? (-b - sq) * 0.5f : inf;        // x/2 == x*0.5 exactly
+            q.t2 = ok ? (-b + sq) * 0.5f : inf;
             q.B = b; q.sq = sq;
             return q;
         }
@@ -189,9 +216,10 @@ RTT_HD Roots solve_roots(const RowDev& R, V3 o, V3 d) {
             const float Cq = (o.x * o.x + o.y * o.y) - R.f[D_R2];
             const float disc = sub_rn(mul_rn(B, B), mul_rn(mul_rn(4.0f, A), Cq));
             const bool ok = disc >= 0.0f;
-            const float sq = sqrtf(fabsf(disc));
-            q.t1 = ok ? (-B - sq) / (2.0f * A) : inf;
-            q.t2 = ok ? (-B + sq) / (2.0f * A) : inf;
+            const float sq = sqrt_(fabsf(disc));
+            const float den = 2.0f * A;
+            q.t1 = ok ? div_(-B - sq, den) : inf;
+            q.t2 = ok ? div_(-B + sq, den) : inf;
             q.A = A; q.B = B; q.C = Cq; q.sq = sq;
             return q;
         }
@@ -211,12 +239,12 @@ RTT_HD Roots solve_roots(const RowDev& R, V3 o, V3 d) {
             const float disc = sub_rn(mul_rn(B, B), mul_rn(mul_rn(4.0f, A), Cq));
             const bool ok = disc >= 0.0f;
             const bool lin = fabsf(A) < 1e-6f;
-            const float sq = sqrtf(fabsf(disc));
+            const float sq = sqrt_(fabsf(disc));
             const float As = lin ? 1.0f : A;
             const float den = 2.0f * As;
-            const float r1 = (-B - sq) / den, r2 = (-B + sq) / den;
+            const float r1 = div_(-B - sq, den), r2 = div_(-B + sq, den);
             const float Bs = (fabsf(B) < 1e-6f) ? 1e-6f : B;
-            const float tl = -Cq / Bs;
+            const float tl = lin ? div_(-Cq, Bs) : 0.0f;
             q.t1 = lin ? tl : (ok ? r1 : inf);
             q.t2 = lin ? tl : (ok ? r2 : inf);
             q.A = A; q.B = B; q.C = Cq; q.sq = sq; q.lin = lin;
@@ -257,7 +285,7 @@ RTT_HD float sag_at(float c, float h, float tz) {                       // geom/
     const float h2 = h * h;
     float term = 1.0f - (c * c) * h2;
     term = term > 0.0f ? term : 0.0f;
-    return (c * h2) / (1.0f + sqrtf(term)) + tz;
+    return div_(c * h2, 1.0f + sqrt_(term)) + tz;
 }
 
 RTT_HD bool shape_in_bounds(const RowDev* rows, int r, V3 h) {
@@ -337,8 +365,8 @@ RTT_HD V3 normal_local(const RowDev& R, V3 h, float* len_out) {
     *len_out = 1.0f;
     switch (R.i[RTT_I_SURF]) {
         case RTT_SURF_PLANE: return v3(0.0f, 0.0f, 1.0f);
-        case RTT_SURF_SPHERE: { const float rr = R.f[RTT_F_RADIUS]; return v3(h.x / rr, h.y / rr, h.z / rr); }
-        case RTT_SURF_CYLINDER: { const float rr = R.f[RTT_F_RADIUS]; return v3(h.x / rr, h.y / rr, 0.0f); }
+        case RTT_SURF_SPHERE: return div3(h, R.f[RTT_F_RADIUS]);
+        case RTT_SURF_CYLINDER: { const V3 q = div3(v3(h.x, h.y, 0.0f), R.f[RTT_F_RADIUS]); return v3(q.x, q.y, 0.0f); }
         default: {
             const float tc = 2.0f * R.f[RTT_F_C], tc1k = 2.0f * R.f[D_C1K];
             const float nx = (R.i[RTT_I_SURF] == RTT_SURF_QUADRIC) ? tc * h.x : 0.0f;
@@ -347,7 +375,7 @@ RTT_HD V3 normal_local(const RowDev& R, V3 h, float* len_out) {
             const float len = norm3(nx, ny, nz);
             const float den = len + 1e-8f;
             *len_out = len;
-            return v3(-(nx / den), -(ny / den), -(nz / den));
+            return -div3(v3(nx, ny, nz), den);
         }
     }
 }
@@ -386,7 +414,7 @@ RTT_HD V3 physics(const RowDev& R, V3 hl, V3 d, V3 n, float mu_enter, float mu_e
                 const float tw = 2.0f * dt;
                 return v3(d.x - tw * n.x, d.y - tw * n.y, d.z - tw * n.z);
             }
-            const float c2 = sqrtf(term > 0.0f ? term : 0.0f);
+            const float c2 = sqrt_(term > 0.0f ? term : 0.0f);
             const float qf = mu * c1 - c2;
             const V3 ne = entering ? n : -n;
             return v3(mu * d.x + qf * ne.x, mu * d.y + qf * ne.y, mu * d.z + qf * ne.z);
@@ -513,7 +541,7 @@ RTT_HD void interact_adjoint(const RowDev& R, V3 p, V3 d, float ni, float no, fl
                 g_d = g_d + (g_dir - (2.0f * gn) * n);
                 g_n = -2.0f * (gn * d + dt * g_dir);
             } else {
-                const float c2 = sqrtf(term > 0.0f ? term : 0.0f);
+                const float c2 = sqrt_(term > 0.0f ? term : 0.0f);
                 const float sgn = entering ? 1.0f : -1.0f;
                 const float qf = mu * c1 - c2;
                 float g_mu = dot(g_dir, d);
@@ -522,7 +550,7 @@ RTT_HD void interact_adjoint(const RowDev& R, V3 p, V3 d, float ni, float no, fl
                 g_n = (qf * sgn) * g_dir;
                 g_mu += c1 * g_q;
                 float g_c1 = mu * g_q;
-                const float g_term = (term > 0.0f) ? (-g_q) / (2.0f * c2) : 0.0f;
+                const float g_term = (term > 0.0f) ? div_(-g_q, 2.0f * c2) : 0.0f;
                 g_mu += g_term * (-2.0f * mu * one_m);
                 g_c1 += g_term * (2.0f * mu * mu * c1);
                 const float g_dt = (dt < 0.0f) ? -g_c1 : ((dt > 0.0f) ? g_c1 : 0.0f);
@@ -530,11 +558,11 @@ RTT_HD void interact_adjoint(const RowDev& R, V3 p, V3 d, float ni, float no, fl
                 g_n = g_n + g_dt * d;
                 if (want & RTT_FLAG_GRAD_IOR) {
                     if (entering) {                                     // mu = no/ni
-                        G.g[RTT_F_IOR_OUT] += g_mu / ni;
-                        G.g[RTT_F_IOR_IN] -= g_mu * no / (ni * ni);
+                        G.g[RTT_F_IOR_OUT] += div_(g_mu, ni);
+                        G.g[RTT_F_IOR_IN] -= div_(g_mu * no, ni * ni);
                     } else {                                            // mu = ni/no
-                        G.g[RTT_F_IOR_IN] += g_mu / no;
-                        G.g[RTT_F_IOR_OUT] -= g_mu * ni / (no * no);
+                        G.g[RTT_F_IOR_IN] += div_(g_mu, no);
+                        G.g[RTT_F_IOR_OUT] -= div_(g_mu * ni, no * no);
                     }
                 }
             }
@@ -557,14 +585,14 @@ RTT_HD void interact_adjoint(const RowDev& R, V3 p, V3 d, float ni, float no, fl
         case RTT_SURF_PLANE: break;
         case RTT_SURF_SPHERE: {
             const float rr = R.f[RTT_F_RADIUS];
-            g_hl = g_hl + v3(g_nl.x / rr, g_nl.y / rr, g_nl.z / rr);
-            G.g[RTT_F_RADIUS] -= dot(g_nl, hl) / (rr * rr);
+            g_hl = g_hl + div3(g_nl, rr);
+            G.g[RTT_F_RADIUS] -= div_(dot(g_nl, hl), rr * rr);
             break;
         }
         case RTT_SURF_CYLINDER: {
             const float rr = R.f[RTT_F_RADIUS];
-            g_hl.x += g_nl.x / rr; g_hl.y += g_nl.y / rr;
-            G.g[RTT_F_RADIUS] -= (g_nl.x * hl.x + g_nl.y * hl.y) / (rr * rr);
+            { const float ir = rcp_(rr); g_hl.x += g_nl.x * ir; g_hl.y += g_nl.y * ir; }
+            G.g[RTT_F_RADIUS] -= div_(g_nl.x * hl.x + g_nl.y * hl.y, rr * rr);
             break;
         }
         default: {
@@ -575,8 +603,9 @@ RTT_HD void interact_adjoint(const RowDev& R, V3 p, V3 d, float ni, float no, fl
             const float den = nlen + 1e-8f;
             // nl = -raw/den, den = |raw| + 1e-8
             const float rg = dot(raw, g_nl);
-            const float s = (nlen > 0.0f) ? rg / (den * den * nlen) : 0.0f;
-            const V3 g_raw = v3(-(g_nl.x / den) + raw.x * s, -(g_nl.y / den) + raw.y * s, -(g_nl.z / den) + raw.z * s);
+            const float s = (nlen > 0.0f) ? div_(rg, den * den * nlen) : 0.0f;
+            const V3 gq = div3(g_nl, den);
+            const V3 g_raw = v3(-gq.x + raw.x * s, -gq.y + raw.y * s, -gq.z + raw.z * s);
             float g_tc = g_raw.y * hl.y;
             if (full) { g_hl.x += tc * g_raw.x; g_tc += g_raw.x * hl.x; }
             g_hl.y += tc * g_raw.y;
@@ -598,23 +627,25 @@ RTT_HD void interact_adjoint(const RowDev& R, V3 p, V3 d, float ni, float no, fl
     switch (R.i[RTT_I_SURF]) {
         case RTT_SURF_PLANE: {
             const float safe = q.B;
-            g_o.z += -g_t / safe;
-            if (!(fabsf(dd.z) < 1e-6f)) g_dd.z += -g_t * t / safe;      // d(-oz/dz)/d dz = -t/dz
+            const float g_t_s = div_(g_t, safe);
+            g_o.z += -g_t_s;
+            if (!(fabsf(dd.z) < 1e-6f)) g_dd.z += -g_t_s * t;      // d(-oz/dz)/d dz = -t/dz
             break;
         }
         case RTT_SURF_SPHERE: {
             const float sg = which ? 1.0f : -1.0f;
             const float b = q.B, sq = q.sq;
-            const float g_b = g_t * (-1.0f + sg * b / sq) * 0.5f;
-            const float g_cc = -g_t * sg / sq;
+            const float isq = rcp_(sq);
+            const float g_b = g_t * (-1.0f + sg * b * isq) * 0.5f;
+            const float g_cc = -g_t * sg * isq;
             g_o = g_o + (2.0f * g_b) * dd + (2.0f * g_cc) * o;
             g_dd = g_dd + (2.0f * g_b) * o;
             G.g[RTT_F_RADIUS] += g_cc * (-2.0f * R.f[RTT_F_RADIUS]);
             break;
         }
         case RTT_SURF_CYLINDER: {
-            const float D = 2.0f * q.A * t + q.B;
-            const float gA = -g_t * t * t / D, gB = -g_t * t / D, gC = -g_t / D;
+            const float gC = -g_t * rcp_(2.0f * q.A * t + q.B);
+            const float gB = gC * t, gA = gB * t;
             g_dd.x += gA * 2.0f * dd.x + gB * 2.0f * o.x;
             g_dd.y += gA * 2.0f * dd.y + gB * 2.0f * o.y;
             g_o.x += gB * 2.0f * dd.x + gC * 2.0f * o.x;
@@ -628,11 +659,11 @@ RTT_HD void interact_adjoint(const RowDev& R, V3 p, V3 d, float ni, float no, fl
             if (q.lin) {
                 const float Bs = (fabsf(q.B) < 1e-6f) ? 1e-6f : q.B;
                 gA = 0.0f;
-                gC = -g_t / Bs;
-                gB = (fabsf(q.B) < 1e-6f) ? 0.0f : g_t * q.C / (Bs * Bs);
+                gC = div_(-g_t, Bs);
+                gB = (fabsf(q.B) < 1e-6f) ? 0.0f : div_(g_t * q.C, Bs * Bs);
             } else {
-                const float D = 2.0f * q.A * t + q.B;
-                gA = -g_t * t * t / D; gB = -g_t * t / D; gC = -g_t / D;
+                gC = -g_t * rcp_(2.0f * q.A * t + q.B);
+                gB = gC * t; gA = gB * t;
             }
             const bool full = R.i[RTT_I_SURF] == RTT_SURF_QUADRIC;
             const float ox = full ? o.x : 0.0f, dx = full ? dd.x : 0.0f;
@@ -667,9 +698,9 @@ RTT_HD void interact_adjoint(const RowDev& R, V3 p, V3 d, float ni, float no, fl
     V3 g_de;
     if (F.len > 1e-12f) {
         const float pr = dot(F.den, g_den);
-        g_de = v3((g_den.x - F.den.x * pr) / F.len, (g_den.y - F.den.y * pr) / F.len, (g_den.z - F.den.z * pr) / F.len);
+        g_de = div3(v3(g_den.x - F.den.x * pr, g_den.y - F.den.y * pr, g_den.z - F.den.z * pr), F.len);
     } else {
-        g_de = v3(g_den.x / 1e-12f, g_den.y / 1e-12f, g_den.z / 1e-12f);
+        g_de = v3(g_den.x * 1e12f, g_den.y * 1e12f, g_den.z * 1e12f);
     }
     // ---- element pose: pe = (p - Te) @ Re ; de = d @ Re ----
     const V3 pte = p - ld3(R.f + RTT_F_TE);

@@ -98,16 +98,64 @@ __device__ __forceinline__ Ior row_ior(const SmemTable& T, int S, int L, int r, 
 __device__ __forceinline__ V3 load3(const float* a, long long i) { return v3(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
 __device__ __forceinline__ void store3(float* a, long long i, V3 v) { a[3 * i] = v.x; a[3 * i + 1] = v.y; a[3 * i + 2] = v.z; }
 
-__device__ __forceinline__ void sensor_deposit(const SensorDev& sd, long long i, V3 hl, float w, int lam) {
+// ---- sensor image accumulation ---------------------------------------------------------------
+// Focused bundles put ~all rays of a launch into a handful of bins (C1: a 1e8-ray bundle focused
+// onto a few pixels), so plain global atomics serialise in L2.  Two levels of privatisation:
+//   1. warp: lanes that target the same bin are found with match.any and summed with shuffles;
+//      one lane per distinct bin goes on;
+//   2. block: a small direct-mapped cache of (bin, partial sum) pairs in shared memory absorbs
+//      the hot bins (shared-memory atomics); a lane whose slot is owned by another bin falls
+//      through to a global atomic, so spread-out images (low contention anyway) only pay one
+//      shared-memory CAS.  The cache is flushed with one global atomic per occupied slot when
+//      the persistent block has finished its rays.
+// Zero weights (dead rays that still cross the sensor) add nothing and are skipped.
+constexpr int kImgSlots = 1024;
+constexpr int kImgKeyBits = 28;        // key = sensor slot << 28 | flat bin index
+
+struct ImgCache {
+    int* tag;          // [kImgSlots], -1 = empty
+    float* val;        // [kImgSlots]
+};
+
+__host__ __device__ inline size_t img_cache_bytes() { return (size_t)kImgSlots * 8; }
+
+__device__ __forceinline__ void img_cache_init(ImgCache c) {
+    for (int idx = threadIdx.x; idx < kImgSlots; idx += blockDim.x) { c.tag[idx] = -1; c.val[idx] = 0.0f; }
+}
+
+__device__ __forceinline__ void img_cache_add(ImgCache c, float* image, int slot, int bin, float w) {
+    const unsigned conv = __activemask();
+    const int key = (slot << kImgKeyBits) | bin;
+    const unsigned peers = __match_any_sync(conv, key);
+    float sum = 0.0f;
+    for (unsigned rem = peers; rem; rem &= rem - 1) sum += __shfl_sync(peers, w, __ffs((int)rem) - 1);
+    if ((int)(threadIdx.x & 31) != __ffs((int)peers) - 1) return;
+    const int s = (key ^ (key >> 10)) & (kImgSlots - 1);
+    const int old = atomicCAS(c.tag + s, -1, key);
+    if (old == -1 || old == key) atomicAdd(c.val + s, sum);
+    else atomicAdd(image + bin, sum);
+}
+
+__device__ __forceinline__ void img_cache_flush(ImgCache c, const SensorDev* sens) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < kImgSlots; idx += blockDim.x) {
+        const int key = c.tag[idx];
+        if (key >= 0 && c.val[idx] != 0.0f)
+            atomicAdd(sens[key >> kImgKeyBits].image + (key & ((1 << kImgKeyBits) - 1)), c.val[idx]);
+    }
+}
+
+__device__ __forceinline__ void sensor_deposit(const SensorDev& sd, ImgCache c, int slot, long long i, V3 hl, float w,
+                                               int lam) {
     if (sd.record) {
         float4* rec = reinterpret_cast<float4*>(sd.record);
         rec[i] = make_float4(hl.x, hl.y, hl.z, w);
     }
-    if (sd.image) {
+    if (sd.image && w != 0.0f) {
         int ix, iy;
         if (sensor_bin(hl.x, hl.y, sd.x0, sd.y0, sd.sx, sd.sy, sd.W, sd.H, &ix, &iy)) {
             const int ch = (sd.C > 1) ? min(lam, sd.C - 1) : 0;
-            atomicAdd(sd.image + ((size_t)ch * sd.H + iy) * sd.W + ix, w);
+            img_cache_add(c, sd.image, slot, (ch * sd.H + iy) * sd.W + ix, w);
         }
     }
 }
@@ -119,6 +167,10 @@ __device__ __forceinline__ void sensor_deposit(const SensorDev& sd, long long i,
 __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_fwd)(const __grid_constant__ SeqFwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemTable T = carve(smem_raw, a.tab.S, a.tab.L);
+    ImgCache cache;
+    cache.tag = reinterpret_cast<int*>(smem_raw + ((smem_table_bytes(a.tab.S, a.tab.L) + 15) / 16) * 16);
+    cache.val = reinterpret_cast<float*>(cache.tag + kImgSlots);
+    img_cache_init(cache);
     stage_table(a.tab, T);
     const int S = a.tab.S, L = a.tab.L;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -134,7 +186,7 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_fwd)(const __gr
             const Ior io = row_ior(T, S, L, r, lam);
             const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
             const int slot = R.i[RTT_I_SENSOR];
-            if (slot >= 0 && slot < a.n_sens) sensor_deposit(a.sens[slot], i, s.hit_local, I, lam);
+            if (slot >= 0 && slot < a.n_sens) sensor_deposit(a.sens[slot], cache, slot, i, s.hit_local, I, lam);
             p = s.hit_global; d = s.new_dir; I = I * s.mod;
             mask |= 1ull << r;
         }
@@ -142,6 +194,7 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_fwd)(const __gr
         a.ointen[i] = I;
         if (a.hitmask) a.hitmask[i] = mask;
     }
+    img_cache_flush(cache, a.sens);
 }
 
 // ============================================================================================
@@ -298,6 +351,10 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_bwd)(const __gr
 __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const __grid_constant__ NonseqFwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemTable T = carve(smem_raw, a.tab.S, a.tab.L);
+    ImgCache cache;
+    cache.tag = reinterpret_cast<int*>(smem_raw + ((smem_table_bytes(a.tab.S, a.tab.L) + 15) / 16) * 16);
+    cache.val = reinterpret_cast<float*>(cache.tag + kImgSlots);
+    img_cache_init(cache);
     stage_table(a.tab, T);
     const int S = a.tab.S, L = a.tab.L, NB = a.nbounces;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -326,7 +383,7 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
             const Ior io = row_ior(T, S, L, win, lam);
             const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
             const int slot = R.i[RTT_I_SENSOR];
-            if (slot >= 0 && slot < a.n_sens) sensor_deposit(a.sens[slot], i, s.hit_local, I, lam);
+            if (slot >= 0 && slot < a.n_sens) sensor_deposit(a.sens[slot], cache, slot, i, s.hit_local, I, lam);
             p = s.hit_global; d = s.new_dir; I = I * s.mod;
             if (a.hit_seq) a.hit_seq[i * NB + nb] = (unsigned char)win;
         }
@@ -335,6 +392,7 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
         store3(a.opos, i, p); store3(a.odir, i, d);
         a.ointen[i] = I;
     }
+    img_cache_flush(cache, a.sens);
 }
 
 // ============================================================================================
@@ -526,12 +584,14 @@ inline int grid_for(long long n, int blocks_per_sm) {
     return (int)g;
 }
 
+inline size_t fwd_smem(int S, int L) { return ((smem_table_bytes(S, L) + 15) / 16) * 16 + img_cache_bytes(); }
+
 inline size_t bwd_smem(int S, int L) {
     return ((smem_table_bytes(S, L) + 15) / 16) * 16 + sizeof(float) * ((size_t)S * RTT_ROW_G + (size_t)L * S * 2);
 }
 
 cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
-    RTT_NAME(k_trace_seq_fwd)<<<grid_for(a.n, 8), kThreads, smem_table_bytes(a.tab.S, a.tab.L), st>>>(a);
+    RTT_NAME(k_trace_seq_fwd)<<<grid_for(a.n, 8), kThreads, fwd_smem(a.tab.S, a.tab.L), st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t RTT_NAME(launch_seq_bwd)(const SeqBwdArgs& a, cudaStream_t st) {
@@ -539,7 +599,7 @@ cudaError_t RTT_NAME(launch_seq_bwd)(const SeqBwdArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 cudaError_t RTT_NAME(launch_nonseq_fwd)(const NonseqFwdArgs& a, cudaStream_t st) {
-    RTT_NAME(k_trace_nonseq_fwd)<<<grid_for(a.n, 8), kThreads, smem_table_bytes(a.tab.S, a.tab.L), st>>>(a);
+    RTT_NAME(k_trace_nonseq_fwd)<<<grid_for(a.n, 8), kThreads, fwd_smem(a.tab.S, a.tab.L), st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t RTT_NAME(launch_nonseq_bwd)(const NonseqBwdArgs& a, cudaStream_t st) {
