@@ -129,7 +129,11 @@ int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float* in_
  * (first row wins ties, NaN distance anywhere = no hit); stop if none; interact }.
  *   hit_seq     : [n, nbounces] uint8, row index per executed bounce, 255 = none (may be NULL)
  *   n_hits      : [n] uint8 number of executed bounces (may be NULL)
- * Sensors: every sensor interaction is accumulated into the image; `record` keeps the LAST. */
+ * Sensors: every sensor interaction is accumulated into the image; `record` keeps the LAST.
+ * `mode` is accepted for symmetry but ignored: the non-sequential trace (and its adjoint) always
+ * run the EXACT arithmetic.  Whether a ray re-hits the surface it is leaving is decided by the
+ * reference's t > 1e-6 rule at the fp32 ulp of scene-scale coordinates, i.e. by its exact rounding
+ * sequence; FMA contraction or approximate division change hit sequences on ~20 % of the rays. */
 int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* in_intensity,
                          const float* in_wavelength,
                          float* out_pos, float* out_dir, float* out_intensity,

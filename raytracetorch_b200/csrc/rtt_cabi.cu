@@ -186,7 +186,8 @@ int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* 
         a.n_sens = n_sensors; a.nbounces = nbounces; a.n = n;                                          \
         return finish(rtt::NS::launch_nonseq_fwd_##NS(a, st));                                         \
     }
-    if (mode == RTT_MODE_EXACT) RTT_BODY(exact) else RTT_BODY(fast)
+    (void)mode;   /* one arithmetic only: see include/rtt_b200.h */
+    RTT_BODY(exact)
 #undef RTT_BODY
 }
 
@@ -215,7 +216,8 @@ int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float* 
         a.nbounces = nbounces; a.n = n;                                                                \
         return finish(rtt::NS::launch_nonseq_bwd_##NS(a, st));                                         \
     }
-    if (mode == RTT_MODE_EXACT) RTT_BODY(exact) else RTT_BODY(fast)
+    (void)mode;   /* one arithmetic only: see include/rtt_b200.h */
+    RTT_BODY(exact)
 #undef RTT_BODY
 }
 

@@ -24,21 +24,6 @@
 
 namespace rtt {
 
-// Separately rounded multiply / subtract that the compiler may NOT contract into an FMA, in
-// either variant.  Used for the discriminant b*b - 4ac only: when a ray starts ON a surface
-// (every non-sequential bounce does) c is O(ulp) and the reference's separately rounded
-// b*b - 4ac collapses to b*b exactly, which makes the near root exactly 0 and the t > 1e-6 rule
-// (geom/primitives.py:32) reject the self-intersection.  An FMA keeps the tiny -4ac term, the
-// near root becomes ~c/b != 0, and ~20 % of otherwise stable rays re-hit the surface they are
-// leaving (measured on the c5 fixture).  Keeping this one expression un-fused costs 1 FLOP.
-#if defined(__CUDA_ARCH__)
-RTT_HD float mul_rn(float a, float b) { return __fmul_rn(a, b); }
-RTT_HD float sub_rn(float a, float b) { return __fsub_rn(a, b); }
-#else
-inline float mul_rn(float a, float b) { volatile float m = a * b; return m; }
-inline float sub_rn(float a, float b) { volatile float m = a - b; return m; }
-#endif
-
 // Division / square root.  EXACT: IEEE (div.rn / sqrt.rn), like the reference's eager ops.  FAST
 // (RTT_APPROX, device only): MUFU approximations (rcp / sqrt .approx.ftz, <= 2 ulp), one reciprocal
 // shared by the three components of a vector; IEEE fp32 division costs ~10 issue slots plus a
@@ -66,13 +51,62 @@ enum {
     D_R2 = 44,        // radius**2               geom/primitives.py:161,214
     D_SB0SQ = 45,     // sb[0]**2                geom/bounded.py:64,157
     D_HB0SQ = 46,     // hb[0]**2                geom/spherics.py:44
-    DI_IDENT = 11     // bit0: Re == I, bit1: Rs == I (exact compare)
+    DI_IDENT = 11,    // bit0: Re == I, bit1: Rs == I (exact compare)
+    DI_OPCODE = 12    // index of the matching KStatic specialisation (RTT_ROW_SPECS), 0 = generic
+};
+
+// Row kinds that get straight-line code: X(opcode, surface, surface bound, shape rule, physics, ident).
+// These cover every row of the reference's lens / stop / sensor elements in the poses users
+// build them with (untilted, or tilted as a whole element); anything else runs the generic path.
+#define RTT_ROW_SPECS(X)                                                                             \
+    X(1, RTT_SURF_QUADRIC, RTT_BOUND_HALF, RTT_SHAPE_SPHERIC_FACE, RTT_PHYS_SNELL, 3)    /* lens face        */ \
+    X(2, RTT_SURF_QUADRIC, RTT_BOUND_HALF, RTT_SHAPE_SPHERIC_FACE, RTT_PHYS_SNELL, 2)    /* tilted lens face */ \
+    X(3, RTT_SURF_CYLINDER, RTT_BOUND_NONE, RTT_SHAPE_SPHERIC_EDGE, RTT_PHYS_BLOCK, 3)   /* inked lens edge  */ \
+    X(4, RTT_SURF_CYLINDER, RTT_BOUND_NONE, RTT_SHAPE_SPHERIC_EDGE, RTT_PHYS_BLOCK, 2)                          \
+    X(5, RTT_SURF_CYLINDER, RTT_BOUND_NONE, RTT_SHAPE_SPHERIC_EDGE, RTT_PHYS_SNELL, 3)   /* clear lens edge  */ \
+    X(6, RTT_SURF_QUADRIC_ZY, RTT_BOUND_HALF, RTT_SHAPE_CYL_FACE, RTT_PHYS_SNELL, 3)     /* cyl. lens face   */ \
+    X(7, RTT_SURF_QUADRIC_ZY, RTT_BOUND_HALF, RTT_SHAPE_CYL_FACE, RTT_PHYS_SNELL, 2)                            \
+    X(8, RTT_SURF_PLANE, RTT_BOUND_NONE, RTT_SHAPE_CYL_EDGE, RTT_PHYS_SNELL, 1)          /* cyl. lens side   */ \
+    X(9, RTT_SURF_PLANE, RTT_BOUND_NONE, RTT_SHAPE_CYL_EDGE, RTT_PHYS_SNELL, 0)                                 \
+    X(10, RTT_SURF_PLANE, RTT_BOUND_NONE, RTT_SHAPE_CYL_EDGE, RTT_PHYS_BLOCK, 1)                                \
+    X(11, RTT_SURF_PLANE, RTT_BOUND_NONE, RTT_SHAPE_CYL_EDGE, RTT_PHYS_BLOCK, 0)                                \
+    X(12, RTT_SURF_PLANE, RTT_BOUND_DISK, RTT_SHAPE_NONE, RTT_PHYS_APERTURE, 3)          /* circular stop    */ \
+    X(13, RTT_SURF_PLANE, RTT_BOUND_DISK, RTT_SHAPE_NONE, RTT_PHYS_TRANSMIT, 3)          /* disk sensor      */ \
+    X(14, RTT_SURF_PLANE, RTT_BOUND_RECT, RTT_SHAPE_NONE, RTT_PHYS_TRANSMIT, 3)          /* rect sensor      */ \
+    X(15, RTT_SURF_QUADRIC, RTT_BOUND_HALF_DISK, RTT_SHAPE_NONE, RTT_PHYS_REFLECT, 3)    /* spherical mirror */ \
+    X(16, RTT_SURF_PLANE, RTT_BOUND_NONE, RTT_SHAPE_POLY, RTT_PHYS_BLOCK, 1)             /* box face         */
+
+// ---- row-kind policies -----------------------------------------------------------------------
+// Every per-row function below is a template over a policy K that answers "what kind of row is
+// this?".  KDyn reads the kinds from the table row at run time (generic path: any scene the
+// compiler can flatten).  KStatic<...> fixes them at compile time, so the switches fold away and
+// a lens face, a lens edge, a stop, a sensor ... each become straight-line code; the kernels
+// dispatch once per row on an opcode computed when the table is staged (classify_row).
+struct KDyn {
+    static RTT_HD int surf(const struct RowDev& R);
+    static RTT_HD int bound(const struct RowDev& R);
+    static RTT_HD int shape(const struct RowDev& R);
+    static RTT_HD int phys(const struct RowDev& R);
+    static RTT_HD int ident(const struct RowDev& R);
+};
+template <int SURF, int BOUND, int SHAPE, int PHYS, int IDENT>
+struct KStatic {
+    static RTT_HD int surf(const struct RowDev&) { return SURF; }
+    static RTT_HD int bound(const struct RowDev&) { return BOUND; }
+    static RTT_HD int shape(const struct RowDev&) { return SHAPE; }
+    static RTT_HD int phys(const struct RowDev&) { return PHYS; }
+    static RTT_HD int ident(const struct RowDev&) { return IDENT; }
 };
 
 struct RowDev {
     float f[RTT_ROW_F];
     int32_t i[RTT_ROW_I];
 };
+RTT_HD int KDyn::surf(const RowDev& R) { return R.i[RTT_I_SURF]; }
+RTT_HD int KDyn::bound(const RowDev& R) { return R.i[RTT_I_BOUND]; }
+RTT_HD int KDyn::shape(const RowDev& R) { return R.i[RTT_I_SHAPE]; }
+RTT_HD int KDyn::phys(const RowDev& R) { return R.i[RTT_I_PHYS]; }
+RTT_HD int KDyn::ident(const RowDev& R) { return R.i[DI_IDENT]; }
 
 struct V3 { float x, y, z; };
 
@@ -84,7 +118,7 @@ RTT_HD V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
 // torch.sum(a*b, dim=1): products rounded, accumulated left to right
 RTT_HD float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 // p + t*d with t broadcast (geom/primitives.py:80-81)
-RTT_HD V3 along(V3 p, float t, V3 d) { return v3(p.x + mul_rn(t, d.x), p.y + mul_rn(t, d.y), p.z + mul_rn(t, d.z)); }
+RTT_HD V3 along(V3 p, float t, V3 d) { return v3(p.x + t * d.x, p.y + t * d.y, p.z + t * d.z); }
 
 RTT_HD float rtt_inf() { return INFINITY; }
 RTT_HD float rtt_nan() { return NAN; }
@@ -143,6 +177,13 @@ RTT_HD void prepare_row(RowDev& R) {
     if (ie) ident |= 1;
     if (is) ident |= 2;
     R.i[DI_IDENT] = ident;
+    int op = 0;
+#define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, IDENT)                                                    \
+    if (R.i[RTT_I_SURF] == SURF && R.i[RTT_I_BOUND] == BOUND && R.i[RTT_I_SHAPE] == SHAPE &&        \
+        R.i[RTT_I_PHYS] == PHYS && ident == IDENT) op = OP;
+    RTT_ROW_SPECS(RTT_X)
+#undef RTT_X
+    R.i[DI_OPCODE] = op;
 }
 
 // ---- poses ---------------------------------------------------------------------------------
@@ -158,9 +199,10 @@ RTT_HD V3 normalize12(V3 v, float* len_out) {
 }
 
 // ---- surface-level bounds (geom/bounded.py) ------------------------------------------------
+template <class K = KDyn>
 RTT_HD bool surface_in_bounds(const RowDev& R, V3 h) {
     const float* sb = R.f + RTT_F_SB;
-    switch (R.i[RTT_I_BOUND]) {
+    switch (K::bound(R)) {
         case RTT_BOUND_DISK:                                            // :60-64
             return (h.x * h.x + h.y * h.y) <= R.f[D_SB0SQ];
         case RTT_BOUND_RECT:                                            // :77-82
@@ -189,11 +231,12 @@ struct Roots {
     bool lin;
 };
 
+template <class K = KDyn>
 RTT_HD Roots solve_roots(const RowDev& R, V3 o, V3 d) {
     Roots q;
     q.n = 2; q.A = q.B = q.C = q.sq = 0.0f; q.lin = false;
     const float inf = rtt_inf();
-    switch (R.i[RTT_I_SURF]) {
+    switch (K::surf(R)) {
         case RTT_SURF_PLANE: {                                          // :124-136
             const float safe = (fabsf(d.z) < 1e-6f) ? 1e-8f : d.z;
             q.t1 = div_(-o.z, safe); q.t2 = inf; q.n = 1; q.B = safe;
@@ -202,7 +245,7 @@ RTT_HD Roots solve_roots(const RowDev& R, V3 o, V3 d) {
         case RTT_SURF_SPHERE: {                                         // :155-184 (a == 1 assumed)
             const float b = 2.0f * dot(o, d);
             const float cc = dot(o, o) - R.f[D_R2];
-            const float disc = sub_rn(mul_rn(b, b), mul_rn(4.0f, cc));
+            const float disc = b * b - 4.0f * cc;
             const bool ok = disc >= 0.0f;
             const float sq = sqrt_(ok ? disc : 0.0f);
             q.t1 = ok ? (-b - sq) * 0.5f : inf;        // x/2 == x*0.5 exactly
@@ -214,7 +257,7 @@ RTT_HD Roots solve_roots(const RowDev& R, V3 o, V3 d) {
             const float A = d.x * d.x + d.y * d.y;
             const float B = 2.0f * (o.x * d.x + o.y * d.y);
             const float Cq = (o.x * o.x + o.y * o.y) - R.f[D_R2];
-            const float disc = sub_rn(mul_rn(B, B), mul_rn(mul_rn(4.0f, A), Cq));
+            const float disc = B * B - (4.0f * A) * Cq;
             const bool ok = disc >= 0.0f;
             const float sq = sqrt_(fabsf(disc));
             const float den = 2.0f * A;
@@ -227,7 +270,7 @@ RTT_HD Roots solve_roots(const RowDev& R, V3 o, V3 d) {
             const float c = R.f[RTT_F_C], c1k = R.f[D_C1K];
             const float tc = 2.0f * c, tc1k = 2.0f * c1k;
             float A, B, Cq;
-            if (R.i[RTT_I_SURF] == RTT_SURF_QUADRIC) {
+            if (K::surf(R) == RTT_SURF_QUADRIC) {
                 A = c * (d.x * d.x + d.y * d.y) + c1k * (d.z * d.z);
                 B = (tc * (o.x * d.x + o.y * d.y) + (tc1k * o.z) * d.z) - 2.0f * d.z;
                 Cq = (c * (o.x * o.x + o.y * o.y) + c1k * (o.z * o.z)) - 2.0f * o.z;
@@ -236,7 +279,7 @@ RTT_HD Roots solve_roots(const RowDev& R, V3 o, V3 d) {
                 B = (tc * (o.y * d.y) + (tc1k * o.z) * d.z) - 2.0f * d.z;
                 Cq = (c * (o.y * o.y) + c1k * (o.z * o.z)) - 2.0f * o.z;
             }
-            const float disc = sub_rn(mul_rn(B, B), mul_rn(mul_rn(4.0f, A), Cq));
+            const float disc = B * B - (4.0f * A) * Cq;
             const bool ok = disc >= 0.0f;
             const bool lin = fabsf(A) < 1e-6f;
             const float sq = sqrt_(fabsf(disc));
@@ -256,19 +299,20 @@ RTT_HD Roots solve_roots(const RowDev& R, V3 o, V3 d) {
 // Smallest admissible root.  Unbounded: geom/primitives.py:28-36; bounded: geom/bounded.py:20-36.
 // NaN propagates like torch.min (a NaN candidate that was not masked makes the result NaN).
 // *which = index of the selected root (0/1).
+template <class K = KDyn>
 RTT_HD float select_root(const RowDev& R, const Roots& q, V3 o, V3 d, int* which) {
     const float inf = rtt_inf();
     float t1 = q.t1, t2 = q.t2;
-    if (R.i[RTT_I_BOUND] == RTT_BOUND_NONE) {
+    if (K::bound(R) == RTT_BOUND_NONE) {
         if (t1 <= 1e-6f) t1 = inf;
         if (q.n == 2 && t2 <= 1e-6f) t2 = inf;
     } else {
         const bool inv = R.i[RTT_I_INVERT] != 0;
-        bool k1 = surface_in_bounds(R, along(o, t1, d));
+        bool k1 = surface_in_bounds<K>(R, along(o, t1, d));
         if (inv) k1 = !k1;
         if (t1 <= 1e-6f || !k1) t1 = inf;
         if (q.n == 2) {
-            bool k2 = surface_in_bounds(R, along(o, t2, d));
+            bool k2 = surface_in_bounds<K>(R, along(o, t2, d));
             if (inv) k2 = !k2;
             if (t2 <= 1e-6f || !k2) t2 = inf;
         }
@@ -288,10 +332,11 @@ RTT_HD float sag_at(float c, float h, float tz) {                       // geom/
     return div_(c * h2, 1.0f + sqrt_(term)) + tz;
 }
 
+template <class K = KDyn>
 RTT_HD bool shape_in_bounds(const RowDev* rows, int r, V3 h) {
     const RowDev& R = rows[r];
     const float* hb = R.f + RTT_F_HB;
-    switch (R.i[RTT_I_SHAPE]) {
+    switch (K::shape(R)) {
         case RTT_SHAPE_SPHERIC_FACE:                                    // geom/spherics.py:40-46
             return (h.x * h.x + h.y * h.y) <= R.f[D_HB0SQ];
         case RTT_SHAPE_SPHERIC_EDGE:                                    // geom/spherics.py:34-39
@@ -300,7 +345,7 @@ RTT_HD bool shape_in_bounds(const RowDev* rows, int r, V3 h) {
         case RTT_SHAPE_CYL_EDGE: {                                      // geom/cylindrics.py:23-55
             const bool ap = (h.x <= hb[1] + 1e-5f) && (h.x >= hb[0] - 1e-5f) &&
                             (h.y <= hb[3] + 1e-5f) && (h.y >= hb[2] - 1e-5f);
-            if (R.i[RTT_I_SHAPE] == RTT_SHAPE_CYL_FACE) return ap;
+            if (K::shape(R) == RTT_SHAPE_CYL_FACE) return ap;
             const float zf = sag_at(hb[4], h.y, hb[5]);
             const float zb = sag_at(hb[6], h.y, hb[7]);
             return (h.z >= zf + 1e-4f) && (h.z <= zb - 1e-4f) && ap;
@@ -330,10 +375,11 @@ struct Frames {
     V3 o, dd;      // surface frame
 };
 
+template <class K = KDyn>
 RTT_HD Frames to_frames(const RowDev& R, V3 p, V3 d) {
     Frames F;
-    const int ident = R.i[DI_IDENT];
-    if (R.i[RTT_I_SHAPE] == RTT_SHAPE_NONE) {                           // geom/primitives.py:49
+    const int ident = K::ident(R);
+    if (K::shape(R) == RTT_SHAPE_NONE) {                           // geom/primitives.py:49
         F.pe = p; F.de = d; F.den = d; F.len = 1.0f;
     } else {                                                            // geom/shape.py:37-38
         F.pe = rot_fwd(p - ld3(R.f + RTT_F_TE), R.f + RTT_F_RE, ident & 1);
@@ -347,29 +393,30 @@ RTT_HD Frames to_frames(const RowDev& R, V3 p, V3 d) {
 
 // Distance with every validity rule; returns true iff `t < inf` and valid.
 // WITH_SHAPE=false is the Element.forward variant (geom/shape.py:61-87: no shape-level rule).
-template <bool WITH_SHAPE>
+template <bool WITH_SHAPE, class K = KDyn>
 RTT_HD bool intersect(const RowDev* rows, int r, V3 p, V3 d, Frames& F, Roots& q, float& t, int& which) {
     const RowDev& R = rows[r];
-    F = to_frames(R, p, d);
-    q = solve_roots(R, F.o, F.dd);
-    t = select_root(R, q, F.o, F.dd, &which);
+    F = to_frames<K>(R, p, d);
+    q = solve_roots<K>(R, F.o, F.dd);
+    t = select_root<K>(R, q, F.o, F.dd, &which);
     bool valid = t < rtt_inf();                                         // false for NaN
-    if (WITH_SHAPE && valid && R.i[RTT_I_SHAPE] != RTT_SHAPE_NONE) {
-        valid = shape_in_bounds(rows, r, along(F.pe, t, F.de));         // un-normalised de: shape.py:47
+    if (WITH_SHAPE && valid && K::shape(R) != RTT_SHAPE_NONE) {
+        valid = shape_in_bounds<K>(rows, r, along(F.pe, t, F.de));         // un-normalised de: shape.py:47
     }
     return valid;
 }
 
 // ---- normals (geom/primitives.py:138-143, 186-187, 233-241, 330-343, 378-395) ---------------
+template <class K = KDyn>
 RTT_HD V3 normal_local(const RowDev& R, V3 h, float* len_out) {
     *len_out = 1.0f;
-    switch (R.i[RTT_I_SURF]) {
+    switch (K::surf(R)) {
         case RTT_SURF_PLANE: return v3(0.0f, 0.0f, 1.0f);
         case RTT_SURF_SPHERE: return div3(h, R.f[RTT_F_RADIUS]);
         case RTT_SURF_CYLINDER: { const V3 q = div3(v3(h.x, h.y, 0.0f), R.f[RTT_F_RADIUS]); return v3(q.x, q.y, 0.0f); }
         default: {
             const float tc = 2.0f * R.f[RTT_F_C], tc1k = 2.0f * R.f[D_C1K];
-            const float nx = (R.i[RTT_I_SURF] == RTT_SURF_QUADRIC) ? tc * h.x : 0.0f;
+            const float nx = (K::surf(R) == RTT_SURF_QUADRIC) ? tc * h.x : 0.0f;
             const float ny = tc * h.y;
             const float nz = tc1k * h.z - 2.0f;
             const float len = norm3(nx, ny, nz);
@@ -380,18 +427,20 @@ RTT_HD V3 normal_local(const RowDev& R, V3 h, float* len_out) {
     }
 }
 
+template <class K = KDyn>
 RTT_HD V3 normal_global(const RowDev& R, V3 nl) {
-    const int ident = R.i[DI_IDENT];
+    const int ident = K::ident(R);
     V3 n = rot_bwd(nl, R.f + RTT_F_RS, ident & 2);
-    if (R.i[RTT_I_SHAPE] != RTT_SHAPE_NONE) n = rot_bwd(n, R.f + RTT_F_RE, ident & 1);
+    if (K::shape(R) != RTT_SHAPE_NONE) n = rot_bwd(n, R.f + RTT_F_RE, ident & 1);
     return n;
 }
 
 // ---- physics (phys/std.py, phys/filter.py) --------------------------------------------------
 // mu_enter = ior_out/ior_in, mu_exit = ior_in/ior_out (per wavelength when a LUT is present).
+template <class K = KDyn>
 RTT_HD V3 physics(const RowDev& R, V3 hl, V3 d, V3 n, float mu_enter, float mu_exit, float* mod) {
     *mod = 1.0f;
-    switch (R.i[RTT_I_PHYS]) {
+    switch (K::phys(R)) {
         case RTT_PHYS_BLOCK:                                            // std.py:243-254
             *mod = 0.0f;
             return v3(0.0f, 0.0f, 0.0f);
@@ -400,7 +449,7 @@ RTT_HD V3 physics(const RowDev& R, V3 hl, V3 d, V3 n, float mu_enter, float mu_e
             return v3(d.x - tw * n.x, d.y - tw * n.y, d.z - tw * n.z);
         }
         case RTT_PHYS_APERTURE: {                                       // filter.py:24-33
-            const float m = surface_in_bounds(R, hl) ? 1.0f : 0.0f;
+            const float m = surface_in_bounds<K>(R, hl) ? 1.0f : 0.0f;
             *mod = m;
             return v3(d.x * m, d.y * m, d.z * m);
         }
@@ -430,14 +479,15 @@ struct Step {
     float mod, t;
 };
 
+template <class K = KDyn>
 RTT_HD Step interact(const RowDev& R, const Frames& F, float t, V3 p, V3 d, float mu_enter, float mu_exit) {
     Step s;
     s.t = t;
     s.hit_local = along(F.o, t, F.dd);                                  // primitives.py:81
     float nlen;
-    s.normal = normal_global(R, normal_local(R, s.hit_local, &nlen));
+    s.normal = normal_global<K>(R, normal_local<K>(R, s.hit_local, &nlen));
     s.hit_global = along(p, t, d);                                      // shape.py:81 / primitives.py:80
-    s.new_dir = physics(R, s.hit_local, d, s.normal, mu_enter, mu_exit, &s.mod);
+    s.new_dir = physics<K>(R, s.hit_local, d, s.normal, mu_enter, mu_exit, &s.mod);
     return s;
 }
 

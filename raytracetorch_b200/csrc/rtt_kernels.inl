@@ -164,6 +164,26 @@ __device__ __forceinline__ void sensor_deposit(const SensorDev& sd, ImgCache c, 
 // Sequential trace, forward (scene/sequential.py:12-36)
 // ============================================================================================
 
+// One row of the sequential walk for one ray (scene/sequential.py:19-34), kinds fixed by K.
+template <class K>
+__device__ __forceinline__ void seq_row(const SmemTable& T, int S, int L, int r, int lam, long long i,
+                                        const SeqFwdArgs& a, ImgCache cache, V3& p, V3& d, float& I,
+                                        unsigned long long& mask) {
+    Frames F; Roots q; float t; int which;
+    if (!intersect<true, K>(T.rows, r, p, d, F, q, t, which)) return;
+    const RowDev& R = T.rows[r];
+    float mu_enter = 0.0f, mu_exit = 0.0f;
+    if (K::phys(R) == RTT_PHYS_SNELL) {
+        const Ior io = row_ior(T, S, L, r, lam);
+        mu_enter = io.mu_enter; mu_exit = io.mu_exit;
+    }
+    const Step s = interact<K>(R, F, t, p, d, mu_enter, mu_exit);
+    const int slot = R.i[RTT_I_SENSOR];
+    if (slot >= 0 && slot < a.n_sens) sensor_deposit(a.sens[slot], cache, slot, i, s.hit_local, I, lam);
+    p = s.hit_global; d = s.new_dir; I = I * s.mod;
+    mask |= 1ull << r;
+}
+
 __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_fwd)(const __grid_constant__ SeqFwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemTable T = carve(smem_raw, a.tab.S, a.tab.L);
@@ -180,15 +200,13 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_fwd)(const __gr
         const int lam = (L > 0) ? wavelength_index(T, L, a.wav[i]) : 0;
         unsigned long long mask = 0ull;
         for (int r = 0; r < S; ++r) {
-            Frames F; Roots q; float t; int which;
-            if (!intersect<true>(T.rows, r, p, d, F, q, t, which)) continue;
-            const RowDev& R = T.rows[r];
-            const Ior io = row_ior(T, S, L, r, lam);
-            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
-            const int slot = R.i[RTT_I_SENSOR];
-            if (slot >= 0 && slot < a.n_sens) sensor_deposit(a.sens[slot], cache, slot, i, s.hit_local, I, lam);
-            p = s.hit_global; d = s.new_dir; I = I * s.mod;
-            mask |= 1ull << r;
+            switch (T.rows[r].i[DI_OPCODE]) {                           // warp-uniform
+#define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, IDENT)                                                    \
+                case OP: seq_row<KStatic<SURF, BOUND, SHAPE, PHYS, IDENT>>(T, S, L, r, lam, i, a, cache, p, d, I, mask); break;
+                RTT_ROW_SPECS(RTT_X)
+#undef RTT_X
+                default: seq_row<KDyn>(T, S, L, r, lam, i, a, cache, p, d, I, mask); break;
+            }
         }
         store3(a.opos, i, p); store3(a.odir, i, d);
         a.ointen[i] = I;
@@ -371,7 +389,14 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
             bool poisoned = false;
             for (int r = 0; r < S; ++r) {
                 Frames F; Roots q; float t; int which;
-                const bool valid = intersect<true>(T.rows, r, p, d, F, q, t, which);
+                bool valid;
+                switch (T.rows[r].i[DI_OPCODE]) {                       // warp-uniform
+#define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, IDENT)                                                    \
+                    case OP: valid = intersect<true, KStatic<SURF, BOUND, SHAPE, PHYS, IDENT>>(T.rows, r, p, d, F, q, t, which); break;
+                    RTT_ROW_SPECS(RTT_X)
+#undef RTT_X
+                    default: valid = intersect<true, KDyn>(T.rows, r, p, d, F, q, t, which); break;
+                }
                 // rows of a Shape report inf when invalid; bare surfaces may report NaN
                 if (T.rows[r].i[RTT_I_SHAPE] == RTT_SHAPE_NONE && is_nan(t)) poisoned = true;
                 if (valid && t < best) { best = t; win = r; }

@@ -106,23 +106,20 @@ def test_nonseq_exact_matches_reference_on_stable_rays(run_exact, name):
     _assert_close_noise_aware(h, d, name, rows=stable)
 
 
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", NONSEQ)
-def test_nonseq_fast_is_statistically_equivalent(run_fast, name):
-    """FAST arithmetic (FMA contraction) cannot reproduce the rounding coincidences that decide
-    whether a ray re-hits the surface it is leaving (t > 1e-6 rule at fp32 ulp ~2e-6): paths of
-    individual rays differ, like the reference's own fp32 and fp64 runs differ.
-    What must hold: first-bounce winners identical, and the energy budget equal within 2 %."""
+def test_nonseq_always_runs_reference_rounding(name):
+    """The non-sequential entry point has ONE arithmetic: which surface a ray hits next depends on
+    the rounding coincidences that decide whether it re-hits the surface it is leaving (t > 1e-6 at
+    an fp32 ulp of ~2e-6), so FMA contraction / approximate division change hit sequences on ~20 %
+    of the rays.  rtt_trace_nonseq_* therefore ignore `mode` and always run the EXACT variant."""
+    from gpusim import GpuSim
     d = parity.load(name)
     nb = int(d["nbounces"])
-    h = run_fast.trace_nonseq(d["table_f"], d["table_i"], d["in_pos"], d["in_dir"], d["in_intensity"], nb)
-    hseq = h["seq"].astype(np.int64)
-    hseq[hseq == 255] = -1
-    np.testing.assert_array_equal(hseq[:, 0], d["f32_seq"][:, 0])
-    ref_disagree = (d["f32_seq"] != d["f64_seq"]).any(axis=1).mean()
-    ours_disagree = (hseq != d["f32_seq"]).any(axis=1).mean()
-    assert ours_disagree <= max(0.05, 1.5 * ref_disagree), (ours_disagree, ref_disagree)
-    alive_ref, alive_got = (d["f32_intensity"] > 0).mean(), (h["intensity"] > 0).mean()
-    assert abs(alive_ref - alive_got) <= 0.02 + 0.5 * abs(alive_ref - (d["f64_intensity"] > 0).mean())
+    a = GpuSim(0).trace_nonseq(d["table_f"], d["table_i"], d["in_pos"], d["in_dir"], d["in_intensity"], nb)
+    b = GpuSim(1).trace_nonseq(d["table_f"], d["table_i"], d["in_pos"], d["in_dir"], d["in_intensity"], nb)
+    for k in ("pos", "dir", "intensity", "seq", "nb"):
+        np.testing.assert_array_equal(a[k], b[k])
 
 
 @pytest.mark.parametrize("name", NONSEQ)
