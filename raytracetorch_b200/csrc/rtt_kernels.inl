@@ -109,18 +109,31 @@ __device__ __forceinline__ void store3(float* a, long long i, V3 v) { a[3 * i] =
 //      shared-memory CAS.  The cache is flushed with one global atomic per occupied slot when
 //      the persistent block has finished its rays.
 // Zero weights (dead rays that still cross the sensor) add nothing and are skipped.
-constexpr int kImgSlots = 1024;
-constexpr int kImgKeyBits = 28;        // key = sensor slot << 28 | flat bin index
+constexpr int kImgLog = 12;
+constexpr int kImgSlots = 1 << kImgLog;   // 4096 (bin, partial sum) pairs = 32 KB per block
+constexpr int kImgProbes = 4;             // linear probes before falling through to a global atomic
+constexpr int kImgMaxFails = 2 * kImgSlots;   // spread-out image: stop probing, go global directly
+constexpr int kImgKeyBits = 28;           // key = sensor slot << 28 | flat bin index
 
 struct ImgCache {
     int* tag;          // [kImgSlots], -1 = empty
     float* val;        // [kImgSlots]
+    int* fails;        // [1] probes that found no slot; the cache switches itself off beyond kImgMaxFails
 };
 
-__host__ __device__ inline size_t img_cache_bytes() { return (size_t)kImgSlots * 8; }
+__host__ __device__ inline size_t img_cache_bytes() { return (size_t)kImgSlots * 8 + 16; }
+
+__device__ __forceinline__ ImgCache img_cache_carve(unsigned char* base) {
+    ImgCache c;
+    c.tag = reinterpret_cast<int*>(base);
+    c.val = reinterpret_cast<float*>(c.tag + kImgSlots);
+    c.fails = reinterpret_cast<int*>(c.val + kImgSlots);
+    return c;
+}
 
 __device__ __forceinline__ void img_cache_init(ImgCache c) {
     for (int idx = threadIdx.x; idx < kImgSlots; idx += blockDim.x) { c.tag[idx] = -1; c.val[idx] = 0.0f; }
+    if (threadIdx.x == 0) *c.fails = 0;
 }
 
 __device__ __forceinline__ void img_cache_add(ImgCache c, float* image, int slot, int bin, float w) {
@@ -130,10 +143,17 @@ __device__ __forceinline__ void img_cache_add(ImgCache c, float* image, int slot
     float sum = 0.0f;
     for (unsigned rem = peers; rem; rem &= rem - 1) sum += __shfl_sync(peers, w, __ffs((int)rem) - 1);
     if ((int)(threadIdx.x & 31) != __ffs((int)peers) - 1) return;
-    const int s = (key ^ (key >> 10)) & (kImgSlots - 1);
-    const int old = atomicCAS(c.tag + s, -1, key);
-    if (old == -1 || old == key) atomicAdd(c.val + s, sum);
-    else atomicAdd(image + bin, sum);
+    if (*reinterpret_cast<volatile int*>(c.fails) < kImgMaxFails) {
+        int s = (int)(((unsigned)key * 2654435761u) >> (32 - kImgLog));
+#pragma unroll 1
+        for (int probe = 0; probe < kImgProbes; ++probe) {
+            const int old = atomicCAS(c.tag + s, -1, key);
+            if (old == -1 || old == key) { atomicAdd(c.val + s, sum); return; }
+            s = (s + 1) & (kImgSlots - 1);
+        }
+        atomicAdd(c.fails, 1);
+    }
+    atomicAdd(image + bin, sum);
 }
 
 __device__ __forceinline__ void img_cache_flush(ImgCache c, const SensorDev* sens) {
@@ -187,9 +207,7 @@ __device__ __forceinline__ void seq_row(const SmemTable& T, int S, int L, int r,
 __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_fwd)(const __grid_constant__ SeqFwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemTable T = carve(smem_raw, a.tab.S, a.tab.L);
-    ImgCache cache;
-    cache.tag = reinterpret_cast<int*>(smem_raw + ((smem_table_bytes(a.tab.S, a.tab.L) + 15) / 16) * 16);
-    cache.val = reinterpret_cast<float*>(cache.tag + kImgSlots);
+    ImgCache cache = img_cache_carve(smem_raw + ((smem_table_bytes(a.tab.S, a.tab.L) + 15) / 16) * 16);
     img_cache_init(cache);
     stage_table(a.tab, T);
     const int S = a.tab.S, L = a.tab.L;
@@ -369,9 +387,7 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_bwd)(const __gr
 __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const __grid_constant__ NonseqFwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemTable T = carve(smem_raw, a.tab.S, a.tab.L);
-    ImgCache cache;
-    cache.tag = reinterpret_cast<int*>(smem_raw + ((smem_table_bytes(a.tab.S, a.tab.L) + 15) / 16) * 16);
-    cache.val = reinterpret_cast<float*>(cache.tag + kImgSlots);
+    ImgCache cache = img_cache_carve(smem_raw + ((smem_table_bytes(a.tab.S, a.tab.L) + 15) / 16) * 16);
     img_cache_init(cache);
     stage_table(a.tab, T);
     const int S = a.tab.S, L = a.tab.L, NB = a.nbounces;
@@ -615,7 +631,15 @@ inline size_t bwd_smem(int S, int L) {
     return ((smem_table_bytes(S, L) + 15) / 16) * 16 + sizeof(float) * ((size_t)S * RTT_ROW_G + (size_t)L * S * 2);
 }
 
+// the forward kernels carry the 32 KB image cache next to the table: opt in above the 48 KB default
+template <class Kern>
+inline cudaError_t allow_smem(Kern kern, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
+    if (cudaError_t e = allow_smem(RTT_NAME(k_trace_seq_fwd), fwd_smem(a.tab.S, a.tab.L))) return e;
     RTT_NAME(k_trace_seq_fwd)<<<grid_for(a.n, 8), kThreads, fwd_smem(a.tab.S, a.tab.L), st>>>(a);
     return cudaGetLastError();
 }
@@ -624,6 +648,7 @@ cudaError_t RTT_NAME(launch_seq_bwd)(const SeqBwdArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 cudaError_t RTT_NAME(launch_nonseq_fwd)(const NonseqFwdArgs& a, cudaStream_t st) {
+    if (cudaError_t e = allow_smem(RTT_NAME(k_trace_nonseq_fwd), fwd_smem(a.tab.S, a.tab.L))) return e;
     RTT_NAME(k_trace_nonseq_fwd)<<<grid_for(a.n, 8), kThreads, fwd_smem(a.tab.S, a.tab.L), st>>>(a);
     return cudaGetLastError();
 }

@@ -9,6 +9,6 @@ $CMD > $OUT/plain_${WL}_$TAG.log 2>&1 || { echo "plain run failed"; tail -20 $OU
 cat $OUT/plain_${WL}_$TAG.log | tail -1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $OUT/launches_${WL}_$TAG.csv $CMD > $OUT/ncu_launches_${WL}_$TAG.log 2>&1
 echo "ncu launches exit $?"
-ncu --set full --clock-control none --import-source on -k regex:k_trace_ -s 4 -c 2 -f -o $OUT/prof_${WL}_$TAG $CMD > $OUT/ncu_full_${WL}_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_trace_ -s 4 -c 3 -f -o $OUT/prof_${WL}_$TAG $CMD > $OUT/ncu_full_${WL}_$TAG.log 2>&1
 echo "ncu full exit $?"
 ls -la $OUT | tail -8

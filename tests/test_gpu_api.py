@@ -50,8 +50,11 @@ def test_sequential_scene_simulate_matches_reference(rtt_ns, name):
         assert locs.shape[0] == d["f32_sensor0_loc"].shape[0]
         np.testing.assert_array_equal(w.cpu().numpy(), d["f32_sensor0_w"])
         live = d["f32_sensor0_w"] > 0
-        e = parity.vec_rel(locs.cpu().numpy()[live], d["f32_sensor0_loc"][live])
-        noise = parity.vec_rel(d["f32_sensor0_loc"], d["f64_sensor0_loc"].astype(np.float32))[live] \
+        # sensor-local coordinates are small numbers (a focused spot sits at ~0): "relative" means
+        # relative to the scene scale, i.e. to the global position of the same hit (|p| ~ 1e2)
+        scale = float(np.abs(d["f32_pos"]).max())
+        e = parity.vec_rel(locs.cpu().numpy()[live], d["f32_sensor0_loc"][live], floor=scale)
+        noise = parity.vec_rel(d["f32_sensor0_loc"], d["f64_sensor0_loc"].astype(np.float32), floor=scale)[live] \
             if d["f64_sensor0_loc"].shape == d["f32_sensor0_loc"].shape else np.zeros_like(e)
         assert np.all(e <= np.maximum(parity.TOL_POINT, np.maximum(16 * noise, 2 * noise.max(initial=0.0))))
 
