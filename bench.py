@@ -230,6 +230,8 @@ def run_gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device visible; this package has no CPU path "
                          "(use --impl reference for the CPU baseline)")
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
     rank, world, local = rdist.init_from_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

@@ -55,26 +55,26 @@ enum {
     DI_OPCODE = 12    // index of the matching KStatic specialisation (RTT_ROW_SPECS), 0 = generic
 };
 
-// Row kinds that get straight-line code: X(opcode, surface, surface bound, shape rule, physics, ident).
+// Row kinds that get straight-line code: X(opcode, surface, surface bound, shape rule, physics, ident, is-sensor).
 // These cover every row of the reference's lens / stop / sensor elements in the poses users
 // build them with (untilted, or tilted as a whole element); anything else runs the generic path.
-#define RTT_ROW_SPECS(X)                                                                             \
-    X(1, RTT_SURF_QUADRIC, RTT_BOUND_HALF, RTT_SHAPE_SPHERIC_FACE, RTT_PHYS_SNELL, 3)    /* lens face        */ \
-    X(2, RTT_SURF_QUADRIC, RTT_BOUND_HALF, RTT_SHAPE_SPHERIC_FACE, RTT_PHYS_SNELL, 2)    /* tilted lens face */ \
-    X(3, RTT_SURF_CYLINDER, RTT_BOUND_NONE, RTT_SHAPE_SPHERIC_EDGE, RTT_PHYS_BLOCK, 3)   /* inked lens edge  */ \
-    X(4, RTT_SURF_CYLINDER, RTT_BOUND_NONE, RTT_SHAPE_SPHERIC_EDGE, RTT_PHYS_BLOCK, 2)                          \
-    X(5, RTT_SURF_CYLINDER, RTT_BOUND_NONE, RTT_SHAPE_SPHERIC_EDGE, RTT_PHYS_SNELL, 3)   /* clear lens edge  */ \
-    X(6, RTT_SURF_QUADRIC_ZY, RTT_BOUND_HALF, RTT_SHAPE_CYL_FACE, RTT_PHYS_SNELL, 3)     /* cyl. lens face   */ \
-    X(7, RTT_SURF_QUADRIC_ZY, RTT_BOUND_HALF, RTT_SHAPE_CYL_FACE, RTT_PHYS_SNELL, 2)                            \
-    X(8, RTT_SURF_PLANE, RTT_BOUND_NONE, RTT_SHAPE_CYL_EDGE, RTT_PHYS_SNELL, 1)          /* cyl. lens side   */ \
-    X(9, RTT_SURF_PLANE, RTT_BOUND_NONE, RTT_SHAPE_CYL_EDGE, RTT_PHYS_SNELL, 0)                                 \
-    X(10, RTT_SURF_PLANE, RTT_BOUND_NONE, RTT_SHAPE_CYL_EDGE, RTT_PHYS_BLOCK, 1)                                \
-    X(11, RTT_SURF_PLANE, RTT_BOUND_NONE, RTT_SHAPE_CYL_EDGE, RTT_PHYS_BLOCK, 0)                                \
-    X(12, RTT_SURF_PLANE, RTT_BOUND_DISK, RTT_SHAPE_NONE, RTT_PHYS_APERTURE, 3)          /* circular stop    */ \
-    X(13, RTT_SURF_PLANE, RTT_BOUND_DISK, RTT_SHAPE_NONE, RTT_PHYS_TRANSMIT, 3)          /* disk sensor      */ \
-    X(14, RTT_SURF_PLANE, RTT_BOUND_RECT, RTT_SHAPE_NONE, RTT_PHYS_TRANSMIT, 3)          /* rect sensor      */ \
-    X(15, RTT_SURF_QUADRIC, RTT_BOUND_HALF_DISK, RTT_SHAPE_NONE, RTT_PHYS_REFLECT, 3)    /* spherical mirror */ \
-    X(16, RTT_SURF_PLANE, RTT_BOUND_NONE, RTT_SHAPE_POLY, RTT_PHYS_BLOCK, 1)             /* box face         */
+#define RTT_ROW_SPECS(X)                                                                                \
+    X(1, RTT_SURF_QUADRIC, RTT_BOUND_HALF, RTT_SHAPE_SPHERIC_FACE, RTT_PHYS_SNELL, 3, 0)    /* lens face        */ \
+    X(2, RTT_SURF_QUADRIC, RTT_BOUND_HALF, RTT_SHAPE_SPHERIC_FACE, RTT_PHYS_SNELL, 2, 0)    /* tilted lens face */ \
+    X(3, RTT_SURF_CYLINDER, RTT_BOUND_NONE, RTT_SHAPE_SPHERIC_EDGE, RTT_PHYS_BLOCK, 3, 0)   /* inked lens edge  */ \
+    X(4, RTT_SURF_CYLINDER, RTT_BOUND_NONE, RTT_SHAPE_SPHERIC_EDGE, RTT_PHYS_BLOCK, 2, 0)                          \
+    X(5, RTT_SURF_CYLINDER, RTT_BOUND_NONE, RTT_SHAPE_SPHERIC_EDGE, RTT_PHYS_SNELL, 3, 0)   /* clear lens edge  */ \
+    X(6, RTT_SURF_QUADRIC_ZY, RTT_BOUND_HALF, RTT_SHAPE_CYL_FACE, RTT_PHYS_SNELL, 3, 0)     /* cyl. lens face   */ \
+    X(7, RTT_SURF_QUADRIC_ZY, RTT_BOUND_HALF, RTT_SHAPE_CYL_FACE, RTT_PHYS_SNELL, 2, 0)                            \
+    X(8, RTT_SURF_PLANE, RTT_BOUND_NONE, RTT_SHAPE_CYL_EDGE, RTT_PHYS_SNELL, 1, 0)          /* cyl. lens side   */ \
+    X(9, RTT_SURF_PLANE, RTT_BOUND_NONE, RTT_SHAPE_CYL_EDGE, RTT_PHYS_SNELL, 0, 0)                                 \
+    X(10, RTT_SURF_PLANE, RTT_BOUND_NONE, RTT_SHAPE_CYL_EDGE, RTT_PHYS_BLOCK, 1, 0)                                \
+    X(11, RTT_SURF_PLANE, RTT_BOUND_NONE, RTT_SHAPE_CYL_EDGE, RTT_PHYS_BLOCK, 0, 0)                                \
+    X(12, RTT_SURF_PLANE, RTT_BOUND_DISK, RTT_SHAPE_NONE, RTT_PHYS_APERTURE, 3, 0)          /* circular stop    */ \
+    X(13, RTT_SURF_PLANE, RTT_BOUND_DISK, RTT_SHAPE_NONE, RTT_PHYS_TRANSMIT, 3, 1)          /* disk sensor      */ \
+    X(14, RTT_SURF_PLANE, RTT_BOUND_RECT, RTT_SHAPE_NONE, RTT_PHYS_TRANSMIT, 3, 1)          /* rect sensor      */ \
+    X(15, RTT_SURF_QUADRIC, RTT_BOUND_HALF_DISK, RTT_SHAPE_NONE, RTT_PHYS_REFLECT, 3, 0)    /* spherical mirror */ \
+    X(16, RTT_SURF_PLANE, RTT_BOUND_NONE, RTT_SHAPE_POLY, RTT_PHYS_BLOCK, 1, 0)             /* box face         */
 
 // ---- row-kind policies -----------------------------------------------------------------------
 // Every per-row function below is a template over a policy K that answers "what kind of row is
@@ -88,9 +88,11 @@ struct KDyn {
     static RTT_HD int shape(const struct RowDev& R);
     static RTT_HD int phys(const struct RowDev& R);
     static RTT_HD int ident(const struct RowDev& R);
+    static RTT_HD bool sensor(const struct RowDev& R);
 };
-template <int SURF, int BOUND, int SHAPE, int PHYS, int IDENT>
+template <int SURF, int BOUND, int SHAPE, int PHYS, int IDENT, int SENSOR = 0>
 struct KStatic {
+    static RTT_HD bool sensor(const struct RowDev&) { return SENSOR != 0; }
     static RTT_HD int surf(const struct RowDev&) { return SURF; }
     static RTT_HD int bound(const struct RowDev&) { return BOUND; }
     static RTT_HD int shape(const struct RowDev&) { return SHAPE; }
@@ -107,6 +109,7 @@ RTT_HD int KDyn::bound(const RowDev& R) { return R.i[RTT_I_BOUND]; }
 RTT_HD int KDyn::shape(const RowDev& R) { return R.i[RTT_I_SHAPE]; }
 RTT_HD int KDyn::phys(const RowDev& R) { return R.i[RTT_I_PHYS]; }
 RTT_HD int KDyn::ident(const RowDev& R) { return R.i[DI_IDENT]; }
+RTT_HD bool KDyn::sensor(const RowDev& R) { return R.i[RTT_I_SENSOR] >= 0; }
 
 struct V3 { float x, y, z; };
 
@@ -165,6 +168,11 @@ RTT_HD void prepare_row(RowDev& R) {
     R.f[D_R2] = R.f[RTT_F_RADIUS] * R.f[RTT_F_RADIUS];
     R.f[D_SB0SQ] = R.f[RTT_F_SB] * R.f[RTT_F_SB];
     R.f[D_HB0SQ] = R.f[RTT_F_HB] * R.f[RTT_F_HB];
+    if (R.i[RTT_I_SHAPE] == RTT_SHAPE_CYL_FACE || R.i[RTT_I_SHAPE] == RTT_SHAPE_CYL_EDGE) {
+        // geom/cylindrics.py:31-37: x_min-1e-5 <= x <= x_max+1e-5 (same fp32 sums, done once per row)
+        R.f[RTT_F_HB + 0] = R.f[RTT_F_HB + 0] - 1e-5f; R.f[RTT_F_HB + 1] = R.f[RTT_F_HB + 1] + 1e-5f;
+        R.f[RTT_F_HB + 2] = R.f[RTT_F_HB + 2] - 1e-5f; R.f[RTT_F_HB + 3] = R.f[RTT_F_HB + 3] + 1e-5f;
+    }
     int ident = 0;
     const float* Re = R.f + RTT_F_RE;
     const float* Rs = R.f + RTT_F_RS;
@@ -178,9 +186,9 @@ RTT_HD void prepare_row(RowDev& R) {
     if (is) ident |= 2;
     R.i[DI_IDENT] = ident;
     int op = 0;
-#define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, IDENT)                                                    \
+#define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR)                                            \
     if (R.i[RTT_I_SURF] == SURF && R.i[RTT_I_BOUND] == BOUND && R.i[RTT_I_SHAPE] == SHAPE &&        \
-        R.i[RTT_I_PHYS] == PHYS && ident == IDENT) op = OP;
+        R.i[RTT_I_PHYS] == PHYS && ident == IDENT && (R.i[RTT_I_SENSOR] >= 0) == (SENSOR != 0)) op = OP;
     RTT_ROW_SPECS(RTT_X)
 #undef RTT_X
     R.i[DI_OPCODE] = op;
@@ -343,8 +351,7 @@ RTT_HD bool shape_in_bounds(const RowDev* rows, int r, V3 h) {
             return (h.z >= hb[0]) && (h.z <= hb[1]);
         case RTT_SHAPE_CYL_FACE:
         case RTT_SHAPE_CYL_EDGE: {                                      // geom/cylindrics.py:23-55
-            const bool ap = (h.x <= hb[1] + 1e-5f) && (h.x >= hb[0] - 1e-5f) &&
-                            (h.y <= hb[3] + 1e-5f) && (h.y >= hb[2] - 1e-5f);
+            const bool ap = (h.x <= hb[1]) && (h.x >= hb[0]) && (h.y <= hb[3]) && (h.y >= hb[2]);   // slack pre-added
             if (K::shape(R) == RTT_SHAPE_CYL_FACE) return ap;
             const float zf = sag_at(hb[4], h.y, hb[5]);
             const float zb = sag_at(hb[6], h.y, hb[7]);
@@ -430,7 +437,9 @@ RTT_HD V3 normal_local(const RowDev& R, V3 h, float* len_out) {
 template <class K = KDyn>
 RTT_HD V3 normal_global(const RowDev& R, V3 nl) {
     const int ident = K::ident(R);
-    V3 n = rot_bwd(nl, R.f + RTT_F_RS, ident & 2);
+    // plane: nl == (0,0,1), so nl @ Rs^T is the third column of Rs (the FMA chain adds exact zeros)
+    V3 n = (K::surf(R) == RTT_SURF_PLANE && !(ident & 2)) ? v3(R.f[RTT_F_RS + 2], R.f[RTT_F_RS + 5], R.f[RTT_F_RS + 8])
+                                                           : rot_bwd(nl, R.f + RTT_F_RS, ident & 2);
     if (K::shape(R) != RTT_SHAPE_NONE) n = rot_bwd(n, R.f + RTT_F_RE, ident & 1);
     return n;
 }

@@ -188,7 +188,7 @@ __device__ __forceinline__ void sensor_deposit(const SensorDev& sd, ImgCache c, 
 template <class K>
 __device__ __forceinline__ void seq_row(const SmemTable& T, int S, int L, int r, int lam, long long i,
                                         const SeqFwdArgs& a, ImgCache cache, V3& p, V3& d, float& I,
-                                        unsigned long long& mask) {
+                                        unsigned long long& mask, unsigned long long bit) {
     Frames F; Roots q; float t; int which;
     if (!intersect<true, K>(T.rows, r, p, d, F, q, t, which)) return;
     const RowDev& R = T.rows[r];
@@ -198,10 +198,12 @@ __device__ __forceinline__ void seq_row(const SmemTable& T, int S, int L, int r,
         mu_enter = io.mu_enter; mu_exit = io.mu_exit;
     }
     const Step s = interact<K>(R, F, t, p, d, mu_enter, mu_exit);
-    const int slot = R.i[RTT_I_SENSOR];
-    if (slot >= 0 && slot < a.n_sens) sensor_deposit(a.sens[slot], cache, slot, i, s.hit_local, I, lam);
+    if (K::sensor(R)) {
+        const int slot = R.i[RTT_I_SENSOR];
+        if (slot >= 0 && slot < a.n_sens) sensor_deposit(a.sens[slot], cache, slot, i, s.hit_local, I, lam);
+    }
     p = s.hit_global; d = s.new_dir; I = I * s.mod;
-    mask |= 1ull << r;
+    mask |= bit;
 }
 
 __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_fwd)(const __grid_constant__ SeqFwdArgs a) {
@@ -216,14 +218,17 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_fwd)(const __gr
         V3 p = load3(a.pos, i), d = load3(a.dir, i);
         float I = a.inten[i];
         const int lam = (L > 0) ? wavelength_index(T, L, a.wav[i]) : 0;
-        unsigned long long mask = 0ull;
-        for (int r = 0; r < S; ++r) {
-            switch (T.rows[r].i[DI_OPCODE]) {                           // warp-uniform
-#define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, IDENT)                                                    \
-                case OP: seq_row<KStatic<SURF, BOUND, SHAPE, PHYS, IDENT>>(T, S, L, r, lam, i, a, cache, p, d, I, mask); break;
+        unsigned long long mask = 0ull, bit = 1ull;
+        int op_next = T.rows[0].i[DI_OPCODE];
+        for (int r = 0; r < S; ++r, bit += bit) {
+            const int op = op_next;                                     // fetched one row ahead: the
+            op_next = T.rows[(r + 1 < S) ? r + 1 : r].i[DI_OPCODE];     // LDS -> BRX latency is hidden
+            switch (op) {                                               // warp-uniform
+#define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR)                                            \
+                case OP: seq_row<KStatic<SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR>>(T, S, L, r, lam, i, a, cache, p, d, I, mask, bit); break;
                 RTT_ROW_SPECS(RTT_X)
 #undef RTT_X
-                default: seq_row<KDyn>(T, S, L, r, lam, i, a, cache, p, d, I, mask); break;
+                default: seq_row<KDyn>(T, S, L, r, lam, i, a, cache, p, d, I, mask, bit); break;
             }
         }
         store3(a.opos, i, p); store3(a.odir, i, d);
@@ -407,8 +412,8 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
                 Frames F; Roots q; float t; int which;
                 bool valid;
                 switch (T.rows[r].i[DI_OPCODE]) {                       // warp-uniform
-#define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, IDENT)                                                    \
-                    case OP: valid = intersect<true, KStatic<SURF, BOUND, SHAPE, PHYS, IDENT>>(T.rows, r, p, d, F, q, t, which); break;
+#define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR)                                            \
+                    case OP: valid = intersect<true, KStatic<SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR>>(T.rows, r, p, d, F, q, t, which); break;
                     RTT_ROW_SPECS(RTT_X)
 #undef RTT_X
                     default: valid = intersect<true, KDyn>(T.rows, r, p, d, F, q, t, which); break;
