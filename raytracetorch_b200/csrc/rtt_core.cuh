@@ -76,6 +76,18 @@ enum {
     X(15, RTT_SURF_QUADRIC, RTT_BOUND_HALF_DISK, RTT_SHAPE_NONE, RTT_PHYS_REFLECT, 3, 0)    /* spherical mirror */ \
     X(16, RTT_SURF_PLANE, RTT_BOUND_NONE, RTT_SHAPE_POLY, RTT_PHYS_BLOCK, 1, 0)             /* box face         */
 
+// Subset of RTT_ROW_SPECS that also gets a specialised ADJOINT (code size: the reverse sweep is ~3x
+// the forward interaction).  Absorbing rows (inked edges, box faces) kill the ray, so live-ray
+// gradients rarely cross them; they and every other kind use the generic adjoint.
+#define RTT_ROW_SPECS_ADJ(X)                                                                            \
+    X(1, RTT_SURF_QUADRIC, RTT_BOUND_HALF, RTT_SHAPE_SPHERIC_FACE, RTT_PHYS_SNELL, 3, 0)                           \
+    X(2, RTT_SURF_QUADRIC, RTT_BOUND_HALF, RTT_SHAPE_SPHERIC_FACE, RTT_PHYS_SNELL, 2, 0)                           \
+    X(6, RTT_SURF_QUADRIC_ZY, RTT_BOUND_HALF, RTT_SHAPE_CYL_FACE, RTT_PHYS_SNELL, 3, 0)                            \
+    X(7, RTT_SURF_QUADRIC_ZY, RTT_BOUND_HALF, RTT_SHAPE_CYL_FACE, RTT_PHYS_SNELL, 2, 0)                            \
+    X(12, RTT_SURF_PLANE, RTT_BOUND_DISK, RTT_SHAPE_NONE, RTT_PHYS_APERTURE, 3, 0)                                 \
+    X(13, RTT_SURF_PLANE, RTT_BOUND_DISK, RTT_SHAPE_NONE, RTT_PHYS_TRANSMIT, 3, 1)                                 \
+    X(14, RTT_SURF_PLANE, RTT_BOUND_RECT, RTT_SHAPE_NONE, RTT_PHYS_TRANSMIT, 3, 1)
+
 // ---- row-kind policies -----------------------------------------------------------------------
 // Every per-row function below is a template over a policy K that answers "what kind of row is
 // this?".  KDyn reads the kinds from the table row at run time (generic path: any scene the
@@ -546,19 +558,20 @@ RTT_HD V3 adj_mul_RT(V3 a, V3 gy, const float* R, bool ident, float* gR, bool wa
 // Produces d/d p, d/d d and accumulates the row's parameter gradients into G.
 // Intensity is handled by the caller (g_I_in = g_I_out * mod; mod is returned).
 // (ni, no) are the (ior_in, ior_out) this ray used (row values, or the wavelength LUT's).
+template <class K = KDyn>
 RTT_HD void interact_adjoint(const RowDev& R, V3 p, V3 d, float ni, float no, float mu_enter, float mu_exit,
                              V3 g_pos, V3 g_dir, V3 g_hl_up, V3 g_n_up, float g_t_up,
                              V3& g_p, V3& g_d, float& mod_out, RowGrad& G, int want) {
     // ---- recompute the forward pieces (same selections as the forward pass) ----
-    const Frames F = to_frames(R, p, d);
-    const Roots q = solve_roots(R, F.o, F.dd);
+    const Frames F = to_frames<K>(R, p, d);
+    const Roots q = solve_roots<K>(R, F.o, F.dd);
     int which;
-    const float t = select_root(R, q, F.o, F.dd, &which);
+    const float t = select_root<K>(R, q, F.o, F.dd, &which);
     const V3 hl = along(F.o, t, F.dd);
     float nlen;
-    const V3 nl = normal_local(R, hl, &nlen);
-    const int ident = R.i[DI_IDENT];
-    const bool has_shape = R.i[RTT_I_SHAPE] != RTT_SHAPE_NONE;
+    const V3 nl = normal_local<K>(R, hl, &nlen);
+    const int ident = K::ident(R);
+    const bool has_shape = K::shape(R) != RTT_SHAPE_NONE;
     const V3 n_e = rot_bwd(nl, R.f + RTT_F_RS, ident & 2);              // element-frame normal
     const V3 n = has_shape ? rot_bwd(n_e, R.f + RTT_F_RE, ident & 1) : n_e;
     const bool w_pose_e = (want & RTT_FLAG_GRAD_POSE_E) != 0;
@@ -572,12 +585,12 @@ RTT_HD void interact_adjoint(const RowDev& R, V3 p, V3 d, float ni, float no, fl
     float mod = 1.0f;
 
     // ---- physics ----
-    switch (R.i[RTT_I_PHYS]) {
+    switch (K::phys(R)) {
         case RTT_PHYS_BLOCK:
             mod = 0.0f;
             break;
         case RTT_PHYS_APERTURE: {
-            const float m = surface_in_bounds(R, hl) ? 1.0f : 0.0f;
+            const float m = surface_in_bounds<K>(R, hl) ? 1.0f : 0.0f;
             mod = m;
             g_d = g_d + m * g_dir;
             break;
@@ -640,7 +653,7 @@ RTT_HD void interact_adjoint(const RowDev& R, V3 p, V3 d, float ni, float no, fl
     const V3 g_nl = adj_mul_RT(nl, g_ne, R.f + RTT_F_RS, ident & 2, G.g + RTT_F_RS, w_pose_s);
 
     // ---- normal_local(hl) ----
-    switch (R.i[RTT_I_SURF]) {
+    switch (K::surf(R)) {
         case RTT_SURF_PLANE: break;
         case RTT_SURF_SPHERE: {
             const float rr = R.f[RTT_F_RADIUS];
@@ -657,7 +670,7 @@ RTT_HD void interact_adjoint(const RowDev& R, V3 p, V3 d, float ni, float no, fl
         default: {
             const float c = R.f[RTT_F_C], k = R.f[RTT_F_K];
             const float tc = 2.0f * c, tc1k = 2.0f * R.f[D_C1K];
-            const bool full = R.i[RTT_I_SURF] == RTT_SURF_QUADRIC;
+            const bool full = K::surf(R) == RTT_SURF_QUADRIC;
             const V3 raw = v3(full ? tc * hl.x : 0.0f, tc * hl.y, tc1k * hl.z - 2.0f);
             const float den = nlen + 1e-8f;
             // nl = -raw/den, den = |raw| + 1e-8
@@ -683,7 +696,7 @@ RTT_HD void interact_adjoint(const RowDev& R, V3 p, V3 d, float ni, float no, fl
 
     // ---- t = selected root ----
     const V3 o = F.o, dd = F.dd;
-    switch (R.i[RTT_I_SURF]) {
+    switch (K::surf(R)) {
         case RTT_SURF_PLANE: {
             const float safe = q.B;
             const float g_t_s = div_(g_t, safe);
@@ -724,7 +737,7 @@ RTT_HD void interact_adjoint(const RowDev& R, V3 p, V3 d, float ni, float no, fl
                 gC = -g_t * rcp_(2.0f * q.A * t + q.B);
                 gB = gC * t; gA = gB * t;
             }
-            const bool full = R.i[RTT_I_SURF] == RTT_SURF_QUADRIC;
+            const bool full = K::surf(R) == RTT_SURF_QUADRIC;
             const float ox = full ? o.x : 0.0f, dx = full ? dd.x : 0.0f;
             const float g_u = gA * (dx * dx + dd.y * dd.y) + gB * 2.0f * (ox * dx + o.y * dd.y) + gC * (ox * ox + o.y * o.y);
             const float g_v = gA * (dd.z * dd.z) + gB * 2.0f * (o.z * dd.z) + gC * (o.z * o.z);

@@ -292,6 +292,48 @@ __device__ __forceinline__ void flush_block_grads(const float* acc, int S, float
 
 struct Checkpoint { V3 p, d; };
 
+// Replay of one recorded interaction (no validity tests: the hit mask says it happened).
+template <class K>
+__device__ __forceinline__ void replay_row(const SmemTable& T, int S, int L, int r, int lam, V3& p, V3& d) {
+    const RowDev& R = T.rows[r];
+    const Frames F = to_frames<K>(R, p, d);
+    const Roots q = solve_roots<K>(R, F.o, F.dd);
+    int which;
+    const float t = select_root<K>(R, q, F.o, F.dd, &which);
+    float mu_enter = 0.0f, mu_exit = 0.0f;
+    if (K::phys(R) == RTT_PHYS_SNELL) {
+        const Ior io = row_ior(T, S, L, r, lam);
+        mu_enter = io.mu_enter; mu_exit = io.mu_exit;
+    }
+    const Step s = interact<K>(R, F, t, p, d, mu_enter, mu_exit);
+    p = s.hit_global; d = s.new_dir;
+}
+
+// Reverse step through one recorded interaction.
+template <class K>
+__device__ __forceinline__ void reverse_row(const SmemTable& T, int S, int L, int r, int lam, long long i,
+                                            const SeqBwdArgs& a, const Checkpoint& ck, V3& gp, V3& gd, float& gI,
+                                            RowGrad& G, int flags) {
+    const RowDev& R = T.rows[r];
+    Ior io;
+    io.ni = io.no = 1.0f; io.mu_enter = io.mu_exit = 1.0f;
+    if (K::phys(R) == RTT_PHYS_SNELL) io = row_ior(T, S, L, r, lam);
+    V3 g_hl = v3(0, 0, 0);
+    float g_w = 0.0f;
+    if (K::sensor(R)) {
+        const int slot = R.i[RTT_I_SENSOR];
+        if (slot >= 0 && slot < a.n_sens && a.g_record[slot]) {
+            const float4 gr = reinterpret_cast<const float4*>(a.g_record[slot])[i];
+            g_hl = v3(gr.x, gr.y, gr.z); g_w = gr.w;
+        }
+    }
+    V3 ngp, ngd; float mod;
+    interact_adjoint<K>(R, ck.p, ck.d, io.ni, io.no, io.mu_enter, io.mu_exit,
+                        gp, gd, g_hl, v3(0, 0, 0), 0.0f, ngp, ngd, mod, G, flags);
+    gp = ngp; gd = ngd;
+    gI = gI * mod + g_w;
+}
+
 __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_bwd)(const __grid_constant__ SeqBwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.tab.S, L = a.tab.L;
@@ -313,20 +355,23 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_bwd)(const __gr
             p = load3(a.pos, i); d = load3(a.dir, i);
             if (L > 0) lam = wavelength_index(T, L, a.wav[i]);
         }
-        // ---- forward replay over the recorded interactions ----
+        // ---- forward replay over the recorded interactions (row loop is warp-uniform) ----
         Checkpoint ck[RTT_MAX_ROWS];
         int nh = 0;
-        for (unsigned long long m = mask; m; m &= m - 1) {
-            const int r = __ffsll((long long)m) - 1;
-            ck[nh].p = p; ck[nh].d = d; ++nh;
-            const RowDev& R = T.rows[r];
-            const Frames F = to_frames(R, p, d);
-            const Roots q = solve_roots(R, F.o, F.dd);
-            int which;
-            const float t = select_root(R, q, F.o, F.dd, &which);
-            const Ior io = row_ior(T, S, L, r, lam);
-            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
-            p = s.hit_global; d = s.new_dir;
+        for (int r = 0; r < S; ++r) {
+            const bool hit = (mask >> r) & 1ull;
+            if (__ballot_sync(kFull, hit) == 0u) continue;
+            const int op = T.rows[r].i[DI_OPCODE];
+            if (hit) {
+                ck[nh].p = p; ck[nh].d = d; ++nh;
+                switch (op) {
+#define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR)                                            \
+                    case OP: replay_row<KStatic<SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR>>(T, S, L, r, lam, p, d); break;
+                    RTT_ROW_SPECS_ADJ(RTT_X)
+#undef RTT_X
+                    default: replay_row<KDyn>(T, S, L, r, lam, p, d); break;
+                }
+            }
         }
         // ---- reverse sweep ----
         V3 gp = v3(0, 0, 0), gd = v3(0, 0, 0);
@@ -341,23 +386,18 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_bwd)(const __gr
             if (__ballot_sync(kFull, hit) == 0u) continue;
             const RowDev& R = T.rows[r];
             const int flags = R.i[RTT_I_FLAGS];
+            const int op = R.i[DI_OPCODE];
             RowGrad G;
             zero(G);
             if (hit) {
                 --nh;
-                const Ior io = row_ior(T, S, L, r, lam);
-                V3 g_hl = v3(0, 0, 0);
-                float g_w = 0.0f;
-                const int slot = R.i[RTT_I_SENSOR];
-                if (slot >= 0 && slot < a.n_sens && a.g_record[slot]) {
-                    const float4 gr = reinterpret_cast<const float4*>(a.g_record[slot])[i];
-                    g_hl = v3(gr.x, gr.y, gr.z); g_w = gr.w;
+                switch (op) {
+#define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR)                                            \
+                    case OP: reverse_row<KStatic<SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR>>(T, S, L, r, lam, i, a, ck[nh], gp, gd, gI, G, flags); break;
+                    RTT_ROW_SPECS_ADJ(RTT_X)
+#undef RTT_X
+                    default: reverse_row<KDyn>(T, S, L, r, lam, i, a, ck[nh], gp, gd, gI, G, flags); break;
                 }
-                V3 ngp, ngd; float mod;
-                interact_adjoint(R, ck[nh].p, ck[nh].d, io.ni, io.no, io.mu_enter, io.mu_exit,
-                                 gp, gd, g_hl, v3(0, 0, 0), 0.0f, ngp, ngd, mod, G, flags);
-                gp = ngp; gd = ngd;
-                gI = gI * mod + g_w;
             }
             if (a.g_table && flags) {
                 if (L > 0 && (flags & RTT_FLAG_GRAD_IOR)) {
