@@ -215,6 +215,9 @@ RTT_HD V3 normalize12(V3 v, float* len_out) {
     const float s = norm3(v.x, v.y, v.z);
     const float den = fmaxf(s, 1e-12f);
     *len_out = s;
+    // v/1 == v and 0/den == 0 bit for bit (signed zeros included): skip the IEEE division, whose
+    // slow path these two operand patterns (unit directions, dead rays) would take every time
+    if (den == 1.0f || (v.x == 0.0f && v.y == 0.0f && v.z == 0.0f)) return v;
     return div3(v, den);
 }
 
@@ -281,8 +284,16 @@ RTT_HD Roots solve_roots(const RowDev& R, V3 o, V3 d) {
             const bool ok = disc >= 0.0f;
             const float sq = sqrt_(fabsf(disc));
             const float den = 2.0f * A;
-            q.t1 = ok ? div_(-B - sq, den) : inf;
-            q.t2 = ok ? div_(-B + sq, den) : inf;
+            if (den == 0.0f) {
+                // axis-parallel ray (every collimated bundle): x / +0 = +-inf, 0 / 0 = NaN, spelled out so
+                // the IEEE slow path is not taken; NaN => miss downstream exactly as in the reference
+                const float n1 = -B - sq, n2 = -B + sq;
+                q.t1 = ok ? (n1 > 0.0f ? inf : (n1 < 0.0f ? -inf : rtt_nan())) : inf;
+                q.t2 = ok ? (n2 > 0.0f ? inf : (n2 < 0.0f ? -inf : rtt_nan())) : inf;
+            } else {
+                q.t1 = ok ? div_(-B - sq, den) : inf;
+                q.t2 = ok ? div_(-B + sq, den) : inf;
+            }
             q.A = A; q.B = B; q.C = Cq; q.sq = sq;
             return q;
         }
@@ -378,6 +389,7 @@ RTT_HD bool shape_in_bounds(const RowDev* rows, int r, V3 h) {
                 const float* Tm = rows[m].f + RTT_F_TS;
                 const float lz = (Rm[6] * (h.x - Tm[0]) + Rm[7] * (h.y - Tm[1])) + Rm[8] * (h.z - Tm[2]);
                 ok = ok && (lz < 1e-4f);
+                if (!ok) break;
             }
             return ok;
         }
@@ -410,18 +422,27 @@ RTT_HD Frames to_frames(const RowDev& R, V3 p, V3 d) {
     return F;
 }
 
-// Distance with every validity rule; returns true iff `t < inf` and valid.
-// WITH_SHAPE=false is the Element.forward variant (geom/shape.py:61-87: no shape-level rule).
-template <bool WITH_SHAPE, class K = KDyn>
-RTT_HD bool intersect(const RowDev* rows, int r, V3 p, V3 d, Frames& F, Roots& q, float& t, int& which) {
+// Distance with the surface-level rules only; returns true iff `t < inf` (false for NaN).
+template <class K = KDyn>
+RTT_HD bool intersect_t(const RowDev* rows, int r, V3 p, V3 d, Frames& F, Roots& q, float& t, int& which) {
     const RowDev& R = rows[r];
     F = to_frames<K>(R, p, d);
     q = solve_roots<K>(R, F.o, F.dd);
     t = select_root<K>(R, q, F.o, F.dd, &which);
-    bool valid = t < rtt_inf();                                         // false for NaN
-    if (WITH_SHAPE && valid && K::shape(R) != RTT_SHAPE_NONE) {
-        valid = shape_in_bounds<K>(rows, r, along(F.pe, t, F.de));         // un-normalised de: shape.py:47
-    }
+    return t < rtt_inf();
+}
+// Shape-level rule of a hit at distance t (geom/shape.py:47-55); true for bare surfaces.
+template <class K = KDyn>
+RTT_HD bool shape_ok(const RowDev* rows, int r, const Frames& F, float t) {
+    if (K::shape(rows[r]) == RTT_SHAPE_NONE) return true;
+    return shape_in_bounds<K>(rows, r, along(F.pe, t, F.de));           // un-normalised de: shape.py:47
+}
+// Distance with every validity rule; returns true iff `t < inf` and valid.
+// WITH_SHAPE=false is the Element.forward variant (geom/shape.py:61-87: no shape-level rule).
+template <bool WITH_SHAPE, class K = KDyn>
+RTT_HD bool intersect(const RowDev* rows, int r, V3 p, V3 d, Frames& F, Roots& q, float& t, int& which) {
+    bool valid = intersect_t<K>(rows, r, p, d, F, q, t, which);
+    if (WITH_SHAPE && valid) valid = shape_ok<K>(rows, r, F, t);
     return valid;
 }
 

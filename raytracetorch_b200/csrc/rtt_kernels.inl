@@ -429,6 +429,17 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_bwd)(const __gr
 // Non-sequential trace, forward (scene/base.py:129-235)
 // ============================================================================================
 
+// One row of the nearest-hit search (scene/base.py:164-176).
+template <class K>
+__device__ __forceinline__ void nonseq_probe(const RowDev* rows, int r, V3 p, V3 d, float& best, int& win,
+                                             bool& poisoned) {
+    Frames F; Roots q; float t; int which;
+    const bool finite_t = intersect_t<K>(rows, r, p, d, F, q, t, which);
+    // rows of a Shape report inf when invalid; bare surfaces may report NaN, which poisons torch.min
+    if (K::shape(rows[r]) == RTT_SHAPE_NONE && is_nan(t)) poisoned = true;
+    if (finite_t && t < best && shape_ok<K>(rows, r, F, t)) { best = t; win = r; }
+}
+
 __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const __grid_constant__ NonseqFwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemTable T = carve(smem_raw, a.tab.S, a.tab.L);
@@ -449,18 +460,15 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
             int win = -1;
             bool poisoned = false;
             for (int r = 0; r < S; ++r) {
-                Frames F; Roots q; float t; int which;
-                bool valid;
+                // min over rows (base.py:169): a row can only become the winner with t < best, so the
+                // shape-level rule (the costly part for box faces and lens edges) is evaluated only then
                 switch (T.rows[r].i[DI_OPCODE]) {                       // warp-uniform
 #define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR)                                            \
-                    case OP: valid = intersect<true, KStatic<SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR>>(T.rows, r, p, d, F, q, t, which); break;
+                    case OP: nonseq_probe<KStatic<SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR>>(T.rows, r, p, d, best, win, poisoned); break;
                     RTT_ROW_SPECS(RTT_X)
 #undef RTT_X
-                    default: valid = intersect<true, KDyn>(T.rows, r, p, d, F, q, t, which); break;
+                    default: nonseq_probe<KDyn>(T.rows, r, p, d, best, win, poisoned); break;
                 }
-                // rows of a Shape report inf when invalid; bare surfaces may report NaN
-                if (T.rows[r].i[RTT_I_SHAPE] == RTT_SHAPE_NONE && is_nan(t)) poisoned = true;
-                if (valid && t < best) { best = t; win = r; }
             }
             if (poisoned || win < 0) break;
             Frames F; Roots q; float t; int which;
