@@ -73,6 +73,10 @@ def build_workload(name: str, device):
         els[4].set_image(512, 512)
         w.update(elements=els, sensor=els[4], source=("disk", 10.0, -5.0), wavelengths=None, rays=10 ** 8,
                  nonseq=True, nbounces=8, desc="C5 non-sequential mirror/lens/box/stop/sensor, 12 rows, 8 bounces")
+    elif name == "c3":
+        els = scenes.c1_singlet(ns, physical=True, grads=True)
+        w.update(elements=els, sensor=els[1], source=("disk", 5.0, -10.0), wavelengths=None, rays=10 ** 7,
+                 desc="C3 singlet optimisation step: SpotSizeLoss forward + adjoint + Adam, 4 rows, 1e7 rays/step")
     else:
         raise SystemExit(f"unknown workload {name}")
     return w
@@ -485,13 +489,137 @@ def run_gpu_arm(args):
         tdist.destroy_process_group()
 
 
+def run_c3(args):
+    """BASELINE config 3: the optimisation loop through the public API only —
+    bundle.sample (on device) -> SequentialScene.simulate -> SpotSizeLoss -> backward -> Adam.step."""
+    import raytracetorch_b200 as rtt
+    from raytracetorch_b200 import _cabi, dist as rdist, roofline as rf
+    import torch.distributed as tdist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; this package has no CPU path")
+    rank, world, local = rdist.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _cabi.load()
+    w = build_workload("c3", dev)
+    n = int(args.rays or w["rays"])
+    scene = rtt.scene.SequentialScene(w["elements"]).to(dev)
+    S = scene.table().n_rows
+    bundle = rtt.rays.CollimatedDisk(5.0, 0, device=dev, transform=rtt.geom.RayTransformBundle(
+        translation=[0.0, 0.0, -10.0]).to(dev))
+    goal = rtt.optim.SpotSizeLoss(w["sensor"], [bundle], N_rays=n)
+    params = [p for p in scene.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-5)
+    torch.manual_seed(100 + rank)
+    loss_host = torch.empty(1).pin_memory()
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = goal(scene)
+        loss.backward()
+        rdist.allreduce_scene_results([], params)
+        opt.step()
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    l0 = lib.launch_count()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    wall = 1e3 * (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+    ms = max(e0.elapsed_time(e1) / args.steps, wall)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = lib.launch_count() - l0
+    value = world * n * S / (ms / 1e3)
+    # adjoint kernel alone
+    tab = scene.table()
+    rays = bundle.sample(n)
+    fwd = torch.ops.rtt_b200.trace_seq_fwd(rays.pos, rays.dir, rays.intensity, None, tab.f.detach(), tab.i, None, None,
+                                           [0.0] * rtt.ops.SENSOR_CFG, True, rtt.ops.get_default_mode())
+    g_rec = torch.randn_like(fwd[4])
+    kt = []
+    for _ in range(max(args.steps, 3)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        torch.ops.rtt_b200.trace_seq_bwd(rays.pos, rays.dir, rays.intensity, None, fwd[3], None, None, None, g_rec,
+                                         tab.f.detach(), tab.i, None, None, False, True, rtt.ops.get_default_mode())
+        b.record()
+        torch.cuda.synchronize()
+        kt.append(a.elapsed_time(b))
+    k_ms = float(np.median(kt))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    bpr = rf.adjoint_bytes_per_ray(wavelength=False, records=1) - 28 - 28      # no upstream ray grads, none written
+    ach = n * bpr / (k_ms / 1e3) / 1e9
+    roof = dict(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, traffic=None,
+                kernel="k_trace_seq_bwd", kernel_ms=k_ms, bytes_per_ray=bpr,
+                peak_source="measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s")
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import trace_oracle as O          # CPU baseline only
+        n_cpu = min(args.cpu_rays, 1_000_000)
+        torch.set_num_threads(os.cpu_count() or 1)
+        els_c = build_workload("c3", "cpu")["elements"]
+        tabc = rtt.compile_elements(els_c)
+        pos, dirs, inten, _ = synth_bundle(w, n_cpu, "cpu", 5)
+        t0 = time.perf_counter()
+        o = O.trace_sequential(tabc.f, tabc.i_host, pos, dirs, inten)
+        m, hl, ww = o["sensor"][0]
+        act = ww > 0
+        xy, ww = hl[act, :2], ww[act]
+        W = ww.sum()
+        cx, cy = (xy[:, 0] * ww).sum() / W, (xy[:, 1] * ww).sum() / W
+        torch.sqrt(((xy[:, 0] - cx) ** 2 + (xy[:, 1] - cy) ** 2) * (ww / W)).sum().backward()
+        tc = time.perf_counter() - t0
+        cpu = dict(value=n_cpu * S / tc, unit=UNIT, cores=os.cpu_count(), kind="port",
+                   sample=f"one forward+backward step of {n_cpu} rays ({tc:.1f} s), eager torch oracle + autograd")
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                    data="synthetic",
+                    config=dict(workload=w["desc"], rays_per_gpu=n, rows=S, direction="forward+adjoint per step",
+                                l2="bundle (280 MB) larger than L2", api="SpotSizeLoss(sensor,[bundle],N)(scene); "
+                                "loss.backward(); Adam.step()"),
+                    clocks=clocks, gpu_launches=launches, roofline=roof,
+                    e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=4, ms_per_step=ms,
+                             note="same loop: the public API samples the bundle on the device (Bundle.sample, as in the "
+                                  "reference's own GPU flow), so a step has no host input; the loss scalar is read back"))
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        tdist.barrier()
+        tdist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c4", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--rays", type=float, default=0, help="rays per GPU (default: the workload's BASELINE size)")
     ap.add_argument("--cpu-rays", type=int, default=2_000_000, help="rays of the CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -502,6 +630,8 @@ def main():
     args.rays = int(args.rays)
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "c3":
+        run_c3(args)
     else:
         run_gpu_arm(args)
 

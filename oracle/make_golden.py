@@ -167,6 +167,55 @@ def gen_grad_case(ns, name):
     return data
 
 
+def gen_camera_case(ns):
+    """Camera.generate_rays (render/camera.py:39-72), 64x36 pixels, BASELINE config-4 geometry."""
+    cam = ns.render.Camera((0.0, 0.0, -200.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 6.0, 64, 36)
+    r = cam.generate_rays()
+    return dict(pos=r.pos.numpy(), dir=r.dir.numpy(), intensity=r.intensity.numpy())
+
+
+GOAL_SEED, GOAL_RAYS, GOAL_BOUNCES = 77, 2000, 6
+
+
+def goal_setup(ns):
+    """Scene + bundles of the goal fixtures (shared with tests/test_goals.py)."""
+    elements = scenes.c1_singlet(ns, physical=True, grads=True)
+    scene = ns.scene.Scene()
+    for e in elements:
+        scene.add_element(e)
+    scene.Nbounces = GOAL_BOUNCES
+    mk = lambda rid, rot: ns.rays.CollimatedDisk(5.0, rid, transform=ns.geom.RayTransformBundle(
+        translation=[0.0, 0.0, -10.0], rotation=rot))
+    bundles = [mk(0, None), mk(1, [0.02, 0.0, 0.0]), mk(2, [0.0, -0.03, 0.0])]
+    return scene, elements, bundles
+
+
+def gen_goal_case(ns):
+    """SpotSizeLoss / SpotTargetLoss (optim/goals.py) on the base Scene, loss and d loss / d c1, c2."""
+    data = {}
+    _scene, _els, bundles = goal_setup(ns)
+    torch.manual_seed(GOAL_SEED)
+    for k, b in enumerate(bundles):                   # the reference's own samples under this seed
+        r = b.sample(GOAL_RAYS)
+        data[f"bundle{k}_pos"], data[f"bundle{k}_dir"] = r.pos.numpy(), r.dir.numpy()
+    for name in ("spot_size", "spot_size_target", "spot_target"):
+        scene, elements, bundles = goal_setup(ns)
+        sensor = elements[1]
+        torch.manual_seed(GOAL_SEED)
+        if name == "spot_size":
+            loss = ns.optim.SpotSizeLoss(sensor, bundles, N_rays=GOAL_RAYS)(scene)
+        elif name == "spot_size_target":
+            loss = ns.optim.SpotSizeLoss(sensor, bundles, N_rays=GOAL_RAYS, target_xy=[0.1, -0.2])(scene)
+        else:
+            loss = ns.optim.SpotTargetLoss(sensor, torch.tensor([[0.0, 0.0], [0.0, 2.0], [3.0, 0.0]]))(
+                scene, bundles, N_rays=GOAL_RAYS)
+        loss.backward()
+        data[f"{name}_loss"] = np.array(loss.item())
+        for k in (0, 1):
+            data[f"{name}_g_c{k}"] = elements[0].shape.surfaces[k].c.grad.numpy().copy()
+    return data
+
+
 def main(argv):
     os.makedirs(OUT, exist_ok=True)
     ns = ref_namespace()
@@ -179,6 +228,11 @@ def main(argv):
         alive = (d["f32_intensity"] > 0).mean()
         print(f"{name:28s} rows={d['table_f'].shape[0]:2d} alive={alive:.3f} "
               f"sensor_hits={d.get('f32_sensor0_w', np.zeros(0)).shape[0]}")
+    if not wanted or "extras" in wanted:
+        np.savez_compressed(os.path.join(OUT, "extra_camera_rays.npz"), **gen_camera_case(ns))
+        g = gen_goal_case(ns)
+        np.savez_compressed(os.path.join(OUT, "extra_goals.npz"), **g)
+        print("extras:", {k: float(v) for k, v in g.items() if k.endswith("_loss")})
     for name in GRAD_CASES:
         if wanted and name not in wanted:
             continue

@@ -1,0 +1,157 @@
+"""Goals that drive forward + adjoint for lens optimisation (mirror of ``optim/goals.py``).
+
+``SpotTargetLoss`` (optim/goals.py:42-96) and ``SpotSizeLoss`` (:99-187) keep the reference's
+constructor signatures and formulas.  They call ``scene.simulate()`` with ``scene.rays`` set, which
+works for both scene classes here (the reference's own call raises for ``SequentialScene``,
+SURVEY section 0.7).  Differences are in execution only:
+
+* the fused kernels hand over one sensor record per ray plus a hit mask, so the weighted moments
+  are computed over the full bundle with masks — no boolean gather, no host synchronisation;
+* with ``torch.distributed`` initialised the moments (W, sum w x, sum w y) and the per-bundle sums
+  are all-reduced, so a bundle sharded over ranks gives the same loss on every rank; after
+  ``loss.backward()`` one ``dist.allreduce_scene_results(sensors, params)`` sums the per-shard
+  parameter gradients into the full gradient.
+
+``FocalLengthLoss`` works on the paraxial 5x5 matrices (no rays) and is outside this package's
+scope.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from .elements import Sensor
+from .rays import Bundle
+
+
+class Goal(nn.Module):
+    """Base class for optimisation goals (optim/goals.py:11-13)."""
+
+
+class _SumOverRanks(torch.autograd.Function):
+    """all_reduce(SUM) whose backward passes the cotangent through unchanged.
+
+    Every rank evaluates the SAME loss from the reduced moments, so the cotangent is identical on
+    all ranks; with an identity backward each rank's parameter gradient is its shard's partial
+    derivative, and the one SUM all-reduce of the gradients (dist.allreduce_scene_results) yields
+    the full gradient — no 1/world_size bookkeeping."""
+
+    @staticmethod
+    def forward(ctx, t):
+        import torch.distributed as dist
+        out = t.clone()
+        dist.all_reduce(out, op=dist.ReduceOp.SUM)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _dist_sum(t: torch.Tensor) -> torch.Tensor:
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return _SumOverRanks.apply(t)
+    return t
+
+
+def _sensor_hits(scene, sensor: Sensor):
+    """(xy [M,2], w [M]) with zero weight on rays that did not reach the sensor.
+
+    Fast path: the raw per-ray record of the latest fused trace (no compaction).  Fallback: the
+    reference's semantics on the hit lists / final rays (optim/goals.py:76-82)."""
+    tr = getattr(scene, "last_trace", None)
+    if tr is not None and tr.get("records") is not None and tr["records"].numel():
+        table = getattr(scene, "_last_table", None) or scene.table()
+        if sensor in table.sensors:
+            slot = table.sensors.index(sensor)
+            rec = tr["records"][slot]
+            if "hitmask" in tr:
+                hit = ((tr["hitmask"] >> table.sensor_rows[slot]) & 1).bool()
+            else:
+                hit = (tr["hit_seq"] == table.sensor_rows[slot]).any(dim=1)
+            return rec[:, :2], torch.where(hit, rec[:, 3], torch.zeros_like(rec[:, 3]))
+    if sensor.hitLocs:
+        locs, w, _ = sensor.getHitsTensors()
+        return locs[:, :2], w
+    return scene.rays.pos[:, :2], scene.rays.intensity
+
+
+def _place(scene, rays):
+    if hasattr(scene, "parameters"):
+        dev = next(iter(scene.parameters()), torch.zeros(1)).device
+        rays = rays.to(dev)
+    scene.rays = rays
+    return rays
+
+
+class SpotTargetLoss(Goal):
+    """Squared distance between each bundle's intensity centroid and a target (optim/goals.py:42-96)."""
+
+    def __init__(self, sensor: Sensor, target_xy: torch.Tensor):
+        super().__init__()
+        self.sensor = sensor
+        target_xy = torch.as_tensor(target_xy, dtype=torch.float32)
+        if target_xy.ndim == 1:
+            target_xy = target_xy.unsqueeze(0)
+        self.register_buffer("target_xy", target_xy)
+
+    def forward(self, scene, bundles: List[Bundle], N_rays: int = 128) -> torch.Tensor:
+        losses = []
+        for i, bundle in enumerate(bundles):
+            self.sensor.reset()
+            _place(scene, bundle.sample(N_rays))
+            scene.simulate()
+            xy, w = _sensor_hits(scene, self.sensor)
+            if w.shape[0] == 0:
+                continue
+            mom = _dist_sum(torch.stack([w.sum(), (xy[:, 0] * w).sum(), (xy[:, 1] * w).sum()]))
+            w_sum = mom[0].clamp(min=1e-12)
+            cx, cy = mom[1] / w_sum, mom[2] / w_sum
+            tidx = min(i, self.target_xy.shape[0] - 1)
+            tx, ty = self.target_xy[tidx, 0].to(xy.device), self.target_xy[tidx, 1].to(xy.device)
+            losses.append((cx - tx) ** 2 + (cy - ty) ** 2)
+        if not losses:
+            return torch.tensor(0.0)
+        return torch.stack(losses).mean()
+
+
+class SpotSizeLoss(Goal):
+    """Mean over bundles of  sum_i sqrt(((x_i-cx)^2 + (y_i-cy)^2) * w_i / W)  (optim/goals.py:99-187;
+    note: a sum of square roots, exactly as the reference writes it)."""
+
+    def __init__(self, sensor: Sensor, bundles: List[Bundle], N_rays: int = 128,
+                 target_xy: Optional[torch.Tensor] = None):
+        super().__init__()
+        self.sensor, self.bundles, self.N_rays = sensor, bundles, N_rays
+        if target_xy is not None:
+            target_xy = torch.as_tensor(target_xy, dtype=torch.float32)
+            if target_xy.ndim == 1:
+                target_xy = target_xy.unsqueeze(0).expand(len(bundles), 2)
+        self._target_xy = target_xy
+
+    def forward(self, scene) -> torch.Tensor:
+        losses = []
+        for i, bundle in enumerate(self.bundles):
+            self.sensor.reset()
+            _place(scene, bundle.sample(self.N_rays))
+            scene.simulate()
+            xy, w = _sensor_hits(scene, self.sensor)
+            active = w > 0                                  # optim/goals.py:165 (as a mask: no gather)
+            wa = torch.where(active, w, torch.zeros_like(w))
+            mom = _dist_sum(torch.stack([wa.sum(), (xy[:, 0] * wa).sum(), (xy[:, 1] * wa).sum()]))
+            w_sum = mom[0].clamp(min=1e-12)
+            if self._target_xy is not None:
+                tidx = min(i, self._target_xy.shape[0] - 1)
+                cx, cy = self._target_xy[tidx, 0].to(xy.device), self._target_xy[tidx, 1].to(xy.device)
+            else:
+                cx, cy = mom[1] / w_sum, mom[2] / w_sum
+            r2w = ((xy[:, 0] - cx) ** 2 + (xy[:, 1] - cy) ** 2) * (wa / w_sum)
+            # sqrt only where active: d sqrt(0) would poison the gradients of the masked rays
+            rms = torch.sqrt(torch.where(active, r2w, torch.ones_like(r2w)))
+            losses.append(_dist_sum(torch.where(active, rms, torch.zeros_like(rms)).sum()))
+        if not losses:
+            return torch.tensor(0.0)
+        return torch.stack(losses).mean()

@@ -103,7 +103,7 @@ class Scene(nn.Module):
                 sensor._pend(records[slot], hit_of_slot(slot), rays_before.id)
 
     def _trace(self, rays: Rays, nbounces: int):
-        table = self.table()
+        table = self._last_table = self.table()
         out = ops.trace_nonsequential(table, rays.pos, rays.dir, rays.intensity, nbounces, rays.wavelength,
                                       want_record=self.record_hits, mode=self.mode)
         self.last_trace = out
@@ -183,7 +183,7 @@ class SequentialScene(Scene):
             rays = self.rays
         if rays is None:
             return None
-        table = self.table()
+        table = self._last_table = self.table()
         out = ops.trace_sequential(table, rays.pos, rays.dir, rays.intensity, rays.wavelength,
                                    want_record=self.record_hits, mode=self.mode)
         self.last_trace = out

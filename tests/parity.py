@@ -27,6 +27,8 @@ def golden_names(prefix=None, grads=False):
     out = []
     for f in sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))):
         n = os.path.basename(f)[:-4]
+        if n.startswith("extra_"):
+            continue
         if n.startswith("grad_") != grads:
             continue
         if prefix and not n.startswith(prefix):
