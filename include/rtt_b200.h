@@ -142,13 +142,16 @@ int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* 
                          int32_t nbounces, int64_t n, int32_t mode, void* stream);
 
 /* Adjoint of rtt_trace_nonseq_fwd: replays the recorded hit sequence (no search), then
- * reverse sweep.  Same gradient conventions as rtt_trace_seq_bwd. */
+ * reverse sweep.  Same gradient conventions as rtt_trace_seq_bwd; g_record[slot] is the upstream
+ * gradient of that sensor's record, i.e. of the LAST interaction of the ray with that sensor. */
 int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float* in_intensity,
                          const float* in_wavelength, const uint8_t* hit_seq, int32_t nbounces,
                          const float* g_out_pos, const float* g_out_dir, const float* g_out_intensity,
+                         const float* const* g_record,
                          float* g_in_pos, float* g_in_dir, float* g_in_intensity,
                          float* g_table, float* g_lut,
-                         const rtt_table_t* table, int64_t n, int32_t mode, void* stream);
+                         const rtt_table_t* table, int32_t n_sensors,
+                         int64_t n, int32_t mode, void* stream);
 
 /* Element.intersectTest(rays) -> [n, K]              (elements/parent.py:30-42,
  * geom/shape.py:25-59, geom/primitives.py:38-57): distances of rows [row0, row0+k) with all

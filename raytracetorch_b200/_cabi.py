@@ -45,8 +45,8 @@ _SIGS = {
                           ct.POINTER(TableReq), ct.c_int32, ct.c_int64, ct.c_int32, _P],
     "rtt_trace_nonseq_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, ct.POINTER(TableReq), ct.POINTER(SensorReq),
                              ct.c_int32, ct.c_int32, ct.c_int64, ct.c_int32, _P],
-    "rtt_trace_nonseq_bwd": [_P, _P, _P, _P, _P, ct.c_int32, _P, _P, _P, _P, _P, _P, _P, _P,
-                             ct.POINTER(TableReq), ct.c_int64, ct.c_int32, _P],
+    "rtt_trace_nonseq_bwd": [_P, _P, _P, _P, _P, ct.c_int32, _P, _P, _P, ct.POINTER(_P), _P, _P, _P, _P, _P,
+                             ct.POINTER(TableReq), ct.c_int32, ct.c_int64, ct.c_int32, _P],
     "rtt_intersect_test": [_P, _P, _P, ct.POINTER(TableReq), ct.c_int32, ct.c_int32, ct.c_int64, ct.c_int32, _P],
     "rtt_surface_step_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, ct.POINTER(TableReq), ct.c_int32,
                              ct.c_int64, ct.c_int32, _P],

@@ -194,13 +194,16 @@ int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* 
 int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float* in_intensity,
                          const float* in_wavelength, const uint8_t* hit_seq, int32_t nbounces,
                          const float* g_out_pos, const float* g_out_dir, const float* g_out_intensity,
+                         const float* const* g_record,
                          float* g_in_pos, float* g_in_dir, float* g_in_intensity,
                          float* g_table, float* g_lut,
-                         const rtt_table_t* table, int64_t n, int32_t mode, void* stream) {
+                         const rtt_table_t* table, int32_t n_sensors,
+                         int64_t n, int32_t mode, void* stream) {
     if (int e = check_table(table)) return e;
     if (n == 0) return RTT_OK;   /* empty bundle: nothing to do, pointers may be NULL */
     if (n < 0 || !in_pos || !in_dir || !in_intensity || !hit_seq) return RTT_E_ARG;
     if (nbounces < 0 || nbounces > RTT_MAX_BOUNCES) return RTT_E_ARG;
+    if (n_sensors < 0 || n_sensors > RTT_MAX_SENSORS) return RTT_E_SENSOR;
     if (table->n_lut > 0 && !in_wavelength) return RTT_E_ARG;
     if (!have_device()) return RTT_E_NO_DEVICE;
     auto st = (cudaStream_t)stream;
@@ -210,10 +213,14 @@ int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float* 
         a.pos = in_pos; a.dir = in_dir; a.inten = in_intensity; a.wav = in_wavelength;                 \
         a.hit_seq = hit_seq;                                                                           \
         a.g_opos = g_out_pos; a.g_odir = g_out_dir; a.g_ointen = g_out_intensity;                      \
+        for (int s = 0; s < RTT_MAX_SENSORS; ++s) {                                                    \
+            a.g_record[s] = (g_record && s < n_sensors) ? g_record[s] : nullptr;                       \
+            if (a.g_record[s] && (reinterpret_cast<uintptr_t>(a.g_record[s]) & 15)) return RTT_E_ALIGN; \
+        }                                                                                              \
         a.g_pos = g_in_pos; a.g_dir = g_in_dir; a.g_inten = g_in_intensity;                            \
         a.g_table = g_table; a.g_lut = (table->n_lut > 0) ? g_lut : nullptr;                           \
         a.tab = make_table<rtt::NS::TableDev>(table);                                                  \
-        a.nbounces = nbounces; a.n = n;                                                                \
+        a.n_sens = n_sensors; a.nbounces = nbounces; a.n = n;                                          \
         return finish(rtt::NS::launch_nonseq_bwd_##NS(a, st));                                         \
     }
     (void)mode;   /* one arithmetic only: see include/rtt_b200.h */

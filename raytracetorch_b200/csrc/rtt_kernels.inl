@@ -527,6 +527,7 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_bwd)(const _
         V3 gp = a.g_opos ? load3(a.g_opos, i) : v3(0, 0, 0);
         V3 gd = a.g_odir ? load3(a.g_odir, i) : v3(0, 0, 0);
         float gI = a.g_ointen ? a.g_ointen[i] : 0.0f;
+        unsigned seen = 0u;      // sensor slots whose record gradient has been consumed (record = LAST hit)
         while (nh > 0) {
             --nh;
             const int r = rows_hit[nh];
@@ -535,10 +536,18 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_bwd)(const _
             const Ior io = row_ior(T, S, L, r, lam);
             RowGrad G;
             zero(G);
+            V3 g_hl = v3(0, 0, 0);
+            float g_w = 0.0f;
+            const int slot = R.i[RTT_I_SENSOR];
+            if (slot >= 0 && slot < a.n_sens && a.g_record[slot] && !((seen >> slot) & 1u)) {
+                seen |= 1u << slot;
+                const float4 gr = reinterpret_cast<const float4*>(a.g_record[slot])[i];
+                g_hl = v3(gr.x, gr.y, gr.z); g_w = gr.w;
+            }
             V3 ngp, ngd; float mod;
             interact_adjoint(R, ck[nh].p, ck[nh].d, io.ni, io.no, io.mu_enter, io.mu_exit,
-                             gp, gd, v3(0, 0, 0), v3(0, 0, 0), 0.0f, ngp, ngd, mod, G, flags);
-            gp = ngp; gd = ngd; gI = gI * mod;
+                             gp, gd, g_hl, v3(0, 0, 0), 0.0f, ngp, ngd, mod, G, flags);
+            gp = ngp; gd = ngd; gI = gI * mod + g_w;
             if (a.g_table && flags) {
                 if (L > 0 && (flags & RTT_FLAG_GRAD_IOR)) {
                     atomicAdd(acc_lut + ((size_t)lam * S + r) * 2, G.g[RTT_F_IOR_IN]);

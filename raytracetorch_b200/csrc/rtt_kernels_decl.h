@@ -65,10 +65,11 @@ struct NonseqBwdArgs {
     const float *pos, *dir, *inten, *wav;
     const unsigned char* hit_seq;
     const float *g_opos, *g_odir, *g_ointen;
+    const float* g_record[RTT_MAX_SENSORS];
     float *g_pos, *g_dir, *g_inten;
     float *g_table, *g_lut;
     TableDev tab;
-    int nbounces;
+    int n_sens, nbounces;
     long long n;
 };
 

@@ -215,6 +215,7 @@ def _(pos, dir, intensity, wavelength, table_f, table_i, lut, lut_w, sensor_cfg,
 def _trace_nonseq_bwd(pos: torch.Tensor, dir: torch.Tensor, intensity: torch.Tensor,
                       wavelength: Optional[torch.Tensor], hit_seq: torch.Tensor,
                       g_pos: Optional[torch.Tensor], g_dir: Optional[torch.Tensor], g_int: Optional[torch.Tensor],
+                      g_records: Optional[torch.Tensor],
                       table_f: torch.Tensor, table_i: torch.Tensor,
                       lut: Optional[torch.Tensor], lut_w: Optional[torch.Tensor],
                       need_rays: bool, need_table: bool, mode: int) -> List[torch.Tensor]:
@@ -228,16 +229,18 @@ def _trace_nonseq_bwd(pos: torch.Tensor, dir: torch.Tensor, intensity: torch.Ten
     gt = torch.zeros((S, C.ROW_G), dtype=torch.float32, device=dev) if need_table else pos.new_empty(0)
     has_lut = lut is not None and lut.numel() > 0
     gl = torch.zeros_like(lut) if (need_table and has_lut) else pos.new_empty(0)
+    ns = 0 if g_records is None else g_records.shape[0]
+    rec_arr = (ct.c_void_p * ns)(*[g_records[s].data_ptr() for s in range(ns)]) if ns else None
     req = _table_req(table_f, table_i, lut, lut_w)
     with torch.cuda.device(dev):
         lib.call("rtt_trace_nonseq_bwd", pos.data_ptr(), dir.data_ptr(), intensity.data_ptr(), _ptr(wavelength),
-                 hit_seq.data_ptr(), hit_seq.shape[1], _ptr(g_pos), _ptr(g_dir), _ptr(g_int),
-                 _ptr(gp), _ptr(gd), _ptr(gi), _ptr(gt), _ptr(gl), ct.byref(req), n, mode, _stream(pos))
+                 hit_seq.data_ptr(), hit_seq.shape[1], _ptr(g_pos), _ptr(g_dir), _ptr(g_int), rec_arr,
+                 _ptr(gp), _ptr(gd), _ptr(gi), _ptr(gt), _ptr(gl), ct.byref(req), ns, n, mode, _stream(pos))
     return [gp, gd, gi, gt, gl]
 
 
 @_trace_nonseq_bwd.register_fake
-def _(pos, dir, intensity, wavelength, hit_seq, g_pos, g_dir, g_int, table_f, table_i, lut, lut_w,
+def _(pos, dir, intensity, wavelength, hit_seq, g_pos, g_dir, g_int, g_records, table_f, table_i, lut, lut_w,
       need_rays, need_table, mode):
     e = pos.new_empty(0)
     return [torch.empty_like(pos) if need_rays else e, torch.empty_like(dir) if need_rays else e,
@@ -370,16 +373,18 @@ class _TraceNonseq(torch.autograd.Function):
         opos, odir, oint, seq, nh, records, images = outs
         ctx.save_for_backward(pos, dir_, intensity, wavelength, seq, table_f, table_i, lut, lut_w)
         ctx.mode = mode
-        ctx.mark_non_differentiable(seq, nh, records, images)
+        ctx.mark_non_differentiable(seq, nh, images)
         return opos, odir, oint, seq, nh, records, images
 
     @staticmethod
-    def backward(ctx, g_pos, g_dir, g_int, *_unused):
+    def backward(ctx, g_pos, g_dir, g_int, _g_seq, _g_nh, g_records, _g_images):
         pos, dir_, intensity, wavelength, seq, table_f, table_i, lut, lut_w = ctx.saved_tensors
         need_rays = any(ctx.needs_input_grad[:3])
         need_table = ctx.needs_input_grad[4] or ctx.needs_input_grad[6]
+        if g_records is not None and g_records.numel() == 0:
+            g_records = None
         gp, gd, gi, gt, gl = torch.ops.rtt_b200.trace_nonseq_bwd(
-            pos, dir_, intensity, wavelength, seq, _cg(g_pos), _cg(g_dir), _cg(g_int),
+            pos, dir_, intensity, wavelength, seq, _cg(g_pos), _cg(g_dir), _cg(g_int), _cg(g_records),
             table_f, table_i, lut, lut_w, need_rays, need_table, ctx.mode)
         return (gp if ctx.needs_input_grad[0] else None, gd if ctx.needs_input_grad[1] else None,
                 gi if ctx.needs_input_grad[2] else None, None,

@@ -106,7 +106,8 @@ class GpuSim:
         return dict(pos=self._np(op), dir=self._np(od), intensity=self._np(oi), seq=self._np(seq), nb=self._np(nh),
                     sensors=[(self._np(r), self._np(i)) for r, i in keep])
 
-    def trace_nonseq_bwd(self, tf, ti, pos, dir_, inten, seq, g_pos, g_dir, g_int, wav=None, lut=None, lut_w=None):
+    def trace_nonseq_bwd(self, tf, ti, pos, dir_, inten, seq, g_pos, g_dir, g_int, wav=None, lut=None, lut_w=None,
+                         g_records=None):
         pos, dir_, inten, wav = _dev(pos), _dev(dir_), _dev(inten), _dev(wav)
         g_pos, g_dir, g_int = _dev(g_pos), _dev(g_dir), _dev(g_int)
         seq = _dev(seq, torch.uint8)
@@ -115,9 +116,12 @@ class GpuSim:
         gp, gd, gi = torch.zeros_like(pos), torch.zeros_like(dir_), torch.zeros_like(inten)
         gt = torch.zeros((req.n_rows, C.ROW_G), device="cuda")
         gl = None if lut is None else torch.zeros_like(hold[2])
+        g_records = [_dev(g) for g in (g_records or [])]
+        ns = len(g_records)
+        rec_arr = (ct.c_void_p * ns)(*[_p(g) or None for g in g_records]) if ns else None
         self.lib.call("rtt_trace_nonseq_bwd", _p(pos), _p(dir_), _p(inten), _p(wav), _p(seq), seq.shape[1],
-                      _p(g_pos), _p(g_dir), _p(g_int), _p(gp), _p(gd), _p(gi), _p(gt), _p(gl),
-                      ct.byref(req), n, self.mode, self._stream())
+                      _p(g_pos), _p(g_dir), _p(g_int), rec_arr, _p(gp), _p(gd), _p(gi), _p(gt), _p(gl),
+                      ct.byref(req), ns, n, self.mode, self._stream())
         torch.cuda.synchronize()
         return dict(g_pos=self._np(gp), g_dir=self._np(gd), g_intensity=self._np(gi), g_table=self._np(gt),
                     g_lut=self._np(gl))

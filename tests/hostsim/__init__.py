@@ -117,7 +117,8 @@ class HostSim:
                       _p(seq), _p(nh), ct.byref(req), sens, ns, nbounces, n, 0, None)
         return dict(pos=op, dir=od, intensity=oi, seq=seq, nb=nh, sensors=keep)
 
-    def trace_nonseq_bwd(self, tf, ti, pos, dir_, inten, seq, g_pos, g_dir, g_int, wav=None, lut=None, lut_w=None):
+    def trace_nonseq_bwd(self, tf, ti, pos, dir_, inten, seq, g_pos, g_dir, g_int, wav=None, lut=None, lut_w=None,
+                         g_records=None):
         pos, dir_, inten, wav = _f32(pos), _f32(dir_), _f32(inten), _f32(wav)
         g_pos, g_dir, g_int = _f32(g_pos), _f32(g_dir), _f32(g_int)
         n = pos.shape[0]
@@ -126,9 +127,12 @@ class HostSim:
         gt = np.zeros((req.n_rows, C.ROW_G), np.float32)
         gl = None if lut is None else np.zeros_like(hold[2])
         seq = np.ascontiguousarray(seq, np.uint8)
+        g_records = [_f32(g) for g in (g_records or [])]
+        ns = len(g_records)
+        rec_arr = (ct.c_void_p * max(ns, 1))(*[_p(g) or None for g in g_records]) if ns else None
         self.lib.call("rtt_trace_nonseq_bwd", _p(pos), _p(dir_), _p(inten), _p(wav), _p(seq), seq.shape[1],
-                      _p(g_pos), _p(g_dir), _p(g_int), _p(gp), _p(gd), _p(gi), _p(gt), _p(gl),
-                      ct.byref(req), n, 0, None)
+                      _p(g_pos), _p(g_dir), _p(g_int), rec_arr, _p(gp), _p(gd), _p(gi), _p(gt), _p(gl),
+                      ct.byref(req), ns, n, 0, None)
         return dict(g_pos=gp, g_dir=gd, g_intensity=gi, g_table=gt, g_lut=gl)
 
     def intersect_test(self, tf, ti, pos, dir_, row0, k):

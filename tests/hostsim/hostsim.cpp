@@ -244,9 +244,10 @@ int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* 
 int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float*,
                          const float* in_wavelength, const uint8_t* hit_seq, int32_t nbounces,
                          const float* g_out_pos, const float* g_out_dir, const float* g_out_intensity,
+                         const float* const* g_record,
                          float* g_in_pos, float* g_in_dir, float* g_in_intensity,
                          float* g_table, float* g_lut,
-                         const rtt_table_t* table, int64_t n, int32_t, void*) {
+                         const rtt_table_t* table, int32_t n_sensors, int64_t n, int32_t, void*) {
     const HostTable T = stage(table);
     std::vector<Ck> ck(nbounces + 1);
     std::vector<int> rows_hit(nbounces + 1);
@@ -270,9 +271,17 @@ int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float*,
         V3 gp = g_out_pos ? load3(g_out_pos, i) : v3(0, 0, 0);
         V3 gd = g_out_dir ? load3(g_out_dir, i) : v3(0, 0, 0);
         float gI = g_out_intensity ? g_out_intensity[i] : 0.0f;
+        unsigned seen = 0u;
         while (nh > 0) {
             --nh;
-            reverse_row(T, rows_hit[nh], lam, ck[nh], gp, gd, gI, v3(0, 0, 0), 0.0f, g_table, g_lut);
+            V3 g_hl = v3(0, 0, 0); float g_w = 0.0f;
+            const int slot = T.rows[rows_hit[nh]].i[RTT_I_SENSOR];
+            if (slot >= 0 && slot < n_sensors && g_record && g_record[slot] && !((seen >> slot) & 1u)) {
+                seen |= 1u << slot;
+                const float* gr = g_record[slot] + 4 * i;
+                g_hl = v3(gr[0], gr[1], gr[2]); g_w = gr[3];
+            }
+            reverse_row(T, rows_hit[nh], lam, ck[nh], gp, gd, gI, g_hl, g_w, g_table, g_lut);
         }
         if (g_in_pos) store3(g_in_pos, i, gp);
         if (g_in_dir) store3(g_in_dir, i, gd);
