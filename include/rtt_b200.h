@@ -69,9 +69,16 @@ enum { RTT_MODE_FAST = 0, RTT_MODE_EXACT = 1 };
  *   (elements/sensor.py:36), channel = wavelength index (0 without a wavelength LUT). */
 typedef struct {
     float* image;      /* [channels, height, width] fp32, accumulated into (caller zeroes), or NULL */
-    float* record;     /* [n, 4] (hit_local x,y,z, weight) written for rays that hit, or NULL      */
+    float* record;     /* [record_hits, n, 4] (hit_local x,y,z, weight): the k-th interaction of ray i with
+                          this sensor goes to record[k][i] for k < record_hits; NULL = no records       */
     int32_t height, width, channels;
     float x0, y0, sx, sy;
+    int32_t record_hits; /* K >= 1 (0 is read as 1).  A sequential trace visits a sensor row once (K = 1);
+                            in a non-sequential trace a ray can cross a sensor several times — and in the
+                            reference it routinely re-hits the plane it just left (t > 1e-6 at an fp32 ulp
+                            of ~8e-6), which its hit lists record as two entries                       */
+    uint8_t* count;    /* [n] number of interactions of ray i with this sensor (saturates at 255), written
+                          by the non-sequential trace only, or NULL                                       */
 } rtt_sensor_t;
 
 typedef struct {
@@ -129,7 +136,8 @@ int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float* in_
  * (first row wins ties, NaN distance anywhere = no hit); stop if none; interact }.
  *   hit_seq     : [n, nbounces] uint8, row index per executed bounce, 255 = none (may be NULL)
  *   n_hits      : [n] uint8 number of executed bounces (may be NULL)
- * Sensors: every sensor interaction is accumulated into the image; `record` keeps the LAST.
+ * Sensors: every sensor interaction is accumulated into the image; `record` keeps the first
+ * `record_hits` interactions per ray and `count` their total number.
  * `mode` is accepted for symmetry but ignored: the non-sequential trace (and its adjoint) always
  * run the EXACT arithmetic.  Whether a ray re-hits the surface it is leaving is decided by the
  * reference's t > 1e-6 rule at the fp32 ulp of scene-scale coordinates, i.e. by its exact rounding
@@ -143,11 +151,11 @@ int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* 
 
 /* Adjoint of rtt_trace_nonseq_fwd: replays the recorded hit sequence (no search), then
  * reverse sweep.  Same gradient conventions as rtt_trace_seq_bwd; g_record[slot] is the upstream
- * gradient of that sensor's record, i.e. of the LAST interaction of the ray with that sensor. */
+ * gradient [record_hits[slot], n, 4] of that sensor's records (record_hits: HOST array, NULL = all 1). */
 int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float* in_intensity,
                          const float* in_wavelength, const uint8_t* hit_seq, int32_t nbounces,
                          const float* g_out_pos, const float* g_out_dir, const float* g_out_intensity,
-                         const float* const* g_record,
+                         const float* const* g_record, const int32_t* record_hits,
                          float* g_in_pos, float* g_in_dir, float* g_in_intensity,
                          float* g_table, float* g_lut,
                          const rtt_table_t* table, int32_t n_sensors,

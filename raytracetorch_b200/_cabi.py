@@ -29,7 +29,8 @@ class RttError(RuntimeError):
 class SensorReq(ct.Structure):
     _fields_ = [("image", ct.c_void_p), ("record", ct.c_void_p),
                 ("height", ct.c_int32), ("width", ct.c_int32), ("channels", ct.c_int32),
-                ("x0", ct.c_float), ("y0", ct.c_float), ("sx", ct.c_float), ("sy", ct.c_float)]
+                ("x0", ct.c_float), ("y0", ct.c_float), ("sx", ct.c_float), ("sy", ct.c_float),
+                ("record_hits", ct.c_int32), ("count", ct.c_void_p)]
 
 
 class TableReq(ct.Structure):
@@ -45,7 +46,8 @@ _SIGS = {
                           ct.POINTER(TableReq), ct.c_int32, ct.c_int64, ct.c_int32, _P],
     "rtt_trace_nonseq_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, ct.POINTER(TableReq), ct.POINTER(SensorReq),
                              ct.c_int32, ct.c_int32, ct.c_int64, ct.c_int32, _P],
-    "rtt_trace_nonseq_bwd": [_P, _P, _P, _P, _P, ct.c_int32, _P, _P, _P, ct.POINTER(_P), _P, _P, _P, _P, _P,
+    "rtt_trace_nonseq_bwd": [_P, _P, _P, _P, _P, ct.c_int32, _P, _P, _P, ct.POINTER(_P), ct.POINTER(ct.c_int32),
+                             _P, _P, _P, _P, _P,
                              ct.POINTER(TableReq), ct.c_int32, ct.c_int64, ct.c_int32, _P],
     "rtt_intersect_test": [_P, _P, _P, ct.POINTER(TableReq), ct.c_int32, ct.c_int32, ct.c_int64, ct.c_int32, _P],
     "rtt_surface_step_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, ct.POINTER(TableReq), ct.c_int32,
@@ -62,14 +64,16 @@ def make_table(f_ptr: int, i_ptr: int, n_rows: int, lut_ptr: int = 0, lut_w_ptr:
 
 
 def make_sensors(reqs: Sequence[dict]):
-    """reqs: dicts with image, record (addresses or 0), height, width, channels, x0, y0, sx, sy."""
+    """reqs: dicts with image, record, count (addresses or 0), height, width, channels, x0, y0, sx, sy,
+    record_hits."""
     if not reqs:
         return None, 0
     arr = (SensorReq * len(reqs))()
     for k, r in enumerate(reqs):
         arr[k] = SensorReq(r.get("image") or None, r.get("record") or None,
                            r.get("height", 0), r.get("width", 0), r.get("channels", 1),
-                           r.get("x0", 0.0), r.get("y0", 0.0), r.get("sx", 0.0), r.get("sy", 0.0))
+                           r.get("x0", 0.0), r.get("y0", 0.0), r.get("sx", 0.0), r.get("sy", 0.0),
+                           r.get("record_hits", 1), r.get("count") or None)
     return arr, len(reqs)
 
 

@@ -51,6 +51,7 @@ int fill_sensors(SD* dst, const rtt_sensor_t* src, int n) {
             if (src[s].image && (long long)src[s].height * src[s].width * src[s].channels >= (1ll << 28)) return RTT_E_SENSOR;
             if (src[s].record && (reinterpret_cast<uintptr_t>(src[s].record) & 15)) return RTT_E_ALIGN;
             q.image = src[s].image; q.record = src[s].record;
+            q.K = src[s].record_hits < 1 ? 1 : src[s].record_hits; q.count = src[s].count;
             q.H = src[s].height; q.W = src[s].width; q.C = src[s].channels;
             q.x0 = src[s].x0; q.y0 = src[s].y0; q.sx = src[s].sx; q.sy = src[s].sy;
         }
@@ -194,7 +195,7 @@ int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* 
 int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float* in_intensity,
                          const float* in_wavelength, const uint8_t* hit_seq, int32_t nbounces,
                          const float* g_out_pos, const float* g_out_dir, const float* g_out_intensity,
-                         const float* const* g_record,
+                         const float* const* g_record, const int32_t* record_hits,
                          float* g_in_pos, float* g_in_dir, float* g_in_intensity,
                          float* g_table, float* g_lut,
                          const rtt_table_t* table, int32_t n_sensors,
@@ -215,6 +216,7 @@ int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float* 
         a.g_opos = g_out_pos; a.g_odir = g_out_dir; a.g_ointen = g_out_intensity;                      \
         for (int s = 0; s < RTT_MAX_SENSORS; ++s) {                                                    \
             a.g_record[s] = (g_record && s < n_sensors) ? g_record[s] : nullptr;                       \
+            a.rec_hits[s] = (record_hits && s < n_sensors && record_hits[s] > 1) ? record_hits[s] : 1; \
             if (a.g_record[s] && (reinterpret_cast<uintptr_t>(a.g_record[s]) & 15)) return RTT_E_ALIGN; \
         }                                                                                              \
         a.g_pos = g_in_pos; a.g_dir = g_in_dir; a.g_inten = g_in_intensity;                            \

@@ -165,11 +165,12 @@ __device__ __forceinline__ void img_cache_flush(ImgCache c, const SensorDev* sen
     }
 }
 
+// `ordinal` = how many times this ray has interacted with this sensor before, `n` = bundle size
 __device__ __forceinline__ void sensor_deposit(const SensorDev& sd, ImgCache c, int slot, long long i, V3 hl, float w,
-                                               int lam) {
-    if (sd.record) {
+                                               int lam, int ordinal = 0, long long n = 0) {
+    if (sd.record && ordinal < sd.K) {
         float4* rec = reinterpret_cast<float4*>(sd.record);
-        rec[i] = make_float4(hl.x, hl.y, hl.z, w);
+        rec[(long long)ordinal * n + i] = make_float4(hl.x, hl.y, hl.z, w);
     }
     if (sd.image && w != 0.0f) {
         int ix, iy;
@@ -452,6 +453,7 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
         V3 p = load3(a.pos, i), d = load3(a.dir, i);
         float I = a.inten[i];
         const int lam = (L > 0) ? wavelength_index(T, L, a.wav[i]) : 0;
+        unsigned cnts = 0u;                                             // 8 bits per sensor slot
         int nb = 0;
         for (; nb < NB; ++nb) {
             if (!(I > 0.0f)) break;                                     // base.py:140,201
@@ -477,10 +479,16 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
             const Ior io = row_ior(T, S, L, win, lam);
             const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
             const int slot = R.i[RTT_I_SENSOR];
-            if (slot >= 0 && slot < a.n_sens) sensor_deposit(a.sens[slot], cache, slot, i, s.hit_local, I, lam);
+            if (slot >= 0 && slot < a.n_sens) {
+                const unsigned c = (cnts >> (8 * slot)) & 255u;
+                sensor_deposit(a.sens[slot], cache, slot, i, s.hit_local, I, lam, (int)c, a.n);
+                if (c < 255u) cnts += 1u << (8 * slot);
+            }
             p = s.hit_global; d = s.new_dir; I = I * s.mod;
             if (a.hit_seq) a.hit_seq[i * NB + nb] = (unsigned char)win;
         }
+        for (int s = 0; s < a.n_sens; ++s)
+            if (a.sens[s].count) a.sens[s].count[i] = (unsigned char)((cnts >> (8 * s)) & 255u);
         if (a.hit_seq) for (int b = nb; b < NB; ++b) a.hit_seq[i * NB + b] = 255;
         if (a.n_hits) a.n_hits[i] = (unsigned char)nb;
         store3(a.opos, i, p); store3(a.odir, i, d);
@@ -510,12 +518,17 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_bwd)(const _
         Checkpoint ck[kMaxReplay];
         unsigned char rows_hit[kMaxReplay];
         int nh = 0;
+        unsigned cnts = 0u;                                             // sensor interactions per slot, 8 bits each
         const int lim = NB < kMaxReplay ? NB : kMaxReplay;
         for (int b = 0; b < lim; ++b) {
             const int r = a.hit_seq[i * NB + b];
             if (r == 255) break;
             ck[nh].p = p; ck[nh].d = d; rows_hit[nh] = (unsigned char)r; ++nh;
             const RowDev& R = T.rows[r];
+            {
+                const int sl = R.i[RTT_I_SENSOR];
+                if (sl >= 0 && sl < a.n_sens && ((cnts >> (8 * sl)) & 255u) < 255u) cnts += 1u << (8 * sl);
+            }
             const Frames F = to_frames(R, p, d);
             const Roots q = solve_roots(R, F.o, F.dd);
             int which;
@@ -527,7 +540,6 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_bwd)(const _
         V3 gp = a.g_opos ? load3(a.g_opos, i) : v3(0, 0, 0);
         V3 gd = a.g_odir ? load3(a.g_odir, i) : v3(0, 0, 0);
         float gI = a.g_ointen ? a.g_ointen[i] : 0.0f;
-        unsigned seen = 0u;      // sensor slots whose record gradient has been consumed (record = LAST hit)
         while (nh > 0) {
             --nh;
             const int r = rows_hit[nh];
@@ -539,10 +551,13 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_bwd)(const _
             V3 g_hl = v3(0, 0, 0);
             float g_w = 0.0f;
             const int slot = R.i[RTT_I_SENSOR];
-            if (slot >= 0 && slot < a.n_sens && a.g_record[slot] && !((seen >> slot) & 1u)) {
-                seen |= 1u << slot;
-                const float4 gr = reinterpret_cast<const float4*>(a.g_record[slot])[i];
-                g_hl = v3(gr.x, gr.y, gr.z); g_w = gr.w;
+            if (slot >= 0 && slot < a.n_sens) {
+                cnts -= 1u << (8 * slot);                               // ordinal of this interaction
+                const int ord = (int)((cnts >> (8 * slot)) & 255u);
+                if (a.g_record[slot] && ord < a.rec_hits[slot]) {
+                    const float4 gr = reinterpret_cast<const float4*>(a.g_record[slot])[(long long)ord * a.n + i];
+                    g_hl = v3(gr.x, gr.y, gr.z); g_w = gr.w;
+                }
             }
             V3 ngp, ngd; float mod;
             interact_adjoint(R, ck[nh].p, ck[nh].d, io.ni, io.no, io.mu_enter, io.mu_exit,

@@ -19,6 +19,8 @@ struct SensorDev {
     float* record;
     int H, W, C;
     float x0, y0, sx, sy;
+    int K;                      // record_hits
+    unsigned char* count;
 };
 
 struct TableDev {
@@ -66,6 +68,7 @@ struct NonseqBwdArgs {
     const unsigned char* hit_seq;
     const float *g_opos, *g_odir, *g_ointen;
     const float* g_record[RTT_MAX_SENSORS];
+    int rec_hits[RTT_MAX_SENSORS];
     float *g_pos, *g_dir, *g_inten;
     float *g_table, *g_lut;
     TableDev tab;

@@ -338,11 +338,22 @@ class Sensor(Element):
     # The fused scene kernels hand over (record [N,4], hit mask [N], ids [N]); compaction to the
     # reference's per-call lists needs a boolean gather (a host sync), so it is deferred until
     # somebody actually reads the lists.
-    def _pend(self, record, hit, ids):
-        self._pending.append((record, hit, ids))
+    def _pend(self, record, hit, ids, overflow=None):
+        """``overflow = (counts, depth)``: per-ray interaction counts of a non-sequential trace, handed over
+        with the last kept ordinal so that dropped interactions are reported when the lists are read."""
+        self._pending.append((record, hit, ids, overflow))
 
     def _flush(self):
-        for record, hit, ids in self._pending:
+        for record, hit, ids, overflow in self._pending:
+            if overflow is not None:
+                counts, depth = overflow
+                most = int(counts.max()) if counts.numel() else 0
+                if most > depth:
+                    import warnings
+                    warnings.warn(f"Sensor: a ray interacted {most} times with this sensor in one non-sequential "
+                                  f"trace but only {depth} interactions per ray were kept; raise Scene.record_depth")
+                if depth > 1 and most < depth:
+                    continue                               # nobody got this far: no empty list entry
             sel = record[hit]
             self._locs.append(sel[:, :3])
             self._w.append(sel[:, 3])

@@ -77,14 +77,15 @@ def _table_req(table_f, table_i, lut, lut_w):
 SENSOR_CFG = 7   # floats per sensor slot in `sensor_cfg`: H, W, C, x0, y0, sx, sy  (H == 0: no image)
 
 
-def _sensor_reqs(sensor_cfg: Sequence[float], n: int, records, images):
+def _sensor_reqs(sensor_cfg: Sequence[float], n: int, records, images, counts=None, record_hits: int = 1):
     reqs = []
     ns = len(sensor_cfg) // SENSOR_CFG
     off = 0
     for s in range(ns):
         H, W, Cn, x0, y0, sx, sy = sensor_cfg[s * SENSOR_CFG:(s + 1) * SENSOR_CFG]
         H, W, Cn = int(H), int(W), int(Cn)
-        r = dict(record=(records[s].data_ptr() if records is not None else 0))
+        r = dict(record=(records[s].data_ptr() if records is not None else 0), record_hits=record_hits,
+                 count=(counts[s].data_ptr() if counts is not None else 0))
         if H > 0:
             r.update(image=images.data_ptr() + 4 * off, height=H, width=W, channels=Cn, x0=x0, y0=y0, sx=sx, sy=sy)
             off += H * W * Cn
@@ -181,8 +182,10 @@ def _(pos, dir, intensity, wavelength, hitmask, g_pos, g_dir, g_int, g_records, 
 def _trace_nonseq_fwd(pos: torch.Tensor, dir: torch.Tensor, intensity: torch.Tensor,
                       wavelength: Optional[torch.Tensor], table_f: torch.Tensor, table_i: torch.Tensor,
                       lut: Optional[torch.Tensor], lut_w: Optional[torch.Tensor],
-                      sensor_cfg: List[float], want_record: bool, nbounces: int, mode: int) -> List[torch.Tensor]:
-    """-> [out_pos, out_dir, out_intensity, hit_seq uint8 [N,B], n_hits uint8 [N], records, images]"""
+                      sensor_cfg: List[float], want_record: bool, nbounces: int, mode: int,
+                      record_depth: int = 1) -> List[torch.Tensor]:
+    """-> [out_pos, out_dir, out_intensity, hit_seq uint8 [N,B], n_hits uint8 [N], records [ns,K,N,4],
+    images (flat), counts uint8 [ns,N]]; K = record_depth = sensor interactions kept per ray."""
     _need_cuda(pos, dir, intensity, table_f, table_i)
     lib = _cabi.load()
     n = pos.shape[0]
@@ -190,25 +193,31 @@ def _trace_nonseq_fwd(pos: torch.Tensor, dir: torch.Tensor, intensity: torch.Ten
     opos, odir, oint = torch.empty_like(pos), torch.empty_like(dir), torch.empty_like(intensity)
     seq = torch.empty((n, nbounces), dtype=torch.uint8, device=pos.device)
     nh = torch.empty(n, dtype=torch.uint8, device=pos.device)
-    records = torch.zeros((ns, n, 4), dtype=torch.float32, device=pos.device) if (want_record and ns) \
-        else torch.empty((0, n, 4), dtype=torch.float32, device=pos.device)
+    K = max(1, int(record_depth))
+    rec_on = bool(want_record and ns)
+    records = torch.zeros((ns, K, n, 4), dtype=torch.float32, device=pos.device) if rec_on \
+        else torch.empty((0, K, n, 4), dtype=torch.float32, device=pos.device)
+    counts = torch.zeros((ns if rec_on else 0, n), dtype=torch.uint8, device=pos.device)
     images = torch.zeros(_image_numel(sensor_cfg), dtype=torch.float32, device=pos.device)
-    sens, cnt = _sensor_reqs(sensor_cfg, n, records if (want_record and ns) else None, images)
+    sens, cnt = _sensor_reqs(sensor_cfg, n, records if rec_on else None, images, counts if rec_on else None, K)
     req = _table_req(table_f, table_i, lut, lut_w)
     with torch.cuda.device(pos.device):
         lib.call("rtt_trace_nonseq_fwd", pos.data_ptr(), dir.data_ptr(), intensity.data_ptr(), _ptr(wavelength),
                  opos.data_ptr(), odir.data_ptr(), oint.data_ptr(), seq.data_ptr(), nh.data_ptr(),
                  ct.byref(req), sens, cnt, nbounces, n, mode, _stream(pos))
-    return [opos, odir, oint, seq, nh, records, images]
+    return [opos, odir, oint, seq, nh, records, images, counts]
 
 
 @_trace_nonseq_fwd.register_fake
-def _(pos, dir, intensity, wavelength, table_f, table_i, lut, lut_w, sensor_cfg, want_record, nbounces, mode):
+def _(pos, dir, intensity, wavelength, table_f, table_i, lut, lut_w, sensor_cfg, want_record, nbounces, mode,
+      record_depth=1):
     n = pos.shape[0]
     ns = len(sensor_cfg) // SENSOR_CFG
+    K = max(1, int(record_depth))
     return [torch.empty_like(pos), torch.empty_like(dir), torch.empty_like(intensity),
             pos.new_empty((n, nbounces), dtype=torch.uint8), pos.new_empty(n, dtype=torch.uint8),
-            pos.new_empty(((ns if want_record else 0), n, 4)), pos.new_empty(_image_numel(sensor_cfg))]
+            pos.new_empty(((ns if want_record else 0), K, n, 4)), pos.new_empty(_image_numel(sensor_cfg)),
+            pos.new_empty(((ns if want_record else 0), n), dtype=torch.uint8)]
 
 
 @torch.library.custom_op("rtt_b200::trace_nonseq_bwd", mutates_args=())
@@ -229,12 +238,13 @@ def _trace_nonseq_bwd(pos: torch.Tensor, dir: torch.Tensor, intensity: torch.Ten
     gt = torch.zeros((S, C.ROW_G), dtype=torch.float32, device=dev) if need_table else pos.new_empty(0)
     has_lut = lut is not None and lut.numel() > 0
     gl = torch.zeros_like(lut) if (need_table and has_lut) else pos.new_empty(0)
-    ns = 0 if g_records is None else g_records.shape[0]
+    ns = 0 if g_records is None else g_records.shape[0]          # g_records: [ns, K, N, 4]
     rec_arr = (ct.c_void_p * ns)(*[g_records[s].data_ptr() for s in range(ns)]) if ns else None
+    depth = (ct.c_int32 * ns)(*([g_records.shape[1]] * ns)) if ns else None
     req = _table_req(table_f, table_i, lut, lut_w)
     with torch.cuda.device(dev):
         lib.call("rtt_trace_nonseq_bwd", pos.data_ptr(), dir.data_ptr(), intensity.data_ptr(), _ptr(wavelength),
-                 hit_seq.data_ptr(), hit_seq.shape[1], _ptr(g_pos), _ptr(g_dir), _ptr(g_int), rec_arr,
+                 hit_seq.data_ptr(), hit_seq.shape[1], _ptr(g_pos), _ptr(g_dir), _ptr(g_int), rec_arr, depth,
                  _ptr(gp), _ptr(gd), _ptr(gi), _ptr(gt), _ptr(gl), ct.byref(req), ns, n, mode, _stream(pos))
     return [gp, gd, gi, gt, gl]
 
@@ -367,17 +377,17 @@ class _TraceSeq(torch.autograd.Function):
 class _TraceNonseq(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pos, dir_, intensity, wavelength, table_f, table_i, lut, lut_w, sensor_cfg, want_record,
-                nbounces, mode):
+                nbounces, mode, record_depth):
         outs = torch.ops.rtt_b200.trace_nonseq_fwd(pos, dir_, intensity, wavelength, table_f, table_i, lut, lut_w,
-                                                   sensor_cfg, want_record, nbounces, mode)
-        opos, odir, oint, seq, nh, records, images = outs
+                                                   sensor_cfg, want_record, nbounces, mode, record_depth)
+        opos, odir, oint, seq, nh, records, images, counts = outs
         ctx.save_for_backward(pos, dir_, intensity, wavelength, seq, table_f, table_i, lut, lut_w)
         ctx.mode = mode
-        ctx.mark_non_differentiable(seq, nh, images)
-        return opos, odir, oint, seq, nh, records, images
+        ctx.mark_non_differentiable(seq, nh, images, counts)
+        return opos, odir, oint, seq, nh, records, images, counts
 
     @staticmethod
-    def backward(ctx, g_pos, g_dir, g_int, _g_seq, _g_nh, g_records, _g_images):
+    def backward(ctx, g_pos, g_dir, g_int, _g_seq, _g_nh, g_records, _g_images, _g_counts):
         pos, dir_, intensity, wavelength, seq, table_f, table_i, lut, lut_w = ctx.saved_tensors
         need_rays = any(ctx.needs_input_grad[:3])
         need_table = ctx.needs_input_grad[4] or ctx.needs_input_grad[6]
@@ -389,7 +399,7 @@ class _TraceNonseq(torch.autograd.Function):
         return (gp if ctx.needs_input_grad[0] else None, gd if ctx.needs_input_grad[1] else None,
                 gi if ctx.needs_input_grad[2] else None, None,
                 _pad_table_grad(gt, table_f) if ctx.needs_input_grad[4] else None, None,
-                gl if ctx.needs_input_grad[6] else None, None, None, None, None, None)
+                gl if ctx.needs_input_grad[6] else None, None, None, None, None, None, None)
 
 
 class _SurfaceStep(torch.autograd.Function):
@@ -466,20 +476,23 @@ def trace_sequential(table: SurfaceTable, pos, dir_, intensity, wavelength=None,
 
 
 def trace_nonsequential(table: SurfaceTable, pos, dir_, intensity, nbounces: int, wavelength=None, *,
-                        want_record=True, sensor_cfg: Optional[List[float]] = None, mode: Optional[int] = None):
+                        want_record=True, sensor_cfg: Optional[List[float]] = None, mode: Optional[int] = None,
+                        record_depth: int = 1):
     """Fused Scene.simulate bounce loop (scene/base.py:129-235).
 
-    Returns dict(pos, dir, intensity, hit_seq [N,B] uint8 (255 = none), n_hits [N] uint8, records, images)."""
+    Returns dict(pos, dir, intensity, hit_seq [N,B] uint8 (255 = none), n_hits [N] uint8,
+    records [n_sensors, K, N, 4] (the k-th interaction of ray i with the sensor, K = record_depth),
+    sensor_counts [n_sensors, N] uint8 (interactions per ray, may exceed K), images)."""
     pos, dir_, intensity, wav = _prep_rays(pos, dir_, intensity, wavelength, table)
     if not 0 <= nbounces <= C.MAX_BOUNCES:
         raise ValueError(f"nbounces must be in [0, {C.MAX_BOUNCES}]")
     cfg = sensor_cfg_of(table) if sensor_cfg is None else list(sensor_cfg)
     mode = _default_mode_nonseq if mode is None else mode
-    opos, odir, oint, seq, nh, records, images = _TraceNonseq.apply(
+    opos, odir, oint, seq, nh, records, images, counts = _TraceNonseq.apply(
         pos, dir_, intensity, wav, table.f, table.i, table.lut, table.lut_wavelengths, cfg, bool(want_record),
-        int(nbounces), mode)
+        int(nbounces), mode, max(1, int(record_depth)))
     return dict(pos=opos, dir=odir, intensity=oint, hit_seq=seq, n_hits=nh, records=records,
-                images=split_images(images, cfg))
+                sensor_counts=counts, images=split_images(images, cfg))
 
 
 def intersect_rows(table: SurfaceTable, pos, dir_, row0: int, k: int, mode: Optional[int] = None) -> torch.Tensor:

@@ -68,10 +68,12 @@ def _sensor_hits(scene, sensor: Sensor):
         if sensor in table.sensors:
             slot = table.sensors.index(sensor)
             rec = tr["records"][slot]
-            if "hitmask" in tr:
+            if "hitmask" in tr:                             # sequential: [N,4], one interaction per ray
                 hit = ((tr["hitmask"] >> table.sensor_rows[slot]) & 1).bool()
-            else:
-                hit = (tr["hit_seq"] == table.sensor_rows[slot]).any(dim=1)
+            else:                                           # non-sequential: [K,N,4], every kept interaction counts
+                cnt = tr["sensor_counts"][slot]
+                hit = (torch.arange(rec.shape[0], device=cnt.device)[:, None] < cnt[None, :]).reshape(-1)
+                rec = rec.reshape(-1, 4)
             return rec[:, :2], torch.where(hit, rec[:, 3], torch.zeros_like(rec[:, 3]))
     if sensor.hitLocs:
         locs, w, _ = sensor.getHitsTensors()

@@ -36,6 +36,11 @@ class Scene(nn.Module):
         self.Nbounces = 100
         self.dispersion: Optional[Dispersion] = None
         self.record_hits = True          # fill Sensor.hitLocs/hitIntensity/hitID like the reference
+        # Non-sequential traces: sensor interactions kept per ray.  The reference appends one hit-list
+        # entry per interaction, and a ray routinely re-hits the sensor plane it has just left (t > 1e-6
+        # at an fp32 ulp of ~8e-6), so 2 is the smallest depth that reproduces its lists on
+        # transmitting sensors; Sensor warns when a ray had more interactions than were kept.
+        self.record_depth = 2
         self.mode: Optional[int] = None  # None = ops default (FAST)
         self.last_trace = None           # raw kernel outputs of the latest simulate()/step()
         self._compiler = SceneCompiler()
@@ -104,16 +109,19 @@ class Scene(nn.Module):
 
     def _trace(self, rays: Rays, nbounces: int):
         table = self._last_table = self.table()
+        depth = max(1, min(int(self.record_depth), nbounces))
         out = ops.trace_nonsequential(table, rays.pos, rays.dir, rays.intensity, nbounces, rays.wavelength,
-                                      want_record=self.record_hits, mode=self.mode)
+                                      want_record=self.record_hits, mode=self.mode, record_depth=depth)
         self.last_trace = out
-        seq = out["hit_seq"]
-
-        def hit_of_slot(slot):
-            row = table.sensor_rows[slot]
-            return (seq == row).any(dim=1)
-
-        self._deliver_to_sensors(table, out["records"], hit_of_slot, rays, out["images"])
+        records, counts = out["records"], out["sensor_counts"]
+        for slot, sensor in enumerate(table.sensors):
+            if out["images"][slot] is not None:
+                sensor.image = out["images"][slot] if sensor.image is None else sensor.image + out["images"][slot]
+            if self.record_hits and records.numel():
+                # one list entry per interaction ordinal (the reference: one per bounce; same multiset)
+                for k in range(depth):
+                    sensor._pend(records[slot, k], counts[slot] > k, rays.id,
+                                 overflow=(counts[slot], depth) if k == depth - 1 else None)
         rays.pos, rays.dir, rays.intensity = out["pos"], out["dir"], out["intensity"]
         return out
 

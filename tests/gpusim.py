@@ -38,19 +38,20 @@ class GpuSim:
         n_lut = 0 if lut is None else lut.shape[0]
         return _cabi.make_table(_p(tf), _p(ti), tf.shape[0], _p(lut), _p(lut_w), n_lut), (tf, ti, lut, lut_w)
 
-    def _sensors(self, n, specs, want_record=True):
+    def _sensors(self, n, specs, want_record=True, K=1, want_count=False):
         reqs, keep = [], []
         for sp in specs or []:
-            rec = torch.zeros((n, 4), device="cuda") if want_record else None
+            rec = torch.zeros((K, n, 4) if K > 1 else (n, 4), device="cuda") if want_record else None
+            cnt_a = torch.zeros(n, dtype=torch.uint8, device="cuda") if want_count else None
             img = None
-            r = dict(record=_p(rec))
+            r = dict(record=_p(rec), record_hits=K, count=_p(cnt_a))
             if sp is not None:
                 H, W, x0, x1, y0, y1, ch = sp
                 img = torch.zeros((ch, H, W), device="cuda")
                 r.update(image=_p(img), height=H, width=W, channels=ch, x0=x0, y0=y0,
                          sx=float(np.float32(W / (x1 - x0))), sy=float(np.float32(H / (y1 - y0))))
             reqs.append(r)
-            keep.append((rec, img))
+            keep.append((rec, img, cnt_a))
         arr, cnt = _cabi.make_sensors(reqs)
         return arr, cnt, keep
 
@@ -70,7 +71,7 @@ class GpuSim:
         torch.cuda.synchronize()
         return dict(pos=self._np(op), dir=self._np(od), intensity=self._np(oi),
                     hitmask=self._np(mask).view(np.uint64),
-                    sensors=[(self._np(r), self._np(i)) for r, i in keep])
+                    sensors=[(self._np(r), self._np(i), self._np(c)) for r, i, c in keep])
 
     def trace_seq_bwd(self, tf, ti, pos, dir_, inten, mask, g_pos, g_dir, g_int, wav=None, lut=None, lut_w=None,
                       g_records=None):
@@ -92,11 +93,12 @@ class GpuSim:
         return dict(g_pos=self._np(gp), g_dir=self._np(gd), g_intensity=self._np(gi), g_table=self._np(gt),
                     g_lut=self._np(gl))
 
-    def trace_nonseq(self, tf, ti, pos, dir_, inten, nbounces, wav=None, lut=None, lut_w=None, sensor_specs=None):
+    def trace_nonseq(self, tf, ti, pos, dir_, inten, nbounces, wav=None, lut=None, lut_w=None, sensor_specs=None,
+                     record_hits=1):
         pos, dir_, inten, wav = _dev(pos), _dev(dir_), _dev(inten), _dev(wav)
         n = pos.shape[0]
         req, hold = self._table(tf, ti, lut, lut_w)
-        sens, ns, keep = self._sensors(n, sensor_specs)
+        sens, ns, keep = self._sensors(n, sensor_specs, K=record_hits, want_count=True)
         op, od, oi = torch.empty_like(pos), torch.empty_like(dir_), torch.empty_like(inten)
         seq = torch.zeros((n, nbounces), dtype=torch.uint8, device="cuda")
         nh = torch.zeros(n, dtype=torch.uint8, device="cuda")
@@ -104,10 +106,10 @@ class GpuSim:
                       _p(seq), _p(nh), ct.byref(req), sens, ns, nbounces, n, self.mode, self._stream())
         torch.cuda.synchronize()
         return dict(pos=self._np(op), dir=self._np(od), intensity=self._np(oi), seq=self._np(seq), nb=self._np(nh),
-                    sensors=[(self._np(r), self._np(i)) for r, i in keep])
+                    sensors=[(self._np(r), self._np(i), self._np(c)) for r, i, c in keep])
 
     def trace_nonseq_bwd(self, tf, ti, pos, dir_, inten, seq, g_pos, g_dir, g_int, wav=None, lut=None, lut_w=None,
-                         g_records=None):
+                         g_records=None, record_hits=1):
         pos, dir_, inten, wav = _dev(pos), _dev(dir_), _dev(inten), _dev(wav)
         g_pos, g_dir, g_int = _dev(g_pos), _dev(g_dir), _dev(g_int)
         seq = _dev(seq, torch.uint8)
@@ -119,8 +121,9 @@ class GpuSim:
         g_records = [_dev(g) for g in (g_records or [])]
         ns = len(g_records)
         rec_arr = (ct.c_void_p * ns)(*[_p(g) or None for g in g_records]) if ns else None
+        hits = (ct.c_int32 * max(ns, 1))(*([record_hits] * max(ns, 1)))
         self.lib.call("rtt_trace_nonseq_bwd", _p(pos), _p(dir_), _p(inten), _p(wav), _p(seq), seq.shape[1],
-                      _p(g_pos), _p(g_dir), _p(g_int), rec_arr, _p(gp), _p(gd), _p(gi), _p(gt), _p(gl),
+                      _p(g_pos), _p(g_dir), _p(g_int), rec_arr, hits, _p(gp), _p(gd), _p(gi), _p(gt), _p(gl),
                       ct.byref(req), ns, n, self.mode, self._stream())
         torch.cuda.synchronize()
         return dict(g_pos=self._np(gp), g_dir=self._np(gd), g_intensity=self._np(gi), g_table=self._np(gt),

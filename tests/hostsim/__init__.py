@@ -60,20 +60,22 @@ class HostSim:
         return req, (tf, ti, lut, lut_w)
 
     @staticmethod
-    def _sensors(n, specs, want_record=True):
-        """specs: list of (H, W, x0, x1, y0, y1, channels) or None per slot."""
+    def _sensors(n, specs, want_record=True, K=1, want_count=False):
+        """specs: list of (H, W, x0, x1, y0, y1, channels) or None per slot.
+        Returns per slot (record [n,4] (K == 1) or [K,n,4], image, count [n] or None)."""
         reqs, keep = [], []
         for sp in specs or []:
-            rec = np.zeros((n, 4), np.float32) if want_record else None
+            rec = np.zeros((K, n, 4) if K > 1 else (n, 4), np.float32) if want_record else None
+            cnt_a = np.zeros(n, np.uint8) if want_count else None
             img = None
-            r = dict(record=_p(rec))
+            r = dict(record=_p(rec), record_hits=K, count=_p(cnt_a))
             if sp is not None:
                 H, W, x0, x1, y0, y1, ch = sp
                 img = np.zeros((ch, H, W), np.float32)
                 r.update(image=_p(img), height=H, width=W, channels=ch, x0=x0, y0=y0,
                          sx=float(np.float32(W / (x1 - x0))), sy=float(np.float32(H / (y1 - y0))))
             reqs.append(r)
-            keep.append((rec, img))
+            keep.append((rec, img, cnt_a))
         arr, cnt = _cabi.make_sensors(reqs)
         return arr, cnt, keep
 
@@ -105,11 +107,12 @@ class HostSim:
                       ct.byref(req), ns, n, 0, None)
         return dict(g_pos=gp, g_dir=gd, g_intensity=gi, g_table=gt, g_lut=gl)
 
-    def trace_nonseq(self, tf, ti, pos, dir_, inten, nbounces, wav=None, lut=None, lut_w=None, sensor_specs=None):
+    def trace_nonseq(self, tf, ti, pos, dir_, inten, nbounces, wav=None, lut=None, lut_w=None, sensor_specs=None,
+                     record_hits=1):
         pos, dir_, inten, wav = _f32(pos), _f32(dir_), _f32(inten), _f32(wav)
         n = pos.shape[0]
         req, hold = self._table(tf, ti, lut, lut_w)
-        sens, ns, keep = self._sensors(n, sensor_specs)
+        sens, ns, keep = self._sensors(n, sensor_specs, K=record_hits, want_count=True)
         op, od, oi = np.empty_like(pos), np.empty_like(dir_), np.empty_like(inten)
         seq = np.zeros((n, nbounces), np.uint8)
         nh = np.zeros(n, np.uint8)
@@ -118,7 +121,7 @@ class HostSim:
         return dict(pos=op, dir=od, intensity=oi, seq=seq, nb=nh, sensors=keep)
 
     def trace_nonseq_bwd(self, tf, ti, pos, dir_, inten, seq, g_pos, g_dir, g_int, wav=None, lut=None, lut_w=None,
-                         g_records=None):
+                         g_records=None, record_hits=1):
         pos, dir_, inten, wav = _f32(pos), _f32(dir_), _f32(inten), _f32(wav)
         g_pos, g_dir, g_int = _f32(g_pos), _f32(g_dir), _f32(g_int)
         n = pos.shape[0]
@@ -130,8 +133,9 @@ class HostSim:
         g_records = [_f32(g) for g in (g_records or [])]
         ns = len(g_records)
         rec_arr = (ct.c_void_p * max(ns, 1))(*[_p(g) or None for g in g_records]) if ns else None
+        hits = (ct.c_int32 * max(ns, 1))(*([record_hits] * max(ns, 1)))
         self.lib.call("rtt_trace_nonseq_bwd", _p(pos), _p(dir_), _p(inten), _p(wav), _p(seq), seq.shape[1],
-                      _p(g_pos), _p(g_dir), _p(g_int), rec_arr, _p(gp), _p(gd), _p(gi), _p(gt), _p(gl),
+                      _p(g_pos), _p(g_dir), _p(g_int), rec_arr, hits, _p(gp), _p(gd), _p(gi), _p(gt), _p(gl),
                       ct.byref(req), ns, n, 0, None)
         return dict(g_pos=gp, g_dir=gd, g_intensity=gi, g_table=gt, g_lut=gl)
 

@@ -71,9 +71,13 @@ Ior row_ior(const HostTable& T, int r, int lam) {
 V3 load3(const float* a, int64_t i) { return v3(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
 void store3(float* a, int64_t i, V3 v) { a[3 * i] = v.x; a[3 * i + 1] = v.y; a[3 * i + 2] = v.z; }
 
-void deposit(const rtt_sensor_t& sd, int64_t i, V3 hl, float w, int lam) {
-    if (sd.record) { float* r = sd.record + 4 * i; r[0] = hl.x; r[1] = hl.y; r[2] = hl.z; r[3] = w; }
-    if (sd.image) {
+void deposit(const rtt_sensor_t& sd, int64_t i, V3 hl, float w, int lam, int ordinal = 0, int64_t n = 0) {
+    const int K = sd.record_hits < 1 ? 1 : sd.record_hits;
+    if (sd.record && ordinal < K) {
+        float* r = sd.record + 4 * ((int64_t)ordinal * n + i);
+        r[0] = hl.x; r[1] = hl.y; r[2] = hl.z; r[3] = w;
+    }
+    if (sd.image && w != 0.0f) {
         int ix, iy;
         if (sensor_bin(hl.x, hl.y, sd.x0, sd.y0, sd.sx, sd.sy, sd.width, sd.height, &ix, &iy)) {
             const int ch = (sd.channels > 1) ? (lam < sd.channels - 1 ? lam : sd.channels - 1) : 0;
@@ -210,6 +214,7 @@ int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* 
         V3 p = load3(in_pos, i), d = load3(in_dir, i);
         float I = in_intensity[i];
         const int lam = T.L > 0 ? lam_index(T, in_wavelength[i]) : 0;
+        int cnt[RTT_MAX_SENSORS] = {0, 0, 0, 0};
         int nb = 0;
         for (; nb < nbounces; ++nb) {
             if (!(I > 0.0f)) break;
@@ -229,12 +234,16 @@ int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* 
             const Ior io = row_ior(T, win, lam);
             const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
             const int slot = R.i[RTT_I_SENSOR];
-            if (slot >= 0 && slot < n_sensors) deposit(sensors[slot], i, s.hit_local, I, lam);
+            if (slot >= 0 && slot < n_sensors) {
+                deposit(sensors[slot], i, s.hit_local, I, lam, cnt[slot], n);
+                if (cnt[slot] < 255) ++cnt[slot];
+            }
             p = s.hit_global; d = s.new_dir; I = I * s.mod;
             if (hit_seq) hit_seq[i * nbounces + nb] = (uint8_t)win;
         }
         if (hit_seq) for (int b = nb; b < nbounces; ++b) hit_seq[i * nbounces + b] = 255;
         if (n_hits) n_hits[i] = (uint8_t)nb;
+        for (int s = 0; s < n_sensors; ++s) if (sensors[s].count) sensors[s].count[i] = (uint8_t)cnt[s];
         store3(out_pos, i, p); store3(out_dir, i, d);
         out_intensity[i] = I;
     }
@@ -244,7 +253,7 @@ int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* 
 int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float*,
                          const float* in_wavelength, const uint8_t* hit_seq, int32_t nbounces,
                          const float* g_out_pos, const float* g_out_dir, const float* g_out_intensity,
-                         const float* const* g_record,
+                         const float* const* g_record, const int32_t* record_hits,
                          float* g_in_pos, float* g_in_dir, float* g_in_intensity,
                          float* g_table, float* g_lut,
                          const rtt_table_t* table, int32_t n_sensors, int64_t n, int32_t, void*) {
@@ -254,12 +263,14 @@ int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float*,
     for (int64_t i = 0; i < n; ++i) {
         V3 p = load3(in_pos, i), d = load3(in_dir, i);
         const int lam = T.L > 0 ? lam_index(T, in_wavelength[i]) : 0;
+        int cnt[RTT_MAX_SENSORS] = {0, 0, 0, 0};
         int nh = 0;
         for (int b = 0; b < nbounces && b < 32; ++b) {
             const int r = hit_seq[i * nbounces + b];
             if (r == 255) break;
             ck[nh].p = p; ck[nh].d = d; rows_hit[nh] = r; ++nh;
             const RowDev& R = T.rows[r];
+            if (R.i[RTT_I_SENSOR] >= 0 && R.i[RTT_I_SENSOR] < n_sensors && cnt[R.i[RTT_I_SENSOR]] < 255) ++cnt[R.i[RTT_I_SENSOR]];
             const Frames F = to_frames(R, p, d);
             const Roots q = solve_roots(R, F.o, F.dd);
             int which;
@@ -271,15 +282,17 @@ int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float*,
         V3 gp = g_out_pos ? load3(g_out_pos, i) : v3(0, 0, 0);
         V3 gd = g_out_dir ? load3(g_out_dir, i) : v3(0, 0, 0);
         float gI = g_out_intensity ? g_out_intensity[i] : 0.0f;
-        unsigned seen = 0u;
         while (nh > 0) {
             --nh;
             V3 g_hl = v3(0, 0, 0); float g_w = 0.0f;
             const int slot = T.rows[rows_hit[nh]].i[RTT_I_SENSOR];
-            if (slot >= 0 && slot < n_sensors && g_record && g_record[slot] && !((seen >> slot) & 1u)) {
-                seen |= 1u << slot;
-                const float* gr = g_record[slot] + 4 * i;
-                g_hl = v3(gr[0], gr[1], gr[2]); g_w = gr[3];
+            if (slot >= 0 && slot < n_sensors) {
+                const int ord = --cnt[slot];
+                const int K = (record_hits && record_hits[slot] > 1) ? record_hits[slot] : 1;
+                if (g_record && g_record[slot] && ord < K) {
+                    const float* gr = g_record[slot] + 4 * ((int64_t)ord * n + i);
+                    g_hl = v3(gr[0], gr[1], gr[2]); g_w = gr[3];
+                }
             }
             reverse_row(T, rows_hit[nh], lam, ck[nh], gp, gd, gI, g_hl, g_w, g_table, g_lut);
         }

@@ -106,6 +106,41 @@ def test_nonseq_exact_matches_reference_on_stable_rays(run_exact, name):
     _assert_close_noise_aware(h, d, name, rows=stable)
 
 
+@pytest.mark.parametrize("name", NONSEQ)
+def test_nonseq_sensor_records_keep_every_interaction(run_exact, ieee_oracle, name):
+    """elements/sensor.py:35-37 appends one entry per interaction; a ray that re-hits the sensor plane
+    it has just left is recorded twice.  record[k][i] = k-th interaction of ray i,
+    count[i] = number of interactions — compared with the oracle's recording order."""
+    d = parity.load(name)
+    tf, ti = torch.from_numpy(d["table_f"]), d["table_i"].tolist()
+    nb = int(d["nbounces"])
+    p, dd, inten = parity.inputs_t(d)
+    o = ieee_oracle.trace_nonsequential(tf, ti, p, dd, inten, nb)
+    K = 3
+    h = run_exact.trace_nonseq(d["table_f"], d["table_i"], d["in_pos"], d["in_dir"], d["in_intensity"], nb,
+                               sensor_specs=[None], record_hits=K)
+    hseq = h["seq"].astype(np.int64)
+    hseq[hseq == 255] = -1
+    same = (hseq == o["seq"].numpy()).all(axis=1)
+    n = p.shape[0]
+    want = np.zeros((K, n, 4), np.float32)
+    cnt = np.zeros(n, np.int64)
+    for idx, slot, hl, w in o["sensor_hits"]:
+        assert slot == 0
+        idx = idx.numpy()
+        k = cnt[idx]
+        keep = k < K
+        want[k[keep], idx[keep], :3] = hl.numpy()[keep]
+        want[k[keep], idx[keep], 3] = w.numpy()[keep]
+        cnt[idx] += 1
+    assert cnt.sum() > 0
+    rec, _img, got_cnt = h["sensors"][0]
+    np.testing.assert_array_equal(got_cnt[same], np.minimum(cnt, 255)[same])
+    np.testing.assert_array_equal(rec[:, same, 3], want[:, same, 3])
+    # hit_local: same arithmetic up to the oracle's BLAS batch effects (mm on the masked sub-batch)
+    np.testing.assert_allclose(rec[:, same, :3], want[:, same, :3], rtol=1e-5, atol=1e-5)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", NONSEQ)
 def test_nonseq_always_runs_reference_rounding(name):
