@@ -187,6 +187,13 @@ int rtt_surface_step_bwd(const float* in_pos, const float* in_dir, const float* 
                          const rtt_table_t* table, int32_t row,
                          int64_t n, int32_t mode, void* stream);
 
+/* Measurement helper (bench.py): launches a pure-FMA kernel (8 independent chains per thread,
+ * 8 blocks of 256 threads per SM, `iters` x 64 FMAs per thread) on `stream` and returns the FLOPs
+ * it executes (FMA = 2), or a negative code.  Timed with CUDA events by the caller, this is the
+ * measured FP32 peak the roofline of the FP32-issue-bound traces is reported against.
+ * `scratch`: one device float (never written in practice). */
+int64_t rtt_probe_fp32(int32_t iters, float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,9 @@ class RttLib:
             self.dll.rtt_layout_query.argtypes, self.dll.rtt_layout_query.restype = [ct.c_int], ct.c_int
             self.dll.rtt_launch_count.argtypes, self.dll.rtt_launch_count.restype = [], ct.c_int64
             self.dll.rtt_version.argtypes, self.dll.rtt_version.restype = [], ct.c_int
+        if hasattr(self.dll, "rtt_probe_fp32"):
+            self.dll.rtt_probe_fp32.argtypes = [ct.c_int32, ct.c_void_p, ct.c_void_p]
+            self.dll.rtt_probe_fp32.restype = ct.c_int64
 
     def check(self, code: int, what: str):
         if code != 0:

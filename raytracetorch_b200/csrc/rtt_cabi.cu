@@ -67,6 +67,23 @@ int finish(cudaError_t e) {
 
 }  // namespace
 
+// FP32 issue-rate probe: 8 independent FMA chains per thread, nothing else in the loop.
+__global__ void __launch_bounds__(256) k_probe_fp32(int iters, float* out) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.0f, a2 = a0 + 2.0f, a3 = a0 + 3.0f;
+    float a4 = a0 + 4.0f, a5 = a0 + 5.0f, a6 = a0 + 6.0f, a7 = a0 + 7.0f;
+    const float m = 0.999f + blockIdx.x * 1e-9f, c = 1e-3f;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+        }
+    }
+    const float s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 123.456f) out[0] = s;                                      // keeps the chains alive
+}
+
 #define RTT_DISPATCH(mode, call_fast, call_exact) ((mode) == RTT_MODE_EXACT ? (call_exact) : (call_fast))
 
 extern "C" {
@@ -100,6 +117,18 @@ const char* rtt_error_string(int code) {
 }
 
 int64_t rtt_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int64_t rtt_probe_fp32(int32_t iters, float* scratch, void* stream) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return RTT_E_NO_DEVICE;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return RTT_E_NO_DEVICE;
+    if (iters < 1 || !scratch) return RTT_E_ARG;
+    const int blocks = sms * 8;
+    k_probe_fp32<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, scratch);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return -(int64_t)e - 1000;
+    return (int64_t)blocks * 256 * (int64_t)iters * 64 * 2;            // FLOPs of the launch (FMA = 2)
+}
 
 int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_intensity,
                       const float* in_wavelength,
