@@ -81,6 +81,34 @@ typedef struct {
                           by the non-sequential trace only, or NULL                                       */
 } rtt_sensor_t;
 
+/* Ray source: the bundle is GENERATED inside the kernels instead of being read from memory
+ * (rays/bundle.py:30-171 `Bundle.sample`, render/camera.py:39-72 `Camera.generate_rays`).
+ * Ray i of a launch draws Philox4x32-10(counter = first + i [+ state[1]], key = seed [state[0]]),
+ * so a trace and its adjoint (and every rank of a sharded bundle) regenerate identical rays
+ * from 16 bytes of state: a 1e9-ray trace reads no ray input from HBM.
+ *   local sample       DISK  : pos = (r cos th, r sin th, 0), th ~ U(a[2],a[3]), r = sqrt(U(a[0],a[1])); dir = +z
+ *                      LINE  : pos = (U(-a[0],a[0]), 0, 0); dir = +z
+ *                      FAN   : pos = 0; dir = (0, sin th, cos th), th ~ U(-a[0],a[0])
+ *                      POINT : pos = 0; dir = (cos th sin ph, sin th sin ph, cos ph),
+ *                              ph = acos(1 - 2 U(a[0],a[1])), th ~ U(a[2],a[3])
+ *   local -> global    pos @ R^T + T, dir @ R^T  (geom/transform.py:245-276), dir renormalised (rays/ray.py:25)
+ *                      CAMERA: pixel (first+i) mod (W*H), sample (first+i) div (W*H); x = linspace(-a[0],a[0],W)[px],
+ *                              y = linspace(a[1],-a[1],H)[py] (+ U(-.5,.5) pixel jitter for sample > 0);
+ *                              dir = normalise(x*R[0:3] + y*R[3:6] + R[6:9]), pos = T   (rows of R = right, up, forward) */
+enum { RTT_SRC_DISK = 0, RTT_SRC_LINE = 1, RTT_SRC_FAN = 2, RTT_SRC_POINT = 3, RTT_SRC_CAMERA = 4 };
+typedef struct {
+    int32_t kind;            /* RTT_SRC_*                                                           */
+    float a[4];              /* kind parameters, see above                                          */
+    int32_t width, height;   /* CAMERA only                                                         */
+    const float* pose;       /* DEVICE [12]: R row-major [9], T [3]                                 */
+    uint64_t seed;           /* Philox key                                                          */
+    int64_t first;           /* counter of this launch's ray 0 (shard offset)                       */
+    const uint64_t* state;   /* optional DEVICE {key, counter}: replaces `seed`, is added to `first`
+                                (lets a captured CUDA graph draw fresh rays on every replay)        */
+    float intensity;         /* intensity of every generated ray (Rays.initialize default 1)        */
+    float wavelength;        /* wavelength of every generated ray (default 0)                       */
+} rtt_source_t;
+
 typedef struct {
     const float* f;        /* [n_rows, RTT_ROW_F] */
     const int32_t* i;      /* [n_rows, RTT_ROW_I] */
@@ -104,9 +132,11 @@ int64_t rtt_launch_count(void);
  *   in_*        : pos/dir [n,3], intensity [n], wavelength [n] (may be NULL iff n_lut==0)
  *   out_*       : same shapes (may alias the inputs)
  *   hitmask     : [n] uint64, bit r set iff the ray interacted with row r (may be NULL)
- *   sensors     : HOST array of n_sensors requests indexed by the rows' sensor slot        */
+ *   sensors     : HOST array of n_sensors requests indexed by the rows' sensor slot
+ *   source      : NULL, or a ray source that replaces the four in_* arrays (which may then be NULL);
+ *                 with a source the out_* arrays may be NULL too (sensor records / images only)  */
 int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_intensity,
-                      const float* in_wavelength,
+                      const float* in_wavelength, const rtt_source_t* source,
                       float* out_pos, float* out_dir, float* out_intensity, uint64_t* hitmask,
                       const rtt_table_t* table, const rtt_sensor_t* sensors, int32_t n_sensors,
                       int64_t n, int32_t mode, void* stream);
@@ -123,7 +153,7 @@ int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_
  *                 [0, RTT_N_DIFF) are d/d table_f; NULL to skip
  *   g_lut       : [L, n_rows, 2] accumulated gradient of the wavelength LUT, or NULL        */
 int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float* in_intensity,
-                      const float* in_wavelength, const uint64_t* hitmask,
+                      const float* in_wavelength, const rtt_source_t* source, const uint64_t* hitmask,
                       const float* g_out_pos, const float* g_out_dir, const float* g_out_intensity,
                       const float* const* g_record,
                       float* g_in_pos, float* g_in_dir, float* g_in_intensity,
@@ -143,7 +173,7 @@ int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float* in_
  * reference's t > 1e-6 rule at the fp32 ulp of scene-scale coordinates, i.e. by its exact rounding
  * sequence; FMA contraction or approximate division change hit sequences on ~20 % of the rays. */
 int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* in_intensity,
-                         const float* in_wavelength,
+                         const float* in_wavelength, const rtt_source_t* source,
                          float* out_pos, float* out_dir, float* out_intensity,
                          uint8_t* hit_seq, uint8_t* n_hits,
                          const rtt_table_t* table, const rtt_sensor_t* sensors, int32_t n_sensors,
@@ -153,7 +183,8 @@ int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* 
  * reverse sweep.  Same gradient conventions as rtt_trace_seq_bwd; g_record[slot] is the upstream
  * gradient [record_hits[slot], n, 4] of that sensor's records (record_hits: HOST array, NULL = all 1). */
 int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float* in_intensity,
-                         const float* in_wavelength, const uint8_t* hit_seq, int32_t nbounces,
+                         const float* in_wavelength, const rtt_source_t* source,
+                         const uint8_t* hit_seq, int32_t nbounces,
                          const float* g_out_pos, const float* g_out_dir, const float* g_out_intensity,
                          const float* const* g_record, const int32_t* record_hits,
                          float* g_in_pos, float* g_in_dir, float* g_in_intensity,
@@ -186,6 +217,32 @@ int rtt_surface_step_bwd(const float* in_pos, const float* in_dir, const float* 
                          float* g_in_pos, float* g_in_dir, float* g_table, float* g_lut,
                          const rtt_table_t* table, int32_t row,
                          int64_t n, int32_t mode, void* stream);
+
+/* Bundle.sample(N) -> Rays on the device          (rays/bundle.py:30-37, render/camera.py:39-72)
+ * Materialises the rays of `source` (the same rays the traces of the same `mode` generate in-kernel from it).
+ * pos/dir [n,3], intensity [n]; wavelength [n] may be NULL. */
+int rtt_sample_bundle(const rtt_source_t* source, float* pos, float* dir, float* intensity, float* wavelength,
+                      int64_t n, int32_t mode, void* stream);
+
+/* Sensor reductions of the optimisation goals      (optim/goals.py:42-96, 99-187;
+ * elements/sensor.py:67-176), on raw sensor records rec[m] = (x, y, z, w) (w == 0: no hit).
+ * Two-stage deterministic sums: per-block partials in `work` (DEVICE, RTT_SPOT_WORK floats, zeroed
+ * once by the caller; the kernels leave it zeroed), last block adds them in a fixed order.
+ *
+ * rtt_spot_moments:      out[0..3] = (sum w, sum w x, sum w y, #{w > 0}); active_only != 0 drops w <= 0
+ *                        (optim/goals.py:165) — SpotTargetLoss takes every recorded hit (:76-88).
+ * rtt_spot_moments_bwd:  g_rec[m] = (g[1] w, g[2] w, 0, g[0] + g[1] x + g[2] y) (0 where dropped); g = DEVICE [3]
+ * rtt_spot_size_fwd:     with W = max(mom[0], 1e-12), centre c = target (DEVICE [2]) or (mom[1], mom[2]) / W:
+ *                        out[0] = sum_i sqrt(q_i), q_i = |xy_i - c|^2 w_i / W over w_i > 0 (optim/goals.py:176-183);
+ *                        out[1..2] = d out[0] / d c (needed by the backward)
+ * rtt_spot_size_bwd:     g_rec[m] = g_loss[0] * d out[0] / d rec[m], through c and W unless target is given */
+enum { RTT_SPOT_WORK = 4 * 1024 + 4 };
+int rtt_spot_moments(const float* rec, int64_t m, int32_t active_only, float* out4, float* work, void* stream);
+int rtt_spot_moments_bwd(const float* rec, int64_t m, int32_t active_only, const float* g3, float* g_rec, void* stream);
+int rtt_spot_size_fwd(const float* rec, int64_t m, const float* mom4, const float* target_xy, float* out3,
+                      float* work, void* stream);
+int rtt_spot_size_bwd(const float* rec, int64_t m, const float* mom4, const float* target_xy, const float* out3,
+                      const float* g_loss, float* g_rec, void* stream);
 
 /* Measurement helper (bench.py): launches a pure-FMA kernel (8 independent chains per thread,
  * 8 blocks of 256 threads per SM, `iters` x 64 FMAs per thread) on `stream` and returns the FLOPs

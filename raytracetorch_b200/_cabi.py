@@ -33,20 +33,39 @@ class SensorReq(ct.Structure):
                 ("record_hits", ct.c_int32), ("count", ct.c_void_p)]
 
 
+class SourceReq(ct.Structure):
+    """rtt_source_t"""
+    _fields_ = [("kind", ct.c_int32), ("a", ct.c_float * 4), ("width", ct.c_int32), ("height", ct.c_int32),
+                ("pose", ct.c_void_p), ("seed", ct.c_uint64), ("first", ct.c_int64), ("state", ct.c_void_p),
+                ("intensity", ct.c_float), ("wavelength", ct.c_float)]
+
+
+SRC_DISK, SRC_LINE, SRC_FAN, SRC_POINT, SRC_CAMERA = 0, 1, 2, 3, 4
+SPOT_WORK = 4 * 1024 + 4
+
+
+def make_source(kind: int, a: Sequence[float], pose_ptr: int, *, seed: int = 0, first: int = 0, state_ptr: int = 0,
+                width: int = 0, height: int = 0, intensity: float = 1.0, wavelength: float = 0.0) -> SourceReq:
+    a = list(a) + [0.0] * (4 - len(a))
+    return SourceReq(kind, (ct.c_float * 4)(*a), width, height, pose_ptr or None, seed & (2 ** 64 - 1), first,
+                     state_ptr or None, intensity, wavelength)
+
+
 class TableReq(ct.Structure):
     _fields_ = [("f", ct.c_void_p), ("i", ct.c_void_p), ("n_rows", ct.c_int32), ("n_lut", ct.c_int32),
                 ("lut", ct.c_void_p), ("lut_w", ct.c_void_p)]
 
 
 _P = ct.c_void_p
+_SRC = ct.POINTER(SourceReq)
 _SIGS = {
-    "rtt_trace_seq_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, ct.POINTER(TableReq), ct.POINTER(SensorReq),
+    "rtt_trace_seq_fwd": [_P, _P, _P, _P, _SRC, _P, _P, _P, _P, ct.POINTER(TableReq), ct.POINTER(SensorReq),
                           ct.c_int32, ct.c_int64, ct.c_int32, _P],
-    "rtt_trace_seq_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, ct.POINTER(_P), _P, _P, _P, _P, _P,
+    "rtt_trace_seq_bwd": [_P, _P, _P, _P, _SRC, _P, _P, _P, _P, ct.POINTER(_P), _P, _P, _P, _P, _P,
                           ct.POINTER(TableReq), ct.c_int32, ct.c_int64, ct.c_int32, _P],
-    "rtt_trace_nonseq_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, ct.POINTER(TableReq), ct.POINTER(SensorReq),
+    "rtt_trace_nonseq_fwd": [_P, _P, _P, _P, _SRC, _P, _P, _P, _P, _P, ct.POINTER(TableReq), ct.POINTER(SensorReq),
                              ct.c_int32, ct.c_int32, ct.c_int64, ct.c_int32, _P],
-    "rtt_trace_nonseq_bwd": [_P, _P, _P, _P, _P, ct.c_int32, _P, _P, _P, ct.POINTER(_P), ct.POINTER(ct.c_int32),
+    "rtt_trace_nonseq_bwd": [_P, _P, _P, _P, _SRC, _P, ct.c_int32, _P, _P, _P, ct.POINTER(_P), ct.POINTER(ct.c_int32),
                              _P, _P, _P, _P, _P,
                              ct.POINTER(TableReq), ct.c_int32, ct.c_int64, ct.c_int32, _P],
     "rtt_intersect_test": [_P, _P, _P, ct.POINTER(TableReq), ct.c_int32, ct.c_int32, ct.c_int64, ct.c_int32, _P],
@@ -54,6 +73,11 @@ _SIGS = {
                              ct.c_int64, ct.c_int32, _P],
     "rtt_surface_step_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ct.POINTER(TableReq), ct.c_int32,
                              ct.c_int64, ct.c_int32, _P],
+    "rtt_sample_bundle": [_SRC, _P, _P, _P, _P, ct.c_int64, ct.c_int32, _P],
+    "rtt_spot_moments": [_P, ct.c_int64, ct.c_int32, _P, _P, _P],
+    "rtt_spot_moments_bwd": [_P, ct.c_int64, ct.c_int32, _P, _P, _P],
+    "rtt_spot_size_fwd": [_P, ct.c_int64, _P, _P, _P, _P, _P],
+    "rtt_spot_size_bwd": [_P, ct.c_int64, _P, _P, _P, _P, _P, _P],
 }
 # symbols every build of the CUDA library must export (tests/test_cabi.py checks them)
 EXPORTS = tuple(_SIGS) + ("rtt_version", "rtt_layout_query", "rtt_error_string", "rtt_launch_count")

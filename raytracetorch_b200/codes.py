@@ -56,3 +56,7 @@ MAX_ROWS = 64               # rows staged in shared memory per launch
 MAX_SENSORS = 4
 MAX_WAVELENGTHS = 8
 MAX_BOUNCES = 255           # hit sequence is stored one byte per bounce
+
+# ray source kinds (rtt_source_t.kind) and the scratch size of the goal reductions
+SRC_DISK, SRC_LINE, SRC_FAN, SRC_POINT, SRC_CAMERA = 0, 1, 2, 3, 4
+SPOT_WORK = 4 * 1024 + 4

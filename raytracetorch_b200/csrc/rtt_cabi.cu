@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "../../include/rtt_b200.h"
+#include "rtt_internal.h"
 
 // Each variant TU defines the same structs in its own namespace; re-declare what we launch.
 #define RTT_VARIANT fast
@@ -65,7 +66,27 @@ int finish(cudaError_t e) {
     return (int)e;
 }
 
+// rtt_source_t -> the kernels' by-value copy; kind = -1 when the rays come from memory
+template <class SD>
+int fill_source(SD& d, const rtt_source_t* s) {
+    std::memset(&d, 0, sizeof(d));
+    d.kind = -1;
+    if (!s) return RTT_OK;
+    if (s->kind < RTT_SRC_DISK || s->kind > RTT_SRC_CAMERA || !s->pose) return RTT_E_ARG;
+    if (s->kind == RTT_SRC_CAMERA && (s->width < 1 || s->height < 1)) return RTT_E_ARG;
+    d.kind = s->kind;
+    for (int k = 0; k < 4; ++k) d.a[k] = s->a[k];
+    d.width = s->width; d.height = s->height; d.pose = s->pose;
+    d.seed = s->seed; d.first = s->first;
+    d.state = reinterpret_cast<const unsigned long long*>(s->state);
+    d.intensity = s->intensity; d.wavelength = s->wavelength;
+    return RTT_OK;
+}
+
 }  // namespace
+
+int rtt_internal_finish(cudaError_t e) { return finish(e); }
+int rtt_internal_have_device() { return have_device(); }
 
 // FP32 issue-rate probe: 8 independent FMA chains per thread, nothing else in the loop.
 __global__ void __launch_bounds__(256) k_probe_fp32(int iters, float* out) {
@@ -131,19 +152,22 @@ int64_t rtt_probe_fp32(int32_t iters, float* scratch, void* stream) {
 }
 
 int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_intensity,
-                      const float* in_wavelength,
+                      const float* in_wavelength, const rtt_source_t* source,
                       float* out_pos, float* out_dir, float* out_intensity, uint64_t* hitmask,
                       const rtt_table_t* table, const rtt_sensor_t* sensors, int32_t n_sensors,
                       int64_t n, int32_t mode, void* stream) {
     if (int e = check_table(table)) return e;
     if (n == 0) return RTT_OK;   /* empty bundle: nothing to do, pointers may be NULL */
-    if (n < 0 || !in_pos || !in_dir || !in_intensity || !out_pos || !out_dir || !out_intensity) return RTT_E_ARG;
-    if (table->n_lut > 0 && !in_wavelength) return RTT_E_ARG;
+    if (n < 0) return RTT_E_ARG;
+    if (!source && (!in_pos || !in_dir || !in_intensity || !out_pos || !out_dir || !out_intensity)) return RTT_E_ARG;
+    if (!source && table->n_lut > 0 && !in_wavelength) return RTT_E_ARG;
+    if ((out_pos != nullptr) != (out_dir != nullptr) || (out_pos != nullptr) != (out_intensity != nullptr)) return RTT_E_ARG;
     if (!have_device()) return RTT_E_NO_DEVICE;
     auto st = (cudaStream_t)stream;
 #define RTT_BODY(NS)                                                                                   \
     {                                                                                                  \
         rtt::NS::SeqFwdArgs a;                                                                         \
+        if (int e = fill_source(a.src, source)) return e;                                              \
         a.pos = in_pos; a.dir = in_dir; a.inten = in_intensity; a.wav = in_wavelength;                 \
         a.opos = out_pos; a.odir = out_dir; a.ointen = out_intensity;                                  \
         a.hitmask = reinterpret_cast<unsigned long long*>(hitmask);                                    \
@@ -157,7 +181,7 @@ int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_
 }
 
 int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float* in_intensity,
-                      const float* in_wavelength, const uint64_t* hitmask,
+                      const float* in_wavelength, const rtt_source_t* source, const uint64_t* hitmask,
                       const float* g_out_pos, const float* g_out_dir, const float* g_out_intensity,
                       const float* const* g_record,
                       float* g_in_pos, float* g_in_dir, float* g_in_intensity,
@@ -166,14 +190,16 @@ int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float* in_
                       int64_t n, int32_t mode, void* stream) {
     if (int e = check_table(table)) return e;
     if (n == 0) return RTT_OK;   /* empty bundle: nothing to do, pointers may be NULL */
-    if (n < 0 || !in_pos || !in_dir || !in_intensity || !hitmask) return RTT_E_ARG;
-    if (table->n_lut > 0 && !in_wavelength) return RTT_E_ARG;
+    if (n < 0 || !hitmask) return RTT_E_ARG;
+    if (!source && (!in_pos || !in_dir || !in_intensity)) return RTT_E_ARG;
+    if (!source && table->n_lut > 0 && !in_wavelength) return RTT_E_ARG;
     if (n_sensors < 0 || n_sensors > RTT_MAX_SENSORS) return RTT_E_SENSOR;
     if (!have_device()) return RTT_E_NO_DEVICE;
     auto st = (cudaStream_t)stream;
 #define RTT_BODY(NS)                                                                                   \
     {                                                                                                  \
         rtt::NS::SeqBwdArgs a;                                                                         \
+        if (int e = fill_source(a.src, source)) return e;                                              \
         a.pos = in_pos; a.dir = in_dir; a.inten = in_intensity; a.wav = in_wavelength;                 \
         a.hitmask = reinterpret_cast<const unsigned long long*>(hitmask);                              \
         a.g_opos = g_out_pos; a.g_odir = g_out_dir; a.g_ointen = g_out_intensity;                      \
@@ -192,22 +218,25 @@ int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float* in_
 }
 
 int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* in_intensity,
-                         const float* in_wavelength,
+                         const float* in_wavelength, const rtt_source_t* source,
                          float* out_pos, float* out_dir, float* out_intensity,
                          uint8_t* hit_seq, uint8_t* n_hits,
                          const rtt_table_t* table, const rtt_sensor_t* sensors, int32_t n_sensors,
                          int32_t nbounces, int64_t n, int32_t mode, void* stream) {
     if (int e = check_table(table)) return e;
     if (n == 0) return RTT_OK;   /* empty bundle: nothing to do, pointers may be NULL */
-    if (n < 0 || !in_pos || !in_dir || !in_intensity || !out_pos || !out_dir || !out_intensity) return RTT_E_ARG;
+    if (n < 0) return RTT_E_ARG;
+    if (!source && (!in_pos || !in_dir || !in_intensity || !out_pos || !out_dir || !out_intensity)) return RTT_E_ARG;
+    if ((out_pos != nullptr) != (out_dir != nullptr) || (out_pos != nullptr) != (out_intensity != nullptr)) return RTT_E_ARG;
     if (nbounces < 0 || (hit_seq && nbounces > RTT_MAX_BOUNCES)) return RTT_E_ARG;
     if (table->n_rows > 255) return RTT_E_ROWS;
-    if (table->n_lut > 0 && !in_wavelength) return RTT_E_ARG;
+    if (!source && table->n_lut > 0 && !in_wavelength) return RTT_E_ARG;
     if (!have_device()) return RTT_E_NO_DEVICE;
     auto st = (cudaStream_t)stream;
 #define RTT_BODY(NS)                                                                                   \
     {                                                                                                  \
         rtt::NS::NonseqFwdArgs a;                                                                      \
+        if (int e = fill_source(a.src, source)) return e;                                              \
         a.pos = in_pos; a.dir = in_dir; a.inten = in_intensity; a.wav = in_wavelength;                 \
         a.opos = out_pos; a.odir = out_dir; a.ointen = out_intensity;                                  \
         a.hit_seq = hit_seq; a.n_hits = n_hits;                                                        \
@@ -222,7 +251,8 @@ int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* 
 }
 
 int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float* in_intensity,
-                         const float* in_wavelength, const uint8_t* hit_seq, int32_t nbounces,
+                         const float* in_wavelength, const rtt_source_t* source,
+                         const uint8_t* hit_seq, int32_t nbounces,
                          const float* g_out_pos, const float* g_out_dir, const float* g_out_intensity,
                          const float* const* g_record, const int32_t* record_hits,
                          float* g_in_pos, float* g_in_dir, float* g_in_intensity,
@@ -231,15 +261,17 @@ int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float* 
                          int64_t n, int32_t mode, void* stream) {
     if (int e = check_table(table)) return e;
     if (n == 0) return RTT_OK;   /* empty bundle: nothing to do, pointers may be NULL */
-    if (n < 0 || !in_pos || !in_dir || !in_intensity || !hit_seq) return RTT_E_ARG;
+    if (n < 0 || !hit_seq) return RTT_E_ARG;
+    if (!source && (!in_pos || !in_dir || !in_intensity)) return RTT_E_ARG;
     if (nbounces < 0 || nbounces > RTT_MAX_BOUNCES) return RTT_E_ARG;
     if (n_sensors < 0 || n_sensors > RTT_MAX_SENSORS) return RTT_E_SENSOR;
-    if (table->n_lut > 0 && !in_wavelength) return RTT_E_ARG;
+    if (!source && table->n_lut > 0 && !in_wavelength) return RTT_E_ARG;
     if (!have_device()) return RTT_E_NO_DEVICE;
     auto st = (cudaStream_t)stream;
 #define RTT_BODY(NS)                                                                                   \
     {                                                                                                  \
         rtt::NS::NonseqBwdArgs a;                                                                      \
+        if (int e = fill_source(a.src, source)) return e;                                              \
         a.pos = in_pos; a.dir = in_dir; a.inten = in_intensity; a.wav = in_wavelength;                 \
         a.hit_seq = hit_seq;                                                                           \
         a.g_opos = g_out_pos; a.g_odir = g_out_dir; a.g_ointen = g_out_intensity;                      \
@@ -256,6 +288,23 @@ int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float* 
     }
     (void)mode;   /* one arithmetic only: see include/rtt_b200.h */
     RTT_BODY(exact)
+#undef RTT_BODY
+}
+
+int rtt_sample_bundle(const rtt_source_t* source, float* pos, float* dir, float* intensity, float* wavelength,
+                      int64_t n, int32_t mode, void* stream) {
+    if (n == 0) return RTT_OK;
+    if (n < 0 || !source || !pos || !dir || !intensity) return RTT_E_ARG;
+    if (!have_device()) return RTT_E_NO_DEVICE;
+    auto st = (cudaStream_t)stream;
+#define RTT_BODY(NS)                                                                                   \
+    {                                                                                                  \
+        rtt::NS::SampleArgs a;                                                                         \
+        if (int e = fill_source(a.src, source)) return e;                                              \
+        a.pos = pos; a.dir = dir; a.inten = intensity; a.wav = wavelength; a.n = n;                    \
+        return finish(rtt::NS::launch_sample_##NS(a, st));                                             \
+    }
+    if (mode == RTT_MODE_EXACT) RTT_BODY(exact) else RTT_BODY(fast)
 #undef RTT_BODY
 }
 

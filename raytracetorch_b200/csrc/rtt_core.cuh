@@ -543,6 +543,105 @@ RTT_HD bool sensor_bin(float x, float y, float x0, float y0, float sx, float sy,
 }
 
 // =============================================================================================
+// Ray sources (rays/bundle.py:30-171, render/camera.py:39-72): rays generated from a counter-based
+// RNG instead of being read from memory.  Integer part (Philox4x32-10) is bit-identical on host
+// and device; the float part uses the accurate libm calls (sincosf / acosf / sqrtf).
+// =============================================================================================
+// The source record is a template parameter: rtt_source_t itself (host checker) or the kernels' by-value
+// copy of it (rtt_kernels_decl.h SourceDev); both have the fields kind, a[4], width, height, pose, seed,
+// first, state.
+RTT_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    for (int round = 0; round < 10; ++round) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// [0, 1) with 24 random bits, like torch.rand in fp32
+RTT_HD float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+// torch.linspace(start, end, steps)[i]: symmetric evaluation from both ends
+RTT_HD float linspace_at(float start, float end, int steps, int i) {
+    if (steps <= 1) return start;
+    const float step = (end - start) / (float)(steps - 1);
+    return (i < steps / 2) ? fmaf(step, (float)i, start) : fmaf(-step, (float)(steps - 1 - i), end);
+}
+
+struct SourceKey { unsigned long long key, base; };
+template <class SRC>
+RTT_HD SourceKey source_key(const SRC& s) {
+    SourceKey k;
+    k.key = s.state ? s.state[0] : s.seed;
+    k.base = (unsigned long long)s.first + (s.state ? s.state[1] : 0ull);
+    return k;
+}
+
+// Ray i of the source, in the global frame, direction normalised (Rays.__post_init__, rays/ray.py:25).
+template <class SRC>
+RTT_HD void source_ray(const SRC& s, SourceKey k, long long i, V3& p, V3& d) {
+    const unsigned long long ctr = k.base + (unsigned long long)i;
+    uint32_t r[4];
+    philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, (uint32_t)k.key, (uint32_t)(k.key >> 32), r);
+    const float u0 = u01(r[0]), u1 = u01(r[1]);
+    const float* R = s.pose;
+    const V3 T = ld3(s.pose + 9);
+    V3 pl = v3(0.0f, 0.0f, 0.0f), dl = v3(0.0f, 0.0f, 1.0f);
+    float len;
+    switch (s.kind) {
+        case RTT_SRC_DISK: {                                            // rays/bundle.py:40-56, 83-100
+            const float th = fmaf(u0, s.a[3] - s.a[2], s.a[2]);
+            const float rr = sqrtf(fmaf(u1, s.a[1] - s.a[0], s.a[0]));
+            float sn, cs;
+            sincosf(th, &sn, &cs);
+            pl = v3(rr * cs, rr * sn, 0.0f);
+            break;
+        }
+        case RTT_SRC_LINE:                                              // rays/bundle.py:103-118
+            pl = v3(fmaf(u0, 2.0f * s.a[0], -s.a[0]), 0.0f, 0.0f);
+            break;
+        case RTT_SRC_FAN: {                                             // rays/bundle.py:121-140
+            const float th = fmaf(u0, 2.0f * s.a[0], -s.a[0]);
+            float sn, cs;
+            sincosf(th, &sn, &cs);
+            dl = v3(0.0f, sn, cs);
+            break;
+        }
+        case RTT_SRC_POINT: {                                           // rays/bundle.py:58-80, 143-170
+            const float ph = acosf(fmaf(-2.0f, fmaf(u0, s.a[1] - s.a[0], s.a[0]), 1.0f));
+            const float th = fmaf(u1, s.a[3] - s.a[2], s.a[2]);
+            float sp, cp, st, ct;
+            sincosf(ph, &sp, &cp);
+            sincosf(th, &st, &ct);
+            dl = v3(ct * sp, st * sp, cp);
+            break;
+        }
+        default: {                                                      // RTT_SRC_CAMERA: render/camera.py:39-72
+            const long long npix = (long long)s.width * s.height;
+            const long long g = (long long)ctr;
+            const long long pix = g % npix, smp = g / npix;
+            const int px = (int)(pix % s.width), py = (int)(pix / s.width);
+            float x = linspace_at(-s.a[0], s.a[0], s.width, px);
+            float y = linspace_at(s.a[1], -s.a[1], s.height, py);
+            if (smp > 0) {                                              // extension: jittered sub-pixel samples
+                x = fmaf(u0 - 0.5f, 2.0f * s.a[0] / (float)(s.width > 1 ? s.width - 1 : 1), x);
+                y = fmaf(u1 - 0.5f, 2.0f * s.a[1] / (float)(s.height > 1 ? s.height - 1 : 1), y);
+            }
+            const V3 dg = v3(fmaf(y, R[3], fmaf(x, R[0], R[6])), fmaf(y, R[4], fmaf(x, R[1], R[7])), fmaf(y, R[5], fmaf(x, R[2], R[8])));
+            p = T;
+            d = normalize12(dg, &len);
+            return;
+        }
+    }
+    p = mul_RT(pl, R) + T;                                              // geom/transform.py:262-268
+    d = normalize12(mul_RT(dl, R), &len);
+}
+
+// =============================================================================================
 // Adjoint
 // =============================================================================================
 // Gradient of one row's differentiable entries, in table_f order [0, RTT_N_DIFF).

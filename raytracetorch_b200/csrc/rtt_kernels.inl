@@ -98,6 +98,28 @@ __device__ __forceinline__ Ior row_ior(const SmemTable& T, int S, int L, int r, 
 __device__ __forceinline__ V3 load3(const float* a, long long i) { return v3(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
 __device__ __forceinline__ void store3(float* a, long long i, V3 v) { a[3 * i] = v.x; a[3 * i + 1] = v.y; a[3 * i + 2] = v.z; }
 
+// Ray i of a launch: read from the caller's arrays, or generated from the ray source (no HBM input).
+struct RayIn { V3 p, d; float I, wav; };
+template <class Args>
+__device__ __forceinline__ RayIn fetch_ray(const Args& a, SourceKey key, long long i, bool want_wav) {
+    RayIn r;
+    if (a.src.kind >= 0) {
+        source_ray(a.src, key, i, r.p, r.d);
+        r.I = a.src.intensity; r.wav = a.src.wavelength;
+    } else {
+        r.p = load3(a.pos, i); r.d = load3(a.dir, i);
+        r.I = a.inten[i];
+        r.wav = want_wav ? a.wav[i] : 0.0f;
+    }
+    return r;
+}
+template <class Args>
+__device__ __forceinline__ SourceKey fetch_key(const Args& a) {
+    SourceKey k; k.key = 0ull; k.base = 0ull;
+    if (a.src.kind >= 0) k = source_key(a.src);
+    return k;
+}
+
 // ---- sensor image accumulation ---------------------------------------------------------------
 // Focused bundles put ~all rays of a launch into a handful of bins (C1: a 1e8-ray bundle focused
 // onto a few pixels), so plain global atomics serialise in L2.  Two levels of privatisation:
@@ -215,10 +237,12 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_fwd)(const __gr
     stage_table(a.tab, T);
     const int S = a.tab.S, L = a.tab.L;
     const long long stride = (long long)gridDim.x * blockDim.x;
+    const SourceKey skey = fetch_key(a);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
-        V3 p = load3(a.pos, i), d = load3(a.dir, i);
-        float I = a.inten[i];
-        const int lam = (L > 0) ? wavelength_index(T, L, a.wav[i]) : 0;
+        const RayIn ray = fetch_ray(a, skey, i, L > 0);
+        V3 p = ray.p, d = ray.d;
+        float I = ray.I;
+        const int lam = (L > 0) ? wavelength_index(T, L, ray.wav) : 0;
         unsigned long long mask = 0ull, bit = 1ull;
         int op_next = T.rows[0].i[DI_OPCODE];
         for (int r = 0; r < S; ++r, bit += bit) {
@@ -232,8 +256,7 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_fwd)(const __gr
                 default: seq_row<KDyn>(T, S, L, r, lam, i, a, cache, p, d, I, mask, bit); break;
             }
         }
-        store3(a.opos, i, p); store3(a.odir, i, d);
-        a.ointen[i] = I;
+        if (a.opos) { store3(a.opos, i, p); store3(a.odir, i, d); a.ointen[i] = I; }
         if (a.hitmask) a.hitmask[i] = mask;
     }
     img_cache_flush(cache, a.sens);
@@ -345,6 +368,7 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_bwd)(const __gr
     stage_table(a.tab, T);
 
     const long long stride = (long long)gridDim.x * blockDim.x;
+    const SourceKey skey = fetch_key(a);
     for (long long base = (long long)blockIdx.x * blockDim.x; base < a.n; base += stride) {
         const long long i = base + threadIdx.x;
         const bool live = i < a.n;
@@ -353,8 +377,9 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_bwd)(const __gr
         int lam = 0;
         if (live) {
             mask = a.hitmask[i];
-            p = load3(a.pos, i); d = load3(a.dir, i);
-            if (L > 0) lam = wavelength_index(T, L, a.wav[i]);
+            const RayIn ray = fetch_ray(a, skey, i, L > 0);
+            p = ray.p; d = ray.d;
+            if (L > 0) lam = wavelength_index(T, L, ray.wav);
         }
         // ---- forward replay over the recorded interactions (row loop is warp-uniform) ----
         Checkpoint ck[RTT_MAX_ROWS];
@@ -449,10 +474,12 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
     stage_table(a.tab, T);
     const int S = a.tab.S, L = a.tab.L, NB = a.nbounces;
     const long long stride = (long long)gridDim.x * blockDim.x;
+    const SourceKey skey = fetch_key(a);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
-        V3 p = load3(a.pos, i), d = load3(a.dir, i);
-        float I = a.inten[i];
-        const int lam = (L > 0) ? wavelength_index(T, L, a.wav[i]) : 0;
+        const RayIn ray = fetch_ray(a, skey, i, L > 0);
+        V3 p = ray.p, d = ray.d;
+        float I = ray.I;
+        const int lam = (L > 0) ? wavelength_index(T, L, ray.wav) : 0;
         unsigned cnts = 0u;                                             // 8 bits per sensor slot
         int nb = 0;
         for (; nb < NB; ++nb) {
@@ -491,8 +518,7 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
             if (a.sens[s].count) a.sens[s].count[i] = (unsigned char)((cnts >> (8 * s)) & 255u);
         if (a.hit_seq) for (int b = nb; b < NB; ++b) a.hit_seq[i * NB + b] = 255;
         if (a.n_hits) a.n_hits[i] = (unsigned char)nb;
-        store3(a.opos, i, p); store3(a.odir, i, d);
-        a.ointen[i] = I;
+        if (a.opos) { store3(a.opos, i, p); store3(a.odir, i, d); a.ointen[i] = I; }
     }
     img_cache_flush(cache, a.sens);
 }
@@ -512,9 +538,11 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_bwd)(const _
     for (int idx = threadIdx.x; idx < S * RTT_ROW_G + L * S * 2; idx += blockDim.x) acc[idx] = 0.0f;
     stage_table(a.tab, T);
     const long long stride = (long long)gridDim.x * blockDim.x;
+    const SourceKey skey = fetch_key(a);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
-        V3 p = load3(a.pos, i), d = load3(a.dir, i);
-        const int lam = (L > 0) ? wavelength_index(T, L, a.wav[i]) : 0;
+        const RayIn ray = fetch_ray(a, skey, i, L > 0);
+        V3 p = ray.p, d = ray.d;
+        const int lam = (L > 0) ? wavelength_index(T, L, ray.wav) : 0;
         Checkpoint ck[kMaxReplay];
         unsigned char rows_hit[kMaxReplay];
         int nh = 0;
@@ -683,6 +711,21 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_surface_step_bwd)(const _
 }
 
 // ============================================================================================
+// Bundle.sample (rays/bundle.py:30-37): materialise the rays of a source
+// ============================================================================================
+__global__ void __launch_bounds__(kThreads) RTT_NAME(k_sample_bundle)(const __grid_constant__ SampleArgs a) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const SourceKey skey = source_key(a.src);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        V3 p, d;
+        source_ray(a.src, skey, i, p, d);
+        store3(a.pos, i, p); store3(a.dir, i, d);
+        a.inten[i] = a.src.intensity;
+        if (a.wav) a.wav[i] = a.src.wavelength;
+    }
+}
+
+// ============================================================================================
 // Host launchers
 // ============================================================================================
 inline int sm_count() {
@@ -743,6 +786,11 @@ cudaError_t RTT_NAME(launch_step_fwd)(const StepFwdArgs& a, cudaStream_t st) {
 }
 cudaError_t RTT_NAME(launch_step_bwd)(const StepBwdArgs& a, cudaStream_t st) {
     RTT_NAME(k_surface_step_bwd)<<<grid_for(a.n, 4), kThreads, bwd_smem(a.tab.S, a.tab.L), st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t RTT_NAME(launch_sample)(const SampleArgs& a, cudaStream_t st) {
+    RTT_NAME(k_sample_bundle)<<<grid_for(a.n, 8), kThreads, 0, st>>>(a);
     return cudaGetLastError();
 }
 

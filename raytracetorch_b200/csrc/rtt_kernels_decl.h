@@ -14,6 +14,23 @@
 namespace rtt {
 namespace RTT_VARIANT {
 
+struct SourceDev {                  // ray source (rtt_source_t); kind < 0 = rays are read from memory
+    int kind;
+    float a[4];
+    int width, height;
+    const float* pose;
+    unsigned long long seed;
+    long long first;
+    const unsigned long long* state;
+    float intensity, wavelength;
+};
+
+struct SampleArgs {
+    SourceDev src;
+    float *pos, *dir, *inten, *wav;
+    long long n;
+};
+
 struct SensorDev {
     float* image;
     float* record;
@@ -32,6 +49,7 @@ struct TableDev {
 };
 
 struct SeqFwdArgs {
+    SourceDev src;
     const float *pos, *dir, *inten, *wav;
     float *opos, *odir, *ointen;
     unsigned long long* hitmask;
@@ -42,6 +60,7 @@ struct SeqFwdArgs {
 };
 
 struct SeqBwdArgs {
+    SourceDev src;
     const float *pos, *dir, *inten, *wav;
     const unsigned long long* hitmask;
     const float *g_opos, *g_odir, *g_ointen;
@@ -54,6 +73,7 @@ struct SeqBwdArgs {
 };
 
 struct NonseqFwdArgs {
+    SourceDev src;
     const float *pos, *dir, *inten, *wav;
     float *opos, *odir, *ointen;
     unsigned char *hit_seq, *n_hits;
@@ -64,6 +84,7 @@ struct NonseqFwdArgs {
 };
 
 struct NonseqBwdArgs {
+    SourceDev src;
     const float *pos, *dir, *inten, *wav;
     const unsigned char* hit_seq;
     const float *g_opos, *g_odir, *g_ointen;
@@ -108,6 +129,7 @@ cudaError_t RTT_NAME(launch_nonseq_bwd)(const NonseqBwdArgs& a, cudaStream_t st)
 cudaError_t RTT_NAME(launch_intersect_test)(const IsectArgs& a, cudaStream_t st);
 cudaError_t RTT_NAME(launch_step_fwd)(const StepFwdArgs& a, cudaStream_t st);
 cudaError_t RTT_NAME(launch_step_bwd)(const StepBwdArgs& a, cudaStream_t st);
+cudaError_t RTT_NAME(launch_sample)(const SampleArgs& a, cudaStream_t st);
 
 }  // namespace RTT_VARIANT
 }  // namespace rtt

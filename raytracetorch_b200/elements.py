@@ -354,6 +354,8 @@ class Sensor(Element):
                                   f"trace but only {depth} interactions per ray were kept; raise Scene.record_depth")
                 if depth > 1 and most < depth:
                     continue                               # nobody got this far: no empty list entry
+            hit = hit() if callable(hit) else hit          # masks / ids are built only when somebody reads the lists
+            ids = ids() if callable(ids) else ids
             sel = record[hit]
             self._locs.append(sel[:, :3])
             self._w.append(sel[:, 3])

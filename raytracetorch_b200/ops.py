@@ -104,6 +104,139 @@ def _image_numel(sensor_cfg: Sequence[float]) -> int:
 # =============================================================================================
 # custom ops (opaque to autograd; the Functions below wire the adjoints)
 # =============================================================================================
+SRC_CFG = 10   # floats per ray source in `src_cfg`: kind, a0..a3, width, height, intensity, wavelength, first
+
+
+def source_cfg_of(rays) -> List[float]:
+    sp = rays.source
+    return [float(sp["kind"]), *map(float, sp["a"]), float(sp["width"]), float(sp["height"]),
+            float(sp["intensity"]), float(sp["wavelength"]), float(sp["first"])]
+
+
+def _source_req(src_cfg: Sequence[float], pose: torch.Tensor, state: torch.Tensor):
+    kind, a0, a1, a2, a3, width, height, inten, wav, first = src_cfg
+    return _cabi.make_source(int(kind), [a0, a1, a2, a3], pose.data_ptr(), first=int(first), state_ptr=state.data_ptr(),
+                             width=int(width), height=int(height), intensity=inten, wavelength=wav)
+
+
+def _seq_fwd_body(dev, n, pos, dir, intensity, wavelength, src, table_f, table_i, lut, lut_w, sensor_cfg,
+                  want_record, want_rays, mode):
+    lib = _cabi.load()
+    ns = len(sensor_cfg) // SENSOR_CFG
+    f32 = dict(dtype=torch.float32, device=dev)
+    opos = torch.empty((n, 3) if want_rays else (0, 3), **f32)
+    odir = torch.empty((n, 3) if want_rays else (0, 3), **f32)
+    oint = torch.empty(n if want_rays else 0, **f32)
+    hitmask = torch.empty(n, dtype=torch.int64, device=dev)
+    records = torch.zeros((ns, n, 4), **f32) if (want_record and ns) else torch.empty((0, n, 4), **f32)
+    images = torch.zeros(_image_numel(sensor_cfg), **f32)
+    sens, cnt = _sensor_reqs(sensor_cfg, n, records if (want_record and ns) else None, images)
+    req = _table_req(table_f, table_i, lut, lut_w)
+    with torch.cuda.device(dev):
+        lib.call("rtt_trace_seq_fwd", _ptr(pos), _ptr(dir), _ptr(intensity), _ptr(wavelength),
+                 ct.byref(src) if src is not None else None,
+                 _ptr(opos), _ptr(odir), _ptr(oint), hitmask.data_ptr(),
+                 ct.byref(req), sens, cnt, n, mode, _stream(table_f))
+    return [opos, odir, oint, hitmask, records, images]
+
+
+def _seq_bwd_body(dev, n, pos, dir, intensity, wavelength, src, hitmask, g_pos, g_dir, g_int, g_records,
+                  table_f, table_i, lut, lut_w, need_rays, need_table, mode):
+    lib = _cabi.load()
+    S = table_f.shape[0]
+    f32 = dict(dtype=torch.float32, device=dev)
+    e = torch.empty(0, **f32)
+    gp = torch.empty((n, 3), **f32) if need_rays else e
+    gd = torch.empty((n, 3), **f32) if need_rays else e
+    gi = torch.empty(n, **f32) if need_rays else e
+    gt = torch.zeros((S, C.ROW_G), **f32) if need_table else e
+    has_lut = lut is not None and lut.numel() > 0
+    gl = torch.zeros_like(lut) if (need_table and has_lut) else e
+    ns = 0 if g_records is None else g_records.shape[0]
+    rec_arr = (ct.c_void_p * ns)(*[g_records[s].data_ptr() for s in range(ns)]) if ns else None
+    req = _table_req(table_f, table_i, lut, lut_w)
+    with torch.cuda.device(dev):
+        lib.call("rtt_trace_seq_bwd", _ptr(pos), _ptr(dir), _ptr(intensity), _ptr(wavelength),
+                 ct.byref(src) if src is not None else None,
+                 hitmask.data_ptr(), _ptr(g_pos), _ptr(g_dir), _ptr(g_int), rec_arr,
+                 _ptr(gp), _ptr(gd), _ptr(gi), _ptr(gt), _ptr(gl), ct.byref(req), ns, n, mode, _stream(table_f))
+    return [gp, gd, gi, gt, gl]
+
+
+def _nonseq_fwd_body(dev, n, pos, dir, intensity, wavelength, src, table_f, table_i, lut, lut_w, sensor_cfg,
+                     want_record, want_rays, nbounces, mode, record_depth):
+    lib = _cabi.load()
+    ns = len(sensor_cfg) // SENSOR_CFG
+    f32 = dict(dtype=torch.float32, device=dev)
+    opos = torch.empty((n, 3) if want_rays else (0, 3), **f32)
+    odir = torch.empty((n, 3) if want_rays else (0, 3), **f32)
+    oint = torch.empty(n if want_rays else 0, **f32)
+    seq = torch.empty((n, nbounces), dtype=torch.uint8, device=dev)
+    nh = torch.empty(n, dtype=torch.uint8, device=dev)
+    K = max(1, int(record_depth))
+    rec_on = bool(want_record and ns)
+    records = torch.zeros((ns, K, n, 4), **f32) if rec_on else torch.empty((0, K, n, 4), **f32)
+    counts = torch.zeros((ns if rec_on else 0, n), dtype=torch.uint8, device=dev)
+    images = torch.zeros(_image_numel(sensor_cfg), **f32)
+    sens, cnt = _sensor_reqs(sensor_cfg, n, records if rec_on else None, images, counts if rec_on else None, K)
+    req = _table_req(table_f, table_i, lut, lut_w)
+    with torch.cuda.device(dev):
+        lib.call("rtt_trace_nonseq_fwd", _ptr(pos), _ptr(dir), _ptr(intensity), _ptr(wavelength),
+                 ct.byref(src) if src is not None else None,
+                 _ptr(opos), _ptr(odir), _ptr(oint), seq.data_ptr(), nh.data_ptr(),
+                 ct.byref(req), sens, cnt, nbounces, n, mode, _stream(table_f))
+    return [opos, odir, oint, seq, nh, records, images, counts]
+
+
+def _nonseq_bwd_body(dev, n, pos, dir, intensity, wavelength, src, hit_seq, g_pos, g_dir, g_int, g_records,
+                     table_f, table_i, lut, lut_w, need_rays, need_table, mode):
+    lib = _cabi.load()
+    S = table_f.shape[0]
+    f32 = dict(dtype=torch.float32, device=dev)
+    e = torch.empty(0, **f32)
+    gp = torch.empty((n, 3), **f32) if need_rays else e
+    gd = torch.empty((n, 3), **f32) if need_rays else e
+    gi = torch.empty(n, **f32) if need_rays else e
+    gt = torch.zeros((S, C.ROW_G), **f32) if need_table else e
+    has_lut = lut is not None and lut.numel() > 0
+    gl = torch.zeros_like(lut) if (need_table and has_lut) else e
+    ns = 0 if g_records is None else g_records.shape[0]          # g_records: [ns, K, N, 4]
+    rec_arr = (ct.c_void_p * ns)(*[g_records[s].data_ptr() for s in range(ns)]) if ns else None
+    depth = (ct.c_int32 * ns)(*([g_records.shape[1]] * ns)) if ns else None
+    req = _table_req(table_f, table_i, lut, lut_w)
+    with torch.cuda.device(dev):
+        lib.call("rtt_trace_nonseq_bwd", _ptr(pos), _ptr(dir), _ptr(intensity), _ptr(wavelength),
+                 ct.byref(src) if src is not None else None,
+                 hit_seq.data_ptr(), hit_seq.shape[1], _ptr(g_pos), _ptr(g_dir), _ptr(g_int), rec_arr, depth,
+                 _ptr(gp), _ptr(gd), _ptr(gi), _ptr(gt), _ptr(gl), ct.byref(req), ns, n, mode, _stream(table_f))
+    return [gp, gd, gi, gt, gl]
+
+
+def _fake_seq_fwd(like, n, sensor_cfg, want_record, want_rays):
+    ns = len(sensor_cfg) // SENSOR_CFG
+    m = n if want_rays else 0
+    return [like.new_empty((m, 3)), like.new_empty((m, 3)), like.new_empty(m), like.new_empty(n, dtype=torch.int64),
+            like.new_empty(((ns if want_record else 0), n, 4)), like.new_empty(_image_numel(sensor_cfg))]
+
+
+def _fake_bwd(like, n, table_f, lut, need_rays, need_table):
+    e = like.new_empty(0)
+    return [like.new_empty((n, 3)) if need_rays else e, like.new_empty((n, 3)) if need_rays else e,
+            like.new_empty(n) if need_rays else e,
+            like.new_empty((table_f.shape[0], C.ROW_G)) if need_table else e,
+            torch.empty_like(lut) if (need_table and lut is not None) else e]
+
+
+def _fake_nonseq_fwd(like, n, sensor_cfg, want_record, want_rays, nbounces, record_depth):
+    ns = len(sensor_cfg) // SENSOR_CFG
+    K = max(1, int(record_depth))
+    m = n if want_rays else 0
+    return [like.new_empty((m, 3)), like.new_empty((m, 3)), like.new_empty(m),
+            like.new_empty((n, nbounces), dtype=torch.uint8), like.new_empty(n, dtype=torch.uint8),
+            like.new_empty(((ns if want_record else 0), K, n, 4)), like.new_empty(_image_numel(sensor_cfg)),
+            like.new_empty(((ns if want_record else 0), n), dtype=torch.uint8)]
+
+
 @torch.library.custom_op("rtt_b200::trace_seq_fwd", mutates_args=())
 def _trace_seq_fwd(pos: torch.Tensor, dir: torch.Tensor, intensity: torch.Tensor,
                    wavelength: Optional[torch.Tensor], table_f: torch.Tensor, table_i: torch.Tensor,
@@ -111,30 +244,13 @@ def _trace_seq_fwd(pos: torch.Tensor, dir: torch.Tensor, intensity: torch.Tensor
                    sensor_cfg: List[float], want_record: bool, mode: int) -> List[torch.Tensor]:
     """-> [out_pos, out_dir, out_intensity, hitmask(int64), records [ns,N,4], images (flat)]"""
     _need_cuda(pos, dir, intensity, table_f, table_i)
-    lib = _cabi.load()
-    n = pos.shape[0]
-    ns = len(sensor_cfg) // SENSOR_CFG
-    opos, odir, oint = torch.empty_like(pos), torch.empty_like(dir), torch.empty_like(intensity)
-    hitmask = torch.empty(n, dtype=torch.int64, device=pos.device)
-    records = torch.zeros((ns, n, 4), dtype=torch.float32, device=pos.device) if (want_record and ns) \
-        else torch.empty((0, n, 4), dtype=torch.float32, device=pos.device)
-    images = torch.zeros(_image_numel(sensor_cfg), dtype=torch.float32, device=pos.device)
-    sens, cnt = _sensor_reqs(sensor_cfg, n, records if (want_record and ns) else None, images)
-    req = _table_req(table_f, table_i, lut, lut_w)
-    with torch.cuda.device(pos.device):
-        lib.call("rtt_trace_seq_fwd", pos.data_ptr(), dir.data_ptr(), intensity.data_ptr(), _ptr(wavelength),
-                 opos.data_ptr(), odir.data_ptr(), oint.data_ptr(), hitmask.data_ptr(),
-                 ct.byref(req), sens, cnt, n, mode, _stream(pos))
-    return [opos, odir, oint, hitmask, records, images]
+    return _seq_fwd_body(pos.device, pos.shape[0], pos, dir, intensity, wavelength, None, table_f, table_i, lut, lut_w,
+                         sensor_cfg, want_record, True, mode)
 
 
 @_trace_seq_fwd.register_fake
 def _(pos, dir, intensity, wavelength, table_f, table_i, lut, lut_w, sensor_cfg, want_record, mode):
-    n = pos.shape[0]
-    ns = len(sensor_cfg) // SENSOR_CFG
-    return [torch.empty_like(pos), torch.empty_like(dir), torch.empty_like(intensity),
-            pos.new_empty(n, dtype=torch.int64), pos.new_empty(((ns if want_record else 0), n, 4)),
-            pos.new_empty(_image_numel(sensor_cfg))]
+    return _fake_seq_fwd(pos, pos.shape[0], sensor_cfg, want_record, True)
 
 
 @torch.library.custom_op("rtt_b200::trace_seq_bwd", mutates_args=())
@@ -147,35 +263,49 @@ def _trace_seq_bwd(pos: torch.Tensor, dir: torch.Tensor, intensity: torch.Tensor
                    need_rays: bool, need_table: bool, mode: int) -> List[torch.Tensor]:
     """-> [g_in_pos, g_in_dir, g_in_intensity, g_table [S,ROW_G], g_lut [L,S,2]]"""
     _need_cuda(pos, dir, intensity, table_f, table_i, hitmask)
-    lib = _cabi.load()
-    n, S = pos.shape[0], table_f.shape[0]
-    dev = pos.device
-    gp = torch.empty_like(pos) if need_rays else pos.new_empty(0)
-    gd = torch.empty_like(dir) if need_rays else pos.new_empty(0)
-    gi = torch.empty_like(intensity) if need_rays else pos.new_empty(0)
-    gt = torch.zeros((S, C.ROW_G), dtype=torch.float32, device=dev) if need_table else pos.new_empty(0)
-    has_lut = lut is not None and lut.numel() > 0
-    gl = torch.zeros_like(lut) if (need_table and has_lut) else pos.new_empty(0)
-    ns = 0 if g_records is None else g_records.shape[0]
-    rec_arr = None
-    if ns:
-        rec_arr = (ct.c_void_p * ns)(*[g_records[s].data_ptr() for s in range(ns)])
-    req = _table_req(table_f, table_i, lut, lut_w)
-    with torch.cuda.device(dev):
-        lib.call("rtt_trace_seq_bwd", pos.data_ptr(), dir.data_ptr(), intensity.data_ptr(), _ptr(wavelength),
-                 hitmask.data_ptr(), _ptr(g_pos), _ptr(g_dir), _ptr(g_int), rec_arr,
-                 _ptr(gp), _ptr(gd), _ptr(gi), _ptr(gt), _ptr(gl), ct.byref(req), ns, n, mode, _stream(pos))
-    return [gp, gd, gi, gt, gl]
+    return _seq_bwd_body(pos.device, pos.shape[0], pos, dir, intensity, wavelength, None, hitmask, g_pos, g_dir, g_int,
+                         g_records, table_f, table_i, lut, lut_w, need_rays, need_table, mode)
 
 
 @_trace_seq_bwd.register_fake
 def _(pos, dir, intensity, wavelength, hitmask, g_pos, g_dir, g_int, g_records, table_f, table_i, lut, lut_w,
       need_rays, need_table, mode):
-    e = pos.new_empty(0)
-    return [torch.empty_like(pos) if need_rays else e, torch.empty_like(dir) if need_rays else e,
-            torch.empty_like(intensity) if need_rays else e,
-            pos.new_empty((table_f.shape[0], C.ROW_G)) if need_table else e,
-            torch.empty_like(lut) if (need_table and lut is not None) else e]
+    return _fake_bwd(pos, pos.shape[0], table_f, lut, need_rays, need_table)
+
+
+@torch.library.custom_op("rtt_b200::trace_seq_src_fwd", mutates_args=())
+def _trace_seq_src_fwd(src_cfg: List[float], pose: torch.Tensor, state: torch.Tensor, n: int,
+                       table_f: torch.Tensor, table_i: torch.Tensor,
+                       lut: Optional[torch.Tensor], lut_w: Optional[torch.Tensor],
+                       sensor_cfg: List[float], want_record: bool, want_rays: bool, mode: int) -> List[torch.Tensor]:
+    """Sequential trace of rays GENERATED in the kernel from a ray source (no ray input in HBM).
+    want_rays=False also skips the final-ray outputs (goals only read the sensor records)."""
+    _need_cuda(pose, state, table_f, table_i)
+    return _seq_fwd_body(pose.device, n, None, None, None, None, _source_req(src_cfg, pose, state), table_f, table_i,
+                         lut, lut_w, sensor_cfg, want_record, want_rays, mode)
+
+
+@_trace_seq_src_fwd.register_fake
+def _(src_cfg, pose, state, n, table_f, table_i, lut, lut_w, sensor_cfg, want_record, want_rays, mode):
+    return _fake_seq_fwd(pose, n, sensor_cfg, want_record, want_rays)
+
+
+@torch.library.custom_op("rtt_b200::trace_seq_src_bwd", mutates_args=())
+def _trace_seq_src_bwd(src_cfg: List[float], pose: torch.Tensor, state: torch.Tensor, n: int, hitmask: torch.Tensor,
+                       g_pos: Optional[torch.Tensor], g_dir: Optional[torch.Tensor], g_int: Optional[torch.Tensor],
+                       g_records: Optional[torch.Tensor],
+                       table_f: torch.Tensor, table_i: torch.Tensor,
+                       lut: Optional[torch.Tensor], lut_w: Optional[torch.Tensor],
+                       need_table: bool, mode: int) -> List[torch.Tensor]:
+    """Adjoint of trace_seq_src_fwd: the rays are regenerated from the same {key, counter}."""
+    _need_cuda(pose, state, table_f, table_i, hitmask)
+    return _seq_bwd_body(pose.device, n, None, None, None, None, _source_req(src_cfg, pose, state), hitmask,
+                         g_pos, g_dir, g_int, g_records, table_f, table_i, lut, lut_w, False, need_table, mode)
+
+
+@_trace_seq_src_bwd.register_fake
+def _(src_cfg, pose, state, n, hitmask, g_pos, g_dir, g_int, g_records, table_f, table_i, lut, lut_w, need_table, mode):
+    return _fake_bwd(pose, n, table_f, lut, False, need_table)
 
 
 @torch.library.custom_op("rtt_b200::trace_nonseq_fwd", mutates_args=())
@@ -187,37 +317,14 @@ def _trace_nonseq_fwd(pos: torch.Tensor, dir: torch.Tensor, intensity: torch.Ten
     """-> [out_pos, out_dir, out_intensity, hit_seq uint8 [N,B], n_hits uint8 [N], records [ns,K,N,4],
     images (flat), counts uint8 [ns,N]]; K = record_depth = sensor interactions kept per ray."""
     _need_cuda(pos, dir, intensity, table_f, table_i)
-    lib = _cabi.load()
-    n = pos.shape[0]
-    ns = len(sensor_cfg) // SENSOR_CFG
-    opos, odir, oint = torch.empty_like(pos), torch.empty_like(dir), torch.empty_like(intensity)
-    seq = torch.empty((n, nbounces), dtype=torch.uint8, device=pos.device)
-    nh = torch.empty(n, dtype=torch.uint8, device=pos.device)
-    K = max(1, int(record_depth))
-    rec_on = bool(want_record and ns)
-    records = torch.zeros((ns, K, n, 4), dtype=torch.float32, device=pos.device) if rec_on \
-        else torch.empty((0, K, n, 4), dtype=torch.float32, device=pos.device)
-    counts = torch.zeros((ns if rec_on else 0, n), dtype=torch.uint8, device=pos.device)
-    images = torch.zeros(_image_numel(sensor_cfg), dtype=torch.float32, device=pos.device)
-    sens, cnt = _sensor_reqs(sensor_cfg, n, records if rec_on else None, images, counts if rec_on else None, K)
-    req = _table_req(table_f, table_i, lut, lut_w)
-    with torch.cuda.device(pos.device):
-        lib.call("rtt_trace_nonseq_fwd", pos.data_ptr(), dir.data_ptr(), intensity.data_ptr(), _ptr(wavelength),
-                 opos.data_ptr(), odir.data_ptr(), oint.data_ptr(), seq.data_ptr(), nh.data_ptr(),
-                 ct.byref(req), sens, cnt, nbounces, n, mode, _stream(pos))
-    return [opos, odir, oint, seq, nh, records, images, counts]
+    return _nonseq_fwd_body(pos.device, pos.shape[0], pos, dir, intensity, wavelength, None, table_f, table_i, lut,
+                            lut_w, sensor_cfg, want_record, True, nbounces, mode, record_depth)
 
 
 @_trace_nonseq_fwd.register_fake
 def _(pos, dir, intensity, wavelength, table_f, table_i, lut, lut_w, sensor_cfg, want_record, nbounces, mode,
       record_depth=1):
-    n = pos.shape[0]
-    ns = len(sensor_cfg) // SENSOR_CFG
-    K = max(1, int(record_depth))
-    return [torch.empty_like(pos), torch.empty_like(dir), torch.empty_like(intensity),
-            pos.new_empty((n, nbounces), dtype=torch.uint8), pos.new_empty(n, dtype=torch.uint8),
-            pos.new_empty(((ns if want_record else 0), K, n, 4)), pos.new_empty(_image_numel(sensor_cfg)),
-            pos.new_empty(((ns if want_record else 0), n), dtype=torch.uint8)]
+    return _fake_nonseq_fwd(pos, pos.shape[0], sensor_cfg, want_record, True, nbounces, record_depth)
 
 
 @torch.library.custom_op("rtt_b200::trace_nonseq_bwd", mutates_args=())
@@ -229,34 +336,144 @@ def _trace_nonseq_bwd(pos: torch.Tensor, dir: torch.Tensor, intensity: torch.Ten
                       lut: Optional[torch.Tensor], lut_w: Optional[torch.Tensor],
                       need_rays: bool, need_table: bool, mode: int) -> List[torch.Tensor]:
     _need_cuda(pos, dir, intensity, table_f, table_i, hit_seq)
-    lib = _cabi.load()
-    n, S = pos.shape[0], table_f.shape[0]
-    dev = pos.device
-    gp = torch.empty_like(pos) if need_rays else pos.new_empty(0)
-    gd = torch.empty_like(dir) if need_rays else pos.new_empty(0)
-    gi = torch.empty_like(intensity) if need_rays else pos.new_empty(0)
-    gt = torch.zeros((S, C.ROW_G), dtype=torch.float32, device=dev) if need_table else pos.new_empty(0)
-    has_lut = lut is not None and lut.numel() > 0
-    gl = torch.zeros_like(lut) if (need_table and has_lut) else pos.new_empty(0)
-    ns = 0 if g_records is None else g_records.shape[0]          # g_records: [ns, K, N, 4]
-    rec_arr = (ct.c_void_p * ns)(*[g_records[s].data_ptr() for s in range(ns)]) if ns else None
-    depth = (ct.c_int32 * ns)(*([g_records.shape[1]] * ns)) if ns else None
-    req = _table_req(table_f, table_i, lut, lut_w)
-    with torch.cuda.device(dev):
-        lib.call("rtt_trace_nonseq_bwd", pos.data_ptr(), dir.data_ptr(), intensity.data_ptr(), _ptr(wavelength),
-                 hit_seq.data_ptr(), hit_seq.shape[1], _ptr(g_pos), _ptr(g_dir), _ptr(g_int), rec_arr, depth,
-                 _ptr(gp), _ptr(gd), _ptr(gi), _ptr(gt), _ptr(gl), ct.byref(req), ns, n, mode, _stream(pos))
-    return [gp, gd, gi, gt, gl]
+    return _nonseq_bwd_body(pos.device, pos.shape[0], pos, dir, intensity, wavelength, None, hit_seq, g_pos, g_dir,
+                            g_int, g_records, table_f, table_i, lut, lut_w, need_rays, need_table, mode)
 
 
 @_trace_nonseq_bwd.register_fake
 def _(pos, dir, intensity, wavelength, hit_seq, g_pos, g_dir, g_int, g_records, table_f, table_i, lut, lut_w,
       need_rays, need_table, mode):
-    e = pos.new_empty(0)
-    return [torch.empty_like(pos) if need_rays else e, torch.empty_like(dir) if need_rays else e,
-            torch.empty_like(intensity) if need_rays else e,
-            pos.new_empty((table_f.shape[0], C.ROW_G)) if need_table else e,
-            torch.empty_like(lut) if (need_table and lut is not None) else e]
+    return _fake_bwd(pos, pos.shape[0], table_f, lut, need_rays, need_table)
+
+
+@torch.library.custom_op("rtt_b200::trace_nonseq_src_fwd", mutates_args=())
+def _trace_nonseq_src_fwd(src_cfg: List[float], pose: torch.Tensor, state: torch.Tensor, n: int,
+                          table_f: torch.Tensor, table_i: torch.Tensor,
+                          lut: Optional[torch.Tensor], lut_w: Optional[torch.Tensor],
+                          sensor_cfg: List[float], want_record: bool, want_rays: bool, nbounces: int, mode: int,
+                          record_depth: int) -> List[torch.Tensor]:
+    _need_cuda(pose, state, table_f, table_i)
+    return _nonseq_fwd_body(pose.device, n, None, None, None, None, _source_req(src_cfg, pose, state), table_f, table_i,
+                            lut, lut_w, sensor_cfg, want_record, want_rays, nbounces, mode, record_depth)
+
+
+@_trace_nonseq_src_fwd.register_fake
+def _(src_cfg, pose, state, n, table_f, table_i, lut, lut_w, sensor_cfg, want_record, want_rays, nbounces, mode,
+      record_depth):
+    return _fake_nonseq_fwd(pose, n, sensor_cfg, want_record, want_rays, nbounces, record_depth)
+
+
+@torch.library.custom_op("rtt_b200::trace_nonseq_src_bwd", mutates_args=())
+def _trace_nonseq_src_bwd(src_cfg: List[float], pose: torch.Tensor, state: torch.Tensor, n: int, hit_seq: torch.Tensor,
+                          g_pos: Optional[torch.Tensor], g_dir: Optional[torch.Tensor], g_int: Optional[torch.Tensor],
+                          g_records: Optional[torch.Tensor],
+                          table_f: torch.Tensor, table_i: torch.Tensor,
+                          lut: Optional[torch.Tensor], lut_w: Optional[torch.Tensor],
+                          need_table: bool, mode: int) -> List[torch.Tensor]:
+    _need_cuda(pose, state, table_f, table_i, hit_seq)
+    return _nonseq_bwd_body(pose.device, n, None, None, None, None, _source_req(src_cfg, pose, state), hit_seq,
+                            g_pos, g_dir, g_int, g_records, table_f, table_i, lut, lut_w, False, need_table, mode)
+
+
+@_trace_nonseq_src_bwd.register_fake
+def _(src_cfg, pose, state, n, hit_seq, g_pos, g_dir, g_int, g_records, table_f, table_i, lut, lut_w, need_table, mode):
+    return _fake_bwd(pose, n, table_f, lut, False, need_table)
+
+
+@torch.library.custom_op("rtt_b200::sample_bundle", mutates_args=())
+def _sample_bundle(src_cfg: List[float], pose: torch.Tensor, state: torch.Tensor, n: int, mode: int) -> List[torch.Tensor]:
+    """Bundle.sample on the device (rays/bundle.py:30-37) -> [pos, dir, intensity, wavelength]."""
+    _need_cuda(pose, state)
+    lib = _cabi.load()
+    f32 = dict(dtype=torch.float32, device=pose.device)
+    pos, dir_ = torch.empty((n, 3), **f32), torch.empty((n, 3), **f32)
+    inten, wav = torch.empty(n, **f32), torch.empty(n, **f32)
+    src = _source_req(src_cfg, pose, state)
+    with torch.cuda.device(pose.device):
+        lib.call("rtt_sample_bundle", ct.byref(src), _ptr(pos), _ptr(dir_), _ptr(inten), _ptr(wav), n, mode,
+                 _stream(pose))
+    return [pos, dir_, inten, wav]
+
+
+@_sample_bundle.register_fake
+def _(src_cfg, pose, state, n, mode):
+    return [pose.new_empty((n, 3)), pose.new_empty((n, 3)), pose.new_empty(n), pose.new_empty(n)]
+
+
+# ---- goal reductions (rtt_goals.cu) ----------------------------------------------------------------
+_SPOT_WORK = {}
+
+
+def _spot_work(dev) -> torch.Tensor:
+    """Per-device, per-stream scratch of the two-stage reductions (zeroed once; the kernels leave it zeroed)."""
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    w = _SPOT_WORK.get(key)
+    if w is None:
+        w = _SPOT_WORK[key] = torch.zeros(_cabi.SPOT_WORK, dtype=torch.float32, device=dev)
+    return w
+
+
+@torch.library.custom_op("rtt_b200::spot_moments", mutates_args=())
+def _spot_moments(rec: torch.Tensor, active_only: bool) -> torch.Tensor:
+    """rec [M,4] -> [sum w, sum w x, sum w y, #(w > 0)]"""
+    _need_cuda(rec)
+    out = torch.empty(4, dtype=torch.float32, device=rec.device)
+    with torch.cuda.device(rec.device):
+        _cabi.load().call("rtt_spot_moments", _ptr(rec), rec.shape[0], int(active_only), out.data_ptr(),
+                          _spot_work(rec.device).data_ptr(), _stream(rec))
+    return out
+
+
+@_spot_moments.register_fake
+def _(rec, active_only):
+    return rec.new_empty(4)
+
+
+@torch.library.custom_op("rtt_b200::spot_moments_bwd", mutates_args=())
+def _spot_moments_bwd(rec: torch.Tensor, active_only: bool, g3: torch.Tensor) -> torch.Tensor:
+    _need_cuda(rec, g3)
+    g = torch.empty_like(rec)
+    with torch.cuda.device(rec.device):
+        _cabi.load().call("rtt_spot_moments_bwd", _ptr(rec), rec.shape[0], int(active_only), g3.data_ptr(), _ptr(g),
+                          _stream(rec))
+    return g
+
+
+@_spot_moments_bwd.register_fake
+def _(rec, active_only, g3):
+    return torch.empty_like(rec)
+
+
+@torch.library.custom_op("rtt_b200::spot_size_fwd", mutates_args=())
+def _spot_size_fwd(rec: torch.Tensor, mom4: torch.Tensor, target: Optional[torch.Tensor]) -> torch.Tensor:
+    """-> [sum_i sqrt(q_i), d/d cx, d/d cy]"""
+    _need_cuda(rec, mom4)
+    out = torch.empty(3, dtype=torch.float32, device=rec.device)
+    with torch.cuda.device(rec.device):
+        _cabi.load().call("rtt_spot_size_fwd", _ptr(rec), rec.shape[0], mom4.data_ptr(), _ptr(target), out.data_ptr(),
+                          _spot_work(rec.device).data_ptr(), _stream(rec))
+    return out
+
+
+@_spot_size_fwd.register_fake
+def _(rec, mom4, target):
+    return rec.new_empty(3)
+
+
+@torch.library.custom_op("rtt_b200::spot_size_bwd", mutates_args=())
+def _spot_size_bwd(rec: torch.Tensor, mom4: torch.Tensor, target: Optional[torch.Tensor], out3: torch.Tensor,
+                   g_loss: torch.Tensor) -> torch.Tensor:
+    _need_cuda(rec, mom4, out3, g_loss)
+    g = torch.empty_like(rec)
+    with torch.cuda.device(rec.device):
+        _cabi.load().call("rtt_spot_size_bwd", _ptr(rec), rec.shape[0], mom4.data_ptr(), _ptr(target), out3.data_ptr(),
+                          g_loss.data_ptr(), _ptr(g), _stream(rec))
+    return g
+
+
+@_spot_size_bwd.register_fake
+def _(rec, mom4, target, out3, g_loss):
+    return torch.empty_like(rec)
 
 
 @torch.library.custom_op("rtt_b200::intersect_test", mutates_args=())
@@ -402,6 +619,117 @@ class _TraceNonseq(torch.autograd.Function):
                 gl if ctx.needs_input_grad[6] else None, None, None, None, None, None, None)
 
 
+class _TraceSeqSrc(torch.autograd.Function):
+    """Sequential trace of in-kernel generated rays; only the table (and LUT) receive gradients."""
+
+    @staticmethod
+    def forward(ctx, src_cfg, pose, state, n, table_f, table_i, lut, lut_w, sensor_cfg, want_record, want_rays, mode):
+        outs = torch.ops.rtt_b200.trace_seq_src_fwd(src_cfg, pose, state, n, table_f, table_i, lut, lut_w,
+                                                    sensor_cfg, want_record, want_rays, mode)
+        opos, odir, oint, hitmask, records, images = outs
+        ctx.save_for_backward(pose, state, hitmask, table_f, table_i, lut, lut_w)
+        ctx.src_cfg, ctx.n, ctx.mode, ctx.want_rays = list(src_cfg), n, mode, want_rays
+        ctx.mark_non_differentiable(hitmask, images)
+        return opos, odir, oint, hitmask, records, images
+
+    @staticmethod
+    def backward(ctx, g_pos, g_dir, g_int, _g_mask, g_records, _g_images):
+        pose, state, hitmask, table_f, table_i, lut, lut_w = ctx.saved_tensors
+        if g_records is not None and g_records.numel() == 0:
+            g_records = None
+        if not ctx.want_rays:
+            g_pos = g_dir = g_int = None
+        _gp, _gd, _gi, gt, gl = torch.ops.rtt_b200.trace_seq_src_bwd(
+            ctx.src_cfg, pose, state, ctx.n, hitmask, _cg(g_pos), _cg(g_dir), _cg(g_int), _cg(g_records),
+            table_f, table_i, lut, lut_w, True, ctx.mode)
+        return (None, None, None, None, _pad_table_grad(gt, table_f) if ctx.needs_input_grad[4] else None, None,
+                gl if ctx.needs_input_grad[6] else None, None, None, None, None, None)
+
+
+class _TraceNonseqSrc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src_cfg, pose, state, n, table_f, table_i, lut, lut_w, sensor_cfg, want_record, want_rays,
+                nbounces, mode, record_depth):
+        outs = torch.ops.rtt_b200.trace_nonseq_src_fwd(src_cfg, pose, state, n, table_f, table_i, lut, lut_w,
+                                                       sensor_cfg, want_record, want_rays, nbounces, mode, record_depth)
+        opos, odir, oint, seq, nh, records, images, counts = outs
+        ctx.save_for_backward(pose, state, seq, table_f, table_i, lut, lut_w)
+        ctx.src_cfg, ctx.n, ctx.mode, ctx.want_rays = list(src_cfg), n, mode, want_rays
+        ctx.mark_non_differentiable(seq, nh, images, counts)
+        return opos, odir, oint, seq, nh, records, images, counts
+
+    @staticmethod
+    def backward(ctx, g_pos, g_dir, g_int, _g_seq, _g_nh, g_records, _g_images, _g_counts):
+        pose, state, seq, table_f, table_i, lut, lut_w = ctx.saved_tensors
+        if g_records is not None and g_records.numel() == 0:
+            g_records = None
+        if not ctx.want_rays:
+            g_pos = g_dir = g_int = None
+        _gp, _gd, _gi, gt, gl = torch.ops.rtt_b200.trace_nonseq_src_bwd(
+            ctx.src_cfg, pose, state, ctx.n, seq, _cg(g_pos), _cg(g_dir), _cg(g_int), _cg(g_records),
+            table_f, table_i, lut, lut_w, True, ctx.mode)
+        return (None, None, None, None, _pad_table_grad(gt, table_f) if ctx.needs_input_grad[4] else None, None,
+                gl if ctx.needs_input_grad[6] else None, None, None, None, None, None, None, None)
+
+
+def _all_reduce_sum(t: torch.Tensor) -> torch.Tensor:
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+class _SpotMoments(torch.autograd.Function):
+    """[W, sum w x, sum w y, count] of sensor records (summed over ranks when torch.distributed is up)."""
+
+    @staticmethod
+    def forward(ctx, rec, active_only):
+        mom = _all_reduce_sum(torch.ops.rtt_b200.spot_moments(rec, active_only))
+        ctx.save_for_backward(rec)
+        ctx.active_only = active_only
+        return mom
+
+    @staticmethod
+    def backward(ctx, g):
+        (rec,) = ctx.saved_tensors
+        return torch.ops.rtt_b200.spot_moments_bwd(rec, ctx.active_only, g[:3].contiguous()), None
+
+
+class _SpotSize(torch.autograd.Function):
+    """sum_i sqrt(|xy_i - c|^2 w_i / W) over the active records (optim/goals.py:165-183), c = weighted centroid
+    or a fixed target.  Two reduction launches forward, one elementwise launch backward; sums are global over
+    ranks, so every rank holds the same loss and its records get the full derivative."""
+
+    @staticmethod
+    def forward(ctx, rec, target):
+        mom = _all_reduce_sum(torch.ops.rtt_b200.spot_moments(rec, True))
+        out3 = _all_reduce_sum(torch.ops.rtt_b200.spot_size_fwd(rec, mom, target))
+        ctx.save_for_backward(rec, mom, out3, target)
+        return out3[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        rec, mom, out3, target = ctx.saved_tensors
+        return torch.ops.rtt_b200.spot_size_bwd(rec, mom, target, out3, g.reshape(1).contiguous()), None
+
+
+def spot_moments(rec: torch.Tensor, active_only: bool = False) -> torch.Tensor:
+    """Differentiable [sum w, sum w x, sum w y, #(w>0)] of sensor records rec [..., 4]."""
+    return _SpotMoments.apply(_f32c(rec).reshape(-1, 4), bool(active_only))
+
+
+def spot_size(rec: torch.Tensor, target_xy: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Differentiable SpotSizeLoss term of ONE bundle from its sensor records rec [..., 4]."""
+    tgt = None if target_xy is None else _f32c(target_xy.to(rec.device)).reshape(2)
+    return _SpotSize.apply(_f32c(rec).reshape(-1, 4), tgt)
+
+
+def sample_source(rays, mode: Optional[int] = None):
+    """Materialise SourceRays: (pos, dir, intensity, wavelength) from rtt_sample_bundle."""
+    mode = _default_mode if mode is None else mode
+    return tuple(torch.ops.rtt_b200.sample_bundle(source_cfg_of(rays), rays.pose, rays.state, rays.n, mode))
+
+
 class _SurfaceStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pos, dir_, wavelength, table_f, table_i, lut, lut_w, row, mode):
@@ -460,15 +788,25 @@ def _prep_rays(pos, dir_, intensity, wavelength, table: SurfaceTable):
     return pos, dir_, intensity, wav
 
 
-def trace_sequential(table: SurfaceTable, pos, dir_, intensity, wavelength=None, *, want_record=True,
-                     sensor_cfg: Optional[List[float]] = None, mode: Optional[int] = None):
+def trace_sequential(table: SurfaceTable, pos=None, dir_=None, intensity=None, wavelength=None, *, want_record=True,
+                     sensor_cfg: Optional[List[float]] = None, mode: Optional[int] = None, source=None,
+                     want_rays: bool = True):
     """Fused SequentialScene.simulate (scene/sequential.py:12-36).
 
+    Rays come from (pos, dir_, intensity, wavelength) or — ``source=SourceRays`` — are generated in the kernel;
+    ``want_rays=False`` (sources only) skips the final-ray outputs.
     Returns dict(pos, dir, intensity, hitmask [N] int64 (bit r = interacted with row r),
     records [n_sensors,N,4] (hit_local xyz, weight-before), images [per sensor: [C,H,W] or None])."""
-    pos, dir_, intensity, wav = _prep_rays(pos, dir_, intensity, wavelength, table)
     cfg = sensor_cfg_of(table) if sensor_cfg is None else list(sensor_cfg)
     mode = _default_mode if mode is None else mode
+    if source is not None:
+        _need_cuda(table.f)
+        opos, odir, oint, hitmask, records, images = _TraceSeqSrc.apply(
+            source_cfg_of(source), source.pose, source.state, source.n, table.f, table.i, table.lut,
+            table.lut_wavelengths, cfg, bool(want_record), bool(want_rays), mode)
+        return dict(pos=opos, dir=odir, intensity=oint, hitmask=hitmask, records=records,
+                    images=split_images(images, cfg))
+    pos, dir_, intensity, wav = _prep_rays(pos, dir_, intensity, wavelength, table)
     opos, odir, oint, hitmask, records, images = _TraceSeq.apply(
         pos, dir_, intensity, wav, table.f, table.i, table.lut, table.lut_wavelengths, cfg, bool(want_record), mode)
     return dict(pos=opos, dir=odir, intensity=oint, hitmask=hitmask, records=records,
@@ -477,17 +815,25 @@ def trace_sequential(table: SurfaceTable, pos, dir_, intensity, wavelength=None,
 
 def trace_nonsequential(table: SurfaceTable, pos, dir_, intensity, nbounces: int, wavelength=None, *,
                         want_record=True, sensor_cfg: Optional[List[float]] = None, mode: Optional[int] = None,
-                        record_depth: int = 1):
+                        record_depth: int = 1, source=None, want_rays: bool = True):
     """Fused Scene.simulate bounce loop (scene/base.py:129-235).
 
     Returns dict(pos, dir, intensity, hit_seq [N,B] uint8 (255 = none), n_hits [N] uint8,
     records [n_sensors, K, N, 4] (the k-th interaction of ray i with the sensor, K = record_depth),
     sensor_counts [n_sensors, N] uint8 (interactions per ray, may exceed K), images)."""
-    pos, dir_, intensity, wav = _prep_rays(pos, dir_, intensity, wavelength, table)
     if not 0 <= nbounces <= C.MAX_BOUNCES:
         raise ValueError(f"nbounces must be in [0, {C.MAX_BOUNCES}]")
     cfg = sensor_cfg_of(table) if sensor_cfg is None else list(sensor_cfg)
     mode = _default_mode_nonseq if mode is None else mode
+    if source is not None:
+        _need_cuda(table.f)
+        opos, odir, oint, seq, nh, records, images, counts = _TraceNonseqSrc.apply(
+            source_cfg_of(source), source.pose, source.state, source.n, table.f, table.i, table.lut,
+            table.lut_wavelengths, cfg, bool(want_record), bool(want_rays), int(nbounces), mode,
+            max(1, int(record_depth)))
+        return dict(pos=opos, dir=odir, intensity=oint, hit_seq=seq, n_hits=nh, records=records,
+                    sensor_counts=counts, images=split_images(images, cfg))
+    pos, dir_, intensity, wav = _prep_rays(pos, dir_, intensity, wavelength, table)
     opos, odir, oint, seq, nh, records, images, counts = _TraceNonseq.apply(
         pos, dir_, intensity, wav, table.f, table.i, table.lut, table.lut_wavelengths, cfg, bool(want_record),
         int(nbounces), mode, max(1, int(record_depth)))

@@ -5,8 +5,11 @@ constructor signatures and formulas.  They call ``scene.simulate()`` with ``scen
 works for both scene classes here (the reference's own call raises for ``SequentialScene``,
 SURVEY section 0.7).  Differences are in execution only:
 
-* the fused kernels hand over one sensor record per ray plus a hit mask, so the weighted moments
-  are computed over the full bundle with masks — no boolean gather, no host synchronisation;
+* the fused kernels hand over one sensor record per ray (zero weight = no hit), and the goals reduce
+  those records with dedicated kernels (``ops.spot_moments`` / ``ops.spot_size``: two reduction launches
+  forward, one elementwise launch backward) — no boolean gather, no host synchronisation, no eager
+  elementwise chain; bundles sampled on the device are generated inside the trace kernels and the trace
+  skips its final-ray outputs, so a goal evaluation moves 24 B/ray forward and 40 B/ray backward;
 * with ``torch.distributed`` initialised the moments (W, sum w x, sum w y) and the per-bundle sums
   are all-reduced, so a bundle sharded over ranks gives the same loss on every rank; after
   ``loss.backward()`` one ``dist.allreduce_scene_results(sensors, params)`` sums the per-shard
@@ -22,6 +25,7 @@ from typing import List, Optional
 import torch
 import torch.nn as nn
 
+from . import ops
 from .elements import Sensor
 from .rays import Bundle
 
@@ -81,6 +85,40 @@ def _sensor_hits(scene, sensor: Sensor):
     return scene.rays.pos[:, :2], scene.rays.intensity
 
 
+def _sensor_records(scene, sensor: Sensor):
+    """Raw records [M,4] of `sensor` from the latest fused trace (M = rays, or depth x rays for the
+    non-sequential trace; entries that were not hit are all zero), or None."""
+    tr = getattr(scene, "last_trace", None)
+    if tr is None or tr.get("records") is None or not tr["records"].numel():
+        return None
+    table = getattr(scene, "_last_table", None) or scene.table()
+    if sensor not in table.sensors:
+        return None
+    return tr["records"][table.sensors.index(sensor)].reshape(-1, 4)
+
+
+class _goal_trace:
+    """While a goal evaluates: keep sensor records, skip the final-ray outputs of generated bundles."""
+
+    def __init__(self, scene):
+        self.scene = scene
+
+    def __enter__(self):
+        sc = self.scene
+        self.saved = (getattr(sc, "record_hits", None), getattr(sc, "final_rays", None))
+        if self.saved[0] is not None:
+            sc.record_hits = True
+        if self.saved[1] is not None:
+            sc.final_rays = False
+
+    def __exit__(self, *exc):
+        sc = self.scene
+        if self.saved[0] is not None:
+            sc.record_hits = self.saved[0]
+        if self.saved[1] is not None:
+            sc.final_rays = self.saved[1]
+
+
 def _place(scene, rays):
     if hasattr(scene, "parameters"):
         dev = next(iter(scene.parameters()), torch.zeros(1)).device
@@ -105,11 +143,19 @@ class SpotTargetLoss(Goal):
         for i, bundle in enumerate(bundles):
             self.sensor.reset()
             _place(scene, bundle.sample(N_rays))
-            scene.simulate()
-            xy, w = _sensor_hits(scene, self.sensor)
-            if w.shape[0] == 0:
-                continue
-            mom = _dist_sum(torch.stack([w.sum(), (xy[:, 0] * w).sum(), (xy[:, 1] * w).sum()]))
+            with _goal_trace(scene):
+                scene.simulate()
+            rec = _sensor_records(scene, self.sensor)
+            if rec is not None and rec.is_cuda:
+                if rec.shape[0] == 0:
+                    continue
+                mom = ops.spot_moments(rec, active_only=False)       # every recorded hit (optim/goals.py:76-88)
+                xy = rec
+            else:
+                xy, w = _sensor_hits(scene, self.sensor)
+                if w.shape[0] == 0:
+                    continue
+                mom = _dist_sum(torch.stack([w.sum(), (xy[:, 0] * w).sum(), (xy[:, 1] * w).sum()]))
             w_sum = mom[0].clamp(min=1e-12)
             cx, cy = mom[1] / w_sum, mom[2] / w_sum
             tidx = min(i, self.target_xy.shape[0] - 1)
@@ -139,7 +185,17 @@ class SpotSizeLoss(Goal):
         for i, bundle in enumerate(self.bundles):
             self.sensor.reset()
             _place(scene, bundle.sample(self.N_rays))
-            scene.simulate()
+            with _goal_trace(scene):
+                scene.simulate()
+            rec = _sensor_records(scene, self.sensor)
+            if rec is not None and rec.is_cuda:             # fused reductions (rtt_goals.cu)
+                tgt = None
+                if self._target_xy is not None:
+                    if self._target_xy.device != rec.device:   # once: no per-step host-to-device copy
+                        self._target_xy = self._target_xy.to(rec.device)
+                    tgt = self._target_xy[min(i, self._target_xy.shape[0] - 1)]
+                losses.append(ops.spot_size(rec, tgt))
+                continue
             xy, w = _sensor_hits(scene, self.sensor)
             active = w > 0                                  # optim/goals.py:165 (as a mask: no gather)
             wa = torch.where(active, w, torch.zeros_like(w))

@@ -9,6 +9,13 @@ NOT renormalise (used by scene/sequential.py:29), ``with_coords`` and ``scatter_
 
 Ray sources draw from torch's generator in the same order as the reference so that a
 seeded script produces the same bundle.
+
+On a CUDA device ``Bundle.sample(N)`` does not run the reference's dozen eager ops: it returns
+``SourceRays`` — a description (source kind, pose, Philox key and counter) of rays that the
+trace kernels GENERATE in registers (rtt_source_t, include/rtt_b200.h).  A trace of such rays
+reads no ray input from HBM, and its adjoint regenerates the same rays from the 16-byte state.
+Any other consumer that touches ``.pos`` / ``.dir`` / ``.intensity`` gets them materialised by
+``rtt_sample_bundle`` (same generator, same rays).
 """
 from __future__ import annotations
 
@@ -22,6 +29,10 @@ import torch.nn.functional as F
 from .geom import RayTransformBundle
 
 _FIELDS = ("pos", "dir", "intensity", "id", "wavelength")
+
+# Bundle.sample on a CUDA device returns SourceRays (in-kernel generation).  Set to False to draw the
+# samples with torch ops in the reference's order instead (e.g. to reproduce a torch-seeded script).
+use_device_sources = True
 
 
 class Rays:
@@ -90,6 +101,74 @@ class Rays:
         return cls(pos=o, dir=d, intensity=w, id=ids, wavelength=lam, batch_size=[n])
 
 
+# ---- device ray sources ------------------------------------------------------------------------
+_SRC_STATE = {}      # device -> (seed the state was built from, int64[2] tensor {Philox key, counter})
+
+
+def source_state(device) -> torch.Tensor:
+    """Per-device {key, counter} of the in-kernel ray generator, keyed to torch's CUDA seed
+    (``torch.manual_seed`` re-keys it).  Lives on the device so that captured CUDA graphs draw
+    fresh rays on every replay."""
+    device = torch.device(device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    seed = int(torch.cuda.default_generators[device.index].initial_seed())
+    hit = _SRC_STATE.get(device)
+    if hit is None or hit[0] != seed:
+        hit = (seed, torch.tensor([seed & (2 ** 63 - 1), 0], dtype=torch.int64, device=device))
+        _SRC_STATE[device] = hit
+    return hit[1]
+
+
+class SourceRays(Rays):
+    """Rays of a device ray source, generated on demand (see the module docstring).
+
+    ``source`` = dict(kind, a, width, height, intensity, wavelength, first); ``pose`` = [12] device
+    tensor (R row-major, T); ``state`` = int64[2] snapshot {key, counter} owned by this object."""
+
+    def __init__(self, source: dict, pose: torch.Tensor, state: torch.Tensor, n: int, ray_id: int = 0):
+        self.source, self.pose, self.state, self.n, self.ray_id = source, pose, state, int(n), int(ray_id)
+        self._fields = {}
+        self.batch_size = torch.Size([self.n])
+
+    @property
+    def generated(self) -> bool:
+        """True while no field has been materialised or overwritten (the kernels can generate)."""
+        return not any(k in self._fields for k in ("pos", "dir", "intensity", "wavelength"))
+
+    def _materialise(self):
+        from . import ops
+        pos, dir_, inten, wav = ops.sample_source(self)
+        for k, v in (("pos", pos), ("dir", dir_), ("intensity", inten), ("wavelength", wav)):
+            self._fields.setdefault(k, v)
+
+    def _get(self, k):
+        if k not in self._fields:
+            if k == "id":
+                self._fields[k] = torch.full((self.n,), self.ray_id, dtype=torch.int8, device=self.pose.device)
+            else:
+                self._materialise()
+        return self._fields[k]
+
+    pos = property(lambda self: self._get("pos"), lambda self, v: self._fields.__setitem__("pos", v))
+    dir = property(lambda self: self._get("dir"), lambda self, v: self._fields.__setitem__("dir", v))
+    intensity = property(lambda self: self._get("intensity"), lambda self, v: self._fields.__setitem__("intensity", v))
+    wavelength = property(lambda self: self._get("wavelength"), lambda self, v: self._fields.__setitem__("wavelength", v))
+    id = property(lambda self: self._get("id"), lambda self, v: self._fields.__setitem__("id", v))
+
+    @property
+    def device(self):
+        return self.pose.device
+
+    def to(self, *a, **k):
+        dev = k.get("device", a[0] if a and isinstance(a[0], (str, torch.device)) else None)
+        if dev is not None and torch.device(dev).type == "cuda" and len(a) + len(k) == 1:
+            d = torch.device(dev)
+            if d.index is None or d.index == self.pose.device.index:
+                return self
+        return super().to(*a, **k)
+
+
 def _uniform(n, lo, hi):
     """Uniform(lo, hi).sample((n,)) for 1-element tensors: rand[n,1]*(hi-lo)+lo."""
     return lo + torch.rand((n,) + tuple(lo.shape), dtype=lo.dtype, device=lo.device) * (hi - lo)
@@ -110,7 +189,33 @@ class Bundle(nn.Module):
     def sample_pos(self, N: int):
         return torch.zeros((N, 3), device=self.device, dtype=self.dtype)
 
+    # (kind, a[4]) of the device ray source equivalent to sample_pos/sample_dir, or None
+    def _source(self):
+        from . import _cabi
+        if type(self).sample_pos is Bundle.sample_pos and type(self).sample_dir is Bundle.sample_dir:
+            return _cabi.SRC_LINE, [0.0, 0.0, 0.0, 0.0]
+        return None
+
+    def _pose12(self, device) -> torch.Tensor:
+        tr = self.transform
+        key = (tr.rot_vec._version, tr.trans._version, tr.rot_vec.device, torch.device(device))
+        hit = getattr(self, "_pose_cache", None)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                pose = torch.cat([tr.rot.reshape(9), tr.trans.reshape(3)]).to(device=device, dtype=torch.float32)
+            hit = (key, pose.contiguous())
+            self._pose_cache = hit
+        return hit[1]
+
     def sample(self, N: int) -> Rays:
+        dev = torch.device(self.device)
+        src = self._source() if (dev.type == "cuda" and self.dtype == torch.float32 and use_device_sources) else None
+        if src is not None and isinstance(self.transform, RayTransformBundle):
+            state = source_state(dev)
+            snap = state.clone()
+            state[1:].add_(int(N))
+            spec = dict(kind=src[0], a=list(src[1]), width=0, height=0, intensity=1.0, wavelength=0.0, first=0)
+            return SourceRays(spec, self._pose12(dev), snap, N, self.ray_id)
         p, d = self.transform.transform_(self.sample_pos(N), self.sample_dir(N))
         return Rays.initialize(p, d, ray_id=self.ray_id, device=self.device, dtype=self.dtype)
 
@@ -157,9 +262,14 @@ class CollimatedDisk(Bundle):
         self.zero = torch.tensor([0.0], device=device, dtype=dtype)
         self.tmax = torch.tensor([2 * math.pi], device=device, dtype=dtype)
         self.disk = DiskSample(self.zero, self.radius2, self.zero, self.tmax)
+        self._src_a = [0.0, float(radius) * float(radius), 0.0, 2 * math.pi]
 
     def sample_pos(self, N: int):
         return self.disk.sample(N)
+
+    def _source(self):
+        from . import _cabi
+        return _cabi.SRC_DISK, self._src_a
 
 
 class CollimatedLine(Bundle):
@@ -167,6 +277,11 @@ class CollimatedLine(Bundle):
                  transform: Optional[RayTransformBundle] = None):
         super().__init__(ray_id, device, dtype, transform)
         self.length_2 = torch.tensor([length], device=device, dtype=dtype)
+        self._src_a = [float(length), 0.0, 0.0, 0.0]
+
+    def _source(self):
+        from . import _cabi
+        return _cabi.SRC_LINE, self._src_a
 
     def sample_pos(self, N: int):
         x = _uniform(N, -self.length_2, self.length_2)
@@ -180,6 +295,11 @@ class Fan(Bundle):
                  transform: Optional[RayTransformBundle] = None):
         super().__init__(ray_id, device, dtype, transform)
         self.angle_2 = torch.tensor([angle / 2], device=device, dtype=dtype)
+        self._src_a = [float(angle) / 2, 0.0, 0.0, 0.0]
+
+    def _source(self):
+        from . import _cabi
+        return _cabi.SRC_FAN, self._src_a
 
     def sample_dir(self, N):
         th = _uniform(N, -self.angle_2, self.angle_2).squeeze()
@@ -196,6 +316,11 @@ class PointSource(Bundle):
         self.twopi = torch.tensor([2 * math.pi], device=device, dtype=dtype)
         self.F_phi_max = SolidAngleSample.CDF_phi(torch.arcsin(torch.tensor(NA, device=device, dtype=dtype)))
         self.angle_dist = SolidAngleSample(self.zero, self.F_phi_max, self.zero, self.twopi)
+        self._src_a = [0.0, float(self.F_phi_max), 0.0, 2 * math.pi]
+
+    def _source(self):
+        from . import _cabi
+        return _cabi.SRC_POINT, self._src_a
 
     def sample_dir(self, N):
         phi, theta = self.angle_dist.sample(N)

@@ -32,6 +32,25 @@ class Camera:
         x_grid = torch.linspace(-scale_x, scale_x, self.width, device=self.device)
         return x_grid, y_grid, float(scale_x), float(scale_y)
 
+    # ---- device ray source (rtt_source_t kind CAMERA): the trace kernels generate these rays in registers ----
+    def source_spec(self, samples: int = 1, first: int = 0) -> dict:
+        _xg, _yg, sx, sy = self._grids()
+        return dict(kind=4, a=[sx, sy, 0.0, 0.0], width=self.width, height=self.height, intensity=1.0,
+                    wavelength=0.0, first=int(first))
+
+    def source_pose(self) -> torch.Tensor:
+        """[12]: rows right / up / forward, then the pinhole position."""
+        return torch.cat([self.right, self.up_cam, self.forward, self.origin]).float().contiguous()
+
+    def generate_source_rays(self, samples: int = 1, seed: int = 0, first: int = 0, count=None):
+        """``samples`` rays per pixel as SourceRays (CUDA cameras): ray g = first + i covers pixel g mod (W*H),
+        sample g div (W*H); sample 0 is the reference's pixel-centre ray, the others are jittered by up to half a
+        pixel.  ``first`` / ``count`` select a shard (multi-GPU)."""
+        from .rays import SourceRays
+        n = self.width * self.height * int(samples) - int(first) if count is None else int(count)
+        state = torch.tensor([int(seed), 0], dtype=torch.int64, device=self.device)
+        return SourceRays(self.source_spec(samples, first), self.source_pose().to(self.device), state, n, 0)
+
     def generate_rays(self, samples: int = 1, seed: int = 0, pixel_range=None) -> Rays:
         """One ray per pixel (render/camera.py:39-72); ``samples`` > 1 adds jittered sub-pixel rays.
         ``pixel_range=(lo, hi)`` restricts to flat pixel indices [lo, hi) (multi-GPU sharding)."""

@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from . import codes as C
 from . import ops
-from .rays import Bundle, Rays
+from .rays import Bundle, Rays, SourceRays
 from .table import Dispersion, SceneCompiler
 
 
@@ -41,6 +41,9 @@ class Scene(nn.Module):
         # at an fp32 ulp of ~8e-6), so 2 is the smallest depth that reproduces its lists on
         # transmitting sensors; Sensor warns when a ray had more interactions than were kept.
         self.record_depth = 2
+        # False: a trace of in-kernel generated rays (SourceRays) skips the final pos/dir/intensity outputs —
+        # what the optimisation goals do, since they only read sensor records
+        self.final_rays = True
         self.mode: Optional[int] = None  # None = ops default (FAST)
         self.last_trace = None           # raw kernel outputs of the latest simulate()/step()
         self._compiler = SceneCompiler()
@@ -105,13 +108,18 @@ class Scene(nn.Module):
             if images[slot] is not None:
                 sensor.image = images[slot] if sensor.image is None else sensor.image + images[slot]
             if self.record_hits and records.numel():
-                sensor._pend(records[slot], hit_of_slot(slot), rays_before.id)
+                sensor._pend(records[slot], (lambda s=slot: hit_of_slot(s)), lambda: rays_before.id)
 
     def _trace(self, rays: Rays, nbounces: int):
         table = self._last_table = self.table()
         depth = max(1, min(int(self.record_depth), nbounces))
-        out = ops.trace_nonsequential(table, rays.pos, rays.dir, rays.intensity, nbounces, rays.wavelength,
-                                      want_record=self.record_hits, mode=self.mode, record_depth=depth)
+        src = rays if (isinstance(rays, SourceRays) and rays.generated) else None
+        if src is not None:
+            out = ops.trace_nonsequential(table, None, None, None, nbounces, want_record=self.record_hits,
+                                          mode=self.mode, record_depth=depth, source=src, want_rays=self.final_rays)
+        else:
+            out = ops.trace_nonsequential(table, rays.pos, rays.dir, rays.intensity, nbounces, rays.wavelength,
+                                          want_record=self.record_hits, mode=self.mode, record_depth=depth)
         self.last_trace = out
         records, counts = out["records"], out["sensor_counts"]
         for slot, sensor in enumerate(table.sensors):
@@ -120,9 +128,10 @@ class Scene(nn.Module):
             if self.record_hits and records.numel():
                 # one list entry per interaction ordinal (the reference: one per bounce; same multiset)
                 for k in range(depth):
-                    sensor._pend(records[slot, k], counts[slot] > k, rays.id,
+                    sensor._pend(records[slot, k], (lambda c=counts[slot], k=k: c > k), lambda: rays.id,
                                  overflow=(counts[slot], depth) if k == depth - 1 else None)
-        rays.pos, rays.dir, rays.intensity = out["pos"], out["dir"], out["intensity"]
+        if src is None or self.final_rays:
+            rays.pos, rays.dir, rays.intensity = out["pos"], out["dir"], out["intensity"]
         return out
 
     def simulate(self):
@@ -192,8 +201,13 @@ class SequentialScene(Scene):
         if rays is None:
             return None
         table = self._last_table = self.table()
-        out = ops.trace_sequential(table, rays.pos, rays.dir, rays.intensity, rays.wavelength,
-                                   want_record=self.record_hits, mode=self.mode)
+        src = rays if (isinstance(rays, SourceRays) and rays.generated) else None
+        if src is not None:     # rays generated in the kernel: no ray input read from HBM
+            out = ops.trace_sequential(table, want_record=self.record_hits, mode=self.mode, source=src,
+                                       want_rays=self.final_rays)
+        else:
+            out = ops.trace_sequential(table, rays.pos, rays.dir, rays.intensity, rays.wavelength,
+                                       want_record=self.record_hits, mode=self.mode)
         self.last_trace = out
         mask = out["hitmask"]
 
@@ -201,7 +215,8 @@ class SequentialScene(Scene):
             return ((mask >> table.sensor_rows[slot]) & 1).bool()
 
         self._deliver_to_sensors(table, out["records"], hit_of_slot, rays, out["images"])
-        rays.pos, rays.dir, rays.intensity = out["pos"], out["dir"], out["intensity"]
+        if src is None or self.final_rays:
+            rays.pos, rays.dir, rays.intensity = out["pos"], out["dir"], out["intensity"]
         return rays
 
     def to_base(self):

@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from raytracetorch_b200 import _cabi, codes as C
+from simcommon import SourceGoalMixin
 
 
 def _dev(a, dtype=torch.float32):
@@ -24,10 +25,32 @@ def _p(t):
     return 0 if t is None or t.numel() == 0 else t.data_ptr()
 
 
-class GpuSim:
+_TORCH_DT = {np.dtype(np.float32): torch.float32, np.dtype(np.int64): torch.int64, np.dtype(np.uint8): torch.uint8,
+             np.dtype(np.int32): torch.int32}
+
+
+class GpuSim(SourceGoalMixin):
     def __init__(self, mode: int):
         self.lib = _cabi.load()
-        self.mode = mode
+        self.mode = self._mode = mode
+
+    # hooks of SourceGoalMixin
+    @staticmethod
+    def _a(x):
+        x = np.ascontiguousarray(x)
+        return torch.as_tensor(x).to("cuda").contiguous()
+
+    @staticmethod
+    def _z(shape, dtype):
+        return torch.zeros(shape, dtype=_TORCH_DT[np.dtype(dtype)], device="cuda")
+
+    _pp = staticmethod(lambda t: 0 if t is None or t.numel() == 0 else t.data_ptr())
+    _host = staticmethod(lambda t: None if t is None else t.cpu().numpy())
+
+    def _st(self):
+        return self._stream()
+
+    _sync = staticmethod(lambda: torch.cuda.synchronize())
 
     def _stream(self):
         return ct.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -66,7 +89,7 @@ class GpuSim:
         sens, ns, keep = self._sensors(n, sensor_specs)
         op, od, oi = torch.empty_like(pos), torch.empty_like(dir_), torch.empty_like(inten)
         mask = torch.zeros(n, dtype=torch.int64, device="cuda")
-        self.lib.call("rtt_trace_seq_fwd", _p(pos), _p(dir_), _p(inten), _p(wav), _p(op), _p(od), _p(oi), _p(mask),
+        self.lib.call("rtt_trace_seq_fwd", _p(pos), _p(dir_), _p(inten), _p(wav), None, _p(op), _p(od), _p(oi), _p(mask),
                       ct.byref(req), sens, ns, n, self.mode, self._stream())
         torch.cuda.synchronize()
         return dict(pos=self._np(op), dir=self._np(od), intensity=self._np(oi),
@@ -86,7 +109,7 @@ class GpuSim:
         g_records = [_dev(g) for g in (g_records or [])]
         ns = len(g_records)
         rec_arr = (ct.c_void_p * ns)(*[_p(g) or None for g in g_records]) if ns else None
-        self.lib.call("rtt_trace_seq_bwd", _p(pos), _p(dir_), _p(inten), _p(wav), _p(mask),
+        self.lib.call("rtt_trace_seq_bwd", _p(pos), _p(dir_), _p(inten), _p(wav), None, _p(mask),
                       _p(g_pos), _p(g_dir), _p(g_int), rec_arr, _p(gp), _p(gd), _p(gi), _p(gt), _p(gl),
                       ct.byref(req), ns, n, self.mode, self._stream())
         torch.cuda.synchronize()
@@ -102,7 +125,7 @@ class GpuSim:
         op, od, oi = torch.empty_like(pos), torch.empty_like(dir_), torch.empty_like(inten)
         seq = torch.zeros((n, nbounces), dtype=torch.uint8, device="cuda")
         nh = torch.zeros(n, dtype=torch.uint8, device="cuda")
-        self.lib.call("rtt_trace_nonseq_fwd", _p(pos), _p(dir_), _p(inten), _p(wav), _p(op), _p(od), _p(oi),
+        self.lib.call("rtt_trace_nonseq_fwd", _p(pos), _p(dir_), _p(inten), _p(wav), None, _p(op), _p(od), _p(oi),
                       _p(seq), _p(nh), ct.byref(req), sens, ns, nbounces, n, self.mode, self._stream())
         torch.cuda.synchronize()
         return dict(pos=self._np(op), dir=self._np(od), intensity=self._np(oi), seq=self._np(seq), nb=self._np(nh),
@@ -122,7 +145,7 @@ class GpuSim:
         ns = len(g_records)
         rec_arr = (ct.c_void_p * ns)(*[_p(g) or None for g in g_records]) if ns else None
         hits = (ct.c_int32 * max(ns, 1))(*([record_hits] * max(ns, 1)))
-        self.lib.call("rtt_trace_nonseq_bwd", _p(pos), _p(dir_), _p(inten), _p(wav), _p(seq), seq.shape[1],
+        self.lib.call("rtt_trace_nonseq_bwd", _p(pos), _p(dir_), _p(inten), _p(wav), None, _p(seq), seq.shape[1],
                       _p(g_pos), _p(g_dir), _p(g_int), rec_arr, hits, _p(gp), _p(gd), _p(gi), _p(gt), _p(gl),
                       ct.byref(req), ns, n, self.mode, self._stream())
         torch.cuda.synchronize()

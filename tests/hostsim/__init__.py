@@ -16,6 +16,7 @@ import subprocess
 import numpy as np
 
 from raytracetorch_b200 import _cabi, codes as C
+from simcommon import SourceGoalMixin
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _BUILD = os.path.join(_HERE, "_build")
@@ -47,9 +48,18 @@ def _f32(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
 
 
-class HostSim:
+class HostSim(SourceGoalMixin):
     def __init__(self, lib: _cabi.RttLib):
         self.lib = lib
+        self._mode = 0
+
+    # hooks of SourceGoalMixin
+    _a = staticmethod(lambda x: np.ascontiguousarray(x))
+    _z = staticmethod(lambda shape, dtype: np.zeros(shape, dtype))
+    _pp = staticmethod(lambda x: 0 if x is None else x.ctypes.data)
+    _host = staticmethod(lambda x: x)
+    _st = staticmethod(lambda: None)
+    _sync = staticmethod(lambda: None)
 
     @staticmethod
     def _table(tf, ti, lut, lut_w):
@@ -86,7 +96,7 @@ class HostSim:
         sens, ns, keep = self._sensors(n, sensor_specs)
         op, od, oi = np.empty_like(pos), np.empty_like(dir_), np.empty_like(inten)
         mask = np.zeros(n, np.uint64)
-        self.lib.call("rtt_trace_seq_fwd", _p(pos), _p(dir_), _p(inten), _p(wav), _p(op), _p(od), _p(oi), _p(mask),
+        self.lib.call("rtt_trace_seq_fwd", _p(pos), _p(dir_), _p(inten), _p(wav), None, _p(op), _p(od), _p(oi), _p(mask),
                       ct.byref(req), sens, ns, n, 0, None)
         return dict(pos=op, dir=od, intensity=oi, hitmask=mask, sensors=keep)
 
@@ -102,7 +112,7 @@ class HostSim:
         g_records = [_f32(g) for g in (g_records or [])]
         ns = len(g_records)
         rec_arr = (ct.c_void_p * max(ns, 1))(*[_p(g) or None for g in g_records]) if ns else None
-        self.lib.call("rtt_trace_seq_bwd", _p(pos), _p(dir_), _p(inten), _p(wav), _p(mask),
+        self.lib.call("rtt_trace_seq_bwd", _p(pos), _p(dir_), _p(inten), _p(wav), None, _p(mask),
                       _p(g_pos), _p(g_dir), _p(g_int), rec_arr, _p(gp), _p(gd), _p(gi), _p(gt), _p(gl),
                       ct.byref(req), ns, n, 0, None)
         return dict(g_pos=gp, g_dir=gd, g_intensity=gi, g_table=gt, g_lut=gl)
@@ -116,7 +126,7 @@ class HostSim:
         op, od, oi = np.empty_like(pos), np.empty_like(dir_), np.empty_like(inten)
         seq = np.zeros((n, nbounces), np.uint8)
         nh = np.zeros(n, np.uint8)
-        self.lib.call("rtt_trace_nonseq_fwd", _p(pos), _p(dir_), _p(inten), _p(wav), _p(op), _p(od), _p(oi),
+        self.lib.call("rtt_trace_nonseq_fwd", _p(pos), _p(dir_), _p(inten), _p(wav), None, _p(op), _p(od), _p(oi),
                       _p(seq), _p(nh), ct.byref(req), sens, ns, nbounces, n, 0, None)
         return dict(pos=op, dir=od, intensity=oi, seq=seq, nb=nh, sensors=keep)
 
@@ -134,7 +144,7 @@ class HostSim:
         ns = len(g_records)
         rec_arr = (ct.c_void_p * max(ns, 1))(*[_p(g) or None for g in g_records]) if ns else None
         hits = (ct.c_int32 * max(ns, 1))(*([record_hits] * max(ns, 1)))
-        self.lib.call("rtt_trace_nonseq_bwd", _p(pos), _p(dir_), _p(inten), _p(wav), _p(seq), seq.shape[1],
+        self.lib.call("rtt_trace_nonseq_bwd", _p(pos), _p(dir_), _p(inten), _p(wav), None, _p(seq), seq.shape[1],
                       _p(g_pos), _p(g_dir), _p(g_int), rec_arr, hits, _p(gp), _p(gd), _p(gi), _p(gt), _p(gl),
                       ct.byref(req), ns, n, 0, None)
         return dict(g_pos=gp, g_dir=gd, g_intensity=gi, g_table=gt, g_lut=gl)

@@ -122,20 +122,36 @@ void reverse_row(const HostTable& T, int r, int lam, const Ck& ck, V3& gp, V3& g
     }
 }
 
+struct HostRay { V3 p, d; float I, wav; };
+HostRay fetch_ray(const rtt_source_t* src, const float* pos, const float* dir, const float* inten, const float* wav,
+                  bool want_wav, int64_t i) {
+    HostRay r;
+    if (src) {
+        source_ray(*src, source_key(*src), (long long)i, r.p, r.d);
+        r.I = src->intensity; r.wav = src->wavelength;
+    } else {
+        r.p = load3(pos, i); r.d = load3(dir, i);
+        r.I = inten ? inten[i] : 1.0f;
+        r.wav = want_wav ? wav[i] : 0.0f;
+    }
+    return r;
+}
+
 }  // namespace
 
 extern "C" {
 
 int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_intensity,
-                      const float* in_wavelength,
+                      const float* in_wavelength, const rtt_source_t* source,
                       float* out_pos, float* out_dir, float* out_intensity, uint64_t* hitmask,
                       const rtt_table_t* table, const rtt_sensor_t* sensors, int32_t n_sensors,
                       int64_t n, int32_t, void*) {
     const HostTable T = stage(table);
     for (int64_t i = 0; i < n; ++i) {
-        V3 p = load3(in_pos, i), d = load3(in_dir, i);
-        float I = in_intensity[i];
-        const int lam = T.L > 0 ? lam_index(T, in_wavelength[i]) : 0;
+        const HostRay ray = fetch_ray(source, in_pos, in_dir, in_intensity, in_wavelength, T.L > 0, i);
+        V3 p = ray.p, d = ray.d;
+        float I = ray.I;
+        const int lam = T.L > 0 ? lam_index(T, ray.wav) : 0;
         uint64_t mask = 0;
         for (int r = 0; r < T.S; ++r) {
             Frames F; Roots q; float t; int which;
@@ -148,15 +164,14 @@ int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_
             p = s.hit_global; d = s.new_dir; I = I * s.mod;
             mask |= 1ull << r;
         }
-        store3(out_pos, i, p); store3(out_dir, i, d);
-        out_intensity[i] = I;
+        if (out_pos) { store3(out_pos, i, p); store3(out_dir, i, d); out_intensity[i] = I; }
         if (hitmask) hitmask[i] = mask;
     }
     return 0;
 }
 
 int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float*,
-                      const float* in_wavelength, const uint64_t* hitmask,
+                      const float* in_wavelength, const rtt_source_t* source, const uint64_t* hitmask,
                       const float* g_out_pos, const float* g_out_dir, const float* g_out_intensity,
                       const float* const* g_record,
                       float* g_in_pos, float* g_in_dir, float* g_in_intensity,
@@ -166,8 +181,9 @@ int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float*,
     const HostTable T = stage(table);
     std::vector<Ck> ck(RTT_MAX_ROWS);
     for (int64_t i = 0; i < n; ++i) {
-        V3 p = load3(in_pos, i), d = load3(in_dir, i);
-        const int lam = T.L > 0 ? lam_index(T, in_wavelength[i]) : 0;
+        const HostRay ray = fetch_ray(source, in_pos, in_dir, nullptr, in_wavelength, T.L > 0, i);
+        V3 p = ray.p, d = ray.d;
+        const int lam = T.L > 0 ? lam_index(T, ray.wav) : 0;
         const uint64_t mask = hitmask[i];
         int nh = 0;
         for (int r = 0; r < T.S; ++r) {
@@ -204,16 +220,17 @@ int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float*,
 }
 
 int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* in_intensity,
-                         const float* in_wavelength,
+                         const float* in_wavelength, const rtt_source_t* source,
                          float* out_pos, float* out_dir, float* out_intensity,
                          uint8_t* hit_seq, uint8_t* n_hits,
                          const rtt_table_t* table, const rtt_sensor_t* sensors, int32_t n_sensors,
                          int32_t nbounces, int64_t n, int32_t, void*) {
     const HostTable T = stage(table);
     for (int64_t i = 0; i < n; ++i) {
-        V3 p = load3(in_pos, i), d = load3(in_dir, i);
-        float I = in_intensity[i];
-        const int lam = T.L > 0 ? lam_index(T, in_wavelength[i]) : 0;
+        const HostRay ray = fetch_ray(source, in_pos, in_dir, in_intensity, in_wavelength, T.L > 0, i);
+        V3 p = ray.p, d = ray.d;
+        float I = ray.I;
+        const int lam = T.L > 0 ? lam_index(T, ray.wav) : 0;
         int cnt[RTT_MAX_SENSORS] = {0, 0, 0, 0};
         int nb = 0;
         for (; nb < nbounces; ++nb) {
@@ -244,14 +261,14 @@ int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* 
         if (hit_seq) for (int b = nb; b < nbounces; ++b) hit_seq[i * nbounces + b] = 255;
         if (n_hits) n_hits[i] = (uint8_t)nb;
         for (int s = 0; s < n_sensors; ++s) if (sensors[s].count) sensors[s].count[i] = (uint8_t)cnt[s];
-        store3(out_pos, i, p); store3(out_dir, i, d);
-        out_intensity[i] = I;
+        if (out_pos) { store3(out_pos, i, p); store3(out_dir, i, d); out_intensity[i] = I; }
     }
     return 0;
 }
 
 int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float*,
-                         const float* in_wavelength, const uint8_t* hit_seq, int32_t nbounces,
+                         const float* in_wavelength, const rtt_source_t* source,
+                         const uint8_t* hit_seq, int32_t nbounces,
                          const float* g_out_pos, const float* g_out_dir, const float* g_out_intensity,
                          const float* const* g_record, const int32_t* record_hits,
                          float* g_in_pos, float* g_in_dir, float* g_in_intensity,
@@ -261,8 +278,9 @@ int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float*,
     std::vector<Ck> ck(nbounces + 1);
     std::vector<int> rows_hit(nbounces + 1);
     for (int64_t i = 0; i < n; ++i) {
-        V3 p = load3(in_pos, i), d = load3(in_dir, i);
-        const int lam = T.L > 0 ? lam_index(T, in_wavelength[i]) : 0;
+        const HostRay ray = fetch_ray(source, in_pos, in_dir, nullptr, in_wavelength, T.L > 0, i);
+        V3 p = ray.p, d = ray.d;
+        const int lam = T.L > 0 ? lam_index(T, ray.wav) : 0;
         int cnt[RTT_MAX_SENSORS] = {0, 0, 0, 0};
         int nh = 0;
         for (int b = 0; b < nbounces && b < 32; ++b) {
@@ -378,6 +396,92 @@ int rtt_surface_step_bwd(const float* in_pos, const float* in_dir, const float* 
             }
             add_row_grad(G, fl, g_table + (size_t)row * RTT_ROW_G);
         }
+    }
+    return 0;
+}
+
+int rtt_sample_bundle(const rtt_source_t* source, float* pos, float* dir, float* intensity, float* wavelength,
+                      int64_t n, int32_t, void*) {
+    if (!source || !source->pose) return RTT_E_ARG;
+    const SourceKey k = source_key(*source);
+    for (int64_t i = 0; i < n; ++i) {
+        V3 p, d;
+        source_ray(*source, k, (long long)i, p, d);
+        store3(pos, i, p); store3(dir, i, d);
+        intensity[i] = source->intensity;
+        if (wavelength) wavelength[i] = source->wavelength;
+    }
+    return 0;
+}
+
+// ---- goal reductions (rtt_goals.cu), restated with plain double-precision loops -----------------------
+namespace {
+struct HCentre { double W, cx, cy; bool clamped; };
+HCentre hcentre(const float* mom4, const float* target_xy) {
+    HCentre c;
+    c.clamped = !(mom4[0] >= 1e-12f);
+    c.W = c.clamped ? 1e-12 : (double)mom4[0];
+    c.cx = target_xy ? (double)target_xy[0] : (double)mom4[1] / c.W;
+    c.cy = target_xy ? (double)target_xy[1] : (double)mom4[2] / c.W;
+    return c;
+}
+}  // namespace
+
+int rtt_spot_moments(const float* rec, int64_t m, int32_t active_only, float* out4, float*, void*) {
+    double a[4] = {0, 0, 0, 0};
+    for (int64_t i = 0; i < m; ++i) {
+        const float x = rec[4 * i], y = rec[4 * i + 1], w = rec[4 * i + 3];
+        if (!active_only || w > 0.0f) { a[0] += w; a[1] += (double)x * w; a[2] += (double)y * w; }
+        if (w > 0.0f) a[3] += 1.0;
+    }
+    for (int k = 0; k < 4; ++k) out4[k] = (float)a[k];
+    return 0;
+}
+
+int rtt_spot_moments_bwd(const float* rec, int64_t m, int32_t active_only, const float* g3, float* g_rec, void*) {
+    for (int64_t i = 0; i < m; ++i) {
+        const float x = rec[4 * i], y = rec[4 * i + 1], w = rec[4 * i + 3];
+        const bool on = !active_only || w > 0.0f;
+        g_rec[4 * i] = on ? g3[1] * w : 0.0f; g_rec[4 * i + 1] = on ? g3[2] * w : 0.0f; g_rec[4 * i + 2] = 0.0f;
+        g_rec[4 * i + 3] = on ? g3[0] + g3[1] * x + g3[2] * y : 0.0f;
+    }
+    return 0;
+}
+
+int rtt_spot_size_fwd(const float* rec, int64_t m, const float* mom4, const float* target_xy, float* out3,
+                      float*, void*) {
+    const HCentre c = hcentre(mom4, target_xy);
+    double L = 0, gx = 0, gy = 0;
+    for (int64_t i = 0; i < m; ++i) {
+        const double x = rec[4 * i], y = rec[4 * i + 1], w = rec[4 * i + 3];
+        if (!(w > 0.0)) continue;
+        const double dx = x - c.cx, dy = y - c.cy, wn = w / c.W;
+        const double q = (dx * dx + dy * dy) * wn, rms = std::sqrt(q);
+        L += rms;
+        const double a = q > 0.0 ? 0.5 / rms : 0.0;
+        gx += a * (-2.0 * dx * wn); gy += a * (-2.0 * dy * wn);
+    }
+    out3[0] = (float)L; out3[1] = (float)gx; out3[2] = (float)gy;
+    return 0;
+}
+
+int rtt_spot_size_bwd(const float* rec, int64_t m, const float* mom4, const float* target_xy, const float* out3,
+                      const float* g_loss, float* g_rec, void*) {
+    const HCentre c = hcentre(mom4, target_xy);
+    const double gL = g_loss[0];
+    const double Gcx = target_xy ? 0.0 : out3[1], Gcy = target_xy ? 0.0 : out3[2];
+    const double gW = c.clamped ? 0.0 : (-0.5 * out3[0] / c.W - (Gcx * c.cx + Gcy * c.cy) / c.W);
+    for (int64_t i = 0; i < m; ++i) {
+        const double x = rec[4 * i], y = rec[4 * i + 1], w = rec[4 * i + 3];
+        double g0 = 0, g1 = 0, g3 = 0;
+        if (w > 0.0) {
+            const double dx = x - c.cx, dy = y - c.cy, wn = w / c.W, r2 = dx * dx + dy * dy, q = r2 * wn;
+            const double a = q > 0.0 ? 0.5 / std::sqrt(q) : 0.0;
+            g0 = gL * (a * 2.0 * dx * wn + Gcx * wn);
+            g1 = gL * (a * 2.0 * dy * wn + Gcy * wn);
+            g3 = gL * (a * r2 / c.W + (Gcx * x + Gcy * y) / c.W + gW);
+        }
+        g_rec[4 * i] = (float)g0; g_rec[4 * i + 1] = (float)g1; g_rec[4 * i + 2] = 0.0f; g_rec[4 * i + 3] = (float)g3;
     }
     return 0;
 }

@@ -78,22 +78,22 @@ def test_argument_validation_and_no_cpu_path():
     req = _cabi.make_table(tf.ctypes.data, ti.ctypes.data, 1)
     f = lib.dll.rtt_trace_seq_fwd
     # null table / null rays / too many rows: negative RTT_E_* codes, never a crash
-    assert f(pos.ctypes.data, pos.ctypes.data, inten.ctypes.data, None, pos.ctypes.data, pos.ctypes.data,
+    assert f(pos.ctypes.data, pos.ctypes.data, inten.ctypes.data, None, None, pos.ctypes.data, pos.ctypes.data,
              inten.ctypes.data, None, None, None, 0, 4, 0, None) == -1
-    assert f(None, pos.ctypes.data, inten.ctypes.data, None, pos.ctypes.data, pos.ctypes.data,
+    assert f(None, pos.ctypes.data, inten.ctypes.data, None, None, pos.ctypes.data, pos.ctypes.data,
              inten.ctypes.data, None, ct.byref(req), None, 0, 4, 0, None) == -1
     big = _cabi.make_table(tf.ctypes.data, ti.ctypes.data, C.MAX_ROWS + 1)
-    assert f(pos.ctypes.data, pos.ctypes.data, inten.ctypes.data, None, pos.ctypes.data, pos.ctypes.data,
+    assert f(pos.ctypes.data, pos.ctypes.data, inten.ctypes.data, None, None, pos.ctypes.data, pos.ctypes.data,
              inten.ctypes.data, None, ct.byref(big), None, 0, 4, 0, None) == -2
     assert b"rows" in lib.dll.rtt_error_string(-2)
     if not torch.cuda.is_available():
         # valid arguments, no device: must refuse (RTT_E_NO_DEVICE), not compute on the host
-        code = f(pos.ctypes.data, pos.ctypes.data, inten.ctypes.data, None, pos.ctypes.data, pos.ctypes.data,
+        code = f(pos.ctypes.data, pos.ctypes.data, inten.ctypes.data, None, None, pos.ctypes.data, pos.ctypes.data,
                  inten.ctypes.data, None, ct.byref(req), None, 0, 4, 0, None)
         assert code == -3
         assert b"no CPU path" in lib.dll.rtt_error_string(code)
         with pytest.raises(_cabi.RttError):
-            lib.call("rtt_trace_seq_fwd", pos.ctypes.data, pos.ctypes.data, inten.ctypes.data, None,
+            lib.call("rtt_trace_seq_fwd", pos.ctypes.data, pos.ctypes.data, inten.ctypes.data, None, None,
                      pos.ctypes.data, pos.ctypes.data, inten.ctypes.data, None, ct.byref(req), None, 0, 4, 0, None)
 
 

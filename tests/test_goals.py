@@ -89,3 +89,91 @@ def test_goals_match_reference_loss_and_gradients(rtt_ns, name):
         assert parity.grad_rel(g, d[f"ieee_{name}_g_c{k}"]) < parity.TOL_GRAD, (k, g, d[f"ieee_{name}_g_c{k}"])
     stock = float(d[f"{name}_loss"])
     assert abs(float(loss.detach()) - stock) <= 2e-2 * abs(stock)
+
+
+@pytest.mark.gpu
+def test_device_bundles_are_generated_inside_the_trace_kernels(rtt_ns):
+    """Bundle.sample on a CUDA device returns SourceRays; SequentialScene.simulate generates them in registers
+    and gives bit-identical results to tracing the materialised bundle (rtt_sample_bundle)."""
+    import raytracetorch_b200 as rtt
+    import scenes
+    from raytracetorch_b200.rays import SourceRays
+    dev = torch.device("cuda", 0)
+    for make in (lambda: rtt.rays.CollimatedDisk(5.0, 3, device=dev, transform=rtt.geom.RayTransformBundle(
+                     translation=[0.0, 0.0, -10.0], rotation=[0.01, -0.02, 0.0]).to(dev)),
+                 lambda: rtt.rays.PointSource(0.05, 1, device=dev, transform=rtt.geom.RayTransformBundle(
+                     translation=[0.0, 0.0, -60.0]).to(dev))):
+        bundle = make()
+        r = bundle.sample(20_000)
+        assert isinstance(r, SourceRays) and r.generated and len(r) == 20_000
+        twin = SourceRays(r.source, r.pose, r.state, r.n, r.ray_id)        # same {key, counter}: the same rays
+        pos0 = twin.pos.clone()                                           # materialises
+        assert not twin.generated and twin.id.dtype == torch.int8 and int(twin.id[0]) == bundle.ray_id
+        np.testing.assert_allclose(torch.linalg.norm(twin.dir, dim=1).cpu().numpy(), 1.0, atol=1e-6)
+        outs = []
+        for rays in (r, twin):
+            els = scenes.c1_singlet(rtt_ns, physical=True)
+            scene = rtt.scene.SequentialScene(els).to(dev)
+            out = scene.simulate(rays)
+            locs, w, ids = els[1].getHitsTensors()
+            outs.append([t.cpu().numpy() for t in (out.pos, out.dir, out.intensity, locs, w, ids)])
+        for a, b in zip(*outs):
+            np.testing.assert_array_equal(a, b)
+        assert outs[0][3].shape[0] > 1000 and not np.array_equal(outs[0][0], pos0.cpu().numpy())
+    # consecutive samples advance the counter: different rays
+    a, b = bundle.sample(100), bundle.sample(100)
+    assert not torch.equal(a.pos, b.pos)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("target", [None, [0.1, -0.2]])
+def test_fused_goal_equals_eager_goal_on_the_same_rays(rtt_ns, target, monkeypatch):
+    """SpotSizeLoss through the fused path (in-kernel bundle, no final-ray outputs, rtt_spot_* reductions) vs the
+    same goal evaluated with eager torch ops on the materialised records: same loss, same parameter gradients."""
+    import raytracetorch_b200 as rtt
+    import scenes
+    from raytracetorch_b200 import optim, rays as R
+    dev = torch.device("cuda", 0)
+    res = []
+    for fused in (True, False):
+        R._SRC_STATE.clear()
+        torch.manual_seed(11)
+        els = scenes.c1_singlet(rtt_ns, physical=True, grads=True)
+        scene = rtt.scene.SequentialScene(els).to(dev)
+        bundles = [rtt.rays.CollimatedDisk(5.0, k, device=dev, transform=rtt.geom.RayTransformBundle(
+            translation=[0.0, 0.0, -10.0], rotation=rot).to(dev)) for k, rot in enumerate((None, [0.02, 0.0, 0.0]))]
+        if not fused:
+            monkeypatch.setattr(optim, "_sensor_records", lambda *a: None)
+        loss = rtt.optim.SpotSizeLoss(els[1], bundles, N_rays=50_000, target_xy=target)(scene)
+        loss.backward()
+        res.append((float(loss), [float(els[0].shape.surfaces[k].c.grad) for k in (0, 1)]))
+    (l1, g1), (l2, g2) = res
+    assert abs(l1 - l2) <= 2e-5 * abs(l2)
+    for a, b in zip(g1, g2):
+        assert abs(a - b) <= 1e-3 * abs(b), (g1, g2)
+
+
+@pytest.mark.gpu
+def test_spot_target_fused_equals_eager(rtt_ns, monkeypatch):
+    import raytracetorch_b200 as rtt
+    import scenes
+    from raytracetorch_b200 import optim, rays as R
+    dev = torch.device("cuda", 0)
+    res = []
+    for fused in (True, False):
+        R._SRC_STATE.clear()
+        torch.manual_seed(5)
+        els = scenes.c1_singlet(rtt_ns, physical=True, grads=True)
+        scene = rtt.scene.SequentialScene(els).to(dev)
+        bundles = [rtt.rays.CollimatedDisk(5.0, k, device=dev, transform=rtt.geom.RayTransformBundle(
+            translation=[0.0, 0.0, -10.0], rotation=rot).to(dev)) for k, rot in enumerate((None, [0.0, -0.03, 0.0]))]
+        if not fused:
+            monkeypatch.setattr(optim, "_sensor_records", lambda *a: None)
+        goal = rtt.optim.SpotTargetLoss(els[1], torch.tensor([[0.0, 0.0], [3.0, 0.0]])).to(dev)
+        loss = goal(scene, bundles, N_rays=30_000)
+        loss.backward()
+        res.append((float(loss), [float(els[0].shape.surfaces[k].c.grad) for k in (0, 1)]))
+    (l1, g1), (l2, g2) = res
+    assert abs(l1 - l2) <= 2e-5 * abs(l2) + 1e-9
+    for a, b in zip(g1, g2):
+        assert abs(a - b) <= 1e-3 * abs(b) + 1e-9, (g1, g2)

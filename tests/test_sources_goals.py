@@ -1,0 +1,164 @@
+"""In-kernel ray sources (rays/bundle.py:30-171, render/camera.py:39-72) and the fused goal reductions
+(optim/goals.py:42-187) on both back-ends: host build of the per-ray source (CPU suite) and the CUDA library."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import parity
+from raytracetorch_b200 import _cabi, codes as C
+
+EYE_POSE = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0.5, -0.25, -10.0], np.float32)
+
+
+def _tilted_pose():
+    from raytracetorch_b200.geom import rotation_from_vector
+    R = rotation_from_vector(torch.tensor([0.1, -0.2, 0.3])).numpy()
+    return np.concatenate([R.reshape(-1), [1.0, 2.0, -3.0]]).astype(np.float32)
+
+
+def test_disk_source_is_area_uniform_and_posed(run_exact):
+    n = 200_000
+    pose = _tilted_pose()
+    R, T = pose[:9].reshape(3, 3), pose[9:]
+    src = dict(kind=_cabi.SRC_DISK, a=[1.0, 25.0, 0.0, 2 * math.pi], pose=pose, seed=1234, first=0)
+    r = run_exact.sample(src, n)
+    local = (r["pos"] - T) @ R                    # invert pos @ R^T + T
+    rad2 = local[:, 0] ** 2 + local[:, 1] ** 2
+    assert np.abs(local[:, 2]).max() < 1e-5
+    assert rad2.min() >= 1.0 - 1e-4 and rad2.max() <= 25.0 + 1e-4
+    assert abs(rad2.mean() - 13.0) < 0.1          # r^2 ~ U(1, 25): area-uniform (rays/bundle.py:50)
+    assert np.abs(local[:, :2].mean(0)).max() < 0.03
+    want_dir = np.array([0, 0, 1], np.float32) @ R.T
+    np.testing.assert_allclose(r["dir"], np.broadcast_to(want_dir, (n, 3)), atol=1e-6)   # + renormalisation
+    assert np.all(r["intensity"] == 1.0) and np.all(r["wavelength"] == 0.0)
+    # counter-based: a shard starting at ray 1000 reproduces rays [1000, 1100) of the full bundle
+    part = run_exact.sample(dict(src, first=1000), 100)
+    np.testing.assert_array_equal(part["pos"], r["pos"][1000:1100])
+    # device-resident {key, counter} state replaces seed/first (CUDA-graph replay)
+    st = run_exact.sample(dict(src, seed=0, first=0, state=[1234, 1000]), 100)
+    np.testing.assert_array_equal(st["pos"], r["pos"][1000:1100])
+    other = run_exact.sample(dict(src, seed=99), 100)
+    assert np.abs(other["pos"] - r["pos"][:100]).max() > 0.1
+
+
+def test_point_line_fan_sources(run_exact):
+    n = 100_000
+    NA = 0.3
+    F_max = (1 - math.cos(math.asin(NA))) / math.pi          # rays/bundle.py:75-80, 153 (the reference's CDF)
+    r = run_exact.sample(dict(kind=_cabi.SRC_POINT, a=[0.0, F_max, 0.0, 2 * math.pi], pose=EYE_POSE, seed=5), n)
+    np.testing.assert_allclose(np.linalg.norm(r["dir"], axis=1), 1.0, atol=1e-6)
+    cosphi = r["dir"][:, 2]
+    assert cosphi.min() >= 1 - 2 * F_max - 1e-6 and cosphi.max() <= 1.0
+    assert abs(cosphi.mean() - (1 - F_max)) < 2e-3            # cos(phi) = 1 - 2F, F uniform
+    np.testing.assert_array_equal(r["pos"], np.broadcast_to(EYE_POSE[9:], (n, 3)))
+    ln = run_exact.sample(dict(kind=_cabi.SRC_LINE, a=[3.0], pose=EYE_POSE, seed=5), n)
+    x = ln["pos"][:, 0] - EYE_POSE[9]
+    assert x.min() >= -3.0 and x.max() <= 3.0 and abs(x.mean()) < 0.03 and abs(x.var() - 3.0) < 0.05
+    fan = run_exact.sample(dict(kind=_cabi.SRC_FAN, a=[0.25], pose=EYE_POSE, seed=5), n)
+    th = np.arctan2(fan["dir"][:, 1], fan["dir"][:, 2])
+    assert np.all(fan["dir"][:, 0] == 0) and th.min() >= -0.25 - 1e-6 and th.max() <= 0.25 + 1e-6
+
+
+def test_camera_source_matches_generate_rays(run_exact):
+    """Sample 0 of every pixel is the reference's pixel-centre ray (fixture from render/camera.py:39-72)."""
+    import raytracetorch_b200 as rtt
+    d = parity.load("extra_camera_rays")
+    cam = rtt.render.Camera((0.0, 0.0, -200.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 6.0, 64, 36)
+    src = cam.source_spec()
+    r = run_exact.sample(dict(src, pose=cam.source_pose().numpy(), seed=3), 3 * 64 * 36)
+    np.testing.assert_allclose(r["dir"][:64 * 36], d["dir"], atol=3e-7)
+    np.testing.assert_array_equal(r["pos"][:64 * 36], d["pos"])
+    # jittered samples stay within half a pixel of the centre ray
+    px = 2 * math.tan(math.radians(3.0)) * (64 / 36) / 63
+    dev = np.abs(r["dir"][64 * 36:2 * 64 * 36] - d["dir"]).max()
+    assert 0 < dev <= 0.51 * px * 1.01
+
+
+@pytest.mark.parametrize("name", ["c1_singlet_physical", "c2_cylindrical"])
+def test_trace_from_source_equals_trace_of_its_rays(run_fast, name):
+    """The trace kernels generate the rays of a source in registers: same outputs, bit for bit, as tracing
+    the bundle materialised by rtt_sample_bundle — forward and adjoint."""
+    d = parity.load(name)
+    n = 5000
+    pose = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, -10.0], np.float32)
+    src = dict(kind=_cabi.SRC_DISK, a=[0.0, 30.0, 0.0, 2 * math.pi], pose=pose, seed=77, first=12345)
+    rays = run_fast.sample(src, n)
+    a = run_fast.trace_seq(d["table_f"], d["table_i"], rays["pos"], rays["dir"], rays["intensity"], sensor_specs=[None])
+    b = run_fast.trace_seq_src(d["table_f"], d["table_i"], src, n, sensor_specs=[None])
+    for k in ("pos", "dir", "intensity", "hitmask"):
+        np.testing.assert_array_equal(a[k], b[k])
+    np.testing.assert_array_equal(a["sensors"][0][0], b["sensors"][0][0])
+    assert (a["hitmask"] != 0).mean() > 0.5
+    # records only: no final-ray outputs
+    c = run_fast.trace_seq_src(d["table_f"], d["table_i"], src, n, sensor_specs=[None], want_rays=False)
+    assert c["pos"] is None
+    np.testing.assert_array_equal(c["sensors"][0][0], a["sensors"][0][0])
+    g_rec = np.random.default_rng(0).standard_normal((n, 4)).astype(np.float32)
+    ti = d["table_i"].copy()
+    ti[:, C.I_FLAGS] = C.FLAG_GRAD_CK | C.FLAG_GRAD_POSE_S | C.FLAG_GRAD_IOR        # ask for parameter gradients
+    d = dict(d, table_i=ti)
+    ga = run_fast.trace_seq_bwd(d["table_f"], d["table_i"], rays["pos"], rays["dir"], rays["intensity"], a["hitmask"],
+                                None, None, None, g_records=[g_rec])
+    gb = run_fast.trace_seq_src_bwd(d["table_f"], d["table_i"], src, n, a["hitmask"], [g_rec])
+    scale = np.abs(ga["g_table"]).max()
+    assert scale > 0
+    np.testing.assert_allclose(gb["g_table"], ga["g_table"], rtol=1e-4, atol=1e-5 * scale)   # atomics: order only
+
+
+def _records(n=20000, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    rec = torch.randn((n, 4), generator=g)
+    rec[:, 0] = rec[:, 0] * 0.3 + 0.1
+    rec[:, 1] = rec[:, 1] * 0.2 - 0.05
+    rec[:, 3] = torch.rand(n, generator=g) + 0.1
+    dead = torch.rand(n, generator=g) < 0.3
+    rec[dead] = 0.0                                        # rays that never reached the sensor
+    rec[::97, 3] = -0.5                                    # negative weights are "inactive" for SpotSize only
+    return rec
+
+
+@pytest.mark.parametrize("active_only", [False, True])
+def test_spot_moments_and_adjoint(run_exact, active_only):
+    rec = _records().double().requires_grad_(True)
+    w = rec[:, 3]
+    on = (w > 0) if active_only else torch.ones_like(w, dtype=torch.bool)
+    mom = torch.stack([(w * on).sum(), (rec[:, 0] * w * on).sum(), (rec[:, 1] * w * on).sum()])
+    g3 = torch.tensor([0.3, -1.2, 0.7], dtype=torch.float64)
+    (mom * g3).sum().backward()
+    got = run_exact.spot_moments(rec.detach().float().numpy(), active_only)
+    np.testing.assert_allclose(got[:3], mom.detach().numpy(), rtol=2e-6)
+    assert got[3] == float((w > 0).sum())
+    gg = run_exact.spot_moments_bwd(rec.detach().float().numpy(), active_only, g3.float().numpy())
+    np.testing.assert_allclose(gg, rec.grad.numpy(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("target", [None, (0.05, -0.1)])
+def test_spot_size_and_adjoint_match_torch_autograd(run_exact, target):
+    """optim/goals.py:165-183 restated in torch (float64) with autograd as the checker."""
+    rec0 = _records(seed=3)
+    rec = rec0.double().requires_grad_(True)
+    act = rec[:, 3] > 0
+    xy, w = rec[act][:, :2], rec[act][:, 3]
+    W = w.sum().clamp(min=1e-12)
+    if target is None:
+        cx, cy = (xy[:, 0] * w).sum() / W, (xy[:, 1] * w).sum() / W
+    else:
+        cx, cy = torch.tensor(target[0], dtype=torch.float64), torch.tensor(target[1], dtype=torch.float64)
+    loss = torch.sqrt(((xy[:, 0] - cx) ** 2 + (xy[:, 1] - cy) ** 2) * (w / W)).sum()
+    (2.5 * loss).backward()
+    mom = run_exact.spot_moments(rec0.numpy(), True)
+    out3, g = run_exact.spot_size(rec0.numpy(), mom, target, g_loss=2.5, repeat=3)
+    assert abs(out3[0] - float(loss)) <= 3e-6 * float(loss)
+    scale = rec.grad.abs().max().item()
+    np.testing.assert_allclose(g, rec.grad.numpy(), rtol=2e-4, atol=2e-5 * scale)
+    assert np.all(g[~act.numpy()] == 0)
+
+
+def test_spot_reductions_on_empty_and_all_dead_records(run_exact):
+    dead = np.zeros((1000, 4), np.float32)
+    mom = run_exact.spot_moments(dead, True)
+    np.testing.assert_array_equal(mom, np.zeros(4, np.float32))
+    out3, g = run_exact.spot_size(dead, mom)
+    assert out3[0] == 0 and np.all(g == 0) and np.all(np.isfinite(g))
