@@ -145,13 +145,13 @@ def _seq_bwd_body(dev, n, pos, dir, intensity, wavelength, src, hitmask, g_pos, 
     lib = _cabi.load()
     S = table_f.shape[0]
     f32 = dict(dtype=torch.float32, device=dev)
-    e = torch.empty(0, **f32)
-    gp = torch.empty((n, 3), **f32) if need_rays else e
-    gd = torch.empty((n, 3), **f32) if need_rays else e
-    gi = torch.empty(n, **f32) if need_rays else e
-    gt = torch.zeros((S, C.ROW_G), **f32) if need_table else e
+    # every unrequested output is its own empty tensor: custom-op returns must not alias each other
+    gp = torch.empty((n, 3) if need_rays else 0, **f32)
+    gd = torch.empty((n, 3) if need_rays else 0, **f32)
+    gi = torch.empty(n if need_rays else 0, **f32)
+    gt = torch.zeros((S, C.ROW_G), **f32) if need_table else torch.empty(0, **f32)
     has_lut = lut is not None and lut.numel() > 0
-    gl = torch.zeros_like(lut) if (need_table and has_lut) else e
+    gl = torch.zeros_like(lut) if (need_table and has_lut) else torch.empty(0, **f32)
     ns = 0 if g_records is None else g_records.shape[0]
     rec_arr = (ct.c_void_p * ns)(*[g_records[s].data_ptr() for s in range(ns)]) if ns else None
     req = _table_req(table_f, table_i, lut, lut_w)
@@ -193,13 +193,13 @@ def _nonseq_bwd_body(dev, n, pos, dir, intensity, wavelength, src, hit_seq, g_po
     lib = _cabi.load()
     S = table_f.shape[0]
     f32 = dict(dtype=torch.float32, device=dev)
-    e = torch.empty(0, **f32)
-    gp = torch.empty((n, 3), **f32) if need_rays else e
-    gd = torch.empty((n, 3), **f32) if need_rays else e
-    gi = torch.empty(n, **f32) if need_rays else e
-    gt = torch.zeros((S, C.ROW_G), **f32) if need_table else e
+    # every unrequested output is its own empty tensor: custom-op returns must not alias each other
+    gp = torch.empty((n, 3) if need_rays else 0, **f32)
+    gd = torch.empty((n, 3) if need_rays else 0, **f32)
+    gi = torch.empty(n if need_rays else 0, **f32)
+    gt = torch.zeros((S, C.ROW_G), **f32) if need_table else torch.empty(0, **f32)
     has_lut = lut is not None and lut.numel() > 0
-    gl = torch.zeros_like(lut) if (need_table and has_lut) else e
+    gl = torch.zeros_like(lut) if (need_table and has_lut) else torch.empty(0, **f32)
     ns = 0 if g_records is None else g_records.shape[0]          # g_records: [ns, K, N, 4]
     rec_arr = (ct.c_void_p * ns)(*[g_records[s].data_ptr() for s in range(ns)]) if ns else None
     depth = (ct.c_int32 * ns)(*([g_records.shape[1]] * ns)) if ns else None
@@ -220,11 +220,10 @@ def _fake_seq_fwd(like, n, sensor_cfg, want_record, want_rays):
 
 
 def _fake_bwd(like, n, table_f, lut, need_rays, need_table):
-    e = like.new_empty(0)
-    return [like.new_empty((n, 3)) if need_rays else e, like.new_empty((n, 3)) if need_rays else e,
-            like.new_empty(n) if need_rays else e,
-            like.new_empty((table_f.shape[0], C.ROW_G)) if need_table else e,
-            torch.empty_like(lut) if (need_table and lut is not None) else e]
+    return [like.new_empty((n, 3) if need_rays else 0), like.new_empty((n, 3) if need_rays else 0),
+            like.new_empty(n if need_rays else 0),
+            like.new_empty((table_f.shape[0], C.ROW_G) if need_table else 0),
+            torch.empty_like(lut) if (need_table and lut is not None) else like.new_empty(0)]
 
 
 def _fake_nonseq_fwd(like, n, sensor_cfg, want_record, want_rays, nbounces, record_depth):
