@@ -376,6 +376,7 @@ RTT_HD bool shape_in_bounds(const RowDev* rows, int r, V3 h) {
         case RTT_SHAPE_CYL_EDGE: {                                      // geom/cylindrics.py:23-55
             const bool ap = (h.x <= hb[1]) && (h.x >= hb[0]) && (h.y <= hb[3]) && (h.y >= hb[2]);   // slack pre-added
             if (K::shape(R) == RTT_SHAPE_CYL_FACE) return ap;
+            if (!ap) return false;                                      // outside the aperture: the sag tests cannot save it
             const float zf = sag_at(hb[4], h.y, hb[5]);
             const float zb = sag_at(hb[6], h.y, hb[7]);
             return (h.z >= zf + 1e-4f) && (h.z <= zb - 1e-4f) && ap;

@@ -15,7 +15,9 @@
 //   * the adjoint kernels recompute the forward per ray (checkpoints = incoming (p, d) of
 //     each interaction) and reduce parameter gradients warp -> block (shared) -> global
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include "rtt_core.cuh"
+#include "rtt_tile.cuh"
 #include "rtt_kernels_decl.h"
 
 namespace rtt {
@@ -162,9 +164,22 @@ __device__ __forceinline__ void img_cache_add(ImgCache c, float* image, int slot
     const unsigned conv = __activemask();
     const int key = (slot << kImgKeyBits) | bin;
     const unsigned peers = __match_any_sync(conv, key);
-    float sum = 0.0f;
-    for (unsigned rem = peers; rem; rem &= rem - 1) sum += __shfl_sync(peers, w, __ffs((int)rem) - 1);
-    if ((int)(threadIdx.x & 31) != __ffs((int)peers) - 1) return;
+    float sum = w;
+    if (peers == kFull) {
+        // the whole warp lands in one bin (focused bundle): butterfly sum, lane 0 goes on
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
+        if (threadIdx.x & 31) return;
+    } else if (__popc(peers) > 1) {
+        // a few lanes share a bin: pairs are folded with one shuffle, larger groups go to the cache lane by
+        // lane (shared-memory atomics on one address serialise in the LSU, not in issue slots)
+        if (__popc(peers) == 2) {
+            const int hi = 31 - __clz((int)peers);
+            const float other = __shfl_sync(peers, w, hi);
+            if ((int)(threadIdx.x & 31) == hi) return;
+            sum = w + other;
+        }
+    }
     if (*reinterpret_cast<volatile int*>(c.fails) < kImgMaxFails) {
         int s = (int)(((unsigned)key * 2654435761u) >> (32 - kImgLog));
 #pragma unroll 1
@@ -261,6 +276,149 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_fwd)(const __gr
     }
     img_cache_flush(cache, a.sens);
 }
+
+#if defined(RTT_APPROX)
+// ============================================================================================
+// Sequential trace, forward, FAST variant: frame-resident ray tiles (rtt_tile.cuh)
+// ============================================================================================
+// Row loop outside, rays inside: every thread carries RPT rays in registers and walks the table
+// once for all of them, so the opcode dispatch, the row constants (shared-memory loads) and the
+// frame change of a row are paid once per RPT rays, and the RPT independent dependency chains
+// give the scheduler instruction-level parallelism on top of the resident warps.
+
+struct TileSmem {
+    Xf* xf;              // [S + 1]: xf[r] = frame(r-1) -> frame(r); xf[S] = frame(S-1) -> global
+};
+
+__host__ __device__ inline size_t tile_xf_bytes(int S) { return sizeof(Xf) * (size_t)(S + 1); }
+
+__device__ __forceinline__ void stage_tile(SmemTable& T, int S, Xf* xf) {
+    for (int r = threadIdx.x; r <= S; r += blockDim.x) {
+        xf[r] = make_xf(r > 0 ? &T.rows[r - 1] : nullptr, r < S ? &T.rows[r] : nullptr);
+        if (r < S) T.rows[r].i[DI_TILE_OP] = tile_opcode(T.rows[r]);
+    }
+    __syncthreads();
+}
+
+// Reference-order walk of one ray (rtt_core.cuh arithmetic): irregular rays of a tile launch.  Out of line and
+// free of pointer arguments into shared memory: it re-derives the table views from the dynamic shared-memory
+// base itself, so the hot loop's table accesses stay provably shared-space (LDS, not generic loads).
+struct WalkState { V3 p, d; float I; unsigned long long mask; };
+__device__ __noinline__ WalkState seq_walk_generic(const SeqFwdArgs& a, int lam, long long i, WalkState w) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = a.tab.S, L = a.tab.L;
+    SmemTable T = carve(smem_raw, S, L);
+    ImgCache cache = img_cache_carve(smem_raw + ((smem_table_bytes(S, L) + 15) / 16) * 16 + tile_xf_bytes(S));
+    unsigned long long bit = 1ull;
+    for (int r = 0; r < S; ++r, bit += bit) seq_row<KDyn>(T, S, L, r, lam, i, a, cache, w.p, w.d, w.I, w.mask, bit);
+    return w;
+}
+
+template <class K, int RPT>
+__device__ __forceinline__ void tile_row(const SmemTable& T, int S, int L, int r, const SeqFwdArgs& a, ImgCache cache,
+                                         long long i0, V3 (&p)[RPT], V3 (&d)[RPT], float (&I)[RPT],
+                                         unsigned long long (&mask)[RPT], const int (&lam)[RPT],
+                                         const bool (&act)[RPT], unsigned long long bit) {
+    const RowDev& R = T.rows[r];
+    float t[RPT];
+    bool hit[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) hit[j] = tile_test<K>(T.rows, r, p[j], d[j], t[j]) && act[j];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        if (hit[j]) {
+            float mu_enter = 0.0f, mu_exit = 0.0f;
+            if (K::phys(R) == RTT_PHYS_SNELL) {
+                const Ior io = row_ior(T, S, L, r, lam[j]);
+                mu_enter = io.mu_enter; mu_exit = io.mu_exit;
+            }
+            V3 np, nd, hl; float mod;
+            tile_interact<K>(R, p[j], d[j], t[j], mu_enter, mu_exit, np, nd, mod, hl);
+            if (K::sensor(R)) {
+                const int slot = R.i[RTT_I_SENSOR];
+                if (slot >= 0 && slot < a.n_sens)
+                    sensor_deposit(a.sens[slot], cache, slot, i0 + (long long)j * kThreads, hl, I[j], lam[j]);
+            }
+            p[j] = np; d[j] = nd; I[j] = I[j] * mod;
+            mask[j] |= bit;
+        }
+    }
+}
+
+template <int RPT, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_tile(const __grid_constant__ SeqFwdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = a.tab.S, L = a.tab.L;
+    SmemTable T = carve(smem_raw, S, L);
+    unsigned char* nxt = smem_raw + ((smem_table_bytes(S, L) + 15) / 16) * 16;
+    Xf* xf = reinterpret_cast<Xf*>(nxt);
+    ImgCache cache = img_cache_carve(nxt + tile_xf_bytes(S));
+    img_cache_init(cache);
+    stage_table(a.tab, T);
+    stage_tile(T, S, xf);
+    const SourceKey skey = fetch_key(a);
+    const long long tile = (long long)kThreads * RPT;
+    for (long long base = (long long)blockIdx.x * tile; base < a.n; base += (long long)gridDim.x * tile) {
+        const long long i0 = base + threadIdx.x;
+        V3 p[RPT], d[RPT];
+        float I[RPT];
+        unsigned long long mask[RPT];
+        int lam[RPT];
+        bool act[RPT], odd[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const long long i = i0 + (long long)j * kThreads;
+            p[j] = v3(0.0f, 0.0f, 0.0f); d[j] = v3(0.0f, 0.0f, 0.0f); I[j] = 0.0f; lam[j] = 0; mask[j] = 0ull;
+            act[j] = false; odd[j] = false;
+            if (i < a.n) {
+                const RayIn ray = fetch_ray(a, skey, i, L > 0);
+                p[j] = ray.p; d[j] = ray.d; I[j] = ray.I;
+                lam[j] = (L > 0) ? wavelength_index(T, L, ray.wav) : 0;
+                act[j] = regular_dir(ray.d);
+                odd[j] = !act[j];
+            }
+        }
+        unsigned long long bit = 1ull;
+        int op_next = T.rows[0].i[DI_TILE_OP];
+        for (int r = 0; r < S; ++r, bit += bit) {
+            const int op = op_next;
+            op_next = T.rows[(r + 1 < S) ? r + 1 : r].i[DI_TILE_OP];
+            const int kind = xf[r].kind;                                // warp-uniform
+            if (kind) {
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) apply_xf(xf[r], p[j], d[j]);
+            }
+            switch (op) {                                               // warp-uniform
+#define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR)                                         \
+                case OP: tile_row<KTile<SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR>, RPT>(T, S, L, r, a, cache, i0, p, d, I, mask, lam, act, bit); break;
+                RTT_TILE_SPECS(RTT_X)
+#undef RTT_X
+                default: tile_row<KDyn, RPT>(T, S, L, r, a, cache, i0, p, d, I, mask, lam, act, bit); break;
+            }
+        }
+        if (xf[S].kind) {
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) apply_xf(xf[S], p[j], d[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const long long i = i0 + (long long)j * kThreads;
+            if (odd[j]) {                                               // un-normalised direction: reference order
+                const RayIn ray = fetch_ray(a, skey, i, L > 0);
+                WalkState w;
+                w.p = ray.p; w.d = ray.d; w.I = ray.I; w.mask = 0ull;
+                w = seq_walk_generic(a, lam[j], i, w);
+                p[j] = w.p; d[j] = w.d; I[j] = w.I; mask[j] = w.mask;
+            }
+            if (i < a.n) {
+                if (a.opos) { store3(a.opos, i, p[j]); store3(a.odir, i, d[j]); a.ointen[i] = I[j]; }
+                if (a.hitmask) a.hitmask[i] = mask[j];
+            }
+        }
+    }
+    img_cache_flush(cache, a.sens);
+}
+#endif  // RTT_APPROX
 
 // ============================================================================================
 // Parameter-gradient reduction helpers (adjoint kernels)
@@ -758,7 +916,41 @@ inline cudaError_t allow_smem(Kern kern, size_t bytes) {
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+#if defined(RTT_APPROX)
+template <int RPT, int MINB>
+inline cudaError_t launch_tile(const SeqFwdArgs& a, cudaStream_t st) {
+    const size_t smem = fwd_smem(a.tab.S, a.tab.L) + tile_xf_bytes(a.tab.S);
+    if (cudaError_t e = allow_smem(k_trace_seq_fwd_tile<RPT, MINB>, smem)) return e;
+    const long long tiles = (a.n + (long long)kThreads * RPT - 1) / ((long long)kThreads * RPT);
+    // several waves of grid-striding blocks: a block that lands on a busier SM costs 1/kWaves of a launch
+    constexpr int kWaves = 4;
+    long long g = (long long)sm_count() * MINB * kWaves;
+    if (tiles < g) g = tiles;
+    if (g < 1) g = 1;
+    k_trace_seq_fwd_tile<RPT, MINB><<<(int)g, kThreads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+// RTT_FWD_TILE = rays per thread of the frame-resident forward kernel (1, 2, 4; 0 = the per-ray kernel)
+inline int fwd_tile_choice() {
+    static int choice = -1;
+    if (choice < 0) {
+        const char* e = getenv("RTT_FWD_TILE");
+        choice = e ? atoi(e) : 2;
+    }
+    return choice;
+}
+#endif
+
 cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
+#if defined(RTT_APPROX)
+    switch (fwd_tile_choice()) {
+        case 1: return launch_tile<1, 4>(a, st);
+        case 2: return launch_tile<2, 3>(a, st);
+        case 3: return launch_tile<2, 4>(a, st);
+        case 4: return launch_tile<4, 2>(a, st);
+        default: break;
+    }
+#endif
     if (cudaError_t e = allow_smem(RTT_NAME(k_trace_seq_fwd), fwd_smem(a.tab.S, a.tab.L))) return e;
     RTT_NAME(k_trace_seq_fwd)<<<grid_for(a.n, 8), kThreads, fwd_smem(a.tab.S, a.tab.L), st>>>(a);
     return cudaGetLastError();

@@ -44,7 +44,8 @@ for ln in dis.splitlines():
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 agg, tot, hdr, active, taken, base_addr = {}, 0.0, None, False, False, None
-base = re.search(r"k_[a-z_]+?(?=_fast|_exact|$)", kern).group(0)
+_m = re.search(r"k_[a-z_]+?(?=_fast|_exact|$)", kern)
+base = _m.group(0) if _m else "k_trace"
 for r in rows:
     if r and r[0] == "Kernel Name":
         active = (base in r[1]) and not taken

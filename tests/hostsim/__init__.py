@@ -20,7 +20,7 @@ from simcommon import SourceGoalMixin
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _BUILD = os.path.join(_HERE, "_build")
-_FLAGS = {"exact": ["-ffp-contract=off", "-mfma"], "fast": ["-ffp-contract=fast", "-mfma"]}
+_FLAGS = {"exact": ["-ffp-contract=off", "-mfma"], "fast": ["-ffp-contract=fast", "-mfma", "-DRTT_HOST_TILE"]}
 _cache = {}
 
 
@@ -31,8 +31,9 @@ def build(variant: str = "exact") -> "HostSim":
     out = os.path.join(_BUILD, f"librtt_hostsim_{variant}.so")
     src = os.path.join(_HERE, "hostsim.cpp")
     core = os.path.join(_HERE, "..", "..", "raytracetorch_b200", "csrc", "rtt_core.cuh")
+    tile = os.path.join(_HERE, "..", "..", "raytracetorch_b200", "csrc", "rtt_tile.cuh")
     hdr = os.path.join(_HERE, "..", "..", "include", "rtt_b200.h")
-    newest = max(os.path.getmtime(src), os.path.getmtime(core), os.path.getmtime(hdr))
+    newest = max(os.path.getmtime(p) for p in (src, core, tile, hdr, __file__))
     if not os.path.exists(out) or os.path.getmtime(out) < newest:
         cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fno-fast-math", *_FLAGS[variant], src, "-o", out]
         subprocess.run(cmd, check=True)

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../raytracetorch_b200/csrc/rtt_core.cuh"
+#include "../../raytracetorch_b200/csrc/rtt_tile.cuh"
 
 using namespace rtt;
 
@@ -147,12 +148,39 @@ int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_
                       const rtt_table_t* table, const rtt_sensor_t* sensors, int32_t n_sensors,
                       int64_t n, int32_t, void*) {
     const HostTable T = stage(table);
+#ifdef RTT_HOST_TILE
+    // mirror of k_trace_seq_fwd_tile (FAST variant): frame-resident walk of rtt_tile.cuh
+    std::vector<Xf> xf(T.S + 1);
+    for (int r = 0; r <= T.S; ++r)
+        xf[r] = make_xf(r > 0 ? &T.rows[r - 1] : nullptr, r < T.S ? &T.rows[r] : nullptr);
+#endif
     for (int64_t i = 0; i < n; ++i) {
         const HostRay ray = fetch_ray(source, in_pos, in_dir, in_intensity, in_wavelength, T.L > 0, i);
         V3 p = ray.p, d = ray.d;
         float I = ray.I;
         const int lam = T.L > 0 ? lam_index(T, ray.wav) : 0;
         uint64_t mask = 0;
+#ifdef RTT_HOST_TILE
+        if (regular_dir(d)) {
+            for (int r = 0; r < T.S; ++r) {
+                apply_xf(xf[r], p, d);
+                float t;
+                if (!tile_test(T.rows.data(), r, p, d, t)) continue;
+                const RowDev& R = T.rows[r];
+                const Ior io = row_ior(T, r, lam);
+                V3 np, nd, hl; float mod;
+                tile_interact(R, p, d, t, io.mu_enter, io.mu_exit, np, nd, mod, hl);
+                const int slot = R.i[RTT_I_SENSOR];
+                if (slot >= 0 && slot < n_sensors) deposit(sensors[slot], i, hl, I, lam);
+                p = np; d = nd; I = I * mod;
+                mask |= 1ull << r;
+            }
+            apply_xf(xf[T.S], p, d);
+            if (out_pos) { store3(out_pos, i, p); store3(out_dir, i, d); out_intensity[i] = I; }
+            if (hitmask) hitmask[i] = mask;
+            continue;
+        }
+#endif
         for (int r = 0; r < T.S; ++r) {
             Frames F; Roots q; float t; int which;
             if (!intersect<true>(T.rows.data(), r, p, d, F, q, t, which)) continue;

@@ -209,8 +209,20 @@ def test_full_size_properties_sequential(rtt_ns, n):
     h = n // 2
     a = rtt.ops.trace_sequential(tab, pos[:h], dirs[:h], inten[:h], want_record=False)
     b = rtt.ops.trace_sequential(tab, pos[h:], dirs[h:], inten[h:], want_record=False)
-    assert torch.equal(torch.cat([a["pos"], b["pos"]]), out["pos"])
-    assert torch.equal(torch.cat([a["intensity"], b["intensity"]]), out["intensity"])
+    # FAST mode: a ray's arithmetic may round differently depending on its slot in a launch tile (the
+    # compiler contracts the unrolled copies independently), so halves == whole to rounding, with
+    # boundary-tie flips allowed on <= 1e-6 of the rays; EXACT mode is bit-identical (checked below)
+    cat_pos, cat_int = torch.cat([a["pos"], b["pos"]]), torch.cat([a["intensity"], b["intensity"]])
+    same = cat_int == out["intensity"]
+    assert float((~same).float().mean()) <= 1e-6
+    assert float((cat_pos - out["pos"])[same].abs().max()) <= 1e-6 * 50.0
+    if n <= 10 ** 6:
+        ex = [rtt.ops.trace_sequential(tab, pos[s], dirs[s], inten[s], want_record=False, mode=rtt.ops.MODE_EXACT)
+              for s in (slice(None), slice(0, h), slice(h, None))]
+        assert torch.equal(torch.cat([ex[1]["pos"], ex[2]["pos"]]), ex[0]["pos"])
+        assert torch.equal(torch.cat([ex[1]["intensity"], ex[2]["intensity"]]), ex[0]["intensity"])
+        del ex
+    del cat_pos, cat_int, same
     img_halves = a["images"][0] + b["images"][0]
     assert float((img_halves - img).abs().sum() / img.sum()) < parity.TOL_IMAGE_L1
     del a, b, out2
