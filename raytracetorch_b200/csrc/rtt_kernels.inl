@@ -298,6 +298,9 @@ __device__ __forceinline__ void stage_tile(SmemTable& T, int S, Xf* xf) {
         if (r < S) T.rows[r].i[DI_TILE_OP] = tile_opcode(T.rows[r]);
     }
     __syncthreads();
+    // runs of lens-edge rows that can be culled together (same element frame)
+    for (int r = threadIdx.x; r < S; r += blockDim.x) edge_run_at(T.rows, S, xf, r);
+    __syncthreads();
 }
 
 // Reference-order walk of one ray (rtt_core.cuh arithmetic): irregular rays of a tile launch.  Out of line and
@@ -379,14 +382,22 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_tile(const __g
             }
         }
         unsigned long long bit = 1ull;
-        int op_next = T.rows[0].i[DI_TILE_OP];
         for (int r = 0; r < S; ++r, bit += bit) {
-            const int op = op_next;
-            op_next = T.rows[(r + 1 < S) ? r + 1 : r].i[DI_TILE_OP];
+            const int op = T.rows[r].i[DI_TILE_OP];
             const int kind = xf[r].kind;                                // warp-uniform
+            const int run = xf[r].run;
             if (kind) {
 #pragma unroll
                 for (int j = 0; j < RPT; ++j) apply_xf(xf[r], p[j], d[j]);
+            }
+            if (run > 0) {                                              // lens-edge rows: skip them when no lane can hit
+                bool away = true;
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) away = away && (!act[j] || edge_culled(xf[r], p[j], d[j]));
+                if (__all_sync(kFull, away)) {
+                    r += run - 1; bit <<= (run - 1);
+                    continue;
+                }
             }
             switch (op) {                                               // warp-uniform
 #define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR)                                         \
@@ -930,12 +941,13 @@ inline cudaError_t launch_tile(const SeqFwdArgs& a, cudaStream_t st) {
     k_trace_seq_fwd_tile<RPT, MINB><<<(int)g, kThreads, smem, st>>>(a);
     return cudaGetLastError();
 }
-// RTT_FWD_TILE = rays per thread of the frame-resident forward kernel (1, 2, 4; 0 = the per-ray kernel)
+// RTT_FWD_TILE selects the frame-resident forward kernel: 1 = 1 ray/thread, 2 = 2 rays (80 regs), 3 = 2 rays
+// (64 regs), 4 = 4 rays; 0 = the per-ray kernel of the EXACT variant's structure
 inline int fwd_tile_choice() {
     static int choice = -1;
     if (choice < 0) {
         const char* e = getenv("RTT_FWD_TILE");
-        choice = e ? atoi(e) : 2;
+        choice = e ? atoi(e) : 3;     // 2 rays per thread at 64 registers (4 blocks / SM): best on C1, C2 and C4
     }
     return choice;
 }

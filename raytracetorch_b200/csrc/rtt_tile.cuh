@@ -63,6 +63,11 @@ struct Xf {
     float M[9];
     float c[3];
     int32_t kind;        // 0: same frame, 1: translation only (M == I), 2: general
+    // lens-edge culling (see below): rows [r, r + run) can be skipped for a ray that passes the test
+    int32_t run;         // 0: row r is not the start / inside of a cullable run
+    float zlo, zhi;      // enclosure of the z range the edge rows accept (element frame)
+    int32_t ctype;       // 1: z test only, 2: + rectangular cross-section b = (x0, x1, y0, y1), 3: + disc, b[0] = r^2
+    float b[4];
     int32_t pad[3];
 };
 
@@ -83,7 +88,8 @@ RTT_HD FramePose frame_pose(const RowDev* R) {           // nullptr = global fra
 RTT_HD Xf make_xf(const RowDev* from, const RowDev* to) {
     const FramePose o = frame_pose(from), n = frame_pose(to);
     Xf x;
-    x.pad[0] = x.pad[1] = x.pad[2] = 0;
+    x.run = 0; x.zlo = 0.0f; x.zhi = 0.0f; x.ctype = 0;
+    x.b[0] = x.b[1] = x.b[2] = x.b[3] = 0.0f; x.pad[0] = x.pad[1] = x.pad[2] = 0;
     bool same_R = true, same_T = true, o_ident = true, n_ident = true;
     for (int a = 0; a < 9; ++a) {
         same_R = same_R && (o.R[a] == n.R[a]);
@@ -117,6 +123,94 @@ RTT_HD void apply_xf(const Xf& x, V3& p, V3& d) {
     if (x.kind == 1) { p = p + c; return; }
     p = mul_R(p, x.M) + c;
     d = mul_R(d, x.M);
+}
+
+// ---- lens-edge culling ---------------------------------------------------------------------------
+// The edge rows of a lens (the cylinder of a spherical lens, geom/spherics.py:34-39; the four side planes
+// of a cylindrical lens, geom/cylindrics.py:38-55) accept a hit only if its element-frame z lies between
+// the two faces, i.e. inside an enclosure [zlo, zhi].  Two result-preserving shortcuts:
+//   (z)  a ray that is beyond the enclosure and does not travel back towards it fails that rule for
+//        every t > 1e-6 (h.z = p.z + t d.z is monotone in t);
+//   (xy) the edge surfaces lie on / outside the boundary of the lens cross-section (rectangle or disc).
+//        If the ray's xy position now and at the moment it leaves the z enclosure are both strictly inside
+//        the (slightly shrunken) cross-section, the segment between them — the cross-section is convex —
+//        crosses no edge surface, so any edge hit lies beyond the enclosure and fails the z rule.
+// Either way the rows of the run report "no hit" exactly as the full test would; the kernel skips them
+// when every lane of the warp passes.  Margins (1e-3) are far above fp32 rounding at scene scale.
+constexpr float kCullMargin = 1e-3f;
+
+struct EdgeInfo { float zlo, zhi; int ctype; float b[4]; };
+
+RTT_HD bool edge_row_info(const RowDev& R, EdgeInfo& e) {
+    const float* hb = R.f + RTT_F_HB;                      // after prepare_row (cyl. aperture slack pre-added)
+    e.ctype = 1; e.b[0] = e.b[1] = e.b[2] = e.b[3] = 0.0f;
+    if (R.i[RTT_I_SHAPE] == RTT_SHAPE_SPHERIC_EDGE) {
+        e.zlo = hb[0] - kCullMargin; e.zhi = hb[1] + kCullMargin;
+        if (R.i[RTT_I_SURF] == RTT_SURF_CYLINDER && (R.i[DI_IDENT] & 2) && R.f[RTT_F_TS] == 0.0f &&
+            R.f[RTT_F_TS + 1] == 0.0f && R.f[RTT_F_RADIUS] > 4.0f * kCullMargin) {
+            const float rin = R.f[RTT_F_RADIUS] - 2.0f * kCullMargin;
+            e.ctype = 3; e.b[0] = rin * rin;
+        }
+        return true;
+    }
+    if (R.i[RTT_I_SHAPE] == RTT_SHAPE_CYL_EDGE) {
+        const float y0 = hb[2], y1 = hb[3];
+        const float ya = fabsf(y0) > fabsf(y1) ? y0 : y1;                       // largest |y| of the aperture
+        const float yi = (y0 <= 0.0f && y1 >= 0.0f) ? 0.0f : (fabsf(y0) < fabsf(y1) ? y0 : y1);   // smallest |y|
+        // sag is monotone in |y|: its extremes over the aperture sit at the two ends
+        const float f0 = sag_at(hb[4], yi, hb[5]), f1 = sag_at(hb[4], ya, hb[5]);
+        const float b0 = sag_at(hb[6], yi, hb[7]), b1 = sag_at(hb[6], ya, hb[7]);
+        e.zlo = fminf(f0, f1) - kCullMargin; e.zhi = fmaxf(b0, b1) + kCullMargin;
+        if (!(e.zlo == e.zlo && e.zhi == e.zhi)) return false;
+        if (R.i[RTT_I_SURF] == RTT_SURF_PLANE) {
+            // the plane (normal = third column of Rs, through Ts) must be vertical and must not cut the shrunken
+            // aperture rectangle: its four corners lie on one side
+            const float nx = R.f[RTT_F_RS + 2], ny = R.f[RTT_F_RS + 5], nz = R.f[RTT_F_RS + 8];
+            const float m = 2.0f * kCullMargin;
+            const float x0 = hb[0] + m, x1 = hb[1] - m, yy0 = hb[2] + m, yy1 = hb[3] - m;
+            if (fabsf(nz) <= 1e-6f && x0 < x1 && yy0 < yy1) {
+                const float tx = R.f[RTT_F_TS], ty = R.f[RTT_F_TS + 1];
+                const float s00 = nx * (x0 - tx) + ny * (yy0 - ty), s01 = nx * (x0 - tx) + ny * (yy1 - ty);
+                const float s10 = nx * (x1 - tx) + ny * (yy0 - ty), s11 = nx * (x1 - tx) + ny * (yy1 - ty);
+                const bool neg = s00 < 0.0f && s01 < 0.0f && s10 < 0.0f && s11 < 0.0f;
+                const bool pos = s00 > 0.0f && s01 > 0.0f && s10 > 0.0f && s11 > 0.0f;
+                if (neg || pos) { e.ctype = 2; e.b[0] = x0; e.b[1] = x1; e.b[2] = yy0; e.b[3] = yy1; }
+            }
+        }
+        return true;
+    }
+    return false;
+}
+
+// Fills xf[r].run / zlo / zhi / ctype / b for the run of cullable rows that starts at r (bounds = union over the
+// rest of the run, cross-section test only if every row of the run agrees on it).  Call after make_xf on all rows.
+RTT_HD void edge_run_at(const RowDev* rows, int S, Xf* xf, int r) {
+    EdgeInfo e;
+    if (!edge_row_info(rows[r], e)) return;
+    int run = 1;
+    for (int m = r + 1; m < S && xf[m].kind == 0; ++m, ++run) {
+        EdgeInfo e2;
+        if (!edge_row_info(rows[m], e2)) break;
+        e.zlo = fminf(e.zlo, e2.zlo); e.zhi = fmaxf(e.zhi, e2.zhi);
+        const bool same = e.ctype == e2.ctype && e.b[0] == e2.b[0] && e.b[1] == e2.b[1] && e.b[2] == e2.b[2] &&
+                          e.b[3] == e2.b[3];
+        if (!same) e.ctype = 1;
+    }
+    xf[r].run = run; xf[r].zlo = e.zlo; xf[r].zhi = e.zhi; xf[r].ctype = e.ctype;
+    for (int a = 0; a < 4; ++a) xf[r].b[a] = e.b[a];
+}
+
+RTT_HD bool edge_culled(const Xf& x, V3 p, V3 d) {
+    if ((p.z > x.zhi && d.z >= 0.0f) || (p.z < x.zlo && d.z <= 0.0f)) return true;          // (z)
+    if (x.ctype < 2 || d.z == 0.0f) return false;
+    // (xy): time at which the ray leaves the z enclosure, stretched a little (a longer segment is conservative)
+    const float zt = d.z > 0.0f ? x.zhi : x.zlo;
+    const float te = fmaf(div_(zt - p.z, d.z), 1.0001f, 1e-4f);
+    const float qx = fmaf(te, d.x, p.x), qy = fmaf(te, d.y, p.y);
+    if (x.ctype == 2)
+        return p.x > x.b[0] && p.x < x.b[1] && p.y > x.b[2] && p.y < x.b[3] &&
+               qx > x.b[0] && qx < x.b[1] && qy > x.b[2] && qy < x.b[3];
+    return (p.x * p.x + p.y * p.y) < x.b[0] && (qx * qx + qy * qy) < x.b[0];
 }
 
 // |d|^2 close enough to 1 (or exactly 0) for the per-row renormalisation to be the identity to 1e-6

@@ -153,6 +153,7 @@ int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_
     std::vector<Xf> xf(T.S + 1);
     for (int r = 0; r <= T.S; ++r)
         xf[r] = make_xf(r > 0 ? &T.rows[r - 1] : nullptr, r < T.S ? &T.rows[r] : nullptr);
+    for (int r = 0; r < T.S; ++r) edge_run_at(T.rows.data(), T.S, xf.data(), r);
 #endif
     for (int64_t i = 0; i < n; ++i) {
         const HostRay ray = fetch_ray(source, in_pos, in_dir, in_intensity, in_wavelength, T.L > 0, i);
@@ -164,6 +165,7 @@ int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_
         if (regular_dir(d)) {
             for (int r = 0; r < T.S; ++r) {
                 apply_xf(xf[r], p, d);
+                if (xf[r].run > 0 && edge_culled(xf[r], p, d)) { r += xf[r].run - 1; continue; }   // lens-edge culling
                 float t;
                 if (!tile_test(T.rows.data(), r, p, d, t)) continue;
                 const RowDev& R = T.rows[r];
