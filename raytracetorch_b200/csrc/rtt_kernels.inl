@@ -290,7 +290,11 @@ struct TileSmem {
     Xf* xf;              // [S + 1]: xf[r] = frame(r-1) -> frame(r); xf[S] = frame(S-1) -> global
 };
 
-__host__ __device__ inline size_t tile_xf_bytes(int S) { return sizeof(Xf) * (size_t)(S + 1); }
+// Shared-memory layout of the tile kernel: everything the hot loop touches sits at a compile-time offset
+// (image cache, frame changes, rows), so no pointer has to be kept in — or recomputed into — registers.
+constexpr size_t kTileOffXf = ((size_t)kImgSlots * 8 + 16 + 15) / 16 * 16;
+constexpr size_t kTileOffTable = (kTileOffXf + sizeof(Xf) * (RTT_MAX_ROWS + 1) + 15) / 16 * 16;
+__host__ __device__ inline size_t tile_smem_bytes(int S, int L) { return kTileOffTable + smem_table_bytes(S, L); }
 
 __device__ __forceinline__ void stage_tile(SmemTable& T, int S, Xf* xf) {
     for (int r = threadIdx.x; r <= S; r += blockDim.x) {
@@ -310,8 +314,8 @@ struct WalkState { V3 p, d; float I; unsigned long long mask; };
 __device__ __noinline__ WalkState seq_walk_generic(const SeqFwdArgs& a, int lam, long long i, WalkState w) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.tab.S, L = a.tab.L;
-    SmemTable T = carve(smem_raw, S, L);
-    ImgCache cache = img_cache_carve(smem_raw + ((smem_table_bytes(S, L) + 15) / 16) * 16 + tile_xf_bytes(S));
+    SmemTable T = carve(smem_raw + kTileOffTable, S, L);
+    ImgCache cache = img_cache_carve(smem_raw);
     unsigned long long bit = 1ull;
     for (int r = 0; r < S; ++r, bit += bit) seq_row<KDyn>(T, S, L, r, lam, i, a, cache, w.p, w.d, w.I, w.mask, bit);
     return w;
@@ -352,10 +356,9 @@ template <int RPT, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_tile(const __grid_constant__ SeqFwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.tab.S, L = a.tab.L;
-    SmemTable T = carve(smem_raw, S, L);
-    unsigned char* nxt = smem_raw + ((smem_table_bytes(S, L) + 15) / 16) * 16;
-    Xf* xf = reinterpret_cast<Xf*>(nxt);
-    ImgCache cache = img_cache_carve(nxt + tile_xf_bytes(S));
+    SmemTable T = carve(smem_raw + kTileOffTable, S, L);
+    Xf* xf = reinterpret_cast<Xf*>(smem_raw + kTileOffXf);
+    ImgCache cache = img_cache_carve(smem_raw);
     img_cache_init(cache);
     stage_table(a.tab, T);
     stage_tile(T, S, xf);
@@ -527,20 +530,62 @@ __device__ __forceinline__ void reverse_row(const SmemTable& T, int S, int L, in
     gI = gI * mod + g_w;
 }
 
-__global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_bwd)(const __grid_constant__ SeqBwdArgs a) {
+// Rays per block iteration of the sequential adjoint.  When no input-ray gradients are requested, a ray whose
+// upstream gradients (final position / direction, sensor-record xyz) are all zero contributes nothing to any
+// parameter gradient — every term of the reverse sweep is linear in them — so the block first compacts the
+// chunk to the rays that matter (dead rays of an intensity-weighted loss, rays that missed everything) and
+// runs the replay + reverse sweep on full warps of those.
+constexpr int kBwdChunk = 4 * kThreads;
+__host__ __device__ inline size_t bwd_queue_bytes() { return sizeof(unsigned short) * kBwdChunk + 16; }
+
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(const __grid_constant__ SeqBwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.tab.S, L = a.tab.L;
     SmemTable T = carve(smem_raw, S, L);
     float* acc = reinterpret_cast<float*>(smem_raw + ((smem_table_bytes(S, L) + 15) / 16) * 16);
     float* acc_lut = acc + S * RTT_ROW_G;
+    int* qcount = reinterpret_cast<int*>(acc_lut + L * S * 2 + ((L * S * 2 + S * RTT_ROW_G) & 1));   // 8-byte aligned
+    unsigned short* queue = reinterpret_cast<unsigned short*>(qcount + 2);
     for (int idx = threadIdx.x; idx < S * RTT_ROW_G + L * S * 2; idx += blockDim.x) acc[idx] = 0.0f;
     stage_table(a.tab, T);
 
-    const long long stride = (long long)gridDim.x * blockDim.x;
+    const bool compact = !a.g_pos && !a.g_dir && !a.g_inten;
     const SourceKey skey = fetch_key(a);
-    for (long long base = (long long)blockIdx.x * blockDim.x; base < a.n; base += stride) {
-        const long long i = base + threadIdx.x;
-        const bool live = i < a.n;
+    for (long long base = (long long)blockIdx.x * kBwdChunk; base < a.n; base += (long long)gridDim.x * kBwdChunk) {
+      int count = (int)((a.n - base) < (long long)kBwdChunk ? (a.n - base) : (long long)kBwdChunk);
+      if (compact) {
+        if (threadIdx.x == 0) *qcount = 0;
+        __syncthreads();
+        for (int k = 0; k < kBwdChunk / kThreads; ++k) {
+            const int loc = k * kThreads + threadIdx.x;
+            const long long i = base + loc;
+            bool need = false;
+            if (loc < count && a.hitmask[i] != 0ull) {
+                if (a.g_opos) { const V3 g = load3(a.g_opos, i); need = need || g.x != 0.0f || g.y != 0.0f || g.z != 0.0f; }
+                if (a.g_odir) { const V3 g = load3(a.g_odir, i); need = need || g.x != 0.0f || g.y != 0.0f || g.z != 0.0f; }
+                for (int sl = 0; sl < a.n_sens; ++sl)
+                    if (a.g_record[sl]) {
+                        const float4 gr = reinterpret_cast<const float4*>(a.g_record[sl])[i];
+                        need = need || gr.x != 0.0f || gr.y != 0.0f || gr.z != 0.0f;
+                    }
+            }
+            const unsigned votes = __ballot_sync(kFull, need);
+            if (votes) {
+                const int lane = threadIdx.x & 31, lead = __ffs((int)votes) - 1;
+                int pos = 0;
+                if (lane == lead) pos = atomicAdd(qcount, __popc(votes));
+                pos = __shfl_sync(kFull, pos, lead);
+                if (need) queue[pos + __popc(votes & ((1u << lane) - 1u))] = (unsigned short)loc;
+            }
+        }
+        __syncthreads();
+        count = *qcount;
+      }
+      for (int q0 = 0; q0 < count; q0 += kThreads) {
+        const int q = q0 + threadIdx.x;
+        const bool live = q < count;
+        const long long i = base + (live ? (compact ? (int)queue[q] : q) : 0);
         unsigned long long mask = 0ull;
         V3 p = v3(0, 0, 0), d = v3(0, 0, 1);
         int lam = 0;
@@ -616,6 +661,8 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_bwd)(const __gr
             if (a.g_dir) store3(a.g_dir, i, gd);
             if (a.g_inten) a.g_inten[i] = gI;
         }
+      }
+      if (compact) __syncthreads();                                       // the queue is rewritten by the next chunk
     }
     flush_block_grads(acc, S, a.g_table, acc_lut, L, a.g_lut);
 }
@@ -930,7 +977,7 @@ inline cudaError_t allow_smem(Kern kern, size_t bytes) {
 #if defined(RTT_APPROX)
 template <int RPT, int MINB>
 inline cudaError_t launch_tile(const SeqFwdArgs& a, cudaStream_t st) {
-    const size_t smem = fwd_smem(a.tab.S, a.tab.L) + tile_xf_bytes(a.tab.S);
+    const size_t smem = tile_smem_bytes(a.tab.S, a.tab.L);
     if (cudaError_t e = allow_smem(k_trace_seq_fwd_tile<RPT, MINB>, smem)) return e;
     const long long tiles = (a.n + (long long)kThreads * RPT - 1) / ((long long)kThreads * RPT);
     // several waves of grid-striding blocks: a block that lands on a busier SM costs 1/kWaves of a launch
@@ -967,8 +1014,23 @@ cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
     RTT_NAME(k_trace_seq_fwd)<<<grid_for(a.n, 8), kThreads, fwd_smem(a.tab.S, a.tab.L), st>>>(a);
     return cudaGetLastError();
 }
+// RTT_BWD_MINB = resident blocks per SM the sequential adjoint is compiled for (2: ~110 registers, 3: <= 85)
+inline int bwd_minb_choice() {
+    static int choice = -1;
+    if (choice < 0) {
+        const char* e = getenv("RTT_BWD_MINB");
+        choice = e ? atoi(e) : 3;     // measured: 3 blocks / SM (80 registers, a few spills) beats 2 by 4-8 %
+    }
+    return choice;
+}
 cudaError_t RTT_NAME(launch_seq_bwd)(const SeqBwdArgs& a, cudaStream_t st) {
-    RTT_NAME(k_trace_seq_bwd)<<<grid_for(a.n, 4), kThreads, bwd_smem(a.tab.S, a.tab.L), st>>>(a);
+    const size_t smem = bwd_smem(a.tab.S, a.tab.L) + 8 + bwd_queue_bytes();
+    const long long chunks = (a.n + kBwdChunk - 1) / kBwdChunk;
+    long long g = (long long)sm_count() * 8;
+    if (chunks < g) g = chunks;
+    if (g < 1) g = 1;
+    if (bwd_minb_choice() == 3) RTT_NAME(k_trace_seq_bwd)<3><<<(int)g, kThreads, smem, st>>>(a);
+    else RTT_NAME(k_trace_seq_bwd)<2><<<(int)g, kThreads, smem, st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t RTT_NAME(launch_nonseq_fwd)(const NonseqFwdArgs& a, cudaStream_t st) {
