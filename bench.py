@@ -254,7 +254,7 @@ def run_reference_arm(args):
                                          f"{threads} host threads (oracle/trace_oracle.py restates the reference's "
                                          f"algorithm; the Python reference itself cannot travel to the GPU box)"),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -470,21 +470,26 @@ def run_gpu_arm(args):
     # ---- end to end through the public API with host buffers --------------------------------------------
     e2e = None
     if not args.no_e2e:
-        host = [t.cpu().pin_memory() for t in (pos, dirs, inten)] + ([wav.cpu().pin_memory()] if wav is not None else [])
-        h2d = sum(t.numel() * t.element_size() for t in host)
+        host = [t.cpu().pin_memory() for t in (pos, dirs, inten)] + \
+               [(wav if wav is not None else torch.full((n,), 550.0, device=dev)).cpu().pin_memory()]
+        h2d = sum(t.numel() * t.element_size() for t in host) + (0 if w["nonseq"] else n)   # + int8 ray ids
         img_host = torch.empty(img_numel, dtype=torch.float32).pin_memory()
         ids = torch.zeros(n, dtype=torch.int8, device=dev)
         sensor = w["sensor"]
 
+        ids_host = torch.zeros(n, dtype=torch.int8).pin_memory()
+
         def e2e_step():
-            dv = [t.to(dev, non_blocking=True) for t in host]
-            rays = rtt.rays.Rays._wrap(pos=dv[0], dir=dv[1], intensity=dv[2], id=ids,
-                                       wavelength=dv[3] if len(dv) > 3 else dv[2])
             sensor.reset()
             if w["nonseq"]:
-                scene.rays = rays
+                dv = [t.to(dev, non_blocking=True) for t in host]
+                scene.rays = rtt.rays.Rays._wrap(pos=dv[0], dir=dv[1], intensity=dv[2], id=ids,
+                                                 wavelength=dv[3] if len(dv) > 3 else dv[2])
                 scene.simulate()
             else:
+                # host-resident Rays straight into the public call: simulate() pipelines the H2D chunks with the trace
+                rays = rtt.rays.Rays._wrap(pos=host[0], dir=host[1], intensity=host[2], id=ids_host,
+                                           wavelength=host[3] if len(host) > 3 else host[2])
                 scene.simulate(rays)
             img = sensor.image
             if world > 1:
@@ -533,7 +538,7 @@ def run_gpu_arm(args):
             line["e2e"] = e2e
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         tdist.barrier()
         tdist.destroy_process_group()
@@ -657,13 +662,33 @@ def run_c3(args):
                                   "reference's own GPU flow), so a step has no host input; the loss scalar is read back"))
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         tdist.barrier()
         tdist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Library chatter (NCCL's version banner, torchrun notices) must not share stdout with the ONE JSON line:
+    fd 1 is pointed at stderr for the whole run and the line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

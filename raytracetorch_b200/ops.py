@@ -812,6 +812,86 @@ def trace_sequential(table: SurfaceTable, pos=None, dir_=None, intensity=None, w
                 images=split_images(images, cfg))
 
 
+_copy_streams = {}
+
+
+def _copy_stream(dev: torch.device) -> "torch.cuda.Stream":
+    key = (dev.type, dev.index)
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device=dev)
+    return _copy_streams[key]
+
+
+def trace_sequential_host(table: SurfaceTable, pos, dir_, intensity, wavelength=None, *, want_record=False,
+                          sensor_cfg: Optional[List[float]] = None, mode: Optional[int] = None,
+                          chunk_rays: int = 1 << 23, ids=None):
+    """``trace_sequential`` for a bundle that lives in HOST memory (pinned for full copy speed).
+
+    The bundle is cut into chunks; chunk k+1 is copied host->device on a side stream while chunk k is traced
+    (one ``rtt_trace_seq_fwd`` launch per chunk, all accumulating into the same sensor images), so the step costs
+    about max(copy, trace) instead of their sum.  Forward only: no autograd graph is recorded (move the rays to
+    the device to differentiate).  Returns the same dict as ``trace_sequential`` plus the device copies of the
+    inputs (``in_pos, in_dir, in_intensity, in_wavelength``), everything on the table's device."""
+    _need_cuda(table.f)
+    for t in (pos, dir_, intensity):
+        if t.is_cuda:
+            raise ValueError("trace_sequential_host takes host tensors; use trace_sequential for device rays")
+    dev = table.f.device
+    lib = _cabi.load()
+    cfg = sensor_cfg_of(table) if sensor_cfg is None else list(sensor_cfg)
+    mode = _default_mode if mode is None else mode
+    f32 = dict(dtype=torch.float32, device=dev)
+    pos, dir_, intensity = (_f32c(t.detach()) for t in (pos, dir_, intensity))
+    use_wav = table.lut is not None and wavelength is not None       # the kernel reads it only with an index table
+    wav = _f32c(wavelength.detach()) if wavelength is not None else None   # but it is part of the Rays state: copied
+    n = pos.shape[0]
+    ns = len(cfg) // SENSOR_CFG
+    tf = table.f.detach()
+    with torch.cuda.device(dev):
+        cur, cp = torch.cuda.current_stream(dev), _copy_stream(dev)
+        d_pos, d_dir, d_int = torch.empty((n, 3), **f32), torch.empty((n, 3), **f32), torch.empty(n, **f32)
+        d_wav = torch.empty(n, **f32) if wav is not None else None
+        opos, odir, oint = torch.empty((n, 3), **f32), torch.empty((n, 3), **f32), torch.empty(n, **f32)
+        hitmask = torch.empty(n, dtype=torch.int64, device=dev)
+        rec_on = bool(want_record and ns)
+        records = torch.zeros((ns, n, 4), **f32) if rec_on else torch.empty((0, n, 4), **f32)
+        images = torch.zeros(_image_numel(cfg), **f32)
+        req = _table_req(tf, table.i, table.lut, table.lut_wavelengths)
+        cp.wait_stream(cur)                       # the fresh buffers may reuse blocks still in flight on `cur`
+        chunk = max(1, int(chunk_rays))
+        ready = []
+        with torch.cuda.stream(cp):
+            for start in range(0, n, chunk):
+                sl = slice(start, min(n, start + chunk))
+                d_pos[sl].copy_(pos[sl], non_blocking=True)
+                d_dir[sl].copy_(dir_[sl], non_blocking=True)
+                d_int[sl].copy_(intensity[sl], non_blocking=True)
+                if wav is not None:
+                    d_wav[sl].copy_(wav[sl], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cp)
+                ready.append((sl, ev))
+            d_id = None
+            if ids is not None:                   # ray ids ride along behind the last chunk
+                d_id = torch.empty(ids.shape, dtype=ids.dtype, device=dev)
+                d_id.copy_(ids, non_blocking=True)
+                d_id.record_stream(cur)
+            tail = torch.cuda.Event()
+            tail.record(cp)
+        for sl, ev in ready:
+            cur.wait_event(ev)
+            m = sl.stop - sl.start
+            sens, cnt = _sensor_reqs(cfg, m, [records[s_, sl] for s_ in range(ns)] if rec_on else None, images)
+            lib.call("rtt_trace_seq_fwd", d_pos[sl].data_ptr(), d_dir[sl].data_ptr(), d_int[sl].data_ptr(),
+                     d_wav[sl].data_ptr() if use_wav else 0, None,
+                     opos[sl].data_ptr(), odir[sl].data_ptr(), oint[sl].data_ptr(), hitmask[sl].data_ptr(),
+                     ct.byref(req), sens, cnt, m, mode, ct.c_void_p(cur.cuda_stream))
+        cur.wait_event(tail)
+    return dict(pos=opos, dir=odir, intensity=oint, hitmask=hitmask, records=records,
+                images=split_images(images, cfg), in_pos=d_pos, in_dir=d_dir, in_intensity=d_int,
+                in_wavelength=d_wav, in_id=d_id)
+
+
 def trace_nonsequential(table: SurfaceTable, pos, dir_, intensity, nbounces: int, wavelength=None, *,
                         want_record=True, sensor_cfg: Optional[List[float]] = None, mode: Optional[int] = None,
                         record_depth: int = 1, source=None, want_rays: bool = True):

@@ -202,6 +202,8 @@ class SequentialScene(Scene):
             return None
         table = self._last_table = self.table()
         src = rays if (isinstance(rays, SourceRays) and rays.generated) else None
+        if src is None and table.f.is_cuda and not rays.pos.is_cuda:
+            return self._simulate_host_bundle(table, rays)
         if src is not None:     # rays generated in the kernel: no ray input read from HBM
             out = ops.trace_sequential(table, want_record=self.record_hits, mode=self.mode, source=src,
                                        want_rays=self.final_rays)
@@ -217,6 +219,26 @@ class SequentialScene(Scene):
         self._deliver_to_sensors(table, out["records"], hit_of_slot, rays, out["images"])
         if src is None or self.final_rays:
             rays.pos, rays.dir, rays.intensity = out["pos"], out["dir"], out["intensity"]
+        return rays
+
+    def _simulate_host_bundle(self, table, rays: Rays):
+        """Rays in host memory, scene on the GPU: host->device copies are pipelined with the trace
+        (ops.trace_sequential_host).  The Rays object ends up on the device, like after ``rays.to(device)``
+        followed by ``simulate``; forward only."""
+        dev = table.f.device
+        out = ops.trace_sequential_host(table, rays.pos, rays.dir, rays.intensity, rays.wavelength,
+                                        want_record=self.record_hits, mode=self.mode, ids=rays.id)
+        self.last_trace = out
+        mask = out["hitmask"]
+        rays.id = out["in_id"]
+        rays.wavelength = out["in_wavelength"] if out["in_wavelength"] is not None \
+            else rays.wavelength.to(dev, non_blocking=True)
+
+        def hit_of_slot(slot):
+            return ((mask >> table.sensor_rows[slot]) & 1).bool()
+
+        self._deliver_to_sensors(table, out["records"], hit_of_slot, rays, out["images"])
+        rays.pos, rays.dir, rays.intensity = out["pos"], out["dir"], out["intensity"]
         return rays
 
     def to_base(self):
