@@ -136,7 +136,7 @@ __device__ __forceinline__ SourceKey fetch_key(const Args& a) {
 constexpr int kImgLog = 12;
 constexpr int kImgSlots = 1 << kImgLog;   // 4096 (bin, partial sum) pairs = 32 KB per block
 constexpr int kImgProbes = 4;             // linear probes before falling through to a global atomic
-constexpr int kImgMaxFails = 2 * kImgSlots;   // spread-out image: stop probing, go global directly
+constexpr int kImgMaxFails = 256;         // spread-out image (the cache is full of other bins): stop probing, go global directly
 constexpr int kImgKeyBits = 28;           // key = sensor slot << 28 | flat bin index
 
 struct ImgCache {
@@ -161,6 +161,10 @@ __device__ __forceinline__ void img_cache_init(ImgCache c) {
 }
 
 __device__ __forceinline__ void img_cache_add(ImgCache c, float* image, int slot, int bin, float w) {
+    if (*reinterpret_cast<volatile int*>(c.fails) >= kImgMaxFails) {     // cache switched off: one RED per deposit
+        atomicAdd(image + bin, w);
+        return;
+    }
     const unsigned conv = __activemask();
     const int key = (slot << kImgKeyBits) | bin;
     const unsigned peers = __match_any_sync(conv, key);
@@ -535,7 +539,7 @@ __device__ __forceinline__ void reverse_row(const SmemTable& T, int S, int L, in
 // parameter gradient — every term of the reverse sweep is linear in them — so the block first compacts the
 // chunk to the rays that matter (dead rays of an intensity-weighted loss, rays that missed everything) and
 // runs the replay + reverse sweep on full warps of those.
-constexpr int kBwdChunk = 4 * kThreads;
+constexpr int kBwdChunk = 16 * kThreads;   // large enough that the compacted chunk still fills whole blocks of warps
 __host__ __device__ inline size_t bwd_queue_bytes() { return sizeof(unsigned short) * kBwdChunk + 16; }
 
 template <int MINB>
@@ -552,12 +556,13 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
 
     const bool compact = !a.g_pos && !a.g_dir && !a.g_inten;
     const SourceKey skey = fetch_key(a);
-    for (long long base = (long long)blockIdx.x * kBwdChunk; base < a.n; base += (long long)gridDim.x * kBwdChunk) {
-      int count = (int)((a.n - base) < (long long)kBwdChunk ? (a.n - base) : (long long)kBwdChunk);
+    const int chunk = a.chunk;
+    for (long long base = (long long)blockIdx.x * chunk; base < a.n; base += (long long)gridDim.x * chunk) {
+      int count = (int)((a.n - base) < (long long)chunk ? (a.n - base) : (long long)chunk);
       if (compact) {
         if (threadIdx.x == 0) *qcount = 0;
         __syncthreads();
-        for (int k = 0; k < kBwdChunk / kThreads; ++k) {
+        for (int k = 0; k < chunk / kThreads; ++k) {
             const int loc = k * kThreads + threadIdx.x;
             const long long i = base + loc;
             bool need = false;
@@ -691,15 +696,27 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
     const int S = a.tab.S, L = a.tab.L, NB = a.nbounces;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const SourceKey skey = fetch_key(a);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
-        const RayIn ray = fetch_ray(a, skey, i, L > 0);
-        V3 p = ray.p, d = ray.d;
-        float I = ray.I;
-        const int lam = (L > 0) ? wavelength_index(T, L, ray.wav) : 0;
-        unsigned cnts = 0u;                                             // 8 bits per sensor slot
-        int nb = 0;
-        for (; nb < NB; ++nb) {
-            if (!(I > 0.0f)) break;                                     // base.py:140,201
+    // Lane refill: rays of a warp need different numbers of bounces (absorbed, escaped, still bouncing), so a lane
+    // whose ray has ended fetches its next ray at once instead of idling until the slowest ray of the warp is done.
+    // One trip of the loop = one bounce for every lane that holds a ray.
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool have = false;
+    V3 p = v3(0, 0, 0), d = v3(0, 0, 0);
+    float I = 0.0f;
+    int lam = 0, nb = 0;
+    unsigned cnts = 0u;                                                 // 8 bits per sensor slot
+    while (true) {
+        if (!have && i < a.n) {
+            const RayIn ray = fetch_ray(a, skey, i, L > 0);
+            p = ray.p; d = ray.d; I = ray.I;
+            lam = (L > 0) ? wavelength_index(T, L, ray.wav) : 0;
+            cnts = 0u; nb = 0;
+            have = true;
+        }
+        if (!__any_sync(kFull, have)) break;
+        if (!have) continue;
+        bool done = (nb >= NB) || !(I > 0.0f);                          // base.py:140,201
+        if (!done) {
             // ray_cast (base.py:164-176): min over all rows, NaN anywhere => no hit
             float best = rtt_inf();
             int win = -1;
@@ -715,26 +732,35 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
                     default: nonseq_probe<KDyn>(T.rows, r, p, d, best, win, poisoned); break;
                 }
             }
-            if (poisoned || win < 0) break;
-            Frames F; Roots q; float t; int which;
-            intersect<false>(T.rows, win, p, d, F, q, t, which);
-            const RowDev& R = T.rows[win];
-            const Ior io = row_ior(T, S, L, win, lam);
-            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
-            const int slot = R.i[RTT_I_SENSOR];
-            if (slot >= 0 && slot < a.n_sens) {
-                const unsigned c = (cnts >> (8 * slot)) & 255u;
-                sensor_deposit(a.sens[slot], cache, slot, i, s.hit_local, I, lam, (int)c, a.n);
-                if (c < 255u) cnts += 1u << (8 * slot);
+            if (poisoned || win < 0) {
+                done = true;
+            } else {
+                Frames F; Roots q; float t; int which;
+                intersect<false>(T.rows, win, p, d, F, q, t, which);
+                const RowDev& R = T.rows[win];
+                const Ior io = row_ior(T, S, L, win, lam);
+                const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
+                const int slot = R.i[RTT_I_SENSOR];
+                if (slot >= 0 && slot < a.n_sens) {
+                    const unsigned c = (cnts >> (8 * slot)) & 255u;
+                    sensor_deposit(a.sens[slot], cache, slot, i, s.hit_local, I, lam, (int)c, a.n);
+                    if (c < 255u) cnts += 1u << (8 * slot);
+                }
+                p = s.hit_global; d = s.new_dir; I = I * s.mod;
+                if (a.hit_seq) a.hit_seq[i * NB + nb] = (unsigned char)win;
+                ++nb;
+                done = nb >= NB;
             }
-            p = s.hit_global; d = s.new_dir; I = I * s.mod;
-            if (a.hit_seq) a.hit_seq[i * NB + nb] = (unsigned char)win;
         }
-        for (int s = 0; s < a.n_sens; ++s)
-            if (a.sens[s].count) a.sens[s].count[i] = (unsigned char)((cnts >> (8 * s)) & 255u);
-        if (a.hit_seq) for (int b = nb; b < NB; ++b) a.hit_seq[i * NB + b] = 255;
-        if (a.n_hits) a.n_hits[i] = (unsigned char)nb;
-        if (a.opos) { store3(a.opos, i, p); store3(a.odir, i, d); a.ointen[i] = I; }
+        if (done) {
+            for (int s = 0; s < a.n_sens; ++s)
+                if (a.sens[s].count) a.sens[s].count[i] = (unsigned char)((cnts >> (8 * s)) & 255u);
+            if (a.hit_seq) for (int b = nb; b < NB; ++b) a.hit_seq[i * NB + b] = 255;
+            if (a.n_hits) a.n_hits[i] = (unsigned char)nb;
+            if (a.opos) { store3(a.opos, i, p); store3(a.odir, i, d); a.ointen[i] = I; }
+            have = false;
+            i += stride;
+        }
     }
     img_cache_flush(cache, a.sens);
 }
@@ -1025,12 +1051,19 @@ inline int bwd_minb_choice() {
 }
 cudaError_t RTT_NAME(launch_seq_bwd)(const SeqBwdArgs& a, cudaStream_t st) {
     const size_t smem = bwd_smem(a.tab.S, a.tab.L) + 8 + bwd_queue_bytes();
-    const long long chunks = (a.n + kBwdChunk - 1) / kBwdChunk;
+    // chunk: as large as the queue allows, but small launches still spread over every resident block slot
+    const long long slots = (long long)(sm_count() > 0 ? sm_count() : 1) * 3 * 2;
+    long long chunk = ((a.n + slots - 1) / slots + kThreads - 1) / kThreads * kThreads;
+    if (chunk < 4 * kThreads) chunk = 4 * kThreads;
+    if (chunk > kBwdChunk) chunk = kBwdChunk;
+    SeqBwdArgs b = a;
+    b.chunk = (int)chunk;
+    const long long chunks = (a.n + chunk - 1) / chunk;
     long long g = (long long)sm_count() * 8;
     if (chunks < g) g = chunks;
     if (g < 1) g = 1;
-    if (bwd_minb_choice() == 3) RTT_NAME(k_trace_seq_bwd)<3><<<(int)g, kThreads, smem, st>>>(a);
-    else RTT_NAME(k_trace_seq_bwd)<2><<<(int)g, kThreads, smem, st>>>(a);
+    if (bwd_minb_choice() == 3) RTT_NAME(k_trace_seq_bwd)<3><<<(int)g, kThreads, smem, st>>>(b);
+    else RTT_NAME(k_trace_seq_bwd)<2><<<(int)g, kThreads, smem, st>>>(b);
     return cudaGetLastError();
 }
 cudaError_t RTT_NAME(launch_nonseq_fwd)(const NonseqFwdArgs& a, cudaStream_t st) {

@@ -70,6 +70,7 @@ struct SeqBwdArgs {
     TableDev tab;
     int n_sens;
     long long n;
+    int chunk;                  // rays per block iteration (set by the launcher, <= kBwdChunk)
 };
 
 struct NonseqFwdArgs {
