@@ -264,7 +264,8 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_fwd)(const __gr
         const int lam = (L > 0) ? wavelength_index(T, L, ray.wav) : 0;
         unsigned long long mask = 0ull, bit = 1ull;
         int op_next = T.rows[0].i[DI_OPCODE];
-        for (int r = 0; r < S; ++r, bit += bit) {
+        const int rows_walked = finite_ray(p, d) ? S : 0;               // NaN / inf rays hit nothing (rtt_tile.cuh)
+        for (int r = 0; r < rows_walked; ++r, bit += bit) {
             const int op = op_next;                                     // fetched one row ahead: the
             op_next = T.rows[(r + 1 < S) ? r + 1 : r].i[DI_OPCODE];     // LDS -> BRX latency is hidden
             switch (op) {                                               // warp-uniform
@@ -384,8 +385,9 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_tile(const __g
                 const RayIn ray = fetch_ray(a, skey, i, L > 0);
                 p[j] = ray.p; d[j] = ray.d; I[j] = ray.I;
                 lam[j] = (L > 0) ? wavelength_index(T, L, ray.wav) : 0;
-                act[j] = regular_dir(ray.d);
-                odd[j] = !act[j];
+                const bool fin = finite_ray(ray.p, ray.d);              // non-finite rays pass through untouched
+                act[j] = fin && regular_dir(ray.d);
+                odd[j] = fin && !act[j];
             }
         }
         unsigned long long bit = 1ull;
@@ -715,7 +717,7 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
         }
         if (!__any_sync(kFull, have)) break;
         if (!have) continue;
-        bool done = (nb >= NB) || !(I > 0.0f);                          // base.py:140,201
+        bool done = (nb >= NB) || !(I > 0.0f) || !finite_ray(p, d);     // base.py:140,201; NaN / inf rays hit nothing
         if (!done) {
             // ray_cast (base.py:164-176): min over all rows, NaN anywhere => no hit
             float best = rtt_inf();

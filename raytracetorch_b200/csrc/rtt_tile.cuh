@@ -213,6 +213,13 @@ RTT_HD bool edge_culled(const Xf& x, V3 p, V3 d) {
     return (p.x * p.x + p.y * p.y) < x.b[0] && (qx * qx + qy * qy) < x.b[0];
 }
 
+// A NaN / inf coordinate reaches every component of the reference's `[N,3] @ [3,3]` poses (NaN * 0 = NaN), so such
+// a ray hits nothing and leaves the trace untouched; the kernels skip identity rotations, hence the explicit test.
+RTT_HD bool finite_ray(V3 p, V3 d) {
+    const float s = ((p.x + p.y) + p.z) + ((d.x + d.y) + d.z);
+    return (s - s) == 0.0f;
+}
+
 // |d|^2 close enough to 1 (or exactly 0) for the per-row renormalisation to be the identity to 1e-6
 RTT_HD bool regular_dir(V3 d) {
     const float l2 = fma3(d.x, d.x, d.y, d.y, d.z, d.z);

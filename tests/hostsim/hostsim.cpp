@@ -161,6 +161,11 @@ int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_
         float I = ray.I;
         const int lam = T.L > 0 ? lam_index(T, ray.wav) : 0;
         uint64_t mask = 0;
+        if (!finite_ray(p, d)) {                                 // NaN / inf rays hit nothing, like the kernels
+            if (out_pos) { store3(out_pos, i, p); store3(out_dir, i, d); out_intensity[i] = I; }
+            if (hitmask) hitmask[i] = 0;
+            continue;
+        }
 #ifdef RTT_HOST_TILE
         if (regular_dir(d)) {
             for (int r = 0; r < T.S; ++r) {
@@ -264,7 +269,7 @@ int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* 
         int cnt[RTT_MAX_SENSORS] = {0, 0, 0, 0};
         int nb = 0;
         for (; nb < nbounces; ++nb) {
-            if (!(I > 0.0f)) break;
+            if (!(I > 0.0f) || !finite_ray(p, d)) break;
             float best = rtt_inf();
             int win = -1;
             bool poisoned = false;

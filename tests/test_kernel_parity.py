@@ -445,3 +445,62 @@ def test_known_answers_of_reference_tests(run_exact, rtt_ns):
     b = run_exact.surface_step_bwd(tf, ti, pos, dr, 0, g_npos=np.ones((1, 3), np.float32))
     tab.f.backward(torch.from_numpy(b["g_table"]))
     np.testing.assert_allclose(tr.trans.grad.numpy()[2], 1.0, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# FAST forward = frame-resident tile path (csrc/rtt_tile.cuh): edge cases of its own
+# ---------------------------------------------------------------------------------------------
+def test_fast_tile_path_edge_cases(run_fast):
+    """Empty / 1 / odd-sized bundles, rays that miss everything, dead and NaN rays, and UN-NORMALISED input
+    directions: the tile kernel must send those through the reference-order walk (normalise per shape row, hit =
+    p + t*d with the raw d) and agree with the oracle like every other ray."""
+    d = parity.load("c2_cylindrical_tilt")
+    tf, ti = d["table_f"], d["table_i"]
+    z3, z1 = np.zeros((0, 3), np.float32), np.zeros(0, np.float32)
+    assert run_fast.trace_seq(tf, ti, z3, z3, z1)["pos"].shape == (0, 3)
+    rng = np.random.default_rng(3)
+    n = 3 * 512 + 77                                   # several launch tiles + a ragged tail
+    pos, dr, inten = d["in_pos"][:n].copy(), d["in_dir"][:n].copy(), d["in_intensity"][:n].copy()
+    scale = np.ones(n, np.float32)
+    odd = rng.random(n) < 0.3
+    scale[odd] = rng.uniform(0.3, 3.0, odd.sum()).astype(np.float32)
+    dr = (dr * scale[:, None]).astype(np.float32)      # |d| != 1 on 30 % of the rays
+    pos[5] = [300.0, 300.0, -10.0]                     # misses both lenses
+    inten[7] = 0.0                                     # enters dead
+    pos[9, 0] = np.nan
+    h = run_fast.trace_seq(tf, ti, pos, dr, inten)
+    o = O.trace_sequential(torch.from_numpy(tf), ti.tolist(), torch.from_numpy(pos), torch.from_numpy(dr),
+                           torch.from_numpy(inten))
+    oi, op, od = o["intensity"].numpy(), o["pos"].numpy(), o["dir"].numpy()
+    ok = np.ones(n, bool)
+    ok[9] = False                                      # NaN ray: compared separately
+    np.testing.assert_array_equal(h["intensity"][ok], oi[ok])
+    live = ok & (oi > 0)
+    assert parity.vec_rel(h["pos"][live], op[live]).max() <= parity.TOL_POINT
+    assert parity.vec_rel(h["dir"][live], od[live]).max() <= parity.TOL_POINT
+    np.testing.assert_array_equal(parity.mask_bits(h["hitmask"], tf.shape[0])[live], o["hit"].numpy()[live])
+    assert parity.vec_rel(h["pos"][5:6], op[5:6]).max() <= parity.TOL_POINT     # far off axis: only the stop plane takes it
+    # NaN position: NaN fails every bound test, which the INVERTED stop turns into a hit — like the reference
+    np.testing.assert_array_equal(parity.mask_bits(h["hitmask"], tf.shape[0])[9], o["hit"].numpy()[9])
+    assert odd[live].sum() > 100                       # the irregular path was really exercised on live rays
+    for m in (1, 2, 31, 33, 255, 257, 513):
+        hh = run_fast.trace_seq(tf, ti, pos[:m], dr[:m], inten[:m])
+        sel = ok[:m]
+        np.testing.assert_array_equal(hh["intensity"][sel], h["intensity"][:m][sel])
+        assert np.abs(hh["pos"][:m][sel] - h["pos"][:m][sel]).max(initial=0.0) <= 1e-5
+
+
+def test_fast_culling_keeps_vignetted_rays_exact(run_fast):
+    """Wide bundles that really hit lens edges (clear and inked, spherical and cylindrical lenses): the lens-edge
+    culling of the FAST forward may only skip rows a ray cannot hit, so the hit masks equal the oracle's."""
+    for name in ("c1_singlet_wide", "c1_singlet_clear_edge", "c2_cylindrical", "c4_camera_lens_field"):
+        d = parity.load(name)
+        tf, ti = d["table_f"], d["table_i"]
+        h = run_fast.trace_seq(tf, ti, d["in_pos"], d["in_dir"], d["in_intensity"])
+        o = _oracle_seq(d)
+        edge_rows = [r for r in range(tf.shape[0]) if ti[r][3] in (2, 4)]       # SPHERIC_EDGE, CYL_EDGE
+        assert edge_rows, name
+        got = parity.mask_bits(h["hitmask"], tf.shape[0])
+        want = o["hit"].numpy()
+        np.testing.assert_array_equal(got, want, err_msg=name)
+        np.testing.assert_array_equal(h["intensity"], o["intensity"].numpy(), err_msg=name)
