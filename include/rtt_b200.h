@@ -49,7 +49,11 @@ enum { RTT_SURF_PLANE = 0, RTT_SURF_QUADRIC, RTT_SURF_QUADRIC_ZY, RTT_SURF_CYLIN
 enum { RTT_BOUND_NONE = 0, RTT_BOUND_DISK, RTT_BOUND_RECT, RTT_BOUND_ELLIPSE, RTT_BOUND_HALF, RTT_BOUND_HALF_DISK };
 enum { RTT_SHAPE_NONE = 0, RTT_SHAPE_SPHERIC_FACE, RTT_SHAPE_SPHERIC_EDGE, RTT_SHAPE_CYL_FACE,
        RTT_SHAPE_CYL_EDGE, RTT_SHAPE_POLY, RTT_SHAPE_OPEN };
-enum { RTT_PHYS_TRANSMIT = 0, RTT_PHYS_SNELL, RTT_PHYS_REFLECT, RTT_PHYS_BLOCK, RTT_PHYS_APERTURE };
+enum { RTT_PHYS_TRANSMIT = 0, RTT_PHYS_SNELL, RTT_PHYS_REFLECT, RTT_PHYS_BLOCK, RTT_PHYS_APERTURE,
+       RTT_PHYS_LINEAR };
+/* RTT_PHYS_LINEAR (phys/std.py:35-88, the ideal thin lens / mirror elements of elements/ideal.py): a plane row
+ * whose otherwise unused scalar slots carry the ray-transfer coefficients — f[RTT_F_C] = Cx, f[RTT_F_K] = Cy,
+ * f[RTT_F_RADIUS] = Dx, f[RTT_F_IOR_IN] = Dy — with the matching gradient flags (CK, RADIUS, IOR). */
 enum { RTT_FLAG_GRAD_POSE_E = 1, RTT_FLAG_GRAD_POSE_S = 2, RTT_FLAG_GRAD_CK = 4,
        RTT_FLAG_GRAD_RADIUS = 8, RTT_FLAG_GRAD_IOR = 16 };
 enum { RTT_MAX_ROWS = 64, RTT_MAX_SENSORS = 4, RTT_MAX_WAVELENGTHS = 8, RTT_MAX_BOUNCES = 255 };

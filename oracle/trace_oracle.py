@@ -267,6 +267,14 @@ def physics_row(row: Row, hit_local, d, n, ior=None):
     if row.phys == C.PHYS_APERTURE:               # phys/filter.py:24-33 (non-inverted bound)
         m = _surface_in_bounds(row, hit_local).to(d.dtype)
         return d * m[:, None], m
+    if row.phys == C.PHYS_LINEAR:                 # phys/std.py:72-88 (Linear.transform = the plane's own pose)
+        Cx, Cy, Dx, Dy = row.c, row.k, row.radius, row.ior_in
+        dl = d @ row.Rs
+        dl = dl / dl[:, 2][:, None]
+        nx = Cx * hit_local[:, 0] + Dx * dl[:, 0]
+        ny = Cy * hit_local[:, 1] + Dy * dl[:, 1]
+        new_local = F.normalize(torch.stack([nx, ny, torch.ones_like(nx)], dim=1), p=2, dim=1)
+        return new_local @ row.Rs.T, ones
     # Snell with TIR fallback: phys/std.py:123-145
     n_in, n_out = (row.ior_in, row.ior_out) if ior is None else (ior[0][:, None], ior[1][:, None])
     dot = torch.sum(d * n, dim=1, keepdim=True)

@@ -43,7 +43,8 @@ SURF_PLANE, SURF_QUADRIC, SURF_QUADRIC_ZY, SURF_CYLINDER, SURF_SPHERE = 0, 1, 2,
 BOUND_NONE, BOUND_DISK, BOUND_RECT, BOUND_ELLIPSE, BOUND_HALF, BOUND_HALF_DISK = 0, 1, 2, 3, 4, 5
 (SHAPE_NONE, SHAPE_SPHERIC_FACE, SHAPE_SPHERIC_EDGE, SHAPE_CYL_FACE, SHAPE_CYL_EDGE,
  SHAPE_POLY, SHAPE_OPEN) = 0, 1, 2, 3, 4, 5, 6
-PHYS_TRANSMIT, PHYS_SNELL, PHYS_REFLECT, PHYS_BLOCK, PHYS_APERTURE = 0, 1, 2, 3, 4
+PHYS_TRANSMIT, PHYS_SNELL, PHYS_REFLECT, PHYS_BLOCK, PHYS_APERTURE, PHYS_LINEAR = 0, 1, 2, 3, 4, 5
+# PHYS_LINEAR rows (phys/std.py:35-88) keep Cx, Cy, Dx, Dy in the F_C, F_K, F_RADIUS, F_IOR_IN slots
 
 # gradient-request flags (host knows them from requires_grad; no device sync needed)
 FLAG_GRAD_POSE_E = 1 << 0   # Re / Te

@@ -511,6 +511,15 @@ RTT_HD V3 physics(const RowDev& R, V3 hl, V3 d, V3 n, float mu_enter, float mu_e
             const V3 ne = entering ? n : -n;
             return v3(mu * d.x + qf * ne.x, mu * d.y + qf * ne.y, mu * d.z + qf * ne.z);
         }
+        case RTT_PHYS_LINEAR: {                                         // std.py:72-88, Linear.transform = plane pose
+            const V3 dl = mul_R(d, R.f + RTT_F_RS);                     // the reference multiplies even by an identity
+            const float u = div_(dl.x, dl.z), v = div_(dl.y, dl.z);
+            const float a = R.f[RTT_F_C] * hl.x + R.f[RTT_F_RADIUS] * u;
+            const float b = R.f[RTT_F_K] * hl.y + R.f[RTT_F_IOR_IN] * v;
+            float len;
+            const V3 nl = normalize12(v3(a, b, 1.0f), &len);
+            return mul_RT(nl, R.f + RTT_F_RS);
+        }
         default:                                                        // Transmit std.py:227-235
             return d;
     }
@@ -759,6 +768,28 @@ RTT_HD void interact_adjoint(const RowDev& R, V3 p, V3 d, float ni, float no, fl
                     }
                 }
             }
+            break;
+        }
+        case RTT_PHYS_LINEAR: {
+            // out = normalize(Cx hl.x + Dx u, Cy hl.y + Dy v, 1) @ Rs^T with (u, v) = (dl.x, dl.y) / dl.z, dl = d @ Rs
+            const float* Rs = R.f + RTT_F_RS;
+            const V3 dl = mul_R(d, Rs);
+            const float iz = rcp_(dl.z);
+            const float u = dl.x * iz, v = dl.y * iz;
+            const float Cx = R.f[RTT_F_C], Cy = R.f[RTT_F_K], Dx = R.f[RTT_F_RADIUS], Dy = R.f[RTT_F_IOR_IN];
+            const float a = Cx * hl.x + Dx * u, b = Cy * hl.y + Dy * v;
+            const float inv = rcp_(norm3(a, b, 1.0f));
+            const V3 nl2 = v3(a * inv, b * inv, inv);
+            const V3 g_nl2 = adj_mul_RT(nl2, g_dir, Rs, false, G.g + RTT_F_RS, w_pose_s);
+            const float pr = dot(nl2, g_nl2);
+            const float g_a = (g_nl2.x - nl2.x * pr) * inv, g_b = (g_nl2.y - nl2.y * pr) * inv;
+            if (want & RTT_FLAG_GRAD_CK) { G.g[RTT_F_C] += g_a * hl.x; G.g[RTT_F_K] += g_b * hl.y; }
+            if (want & RTT_FLAG_GRAD_RADIUS) G.g[RTT_F_RADIUS] += g_a * u;
+            if (want & RTT_FLAG_GRAD_IOR) G.g[RTT_F_IOR_IN] += g_b * v;
+            g_hl.x += g_a * Cx; g_hl.y += g_b * Cy;
+            const float g_u = g_a * Dx, g_v = g_b * Dy;
+            const V3 g_dl = v3(g_u * iz, g_v * iz, -(g_u * u + g_v * v) * iz);
+            g_d = g_d + adj_mul_R(d, g_dl, Rs, false, G.g + RTT_F_RS, w_pose_s);
             break;
         }
         default:

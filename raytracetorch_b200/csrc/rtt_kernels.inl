@@ -564,7 +564,10 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
       if (compact) {
         if (threadIdx.x == 0) *qcount = 0;
         __syncthreads();
-        for (int k = 0; k < chunk / kThreads; ++k) {
+        // pass 1: which of this thread's rays matter (independent loads, all in flight together)
+        unsigned needs = 0u;
+#pragma unroll
+        for (int k = 0; k < kBwdChunk / kThreads; ++k) {
             const int loc = k * kThreads + threadIdx.x;
             const long long i = base + loc;
             bool need = false;
@@ -577,13 +580,18 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
                         need = need || gr.x != 0.0f || gr.y != 0.0f || gr.z != 0.0f;
                     }
             }
+            needs |= (need ? 1u : 0u) << k;
+        }
+        // pass 2: append them to the block's queue (warp-aggregated)
+        for (int k = 0; k < chunk / kThreads; ++k) {
+            const bool need = (needs >> k) & 1u;
             const unsigned votes = __ballot_sync(kFull, need);
             if (votes) {
                 const int lane = threadIdx.x & 31, lead = __ffs((int)votes) - 1;
                 int pos = 0;
                 if (lane == lead) pos = atomicAdd(qcount, __popc(votes));
                 pos = __shfl_sync(kFull, pos, lead);
-                if (need) queue[pos + __popc(votes & ((1u << lane) - 1u))] = (unsigned short)loc;
+                if (need) queue[pos + __popc(votes & ((1u << lane) - 1u))] = (unsigned short)(k * kThreads + threadIdx.x);
             }
         }
         __syncthreads();

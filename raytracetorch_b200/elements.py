@@ -321,6 +321,86 @@ class EllipticAperture(_Aperture):
 
 
 # ---- sensor (elements/sensor.py) -----------------------------------------------------------
+class LinearElement(Element):
+    """A plane with ``Linear`` physics bound to the plane's own pose (elements/ideal.py:47-61)."""
+
+    def __init__(self, shape: G.Plane, linSurfFunc: P.Linear):
+        super().__init__()
+        self.shape = shape
+        linSurfFunc.transform = shape.transform
+        self.surface_functions.append(linSurfFunc)
+
+
+def _ideal_plane(diameter, transform):
+    return G.Plane(transform=transform) if diameter == float("inf") else G.Disk(radius=diameter / 2, transform=transform)
+
+
+class IdealThinLens(LinearElement):
+    """Thin lens of focal length ``focal``: P = -1/f on both axes (elements/ideal.py:64-87)."""
+
+    def __init__(self, focal: float, focal_grad: bool = False, diameter: float = float("inf"),
+                 transform: Optional[G.RayTransform] = None):
+        super().__init__(shape=_ideal_plane(diameter, transform), linSurfFunc=P.Linear())
+        self.P = nn.Parameter(torch.as_tensor(-1.0 / focal), requires_grad=focal_grad)
+        self.surface_functions[0].Cx = self.P
+        self.surface_functions[0].Cy = self.P
+
+    @property
+    def f(self):
+        return -1 / self.P
+
+
+class IdealCylThinLens(LinearElement):
+    """Thin lens with separate focal lengths in x and y (elements/ideal.py:90-119).  The reference assigns ``Cy``
+    to ``surface_functions[1]``, which does not exist (IndexError at construction); here both powers go to the
+    element's one surface function, which is what the class documents."""
+
+    def __init__(self, focal_x: float, focal_y: float, focal_x_grad: bool = False, focal_y_grad: bool = False,
+                 diameter: float = float("inf"), transform: Optional[G.RayTransform] = None):
+        super().__init__(shape=_ideal_plane(diameter, transform), linSurfFunc=P.Linear())
+        self.Px = nn.Parameter(torch.as_tensor(-1.0 / focal_x), requires_grad=focal_x_grad)
+        self.Py = nn.Parameter(torch.as_tensor(-1.0 / focal_y), requires_grad=focal_y_grad)
+        self.surface_functions[0].Cx = self.Px
+        self.surface_functions[0].Cy = self.Py
+
+    @property
+    def fx(self):
+        return -1 / self.Px
+
+    @property
+    def fy(self):
+        return -1 / self.Py
+
+
+class IdealMirror(LinearElement):
+    """Paraxial mirror of radii (Rx, Ry): Px = -2/Rx, Py = -2/Ry (elements/ideal.py:122-163).  Like the reference's
+    ``Linear`` physics it keeps rays travelling towards +z of the plane (new local direction z = +1)."""
+
+    def __init__(self, radius_x: float, radius_y: float, radius_x_grad: bool = False, radius_y_grad: bool = False,
+                 diameter: float = float("inf"), transform: Optional[G.RayTransform] = None):
+        super().__init__(shape=_ideal_plane(diameter, transform), linSurfFunc=P.Linear())
+        self.Px = nn.Parameter(torch.as_tensor(-2.0 / radius_x), requires_grad=radius_x_grad)
+        self.Py = nn.Parameter(torch.as_tensor(-2.0 / radius_y), requires_grad=radius_y_grad)
+        self.surface_functions[0].Cx = self.Px
+        self.surface_functions[0].Cy = self.Py
+
+    @property
+    def fx(self):
+        return -1 / self.Px
+
+    @property
+    def fy(self):
+        return -1 / self.Py
+
+    @property
+    def Rx(self):
+        return -2 / self.Px
+
+    @property
+    def Ry(self):
+        return -2 / self.Py
+
+
 class Sensor(Element):
     """Transmitting surface that records ``(hit_local, intensity_before, id)`` per call
     (elements/sensor.py:9-65).  The fused scene kernels fill the same three lists, and —

@@ -5,8 +5,10 @@ Like ``geom.py`` these are parameter holders: the arithmetic of each interaction
 ``:243-254`` Block, ``phys/filter.py:24-33`` ApertureFilter) lives in the CUDA kernels;
 ``PHYS`` is the code the scene compiler writes into the surface table.
 
+``Linear`` (``phys/std.py:35-88``, the ray-transfer physics of the ideal elements) is code ``PHYS_LINEAR``.
+
 Not provided: ``RefractFresnel`` (stochastic, RNG-dependent — no parity definition),
-``Fuzzy`` (arbitrary Python callable), ``Linear`` (ideal elements; listed "next").
+``Fuzzy`` (arbitrary Python callable).
 """
 from __future__ import annotations
 
@@ -29,6 +31,26 @@ class SurfaceFunction(nn.Module):
 
 class Transmit(SurfaceFunction):
     PHYS = C.PHYS_TRANSMIT
+
+
+class Linear(SurfaceFunction):
+    """Paraxial ray-transfer physics (phys/std.py:35-88): in the frame of ``transform`` (the plane's own pose —
+    ``LinearElement`` rebinds it, elements/ideal.py:54), with slopes (u, v) = (dx, dy)/dz,
+    new slopes = (Cx x + Dx u, Cy y + Dy v), new direction = normalize(u', v', 1) rotated back."""
+
+    PHYS = C.PHYS_LINEAR
+
+    def __init__(self, Cx: float = 0, Cy: float = 0, Dx: float = 1, Dy=1,
+                 Cx_grad=False, Cy_grad=False, Dx_grad=False, Dy_grad=False, transform=None):
+        super().__init__()
+        self.Cx = nn.Parameter(torch.as_tensor(float(Cx)), requires_grad=Cx_grad)
+        self.Cy = nn.Parameter(torch.as_tensor(float(Cy)), requires_grad=Cy_grad)
+        self.Dx = nn.Parameter(torch.as_tensor(float(Dx)), requires_grad=Dx_grad)
+        self.Dy = nn.Parameter(torch.as_tensor(float(Dy)), requires_grad=Dy_grad)
+        if transform is None:
+            from .geom import RayTransform
+            transform = RayTransform()
+        self.transform = transform
 
 
 class Reflect(SurfaceFunction):

@@ -33,7 +33,8 @@ SHAPE = {             # shape_in_bounds (ALONG added separately); POLY is per si
 NORMAL = {            # normal_local
     C.SURF_PLANE: 0, C.SURF_SPHERE: 3, C.SURF_CYLINDER: 2, C.SURF_QUADRIC: 18, C.SURF_QUADRIC_ZY: 15}
 PHYS = {              # physics
-    C.PHYS_TRANSMIT: 0, C.PHYS_SNELL: 27, C.PHYS_REFLECT: 12, C.PHYS_BLOCK: 0, C.PHYS_APERTURE: 6}
+    C.PHYS_TRANSMIT: 0, C.PHYS_SNELL: 27, C.PHYS_REFLECT: 12, C.PHYS_BLOCK: 0, C.PHYS_APERTURE: 6,
+    C.PHYS_LINEAR: 46}   # two [3]@[3,3], 2 div, 2 x (mul + mul + add), normalize
 ADJOINT_FACTOR = 3.5  # reverse sweep ~2.5x the forward interaction + 1x recompute (interact_adjoint)
 
 

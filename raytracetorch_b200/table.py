@@ -80,7 +80,9 @@ def _phys_kind(sf) -> int:
         return C.PHYS_REFLECT
     if "Block" in n:
         return C.PHYS_BLOCK
-    if "Fuzzy" in n or "RefractFresnel" in n or "Linear" in n:
+    if "Linear" in n:
+        return C.PHYS_LINEAR
+    if "Fuzzy" in n or "RefractFresnel" in n:
         raise UnsupportedSceneError(f"surface function {type(sf).__name__} is outside the fused path")
     if "Transmit" in n:
         return C.PHYS_TRANSMIT
@@ -186,6 +188,13 @@ def plan_elements(elements) -> tuple:
                     surf.radius if kind in (C.SURF_SPHERE, C.SURF_CYLINDER) else None,
                     getattr(sf, "ior_in", None) if phys == C.PHYS_SNELL else None,
                     getattr(sf, "ior_out", None) if phys == C.PHYS_SNELL else None]
+            if phys == C.PHYS_LINEAR:
+                # ray-transfer coefficients ride in the scalar slots a plane does not use (codes.py)
+                if kind != C.SURF_PLANE or is_shape:
+                    raise UnsupportedSceneError("Linear physics is defined on a bare plane (elements/ideal.py:47-54)")
+                if getattr(sf, "transform", None) is not surf.transform:
+                    raise UnsupportedSceneError("Linear.transform must be the plane's own transform (LinearElement)")
+                scal = [sf.Cx, sf.Cy, sf.Dx, sf.Dy, None]
             sb: List[Optional[torch.Tensor]] = [None] * 4
             if bound == C.BOUND_DISK:
                 sb[0] = surf.radius

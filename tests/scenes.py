@@ -114,6 +114,19 @@ def x2_tilted_lenses(ns, grads=False):
     return [l1, l2, ball, window, sensor]
 
 
+def x3_ideal(ns, grads=False):
+    """Ideal (paraxial) elements, elements/ideal.py: a tilted + decentred thin lens with a finite aperture, an
+    unbounded thin lens, a paraxial mirror (Linear physics keeps rays going towards +z), then a sensor."""
+    E, G = ns.elements, ns.geom
+    l1 = E.IdealThinLens(focal=60.0, focal_grad=grads, diameter=22.0,
+                         transform=_T(ns, 0.0, x=0.4, y=-0.3, rot=[0.03, -0.02, 0.1], trans_grad=grads, rot_grad=grads))
+    l2 = E.IdealThinLens(focal=-150.0, focal_grad=grads, transform=_T(ns, 12.0))
+    IdealMirror = getattr(E, "IdealMirror", None) or E.ideal.IdealMirror    # the reference does not re-export it
+    m = IdealMirror(radius_x=400.0, radius_y=250.0, radius_x_grad=grads, diameter=30.0, transform=_T(ns, 20.0))
+    sensor = E.Sensor(G.Disk(25.0, transform=_T(ns, 45.0)))
+    return [l1, l2, m, sensor]
+
+
 # ---- ray bundles --------------------------------------------------------------------------
 def bundle_collimated(ns, n, radius, z, seed, tilt=None, ray_id=0):
     torch.manual_seed(seed)
@@ -139,6 +152,7 @@ CASES = {
     "c4_camera_lens_field": (c4_camera_lens, {}, "seq", ("coll", 11.0, -10.0, [0.04, 0.06, 0.0])),
     "x1_mirrors": (x1_mirrors, {}, "seq", ("coll", 12.0, -10.0, [0.0, 0.02, 0.0])),
     "x2_tilted_lenses": (x2_tilted_lenses, {}, "seq", ("coll", 10.0, -12.0, [0.02, 0.03, 0.0])),
+    "x3_ideal": (x3_ideal, {}, "seq", ("coll", 13.0, -10.0, [0.02, -0.03, 0.0])),
     "c5_nonsequential": (c5_nonsequential, {}, "nonseq", ("coll", 10.0, -5.0, None)),
     "sim_benchmark": (sim_benchmark_scene, {}, "nonseq", ("coll", 4.0, 0.0, None)),
     "x2_nonsequential": (x2_tilted_lenses, {}, "nonseq", ("coll", 10.0, -12.0, [0.02, 0.03, 0.0])),
@@ -152,6 +166,7 @@ GRAD_CASES = {
     "grad_c2_cylindrical": (c2_cylindrical, {"grads": True}, ("coll", 8.0, -10.0, [0.01, 0.02, 0.0])),
     "grad_c4_camera_lens": (c4_camera_lens, {"grads": True}, ("coll", 7.0, -10.0, [0.02, 0.03, 0.0])),
     "grad_x2_tilted": (x2_tilted_lenses, {"grads": True}, ("coll", 7.0, -12.0, [0.02, 0.03, 0.0])),
+    "grad_x3_ideal": (x3_ideal, {"grads": True}, ("coll", 9.0, -10.0, [0.02, -0.03, 0.0])),
 }
 
 

@@ -304,7 +304,10 @@ def test_seq_adjoint_matches_reference_autograd(runner_of, rtt_ns, name, variant
             assert np.linalg.norm(g) == 0, k
         else:
             assert parity.grad_rel(g, ref) < parity.TOL_GRAD, (k, g, ref)
-            assert parity.grad_rel(g, d["f32_gp::" + k]) < parity.TOL_GRAD, k
+            # against the reference's own fp32 autograd: the bar is its distance from its fp64 run when that is
+            # larger than the tolerance (rot_vec gradients are sums with heavy cancellation)
+            ref32 = d["f32_gp::" + k]
+            assert parity.grad_rel(g, ref32) < max(parity.TOL_GRAD, 2.0 * parity.grad_rel(ref32, ref)), k
 
 
 def test_sensor_record_adjoint(rtt_ns, run_exact):
@@ -504,3 +507,39 @@ def test_fast_culling_keeps_vignetted_rays_exact(run_fast):
         want = o["hit"].numpy()
         np.testing.assert_array_equal(got, want, err_msg=name)
         np.testing.assert_array_equal(h["intensity"], o["intensity"].numpy(), err_msg=name)
+
+
+def test_ideal_thin_lens_known_answers(run_exact, rtt_ns):
+    """The reference's analytic checks for the ideal elements (tests/test_ideal.py:60-106 and :150-186): a thin lens
+    of f = 100 images a point at z = -2f onto z = +2f, stigmatically; and for an object at z = -300 the image
+    moves by (z_i/z_o)^2 = 0.25 per unit of axial object shift and by z_i/z_o = -0.5 laterally (finite differences
+    of the forward kernel; the adjoint of the same row is checked against the reference's autograd by grad_x3_ideal)."""
+    import raytracetorch_b200 as rtt
+    lens = rtt.elements.IdealThinLens(focal=100.0)
+    tab = rtt.compile_elements([lens])
+    tf, ti = tab.f.detach().numpy(), tab.i.numpy()
+    assert ti[0][4] == 5                                   # PHYS_LINEAR
+
+    def image_of(origin, n=200, na=0.3, seed=0):
+        rng = np.random.default_rng(seed)
+        th = rng.uniform(0, 2 * np.pi, n)
+        ph = np.arccos(1 - rng.uniform(0, 1 - np.cos(np.arcsin(na)), n))
+        dr = np.stack([np.cos(th) * np.sin(ph), np.sin(th) * np.sin(ph), np.cos(ph)], 1).astype(np.float32)
+        pos = np.tile(np.asarray(origin, np.float32), (n, 1))
+        s = run_exact.surface_step(tf, ti, pos, dr, 0)
+        p, d = s["pos"].astype(np.float64), s["dir"].astype(np.float64)
+        # least-squares point closest to all outgoing rays
+        A = np.eye(3)[None] - d[:, :, None] * d[:, None, :]
+        return np.linalg.solve(A.sum(0), (A @ p[:, :, None]).sum(0))[:, 0], p, d
+
+    img, p, d = image_of([0.0, 0.0, -200.0])
+    assert abs(img[2] - 200.0) < 1e-1 and np.hypot(img[0], img[1]) < 1e-3
+    keep = np.abs(d[:, 0]) > 1e-5
+    z_cross = p[keep, 2] - p[keep, 0] / d[keep, 0] * d[keep, 2]
+    assert z_cross.std() < 1e-2                            # sharp point (test_ideal.py:105 asks 1e-3 in fp32 torch)
+    i0, _, _ = image_of([0.0, 0.0, -300.0])
+    iz, _, _ = image_of([0.0, 0.0, -299.0])
+    ix, _, _ = image_of([1.0, 0.0, -300.0])
+    assert abs(i0[2] - 150.0) < 1e-1
+    assert abs((iz[2] - i0[2]) - 0.25) < 5e-3              # axial magnification (z_i / z_o)^2
+    assert abs((ix[0] - i0[0]) + 0.5) < 5e-3               # lateral magnification z_i / z_o

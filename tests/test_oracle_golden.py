@@ -116,4 +116,7 @@ def test_oracle_autograd_matches_reference_autograd(rtt_ns, name):
         if np.linalg.norm(ref) == 0:
             assert np.linalg.norm(g) == 0
         else:
-            assert parity.grad_rel(g, ref) < 5e-5, k
+            # 5e-5, or the reference's own fp32-vs-fp64 distance where its fp32 gradient is that noisy
+            # (summation-order noise of an ill-conditioned rot_vec gradient, x3_ideal)
+            noise = parity.grad_rel(ref, d["f64_gp::" + k].astype(np.float32))
+            assert parity.grad_rel(g, ref) < max(5e-5, 2.0 * noise), k
