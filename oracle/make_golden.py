@@ -174,6 +174,13 @@ def gen_camera_case(ns):
     return dict(pos=r.pos.numpy(), dir=r.dir.numpy(), intensity=r.intensity.numpy())
 
 
+def gen_render_case(ns):
+    """Renderer.render_3d (render/camera.py:191-257) of the reference, fp32, 96x64 pixels."""
+    scene, cam = scenes.render_setup(ns)
+    img = ns.render.Renderer(scene).render_3d(cam)
+    return dict(image=img.numpy())
+
+
 GOAL_SEED, GOAL_RAYS, GOAL_BOUNCES = 77, 2000, 6
 
 
@@ -258,6 +265,9 @@ def main(argv):
               f"sensor_hits={d.get('f32_sensor0_w', np.zeros(0)).shape[0]}")
     if not wanted or "extras" in wanted:
         np.savez_compressed(os.path.join(OUT, "extra_camera_rays.npz"), **gen_camera_case(ns))
+        r3 = gen_render_case(ns)
+        np.savez_compressed(os.path.join(OUT, "extra_render3d.npz"), **r3)
+        print("render_3d: non-background pixels", int((np.abs(r3["image"] - 1.0).sum(-1) > 0).sum()))
         g = gen_goal_case(ns)
         np.savez_compressed(os.path.join(OUT, "extra_goals.npz"), **g)
         print("extras:", {k: float(v) for k, v in g.items() if k.endswith("_loss")})

@@ -1,8 +1,9 @@
 """Pinhole camera ray source (mirror of ``render/camera.py:16-72``).
 
-Only ``Camera.generate_rays`` is on the hot path (it feeds the sequential trace of BASELINE
-config 4).  ``Renderer.render_3d`` (a single nearest-hit bounce plus Lambert shading) is listed as
-"next" in SURVEY section 8(f) and is not provided.
+``Camera.generate_rays`` feeds the sequential trace of BASELINE config 4.  ``Renderer.render_3d``
+(``render/camera.py:191-257``: a single nearest-hit bounce over the non-aperture elements plus Lambert shading)
+is built from the fused ops: one ``rtt_trace_nonseq_fwd`` launch finds the winning row of every pixel ray, one
+``rtt_surface_step_fwd`` launch per row that won somewhere yields the normals, the shading is elementwise torch.
 
 Extension: ``generate_rays(samples=k, seed=...)`` draws k jittered sub-pixel samples per pixel
 (sample 0 is the reference's pixel-centre ray), which is how config 4 reaches ~1e9 rays.
@@ -71,3 +72,71 @@ class Camera:
         dirs = xx.unsqueeze(1) * self.right + yy.unsqueeze(1) * self.up_cam + self.forward
         origins = self.origin.expand_as(dirs)
         return Rays.initialize(origins, dirs, device=self.device)
+
+
+def _is_aperture(el) -> bool:
+    return any("ApertureFilter" in type(f).__name__ or "Fuzzy" in type(f).__name__ for f in el.surface_functions)
+
+
+def _base_color(phys_func) -> torch.Tensor:
+    """Colour rules of render/camera.py:259-301 (class-name based, like the reference)."""
+    name = type(phys_func).__name__
+    if "Reflect" in name:
+        return torch.tensor([1.0, 0.6, 0.0])
+    if "Block" in name:
+        return torch.tensor([0.2, 0.2, 0.2])
+    if "Transmit" in name:
+        return torch.tensor([0.0, 0.8, 0.2])
+    if "RefractSnell" in name or "RefractFresnel" in name:
+        n1, n2 = float(getattr(phys_func, "ior_in", 1.5)), float(getattr(phys_func, "ior_out", 1.5))
+        n = max(n1, n2)
+        white, cyan = torch.tensor([0.9, 0.9, 0.9]), torch.tensor([0.0, 1.0, 1.0])
+        blue, navy, purp = torch.tensor([0.3, 0.6, 1.0]), torch.tensor([0.0, 0.0, 0.5]), torch.tensor([0.3, 0.0, 0.3])
+        if n <= 1.0:
+            return white
+        if n <= 1.3:
+            return torch.lerp(white, cyan, (n - 1.0) / 0.3)
+        if n <= 1.4:
+            return torch.lerp(cyan, blue, (n - 1.3) / 0.1)
+        if n <= 1.7:
+            return torch.lerp(blue, navy, (n - 1.4) / 0.3)
+        return torch.lerp(navy, purp, min((n - 1.7) / 0.3, 1.0))
+    return torch.tensor([1.0, 0.0, 1.0])
+
+
+class Renderer:
+    """Visual ray cast of a scene (render/camera.py:173-301)."""
+
+    def __init__(self, scene, background_color=(1.0, 1.0, 1.0), light_dir=(-0.5, 1.0, -1.0)):
+        self.scene = scene
+        dev = scene.map_to_element.device
+        self.bg_color = torch.tensor(background_color, dtype=torch.float32, device=dev)
+        self.light_dir = F.normalize(torch.as_tensor(light_dir, dtype=torch.float32, device=dev), dim=0)
+
+    def render_3d(self, camera) -> torch.Tensor:
+        """[H, W, 3] image on the CPU: nearest hit of every pixel ray over the non-aperture elements, base colour by
+        surface physics, 0.3 ambient + 0.7 |n . light| shading, background elsewhere."""
+        from . import ops
+        from .table import compile_elements
+        self.scene._build_index_maps()
+        rays = camera.generate_rays()
+        n = rays.batch_size[0]
+        dev = rays.pos.device
+        colors = self.bg_color.to(dev).expand(n, 3).clone()
+        renderable = [el for el in self.scene.elements if not _is_aperture(el)]
+        if not renderable:
+            return colors.reshape(camera.height, camera.width, 3).cpu()
+        with torch.no_grad():
+            table = compile_elements(renderable, dispersion=getattr(self.scene, "dispersion", None))
+            out = ops.trace_nonsequential(table, rays.pos, rays.dir, torch.ones_like(rays.intensity), 1,
+                                          want_record=False, sensor_cfg=[])
+            win = out["hit_seq"][:, 0].long()
+            light = self.light_dir.to(dev)
+            rows_of = [(el, j) for el in renderable for j in range(len(el.shape))]
+            for r in torch.unique(win[win != 255]).tolist():
+                sel = win == r
+                el, j = rows_of[r]
+                normal = ops.step_row(table, rays.pos[sel], rays.dir[sel], r, mode=ops.MODE_EXACT)[5]
+                shade = 0.3 + 0.7 * torch.sum(normal * light, dim=1).abs()
+                colors[sel] = _base_color(el.surface_functions[j]).to(dev) * shade.unsqueeze(1)
+        return torch.clamp(colors.reshape(camera.height, camera.width, 3), 0.0, 1.0).cpu()

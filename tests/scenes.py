@@ -127,6 +127,20 @@ def x3_ideal(ns, grads=False):
     return [l1, l2, m, sensor]
 
 
+RENDER_CAMERA = ((60.0, 45.0, -70.0), (0.0, 2.0, 35.0), (0.0, 1.0, 0.0), 24.0, 96, 64)
+
+
+def render_setup(ns, device="cpu"):
+    """Scene + camera of the render fixture (oracle/make_golden.py::gen_render_case, tests/test_goals.py): the C5
+    elements seen from off-axis."""
+    scene = ns.scene.Scene()
+    for e in c5_nonsequential(ns):
+        scene.add_element(e)
+    scene._build_index_maps()
+    cam = ns.render.Camera(*RENDER_CAMERA, device=device)
+    return scene, cam
+
+
 # ---- ray bundles --------------------------------------------------------------------------
 def bundle_collimated(ns, n, radius, z, seed, tilt=None, ray_id=0):
     torch.manual_seed(seed)
