@@ -123,7 +123,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", self.sel, f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -316,7 +316,10 @@ def run_gpu_arm(args):
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- warm-up -------------------------------------------------------------------------------
+    # ---- warm-up (the clock sampler starts here: nvidia-smi needs ~0.1 s before its first sample, the timed
+    # region of a 10-step run lasts ~50 ms; warm-up steps are the same load) ------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
     out = None
     for _ in range(max(args.warmup, 1)):
         out = fwd_step()
@@ -334,17 +337,14 @@ def run_gpu_arm(args):
     del out
 
     # ---- timed: K forward steps, device-resident inputs -------------------------------------------
-    sampler = ClockSampler(local)
     launches0 = lib.launch_count()
     barrier()
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         fwd_step()
     e1.record()
     barrier()
-    clocks = sampler.stop()
     launches = lib.launch_count() - launches0
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     value = world * n * tests_per_ray / (ms_step / 1e3)
@@ -368,6 +368,7 @@ def run_gpu_arm(args):
         kt.append(a.elapsed_time(b))
         del images
     k_ms = float(np.median(kt))
+    clocks = sampler.stop()          # sampled under load: warm-up + timed steps + the per-launch timing above
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -581,12 +582,12 @@ def run_c3(args):
             tdist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 1)):
         step()
     barrier()
-    sampler = ClockSampler(local)
     l0 = lib.launch_count()
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
