@@ -700,10 +700,14 @@ __device__ __forceinline__ void nonseq_probe(const RowDev* rows, int r, V3 p, V3
 __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const __grid_constant__ NonseqFwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemTable T = carve(smem_raw, a.tab.S, a.tab.L);
-    ImgCache cache = img_cache_carve(smem_raw + ((smem_table_bytes(a.tab.S, a.tab.L) + 15) / 16) * 16);
+    unsigned char* after = smem_raw + ((smem_table_bytes(a.tab.S, a.tab.L) + 15) / 16) * 16;
+    ImgCache cache = img_cache_carve(after);
+    NsCull* cull = reinterpret_cast<NsCull*>(after + ((img_cache_bytes() + 15) / 16) * 16);
     img_cache_init(cache);
     stage_table(a.tab, T);
     const int S = a.tab.S, L = a.tab.L, NB = a.nbounces;
+    for (int r = threadIdx.x; r < S; r += blockDim.x) cull[r] = box_cull_info(T.rows, S, r);
+    __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
     const SourceKey skey = fetch_key(a);
     // Lane refill: rays of a warp need different numbers of bounces (absorbed, escaped, still bouncing), so a lane
@@ -732,6 +736,10 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
             int win = -1;
             bool poisoned = false;
             for (int r = 0; r < S; ++r) {
+                if (cull[r].run > 0) {                                  // a box: skip its six faces when no lane can hit it
+                    const bool missed = sphere_missed(cull[r], p, d);
+                    if (__all_sync(__activemask(), missed)) { r += cull[r].run - 1; continue; }
+                }
                 // min over rows (base.py:169): a row can only become the winner with t < best, so the
                 // shape-level rule (the costly part for box faces and lens edges) is evaluated only then
                 switch (T.rows[r].i[DI_OPCODE]) {                       // warp-uniform
@@ -998,6 +1006,9 @@ inline int grid_for(long long n, int blocks_per_sm) {
 }
 
 inline size_t fwd_smem(int S, int L) { return ((smem_table_bytes(S, L) + 15) / 16) * 16 + img_cache_bytes(); }
+inline size_t nonseq_fwd_smem(int S, int L) {
+    return ((smem_table_bytes(S, L) + 15) / 16) * 16 + ((img_cache_bytes() + 15) / 16) * 16 + sizeof(NsCull) * (size_t)S;
+}
 
 inline size_t bwd_smem(int S, int L) {
     return ((smem_table_bytes(S, L) + 15) / 16) * 16 + sizeof(float) * ((size_t)S * RTT_ROW_G + (size_t)L * S * 2);
@@ -1077,8 +1088,8 @@ cudaError_t RTT_NAME(launch_seq_bwd)(const SeqBwdArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 cudaError_t RTT_NAME(launch_nonseq_fwd)(const NonseqFwdArgs& a, cudaStream_t st) {
-    if (cudaError_t e = allow_smem(RTT_NAME(k_trace_nonseq_fwd), fwd_smem(a.tab.S, a.tab.L))) return e;
-    RTT_NAME(k_trace_nonseq_fwd)<<<grid_for(a.n, 8), kThreads, fwd_smem(a.tab.S, a.tab.L), st>>>(a);
+    if (cudaError_t e = allow_smem(RTT_NAME(k_trace_nonseq_fwd), nonseq_fwd_smem(a.tab.S, a.tab.L))) return e;
+    RTT_NAME(k_trace_nonseq_fwd)<<<grid_for(a.n, 8), kThreads, nonseq_fwd_smem(a.tab.S, a.tab.L), st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t RTT_NAME(launch_nonseq_bwd)(const NonseqBwdArgs& a, cudaStream_t st) {

@@ -213,6 +213,75 @@ RTT_HD bool edge_culled(const Xf& x, V3 p, V3 d) {
     return (p.x * p.x + p.y * p.y) < x.b[0] && (qx * qx + qy * qy) < x.b[0];
 }
 
+// ---- box culling (non-sequential search) ----------------------------------------------------------
+// A face row of a convex polyhedron accepts a hit only if the hit point lies within 1e-4 of the inside of every
+// sibling half-space (geom/shape.py:122-132), i.e. inside the slightly inflated solid.  For a box (three
+// antiparallel, mutually orthogonal pairs of face planes) that solid fits in a sphere, so a ray whose line stays
+// outside the sphere — or which starts outside and points away — cannot hit any of the six rows.  The sphere is
+// derived from the face planes themselves and kept in the GLOBAL frame (the non-sequential state's frame).
+struct NsCull {
+    int32_t run;             // > 0 at the first row of a verified box: rows [r, r + run) can be skipped together
+    float cx, cy, cz, r2;
+    int32_t pad[3];
+};
+
+RTT_HD NsCull box_cull_info(const RowDev* rows, int S, int r) {
+    NsCull c;
+    c.run = 0; c.cx = c.cy = c.cz = c.r2 = 0.0f; c.pad[0] = c.pad[1] = c.pad[2] = 0;
+    const RowDev& R0 = rows[r];
+    if (R0.i[RTT_I_SHAPE] != RTT_SHAPE_POLY || R0.i[RTT_I_POLY_FIRST] != r || R0.i[RTT_I_POLY_COUNT] != 6 || r + 6 > S)
+        return c;
+    V3 n[6]; float off[6];
+    for (int f = 0; f < 6; ++f) {
+        const RowDev& R = rows[r + f];
+        if (R.i[RTT_I_SURF] != RTT_SURF_PLANE || R.i[RTT_I_SHAPE] != RTT_SHAPE_POLY || R.i[RTT_I_POLY_FIRST] != r) return c;
+        n[f] = v3(R.f[RTT_F_RS + 2], R.f[RTT_F_RS + 5], R.f[RTT_F_RS + 8]);     // plane normal (third column of Rs)
+        off[f] = dot(n[f], ld3(R.f + RTT_F_TS));                                 // signed offset of the plane
+    }
+    // pair the faces: partner = the antiparallel one
+    int axis_a[3], axis_b[3], na = 0;
+    bool used[6] = {false, false, false, false, false, false};
+    for (int f = 0; f < 6; ++f) {
+        if (used[f]) continue;
+        int partner = -1;
+        for (int g = f + 1; g < 6; ++g)
+            if (!used[g] && dot(n[f], n[g]) < -0.99999f) { partner = g; break; }
+        if (partner < 0 || na == 3) return c;
+        used[f] = used[partner] = true;
+        axis_a[na] = f; axis_b[na] = partner; ++na;
+    }
+    if (na != 3) return c;
+    for (int a = 0; a < 3; ++a) {
+        const float len = norm3(n[axis_a[a]].x, n[axis_a[a]].y, n[axis_a[a]].z);
+        if (fabsf(len - 1.0f) > 1e-5f) return c;
+        for (int b = a + 1; b < 3; ++b)
+            if (fabsf(dot(n[axis_a[a]], n[axis_a[b]])) > 1e-5f) return c;
+    }
+    // centre and half extents along the three axes (element frame)
+    V3 ce = v3(0.0f, 0.0f, 0.0f);
+    float h2 = 0.0f;
+    for (int a = 0; a < 3; ++a) {
+        const V3 na_ = n[axis_a[a]];
+        const float o1 = off[axis_a[a]], o2 = -off[axis_b[a]];                   // partner's offset along +n_a
+        const float mid = 0.5f * (o1 + o2), half = 0.5f * fabsf(o1 - o2);
+        ce = ce + mid * na_;
+        h2 += half * half;
+    }
+    const float rad = sqrt_(h2) * 1.01f + 2e-3f;                                 // inflated: 1e-4 slack + rounding
+    const V3 cg = mul_RT(ce, R0.f + RTT_F_RE) + ld3(R0.f + RTT_F_TE);            // element -> global
+    if (!(rad == rad) || !((cg.x + cg.y + cg.z) - (cg.x + cg.y + cg.z) == 0.0f)) return c;
+    c.run = 6; c.cx = cg.x; c.cy = cg.y; c.cz = cg.z; c.r2 = rad * rad;
+    return c;
+}
+
+// true iff the ray (p, d) — d of any length, possibly zero — cannot touch the sphere
+RTT_HD bool sphere_missed(const NsCull& c, V3 p, V3 d) {
+    const V3 m = v3(c.cx - p.x, c.cy - p.y, c.cz - p.z);
+    const float mm = dot(m, m), md = dot(m, d), dd = dot(d, d);
+    if (mm > c.r2 && md <= 0.0f) return true;                                    // outside and not approaching
+    return (mm * dd - md * md) > c.r2 * dd * 1.001f;                             // line passes outside
+}
+
 // A NaN / inf coordinate reaches every component of the reference's `[N,3] @ [3,3]` poses (NaN * 0 = NaN), so such
 // a ray hits nothing and leaves the trace untouched; the kernels skip identity rotations, hence the explicit test.
 RTT_HD bool finite_ray(V3 p, V3 d) {

@@ -261,6 +261,8 @@ int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* 
                          const rtt_table_t* table, const rtt_sensor_t* sensors, int32_t n_sensors,
                          int32_t nbounces, int64_t n, int32_t, void*) {
     const HostTable T = stage(table);
+    std::vector<NsCull> cull(T.S);
+    for (int r = 0; r < T.S; ++r) cull[r] = box_cull_info(T.rows.data(), T.S, r);
     for (int64_t i = 0; i < n; ++i) {
         const HostRay ray = fetch_ray(source, in_pos, in_dir, in_intensity, in_wavelength, T.L > 0, i);
         V3 p = ray.p, d = ray.d;
@@ -274,6 +276,8 @@ int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* 
             int win = -1;
             bool poisoned = false;
             for (int r = 0; r < T.S; ++r) {
+                const NsCull& bc = cull[r];                                   // box culling, as in the kernel
+                if (bc.run > 0 && sphere_missed(bc, p, d)) { r += bc.run - 1; continue; }
                 Frames F; Roots q; float t; int which;
                 const bool valid = intersect<true>(T.rows.data(), r, p, d, F, q, t, which);
                 if (T.rows[r].i[RTT_I_SHAPE] == RTT_SHAPE_NONE && is_nan(t)) poisoned = true;
