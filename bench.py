@@ -10,7 +10,8 @@ forward+adjoint figure rides along in "fwd_bwd".  Workload at one GPU = BASELINE
 
   value      device-resident inputs, CUDA-event timed, K steps, max over ranks
   e2e        same metric through the public API (SequentialScene.simulate) with HOST (pinned) ray
-             buffers: H2D of the bundle + kernel + D2H of the sensor image inside the timed region
+             buffers: H2D of the bundle (chunks pipelined with the trace) + kernels + D2H of the
+             sensor image inside the timed region
   roofline   dominant kernel (k_trace_seq_fwd): algorithmic bytes / mean launch time vs the measured
              HBM peak; "fp32" carries the FLOP view (this path has no dense contraction)
   cpu_baseline  the CPU oracle (port of the reference's algorithm) on a bounded sample, host cores

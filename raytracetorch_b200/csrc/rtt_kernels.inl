@@ -8,12 +8,16 @@
 //   * the surface table ([S,48] f32 + [S,16] i32, a few KB) is read from device memory and
 //     staged once per thread block in shared memory together with per-row derived constants;
 //     every row access afterwards is a shared-memory broadcast
-//   * one thread owns one ray at a time and keeps its state (p, d, I, hit mask) in
-//     registers through the whole surface stack; blocks are persistent and walk the bundle
-//     with a grid stride, so the staging cost is paid once per SM-resident block
+//   * one thread owns its rays and keeps their state (p, d, I, hit mask) in registers through
+//     the whole surface stack; blocks are persistent and walk the bundle with a grid stride, so
+//     the staging cost is paid once per block
+//   * FAST sequential forward = k_trace_seq_fwd_tile (rtt_tile.cuh): element-frame ray state,
+//     2 rays per thread, lens-edge culling; EXACT = k_trace_seq_fwd in the reference's order
 //   * sensor hits are binned in the same kernel (no hit lists unless requested)
 //   * the adjoint kernels recompute the forward per ray (checkpoints = incoming (p, d) of
-//     each interaction) and reduce parameter gradients warp -> block (shared) -> global
+//     each interaction), compact each chunk to the rays with non-zero upstream gradients, and
+//     reduce parameter gradients warp -> block (shared) -> global
+//   * the non-sequential forward refills a lane as soon as its ray has ended
 #include <cuda_runtime.h>
 #include <stdlib.h>
 #include "rtt_core.cuh"
@@ -291,12 +295,9 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_seq_fwd)(const __gr
 // frame change of a row are paid once per RPT rays, and the RPT independent dependency chains
 // give the scheduler instruction-level parallelism on top of the resident warps.
 
-struct TileSmem {
-    Xf* xf;              // [S + 1]: xf[r] = frame(r-1) -> frame(r); xf[S] = frame(S-1) -> global
-};
-
-// Shared-memory layout of the tile kernel: everything the hot loop touches sits at a compile-time offset
-// (image cache, frame changes, rows), so no pointer has to be kept in — or recomputed into — registers.
+// Shared-memory layout of the tile kernel: [image cache | Xf[RTT_MAX_ROWS + 1] | table]; xf[r] = frame(r-1) -> frame(r),
+// xf[S] = frame(S-1) -> global.  Everything the hot loop touches sits at a compile-time offset, so no pointer has to
+// be kept in — or recomputed into — registers.
 constexpr size_t kTileOffXf = ((size_t)kImgSlots * 8 + 16 + 15) / 16 * 16;
 constexpr size_t kTileOffTable = (kTileOffXf + sizeof(Xf) * (RTT_MAX_ROWS + 1) + 15) / 16 * 16;
 __host__ __device__ inline size_t tile_smem_bytes(int S, int L) { return kTileOffTable + smem_table_bytes(S, L); }
