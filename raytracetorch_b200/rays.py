@@ -101,6 +101,48 @@ class Rays:
         return cls(pos=o, dir=d, intensity=w, id=ids, wavelength=lam, batch_size=[n])
 
 
+class Paths:
+    """Proxy around a ``Rays`` that keeps the position of every ray after each bounce, for the GUI overlay
+    (rays/ray.py:100-225).  ``scene.rays = Paths(scene.rays)``; every ``scene.step()`` that moved a ray appends one
+    ``[N,3]`` CPU snapshot (``scene.simulate()`` then runs its bounces as single-bounce launches so the history has
+    one entry per bounce, like the reference's step loop); ``get_history()`` / ``unwrap()`` as in the reference."""
+
+    def __init__(self, rays: "Rays"):
+        self._rays = rays
+        self._history = [rays.pos.clone().detach().cpu()]
+
+    pos = property(lambda self: self._rays.pos, lambda self, v: setattr(self._rays, "pos", v))
+    dir = property(lambda self: self._rays.dir, lambda self, v: setattr(self._rays, "dir", v))
+    intensity = property(lambda self: self._rays.intensity, lambda self, v: setattr(self._rays, "intensity", v))
+    id = property(lambda self: self._rays.id)
+    wavelength = property(lambda self: self._rays.wavelength)
+    batch_size = property(lambda self: self._rays.batch_size)
+
+    def __getitem__(self, idx):
+        return self._rays[idx]
+
+    def __len__(self):
+        return len(self._rays)
+
+    def scatter_update(self, mask, new_pos, new_dir, intensity_mod):
+        self._rays.scatter_update(mask, new_pos, new_dir, intensity_mod)
+        self.snapshot()
+
+    def snapshot(self):
+        """Append the current positions (called by Scene.step after a bounce that hit something)."""
+        self._history.append(self._rays.pos.clone().detach().cpu())
+
+    def unwrap(self) -> "Rays":
+        return self._rays
+
+    def get_history(self) -> list:
+        return self._history
+
+    def to(self, device):
+        self._rays = self._rays.to(device)
+        return self
+
+
 # ---- device ray sources ------------------------------------------------------------------------
 _SRC_STATE = {}      # device -> (seed the state was built from, int64[2] tensor {Philox key, counter})
 

@@ -141,6 +141,14 @@ class Scene(nn.Module):
         if self.rays is None:
             return
         self._build_index_maps()
+        if hasattr(self.rays, "snapshot"):
+            # Paths proxy (visualisation): one launch per bounce so every bounce lands in the history,
+            # like the reference's loop (scene/base.py:139-142)
+            for _ in range(min(int(self.Nbounces), C.MAX_BOUNCES)):
+                if not bool((self.rays.intensity > 0).any()):
+                    break
+                self.step()
+            return
         rays = self.rays.unwrap() if hasattr(self.rays, "unwrap") else self.rays
         self._trace(rays, min(int(self.Nbounces), C.MAX_BOUNCES))
 
@@ -149,7 +157,9 @@ class Scene(nn.Module):
         if self.rays is None:
             return
         rays = self.rays.unwrap() if hasattr(self.rays, "unwrap") else self.rays
-        self._trace(rays, 1)
+        out = self._trace(rays, 1)
+        if hasattr(self.rays, "snapshot") and bool((out["n_hits"] > 0).any()):
+            self.rays.snapshot()              # the reference records in scatter_update, i.e. only when a ray was hit
 
     def ray_cast(self, rays):
         """(hit_mask, winner_element_ids, winner_surf_ids) or None (scene/base.py:144-178)."""

@@ -327,3 +327,42 @@ def test_host_resident_bundle_is_streamed_and_equals_the_device_trace(rtt_ns):
         outs.append([t.cpu() for t in (out.pos, out.intensity, locs, w, hid)])
     for x, y in zip(*outs):
         assert torch.equal(x, y)
+
+
+def test_paths_proxy_records_one_snapshot_per_bounce(rtt_ns):
+    """rays/ray.py:100-225 ``Paths``: the GUI's per-bounce position history.  Each ``Scene.step()`` that hit
+    something appends one CPU snapshot; ``simulate()`` on a Paths runs bounce by bounce and ends where the fused
+    multi-bounce launch ends (same per-bounce arithmetic)."""
+    import raytracetorch_b200 as rtt
+    from raytracetorch_b200.rays import Paths
+
+    def make():
+        scene = rtt.scene.Scene()
+        for e in scenes.c5_nonsequential(rtt_ns):
+            scene.add_element(e)
+        scene.Nbounces = 6
+        return scene.cuda()
+
+    rays0 = scenes.make_bundle(rtt_ns, ("coll", 10.0, -5.0, None), 20_000, 5).to("cuda")
+    # step loop with the proxy vs the same loop on plain rays
+    a, b = make(), make()
+    a.rays, b.rays = Paths(rays0.clone()), rays0.clone()
+    expect = [rays0.pos.cpu()]
+    for _ in range(4):
+        a.step()
+        b.step()
+        expect.append(b.rays.pos.cpu())
+    hist = a.rays.get_history()
+    assert len(hist) == 5 and all(h.device.type == "cpu" and h.shape == (20_000, 3) for h in hist)
+    for h, e in zip(hist, expect):
+        assert torch.equal(h, e)
+    assert not torch.equal(hist[1], hist[0]) and not torch.equal(hist[2], hist[1])
+    plain = a.rays.unwrap()
+    assert isinstance(plain, rtt.rays.Rays) and torch.equal(plain.pos.cpu(), hist[-1])
+    # simulate(): bounce-by-bounce with the proxy == one fused launch without it
+    c, d = make(), make()
+    c.rays, d.rays = Paths(rays0.clone()), rays0.clone()
+    c.simulate()
+    d.simulate()
+    assert torch.equal(c.rays.pos, d.rays.pos) and torch.equal(c.rays.intensity, d.rays.intensity)
+    assert 2 <= len(c.rays.get_history()) <= 7
