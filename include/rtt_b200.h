@@ -45,8 +45,10 @@ enum {
     RTT_I_PHYS = 4, RTT_I_SENSOR = 5, RTT_I_POLY_FIRST = 6, RTT_I_POLY_COUNT = 7,
     RTT_I_ELEM = 8, RTT_I_SIDX = 9, RTT_I_FLAGS = 10
 };
-enum { RTT_SURF_PLANE = 0, RTT_SURF_QUADRIC, RTT_SURF_QUADRIC_ZY, RTT_SURF_CYLINDER, RTT_SURF_SPHERE };
-enum { RTT_BOUND_NONE = 0, RTT_BOUND_DISK, RTT_BOUND_RECT, RTT_BOUND_ELLIPSE, RTT_BOUND_HALF, RTT_BOUND_HALF_DISK };
+enum { RTT_SURF_PLANE = 0, RTT_SURF_QUADRIC, RTT_SURF_QUADRIC_ZY, RTT_SURF_CYLINDER, RTT_SURF_SPHERE,
+       RTT_SURF_CONE };      /* double cone z^2 = slope^2 (x^2 + y^2), slope in f[RTT_F_C] (geom/primitives.py:398-494) */
+enum { RTT_BOUND_NONE = 0, RTT_BOUND_DISK, RTT_BOUND_RECT, RTT_BOUND_ELLIPSE, RTT_BOUND_HALF, RTT_BOUND_HALF_DISK,
+       RTT_BOUND_NAPPE };    /* one nappe of a cone: z * slope >= -1e-6 (geom/bounded.py:189-217) */
 enum { RTT_SHAPE_NONE = 0, RTT_SHAPE_SPHERIC_FACE, RTT_SHAPE_SPHERIC_EDGE, RTT_SHAPE_CYL_FACE,
        RTT_SHAPE_CYL_EDGE, RTT_SHAPE_POLY, RTT_SHAPE_OPEN };
 enum { RTT_PHYS_TRANSMIT = 0, RTT_PHYS_SNELL, RTT_PHYS_REFLECT, RTT_PHYS_BLOCK, RTT_PHYS_APERTURE,

@@ -110,6 +110,25 @@ def _roots(row: Row, o, d):
         sq = _sqrt(torch.abs(disc))
         inf = torch.full_like(A, INF)
         return [torch.where(ok, (-B - sq) / (2.0 * A), inf), torch.where(ok, (-B + sq) / (2.0 * A), inf)]
+    if row.surf == C.SURF_CONE:                   # geom/primitives.py:416-468 (slope in the c slot)
+        ox, oy, oz, dx, dy, dz = o[:, 0], o[:, 1], o[:, 2], d[:, 0], d[:, 1], d[:, 2]
+        k2 = row.c ** 2
+        A = dz ** 2 - k2 * (dx ** 2 + dy ** 2)
+        B = 2.0 * (oz * dz - k2 * (ox * dx + oy * dy))
+        Cq = oz ** 2 - k2 * (ox ** 2 + oy ** 2)
+        disc = B ** 2 - 4.0 * A * Cq
+        ok = disc >= 0
+        sq = _sqrt(torch.where(ok, disc, torch.zeros_like(disc)))
+        lin = torch.abs(A) < EPS_S
+        A_safe = torch.where(lin, torch.ones_like(A), A)
+        t1 = (-B - sq) / (2.0 * A_safe)
+        t2 = (-B + sq) / (2.0 * A_safe)
+        B_safe = torch.where(torch.abs(B) < EPS_S, torch.full_like(B, EPS_S), B)
+        t_lin = -Cq / B_safe
+        inf = torch.full_like(A, INF)
+        t1 = torch.where(lin, t_lin, torch.where(ok, t1, inf))
+        t2 = torch.where(lin, t_lin, torch.where(ok, t2, inf))
+        return [t1, t2]
     # conic sections: geom/primitives.py:266-320 and :356-376
     c, k = row.c, row.k
     oy, oz, dy, dz = o[:, 1], o[:, 2], d[:, 1], d[:, 2]
@@ -153,6 +172,8 @@ def _surface_in_bounds(row: Row, h):
         if row.bound == C.BOUND_HALF_DISK:        # geom/bounded.py:151-159
             keep = keep & (h[:, 0] ** 2 + h[:, 1] ** 2 <= sb[0] ** 2)
         return keep
+    if row.bound == C.BOUND_NAPPE:                # geom/bounded.py:208-217
+        return (h[:, 2] * row.c.detach()) >= -1e-6
     return torch.ones(h.shape[0], dtype=torch.bool, device=h.device)
 
 
@@ -228,6 +249,12 @@ def _normal_local(row: Row, h):
         return h / row.radius
     if row.surf == C.SURF_CYLINDER:               # geom/primitives.py:233-241
         return torch.stack([h[:, 0] / row.radius, h[:, 1] / row.radius, torch.zeros_like(h[:, 0])], dim=1)
+    if row.surf == C.SURF_CONE:                   # geom/primitives.py:470-494
+        k2 = row.c ** 2
+        raw = torch.stack([-k2 * h[:, 0], -k2 * h[:, 1], h[:, 2]], dim=1)
+        ln = torch.norm(raw, dim=1, keepdim=True)
+        up = torch.tensor([0.0, 0.0, 1.0], device=raw.device, dtype=raw.dtype)
+        return torch.where(ln > 1e-8, raw / (ln + 1e-8), up)
     c, k = row.c, row.k                           # geom/primitives.py:330-343, 378-395
     nx = 2 * c * h[:, 0] if row.surf == C.SURF_QUADRIC else torch.zeros_like(h[:, 0])
     ny = 2 * c * h[:, 1]

@@ -39,8 +39,9 @@ I_ELEM = 8          # element index   (scene/base.py map_to_element)
 I_SIDX = 9          # surface index   (scene/base.py map_to_surface)
 I_FLAGS = 10        # bit field, see FLAG_*
 
-SURF_PLANE, SURF_QUADRIC, SURF_QUADRIC_ZY, SURF_CYLINDER, SURF_SPHERE = 0, 1, 2, 3, 4
-BOUND_NONE, BOUND_DISK, BOUND_RECT, BOUND_ELLIPSE, BOUND_HALF, BOUND_HALF_DISK = 0, 1, 2, 3, 4, 5
+SURF_PLANE, SURF_QUADRIC, SURF_QUADRIC_ZY, SURF_CYLINDER, SURF_SPHERE, SURF_CONE = 0, 1, 2, 3, 4, 5
+BOUND_NONE, BOUND_DISK, BOUND_RECT, BOUND_ELLIPSE, BOUND_HALF, BOUND_HALF_DISK, BOUND_NAPPE = 0, 1, 2, 3, 4, 5, 6
+# SURF_CONE rows (geom/primitives.py:398-494) keep the slope in the F_C slot; BOUND_NAPPE = SingleCone
 (SHAPE_NONE, SHAPE_SPHERIC_FACE, SHAPE_SPHERIC_EDGE, SHAPE_CYL_FACE, SHAPE_CYL_EDGE,
  SHAPE_POLY, SHAPE_OPEN) = 0, 1, 2, 3, 4, 5, 6
 PHYS_TRANSMIT, PHYS_SNELL, PHYS_REFLECT, PHYS_BLOCK, PHYS_APERTURE, PHYS_LINEAR = 0, 1, 2, 3, 4, 5

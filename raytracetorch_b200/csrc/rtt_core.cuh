@@ -240,6 +240,8 @@ RTT_HD bool surface_in_bounds(const RowDev& R, V3 h) {
             return fabsf(h.z * R.f[RTT_F_C]) < 1.000001f;
         case RTT_BOUND_HALF_DISK:                                       // :151-159
             return (fabsf(h.z * R.f[RTT_F_C]) < 1.000001f) && ((h.x * h.x + h.y * h.y) <= R.f[D_SB0SQ]);
+        case RTT_BOUND_NAPPE:                                           // :208-217 (slope in the c slot)
+            return (h.z * R.f[RTT_F_C]) >= -1e-6f;
         default:
             return true;
     }
@@ -295,6 +297,24 @@ RTT_HD Roots solve_roots(const RowDev& R, V3 o, V3 d) {
                 q.t2 = ok ? div_(-B + sq, den) : inf;
             }
             q.A = A; q.B = B; q.C = Cq; q.sq = sq;
+            return q;
+        }
+        case RTT_SURF_CONE: {                                           // :416-468, z^2 = k^2 (x^2 + y^2)
+            const float k2 = R.f[RTT_F_C] * R.f[RTT_F_C];
+            const float A = d.z * d.z - k2 * (d.x * d.x + d.y * d.y);
+            const float B = 2.0f * (o.z * d.z - k2 * (o.x * d.x + o.y * d.y));
+            const float Cq = o.z * o.z - k2 * (o.x * o.x + o.y * o.y);
+            const float disc = B * B - (4.0f * A) * Cq;
+            const bool ok = disc >= 0.0f;
+            const bool lin = fabsf(A) < 1e-6f;
+            const float sq = sqrt_(ok ? disc : 0.0f);
+            const float den = 2.0f * (lin ? 1.0f : A);
+            const float r1 = div_(-B - sq, den), r2 = div_(-B + sq, den);
+            const float Bs = (fabsf(B) < 1e-6f) ? 1e-6f : B;
+            const float tl = lin ? div_(-Cq, Bs) : 0.0f;
+            q.t1 = lin ? tl : (ok ? r1 : inf);
+            q.t2 = lin ? tl : (ok ? r2 : inf);
+            q.A = A; q.B = B; q.C = Cq; q.sq = sq; q.lin = lin;
             return q;
         }
         default: {                                                      // conics :266-320, :356-376
@@ -455,6 +475,14 @@ RTT_HD V3 normal_local(const RowDev& R, V3 h, float* len_out) {
         case RTT_SURF_PLANE: return v3(0.0f, 0.0f, 1.0f);
         case RTT_SURF_SPHERE: return div3(h, R.f[RTT_F_RADIUS]);
         case RTT_SURF_CYLINDER: { const V3 q = div3(v3(h.x, h.y, 0.0f), R.f[RTT_F_RADIUS]); return v3(q.x, q.y, 0.0f); }
+        case RTT_SURF_CONE: {                                           // :470-494, +z at the vertex / flat limit
+            const float k2 = R.f[RTT_F_C] * R.f[RTT_F_C];
+            const V3 raw = v3(-k2 * h.x, -k2 * h.y, h.z);
+            const float len = norm3(raw.x, raw.y, raw.z);
+            *len_out = len;
+            if (!(len > 1e-8f)) return v3(0.0f, 0.0f, 1.0f);
+            return div3(raw, len + 1e-8f);
+        }
         default: {
             const float tc = 2.0f * R.f[RTT_F_C], tc1k = 2.0f * R.f[D_C1K];
             const float nx = (K::surf(R) == RTT_SURF_QUADRIC) ? tc * h.x : 0.0f;
@@ -819,6 +847,19 @@ RTT_HD void interact_adjoint(const RowDev& R, V3 p, V3 d, float ni, float no, fl
             G.g[RTT_F_RADIUS] -= div_(g_nl.x * hl.x + g_nl.y * hl.y, rr * rr);
             break;
         }
+        case RTT_SURF_CONE: {
+            if (nlen > 1e-8f) {                                         // nl = raw / (|raw| + 1e-8), raw = (-k2 x, -k2 y, z)
+                const float sl = R.f[RTT_F_C], k2 = sl * sl;
+                const V3 raw = v3(-k2 * hl.x, -k2 * hl.y, hl.z);
+                const float den = nlen + 1e-8f;
+                const float s = div_(dot(raw, g_nl), den * den * nlen);
+                const V3 gq = div3(g_nl, den);
+                const V3 g_raw = v3(gq.x - raw.x * s, gq.y - raw.y * s, gq.z - raw.z * s);
+                g_hl.x += -k2 * g_raw.x; g_hl.y += -k2 * g_raw.y; g_hl.z += g_raw.z;
+                G.g[RTT_F_C] += -(hl.x * g_raw.x + hl.y * g_raw.y) * (2.0f * sl);
+            }
+            break;
+        }
         default: {
             const float c = R.f[RTT_F_C], k = R.f[RTT_F_K];
             const float tc = 2.0f * c, tc1k = 2.0f * R.f[D_C1K];
@@ -875,6 +916,30 @@ RTT_HD void interact_adjoint(const RowDev& R, V3 p, V3 d, float ni, float no, fl
             g_o.x += gB * 2.0f * dd.x + gC * 2.0f * o.x;
             g_o.y += gB * 2.0f * dd.y + gC * 2.0f * o.y;
             G.g[RTT_F_RADIUS] += gC * (-2.0f * R.f[RTT_F_RADIUS]);
+            break;
+        }
+        case RTT_SURF_CONE: {
+            const float sl = R.f[RTT_F_C], k2 = sl * sl;
+            float gA, gB, gC;
+            if (q.lin) {
+                const float Bs = (fabsf(q.B) < 1e-6f) ? 1e-6f : q.B;
+                gA = 0.0f;
+                gC = div_(-g_t, Bs);
+                gB = (fabsf(q.B) < 1e-6f) ? 0.0f : div_(g_t * q.C, Bs * Bs);
+            } else {
+                gC = -g_t * rcp_(2.0f * q.A * t + q.B);
+                gB = gC * t; gA = gB * t;
+            }
+            // A = dz^2 - k2 (dx^2+dy^2), B = 2 (oz dz - k2 (ox dx + oy dy)), C = oz^2 - k2 (ox^2+oy^2)
+            g_dd.x += -2.0f * k2 * (gA * dd.x + gB * o.x);
+            g_dd.y += -2.0f * k2 * (gA * dd.y + gB * o.y);
+            g_dd.z += 2.0f * (gA * dd.z + gB * o.z);
+            g_o.x += -2.0f * k2 * (gB * dd.x + gC * o.x);
+            g_o.y += -2.0f * k2 * (gB * dd.y + gC * o.y);
+            g_o.z += 2.0f * (gB * dd.z + gC * o.z);
+            const float g_k2 = -(gA * (dd.x * dd.x + dd.y * dd.y) + 2.0f * gB * (o.x * dd.x + o.y * dd.y) +
+                                 gC * (o.x * o.x + o.y * o.y));
+            G.g[RTT_F_C] += g_k2 * (2.0f * sl);
             break;
         }
         default: {

@@ -179,6 +179,17 @@ class QuadricZY(Quadric):
     KIND = C.SURF_QUADRIC_ZY
 
 
+class Cone(Surface):
+    """Double cone z^2 = slope^2 (x^2 + y^2), vertex at the local origin; slope = dz/dr, 0 = plane
+    (geom/primitives.py:398-494)."""
+
+    KIND = C.SURF_CONE
+
+    def __init__(self, slope: float, slope_grad: bool = False, transform: Optional[RayTransform] = None):
+        super().__init__(transform)
+        self.slope = nn.Parameter(torch.as_tensor(float(slope)), requires_grad=slope_grad)
+
+
 class SurfaceBounded(Surface):
     """Per-root bound test with optional inversion (geom/bounded.py:9-48)."""
 
@@ -189,6 +200,17 @@ class SurfaceBounded(Surface):
     def inBounds(self, local_pos):
         from .ops import surface_in_bounds
         return surface_in_bounds(self, local_pos)
+
+
+class SingleCone(Cone, SurfaceBounded):
+    """One nappe of the cone: hits with z * slope >= -1e-6 (geom/bounded.py:189-217; like the reference, the
+    ``invert`` argument is accepted and ignored)."""
+
+    BOUND = C.BOUND_NAPPE
+
+    def __init__(self, slope: float, slope_grad: bool = False, invert: bool = False,
+                 transform: Optional[RayTransform] = None):
+        Cone.__init__(self, slope=slope, slope_grad=slope_grad, transform=transform)
 
 
 class Disk(Plane, SurfaceBounded):

@@ -24,14 +24,17 @@ POSE_ROT = 15         # one [3]@[3,3]: 3 x (mul + 2 fma)            mul_R / mul_
 NORMALIZE = 10        # norm3 (mul + 2 fma + sqrt) + max + 3 div      normalize12
 ALONG = 6             # p + t*d                                       along
 ROOTS = {             # solve_roots
-    C.SURF_PLANE: 2, C.SURF_SPHERE: 18, C.SURF_CYLINDER: 25, C.SURF_QUADRIC: 37, C.SURF_QUADRIC_ZY: 29}
+    C.SURF_PLANE: 2, C.SURF_SPHERE: 18, C.SURF_CYLINDER: 25, C.SURF_QUADRIC: 37, C.SURF_QUADRIC_ZY: 29,
+    C.SURF_CONE: 38}
 BOUND = {             # surface_in_bounds, per candidate root (ALONG added separately)
-    C.BOUND_NONE: 0, C.BOUND_DISK: 3, C.BOUND_RECT: 2, C.BOUND_ELLIPSE: 11, C.BOUND_HALF: 2, C.BOUND_HALF_DISK: 5}
+    C.BOUND_NONE: 0, C.BOUND_DISK: 3, C.BOUND_RECT: 2, C.BOUND_ELLIPSE: 11, C.BOUND_HALF: 2, C.BOUND_HALF_DISK: 5,
+    C.BOUND_NAPPE: 1}
 SHAPE = {             # shape_in_bounds (ALONG added separately); POLY is per sibling plane
     C.SHAPE_NONE: 0, C.SHAPE_SPHERIC_FACE: 3, C.SHAPE_SPHERIC_EDGE: 0, C.SHAPE_CYL_FACE: 4, C.SHAPE_CYL_EDGE: 28,
     C.SHAPE_POLY: 8, C.SHAPE_OPEN: 0}
 NORMAL = {            # normal_local
-    C.SURF_PLANE: 0, C.SURF_SPHERE: 3, C.SURF_CYLINDER: 2, C.SURF_QUADRIC: 18, C.SURF_QUADRIC_ZY: 15}
+    C.SURF_PLANE: 0, C.SURF_SPHERE: 3, C.SURF_CYLINDER: 2, C.SURF_QUADRIC: 18, C.SURF_QUADRIC_ZY: 15,
+    C.SURF_CONE: 14}
 PHYS = {              # physics
     C.PHYS_TRANSMIT: 0, C.PHYS_SNELL: 27, C.PHYS_REFLECT: 12, C.PHYS_BLOCK: 0, C.PHYS_APERTURE: 6,
     C.PHYS_LINEAR: 46}   # two [3]@[3,3], 2 div, 2 x (mul + mul + add), normalize

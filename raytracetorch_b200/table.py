@@ -38,8 +38,10 @@ def _names(obj) -> set:
 
 def _surface_kind(surf) -> int:
     n = _names(surf)
+    if "WedgeYZ" in n:
+        raise UnsupportedSceneError("WedgeYZ is unfinished in the reference (geom/primitives.py:497-502)")
     if "Cone" in n:
-        raise UnsupportedSceneError("Cone/SingleCone surfaces are not on the fused path yet")
+        return C.SURF_CONE
     if "Sphere" in n:
         return C.SURF_SPHERE
     if "Cylinder" in n:
@@ -59,6 +61,8 @@ def _bound_kind(surf) -> int:
         return C.BOUND_HALF_DISK
     if "HalfSphere" in n or "HalfCyl" in n:
         return C.BOUND_HALF
+    if "SingleCone" in n:
+        return C.BOUND_NAPPE
     if "Disk" in n:
         return C.BOUND_DISK
     if "Rectangle" in n:
@@ -184,7 +188,8 @@ def plan_elements(elements) -> tuple:
                 owner = getattr(getattr(sf, "_inBounds", None), "__self__", None)
                 if owner is not surf:
                     raise UnsupportedSceneError("ApertureFilter must filter on its own element's surface")
-            scal = [getattr(surf, "c", None), getattr(surf, "k", None),
+            scal = [getattr(surf, "slope", None) if kind == C.SURF_CONE else getattr(surf, "c", None),
+                    getattr(surf, "k", None),
                     surf.radius if kind in (C.SURF_SPHERE, C.SURF_CYLINDER) else None,
                     getattr(sf, "ior_in", None) if phys == C.PHYS_SNELL else None,
                     getattr(sf, "ior_out", None) if phys == C.PHYS_SNELL else None]

@@ -127,6 +127,24 @@ def x3_ideal(ns, grads=False):
     return [l1, l2, m, sensor]
 
 
+def x4_cones(ns, grads=False):
+    """Cone primitives (geom/primitives.py:398-494, geom/bounded.py:189-217) as bare surfaces: a reflecting axicon
+    (one nappe, tilted + decentred), a transmitting double cone, a refracting shallow nappe, then a sensor."""
+    G, P, E = ns.geom, ns.phys, ns.elements
+    Cone = getattr(G, "Cone", None) or G.primitives.Cone                 # the reference does not re-export them
+    SingleCone = getattr(G, "SingleCone", None) or G.bounded.SingleCone
+    # every vertex sits outside the beam: rays through a cone's tip are chaotic in the reference itself (its fp32
+    # and fp64 runs end 20 units apart), which would only measure noise
+    axicon = _adhoc(ns, SingleCone(slope=0.35, slope_grad=grads,
+                                   transform=_T(ns, 30.0, x=-13.0, rot=[0.02, -0.03, 0.0],
+                                                trans_grad=grads, rot_grad=grads)), P.Reflect)
+    dbl = _adhoc(ns, Cone(slope=2.5, slope_grad=grads, transform=_T(ns, 8.0, y=-14.0)), P.Transmit)
+    shallow = _adhoc(ns, SingleCone(slope=0.08, slope_grad=grads, transform=_T(ns, 3.0, x=14.0)),
+                     lambda: P.RefractSnell(1.0, 1.5))
+    sensor = E.Sensor(G.Disk(90.0, transform=_T(ns, -20.0)))
+    return [shallow, dbl, axicon, sensor]
+
+
 RENDER_CAMERA = ((60.0, 45.0, -70.0), (0.0, 2.0, 35.0), (0.0, 1.0, 0.0), 24.0, 96, 64)
 
 
@@ -166,6 +184,7 @@ CASES = {
     "c4_camera_lens_field": (c4_camera_lens, {}, "seq", ("coll", 11.0, -10.0, [0.04, 0.06, 0.0])),
     "x1_mirrors": (x1_mirrors, {}, "seq", ("coll", 12.0, -10.0, [0.0, 0.02, 0.0])),
     "x2_tilted_lenses": (x2_tilted_lenses, {}, "seq", ("coll", 10.0, -12.0, [0.02, 0.03, 0.0])),
+    "x4_cones": (x4_cones, {}, "seq", ("coll", 9.0, -10.0, [0.03, 0.02, 0.0])),
     "x3_ideal": (x3_ideal, {}, "seq", ("coll", 13.0, -10.0, [0.02, -0.03, 0.0])),
     "c5_nonsequential": (c5_nonsequential, {}, "nonseq", ("coll", 10.0, -5.0, None)),
     "sim_benchmark": (sim_benchmark_scene, {}, "nonseq", ("coll", 4.0, 0.0, None)),
@@ -180,6 +199,7 @@ GRAD_CASES = {
     "grad_c2_cylindrical": (c2_cylindrical, {"grads": True}, ("coll", 8.0, -10.0, [0.01, 0.02, 0.0])),
     "grad_c4_camera_lens": (c4_camera_lens, {"grads": True}, ("coll", 7.0, -10.0, [0.02, 0.03, 0.0])),
     "grad_x2_tilted": (x2_tilted_lenses, {"grads": True}, ("coll", 7.0, -12.0, [0.02, 0.03, 0.0])),
+    "grad_x4_cones": (x4_cones, {"grads": True}, ("coll", 7.0, -10.0, [0.03, 0.02, 0.0])),
     "grad_x3_ideal": (x3_ideal, {"grads": True}, ("coll", 9.0, -10.0, [0.02, -0.03, 0.0])),
 }
 
