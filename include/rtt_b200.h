@@ -52,7 +52,13 @@ enum { RTT_BOUND_NONE = 0, RTT_BOUND_DISK, RTT_BOUND_RECT, RTT_BOUND_ELLIPSE, RT
 enum { RTT_SHAPE_NONE = 0, RTT_SHAPE_SPHERIC_FACE, RTT_SHAPE_SPHERIC_EDGE, RTT_SHAPE_CYL_FACE,
        RTT_SHAPE_CYL_EDGE, RTT_SHAPE_POLY, RTT_SHAPE_OPEN };
 enum { RTT_PHYS_TRANSMIT = 0, RTT_PHYS_SNELL, RTT_PHYS_REFLECT, RTT_PHYS_BLOCK, RTT_PHYS_APERTURE,
-       RTT_PHYS_LINEAR };
+       RTT_PHYS_LINEAR, RTT_PHYS_FRESNEL };
+/* RTT_PHYS_FRESNEL (phys/std.py:146-224): reflect with probability R (unpolarised Fresnel reflectance, 1 under total
+ * internal reflection), else refract.  The reference draws torch.rand_like; here the uniform number of (ray i, row r,
+ * bounce b) is Philox4x32-10(counter = {i, r + 256 b, "Fr"}, key = the 64-bit seed stored in ints
+ * [RTT_I_RNG_LO, RTT_I_RNG_HI] of table row 0), so a trace and its adjoint take the same branch and the parity
+ * with the reference is statistical.  i counts from the start of the launch (plus the source's `first`). */
+enum { RTT_I_RNG_LO = 14, RTT_I_RNG_HI = 15 };
 /* RTT_PHYS_LINEAR (phys/std.py:35-88, the ideal thin lens / mirror elements of elements/ideal.py): a plane row
  * whose otherwise unused scalar slots carry the ray-transfer coefficients — f[RTT_F_C] = Cx, f[RTT_F_K] = Cy,
  * f[RTT_F_RADIUS] = Dx, f[RTT_F_IOR_IN] = Dy — with the matching gradient flags (CK, RADIUS, IOR). */

@@ -181,6 +181,18 @@ def gen_render_case(ns):
     return dict(image=img.numpy())
 
 
+def gen_fresnel_case(ns):
+    """Statistics of the reference's RefractFresnel singlet (phys/std.py:146-224): fraction of rays that leave the
+    sequential trace travelling backwards.  Its draws are torch.rand_like, so only the statistic is comparable."""
+    n = 200_000
+    torch.manual_seed(99)
+    els = scenes.c1_singlet(ns, physical=True, inked=False, fresnel=True)
+    rays = scenes.make_bundle(ns, ("coll", 11.0, -10.0, [0.3, 0.1, 0.0]), n, 8)
+    with torch.no_grad():
+        out = _run_seq(ns, els, rays)
+    return dict(n_rays=np.array(n), back_fraction=np.array(float((out.dir[:, 2] < 0).float().mean())))
+
+
 GOAL_SEED, GOAL_RAYS, GOAL_BOUNCES = 77, 2000, 6
 
 
@@ -265,6 +277,9 @@ def main(argv):
               f"sensor_hits={d.get('f32_sensor0_w', np.zeros(0)).shape[0]}")
     if not wanted or "extras" in wanted:
         np.savez_compressed(os.path.join(OUT, "extra_camera_rays.npz"), **gen_camera_case(ns))
+        fr = gen_fresnel_case(ns)
+        np.savez_compressed(os.path.join(OUT, "extra_fresnel.npz"), **fr)
+        print("fresnel: back fraction", float(fr["back_fraction"]))
         r3 = gen_render_case(ns)
         np.savez_compressed(os.path.join(OUT, "extra_render3d.npz"), **r3)
         print("render_3d: non-background pixels", int((np.abs(r3["image"] - 1.0).sum(-1) > 0).sum()))

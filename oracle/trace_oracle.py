@@ -281,9 +281,30 @@ def geometry_row(rows: List[Row], r_idx: int, p, d):
     return t, p + t[:, None] * d, n_glob, hit_local
 
 
-def physics_row(row: Row, hit_local, d, n, ior=None):
-    """(new_dir, intensity_mod).  ``ior`` optionally overrides (ior_in, ior_out) per ray."""
+def physics_row(row: Row, hit_local, d, n, ior=None, u=None):
+    """(new_dir, intensity_mod).  ``ior`` optionally overrides (ior_in, ior_out) per ray; ``u`` = the uniform
+    draws of a Fresnel row (the reference calls torch.rand_like, phys/std.py:190)."""
     ones = torch.ones_like(d[:, 0])
+    if row.phys == C.PHYS_FRESNEL:                # phys/std.py:175-224
+        ior_in, ior_out = (row.ior_in, row.ior_out) if ior is None else (ior[0][:, None], ior[1][:, None])
+        dot = torch.sum(d * n, dim=1, keepdim=True)
+        entering = dot < 0
+        n_eff = torch.where(entering, n, -n)
+        cos_i = torch.abs(dot)
+        n1 = torch.where(entering, ior_in, ior_out)
+        n2 = torch.where(entering, ior_out, ior_in)
+        mu = n2 / n1
+        sin2_t = (mu ** 2) * (1.0 - cos_i ** 2)
+        is_tir = sin2_t > 1.0
+        cos_t = _sqrt(torch.relu(1.0 - sin2_t))
+        n1_ci, n2_ct, n1_ct, n2_ci = n1 * cos_i, n2 * cos_t, n1 * cos_t, n2 * cos_i
+        rs = ((n1_ci - n2_ct) / (n1_ci + n2_ct + 1e-8)) ** 2
+        rp = ((n1_ct - n2_ci) / (n1_ct + n2_ci + 1e-8)) ** 2
+        R = torch.where(is_tir, torch.ones_like(rs), 0.5 * (rs + rp))
+        reflect = u.to(R.dtype)[:, None] < R
+        v_reflect = d - 2 * dot * n
+        v_refract = mu * d + (mu * cos_i - cos_t) * n_eff
+        return torch.where(reflect, v_reflect, v_refract), ones
     if row.phys == C.PHYS_TRANSMIT:               # phys/std.py:227-235
         return d, ones
     if row.phys == C.PHYS_BLOCK:                  # phys/std.py:243-254
@@ -321,15 +342,58 @@ def make_rows(table_f: torch.Tensor, table_i) -> List[Row]:
     return [Row(table_f[r], meta[r]) for r in range(table_f.shape[0])]
 
 
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 on numpy uint32 arrays (Salmon et al. 2011; the rounds of rtt_core.cuh::philox4x32_10)."""
+    import numpy as np
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) for c in (c0, c1, c2, c3))
+    k0, k1 = np.uint64(k0), np.uint64(k1)
+    M0, M1, W0, W1, LO = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85), \
+        np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        n0 = ((p1 >> np.uint64(32)) ^ c1 ^ k0) & LO
+        n1 = p1 & LO
+        n2 = ((p0 >> np.uint64(32)) ^ c3 ^ k1) & LO
+        n3 = p0 & LO
+        c0, c1, c2, c3 = n0, n1, n2, n3
+        k0, k1 = (k0 + W0) & LO, (k1 + W1) & LO
+    return c0, c1, c2, c3
+
+
+def fresnel_u(seed: int, ray_index, row: int, bounce: int):
+    """The uniform [0,1) draw of (ray, row, bounce) under ``seed`` (include/rtt_b200.h, RTT_PHYS_FRESNEL)."""
+    import numpy as np
+    i = np.asarray(ray_index, dtype=np.uint64)
+    out = philox4x32_10(i & np.uint64(0xFFFFFFFF), i >> np.uint64(32), np.full_like(i, row + 256 * bounce),
+                        np.full_like(i, 0x4672), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)[0]
+    return torch.from_numpy(((out >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)))
+
+
+def table_seed(table_i) -> int:
+    meta = table_i.tolist() if isinstance(table_i, torch.Tensor) else table_i
+    return ((meta[0][C.I_RNG_HI] & 0xFFFFFFFF) << 32) | (meta[0][C.I_RNG_LO] & 0xFFFFFFFF)
+
+
 def _lut_index(wavelength, lut_w):
     return torch.argmin(torch.abs(wavelength[:, None] - lut_w[None, :]), dim=1)
 
 
-def element_step(rows: List[Row], r_idx: int, p, d, ior=None):
+def element_step(rows: List[Row], r_idx: int, p, d, ior=None, u=None):
     """One Element.forward on rays assumed to hit (elements/parent.py:44-58)."""
     t, hit, n, hit_local = geometry_row(rows, r_idx, p, d)
-    new_d, mod = physics_row(rows[r_idx], hit_local, d, n, ior)
+    new_d, mod = physics_row(rows[r_idx], hit_local, d, n, ior, u)
     return hit, new_d, mod, hit_local, t, n
+
+
+def _row_extras(rows, r, mask, lam, lut, seed, bounce):
+    """(ior override, Fresnel draws) of the rays selected by ``mask`` at row r."""
+    ior = u = None
+    if lam is not None and rows[r].phys in (C.PHYS_SNELL, C.PHYS_FRESNEL):
+        sel = lut[lam[mask], r]                    # [M,2]
+        ior = (sel[:, 0], sel[:, 1])
+    if rows[r].phys == C.PHYS_FRESNEL:
+        u = fresnel_u(seed, torch.nonzero(mask)[:, 0].cpu().numpy(), r, bounce).to(mask.device)
+    return ior, u
 
 
 def trace_sequential(table_f, table_i, pos, dir_, intensity, *, wavelength=None, lut=None, lut_w=None):
@@ -337,6 +401,7 @@ def trace_sequential(table_f, table_i, pos, dir_, intensity, *, wavelength=None,
 
     Returns dict(pos, dir, intensity, hit [N,S] bool, sensor={slot: (mask, hit_local, w)})."""
     rows = make_rows(table_f, table_i)
+    seed = table_seed(table_i)
     N, S = pos.shape[0], len(rows)
     hit_log = torch.zeros(N, S, dtype=torch.bool, device=pos.device)
     sensor: Dict[int, tuple] = {}
@@ -348,11 +413,8 @@ def trace_sequential(table_f, table_i, pos, dir_, intensity, *, wavelength=None,
         hit_log[:, r] = mask
         if not bool(mask.any()):
             continue
-        ior = None
-        if lam is not None and rows[r].phys == C.PHYS_SNELL:
-            sel = lut[lam[mask], r]                # [M,2]
-            ior = (sel[:, 0], sel[:, 1])
-        hit, new_d, mod, hit_local, _, _ = element_step(rows, r, pos[mask], dir_[mask], ior)
+        ior, u = _row_extras(rows, r, mask, lam, lut, seed, 0)
+        hit, new_d, mod, hit_local, _, _ = element_step(rows, r, pos[mask], dir_[mask], ior, u)
         if rows[r].sensor >= 0:                    # elements/sensor.py:35-37: intensity BEFORE update
             sensor[rows[r].sensor] = (mask, hit_local, intensity[mask])
         idx = (mask,)
@@ -377,6 +439,7 @@ def trace_nonsequential(table_f, table_i, pos, dir_, intensity, nbounces: int, *
     Returns dict(pos, dir, intensity, seq [N,B] int (row per bounce, -1 none), nb [N],
     sensor_hits=[(ray_index, slot, hit_local, w)] in recording order)."""
     rows = make_rows(table_f, table_i)
+    seed = table_seed(table_i)
     N = pos.shape[0]
     seq = torch.full((N, nbounces), -1, dtype=torch.long, device=pos.device)
     sensor_hits = []
@@ -395,11 +458,8 @@ def trace_nonsequential(table_f, table_i, pos, dir_, intensity, nbounces: int, *
             m = active & (win == r)
             if not bool(m.any()):
                 continue
-            ior = None
-            if lam is not None and rows[r].phys == C.PHYS_SNELL:
-                sel = lut[lam[m], r]
-                ior = (sel[:, 0], sel[:, 1])
-            hit, nd, mod, hit_local, _, _ = element_step(rows, r, pos[m], dir_[m], ior)
+            ior, u = _row_extras(rows, r, m, lam, lut, seed, b)
+            hit, nd, mod, hit_local, _, _ = element_step(rows, r, pos[m], dir_[m], ior, u)
             if rows[r].sensor >= 0:
                 sensor_hits.append((torch.nonzero(m)[:, 0], rows[r].sensor, hit_local, intensity[m]))
             new_p = new_p.index_put((m,), hit)

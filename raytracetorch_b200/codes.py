@@ -44,7 +44,8 @@ BOUND_NONE, BOUND_DISK, BOUND_RECT, BOUND_ELLIPSE, BOUND_HALF, BOUND_HALF_DISK, 
 # SURF_CONE rows (geom/primitives.py:398-494) keep the slope in the F_C slot; BOUND_NAPPE = SingleCone
 (SHAPE_NONE, SHAPE_SPHERIC_FACE, SHAPE_SPHERIC_EDGE, SHAPE_CYL_FACE, SHAPE_CYL_EDGE,
  SHAPE_POLY, SHAPE_OPEN) = 0, 1, 2, 3, 4, 5, 6
-PHYS_TRANSMIT, PHYS_SNELL, PHYS_REFLECT, PHYS_BLOCK, PHYS_APERTURE, PHYS_LINEAR = 0, 1, 2, 3, 4, 5
+PHYS_TRANSMIT, PHYS_SNELL, PHYS_REFLECT, PHYS_BLOCK, PHYS_APERTURE, PHYS_LINEAR, PHYS_FRESNEL = 0, 1, 2, 3, 4, 5, 6
+I_RNG_LO, I_RNG_HI = 14, 15   # row 0 only: 64-bit seed of the Fresnel reflect / refract draws
 # PHYS_LINEAR rows (phys/std.py:35-88) keep Cx, Cy, Dx, Dy in the F_C, F_K, F_RADIUS, F_IOR_IN slots
 
 # gradient-request flags (host knows them from requires_grad; no device sync needed)

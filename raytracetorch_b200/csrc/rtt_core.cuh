@@ -506,12 +506,46 @@ RTT_HD V3 normal_global(const RowDev& R, V3 nl) {
     return n;
 }
 
+// ---- per-interaction extras of the stochastic Fresnel physics -------------------------------------
+struct PhysAux {
+    float ni, no;      // (ior_in, ior_out) this ray uses at the row (row values or the wavelength LUT's)
+    float u;           // uniform [0, 1) draw of (ray, row, bounce)
+};
+RTT_HD PhysAux no_aux() { PhysAux a; a.ni = a.no = 1.0f; a.u = 0.0f; return a; }
+
+// Fresnel decision (phys/std.py:177-199): true = reflect.  R = 1 under total internal reflection.
+RTT_HD bool fresnel_reflects(float cos_i, float mu, float n1, float n2, float u, float* cos_t_out) {
+    const float sin2_t = (mu * mu) * (1.0f - cos_i * cos_i);
+    const float ct = sqrt_(fmaxf(1.0f - sin2_t, 0.0f));
+    *cos_t_out = ct;
+    if (sin2_t > 1.0f) return u < 1.0f;
+    const float n1ci = n1 * cos_i, n2ct = n2 * ct, n1ct = n1 * ct, n2ci = n2 * cos_i;
+    const float rs = div_(n1ci - n2ct, (n1ci + n2ct) + 1e-8f), rp = div_(n1ct - n2ci, (n1ct + n2ci) + 1e-8f);
+    return u < 0.5f * (rs * rs + rp * rp);
+}
+
 // ---- physics (phys/std.py, phys/filter.py) --------------------------------------------------
 // mu_enter = ior_out/ior_in, mu_exit = ior_in/ior_out (per wavelength when a LUT is present).
 template <class K = KDyn>
-RTT_HD V3 physics(const RowDev& R, V3 hl, V3 d, V3 n, float mu_enter, float mu_exit, float* mod) {
+RTT_HD V3 physics(const RowDev& R, V3 hl, V3 d, V3 n, float mu_enter, float mu_exit, float* mod,
+                  PhysAux aux = no_aux()) {
     *mod = 1.0f;
     switch (K::phys(R)) {
+        case RTT_PHYS_FRESNEL: {                                        // std.py:146-224
+            const float dt = dot(d, n);
+            const bool entering = dt < 0.0f;
+            const float ci = fabsf(dt);
+            const float n1 = entering ? aux.ni : aux.no, n2 = entering ? aux.no : aux.ni;
+            const float mu = entering ? mu_enter : mu_exit;             // == n2 / n1
+            float ct;
+            if (fresnel_reflects(ci, mu, n1, n2, aux.u, &ct)) {
+                const float tw = 2.0f * dt;
+                return v3(d.x - tw * n.x, d.y - tw * n.y, d.z - tw * n.z);
+            }
+            const float qf = mu * ci - ct;
+            const V3 ne = entering ? n : -n;
+            return v3(mu * d.x + qf * ne.x, mu * d.y + qf * ne.y, mu * d.z + qf * ne.z);
+        }
         case RTT_PHYS_BLOCK:                                            // std.py:243-254
             *mod = 0.0f;
             return v3(0.0f, 0.0f, 0.0f);
@@ -560,14 +594,15 @@ struct Step {
 };
 
 template <class K = KDyn>
-RTT_HD Step interact(const RowDev& R, const Frames& F, float t, V3 p, V3 d, float mu_enter, float mu_exit) {
+RTT_HD Step interact(const RowDev& R, const Frames& F, float t, V3 p, V3 d, float mu_enter, float mu_exit,
+                     PhysAux aux = no_aux()) {
     Step s;
     s.t = t;
     s.hit_local = along(F.o, t, F.dd);                                  // primitives.py:81
     float nlen;
     s.normal = normal_global<K>(R, normal_local<K>(R, s.hit_local, &nlen));
     s.hit_global = along(p, t, d);                                      // shape.py:81 / primitives.py:80
-    s.new_dir = physics<K>(R, s.hit_local, d, s.normal, mu_enter, mu_exit, &s.mod);
+    s.new_dir = physics<K>(R, s.hit_local, d, s.normal, mu_enter, mu_exit, &s.mod, aux);
     return s;
 }
 
@@ -603,6 +638,25 @@ RTT_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
 }
 // [0, 1) with 24 random bits, like torch.rand in fp32
 RTT_HD float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// Uniform draw of the Fresnel decision of (ray i, row r, bounce b) under the table's seed (rtt_b200.h).
+RTT_HD unsigned long long table_seed(const RowDev* rows) {
+    return ((unsigned long long)(uint32_t)rows[0].i[RTT_I_RNG_HI] << 32) | (uint32_t)rows[0].i[RTT_I_RNG_LO];
+}
+RTT_HD float fresnel_u(unsigned long long seed, long long i, int r, int b) {
+    uint32_t out[4];
+    philox4x32_10((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), (uint32_t)(r + 256 * b), 0x4672u,
+                  (uint32_t)seed, (uint32_t)(seed >> 32), out);
+    return u01(out[0]);
+}
+// Extras of one interaction; the draw is only made for Fresnel rows.
+template <class K = KDyn>
+RTT_HD PhysAux make_aux(const RowDev* rows, const RowDev& R, float ni, float no, long long i, int r, int b) {
+    PhysAux a;
+    a.ni = ni; a.no = no; a.u = 0.0f;
+    if (K::phys(R) == RTT_PHYS_FRESNEL) a.u = fresnel_u(table_seed(rows), i, r, b);
+    return a;
+}
 // torch.linspace(start, end, steps)[i]: symmetric evaluation from both ends
 RTT_HD float linspace_at(float start, float end, int steps, int i) {
     if (steps <= 1) return start;
@@ -719,7 +773,7 @@ RTT_HD V3 adj_mul_RT(V3 a, V3 gy, const float* R, bool ident, float* gR, bool wa
 template <class K = KDyn>
 RTT_HD void interact_adjoint(const RowDev& R, V3 p, V3 d, float ni, float no, float mu_enter, float mu_exit,
                              V3 g_pos, V3 g_dir, V3 g_hl_up, V3 g_n_up, float g_t_up,
-                             V3& g_p, V3& g_d, float& mod_out, RowGrad& G, int want) {
+                             V3& g_p, V3& g_d, float& mod_out, RowGrad& G, int want, float fresnel_u = 0.0f) {
     // ---- recompute the forward pieces (same selections as the forward pass) ----
     const Frames F = to_frames<K>(R, p, d);
     const Roots q = solve_roots<K>(R, F.o, F.dd);
@@ -743,7 +797,17 @@ RTT_HD void interact_adjoint(const RowDev& R, V3 p, V3 d, float ni, float no, fl
     float mod = 1.0f;
 
     // ---- physics ----
-    switch (K::phys(R)) {
+    int phys_eff = K::phys(R);
+    if (K::phys(R) == RTT_PHYS_FRESNEL) {
+        // the branch is a non-differentiable choice (std.py:190-193): differentiate the one the forward pass took
+        const float dt = dot(d, n);
+        const bool entering = dt < 0.0f;
+        float ct;
+        const bool refl = fresnel_reflects(fabsf(dt), entering ? mu_enter : mu_exit, entering ? ni : no,
+                                           entering ? no : ni, fresnel_u, &ct);
+        phys_eff = refl ? RTT_PHYS_REFLECT : RTT_PHYS_SNELL;
+    }
+    switch (phys_eff) {
         case RTT_PHYS_BLOCK:
             mod = 0.0f;
             break;

@@ -101,6 +101,11 @@ __device__ __forceinline__ Ior row_ior(const SmemTable& T, int S, int L, int r, 
     return q;
 }
 
+template <class K>
+__device__ __forceinline__ bool uses_ior(const RowDev& R) {
+    return K::phys(R) == RTT_PHYS_SNELL || K::phys(R) == RTT_PHYS_FRESNEL;
+}
+
 __device__ __forceinline__ V3 load3(const float* a, long long i) { return v3(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
 __device__ __forceinline__ void store3(float* a, long long i, V3 v) { a[3 * i] = v.x; a[3 * i + 1] = v.y; a[3 * i + 2] = v.z; }
 
@@ -238,12 +243,10 @@ __device__ __forceinline__ void seq_row(const SmemTable& T, int S, int L, int r,
     Frames F; Roots q; float t; int which;
     if (!intersect<true, K>(T.rows, r, p, d, F, q, t, which)) return;
     const RowDev& R = T.rows[r];
-    float mu_enter = 0.0f, mu_exit = 0.0f;
-    if (K::phys(R) == RTT_PHYS_SNELL) {
-        const Ior io = row_ior(T, S, L, r, lam);
-        mu_enter = io.mu_enter; mu_exit = io.mu_exit;
-    }
-    const Step s = interact<K>(R, F, t, p, d, mu_enter, mu_exit);
+    Ior io;
+    io.ni = io.no = 1.0f; io.mu_enter = io.mu_exit = 0.0f;
+    if (uses_ior<K>(R)) io = row_ior(T, S, L, r, lam);
+    const Step s = interact<K>(R, F, t, p, d, io.mu_enter, io.mu_exit, make_aux<K>(T.rows, R, io.ni, io.no, i, r, 0));
     if (K::sensor(R)) {
         const int slot = R.i[RTT_I_SENSOR];
         if (slot >= 0 && slot < a.n_sens) sensor_deposit(a.sens[slot], cache, slot, i, s.hit_local, I, lam);
@@ -340,13 +343,12 @@ __device__ __forceinline__ void tile_row(const SmemTable& T, int S, int L, int r
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
         if (hit[j]) {
-            float mu_enter = 0.0f, mu_exit = 0.0f;
-            if (K::phys(R) == RTT_PHYS_SNELL) {
-                const Ior io = row_ior(T, S, L, r, lam[j]);
-                mu_enter = io.mu_enter; mu_exit = io.mu_exit;
-            }
+            Ior io;
+            io.ni = io.no = 1.0f; io.mu_enter = io.mu_exit = 0.0f;
+            if (uses_ior<K>(R)) io = row_ior(T, S, L, r, lam[j]);
             V3 np, nd, hl; float mod;
-            tile_interact<K>(R, p[j], d[j], t[j], mu_enter, mu_exit, np, nd, mod, hl);
+            tile_interact<K>(R, p[j], d[j], t[j], io.mu_enter, io.mu_exit, np, nd, mod, hl,
+                             make_aux<K>(T.rows, R, io.ni, io.no, i0 + (long long)j * kThreads, r, 0));
             if (K::sensor(R)) {
                 const int slot = R.i[RTT_I_SENSOR];
                 if (slot >= 0 && slot < a.n_sens)
@@ -497,18 +499,16 @@ struct Checkpoint { V3 p, d; };
 
 // Replay of one recorded interaction (no validity tests: the hit mask says it happened).
 template <class K>
-__device__ __forceinline__ void replay_row(const SmemTable& T, int S, int L, int r, int lam, V3& p, V3& d) {
+__device__ __forceinline__ void replay_row(const SmemTable& T, int S, int L, int r, int lam, long long i, V3& p, V3& d) {
     const RowDev& R = T.rows[r];
     const Frames F = to_frames<K>(R, p, d);
     const Roots q = solve_roots<K>(R, F.o, F.dd);
     int which;
     const float t = select_root<K>(R, q, F.o, F.dd, &which);
-    float mu_enter = 0.0f, mu_exit = 0.0f;
-    if (K::phys(R) == RTT_PHYS_SNELL) {
-        const Ior io = row_ior(T, S, L, r, lam);
-        mu_enter = io.mu_enter; mu_exit = io.mu_exit;
-    }
-    const Step s = interact<K>(R, F, t, p, d, mu_enter, mu_exit);
+    Ior io;
+    io.ni = io.no = 1.0f; io.mu_enter = io.mu_exit = 0.0f;
+    if (uses_ior<K>(R)) io = row_ior(T, S, L, r, lam);
+    const Step s = interact<K>(R, F, t, p, d, io.mu_enter, io.mu_exit, make_aux<K>(T.rows, R, io.ni, io.no, i, r, 0));
     p = s.hit_global; d = s.new_dir;
 }
 
@@ -520,7 +520,7 @@ __device__ __forceinline__ void reverse_row(const SmemTable& T, int S, int L, in
     const RowDev& R = T.rows[r];
     Ior io;
     io.ni = io.no = 1.0f; io.mu_enter = io.mu_exit = 1.0f;
-    if (K::phys(R) == RTT_PHYS_SNELL) io = row_ior(T, S, L, r, lam);
+    if (uses_ior<K>(R)) io = row_ior(T, S, L, r, lam);
     V3 g_hl = v3(0, 0, 0);
     float g_w = 0.0f;
     if (K::sensor(R)) {
@@ -532,7 +532,8 @@ __device__ __forceinline__ void reverse_row(const SmemTable& T, int S, int L, in
     }
     V3 ngp, ngd; float mod;
     interact_adjoint<K>(R, ck.p, ck.d, io.ni, io.no, io.mu_enter, io.mu_exit,
-                        gp, gd, g_hl, v3(0, 0, 0), 0.0f, ngp, ngd, mod, G, flags);
+                        gp, gd, g_hl, v3(0, 0, 0), 0.0f, ngp, ngd, mod, G, flags,
+                        make_aux<K>(T.rows, R, io.ni, io.no, i, r, 0).u);
     gp = ngp; gd = ngd;
     gI = gI * mod + g_w;
 }
@@ -622,10 +623,10 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
                 ck[nh].p = p; ck[nh].d = d; ++nh;
                 switch (op) {
 #define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR)                                            \
-                    case OP: replay_row<KStatic<SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR>>(T, S, L, r, lam, p, d); break;
+                    case OP: replay_row<KStatic<SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR>>(T, S, L, r, lam, i, p, d); break;
                     RTT_ROW_SPECS_ADJ(RTT_X)
 #undef RTT_X
-                    default: replay_row<KDyn>(T, S, L, r, lam, p, d); break;
+                    default: replay_row<KDyn>(T, S, L, r, lam, i, p, d); break;
                 }
             }
         }
@@ -758,7 +759,8 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
                 intersect<false>(T.rows, win, p, d, F, q, t, which);
                 const RowDev& R = T.rows[win];
                 const Ior io = row_ior(T, S, L, win, lam);
-                const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
+                const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit,
+                                        make_aux(T.rows, R, io.ni, io.no, i, win, nb));
                 const int slot = R.i[RTT_I_SENSOR];
                 if (slot >= 0 && slot < a.n_sens) {
                     const unsigned c = (cnts >> (8 * slot)) & 255u;
@@ -823,7 +825,7 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_bwd)(const _
             int which;
             const float t = select_root(R, q, F.o, F.dd, &which);
             const Ior io = row_ior(T, S, L, r, lam);
-            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
+            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit, make_aux(T.rows, R, io.ni, io.no, i, r, b));
             p = s.hit_global; d = s.new_dir;
         }
         V3 gp = a.g_opos ? load3(a.g_opos, i) : v3(0, 0, 0);
@@ -850,7 +852,8 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_bwd)(const _
             }
             V3 ngp, ngd; float mod;
             interact_adjoint(R, ck[nh].p, ck[nh].d, io.ni, io.no, io.mu_enter, io.mu_exit,
-                             gp, gd, g_hl, v3(0, 0, 0), 0.0f, ngp, ngd, mod, G, flags);
+                             gp, gd, g_hl, v3(0, 0, 0), 0.0f, ngp, ngd, mod, G, flags,
+                             make_aux(T.rows, R, io.ni, io.no, i, r, nh).u);       // nh == bounce index of this interaction
             gp = ngp; gd = ngd; gI = gI * mod + g_w;
             if (a.g_table && flags) {
                 if (L > 0 && (flags & RTT_FLAG_GRAD_IOR)) {
@@ -910,7 +913,7 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_surface_step_fwd)(const _
         int which;
         const float t = select_root(R, q, F.o, F.dd, &which);
         const Ior io = row_ior(T, S, L, r, lam);
-        const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
+        const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit, make_aux(T.rows, R, io.ni, io.no, i, r, 0));
         store3(a.npos, i, s.hit_global); store3(a.ndir, i, s.new_dir);
         a.mod[i] = s.mod;
         if (a.hit_local) store3(a.hit_local, i, s.hit_local);
@@ -948,7 +951,7 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_surface_step_bwd)(const _
             const float gtt = a.g_t ? a.g_t[i] : 0.0f;
             V3 gp, gd; float mod;
             interact_adjoint(R, p, d, io.ni, io.no, io.mu_enter, io.mu_exit, gnp, gnd, ghl, gnn, gtt,
-                             gp, gd, mod, G, flags);
+                             gp, gd, mod, G, flags, make_aux(T.rows, R, io.ni, io.no, i, r, 0).u);
             if (a.g_pos) store3(a.g_pos, i, gp);
             if (a.g_dir) store3(a.g_dir, i, gd);
         }

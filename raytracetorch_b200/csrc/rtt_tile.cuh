@@ -329,7 +329,7 @@ RTT_HD bool tile_test(const RowDev* rows, int r, V3 pe, V3 de, float& t) {
 // frame, intensity factor, and the surface-frame hit point (sensor records, aperture physics).
 template <class K = KDyn>
 RTT_HD void tile_interact(const RowDev& R, V3 pe, V3 de, float t, float mu_enter, float mu_exit,
-                          V3& np, V3& nd, float& mod, V3& hit_local) {
+                          V3& np, V3& nd, float& mod, V3& hit_local, PhysAux aux = no_aux()) {
     const bool rs_ident = (K::ident(R) & 2) != 0;
     const V3 o = rot_fwd(pe - ld3(R.f + RTT_F_TS), R.f + RTT_F_RS, rs_ident);
     const V3 dd = rot_fwd(de, R.f + RTT_F_RS, rs_ident);
@@ -340,7 +340,7 @@ RTT_HD void tile_interact(const RowDev& R, V3 pe, V3 de, float t, float mu_enter
                      ? v3(R.f[RTT_F_RS + 2], R.f[RTT_F_RS + 5], R.f[RTT_F_RS + 8])
                      : rot_bwd(nl, R.f + RTT_F_RS, rs_ident);            // element-frame normal
     np = along(pe, t, de);                                               // shape.py:81 in the element frame
-    nd = physics<K>(R, hit_local, de, n, mu_enter, mu_exit, &mod);
+    nd = physics<K>(R, hit_local, de, n, mu_enter, mu_exit, &mod, aux);
 }
 
 }  // namespace rtt

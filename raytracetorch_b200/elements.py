@@ -52,8 +52,8 @@ class ElementCustom(Element):
         self.surface_functions.extend(len(shape) * [surface_function])
 
 
-def _snell(ior_in: nn.Parameter, ior_out: nn.Parameter) -> P.RefractSnell:
-    sf = P.RefractSnell(0.0, 0.0)
+def _snell(ior_in: nn.Parameter, ior_out: nn.Parameter, fresnel: bool = False) -> P.RefractSnell:
+    sf = (P.RefractFresnel if fresnel else P.RefractSnell)(0.0, 0.0)     # elements/lens.py:35-38
     sf.ior_in, sf.ior_out = ior_in, ior_out      # shared Parameters, as in elements/lens.py:41-47
     return sf
 
@@ -69,14 +69,12 @@ class SingletLens(Element):
                  ior_glass_grad: bool = False, ior_media_grad: bool = False,
                  fresnel: bool = False, inked: bool = False, transform: Optional[G.RayTransform] = None):
         super().__init__()
-        if fresnel:
-            raise NotImplementedError("RefractFresnel is stochastic and outside the fused path")
         self.ior_glass = _scalar_param(ior_glass, ior_glass_grad)
         self.ior_media = _scalar_param(ior_media, ior_media_grad)
         self.shape = self._make_shape(c1, c2, d, t, c1_grad, c2_grad, t_grad, d_grad, transform)
-        self.surface_functions.append(_snell(self.ior_glass, self.ior_media))
-        self.surface_functions.append(_snell(self.ior_media, self.ior_glass))
-        self.surface_functions.append(P.Block() if inked else _snell(self.ior_glass, self.ior_media))
+        self.surface_functions.append(_snell(self.ior_glass, self.ior_media, fresnel))
+        self.surface_functions.append(_snell(self.ior_media, self.ior_glass, fresnel))
+        self.surface_functions.append(P.Block() if inked else _snell(self.ior_glass, self.ior_media, fresnel))
 
     def _make_shape(self, c1, c2, d, t, c1_grad, c2_grad, t_grad, d_grad, transform):
         return G.Singlet(C1=c1, C2=c2, D=d, T=t, C1_grad=c1_grad, C2_grad=c2_grad,
@@ -151,9 +149,9 @@ class _CementedLens(Element):
     """Shared construction of cemented stacks: faces refract media->g1->...->media,
     edges absorb (elements/lens.py:231-279, 325-387)."""
 
-    def _finish(self, iors, n_edges):
+    def _finish(self, iors, n_edges, fresnel=False):
         for a, b in zip(iors[:-1], iors[1:]):
-            self.surface_functions.append(_snell(a, b))
+            self.surface_functions.append(_snell(a, b, fresnel))
         for _ in range(n_edges):
             self.surface_functions.append(P.Block())
 
@@ -164,15 +162,13 @@ class DoubletLens(_CementedLens):
                  ior_glass1_grad=False, ior_glass2_grad=False, ior_media_grad=False,
                  fresnel=False, inked=True, transform: Optional[G.RayTransform] = None):
         super().__init__()
-        if fresnel:
-            raise NotImplementedError("RefractFresnel is stochastic and outside the fused path")
         self.ior_glass1 = _scalar_param(ior_glass1, ior_glass1_grad)
         self.ior_glass2 = _scalar_param(ior_glass2, ior_glass2_grad)
         self.ior_media = _scalar_param(ior_media, ior_media_grad)
         self.shape = G.Doublet(C1=c1, C2=c2, C3=c3, D=d, T1=t1, T2=t2,
                                C1_grad=c1_grad, C2_grad=c2_grad, C3_grad=c3_grad, D_grad=d_grad,
                                T1_grad=t1_grad, T2_grad=t2_grad, transform=transform)
-        self._finish([self.ior_media, self.ior_glass1, self.ior_glass2, self.ior_media], 2)
+        self._finish([self.ior_media, self.ior_glass1, self.ior_glass2, self.ior_media], 2, fresnel)
 
     @property
     def T1(self):
@@ -190,8 +186,6 @@ class TripletLens(_CementedLens):
                  ior_glass1_grad=False, ior_glass2_grad=False, ior_glass3_grad=False, ior_media_grad=False,
                  fresnel=False, inked=True, transform: Optional[G.RayTransform] = None):
         super().__init__()
-        if fresnel:
-            raise NotImplementedError("RefractFresnel is stochastic and outside the fused path")
         self.ior_glass1 = _scalar_param(ior_glass1, ior_glass1_grad)
         self.ior_glass2 = _scalar_param(ior_glass2, ior_glass2_grad)
         self.ior_glass3 = _scalar_param(ior_glass3, ior_glass3_grad)
@@ -200,7 +194,7 @@ class TripletLens(_CementedLens):
                                C1_grad=c1_grad, C2_grad=c2_grad, C3_grad=c3_grad, C4_grad=c4_grad,
                                D_grad=d_grad, T1_grad=t1_grad, T2_grad=t2_grad, T3_grad=t3_grad,
                                transform=transform)
-        self._finish([self.ior_media, self.ior_glass1, self.ior_glass2, self.ior_glass3, self.ior_media], 3)
+        self._finish([self.ior_media, self.ior_glass1, self.ior_glass2, self.ior_glass3, self.ior_media], 3, fresnel)
 
     @property
     def T1(self):

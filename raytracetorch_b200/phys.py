@@ -7,8 +7,11 @@ Like ``geom.py`` these are parameter holders: the arithmetic of each interaction
 
 ``Linear`` (``phys/std.py:35-88``, the ray-transfer physics of the ideal elements) is code ``PHYS_LINEAR``.
 
-Not provided: ``RefractFresnel`` (stochastic, RNG-dependent — no parity definition),
-``Fuzzy`` (arbitrary Python callable).
+``RefractFresnel`` (``phys/std.py:146-224``) is code ``PHYS_FRESNEL``: the reflect / refract choice is drawn from a
+counter-based generator keyed by a seed stored in the table (``table.with_seed``), so parity with the reference's
+``torch.rand_like`` is statistical.
+
+Not provided: ``Fuzzy`` (arbitrary Python callable).
 """
 from __future__ import annotations
 
@@ -71,6 +74,12 @@ class RefractSnell(SurfaceFunction):
         super().__init__()
         self.ior_in = nn.Parameter(torch.as_tensor(float(ior_in)), requires_grad=ior_in_grad)
         self.ior_out = nn.Parameter(torch.as_tensor(float(ior_out)), requires_grad=ior_out_grad)
+
+
+class RefractFresnel(RefractSnell):
+    """Stochastic Fresnel interface (phys/std.py:146-224): reflects with probability R, refracts otherwise."""
+
+    PHYS = C.PHYS_FRESNEL
 
 
 class ApertureFilter(Transmit):

@@ -101,7 +101,16 @@ class Scene(nn.Module):
 
     # ---- kernels --------------------------------------------------------------------------------
     def table(self):
-        return self._compiler.table(self.elements, dispersion=self.dispersion)
+        """The compiled surface table.  Scenes with RefractFresnel rows get a fresh seed per call (one per simulate /
+        step, like the reference's torch.rand_like per interaction): drawn from torch's generator, so
+        ``torch.manual_seed`` makes a run reproducible.  ``self.rng_seed = int`` pins it instead."""
+        tab = self._compiler.table(self.elements, dispersion=self.dispersion)
+        if tab.stochastic:
+            seed = getattr(self, "rng_seed", None)
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            tab = tab.with_seed(int(seed))
+        return tab
 
     def _deliver_to_sensors(self, table, records, hit_of_slot, rays_before: Rays, images):
         for slot, sensor in enumerate(table.sensors):

@@ -78,6 +78,8 @@ def _phys_kind(sf) -> int:
     n = _names(sf)
     if "ApertureFilter" in n:
         return C.PHYS_APERTURE
+    if "RefractFresnel" in n:
+        return C.PHYS_FRESNEL
     if "RefractSnell" in n:
         return C.PHYS_SNELL
     if "Reflect" in n:
@@ -86,7 +88,7 @@ def _phys_kind(sf) -> int:
         return C.PHYS_BLOCK
     if "Linear" in n:
         return C.PHYS_LINEAR
-    if "Fuzzy" in n or "RefractFresnel" in n:
+    if "Fuzzy" in n:
         raise UnsupportedSceneError(f"surface function {type(sf).__name__} is outside the fused path")
     if "Transmit" in n:
         return C.PHYS_TRANSMIT
@@ -137,6 +139,24 @@ class SurfaceTable:
     @property
     def n_rows(self) -> int:
         return self.f.shape[0]
+
+    @property
+    def stochastic(self) -> bool:
+        """True iff some row draws random numbers (RefractFresnel)."""
+        return any(m[C.I_PHYS] == C.PHYS_FRESNEL for m in self.i_host)
+
+    def with_seed(self, seed: int) -> "SurfaceTable":
+        """Copy of this table whose Fresnel draws are keyed by ``seed`` (ints [I_RNG_LO, I_RNG_HI] of row 0).  The seed
+        travels inside ``table.i`` through the forward AND the adjoint op, so both take the same branches."""
+        import dataclasses
+        seed &= (1 << 64) - 1
+        lo, hi = seed & 0xFFFFFFFF, seed >> 32
+        to_i32 = lambda v: v - (1 << 32) if v >= (1 << 31) else v
+        meta = [list(m) for m in self.i_host]
+        meta[0][C.I_RNG_LO], meta[0][C.I_RNG_HI] = to_i32(lo), to_i32(hi)
+        i = self.i.clone()
+        i[0, C.I_RNG_LO], i[0, C.I_RNG_HI] = to_i32(lo), to_i32(hi)
+        return dataclasses.replace(self, i=i, i_host=meta)
 
 
 class Dispersion:
@@ -191,8 +211,8 @@ def plan_elements(elements) -> tuple:
             scal = [getattr(surf, "slope", None) if kind == C.SURF_CONE else getattr(surf, "c", None),
                     getattr(surf, "k", None),
                     surf.radius if kind in (C.SURF_SPHERE, C.SURF_CYLINDER) else None,
-                    getattr(sf, "ior_in", None) if phys == C.PHYS_SNELL else None,
-                    getattr(sf, "ior_out", None) if phys == C.PHYS_SNELL else None]
+                    getattr(sf, "ior_in", None) if phys in (C.PHYS_SNELL, C.PHYS_FRESNEL) else None,
+                    getattr(sf, "ior_out", None) if phys in (C.PHYS_SNELL, C.PHYS_FRESNEL) else None]
             if phys == C.PHYS_LINEAR:
                 # ray-transfer coefficients ride in the scalar slots a plane does not use (codes.py)
                 if kind != C.SURF_PLANE or is_shape:

@@ -100,7 +100,7 @@ struct Ck { V3 p, d; };
 
 // shared reverse step used by both adjoint drivers
 void reverse_row(const HostTable& T, int r, int lam, const Ck& ck, V3& gp, V3& gd, float& gI,
-                 V3 g_hl, float g_w, float* g_table, float* g_lut) {
+                 V3 g_hl, float g_w, float* g_table, float* g_lut, int64_t i, int b) {
     const RowDev& R = T.rows[r];
     const int flags = R.i[RTT_I_FLAGS];
     const Ior io = row_ior(T, r, lam);
@@ -108,7 +108,7 @@ void reverse_row(const HostTable& T, int r, int lam, const Ck& ck, V3& gp, V3& g
     zero(G);
     V3 ngp, ngd; float mod;
     interact_adjoint(R, ck.p, ck.d, io.ni, io.no, io.mu_enter, io.mu_exit, gp, gd, g_hl, v3(0, 0, 0), 0.0f,
-                     ngp, ngd, mod, G, flags);
+                     ngp, ngd, mod, G, flags, make_aux(T.rows.data(), R, io.ni, io.no, i, r, b).u);
     gp = ngp; gd = ngd; gI = gI * mod + g_w;
     if (g_table && flags) {
         int fl = flags;
@@ -176,7 +176,8 @@ int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_
                 const RowDev& R = T.rows[r];
                 const Ior io = row_ior(T, r, lam);
                 V3 np, nd, hl; float mod;
-                tile_interact(R, p, d, t, io.mu_enter, io.mu_exit, np, nd, mod, hl);
+                tile_interact(R, p, d, t, io.mu_enter, io.mu_exit, np, nd, mod, hl,
+                              make_aux(T.rows.data(), R, io.ni, io.no, i, r, 0));
                 const int slot = R.i[RTT_I_SENSOR];
                 if (slot >= 0 && slot < n_sensors) deposit(sensors[slot], i, hl, I, lam);
                 p = np; d = nd; I = I * mod;
@@ -193,7 +194,7 @@ int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_
             if (!intersect<true>(T.rows.data(), r, p, d, F, q, t, which)) continue;
             const RowDev& R = T.rows[r];
             const Ior io = row_ior(T, r, lam);
-            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
+            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit, make_aux(T.rows.data(), R, io.ni, io.no, i, r, 0));
             const int slot = R.i[RTT_I_SENSOR];
             if (slot >= 0 && slot < n_sensors) deposit(sensors[slot], i, s.hit_local, I, lam);
             p = s.hit_global; d = s.new_dir; I = I * s.mod;
@@ -230,7 +231,7 @@ int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float*,
             int which;
             const float t = select_root(R, q, F.o, F.dd, &which);
             const Ior io = row_ior(T, r, lam);
-            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
+            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit, make_aux(T.rows.data(), R, io.ni, io.no, i, r, 0));
             p = s.hit_global; d = s.new_dir;
         }
         V3 gp = g_out_pos ? load3(g_out_pos, i) : v3(0, 0, 0);
@@ -245,7 +246,7 @@ int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float*,
                 const float* gr = g_record[slot] + 4 * i;
                 g_hl = v3(gr[0], gr[1], gr[2]); g_w = gr[3];
             }
-            reverse_row(T, r, lam, ck[nh], gp, gd, gI, g_hl, g_w, g_table, g_lut);
+            reverse_row(T, r, lam, ck[nh], gp, gd, gI, g_hl, g_w, g_table, g_lut, i, 0);
         }
         if (g_in_pos) store3(g_in_pos, i, gp);
         if (g_in_dir) store3(g_in_dir, i, gd);
@@ -288,7 +289,7 @@ int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* 
             intersect<false>(T.rows.data(), win, p, d, F, q, t, which);
             const RowDev& R = T.rows[win];
             const Ior io = row_ior(T, win, lam);
-            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
+            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit, make_aux(T.rows.data(), R, io.ni, io.no, i, win, nb));
             const int slot = R.i[RTT_I_SENSOR];
             if (slot >= 0 && slot < n_sensors) {
                 deposit(sensors[slot], i, s.hit_local, I, lam, cnt[slot], n);
@@ -333,7 +334,7 @@ int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float*,
             int which;
             const float t = select_root(R, q, F.o, F.dd, &which);
             const Ior io = row_ior(T, r, lam);
-            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
+            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit, make_aux(T.rows.data(), R, io.ni, io.no, i, r, b));
             p = s.hit_global; d = s.new_dir;
         }
         V3 gp = g_out_pos ? load3(g_out_pos, i) : v3(0, 0, 0);
@@ -351,7 +352,7 @@ int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float*,
                     g_hl = v3(gr[0], gr[1], gr[2]); g_w = gr[3];
                 }
             }
-            reverse_row(T, rows_hit[nh], lam, ck[nh], gp, gd, gI, g_hl, g_w, g_table, g_lut);
+            reverse_row(T, rows_hit[nh], lam, ck[nh], gp, gd, gI, g_hl, g_w, g_table, g_lut, i, nh);
         }
         if (g_in_pos) store3(g_in_pos, i, gp);
         if (g_in_dir) store3(g_in_dir, i, gd);
@@ -391,7 +392,7 @@ int rtt_surface_step_fwd(const float* in_pos, const float* in_dir, const float* 
         int which;
         const float t = select_root(R, q, F.o, F.dd, &which);
         const Ior io = row_ior(T, row, lam);
-        const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit);
+        const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit, make_aux(T.rows.data(), R, io.ni, io.no, i, row, 0));
         store3(new_pos, i, s.hit_global); store3(new_dir, i, s.new_dir);
         mod[i] = s.mod;
         if (hit_local) store3(hit_local, i, s.hit_local);
@@ -421,7 +422,7 @@ int rtt_surface_step_bwd(const float* in_pos, const float* in_dir, const float* 
                          g_new_dir ? load3(g_new_dir, i) : v3(0, 0, 0),
                          g_hit_local ? load3(g_hit_local, i) : v3(0, 0, 0),
                          g_normal ? load3(g_normal, i) : v3(0, 0, 0), g_t ? g_t[i] : 0.0f,
-                         gp, gd, mod, G, flags);
+                         gp, gd, mod, G, flags, make_aux(T.rows.data(), R, io.ni, io.no, i, row, 0).u);
         if (g_in_pos) store3(g_in_pos, i, gp);
         if (g_in_dir) store3(g_in_dir, i, gd);
         if (g_table && flags) {

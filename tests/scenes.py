@@ -26,11 +26,11 @@ def _adhoc(ns, shape, make_fn):
 
 
 # ---- C1: singlet + sensor (tests/test_optimize_singlet.py:29-49 values) ----------------
-def c1_singlet(ns, physical=False, grads=False, inked=True):
+def c1_singlet(ns, physical=False, grads=False, inked=True, fresnel=False):
     E = ns.elements
     glass, media = (1.0, 1.5168) if physical else (1.5168, 1.0)
     lens = E.SingletLens(c1=0.016667, c2=-0.00283, d=25.4, t=4.0, ior_glass=glass, ior_media=media,
-                         inked=inked, c1_grad=grads, c2_grad=grads)
+                         inked=inked, c1_grad=grads, c2_grad=grads, fresnel=fresnel)
     sensor = E.Sensor(ns.geom.Disk(radius=20.0, transform=_T(ns, 100.0)))
     return [lens, sensor]
 

@@ -543,3 +543,97 @@ def test_ideal_thin_lens_known_answers(run_exact, rtt_ns):
     assert abs(i0[2] - 150.0) < 1e-1
     assert abs((iz[2] - i0[2]) - 0.25) < 5e-3              # axial magnification (z_i / z_o)^2
     assert abs((ix[0] - i0[0]) + 0.5) < 5e-3               # lateral magnification z_i / z_o
+
+
+# ---------------------------------------------------------------------------------------------
+# RefractFresnel (phys/std.py:146-224): stochastic reflect / refract with a counter-based generator
+# ---------------------------------------------------------------------------------------------
+def _fresnel_table(rtt_ns, seed, grads=False, inked=False):
+    import raytracetorch_b200 as rtt
+    els = scenes.c1_singlet(rtt_ns, physical=True, inked=inked, fresnel=True, grads=grads)
+    tab = rtt.compile_elements(els)
+    assert tab.stochastic
+    return els, tab.with_seed(seed)
+
+
+@pytest.mark.parametrize("seed", [1, 0x9E3779B97F4A7C15])
+def test_fresnel_kernels_take_the_oracles_branches(run_exact, run_fast, ieee_oracle, rtt_ns, seed):
+    """Same seed => same uniform draws (Philox counter = ray, row, bounce) => the kernels reflect / refract exactly
+    where the oracle does: EXACT bit-identical, FAST within tolerance; sequential and non-sequential."""
+    _, tab = _fresnel_table(rtt_ns, seed)
+    tf, ti = tab.f.detach().numpy(), tab.i.numpy()
+    rays = scenes.make_bundle(rtt_ns, ("coll", 11.0, -10.0, [0.3, 0.1, 0.0]), 4000, 8)
+    pos, dr, inten = (t.numpy() for t in (rays.pos, rays.dir, rays.intensity))
+    o = ieee_oracle.trace_sequential(tab.f.detach(), tab.i_host, rays.pos, rays.dir, rays.intensity)
+    h = run_exact.trace_seq(tf, ti, pos, dr, inten)
+    for k in ("pos", "dir", "intensity"):
+        np.testing.assert_array_equal(h[k], o[k].numpy(), err_msg=k)
+    back = o["dir"].numpy()[:, 2] < 0
+    assert 0.02 < back.mean() < 0.5                       # a real mix of reflected and refracted rays
+    hf = run_fast.trace_seq(tf, ti, pos, dr, inten)
+    np.testing.assert_array_equal(hf["intensity"], o["intensity"].numpy())
+    assert parity.vec_rel(hf["pos"], o["pos"].numpy()).max() <= parity.TOL_POINT
+    assert parity.vec_rel(hf["dir"], o["dir"].numpy()).max() <= parity.TOL_POINT
+    # a different seed decides differently
+    _, tab2 = _fresnel_table(rtt_ns, seed + 1)
+    h2 = run_exact.trace_seq(tab2.f.detach().numpy(), tab2.i.numpy(), pos, dr, inten)
+    assert not np.array_equal(h2["dir"], h["dir"])
+    # non-sequential: the bounce index enters the counter
+    nb = 5
+    on = ieee_oracle.trace_nonsequential(tab.f.detach(), tab.i_host, rays.pos, rays.dir, rays.intensity, nb)
+    hn = run_exact.trace_nonseq(tf, ti, pos, dr, inten, nb)
+    hseq = hn["seq"].astype(np.int64)
+    hseq[hseq == 255] = -1
+    clean = parity.self_hit_free(dict(in_pos=pos, in_dir=dr, in_intensity=inten, nbounces=nb), tab.f.detach(),
+                                 tab.i_host, nbounces=nb)
+    assert clean.mean() > 0.1
+    np.testing.assert_array_equal(hseq[clean], on["seq"].numpy()[clean])
+    assert parity.vec_rel(hn["pos"][clean], on["pos"].numpy()[clean]).max() <= parity.TOL_POINT
+
+
+def test_fresnel_reflectance_statistics(run_fast, rtt_ns):
+    """Statistical parity with the reference (its draws come from torch.rand_like): at normal incidence on an
+    n = 1 -> 1.5168 face the reflected fraction is ((n1-n2)/(n1+n2))^2 = 4.21 %; and the fraction of rays sent back
+    by the whole fresnel singlet matches the reference's own run (fixture extra_fresnel) within 5 sigma."""
+    import raytracetorch_b200 as rtt
+    n = 400_000
+    face = rtt.ops._Holder(rtt.geom.Plane(), [rtt.phys.RefractFresnel(1.0, 1.5168)])
+    tab = rtt.compile_elements([face]).with_seed(77)
+    pos = np.zeros((n, 3), np.float32)
+    pos[:, 2] = -1.0
+    dr = np.tile(np.array([[0.0, 0.0, 1.0]], np.float32), (n, 1))
+    h = run_fast.trace_seq(tab.f.detach().numpy(), tab.i.numpy(), pos, dr, np.ones(n, np.float32))
+    frac = float((h["dir"][:, 2] < 0).mean())
+    R = ((1.0 - 1.5168) / (1.0 + 1.5168)) ** 2
+    assert abs(frac - R) < 5 * np.sqrt(R * (1 - R) / n), (frac, R)
+    d = parity.load("extra_fresnel")
+    _, tab = _fresnel_table(rtt_ns, 2024)
+    rays = scenes.make_bundle(rtt_ns, ("coll", 11.0, -10.0, [0.3, 0.1, 0.0]), int(d["n_rays"]), 8)
+    h = run_fast.trace_seq(tab.f.detach().numpy(), tab.i.numpy(), rays.pos.numpy(), rays.dir.numpy(),
+                           rays.intensity.numpy())
+    mine, ref = float((h["dir"][:, 2] < 0).mean()), float(d["back_fraction"])
+    sigma = np.sqrt(ref * (1 - ref) / int(d["n_rays"]))
+    assert abs(mine - ref) < 5 * np.sqrt(2) * sigma, (mine, ref, sigma)
+
+
+@pytest.mark.parametrize("variant", ["exact", "fast"])
+def test_fresnel_adjoint_differentiates_the_branch_taken(runner_of, rtt_ns, variant):
+    """The reflect / refract choice is not differentiable (phys/std.py:190-193); gradients flow through the chosen
+    branch.  Hand-written adjoint vs oracle autograd under the same seed."""
+    import raytracetorch_b200 as rtt
+    hs = runner_of(variant)
+    els, tab = _fresnel_table(rtt_ns, 4242, grads=True)
+    rays = scenes.make_bundle(rtt_ns, ("coll", 9.0, -10.0, [0.2, 0.1, 0.0]), 3000, 9)
+    tf = tab.f.detach().clone().requires_grad_(True)
+    p, dd, w = (t.clone().requires_grad_(True) for t in (rays.pos, rays.dir, rays.intensity))
+    o = O.trace_sequential(tf, tab.i_host, p, dd, w)
+    parity.golden_loss(o["pos"], o["dir"], o["intensity"]).backward()
+    fwd = hs.trace_seq(tab.f.detach().numpy(), tab.i.numpy(), rays.pos.numpy(), rays.dir.numpy(), rays.intensity.numpy())
+    gp, gd, gi = parity.golden_loss_grads(fwd["pos"], fwd["dir"], fwd["intensity"])
+    bwd = hs.trace_seq_bwd(tab.f.detach().numpy(), tab.i.numpy(), rays.pos.numpy(), rays.dir.numpy(),
+                           rays.intensity.numpy(), fwd["hitmask"], gp, gd, gi)
+    assert parity.grad_rel(bwd["g_pos"], p.grad.numpy()) < parity.TOL_GRAD
+    assert parity.grad_rel(bwd["g_dir"], dd.grad.numpy()) < parity.TOL_GRAD
+    for r in (0, 1):                                       # d loss / d c of both faces (flag GRAD_CK)
+        ref = float(tf.grad[r, 24])
+        assert abs(float(bwd["g_table"][r, 24]) - ref) <= parity.TOL_GRAD * abs(ref), (r, bwd["g_table"][r, 24], ref)
