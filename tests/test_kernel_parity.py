@@ -562,7 +562,7 @@ def test_fresnel_kernels_take_the_oracles_branches(run_exact, run_fast, ieee_ora
     where the oracle does: EXACT bit-identical, FAST within tolerance; sequential and non-sequential."""
     _, tab = _fresnel_table(rtt_ns, seed)
     tf, ti = tab.f.detach().numpy(), tab.i.numpy()
-    rays = scenes.make_bundle(rtt_ns, ("coll", 11.0, -10.0, [0.3, 0.1, 0.0]), 4000, 8)
+    rays = scenes.make_bundle(rtt_ns, ("coll", 10.0, -10.0, [0.12, 0.05, 0.0]), 4000, 8)
     pos, dr, inten = (t.numpy() for t in (rays.pos, rays.dir, rays.intensity))
     o = ieee_oracle.trace_sequential(tab.f.detach(), tab.i_host, rays.pos, rays.dir, rays.intensity)
     h = run_exact.trace_seq(tf, ti, pos, dr, inten)
