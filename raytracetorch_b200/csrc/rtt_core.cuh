@@ -51,6 +51,7 @@ enum {
     D_R2 = 44,        // radius**2               geom/primitives.py:161,214
     D_SB0SQ = 45,     // sb[0]**2                geom/bounded.py:64,157
     D_HB0SQ = 46,     // hb[0]**2                geom/spherics.py:44
+    D_ACC_SLOT = 47,  // sequential adjoint: index of the row's private gradient slots (as a float), -1 = none
     DI_IDENT = 11,    // bit0: Re == I, bit1: Rs == I (exact compare)
     DI_OPCODE = 12    // index of the matching KStatic specialisation (RTT_ROW_SPECS), 0 = generic
 };

@@ -543,6 +543,7 @@ __device__ __forceinline__ void reverse_row(const SmemTable& T, int S, int L, in
 // parameter gradient — every term of the reverse sweep is linear in them — so the block first compacts the
 // chunk to the rays that matter (dead rays of an intensity-weighted loss, rays that missed everything) and
 // runs the replay + reverse sweep on full warps of those.
+constexpr int kAccRows = 12, kAccPerRow = 5;      // private gradient slots: rows x (c, k, radius, ior_in, ior_out)
 constexpr int kBwdChunk = 16 * kThreads;   // large enough that the compacted chunk still fills whole blocks of warps
 __host__ __device__ inline size_t bwd_queue_bytes() { return sizeof(unsigned short) * kBwdChunk + 16; }
 
@@ -557,6 +558,24 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
     unsigned short* queue = reinterpret_cast<unsigned short*>(qcount + 2);
     for (int idx = threadIdx.x; idx < S * RTT_ROW_G + L * S * 2; idx += blockDim.x) acc[idx] = 0.0f;
     stage_table(a.tab, T);
+
+    // Private gradient accumulators: rows whose requested gradients are scalars only (c, k, radius, indices —
+    // the usual lens-design variables) add into per-thread slots (local memory, L1) ray after ray and are reduced
+    // over the warp ONCE at the end of the block, instead of 5 shuffles + a shared atomic per entry per ray row.
+    // Rows with pose gradients, wavelength-resolved indices or beyond kAccRows keep the per-row warp reduction.
+    if (threadIdx.x == 0) {
+        int used = 0;
+        for (int r = 0; r < S; ++r) {
+            const int fl = T.rows[r].i[RTT_I_FLAGS];
+            const bool scalar_only = fl != 0 && !(fl & (RTT_FLAG_GRAD_POSE_E | RTT_FLAG_GRAD_POSE_S)) &&
+                                     !(L > 0 && (fl & RTT_FLAG_GRAD_IOR));
+            T.rows[r].f[D_ACC_SLOT] = (a.g_table && scalar_only && used < kAccRows) ? (float)(used++) : -1.0f;
+        }
+    }
+    __syncthreads();
+    float pacc[kAccRows * kAccPerRow];
+#pragma unroll
+    for (int e = 0; e < kAccRows * kAccPerRow; ++e) pacc[e] = 0.0f;
 
     const bool compact = !a.g_pos && !a.g_dir && !a.g_inten;
     const SourceKey skey = fetch_key(a);
@@ -656,7 +675,14 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
                     default: reverse_row<KDyn>(T, S, L, r, lam, i, a, ck[nh], gp, gd, gI, G, flags); break;
                 }
             }
-            if (a.g_table && flags) {
+            const int slot = (int)R.f[D_ACC_SLOT];
+            if (a.g_table && flags && slot >= 0) {
+                if (hit) {                                               // G is zero where nothing was requested
+                    float* pa = pacc + slot * kAccPerRow;
+                    pa[0] += G.g[RTT_F_C]; pa[1] += G.g[RTT_F_K]; pa[2] += G.g[RTT_F_RADIUS];
+                    pa[3] += G.g[RTT_F_IOR_IN]; pa[4] += G.g[RTT_F_IOR_OUT];
+                }
+            } else if (a.g_table && flags) {
                 if (L > 0 && (flags & RTT_FLAG_GRAD_IOR)) {
                     // wavelength-resolved index gradients go to the LUT accumulator
                     for (int l = 0; l < L; ++l) {
@@ -680,6 +706,17 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
         }
       }
       if (compact) __syncthreads();                                       // the queue is rewritten by the next chunk
+    }
+    // private slots -> block accumulator: one warp reduction per entry for the whole block's work
+    for (int r = 0; r < S; ++r) {
+        const int slot = (int)T.rows[r].f[D_ACC_SLOT];
+        if (slot < 0) continue;
+        const int entry[kAccPerRow] = {RTT_F_C, RTT_F_K, RTT_F_RADIUS, RTT_F_IOR_IN, RTT_F_IOR_OUT};
+#pragma unroll
+        for (int e = 0; e < kAccPerRow; ++e) {
+            const float sum = warp_sum(pacc[slot * kAccPerRow + e]);
+            if ((threadIdx.x & 31) == 0 && sum != 0.0f) atomicAdd(acc + r * RTT_ROW_G + entry[e], sum);
+        }
     }
     flush_block_grads(acc, S, a.g_table, acc_lut, L, a.g_lut);
 }
