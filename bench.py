@@ -566,16 +566,25 @@ def run_c3(args):
         translation=[0.0, 0.0, -10.0]).to(dev))
     goal = rtt.optim.SpotSizeLoss(w["sensor"], [bundle], N_rays=n)
     params = [p for p in scene.parameters() if p.requires_grad]
-    opt = torch.optim.Adam(params, lr=1e-5)
     torch.manual_seed(100 + rank)
     loss_host = torch.empty(1).pin_memory()
+    graphed = None
+    if world == 1 and not args.no_graph:
+        # one GPU: the whole step (zero_grad, goal, backward, Adam) replays as ONE CUDA graph (optim.GraphedStep)
+        opt = torch.optim.Adam(params, lr=1e-5, capturable=True)
+        graphed = rtt.optim.GraphedStep.try_build(scene, goal, opt)
+    if graphed is None:
+        opt = torch.optim.Adam(params, lr=1e-5)
 
     def step():
-        opt.zero_grad(set_to_none=True)
-        loss = goal(scene)
-        loss.backward()
-        rdist.allreduce_scene_results([], params)
-        opt.step()
+        if graphed is not None:
+            loss = graphed()
+        else:
+            opt.zero_grad(set_to_none=True)
+            loss = goal(scene)
+            loss.backward()
+            rdist.allreduce_scene_results([], params)
+            opt.step()
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
 
     def barrier():
@@ -604,6 +613,8 @@ def run_c3(args):
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
         ms = float(t.item())
     launches = lib.launch_count() - l0
+    if graphed is not None:                                  # replays launch the captured kernels without the host counter
+        launches += graphed.launches_per_step * args.steps
     value = world * n * S / (ms / 1e3)
     # adjoint kernel alone
     tab = scene.table()
@@ -656,6 +667,7 @@ def run_c3(args):
                     ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                     data="synthetic",
                     config=dict(workload=w["desc"], rays_per_gpu=n, rows=S, direction="forward+adjoint per step",
+                                cuda_graph=graphed is not None,
                                 l2="bundle (280 MB) larger than L2", api="SpotSizeLoss(sensor,[bundle],N)(scene); "
                                 "loss.backward(); Adam.step()"),
                     clocks=clocks, gpu_launches=launches, roofline=roof,
@@ -704,6 +716,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-bwd", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="c3: run the optimisation step eagerly (no CUDA graph)")
     args = ap.parse_args()
     args.rays = int(args.rays)
     if args.impl == "reference":

@@ -213,3 +213,51 @@ class SpotSizeLoss(Goal):
         if not losses:
             return torch.tensor(0.0)
         return torch.stack(losses).mean()
+
+
+class GraphedStep:
+    """One optimisation step — ``zero_grad -> goal(scene) -> backward -> optimizer.step`` — captured in a CUDA graph.
+
+    A step of the singlet optimisation is ~25 launches (two trace kernels, three goal reductions, the table-building
+    elementwise ops, the optimiser) for ~1.3 ms of GPU work at 1e7 rays; replaying one graph removes the launch gaps.
+    Device-generated bundles advance their {key, counter} state on the device, so every replay traces fresh rays.
+
+    Requirements: CUDA scene and bundles, a capturable optimiser (e.g. ``torch.optim.Adam(..., capturable=True)``), no
+    trainable rotation vectors (``matrix_exp`` synchronises) and no stochastic rows (their seed is drawn on the host).
+    ``GraphedStep.try_build`` returns None instead of raising when the capture is refused."""
+
+    def __init__(self, scene, goal, optimizer, warmup: int = 3):
+        self.scene, self.goal, self.optimizer = scene, goal, optimizer
+        dev = next(p for p in scene.parameters()).device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                       # eager warm-up: allocator, caches, optimiser state
+            for _ in range(max(1, warmup)):
+                optimizer.zero_grad(set_to_none=True)
+                loss = goal(scene)
+                loss.backward()
+                optimizer.step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        from . import _cabi
+        lib = _cabi.load()
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        before = lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.loss = goal(scene)
+            self.loss.backward()
+            optimizer.step()
+        self.launches_per_step = lib.launch_count() - before     # this library's kernels inside one replay
+
+    def __call__(self) -> torch.Tensor:
+        """Run one step; returns the (static) loss tensor of that step."""
+        self.graph.replay()
+        return self.loss
+
+    @classmethod
+    def try_build(cls, scene, goal, optimizer, warmup: int = 3):
+        try:
+            return cls(scene, goal, optimizer, warmup)
+        except Exception:                                    # capture refused: callers fall back to eager steps
+            torch.cuda.synchronize()
+            return None

@@ -308,6 +308,22 @@ def _first_device(rows: List[RowPlan]) -> torch.device:
     return rows[0].trans_s.device if rows else torch.device("cpu")
 
 
+_INT_TABLES: Dict[tuple, torch.Tensor] = {}
+
+
+def _int_table(meta, S: int, dev) -> torch.Tensor:
+    """Device copy of the int block, cached by content: it depends on the scene's structure and requires_grad flags
+    only, so optimisation loops (and CUDA-graph captures, where a pageable host-to-device copy is illegal) reuse it."""
+    key = (tuple(tuple(m) for m in meta), str(dev))
+    hit = _INT_TABLES.get(key)
+    if hit is None:
+        if len(_INT_TABLES) > 256:
+            _INT_TABLES.clear()
+        hit = torch.tensor(meta, dtype=torch.int32).view(S, C.ROW_I).to(dev)
+        _INT_TABLES[key] = hit
+    return hit
+
+
 def build_table(rows: List[RowPlan], sensors, sensor_rows, elements, *, dtype=torch.float32,
                 device: Optional[torch.device] = None,
                 dispersion: Optional[Dispersion] = None) -> SurfaceTable:
@@ -367,7 +383,7 @@ def build_table(rows: List[RowPlan], sensors, sensor_rows, elements, *, dtype=to
             fl |= C.FLAG_GRAD_IOR
         m[C.I_FLAGS] = fl
         meta.append(m)
-    i = torch.tensor(meta, dtype=torch.int32).view(S, C.ROW_I).to(dev)
+    i = _int_table(meta, S, dev)
 
     lut = lut_w = None
     if dispersion is not None:

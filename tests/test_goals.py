@@ -196,3 +196,43 @@ def test_renderer_render_3d_matches_reference(rtt_ns):
     assert (diff > 1e-4).mean() <= 0.005, f"{(diff > 1e-4).sum()} pixels differ"
     assert (np.abs(ref - 1.0).sum(-1) > 0).sum() > 800      # the fixture really shows the elements
     assert len(np.unique(np.round(ref.reshape(-1, 3), 3), axis=0)) > 20
+
+
+@pytest.mark.gpu
+def test_graphed_optimisation_step_follows_the_eager_loop(rtt_ns):
+    """optim.GraphedStep: zero_grad -> SpotSizeLoss -> backward -> Adam captured in one CUDA graph.  Every replay
+    draws fresh rays (device-side counter) and moves the parameters like the eager loop under the same seed."""
+    import raytracetorch_b200 as rtt
+    import scenes
+    dev = torch.device("cuda", 0)
+
+    def setup():
+        els = scenes.c1_singlet(rtt_ns, physical=True, grads=True)
+        scene = rtt.scene.SequentialScene(els).to(dev)
+        bundle = rtt.rays.CollimatedDisk(5.0, 0, device=dev, transform=rtt.geom.RayTransformBundle(
+            translation=[0.0, 0.0, -10.0]).to(dev))
+        goal = rtt.optim.SpotSizeLoss(els[1], [bundle], N_rays=200_000)
+        params = [p for p in scene.parameters() if p.requires_grad]
+        opt = torch.optim.Adam(params, lr=1e-5, capturable=True)
+        return scene, goal, opt, params
+
+    warm, steps = 2, 5
+    torch.manual_seed(7)
+    scene, goal, opt, params = setup()
+    losses_e = []
+    for _ in range(warm + steps):
+        opt.zero_grad(set_to_none=True)
+        loss = goal(scene)
+        loss.backward()
+        opt.step()
+        losses_e.append(float(loss))
+    eager = [p.detach().clone() for p in params]
+    torch.manual_seed(7)
+    scene, goal, opt, params = setup()
+    g = rtt.optim.GraphedStep(scene, goal, opt, warmup=warm)
+    assert g.launches_per_step >= 5                         # trace + goal reductions + their adjoints
+    losses_g = [float(g()) for _ in range(steps)]
+    for a, b in zip(eager, params):
+        assert torch.allclose(a, b.detach(), rtol=1e-5, atol=1e-9), (a, b)
+    np.testing.assert_allclose(losses_g, losses_e[warm:], rtol=1e-4)
+    assert len(set(losses_g)) == steps                      # fresh rays on every replay
