@@ -363,7 +363,8 @@ def build_table(rows: List[RowPlan], sensors, sensor_rows, elements, *, dtype=to
 
             zz = torch.stack([sag(sg[:, 0], sg[:, 1]), sag(sg[:, 2], sg[:, 3])], dim=1)
             hb = hb.clone()
-            hb[torch.as_tensor(edge_rows, device=dev), 0:2] = zz
+            for k_edge, n_edge in enumerate(edge_rows):           # int indices: no host-to-device index tensor
+                hb[n_edge, 0:2] = zz[k_edge]                      # (a pageable H2D copy is illegal in graph capture)
         pad = torch.zeros(S, C.ROW_F - C.F_HB - 8, dtype=dtype, device=dev)
     f = torch.cat([Re.reshape(S, 9), vecs[:, 0], Rs.reshape(S, 9), vecs[:, 1], scal, sb, hb, pad], dim=1)
 
