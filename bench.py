@@ -621,7 +621,8 @@ def run_c3(args):
     rays = bundle.sample(n)
     fwd = torch.ops.rtt_b200.trace_seq_fwd(rays.pos, rays.dir, rays.intensity, None, tab.f.detach(), tab.i, None, None,
                                            [0.0] * rtt.ops.SENSOR_CFG, True, rtt.ops.get_default_mode())
-    g_rec = torch.randn_like(fwd[4])
+    # (own generator: the default CUDA generator is registered with the captured graph of the timed loop)
+    g_rec = torch.randn(fwd[4].shape, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
     kt = []
     for _ in range(max(args.steps, 3)):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
