@@ -573,6 +573,8 @@ def run_c3(args):
         # one GPU: the whole step (zero_grad, goal, backward, Adam) replays as ONE CUDA graph (optim.GraphedStep)
         opt = torch.optim.Adam(params, lr=1e-5, capturable=True)
         graphed = rtt.optim.GraphedStep.try_build(scene, goal, opt)
+        if graphed is None:
+            print(f"bench c3: CUDA-graph capture refused ({rtt.optim.GraphedStep.last_error}); eager steps", file=sys.stderr)
     if graphed is None:
         opt = torch.optim.Adam(params, lr=1e-5)
 

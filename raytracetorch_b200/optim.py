@@ -224,11 +224,29 @@ class GraphedStep:
 
     Requirements: CUDA scene and bundles, a capturable optimiser (e.g. ``torch.optim.Adam(..., capturable=True)``), no
     trainable rotation vectors (``matrix_exp`` synchronises) and no stochastic rows (their seed is drawn on the host).
-    ``GraphedStep.try_build`` returns None instead of raising when the capture is refused."""
+    ``GraphedStep.try_build`` returns None instead of raising when the capture is refused (reason in ``last_error``)."""
+
+    last_error = None
 
     def __init__(self, scene, goal, optimizer, warmup: int = 3):
         self.scene, self.goal, self.optimizer = scene, goal, optimizer
         dev = next(p for p in scene.parameters()).device
+
+        def drop_graph_refs():
+            # Autograd keeps ONE AccumulateGrad node per Parameter alive as long as any graph references it, and the
+            # node remembers the stream it was created on.  A table cached by the scene (or a loss kept by the caller)
+            # from an earlier eager call would pin nodes of the default stream, which invalidates the capture.
+            comp = getattr(scene, "_compiler", None)
+            if comp is not None:
+                comp._table = None
+            scene._last_table = None
+            scene.last_trace = None
+            for el in getattr(scene, "elements", []):
+                if hasattr(el, "reset"):
+                    el.reset()
+            optimizer.zero_grad(set_to_none=True)
+
+        drop_graph_refs()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                       # eager warm-up: allocator, caches, optimiser state
@@ -237,6 +255,8 @@ class GraphedStep:
                 loss = goal(scene)
                 loss.backward()
                 optimizer.step()
+                del loss
+                drop_graph_refs()
         torch.cuda.current_stream(dev).wait_stream(side)
         from . import _cabi
         lib = _cabi.load()
@@ -256,8 +276,10 @@ class GraphedStep:
 
     @classmethod
     def try_build(cls, scene, goal, optimizer, warmup: int = 3):
+        cls.last_error = None
         try:
             return cls(scene, goal, optimizer, warmup)
-        except Exception:                                    # capture refused: callers fall back to eager steps
+        except Exception as exc:                             # capture refused: callers fall back to eager steps
+            cls.last_error = f"{type(exc).__name__}: {exc}"
             torch.cuda.synchronize()
             return None
