@@ -29,7 +29,7 @@ from .geom import rotation_from_vector
 
 
 class UnsupportedSceneError(NotImplementedError):
-    """Raised for objects outside the fused path (Fresnel, Linear, Cone, custom callables)."""
+    """Raised for objects outside the fused path (custom callables such as ``Fuzzy``, unfinished reference classes)."""
 
 
 def _names(obj) -> set:
