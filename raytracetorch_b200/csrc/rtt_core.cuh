@@ -102,10 +102,12 @@ struct KDyn {
     static RTT_HD int phys(const struct RowDev& R);
     static RTT_HD int ident(const struct RowDev& R);
     static RTT_HD bool sensor(const struct RowDev& R);
+    static RTT_HD bool specialised() { return false; }
 };
 template <int SURF, int BOUND, int SHAPE, int PHYS, int IDENT, int SENSOR = 0>
 struct KStatic {
     static RTT_HD bool sensor(const struct RowDev&) { return SENSOR != 0; }
+    static RTT_HD bool specialised() { return true; }
     static RTT_HD int surf(const struct RowDev&) { return SURF; }
     static RTT_HD int bound(const struct RowDev&) { return BOUND; }
     static RTT_HD int shape(const struct RowDev&) { return SHAPE; }

@@ -53,6 +53,9 @@ RTT_HD int tile_opcode(const RowDev& R) {
         R.i[RTT_I_PHYS] == PHYS && rs == RS_IDENT && (R.i[RTT_I_SENSOR] >= 0) == (SENSOR != 0)) op = OP;
     RTT_TILE_SPECS(RTT_X)
 #undef RTT_X
+    // specialised HALF-bounded conics assume the usual, non-inverted bound (lean root selection); an inverted one
+    // takes the generic path
+    if (R.i[RTT_I_BOUND] == RTT_BOUND_HALF && R.i[RTT_I_INVERT] != 0) op = 0;
     return op;
 }
 
@@ -295,6 +298,41 @@ RTT_HD bool regular_dir(V3 d) {
     return (l2 == 0.0f) || (fabsf(l2 - 1.0f) <= 4e-6f);
 }
 
+// ---- lean root selection for lens faces (RTT_TILE_LEAN: FAST builds) ------------------------------
+// A HALF-bounded, non-inverted conic (every lens face): the reference masks each of the two roots with
+// (t > 1e-6) & (|z c| < 1 + 1e-6) and takes the smaller survivor (geom/bounded.py:20-36).  Same decision, fewer
+// selects: order the roots, test both, keep the lower valid one; the A ~ 0 fallback (geom/primitives.py:305-313) is a
+// rarely taken branch instead of a blend.  Root values are those of solve_roots (identical expressions).
+template <class K>
+RTT_HD bool conic_half_hit(const RowDev& R, V3 o, V3 d, float& t) {
+    const float c = R.f[RTT_F_C], c1k = R.f[D_C1K];
+    const float tc = 2.0f * c, tc1k = 2.0f * c1k;
+    float A, B, Cq;
+    if (K::surf(R) == RTT_SURF_QUADRIC) {
+        A = c * (d.x * d.x + d.y * d.y) + c1k * (d.z * d.z);
+        B = (tc * (o.x * d.x + o.y * d.y) + (tc1k * o.z) * d.z) - 2.0f * d.z;
+        Cq = (c * (o.x * o.x + o.y * o.y) + c1k * (o.z * o.z)) - 2.0f * o.z;
+    } else {
+        A = c * (d.y * d.y) + c1k * (d.z * d.z);
+        B = (tc * (o.y * d.y) + (tc1k * o.z) * d.z) - 2.0f * d.z;
+        Cq = (c * (o.y * o.y) + c1k * (o.z * o.z)) - 2.0f * o.z;
+    }
+    if (fabsf(A) < 1e-6f) {                                             // flat face / ray along a generator
+        const float Bs = (fabsf(B) < 1e-6f) ? 1e-6f : B;
+        t = div_(-Cq, Bs);
+        return (t > 1e-6f) && (fabsf(fmaf(t, d.z, o.z) * c) < 1.000001f);
+    }
+    const float disc = B * B - (4.0f * A) * Cq;
+    const float sq = sqrt_(fabsf(disc));
+    const float inv = rcp_(2.0f * A);
+    const float r1 = (-B - sq) * inv, r2 = (-B + sq) * inv;
+    const float lo = fminf(r1, r2), hi = fmaxf(r1, r2);
+    const bool oklo = (lo > 1e-6f) && (fabsf(fmaf(lo, d.z, o.z) * c) < 1.000001f);
+    const bool okhi = (hi > 1e-6f) && (fabsf(fmaf(hi, d.z, o.z) * c) < 1.000001f);
+    t = oklo ? lo : hi;
+    return (disc >= 0.0f) && (oklo || okhi);
+}
+
 // ---- one row ------------------------------------------------------------------------------------
 // Distance along the ray with every validity rule of the sequential walk (surface bounds, t > 1e-6,
 // shape-level rule); (pe, de) are in the row's frame.  Returns true iff the ray interacts with the row.
@@ -317,10 +355,19 @@ RTT_HD bool tile_test(const RowDev* rows, int r, V3 pe, V3 de, float& t) {
         o = rot_fwd(pe - ld3(R.f + RTT_F_TS), R.f + RTT_F_RS, rs_ident);
         dd = rot_fwd(de, R.f + RTT_F_RS, rs_ident);
     }
-    const Roots q = solve_roots<K>(R, o, dd);
-    int which;
-    t = select_root<K>(R, q, o, dd, &which);
-    bool valid = t < rtt_inf();
+    bool valid;
+#if defined(RTT_TILE_LEAN)
+    if (K::specialised() && (K::surf(R) == RTT_SURF_QUADRIC || K::surf(R) == RTT_SURF_QUADRIC_ZY) &&
+        K::bound(R) == RTT_BOUND_HALF) {                                // tile_opcode: never an inverted bound here
+        valid = conic_half_hit<K>(R, o, dd, t);
+    } else
+#endif
+    {
+        const Roots q = solve_roots<K>(R, o, dd);
+        int which;
+        t = select_root<K>(R, q, o, dd, &which);
+        valid = t < rtt_inf();
+    }
     if (K::shape(R) != RTT_SHAPE_NONE && valid) valid = shape_in_bounds<K>(rows, r, along(pe, t, de));
     return valid;
 }

@@ -3,7 +3,7 @@
 set -u
 TAG="${1:-sweep}"; OUT=gpurun_out; mkdir -p $OUT
 for wl in c2 c1 c4; do
-  for t in 1 3; do
+  for t in 3; do
     RTT_FWD_TILE=$t timeout 300 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu --no-e2e --no-bwd > $OUT/sweep_${wl}_t${t}_$TAG.json 2> $OUT/sweep_${wl}_t${t}_$TAG.err
     python - <<PY
 import json

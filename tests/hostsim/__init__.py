@@ -20,7 +20,7 @@ from simcommon import SourceGoalMixin
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _BUILD = os.path.join(_HERE, "_build")
-_FLAGS = {"exact": ["-ffp-contract=off", "-mfma"], "fast": ["-ffp-contract=fast", "-mfma", "-DRTT_HOST_TILE"]}
+_FLAGS = {"exact": ["-ffp-contract=off", "-mfma"], "fast": ["-ffp-contract=fast", "-mfma", "-DRTT_HOST_TILE", "-DRTT_TILE_LEAN"]}
 _cache = {}
 
 
