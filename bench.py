@@ -69,6 +69,15 @@ def build_workload(name: str, device):
         els[4].set_image(2160, 3840)
         w.update(elements=els, sensor=els[4], source=("disk", 9.0, -10.0), wavelengths=None, rays=10 ** 8,
                  desc="C4 doublet + stop + triplet + singlet + 4K sensor, 17 rows")
+    elif name == "c4cam":
+        # BASELINE configs[3] as written: the same lens, rays of a pinhole Camera (render/camera.py:39-72) generated
+        # INSIDE the trace kernel (no ray input from HBM), 120 jittered samples per pixel of a 3840x2160 camera
+        # = 9.95e8 rays over 8 GPUs, i.e. 15 samples (1.24e8 rays) per GPU; each GPU traces its own sample range
+        els = scenes.c4_camera_lens(ns)
+        els[4].set_image(2160, 3840)
+        w.update(elements=els, sensor=els[4], source=("camera", 15), wavelengths=None, rays=3840 * 2160 * 15,
+                 desc="C4 camera render: doublet + stop + triplet + singlet + 4K sensor, 17 rows, in-kernel pinhole "
+                      "camera rays, 15 samples/pixel per GPU")
     elif name == "c5":
         els = scenes.c5_nonsequential(ns)
         els[4].set_image(512, 512)
@@ -289,11 +298,26 @@ def run_gpu_arm(args):
     scene.record_hits = False
     table = scene.table()
     S = table.n_rows
-    pos, dirs, inten, wav = synth_bundle(w, n, dev, 1000 + rank)
+    camera_src = None
+    if w["source"][0] == "camera":
+        cam = rtt.render.Camera((0.0, 0.0, -200.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 6.0, 3840, 2160, device=dev)
+        per_gpu = int(n)
+        camera_src = cam.generate_source_rays(samples=w["source"][1] * world, seed=1234, first=rank * per_gpu,
+                                              count=per_gpu)
+        pos = dirs = inten = wav = None
+    else:
+        pos, dirs, inten, wav = synth_bundle(w, n, dev, 1000 + rank)
     cfg = rtt.ops.sensor_cfg_of(table)
     img_numel = sum(int(cfg[k]) * int(cfg[k + 1]) * int(cfg[k + 2]) for k in range(0, len(cfg), rtt.ops.SENSOR_CFG))
 
     def fwd_step():
+        if camera_src is not None:
+            out = rtt.ops.trace_sequential(table, want_record=False, sensor_cfg=cfg, source=camera_src, want_rays=False)
+            if world > 1:
+                red = rdist.FlatReducer()
+                red.extend(out["images"])
+                red.reduce()
+            return out
         if w["nonseq"]:
             out = rtt.ops.trace_nonsequential(table, pos, dirs, inten, w["nbounces"], wav, want_record=False,
                                               sensor_cfg=cfg)
@@ -334,7 +358,7 @@ def run_gpu_arm(args):
         tests_per_ray = float(S)
         hm = out["hitmask"]
         hit_frac = [float(((hm >> r) & 1).float().mean().item()) for r in range(S)]
-    alive = float((out["intensity"] > 0).float().mean().item())
+    alive = float((out["intensity"] > 0).float().mean().item()) if out["intensity"].numel() else None
     del out
 
     # ---- timed: K forward steps, device-resident inputs -------------------------------------------
@@ -357,7 +381,11 @@ def run_gpu_arm(args):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         images = torch.zeros(img_numel, dtype=torch.float32, device=dev)
         a.record()
-        if w["nonseq"]:
+        if camera_src is not None:
+            torch.ops.rtt_b200.trace_seq_src_fwd(rtt.ops.source_cfg_of(camera_src), camera_src.pose, camera_src.state,
+                                                 camera_src.n, table.f, table.i, table.lut, table.lut_wavelengths, cfg,
+                                                 False, False, rtt.ops.get_default_mode())
+        elif w["nonseq"]:
             torch.ops.rtt_b200.trace_nonseq_fwd(pos, dirs, inten, wav, table.f, table.i, table.lut,
                                                 table.lut_wavelengths, cfg, False, w["nbounces"],
                                                 rtt.ops._default_mode_nonseq)
@@ -382,6 +410,8 @@ def run_gpu_arm(args):
         flops_per_ray = None
     else:
         bytes_per_ray = rf.sequential_bytes_per_ray(wavelength=wav is not None, hitmask=True)
+        if camera_src is not None:
+            bytes_per_ray = 8                       # rays generated in registers, no final-ray outputs: the hit mask only
         tf_host, ti_host = table.f.detach().cpu().tolist(), table.i_host
         flops_per_ray = rf.sequential_flops_per_ray(tf_host, ti_host, hit_frac)
     achieved = n * bytes_per_ray / (k_ms / 1e3) / 1e9
@@ -424,7 +454,7 @@ def run_gpu_arm(args):
 
     # ---- forward + adjoint (optimisation step: loss on the final rays, grads to the lens parameters) ----
     fb = None
-    if not w["nonseq"] and not args.no_bwd:
+    if not w["nonseq"] and not args.no_bwd and camera_src is None:
         for p in scene.parameters():
             p.requires_grad_(False)
         trainable = []
@@ -471,7 +501,33 @@ def run_gpu_arm(args):
 
     # ---- end to end through the public API with host buffers --------------------------------------------
     e2e = None
-    if not args.no_e2e:
+    if camera_src is not None:
+        # the public call has no host input: the camera's rays are generated on the device; the 4K image is read back
+        img_host = torch.empty(img_numel, dtype=torch.float32).pin_memory()
+        sensor = w["sensor"]
+        scene.final_rays = False
+
+        def cam_step():
+            sensor.reset()
+            scene.simulate(camera_src)
+            img = sensor.image
+            if world > 1:
+                tdist.all_reduce(img)
+            img_host.copy_(img.reshape(-1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(2):
+            cam_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            cam_step()
+        barrier()
+        e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / args.e2e_steps)
+        e2e = dict(value=world * n * tests_per_ray / (e_ms / 1e3), unit=UNIT, h2d_bytes_per_step=0,
+                   d2h_bytes_per_step=img_numel * 4, ms_per_step=e_ms, steps=args.e2e_steps,
+                   api="SequentialScene.simulate(Camera.generate_source_rays(...))")
+    elif not args.no_e2e:
         host = [t.cpu().pin_memory() for t in (pos, dirs, inten)] + \
                [(wav if wav is not None else torch.full((n,), 550.0, device=dev)).cpu().pin_memory()]
         h2d = sum(t.numel() * t.element_size() for t in host) + (0 if w["nonseq"] else n)   # + int8 ray ids
@@ -518,7 +574,7 @@ def run_gpu_arm(args):
 
     # ---- CPU baseline on rank 0, N=1 only --------------------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and camera_src is None:
         t, reps, rows, threads = cpu_port_sample(w, args.cpu_rays, args.cpu_seconds)
         per_ray = rows * (w["nbounces"] if w["nonseq"] else 1)
         cpu = dict(value=reps * args.cpu_rays * per_ray / t, unit=UNIT, cores=threads, kind="port",
@@ -711,7 +767,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c4cam", "c5"])
     ap.add_argument("--rays", type=float, default=0, help="rays per GPU (default: the workload's BASELINE size)")
     ap.add_argument("--cpu-rays", type=int, default=2_000_000, help="rays per CPU trace")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work of the cpu_baseline sample")

@@ -11,7 +11,7 @@ timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1
 tail -5 $OUT/pytest_gpu_$TAG.log
 timeout 900 python bench.py --steps 10 --warmup 3 > $OUT/bench_c2_$TAG.json 2> $OUT/bench_c2_$TAG.err; echo "bench c2 exit $?" | tee -a $OUT/status_$TAG.txt
 cat $OUT/bench_c2_$TAG.json
-for wl in c1 c3 c4 c5; do
+for wl in c1 c3 c4 c4cam c5; do
   timeout 600 python bench.py --workload $wl --steps 5 --warmup 3 --no-cpu > $OUT/bench_${wl}_$TAG.json 2> $OUT/bench_${wl}_$TAG.err; echo "bench $wl exit $?" | tee -a $OUT/status_$TAG.txt
   cat $OUT/bench_${wl}_$TAG.json
 done
