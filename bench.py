@@ -354,6 +354,9 @@ def run_gpu_arm(args):
         bounces = float(out["n_hits"].float().mean().item())
         tests_per_ray = S * min(bounces + 1.0, w["nbounces"])   # the bounce that finds no hit also tests every row
         hit_frac = None
+        # interactions per ray and row (winner histogram over all bounces), for the FLOP view
+        seq = out["hit_seq"].reshape(-1).long()
+        hits_per_row = (torch.bincount(seq[seq != 255], minlength=S)[:S].double() / n).tolist()
     else:
         tests_per_ray = float(S)
         hm = out["hitmask"]
@@ -407,7 +410,8 @@ def run_gpu_arm(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     if w["nonseq"]:
         bytes_per_ray = 28 + 28 + w["nbounces"] + 1
-        flops_per_ray = None
+        flops_per_ray = rf.nonsequential_flops_per_ray(table.f.detach().cpu().tolist(), table.i_host,
+                                                       tests_per_ray / S, hits_per_row)
     else:
         bytes_per_ray = rf.sequential_bytes_per_ray(wavelength=wav is not None, hitmask=True)
         if camera_src is not None:

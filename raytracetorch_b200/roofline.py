@@ -75,6 +75,17 @@ def sequential_flops_per_ray(table_f, table_i, hit_fraction: Sequence[float]) ->
     return tot
 
 
+def nonsequential_flops_per_ray(table_f, table_i, searches_per_ray: float, hits_per_row: Sequence[float]) -> float:
+    """Non-sequential forward: every executed nearest-hit search tests all rows (scene/base.py:164-176), every bounce
+    then interacts with its winner.  ``searches_per_ray`` = executed searches per ray (bounces + the final miss),
+    ``hits_per_row[r]`` = interactions per ray with row r."""
+    tot = 0.0
+    for r in range(len(table_i)):
+        c = row_costs(table_f[r], table_i[r])
+        tot += searches_per_ray * c["test"] + float(hits_per_row[r]) * c["interact"]
+    return tot
+
+
 def adjoint_flops_per_ray(table_f, table_i, hit_fraction: Sequence[float]) -> float:
     """Adjoint kernel: replay of the recorded interactions (roots + interaction, no validity rules)
     followed by the reverse sweep."""
