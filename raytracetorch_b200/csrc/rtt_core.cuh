@@ -53,6 +53,7 @@ enum {
     D_SB0SQ = 45,     // sb[0]**2                geom/bounded.py:64,157
     D_HB0SQ = 46,     // hb[0]**2                geom/spherics.py:44
     D_ACC_SLOT = 47,  // sequential adjoint: index of the row's private gradient slots (as a float), -1 = none
+    D_SAME_ELEM = 47, // non-sequential forward (same slot, other kernel): 1 = same element pose as the previous row
     DI_IDENT = 11,    // bit0: Re == I, bit1: Rs == I (exact compare)
     DI_OPCODE = 12    // index of the matching KStatic specialisation (RTT_ROW_SPECS), 0 = generic
 };
@@ -448,10 +449,20 @@ RTT_HD Frames to_frames(const RowDev& R, V3 p, V3 d) {
 }
 
 // Distance with the surface-level rules only; returns true iff `t < inf` (false for NaN).
+// reuse_elem: the element-frame part of F (pe, de, den, len) already holds this ray in THIS row's element frame
+// (the previous row probed belongs to the same element: bit-identical pose, hence bit-identical values), so only
+// the surface-frame part is recomputed — the nearest-hit search shares one element pose among a lens's or a box's rows.
 template <class K = KDyn>
-RTT_HD bool intersect_t(const RowDev* rows, int r, V3 p, V3 d, Frames& F, Roots& q, float& t, int& which) {
+RTT_HD bool intersect_t(const RowDev* rows, int r, V3 p, V3 d, Frames& F, Roots& q, float& t, int& which,
+                        bool reuse_elem = false) {
     const RowDev& R = rows[r];
-    F = to_frames<K>(R, p, d);
+    if (reuse_elem && K::shape(R) != RTT_SHAPE_NONE) {
+        const int ident = K::ident(R);
+        F.o = rot_fwd(F.pe - ld3(R.f + RTT_F_TS), R.f + RTT_F_RS, ident & 2);
+        F.dd = rot_fwd(F.den, R.f + RTT_F_RS, ident & 2);
+    } else {
+        F = to_frames<K>(R, p, d);
+    }
     q = solve_roots<K>(R, F.o, F.dd);
     t = select_root<K>(R, q, F.o, F.dd, &which);
     return t < rtt_inf();

@@ -728,9 +728,9 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
 // One row of the nearest-hit search (scene/base.py:164-176).
 template <class K>
 __device__ __forceinline__ void nonseq_probe(const RowDev* rows, int r, V3 p, V3 d, float& best, int& win,
-                                             bool& poisoned) {
-    Frames F; Roots q; float t; int which;
-    const bool finite_t = intersect_t<K>(rows, r, p, d, F, q, t, which);
+                                             bool& poisoned, Frames& F) {
+    Roots q; float t; int which;
+    const bool finite_t = intersect_t<K>(rows, r, p, d, F, q, t, which, rows[r].f[D_SAME_ELEM] != 0.0f);
     // rows of a Shape report inf when invalid; bare surfaces may report NaN, which poisons torch.min
     if (K::shape(rows[r]) == RTT_SHAPE_NONE && is_nan(t)) poisoned = true;
     if (finite_t && t < best && shape_ok<K>(rows, r, F, t)) { best = t; win = r; }
@@ -745,7 +745,12 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
     img_cache_init(cache);
     stage_table(a.tab, T);
     const int S = a.tab.S, L = a.tab.L, NB = a.nbounces;
-    for (int r = threadIdx.x; r < S; r += blockDim.x) cull[r] = box_cull_info(T.rows, S, r);
+    for (int r = threadIdx.x; r < S; r += blockDim.x) {
+        cull[r] = box_cull_info(T.rows, S, r);
+        bool same = r > 0 && T.rows[r].i[RTT_I_SHAPE] != RTT_SHAPE_NONE && T.rows[r - 1].i[RTT_I_SHAPE] != RTT_SHAPE_NONE;
+        for (int e = RTT_F_RE; same && e < RTT_F_TE + 3; ++e) same = T.rows[r].f[e] == T.rows[r - 1].f[e];
+        T.rows[r].f[D_SAME_ELEM] = same ? 1.0f : 0.0f;
+    }
     __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
     const SourceKey skey = fetch_key(a);
@@ -774,6 +779,8 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
             float best = rtt_inf();
             int win = -1;
             bool poisoned = false;
+            Frames Fs;                                                  // element-frame part shared by the rows of an element
+            Fs.pe = Fs.de = Fs.den = Fs.o = Fs.dd = v3(0.0f, 0.0f, 0.0f); Fs.len = 0.0f;
             for (int r = 0; r < S; ++r) {
                 if (cull[r].run > 0) {                                  // a box: skip its six faces when no lane can hit it
                     const bool missed = sphere_missed(cull[r], p, d);
@@ -783,10 +790,10 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
                 // shape-level rule (the costly part for box faces and lens edges) is evaluated only then
                 switch (T.rows[r].i[DI_OPCODE]) {                       // warp-uniform
 #define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR)                                            \
-                    case OP: nonseq_probe<KStatic<SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR>>(T.rows, r, p, d, best, win, poisoned); break;
+                    case OP: nonseq_probe<KStatic<SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR>>(T.rows, r, p, d, best, win, poisoned, Fs); break;
                     RTT_ROW_SPECS(RTT_X)
 #undef RTT_X
-                    default: nonseq_probe<KDyn>(T.rows, r, p, d, best, win, poisoned); break;
+                    default: nonseq_probe<KDyn>(T.rows, r, p, d, best, win, poisoned, Fs); break;
                 }
             }
             if (poisoned || win < 0) {
