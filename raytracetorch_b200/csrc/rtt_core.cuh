@@ -43,17 +43,6 @@ RTT_HD float sqrt_(float x) { return sqrtf(x); }
 RTT_HD float div_(float a, float b) { return a / b; }
 #endif
 
-// a / b for a root candidate whose denominator is known to be non-zero.  A ray that starts ON a surface (it has just
-// interacted with it: the usual state of a non-sequential bounce) gives an exactly zero numerator, and IEEE division
-// sends zero operands through its slow-path subroutine (7 % of the non-sequential kernel's instructions, at 4 active
-// lanes).  0 / b is +-0 and every caller masks candidates t <= 1e-6 (geom/primitives.py:32, bounded.py:32), so the
-// sign of that zero never matters: return 0 directly.
-#if defined(RTT_APPROX) && defined(__CUDA_ARCH__)
-RTT_HD float div0_(float a, float b) { return a * rcp_(b); }
-#else
-RTT_HD float div0_(float a, float b) { return (a == 0.0f) ? 0.0f : a / b; }
-#endif
-
 // ---- row record as staged in shared memory ------------------------------------------------
 // f[0..40] is the caller's table row; f[41..47] and i[11] are derived once per block.
 enum {
@@ -280,7 +269,7 @@ RTT_HD Roots solve_roots(const RowDev& R, V3 o, V3 d) {
     switch (K::surf(R)) {
         case RTT_SURF_PLANE: {                                          // :124-136
             const float safe = (fabsf(d.z) < 1e-6f) ? 1e-8f : d.z;
-            q.t1 = div0_(-o.z, safe); q.t2 = inf; q.n = 1; q.B = safe;
+            q.t1 = div_(-o.z, safe); q.t2 = inf; q.n = 1; q.B = safe;
             return q;
         }
         case RTT_SURF_SPHERE: {                                         // :155-184 (a == 1 assumed)
@@ -309,8 +298,8 @@ RTT_HD Roots solve_roots(const RowDev& R, V3 o, V3 d) {
                 q.t1 = ok ? (n1 > 0.0f ? inf : (n1 < 0.0f ? -inf : rtt_nan())) : inf;
                 q.t2 = ok ? (n2 > 0.0f ? inf : (n2 < 0.0f ? -inf : rtt_nan())) : inf;
             } else {
-                q.t1 = ok ? div0_(-B - sq, den) : inf;
-                q.t2 = ok ? div0_(-B + sq, den) : inf;
+                q.t1 = ok ? div_(-B - sq, den) : inf;
+                q.t2 = ok ? div_(-B + sq, den) : inf;
             }
             q.A = A; q.B = B; q.C = Cq; q.sq = sq;
             return q;
@@ -352,7 +341,7 @@ RTT_HD Roots solve_roots(const RowDev& R, V3 o, V3 d) {
             const float sq = sqrt_(fabsf(disc));
             const float As = lin ? 1.0f : A;
             const float den = 2.0f * As;
-            const float r1 = div0_(-B - sq, den), r2 = div0_(-B + sq, den);
+            const float r1 = div_(-B - sq, den), r2 = div_(-B + sq, den);
             const float Bs = (fabsf(B) < 1e-6f) ? 1e-6f : B;
             const float tl = lin ? div_(-Cq, Bs) : 0.0f;
             q.t1 = lin ? tl : (ok ? r1 : inf);
