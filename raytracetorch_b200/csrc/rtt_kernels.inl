@@ -388,9 +388,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_tile(const __g
                 const RayIn ray = fetch_ray(a, skey, i, L > 0);
                 p[j] = ray.p; d[j] = ray.d; I[j] = ray.I;
                 lam[j] = (L > 0) ? wavelength_index(T, L, ray.wav) : 0;
-                const bool fin = finite_ray(ray.p, ray.d);              // non-finite rays pass through untouched
-                act[j] = fin && regular_dir(ray.d);
-                odd[j] = fin && !act[j];
+                act[j] = finite_ray(ray.p, ray.d) && regular_dir(ray.d);
+                odd[j] = !act[j];                                       // re-read below: un-normalised or non-finite ray
             }
         }
         unsigned long long bit = 1ull;
@@ -426,11 +425,12 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_tile(const __g
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
             const long long i = i0 + (long long)j * kThreads;
-            if (odd[j]) {                                               // un-normalised direction: reference order
+            if (odd[j]) {
+                // un-normalised direction: walk in the reference's order; NaN / inf ray: hits nothing, stays as it was
                 const RayIn ray = fetch_ray(a, skey, i, L > 0);
                 WalkState w;
                 w.p = ray.p; w.d = ray.d; w.I = ray.I; w.mask = 0ull;
-                w = seq_walk_generic(a, lam[j], i, w);
+                if (finite_ray(ray.p, ray.d)) w = seq_walk_generic(a, lam[j], i, w);
                 p[j] = w.p; d[j] = w.d; I[j] = w.I; mask[j] = w.mask;
             }
             if (i < a.n) {

@@ -483,8 +483,11 @@ def test_fast_tile_path_edge_cases(run_fast):
     assert parity.vec_rel(h["dir"][live], od[live]).max() <= parity.TOL_POINT
     np.testing.assert_array_equal(parity.mask_bits(h["hitmask"], tf.shape[0])[live], o["hit"].numpy()[live])
     assert parity.vec_rel(h["pos"][5:6], op[5:6]).max() <= parity.TOL_POINT     # far off axis: only the stop plane takes it
-    # NaN position: NaN fails every bound test, which the INVERTED stop turns into a hit — like the reference
+    # NaN position: the reference's matmul poses spread the NaN to every component, so the ray hits nothing and is
+    # returned exactly as it came in (the finite components bit for bit)
     np.testing.assert_array_equal(parity.mask_bits(h["hitmask"], tf.shape[0])[9], o["hit"].numpy()[9])
+    np.testing.assert_array_equal(h["pos"][9], pos[9])
+    np.testing.assert_array_equal(h["dir"][9], dr[9])
     assert odd[live].sum() > 100                       # the irregular path was really exercised on live rays
     for m in (1, 2, 31, 33, 255, 257, 513):
         hh = run_fast.trace_seq(tf, ti, pos[:m], dr[:m], inten[:m])
