@@ -475,7 +475,8 @@ def run_gpu_arm(args):
                 p.grad = None
             tab = scene.table()
             o = rtt.ops.trace_sequential(tab, pos, dirs, inten, wav, want_record=False, sensor_cfg=[])
-            loss = (o["intensity"] * (o["pos"][:, 0] ** 2 + o["pos"][:, 1] ** 2)).sum()
+            xy = o["pos"][:, :2]
+            loss = torch.dot(o["intensity"], (xy * xy).sum(1))          # sum_i I_i (x_i^2 + y_i^2), 3 kernels forward
             loss.backward()
             if world > 1:
                 red = rdist.FlatReducer()
