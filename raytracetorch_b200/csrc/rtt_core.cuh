@@ -408,6 +408,13 @@ RTT_HD bool shape_in_bounds(const RowDev* rows, int r, V3 h) {
         }
         case RTT_SHAPE_POLY: {                                          // geom/shape.py:122-132
             const int first = R.i[RTT_I_POLY_FIRST], cnt = R.i[RTT_I_POLY_COUNT];
+            if (R.f[D_SB0SQ] > 0.0f) {
+                // a verified box (non-sequential kernel staging, rtt_tile.cuh::box_cull_info): a point that passes the
+                // sibling half-space tests lies in the box inflated by 1e-4, hence inside its bounding sphere — a point
+                // outside the sphere fails them, without evaluating the five planes
+                const float ux = h.x - R.f[RTT_F_C], uy = h.y - R.f[RTT_F_K], uz = h.z - R.f[RTT_F_RADIUS];
+                if ((ux * ux + uy * uy) + uz * uz > R.f[D_SB0SQ]) return false;
+            }
             bool ok = true;
             for (int m = first; m < first + cnt; ++m) {
                 if (m == r) continue;

@@ -752,6 +752,17 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
         T.rows[r].f[D_SAME_ELEM] = same ? 1.0f : 0.0f;
     }
     __syncthreads();
+    // verified boxes: the element-frame bounding sphere goes into scalar slots a box face (plane, no surface bound)
+    // does not use, where shape_in_bounds finds it (rows are this block's private copy)
+    for (int r = threadIdx.x; r < S; r += blockDim.x) {
+        if (cull[r].run != 6) continue;
+        for (int f = 0; f < 6; ++f) {
+            RowDev& B = T.rows[r + f];
+            B.f[RTT_F_C] = cull[r].ex; B.f[RTT_F_K] = cull[r].ey; B.f[RTT_F_RADIUS] = cull[r].ez;
+            B.f[D_SB0SQ] = cull[r].r2;
+        }
+    }
+    __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
     const SourceKey skey = fetch_key(a);
     // Lane refill: rays of a warp need different numbers of bounces (absorbed, escaped, still bouncing), so a lane

@@ -224,20 +224,21 @@ RTT_HD bool edge_culled(const Xf& x, V3 p, V3 d) {
 // derived from the face planes themselves and kept in the GLOBAL frame (the non-sequential state's frame).
 struct NsCull {
     int32_t run;             // > 0 at the first row of a verified box: rows [r, r + run) can be skipped together
-    float cx, cy, cz, r2;
-    int32_t pad[3];
+    float cx, cy, cz, r2;    // bounding sphere, global frame
+    float ex, ey, ez;        // its centre in the element frame (shape_in_bounds works there)
 };
 
 RTT_HD NsCull box_cull_info(const RowDev* rows, int S, int r) {
     NsCull c;
-    c.run = 0; c.cx = c.cy = c.cz = c.r2 = 0.0f; c.pad[0] = c.pad[1] = c.pad[2] = 0;
+    c.run = 0; c.cx = c.cy = c.cz = c.r2 = 0.0f; c.ex = c.ey = c.ez = 0.0f;
     const RowDev& R0 = rows[r];
     if (R0.i[RTT_I_SHAPE] != RTT_SHAPE_POLY || R0.i[RTT_I_POLY_FIRST] != r || R0.i[RTT_I_POLY_COUNT] != 6 || r + 6 > S)
         return c;
     V3 n[6]; float off[6];
     for (int f = 0; f < 6; ++f) {
         const RowDev& R = rows[r + f];
-        if (R.i[RTT_I_SURF] != RTT_SURF_PLANE || R.i[RTT_I_SHAPE] != RTT_SHAPE_POLY || R.i[RTT_I_POLY_FIRST] != r) return c;
+        if (R.i[RTT_I_SURF] != RTT_SURF_PLANE || R.i[RTT_I_SHAPE] != RTT_SHAPE_POLY || R.i[RTT_I_POLY_FIRST] != r ||
+            R.i[RTT_I_BOUND] != RTT_BOUND_NONE || R.i[RTT_I_PHYS] == RTT_PHYS_LINEAR) return c;
         n[f] = v3(R.f[RTT_F_RS + 2], R.f[RTT_F_RS + 5], R.f[RTT_F_RS + 8]);     // plane normal (third column of Rs)
         off[f] = dot(n[f], ld3(R.f + RTT_F_TS));                                 // signed offset of the plane
     }
@@ -274,6 +275,7 @@ RTT_HD NsCull box_cull_info(const RowDev* rows, int S, int r) {
     const V3 cg = mul_RT(ce, R0.f + RTT_F_RE) + ld3(R0.f + RTT_F_TE);            // element -> global
     if (!(rad == rad) || !((cg.x + cg.y + cg.z) - (cg.x + cg.y + cg.z) == 0.0f)) return c;
     c.run = 6; c.cx = cg.x; c.cy = cg.y; c.cz = cg.z; c.r2 = rad * rad;
+    c.ex = ce.x; c.ey = ce.y; c.ez = ce.z;
     return c;
 }
 
