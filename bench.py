@@ -500,6 +500,46 @@ def run_gpu_arm(args):
                   launches=lib.launch_count() - l0,
                   note="trace forward + loss (torch elementwise) + hand-written adjoint kernel + table->Parameter "
                        "autograd; interactions counted once per ray and row")
+
+        # the same step with the reference's own goal (optim/goals.py:99-187) through the public API: the loss is
+        # evaluated on the sensor records by the fused goal kernels instead of eager torch ops on the final rays
+        ids = torch.zeros(n, dtype=torch.int8, device=dev)
+        wav_r = wav if wav is not None else torch.zeros(n, device=dev)
+
+        class ResidentBundle(rtt.rays.Bundle):
+            def sample(self, N):
+                return rtt.rays.Rays._wrap(pos=pos, dir=dirs, intensity=inten, id=ids, wavelength=wav_r)
+
+        goal = rtt.optim.SpotSizeLoss(w["sensor"], [ResidentBundle(0, device=dev)], N_rays=n,
+                                      target_xy=torch.zeros(2))
+
+        def goal_step():
+            for p in opt_params:
+                p.grad = None
+            loss = goal(scene)
+            loss.backward()
+            if world > 1:
+                rdist.allreduce_scene_results([], opt_params)
+            return loss
+
+        for _ in range(max(args.warmup, 1)):
+            goal_step()
+        barrier()
+        l0 = lib.launch_count()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            goal_step()
+        f1.record()
+        barrier()
+        fg_ms = max_over_ranks(f0.elapsed_time(f1) / args.steps)
+        fb["goal"] = dict(value=world * n_fb * S / (fg_ms / 1e3), unit=UNIT, ms_per_step=fg_ms,
+                          launches=lib.launch_count() - l0,
+                          api="SpotSizeLoss(sensor, [bundle], N, target_xy)(scene); loss.backward()",
+                          note="same step with the goal evaluated by the fused record reductions (rtt_spot_*)")
+        scene.last_trace = None
+        w["sensor"].reset()
+        del goal, ids
         for p in opt_params:
             p.requires_grad_(False)
             p.grad = None

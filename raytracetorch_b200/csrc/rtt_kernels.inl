@@ -585,23 +585,44 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
       if (compact) {
         if (threadIdx.x == 0) *qcount = 0;
         __syncthreads();
-        // pass 1: which of this thread's rays matter (independent loads, all in flight together)
+        // pass 1: which of this thread's rays matter.  Four rays at a time, every load of the group issued before the
+        // first is consumed: the hit mask does not gate the gradient loads (a dependent second round trip to DRAM per
+        // ray, with the whole block waiting at the barrier below, was a quarter of this kernel's warp time).
         unsigned needs = 0u;
+        constexpr int kGroup = 4;
 #pragma unroll
-        for (int k = 0; k < kBwdChunk / kThreads; ++k) {
-            const int loc = k * kThreads + threadIdx.x;
-            const long long i = base + loc;
-            bool need = false;
-            if (loc < count && a.hitmask[i] != 0ull) {
-                if (a.g_opos) { const V3 g = load3(a.g_opos, i); need = need || g.x != 0.0f || g.y != 0.0f || g.z != 0.0f; }
-                if (a.g_odir) { const V3 g = load3(a.g_odir, i); need = need || g.x != 0.0f || g.y != 0.0f || g.z != 0.0f; }
-                for (int sl = 0; sl < a.n_sens; ++sl)
-                    if (a.g_record[sl]) {
-                        const float4 gr = reinterpret_cast<const float4*>(a.g_record[sl])[i];
-                        need = need || gr.x != 0.0f || gr.y != 0.0f || gr.z != 0.0f;
-                    }
+        for (int k0 = 0; k0 < kBwdChunk / kThreads; k0 += kGroup) {
+            unsigned long long hm[kGroup];
+            V3 ga[kGroup], gb[kGroup];
+            float4 gr[kGroup];
+            bool ok[kGroup];
+#pragma unroll
+            for (int j = 0; j < kGroup; ++j) {
+                const int loc = (k0 + j) * kThreads + threadIdx.x;
+                ok[j] = loc < count;
+                const long long i = base + (ok[j] ? loc : 0);
+                hm[j] = a.hitmask[i];
+                ga[j] = a.g_opos ? load3(a.g_opos, i) : v3(0.0f, 0.0f, 0.0f);
+                gb[j] = a.g_odir ? load3(a.g_odir, i) : v3(0.0f, 0.0f, 0.0f);
+                gr[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (a.n_sens > 0 && a.g_record[0]) gr[j] = reinterpret_cast<const float4*>(a.g_record[0])[i];
             }
-            needs |= (need ? 1u : 0u) << k;
+#pragma unroll
+            for (int j = 0; j < kGroup; ++j) {
+                bool need = ga[j].x != 0.0f || ga[j].y != 0.0f || ga[j].z != 0.0f ||
+                            gb[j].x != 0.0f || gb[j].y != 0.0f || gb[j].z != 0.0f ||
+                            gr[j].x != 0.0f || gr[j].y != 0.0f || gr[j].z != 0.0f;
+                if (ok[j] && hm[j] != 0ull && !need) {                   // further sensors (rare): dependent loads
+                    const long long i = base + (k0 + j) * kThreads + threadIdx.x;
+                    for (int sl = 1; sl < a.n_sens; ++sl)
+                        if (a.g_record[sl]) {
+                            const float4 g2 = reinterpret_cast<const float4*>(a.g_record[sl])[i];
+                            need = need || g2.x != 0.0f || g2.y != 0.0f || g2.z != 0.0f;
+                        }
+                }
+                need = need && ok[j] && hm[j] != 0ull;
+                needs |= (need ? 1u : 0u) << (k0 + j);
+            }
         }
         // pass 2: append them to the block's queue (warp-aggregated)
         for (int k = 0; k < chunk / kThreads; ++k) {

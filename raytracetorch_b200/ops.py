@@ -572,6 +572,7 @@ class _TraceSeq(torch.autograd.Function):
         ctx.save_for_backward(pos, dir_, intensity, wavelength, hitmask, table_f, table_i, lut, lut_w)
         ctx.mode = mode
         ctx.mark_non_differentiable(hitmask, images)
+        ctx.set_materialize_grads(False)     # unused outputs hand None to backward, not [N,3] zero tensors
         return opos, odir, oint, hitmask, records, images
 
     @staticmethod
@@ -600,6 +601,7 @@ class _TraceNonseq(torch.autograd.Function):
         ctx.save_for_backward(pos, dir_, intensity, wavelength, seq, table_f, table_i, lut, lut_w)
         ctx.mode = mode
         ctx.mark_non_differentiable(seq, nh, images, counts)
+        ctx.set_materialize_grads(False)     # unused outputs hand None to backward, not [N,3] zero tensors
         return opos, odir, oint, seq, nh, records, images, counts
 
     @staticmethod
@@ -629,6 +631,7 @@ class _TraceSeqSrc(torch.autograd.Function):
         ctx.save_for_backward(pose, state, hitmask, table_f, table_i, lut, lut_w)
         ctx.src_cfg, ctx.n, ctx.mode, ctx.want_rays = list(src_cfg), n, mode, want_rays
         ctx.mark_non_differentiable(hitmask, images)
+        ctx.set_materialize_grads(False)     # unused outputs hand None to backward, not [N,3] zero tensors
         return opos, odir, oint, hitmask, records, images
 
     @staticmethod
@@ -655,6 +658,7 @@ class _TraceNonseqSrc(torch.autograd.Function):
         ctx.save_for_backward(pose, state, seq, table_f, table_i, lut, lut_w)
         ctx.src_cfg, ctx.n, ctx.mode, ctx.want_rays = list(src_cfg), n, mode, want_rays
         ctx.mark_non_differentiable(seq, nh, images, counts)
+        ctx.set_materialize_grads(False)     # unused outputs hand None to backward, not [N,3] zero tensors
         return opos, odir, oint, seq, nh, records, images, counts
 
     @staticmethod

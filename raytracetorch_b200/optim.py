@@ -94,7 +94,10 @@ def _sensor_records(scene, sensor: Sensor):
     table = getattr(scene, "_last_table", None) or scene.table()
     if sensor not in table.sensors:
         return None
-    return tr["records"][table.sensors.index(sensor)].reshape(-1, 4)
+    recs = tr["records"]
+    if recs.shape[0] == 1:          # one sensor: a view whose backward is a view too (select's backward would
+        return recs.reshape(-1, 4)  # allocate and fill a zero tensor of the records' size first)
+    return recs[table.sensors.index(sensor)].reshape(-1, 4)
 
 
 class _goal_trace:
