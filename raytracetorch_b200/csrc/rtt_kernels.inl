@@ -699,9 +699,10 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
             const int slot = (int)R.f[D_ACC_SLOT];
             if (a.g_table && flags && slot >= 0) {
                 if (hit) {                                               // G is zero where nothing was requested
-                    float* pa = pacc + slot * kAccPerRow;
-                    pa[0] += G.g[RTT_F_C]; pa[1] += G.g[RTT_F_K]; pa[2] += G.g[RTT_F_RADIUS];
-                    pa[3] += G.g[RTT_F_IOR_IN]; pa[4] += G.g[RTT_F_IOR_OUT];
+                    float* pa = pacc + slot * kAccPerRow;                // only the requested entries: each is a
+                    if (flags & RTT_FLAG_GRAD_CK) { pa[0] += G.g[RTT_F_C]; pa[1] += G.g[RTT_F_K]; }   // local-memory
+                    if (flags & RTT_FLAG_GRAD_RADIUS) pa[2] += G.g[RTT_F_RADIUS];                      // read-modify-write
+                    if (flags & RTT_FLAG_GRAD_IOR) { pa[3] += G.g[RTT_F_IOR_IN]; pa[4] += G.g[RTT_F_IOR_OUT]; }
                 }
             } else if (a.g_table && flags) {
                 if (L > 0 && (flags & RTT_FLAG_GRAD_IOR)) {
