@@ -731,7 +731,8 @@ def run_c3(args):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         torch.ops.rtt_b200.trace_seq_bwd(rays.pos, rays.dir, rays.intensity, None, fwd[3], None, None, None, g_rec,
-                                         tab.f.detach(), tab.i, None, None, False, True, rtt.ops.get_default_mode())
+                                         tab.f.detach(), tab.i, None, None, False, True,
+                                         rtt.ops.get_default_mode() | rtt.ops.adjoint_hint(tab))
         b.record()
         torch.cuda.synchronize()
         kt.append(a.elapsed_time(b))

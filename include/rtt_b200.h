@@ -73,6 +73,11 @@ enum { RTT_OK = 0, RTT_E_ARG = -1, RTT_E_ROWS = -2, RTT_E_NO_DEVICE = -3, RTT_E_
  * multiplies; EXACT keeps every rounding step of the reference's eager fp32 ops (separately
  * rounded mul/add, IEEE div/sqrt) — used by the parity tests to get bit-exact masks. */
 enum { RTT_MODE_FAST = 0, RTT_MODE_EXACT = 1 };
+/* Optional hint OR-ed into `mode` of rtt_trace_seq_bwd: the caller guarantees that no row of the table requests
+ * pose gradients (RTT_FLAG_GRAD_POSE_E / _POSE_S) — the usual lens-design case (curvatures, conic constants, radii,
+ * indices).  The adjoint then runs a build without the pose-gradient code (72 instead of 80+ registers, four blocks
+ * per SM); pose flags present in the table are ignored under this hint.  Every other entry ignores the bit. */
+enum { RTT_MODE_SCALAR_GRADS = 0x100, RTT_MODE_ARITH_MASK = 0xff };
 
 /* Sensor image request for one sensor slot.  Bin rule (restating the fixed-range
  * histogram of gui/workbench.py:615-624 in fp32):
@@ -163,7 +168,8 @@ int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_
  *   g_in_*      : gradients w.r.t. the input rays (NULL to skip)
  *   g_table     : [n_rows, RTT_ROW_G] fp32, ACCUMULATED into (caller zeroes); entries
  *                 [0, RTT_N_DIFF) are d/d table_f; NULL to skip
- *   g_lut       : [L, n_rows, 2] accumulated gradient of the wavelength LUT, or NULL        */
+ *   g_lut       : [L, n_rows, 2] accumulated gradient of the wavelength LUT, or NULL
+ *   mode        : RTT_MODE_FAST / RTT_MODE_EXACT, optionally | RTT_MODE_SCALAR_GRADS             */
 int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float* in_intensity,
                       const float* in_wavelength, const rtt_source_t* source, const uint64_t* hitmask,
                       const float* g_out_pos, const float* g_out_dir, const float* g_out_intensity,

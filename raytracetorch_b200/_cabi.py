@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librtt_b200.so")
 
 MODE_FAST, MODE_EXACT = 0, 1
+MODE_SCALAR_GRADS = 0x100   # hint for rtt_trace_seq_bwd (include/rtt_b200.h): no row requests pose gradients
 
 
 class RttLibraryMissing(RuntimeError):

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) k_probe_fp32(int iters, float* out) {
     if (s == 123.456f) out[0] = s;                                      // keeps the chains alive
 }
 
-#define RTT_DISPATCH(mode, call_fast, call_exact) ((mode) == RTT_MODE_EXACT ? (call_exact) : (call_fast))
+#define RTT_DISPATCH(mode, call_fast, call_exact) (((mode) & RTT_MODE_ARITH_MASK) == RTT_MODE_EXACT ? (call_exact) : (call_fast))
 
 extern "C" {
 
@@ -176,7 +176,7 @@ int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_
         a.n_sens = n_sensors; a.n = n;                                                                 \
         return finish(rtt::NS::launch_seq_fwd_##NS(a, st));                                            \
     }
-    if (mode == RTT_MODE_EXACT) RTT_BODY(exact) else RTT_BODY(fast)
+    if ((mode & RTT_MODE_ARITH_MASK) == RTT_MODE_EXACT) RTT_BODY(exact) else RTT_BODY(fast)
 #undef RTT_BODY
 }
 
@@ -211,9 +211,10 @@ int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float* in_
         a.g_table = g_table; a.g_lut = (table->n_lut > 0) ? g_lut : nullptr;                           \
         a.tab = make_table<rtt::NS::TableDev>(table);                                                  \
         a.n_sens = n_sensors; a.n = n;                                                                 \
+        a.scalar_grads = (mode & RTT_MODE_SCALAR_GRADS) ? 1 : 0;                                       \
         return finish(rtt::NS::launch_seq_bwd_##NS(a, st));                                            \
     }
-    if (mode == RTT_MODE_EXACT) RTT_BODY(exact) else RTT_BODY(fast)
+    if ((mode & RTT_MODE_ARITH_MASK) == RTT_MODE_EXACT) RTT_BODY(exact) else RTT_BODY(fast)
 #undef RTT_BODY
 }
 
@@ -304,7 +305,7 @@ int rtt_sample_bundle(const rtt_source_t* source, float* pos, float* dir, float*
         a.pos = pos; a.dir = dir; a.inten = intensity; a.wav = wavelength; a.n = n;                    \
         return finish(rtt::NS::launch_sample_##NS(a, st));                                             \
     }
-    if (mode == RTT_MODE_EXACT) RTT_BODY(exact) else RTT_BODY(fast)
+    if ((mode & RTT_MODE_ARITH_MASK) == RTT_MODE_EXACT) RTT_BODY(exact) else RTT_BODY(fast)
 #undef RTT_BODY
 }
 
@@ -325,7 +326,7 @@ int rtt_intersect_test(const float* in_pos, const float* in_dir, float* t_out,
         a.row0 = row0; a.k = k; a.n = n;                                                               \
         return finish(rtt::NS::launch_intersect_test_##NS(a, st));                                     \
     }
-    if (mode == RTT_MODE_EXACT) RTT_BODY(exact) else RTT_BODY(fast)
+    if ((mode & RTT_MODE_ARITH_MASK) == RTT_MODE_EXACT) RTT_BODY(exact) else RTT_BODY(fast)
 #undef RTT_BODY
 }
 
@@ -351,7 +352,7 @@ int rtt_surface_step_fwd(const float* in_pos, const float* in_dir, const float* 
         a.row = row; a.n = n;                                                                          \
         return finish(rtt::NS::launch_step_fwd_##NS(a, st));                                           \
     }
-    if (mode == RTT_MODE_EXACT) RTT_BODY(exact) else RTT_BODY(fast)
+    if ((mode & RTT_MODE_ARITH_MASK) == RTT_MODE_EXACT) RTT_BODY(exact) else RTT_BODY(fast)
 #undef RTT_BODY
 }
 
@@ -380,7 +381,7 @@ int rtt_surface_step_bwd(const float* in_pos, const float* in_dir, const float* 
         a.row = row; a.n = n;                                                                          \
         return finish(rtt::NS::launch_step_bwd_##NS(a, st));                                           \
     }
-    if (mode == RTT_MODE_EXACT) RTT_BODY(exact) else RTT_BODY(fast)
+    if ((mode & RTT_MODE_ARITH_MASK) == RTT_MODE_EXACT) RTT_BODY(exact) else RTT_BODY(fast)
 #undef RTT_BODY
 }
 

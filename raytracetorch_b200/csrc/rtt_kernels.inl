@@ -547,7 +547,9 @@ constexpr int kAccRows = 12, kAccPerRow = 5;      // private gradient slots: row
 constexpr int kBwdChunk = 16 * kThreads;   // large enough that the compacted chunk still fills whole blocks of warps
 __host__ __device__ inline size_t bwd_queue_bytes() { return sizeof(unsigned short) * kBwdChunk + 16; }
 
-template <int MINB>
+// POSE = false: the caller guarantees that no row requests pose gradients (RTT_MODE_SCALAR_GRADS); the pose-gradient
+// outer products and their 24 accumulator registers per row are compiled out.
+template <int MINB, bool POSE>
 __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(const __grid_constant__ SeqBwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.tab.S, L = a.tab.L;
@@ -682,7 +684,8 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
             const bool hit = (mask >> r) & 1ull;
             if (__ballot_sync(kFull, hit) == 0u) continue;
             const RowDev& R = T.rows[r];
-            const int flags = R.i[RTT_I_FLAGS];
+            const int flags = POSE ? R.i[RTT_I_FLAGS]
+                                   : (R.i[RTT_I_FLAGS] & ~(RTT_FLAG_GRAD_POSE_E | RTT_FLAG_GRAD_POSE_S));
             const int op = R.i[DI_OPCODE];
             RowGrad G;
             zero(G);
@@ -1154,7 +1157,7 @@ inline int bwd_minb_choice() {
 cudaError_t RTT_NAME(launch_seq_bwd)(const SeqBwdArgs& a, cudaStream_t st) {
     const size_t smem = bwd_smem(a.tab.S, a.tab.L) + 8 + bwd_queue_bytes();
     // chunk: as large as the queue allows, but small launches still spread over every resident block slot
-    const long long slots = (long long)(sm_count() > 0 ? sm_count() : 1) * 3 * 2;
+    const long long slots = (long long)(sm_count() > 0 ? sm_count() : 1) * 4 * 2;
     long long chunk = ((a.n + slots - 1) / slots + kThreads - 1) / kThreads * kThreads;
     if (chunk < 4 * kThreads) chunk = 4 * kThreads;
     if (chunk > kBwdChunk) chunk = kBwdChunk;
@@ -1164,8 +1167,17 @@ cudaError_t RTT_NAME(launch_seq_bwd)(const SeqBwdArgs& a, cudaStream_t st) {
     long long g = (long long)sm_count() * 8;
     if (chunks < g) g = chunks;
     if (g < 1) g = 1;
-    if (bwd_minb_choice() == 3) RTT_NAME(k_trace_seq_bwd)<3><<<(int)g, kThreads, smem, st>>>(b);
-    else RTT_NAME(k_trace_seq_bwd)<2><<<(int)g, kThreads, smem, st>>>(b);
+    // without pose gradients the kernel needs 64-72 registers: four resident blocks (measured: C2 -10 %, C4 -5 % against
+    // three; RTT_BWD_MINB=3 selects the 72-register build)
+    static int minb_env = -1;
+    if (minb_env < 0) { const char* e = getenv("RTT_BWD_MINB"); minb_env = e ? atoi(e) : 0; }
+    if (a.scalar_grads) {
+        if (minb_env == 3) RTT_NAME(k_trace_seq_bwd)<3, false><<<(int)g, kThreads, smem, st>>>(b);
+        else RTT_NAME(k_trace_seq_bwd)<4, false><<<(int)g, kThreads, smem, st>>>(b);
+    } else {
+        if (bwd_minb_choice() == 3) RTT_NAME(k_trace_seq_bwd)<3, true><<<(int)g, kThreads, smem, st>>>(b);
+        else RTT_NAME(k_trace_seq_bwd)<2, true><<<(int)g, kThreads, smem, st>>>(b);
+    }
     return cudaGetLastError();
 }
 cudaError_t RTT_NAME(launch_nonseq_fwd)(const NonseqFwdArgs& a, cudaStream_t st) {

@@ -71,6 +71,7 @@ struct SeqBwdArgs {
     int n_sens;
     long long n;
     int chunk;                  // rays per block iteration (set by the launcher, <= kBwdChunk)
+    int scalar_grads;           // RTT_MODE_SCALAR_GRADS: no row requests pose gradients
 };
 
 struct NonseqFwdArgs {

@@ -19,6 +19,7 @@ from . import _cabi, codes as C
 from .table import SurfaceTable, compile_elements
 
 MODE_FAST, MODE_EXACT = _cabi.MODE_FAST, _cabi.MODE_EXACT
+MODE_SCALAR_GRADS = _cabi.MODE_SCALAR_GRADS
 # Arithmetic defaults.  Sequential traces: FAST (FMA contraction; masks verified identical to
 # the reference on every fixture, points within 1e-5).  Non-sequential traces: EXACT — the
 # reference's t > 1e-6 self-intersection rule sits at the fp32 ulp of scene-scale coordinates,
@@ -565,12 +566,13 @@ class _TraceSeq(torch.autograd.Function):
     """forward = rtt_trace_seq_fwd, backward = rtt_trace_seq_bwd (hand-written adjoint)."""
 
     @staticmethod
-    def forward(ctx, pos, dir_, intensity, wavelength, table_f, table_i, lut, lut_w, sensor_cfg, want_record, mode):
+    def forward(ctx, pos, dir_, intensity, wavelength, table_f, table_i, lut, lut_w, sensor_cfg, want_record, mode,
+                bwd_hint=0):
         outs = torch.ops.rtt_b200.trace_seq_fwd(pos, dir_, intensity, wavelength, table_f, table_i, lut, lut_w,
                                                 sensor_cfg, want_record, mode)
         opos, odir, oint, hitmask, records, images = outs
         ctx.save_for_backward(pos, dir_, intensity, wavelength, hitmask, table_f, table_i, lut, lut_w)
-        ctx.mode = mode
+        ctx.mode = mode | bwd_hint
         ctx.mark_non_differentiable(hitmask, images)
         ctx.set_materialize_grads(False)     # unused outputs hand None to backward, not [N,3] zero tensors
         return opos, odir, oint, hitmask, records, images
@@ -588,7 +590,7 @@ class _TraceSeq(torch.autograd.Function):
         return (gp if ctx.needs_input_grad[0] else None, gd if ctx.needs_input_grad[1] else None,
                 gi if ctx.needs_input_grad[2] else None, None,
                 _pad_table_grad(gt, table_f) if ctx.needs_input_grad[4] else None, None,
-                gl if ctx.needs_input_grad[6] else None, None, None, None, None)
+                gl if ctx.needs_input_grad[6] else None, None, None, None, None, None)
 
 
 class _TraceNonseq(torch.autograd.Function):
@@ -624,12 +626,13 @@ class _TraceSeqSrc(torch.autograd.Function):
     """Sequential trace of in-kernel generated rays; only the table (and LUT) receive gradients."""
 
     @staticmethod
-    def forward(ctx, src_cfg, pose, state, n, table_f, table_i, lut, lut_w, sensor_cfg, want_record, want_rays, mode):
+    def forward(ctx, src_cfg, pose, state, n, table_f, table_i, lut, lut_w, sensor_cfg, want_record, want_rays, mode,
+                bwd_hint=0):
         outs = torch.ops.rtt_b200.trace_seq_src_fwd(src_cfg, pose, state, n, table_f, table_i, lut, lut_w,
                                                     sensor_cfg, want_record, want_rays, mode)
         opos, odir, oint, hitmask, records, images = outs
         ctx.save_for_backward(pose, state, hitmask, table_f, table_i, lut, lut_w)
-        ctx.src_cfg, ctx.n, ctx.mode, ctx.want_rays = list(src_cfg), n, mode, want_rays
+        ctx.src_cfg, ctx.n, ctx.mode, ctx.want_rays = list(src_cfg), n, mode | bwd_hint, want_rays
         ctx.mark_non_differentiable(hitmask, images)
         ctx.set_materialize_grads(False)     # unused outputs hand None to backward, not [N,3] zero tensors
         return opos, odir, oint, hitmask, records, images
@@ -645,7 +648,7 @@ class _TraceSeqSrc(torch.autograd.Function):
             ctx.src_cfg, pose, state, ctx.n, hitmask, _cg(g_pos), _cg(g_dir), _cg(g_int), _cg(g_records),
             table_f, table_i, lut, lut_w, True, ctx.mode)
         return (None, None, None, None, _pad_table_grad(gt, table_f) if ctx.needs_input_grad[4] else None, None,
-                gl if ctx.needs_input_grad[6] else None, None, None, None, None, None)
+                gl if ctx.needs_input_grad[6] else None, None, None, None, None, None, None)
 
 
 class _TraceNonseqSrc(torch.autograd.Function):
@@ -791,6 +794,13 @@ def _prep_rays(pos, dir_, intensity, wavelength, table: SurfaceTable):
     return pos, dir_, intensity, wav
 
 
+def adjoint_hint(table: SurfaceTable) -> int:
+    """``MODE_SCALAR_GRADS`` when no row of ``table`` requests pose gradients (read from the host copy of the int
+    block), else 0: OR-ed into the mode of the sequential adjoint, which then runs its build without pose-gradient code."""
+    pose = C.FLAG_GRAD_POSE_E | C.FLAG_GRAD_POSE_S
+    return 0 if any(m[C.I_FLAGS] & pose for m in table.i_host) else MODE_SCALAR_GRADS
+
+
 def trace_sequential(table: SurfaceTable, pos=None, dir_=None, intensity=None, wavelength=None, *, want_record=True,
                      sensor_cfg: Optional[List[float]] = None, mode: Optional[int] = None, source=None,
                      want_rays: bool = True):
@@ -802,16 +812,18 @@ def trace_sequential(table: SurfaceTable, pos=None, dir_=None, intensity=None, w
     records [n_sensors,N,4] (hit_local xyz, weight-before), images [per sensor: [C,H,W] or None])."""
     cfg = sensor_cfg_of(table) if sensor_cfg is None else list(sensor_cfg)
     mode = _default_mode if mode is None else mode
+    hint = adjoint_hint(table)
     if source is not None:
         _need_cuda(table.f)
         opos, odir, oint, hitmask, records, images = _TraceSeqSrc.apply(
             source_cfg_of(source), source.pose, source.state, source.n, table.f, table.i, table.lut,
-            table.lut_wavelengths, cfg, bool(want_record), bool(want_rays), mode)
+            table.lut_wavelengths, cfg, bool(want_record), bool(want_rays), mode, hint)
         return dict(pos=opos, dir=odir, intensity=oint, hitmask=hitmask, records=records,
                     images=split_images(images, cfg))
     pos, dir_, intensity, wav = _prep_rays(pos, dir_, intensity, wavelength, table)
     opos, odir, oint, hitmask, records, images = _TraceSeq.apply(
-        pos, dir_, intensity, wav, table.f, table.i, table.lut, table.lut_wavelengths, cfg, bool(want_record), mode)
+        pos, dir_, intensity, wav, table.f, table.i, table.lut, table.lut_wavelengths, cfg, bool(want_record), mode,
+        hint)
     return dict(pos=opos, dir=odir, intensity=oint, hitmask=hitmask, records=records,
                 images=split_images(images, cfg))
 

@@ -39,7 +39,8 @@ g_int = (opos[:, :2] ** 2).sum(1)
 
 def bwd():
     return torch.ops.rtt_b200.trace_seq_bwd(pos, dirs, inten, wav, hitmask, g_pos, None, g_int, None, tab.f.detach(),
-                                            tab.i, tab.lut, tab.lut_wavelengths, False, True, mode)
+                                            tab.i, tab.lut, tab.lut_wavelengths, False, True,
+                                            mode | rtt.ops.adjoint_hint(tab))
 
 
 ts = []
@@ -50,6 +51,30 @@ for k in range(8):
     ts.append(a.elapsed_time(b))
 gt = out[3]
 print(f"{wl} n={n} adjoint kernel ms: median {np.median(ts[2:]):.3f} min {min(ts):.3f}  |g_table| {float(gt.abs().sum()):.6e}")
+
+if "--goal" in sys.argv:
+    ids = torch.zeros(n, dtype=torch.int8, device=dev)
+    wav_r = wav if wav is not None else torch.zeros(n, device=dev)
+
+    class ResidentBundle(rtt.rays.Bundle):
+        def sample(self, N):
+            return rtt.rays.Rays._wrap(pos=pos, dir=dirs, intensity=inten, id=ids, wavelength=wav_r)
+
+    goal = rtt.optim.SpotSizeLoss(w["sensor"], [ResidentBundle(0, device=dev)], N_rays=n, target_xy=torch.zeros(2))
+
+    def gstep():
+        for p in params:
+            p.grad = None
+        goal(scene).backward()
+    for _ in range(3):
+        gstep()
+    torch.cuda.synchronize()
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(3):
+            gstep()
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=90))
 
 if "--profile" in sys.argv:
     def step():

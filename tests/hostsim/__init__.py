@@ -102,7 +102,7 @@ class HostSim(SourceGoalMixin):
         return dict(pos=op, dir=od, intensity=oi, hitmask=mask, sensors=keep)
 
     def trace_seq_bwd(self, tf, ti, pos, dir_, inten, mask, g_pos, g_dir, g_int, wav=None, lut=None, lut_w=None,
-                      g_records=None):
+                      g_records=None, hint=0):
         pos, dir_, inten, wav = _f32(pos), _f32(dir_), _f32(inten), _f32(wav)
         g_pos, g_dir, g_int = _f32(g_pos), _f32(g_dir), _f32(g_int)
         n = pos.shape[0]
@@ -115,7 +115,7 @@ class HostSim(SourceGoalMixin):
         rec_arr = (ct.c_void_p * max(ns, 1))(*[_p(g) or None for g in g_records]) if ns else None
         self.lib.call("rtt_trace_seq_bwd", _p(pos), _p(dir_), _p(inten), _p(wav), None, _p(mask),
                       _p(g_pos), _p(g_dir), _p(g_int), rec_arr, _p(gp), _p(gd), _p(gi), _p(gt), _p(gl),
-                      ct.byref(req), ns, n, 0, None)
+                      ct.byref(req), ns, n, hint, None)
         return dict(g_pos=gp, g_dir=gd, g_intensity=gi, g_table=gt, g_lut=gl)
 
     def trace_nonseq(self, tf, ti, pos, dir_, inten, nbounces, wav=None, lut=None, lut_w=None, sensor_specs=None,

@@ -100,9 +100,9 @@ struct Ck { V3 p, d; };
 
 // shared reverse step used by both adjoint drivers
 void reverse_row(const HostTable& T, int r, int lam, const Ck& ck, V3& gp, V3& gd, float& gI,
-                 V3 g_hl, float g_w, float* g_table, float* g_lut, int64_t i, int b) {
+                 V3 g_hl, float g_w, float* g_table, float* g_lut, int64_t i, int b, int flag_mask = ~0) {
     const RowDev& R = T.rows[r];
-    const int flags = R.i[RTT_I_FLAGS];
+    const int flags = R.i[RTT_I_FLAGS] & flag_mask;
     const Ior io = row_ior(T, r, lam);
     RowGrad G;
     zero(G);
@@ -213,8 +213,10 @@ int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float*,
                       float* g_in_pos, float* g_in_dir, float* g_in_intensity,
                       float* g_table, float* g_lut,
                       const rtt_table_t* table, int32_t n_sensors,
-                      int64_t n, int32_t, void*) {
+                      int64_t n, int32_t mode, void*) {
     const HostTable T = stage(table);
+    // RTT_MODE_SCALAR_GRADS: pose-gradient requests are ignored (include/rtt_b200.h)
+    const int flag_mask = (mode & RTT_MODE_SCALAR_GRADS) ? ~(RTT_FLAG_GRAD_POSE_E | RTT_FLAG_GRAD_POSE_S) : ~0;
     std::vector<Ck> ck(RTT_MAX_ROWS);
     for (int64_t i = 0; i < n; ++i) {
         const HostRay ray = fetch_ray(source, in_pos, in_dir, nullptr, in_wavelength, T.L > 0, i);
@@ -246,7 +248,7 @@ int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float*,
                 const float* gr = g_record[slot] + 4 * i;
                 g_hl = v3(gr[0], gr[1], gr[2]); g_w = gr[3];
             }
-            reverse_row(T, r, lam, ck[nh], gp, gd, gI, g_hl, g_w, g_table, g_lut, i, 0);
+            reverse_row(T, r, lam, ck[nh], gp, gd, gI, g_hl, g_w, g_table, g_lut, i, 0, flag_mask);
         }
         if (g_in_pos) store3(g_in_pos, i, gp);
         if (g_in_dir) store3(g_in_dir, i, gd);

@@ -343,6 +343,36 @@ def test_sensor_record_adjoint(rtt_ns, run_exact):
     assert parity.grad_rel(bwd["g_pos"], ref_gpos) < parity.TOL_GRAD
 
 
+@pytest.mark.parametrize("variant", ["exact", "fast"])
+@pytest.mark.parametrize("name", parity.golden_names(grads=True))
+def test_seq_adjoint_scalar_grads_hint(runner_of, rtt_ns, name, variant):
+    """RTT_MODE_SCALAR_GRADS (include/rtt_b200.h): the adjoint build without pose-gradient code gives the same ray
+    gradients and the same scalar parameter gradients (c, k, radius, indices) as the full build, and leaves the pose
+    columns of the gradient table untouched — with compaction (no ray gradients requested) and without."""
+    import raytracetorch_b200 as rtt
+    from raytracetorch_b200 import codes as C
+    hs = runner_of(variant)
+    builder, kw, _ = scenes.GRAD_CASES[name]
+    d = parity.load(name)
+    tab = rtt.compile_elements(builder(rtt_ns, **kw))
+    tf, ti = tab.f.detach().numpy(), tab.i.numpy().copy()
+    ti[:, C.I_FLAGS] |= C.FLAG_GRAD_CK | C.FLAG_GRAD_RADIUS | C.FLAG_GRAD_IOR      # scalar gradients on every row
+    fwd = hs.trace_seq(tf, ti, d["in_pos"], d["in_dir"], d["in_intensity"])
+    gp, gd, gi = parity.golden_loss_grads(fwd["pos"], fwd["dir"], fwd["intensity"])
+    args = (tf, ti, d["in_pos"], d["in_dir"], d["in_intensity"], fwd["hitmask"], gp, gd, gi)
+    full = hs.trace_seq_bwd(*args)
+    lean = hs.trace_seq_bwd(*args, hint=rtt.ops.MODE_SCALAR_GRADS)
+    tol = 0 if variant == "exact" else 2e-5
+    for k in ("g_pos", "g_dir", "g_intensity"):
+        assert parity.grad_rel(lean[k], full[k]) <= tol, k
+    scalar = slice(C.F_C, C.N_DIFF)
+    assert parity.grad_rel(lean["g_table"][:, scalar], full["g_table"][:, scalar]) <= max(tol, 1e-5)
+    assert np.abs(full["g_table"][:, scalar]).sum() > 0
+    assert not lean["g_table"][:, :C.F_C].any()
+    # the Python side sets the hint only for tables without pose requests
+    assert rtt.ops.adjoint_hint(tab) == (0 if any(m[C.I_FLAGS] & 3 for m in tab.i_host) else rtt.ops.MODE_SCALAR_GRADS)
+
+
 def test_nonseq_adjoint_matches_oracle_autograd(rtt_ns, run_exact, ieee_oracle):
     import raytracetorch_b200 as rtt
     d = parity.load("x2_nonsequential")
