@@ -1137,7 +1137,8 @@ cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
         case 1: return launch_tile<1, 4>(a, st);
         case 2: return launch_tile<2, 3>(a, st);
         case 3: return launch_tile<2, 4>(a, st);
-        case 4: return launch_tile<4, 2>(a, st);
+        case 4: return launch_tile<2, 5>(a, st);
+        case 5: return launch_tile<1, 5>(a, st);
         default: break;
     }
 #endif
