@@ -1120,7 +1120,9 @@ inline cudaError_t launch_tile(const SeqFwdArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 // RTT_FWD_TILE selects the frame-resident forward kernel: 1 = 1 ray/thread, 2 = 2 rays (80 regs), 3 = 2 rays
-// (64 regs), 4 = 4 rays; 0 = the per-ray kernel of the EXACT variant's structure
+// (64 regs), 5 = 1 ray at 48 registers / five blocks per SM (C1 -4 %, C2 +3 %, C4 +9 % against 3); 0 = the per-ray
+// kernel of the EXACT variant's structure.  Measured and dropped: 4 rays per thread (128 registers, -20 %), 2 rays at
+// 48 registers (spills, -17 %).
 inline int fwd_tile_choice() {
     static int choice = -1;
     if (choice < 0) {
@@ -1137,7 +1139,6 @@ cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
         case 1: return launch_tile<1, 4>(a, st);
         case 2: return launch_tile<2, 3>(a, st);
         case 3: return launch_tile<2, 4>(a, st);
-        case 4: return launch_tile<2, 5>(a, st);
         case 5: return launch_tile<1, 5>(a, st);
         default: break;
     }
