@@ -575,7 +575,7 @@ def run_gpu_arm(args):
     elif not args.no_e2e:
         host = [t.cpu().pin_memory() for t in (pos, dirs, inten)] + \
                [(wav if wav is not None else torch.full((n,), 550.0, device=dev)).cpu().pin_memory()]
-        h2d = sum(t.numel() * t.element_size() for t in host) + (0 if w["nonseq"] else n)   # + int8 ray ids
+        h2d = sum(t.numel() * t.element_size() for t in host) + n                             # + int8 ray ids
         img_host = torch.empty(img_numel, dtype=torch.float32).pin_memory()
         ids = torch.zeros(n, dtype=torch.int8, device=dev)
         sensor = w["sensor"]
@@ -585,9 +585,9 @@ def run_gpu_arm(args):
         def e2e_step():
             sensor.reset()
             if w["nonseq"]:
-                dv = [t.to(dev, non_blocking=True) for t in host]
-                scene.rays = rtt.rays.Rays._wrap(pos=dv[0], dir=dv[1], intensity=dv[2], id=ids,
-                                                 wavelength=dv[3] if len(dv) > 3 else dv[2])
+                # host-resident Rays: Scene.simulate() pipelines the H2D chunks with the bounce loop
+                scene.rays = rtt.rays.Rays._wrap(pos=host[0], dir=host[1], intensity=host[2], id=ids_host,
+                                                 wavelength=host[3] if len(host) > 3 else host[2])
                 scene.simulate()
             else:
                 # host-resident Rays straight into the public call: simulate() pipelines the H2D chunks with the trace

@@ -936,6 +936,82 @@ def trace_nonsequential(table: SurfaceTable, pos, dir_, intensity, nbounces: int
                 sensor_counts=counts, images=split_images(images, cfg))
 
 
+def trace_nonsequential_host(table: SurfaceTable, pos, dir_, intensity, nbounces: int, wavelength=None, *,
+                             want_record=False, sensor_cfg: Optional[List[float]] = None, mode: Optional[int] = None,
+                             record_depth: int = 1, chunk_rays: int = 1 << 23, ids=None):
+    """``trace_nonsequential`` for a bundle that lives in HOST memory (pinned for full copy speed): chunk k+1 is copied
+    host->device on a side stream while chunk k runs its bounce loop (one ``rtt_trace_nonseq_fwd`` launch per chunk,
+    all accumulating into the same sensor images).  Forward only, like ``trace_sequential_host``; same dict as
+    ``trace_nonsequential`` plus the device copies of the inputs."""
+    if not 0 <= nbounces <= C.MAX_BOUNCES:
+        raise ValueError(f"nbounces must be in [0, {C.MAX_BOUNCES}]")
+    _need_cuda(table.f)
+    for t in (pos, dir_, intensity):
+        if t.is_cuda:
+            raise ValueError("trace_nonsequential_host takes host tensors; use trace_nonsequential for device rays")
+    dev = table.f.device
+    lib = _cabi.load()
+    cfg = sensor_cfg_of(table) if sensor_cfg is None else list(sensor_cfg)
+    mode = _default_mode_nonseq if mode is None else mode
+    f32 = dict(dtype=torch.float32, device=dev)
+    pos, dir_, intensity = (_f32c(t.detach()) for t in (pos, dir_, intensity))
+    use_wav = table.lut is not None and wavelength is not None
+    wav = _f32c(wavelength.detach()) if wavelength is not None else None
+    n, nb = pos.shape[0], int(nbounces)
+    ns = len(cfg) // SENSOR_CFG
+    K = max(1, int(record_depth))
+    tf = table.f.detach()
+    with torch.cuda.device(dev):
+        cur, cp = torch.cuda.current_stream(dev), _copy_stream(dev)
+        d_pos, d_dir, d_int = torch.empty((n, 3), **f32), torch.empty((n, 3), **f32), torch.empty(n, **f32)
+        d_wav = torch.empty(n, **f32) if wav is not None else None
+        opos, odir, oint = torch.empty((n, 3), **f32), torch.empty((n, 3), **f32), torch.empty(n, **f32)
+        seq = torch.empty((n, nb), dtype=torch.uint8, device=dev)
+        nh = torch.empty(n, dtype=torch.uint8, device=dev)
+        rec_on = bool(want_record and ns)
+        counts = torch.zeros((ns if rec_on else 0, n), dtype=torch.uint8, device=dev)
+        images = torch.zeros(_image_numel(cfg), **f32)
+        req = _table_req(tf, table.i, table.lut, table.lut_wavelengths)
+        cp.wait_stream(cur)
+        chunk = max(1, int(chunk_rays))
+        ready, rec_chunks = [], []
+        with torch.cuda.stream(cp):
+            for start in range(0, n, chunk):
+                sl = slice(start, min(n, start + chunk))
+                d_pos[sl].copy_(pos[sl], non_blocking=True)
+                d_dir[sl].copy_(dir_[sl], non_blocking=True)
+                d_int[sl].copy_(intensity[sl], non_blocking=True)
+                if wav is not None:
+                    d_wav[sl].copy_(wav[sl], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cp)
+                ready.append((sl, ev))
+            d_id = None
+            if ids is not None:
+                d_id = torch.empty(ids.shape, dtype=ids.dtype, device=dev)
+                d_id.copy_(ids, non_blocking=True)
+                d_id.record_stream(cur)
+            tail = torch.cuda.Event()
+            tail.record(cp)
+        for sl, ev in ready:
+            cur.wait_event(ev)
+            m = sl.stop - sl.start
+            # the kernel addresses records as [K, m, 4] of ITS launch: one buffer per chunk, joined below
+            rec_c = torch.zeros((ns, K, m, 4), **f32) if rec_on else None
+            if rec_on:
+                rec_chunks.append(rec_c)
+            sens, cnt = _sensor_reqs(cfg, m, rec_c, images, [counts[s_, sl] for s_ in range(ns)] if rec_on else None, K)
+            lib.call("rtt_trace_nonseq_fwd", d_pos[sl].data_ptr(), d_dir[sl].data_ptr(), d_int[sl].data_ptr(),
+                     d_wav[sl].data_ptr() if use_wav else 0, None,
+                     opos[sl].data_ptr(), odir[sl].data_ptr(), oint[sl].data_ptr(), seq[sl].data_ptr(),
+                     nh[sl].data_ptr(), ct.byref(req), sens, cnt, nb, m, mode, ct.c_void_p(cur.cuda_stream))
+        cur.wait_event(tail)
+        records = torch.cat(rec_chunks, dim=2) if rec_chunks else torch.empty((0, K, n, 4), **f32)
+    return dict(pos=opos, dir=odir, intensity=oint, hit_seq=seq, n_hits=nh, records=records, sensor_counts=counts,
+                images=split_images(images, cfg), in_pos=d_pos, in_dir=d_dir, in_intensity=d_int,
+                in_wavelength=d_wav, in_id=d_id)
+
+
 def intersect_rows(table: SurfaceTable, pos, dir_, row0: int, k: int, mode: Optional[int] = None) -> torch.Tensor:
     _need_cuda(pos, dir_, table.f)
     mode = _default_mode if mode is None else mode

@@ -126,6 +126,15 @@ class Scene(nn.Module):
         if src is not None:
             out = ops.trace_nonsequential(table, None, None, None, nbounces, want_record=self.record_hits,
                                           mode=self.mode, record_depth=depth, source=src, want_rays=self.final_rays)
+        elif table.f.is_cuda and not rays.pos.is_cuda:
+            # rays in host memory, scene on the GPU: the host->device copies are pipelined with the bounce loop; the
+            # Rays object ends up on the device, like after ``rays.to(device)`` followed by ``simulate``; forward only
+            out = ops.trace_nonsequential_host(table, rays.pos, rays.dir, rays.intensity, nbounces, rays.wavelength,
+                                               want_record=self.record_hits, mode=self.mode, record_depth=depth,
+                                               ids=rays.id)
+            rays.id = out["in_id"]
+            rays.wavelength = out["in_wavelength"] if out["in_wavelength"] is not None \
+                else rays.wavelength.to(table.f.device, non_blocking=True)
         else:
             out = ops.trace_nonsequential(table, rays.pos, rays.dir, rays.intensity, nbounces, rays.wavelength,
                                           want_record=self.record_hits, mode=self.mode, record_depth=depth)

@@ -329,6 +329,55 @@ def test_host_resident_bundle_is_streamed_and_equals_the_device_trace(rtt_ns):
         assert torch.equal(x, y)
 
 
+def test_host_resident_bundle_nonsequential_equals_the_device_trace(rtt_ns):
+    """Scene.simulate on Rays in (pinned) host memory: H2D chunks pipelined with per-chunk bounce-loop launches
+    (ops.trace_nonsequential_host).  Rays are independent and the entry runs EXACT arithmetic, so every per-ray output
+    is bit-identical to tracing the device-resident bundle in one launch; images agree to accumulation order."""
+    import raytracetorch_b200 as rtt
+    n = 200_003
+    g = torch.Generator().manual_seed(9)
+    th = torch.rand(n, generator=g) * (2 * np.pi)
+    r = torch.sqrt(torch.rand(n, generator=g)) * 10.0
+    pos = torch.stack([r * torch.cos(th), r * torch.sin(th), torch.full_like(r, -5.0)], 1).contiguous().pin_memory()
+    dirs = torch.zeros(n, 3)
+    dirs[:, 2] = 1.0
+    dirs, inten = dirs.pin_memory(), torch.ones(n).pin_memory()
+    lam = torch.full((n,), 0.55).pin_memory()
+    ids = (torch.arange(n) % 7).to(torch.int8).pin_memory()
+
+    def make():
+        els = scenes.c5_nonsequential(rtt_ns)
+        els[4].set_image(128, 128)
+        scene = rtt.scene.Scene()
+        for e in els:
+            scene.add_element(e)
+        scene.Nbounces = 6
+        return scene.cuda(), els
+
+    scene, els = make()
+    tab = scene.table()
+    a = rtt.ops.trace_nonsequential_host(tab, pos, dirs, inten, 6, lam, want_record=True, record_depth=2,
+                                         chunk_rays=50_000, ids=ids)
+    b = rtt.ops.trace_nonsequential(tab, pos.cuda(), dirs.cuda(), inten.cuda(), 6, lam.cuda(), want_record=True,
+                                    record_depth=2)
+    for k in ("pos", "dir", "intensity", "hit_seq", "n_hits", "records", "sensor_counts"):
+        assert a[k].shape == b[k].shape and torch.equal(a[k], b[k]), k
+    assert parity.rel_l1(a["images"][0].cpu().numpy(), b["images"][0].cpu().numpy()) <= 1e-6
+    assert torch.equal(a["in_id"].cpu(), ids) and torch.equal(a["in_wavelength"].cpu(), lam)
+    outs = []
+    for host in (True, False):
+        scene, els = make()
+        mv = (lambda t: t) if host else (lambda t: t.cuda())
+        scene.rays = rtt.rays.Rays._wrap(pos=mv(pos), dir=mv(dirs), intensity=mv(inten), id=mv(ids), wavelength=mv(lam))
+        scene.simulate()
+        out = scene.rays
+        assert out.pos.is_cuda and out.id.is_cuda and out.wavelength.is_cuda
+        locs, w, hid = els[4].getHitsTensors()
+        outs.append([t.cpu() for t in (out.pos, out.intensity, locs, w, hid)])
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
+
+
 def test_paths_proxy_records_one_snapshot_per_bounce(rtt_ns):
     """rays/ray.py:100-225 ``Paths``: the GUI's per-bounce position history.  Each ``Scene.step()`` that hit
     something appends one CPU snapshot; ``simulate()`` on a Paths runs bounce by bounce and ends where the fused
