@@ -231,6 +231,14 @@ def measure_fp32_peak(lib, dev):
     return best
 
 
+def hit_frac_live(hitmask, g_pos, n_rows):
+    """Per row: fraction of ALL rays that interacted with it and carry a non-zero upstream gradient."""
+    livem = (g_pos != 0).any(1)
+    m = hitmask[livem]
+    tot = float(hitmask.shape[0])
+    return [float(((m >> r) & 1).sum().item()) / tot for r in range(n_rows)]
+
+
 def units_per_ray(w, n_rows):
     """Interactions counted per ray: every row is tested once per sequential trace; the
     non-sequential kernel tests every row at every executed bounce (counted by the caller)."""
@@ -501,6 +509,42 @@ def run_gpu_arm(args):
                   note="trace forward + loss (torch elementwise) + hand-written adjoint kernel + table->Parameter "
                        "autograd; interactions counted once per ray and row")
 
+        # the adjoint kernel alone, against its own roofline (same upstream gradients as the loss above)
+        try:
+            tab_a = scene.table()
+            of = torch.ops.rtt_b200.trace_seq_fwd(pos, dirs, inten, wav, tab_a.f.detach(), tab_a.i, tab_a.lut,
+                                                  tab_a.lut_wavelengths, [], False, rtt.ops.get_default_mode())
+            g_p = torch.zeros_like(of[0])
+            g_p[:, :2] = 2.0 * of[2][:, None] * of[0][:, :2]
+            g_i = (of[0][:, :2] ** 2).sum(1)
+            at = []
+            for _ in range(max(args.steps, 3)):
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                torch.ops.rtt_b200.trace_seq_bwd(pos, dirs, inten, wav, of[3], g_p, None, g_i, None, tab_a.f.detach(),
+                                                 tab_a.i, tab_a.lut, tab_a.lut_wavelengths, False, True,
+                                                 rtt.ops.get_default_mode() | rtt.ops.adjoint_hint(tab_a))
+                a1.record()
+                torch.cuda.synchronize()
+                at.append(a0.elapsed_time(a1))
+            a_ms = float(np.median(at))
+            # rays that reach the reverse sweep: non-zero upstream gradient (the kernel compacts to those)
+            live = ((g_p != 0).any(1)).float().mean().item()
+            a_flops = rf.adjoint_flops_per_ray(tf_host, ti_host, hit_frac_live(of[3], g_p, S))    # per ray of the bundle
+            a_bytes = rf.adjoint_bytes_per_ray(wavelength=wav is not None) - 28 - 12      # no ray gradients out, no g_dir in
+            pk32 = roof.get("fp32", {}).get("peak")
+            adj = dict(kernel="k_trace_seq_bwd", kernel_ms=a_ms, live_fraction=live, flops_per_ray=a_flops,
+                       bytes_per_ray=a_bytes, hbm_frac=n * a_bytes / (a_ms / 1e3) / 1e9 / hbm_peak)
+            if pk32:
+                adj.update(achieved=n * a_flops / (a_ms / 1e3) / 1e12, peak=pk32, unit="TFLOP/s",
+                           frac=n * a_flops / (a_ms / 1e3) / 1e12 / pk32, bound="fp32",
+                           note="algorithmic FLOPs = 3.5 x (root solve + interaction) of the rows each live ray hit "
+                                "(raytracetorch_b200/roofline.py adjoint_flops_per_ray)")
+            fb["adjoint"] = adj
+            del of, g_p, g_i
+        except Exception as exc:                                       # the extra figure must not cost the bench line
+            fb["adjoint"] = dict(error=f"{type(exc).__name__}: {exc}")
+
         # the same step with the reference's own goal (optim/goals.py:99-187) through the public API: the loss is
         # evaluated on the sensor records by the fused goal kernels instead of eager torch ops on the final rays
         ids = torch.zeros(n, dtype=torch.int8, device=dev)
@@ -748,6 +792,20 @@ def run_c3(args):
     roof = dict(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, traffic=None,
                 kernel="k_trace_seq_bwd", kernel_ms=k_ms, bytes_per_ray=bpr,
                 peak_source="measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s")
+    # the bound that binds: FP32 issue rate — 3.5 x (root solve + interaction) per recorded interaction
+    hm = fwd[3]
+    hit_frac = [float(((hm >> r) & 1).float().mean().item()) for r in range(S)]
+    a_flops = rf.adjoint_flops_per_ray(tab.f.detach().cpu().tolist(), tab.i_host, hit_frac)
+    pk = measure_fp32_peak(lib, dev) or rf.fp32_peak_tflops(torch.cuda.get_device_properties(dev).multi_processor_count,
+                                                            float(peaks.get("sm_max_mhz", 1965.0)))
+    a_ach = n * a_flops / (k_ms / 1e3) / 1e12
+    if a_flops / (pk * 1e12) > bpr / (hbm_peak * 1e9):
+        roof = dict(bound="fp32", achieved=a_ach, peak=pk, unit="TFLOP/s", frac=a_ach / pk, traffic=None,
+                    kernel="k_trace_seq_bwd", kernel_ms=k_ms, flops_per_ray=a_flops,
+                    peak_source="measured in this run: rtt_probe_fp32 (pure FMA kernel, CUDA events)",
+                    note="algorithmic FLOPs of the adjoint (raytracetorch_b200/roofline.py adjoint_flops_per_ray); "
+                         "'hbm' carries the memory view of the same launch",
+                    hbm=roof)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import trace_oracle as O          # CPU baseline only
