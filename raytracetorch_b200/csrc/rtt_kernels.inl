@@ -1127,15 +1127,22 @@ inline int fwd_tile_choice() {
     static int choice = -1;
     if (choice < 0) {
         const char* e = getenv("RTT_FWD_TILE");
-        choice = e ? atoi(e) : 3;     // 2 rays per thread at 64 registers (4 blocks / SM): best on C1, C2 and C4
+        choice = e ? atoi(e) : 100;   // 100 = by table size (below)
     }
     return choice;
+}
+// Default: 2 rays per thread at 64 registers (4 blocks / SM) — best on C2 and C4; a short table (a singlet and its
+// sensor) has too little arithmetic per ray to hide the ray loads behind 32 warps, there 1 ray per thread at 48
+// registers (40 warps / SM) wins (C1, 4 rows: 2.69 -> 2.58 ms per 1e8 rays).
+inline int fwd_tile_for(int S, bool from_memory) {
+    const int c = fwd_tile_choice();
+    return c == 100 ? ((S <= 6 && from_memory) ? 5 : 3) : c;
 }
 #endif
 
 cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
 #if defined(RTT_APPROX)
-    switch (fwd_tile_choice()) {
+    switch (fwd_tile_for(a.tab.S, a.pos != nullptr)) {
         case 1: return launch_tile<1, 4>(a, st);
         case 2: return launch_tile<2, 3>(a, st);
         case 3: return launch_tile<2, 4>(a, st);
