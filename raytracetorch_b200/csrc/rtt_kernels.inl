@@ -1134,15 +1134,17 @@ inline int fwd_tile_choice() {
 // Default: 2 rays per thread at 64 registers (4 blocks / SM) — best on C2 and C4; a short table (a singlet and its
 // sensor) has too little arithmetic per ray to hide the ray loads behind 32 warps, there 1 ray per thread at 48
 // registers (40 warps / SM) wins (C1, 4 rows: 2.69 -> 2.58 ms per 1e8 rays).
-inline int fwd_tile_for(int S, bool from_memory) {
+// The choice depends on the table only, so a bundle generated in the kernel and its materialised twin run the same
+// build and stay bit-identical (tests/test_goals.py).
+inline int fwd_tile_for(int S) {
     const int c = fwd_tile_choice();
-    return c == 100 ? ((S <= 6 && from_memory) ? 5 : 3) : c;
+    return c == 100 ? (S <= 6 ? 5 : 3) : c;
 }
 #endif
 
 cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
 #if defined(RTT_APPROX)
-    switch (fwd_tile_for(a.tab.S, a.pos != nullptr)) {
+    switch (fwd_tile_for(a.tab.S)) {
         case 1: return launch_tile<1, 4>(a, st);
         case 2: return launch_tile<2, 3>(a, st);
         case 3: return launch_tile<2, 4>(a, st);
