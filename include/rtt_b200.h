@@ -147,7 +147,8 @@ int64_t rtt_launch_count(void);
  * Every ray walks all n_rows rows once, in order, state in registers.  Rays that miss a
  * row are left untouched; dead rays keep walking (reference behaviour).
  *   in_*        : pos/dir [n,3], intensity [n], wavelength [n] (may be NULL iff n_lut==0)
- *   out_*       : same shapes (may alias the inputs)
+ *   out_*       : same shapes (may alias the inputs); all three NULL = the final rays are not written (goal
+ *                 evaluations that only read sensor records / images)
  *   hitmask     : [n] uint64, bit r set iff the ray interacted with row r (may be NULL)
  *   sensors     : HOST array of n_sensors requests indexed by the rows' sensor slot
  *   source      : NULL, or a ray source that replaces the four in_* arrays (which may then be NULL);

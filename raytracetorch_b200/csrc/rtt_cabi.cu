@@ -159,7 +159,7 @@ int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_
     if (int e = check_table(table)) return e;
     if (n == 0) return RTT_OK;   /* empty bundle: nothing to do, pointers may be NULL */
     if (n < 0) return RTT_E_ARG;
-    if (!source && (!in_pos || !in_dir || !in_intensity || !out_pos || !out_dir || !out_intensity)) return RTT_E_ARG;
+    if (!source && (!in_pos || !in_dir || !in_intensity)) return RTT_E_ARG;
     if (!source && table->n_lut > 0 && !in_wavelength) return RTT_E_ARG;
     if ((out_pos != nullptr) != (out_dir != nullptr) || (out_pos != nullptr) != (out_intensity != nullptr)) return RTT_E_ARG;
     if (!have_device()) return RTT_E_NO_DEVICE;

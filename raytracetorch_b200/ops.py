@@ -20,6 +20,7 @@ from .table import SurfaceTable, compile_elements
 
 MODE_FAST, MODE_EXACT = _cabi.MODE_FAST, _cabi.MODE_EXACT
 MODE_SCALAR_GRADS = _cabi.MODE_SCALAR_GRADS
+MODE_NO_FINAL_RAYS = 0x200    # trace_seq_fwd op only: skip the final pos / dir / intensity outputs (goal evaluations)
 # Arithmetic defaults.  Sequential traces: FAST (FMA contraction; masks verified identical to
 # the reference on every fixture, points within 1e-5).  Non-sequential traces: EXACT — the
 # reference's t > 1e-6 self-intersection rule sits at the fp32 ulp of scene-scale coordinates,
@@ -244,13 +245,14 @@ def _trace_seq_fwd(pos: torch.Tensor, dir: torch.Tensor, intensity: torch.Tensor
                    sensor_cfg: List[float], want_record: bool, mode: int) -> List[torch.Tensor]:
     """-> [out_pos, out_dir, out_intensity, hitmask(int64), records [ns,N,4], images (flat)]"""
     _need_cuda(pos, dir, intensity, table_f, table_i)
+    want_rays = not (mode & MODE_NO_FINAL_RAYS)         # op-level flag (not part of the C ABI): empty final-ray outputs
     return _seq_fwd_body(pos.device, pos.shape[0], pos, dir, intensity, wavelength, None, table_f, table_i, lut, lut_w,
-                         sensor_cfg, want_record, True, mode)
+                         sensor_cfg, want_record, want_rays, mode & ~MODE_NO_FINAL_RAYS)
 
 
 @_trace_seq_fwd.register_fake
 def _(pos, dir, intensity, wavelength, table_f, table_i, lut, lut_w, sensor_cfg, want_record, mode):
-    return _fake_seq_fwd(pos, pos.shape[0], sensor_cfg, want_record, True)
+    return _fake_seq_fwd(pos, pos.shape[0], sensor_cfg, want_record, not (mode & MODE_NO_FINAL_RAYS))
 
 
 @torch.library.custom_op("rtt_b200::trace_seq_bwd", mutates_args=())
@@ -572,7 +574,7 @@ class _TraceSeq(torch.autograd.Function):
                                                 sensor_cfg, want_record, mode)
         opos, odir, oint, hitmask, records, images = outs
         ctx.save_for_backward(pos, dir_, intensity, wavelength, hitmask, table_f, table_i, lut, lut_w)
-        ctx.mode = mode | bwd_hint
+        ctx.mode = (mode & ~MODE_NO_FINAL_RAYS) | bwd_hint
         ctx.mark_non_differentiable(hitmask, images)
         ctx.set_materialize_grads(False)     # unused outputs hand None to backward, not [N,3] zero tensors
         return opos, odir, oint, hitmask, records, images
@@ -807,7 +809,7 @@ def trace_sequential(table: SurfaceTable, pos=None, dir_=None, intensity=None, w
     """Fused SequentialScene.simulate (scene/sequential.py:12-36).
 
     Rays come from (pos, dir_, intensity, wavelength) or — ``source=SourceRays`` — are generated in the kernel;
-    ``want_rays=False`` (sources only) skips the final-ray outputs.
+    ``want_rays=False`` skips the final-ray outputs (empty tensors; what the goals ask for: they read sensor records).
     Returns dict(pos, dir, intensity, hitmask [N] int64 (bit r = interacted with row r),
     records [n_sensors,N,4] (hit_local xyz, weight-before), images [per sensor: [C,H,W] or None])."""
     cfg = sensor_cfg_of(table) if sensor_cfg is None else list(sensor_cfg)
@@ -822,8 +824,8 @@ def trace_sequential(table: SurfaceTable, pos=None, dir_=None, intensity=None, w
                     images=split_images(images, cfg))
     pos, dir_, intensity, wav = _prep_rays(pos, dir_, intensity, wavelength, table)
     opos, odir, oint, hitmask, records, images = _TraceSeq.apply(
-        pos, dir_, intensity, wav, table.f, table.i, table.lut, table.lut_wavelengths, cfg, bool(want_record), mode,
-        hint)
+        pos, dir_, intensity, wav, table.f, table.i, table.lut, table.lut_wavelengths, cfg, bool(want_record),
+        mode | (0 if want_rays else MODE_NO_FINAL_RAYS), hint)
     return dict(pos=opos, dir=odir, intensity=oint, hitmask=hitmask, records=records,
                 images=split_images(images, cfg))
 

@@ -41,8 +41,9 @@ class Scene(nn.Module):
         # at an fp32 ulp of ~8e-6), so 2 is the smallest depth that reproduces its lists on
         # transmitting sensors; Sensor warns when a ray had more interactions than were kept.
         self.record_depth = 2
-        # False: a trace of in-kernel generated rays (SourceRays) skips the final pos/dir/intensity outputs —
-        # what the optimisation goals do, since they only read sensor records
+        # False: a sequential trace (and a non-sequential trace of in-kernel generated rays) skips the final
+        # pos/dir/intensity outputs and leaves the Rays as they were — what the optimisation goals do while they
+        # evaluate, since they only read sensor records
         self.final_rays = True
         self.mode: Optional[int] = None  # None = ops default (FAST)
         self.last_trace = None           # raw kernel outputs of the latest simulate()/step()
@@ -237,7 +238,7 @@ class SequentialScene(Scene):
                                        want_rays=self.final_rays)
         else:
             out = ops.trace_sequential(table, rays.pos, rays.dir, rays.intensity, rays.wavelength,
-                                       want_record=self.record_hits, mode=self.mode)
+                                       want_record=self.record_hits, mode=self.mode, want_rays=self.final_rays)
         self.last_trace = out
         mask = out["hitmask"]
 
@@ -245,7 +246,7 @@ class SequentialScene(Scene):
             return ((mask >> table.sensor_rows[slot]) & 1).bool()
 
         self._deliver_to_sensors(table, out["records"], hit_of_slot, rays, out["images"])
-        if src is None or self.final_rays:
+        if self.final_rays:
             rays.pos, rays.dir, rays.intensity = out["pos"], out["dir"], out["intensity"]
         return rays
 

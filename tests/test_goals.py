@@ -154,6 +154,47 @@ def test_fused_goal_equals_eager_goal_on_the_same_rays(rtt_ns, target, monkeypat
 
 
 @pytest.mark.gpu
+def test_goal_on_memory_resident_rays_skips_the_final_ray_outputs(rtt_ns):
+    """A goal over rays that live in device memory (any Bundle whose sample() returns plain Rays): the trace writes no
+    final rays (empty outputs, the Rays object is left as it was), loss and gradients equal the explicit evaluation."""
+    import raytracetorch_b200 as rtt
+    import scenes
+    dev = torch.device("cuda", 0)
+    n = 40_000
+    g = torch.Generator().manual_seed(4)
+    th = torch.rand(n, generator=g) * (2 * np.pi)
+    r = torch.sqrt(torch.rand(n, generator=g)) * 5.0
+    pos = torch.stack([r * torch.cos(th), r * torch.sin(th), torch.full_like(r, -10.0)], 1).contiguous().to(dev)
+    dirs = torch.zeros(n, 3, device=dev)
+    dirs[:, 2] = 1.0
+    inten = torch.ones(n, device=dev)
+
+    class Resident(rtt.rays.Bundle):
+        def sample(self, N):
+            return rtt.rays.Rays._wrap(pos=pos, dir=dirs, intensity=inten, wavelength=torch.zeros(n, device=dev),
+                                       id=torch.zeros(n, dtype=torch.int8, device=dev))
+
+    res = []
+    for through_goal in (True, False):
+        els = scenes.c1_singlet(rtt_ns, physical=True, grads=True)
+        scene = rtt.scene.SequentialScene(els).to(dev)
+        if through_goal:
+            loss = rtt.optim.SpotSizeLoss(els[1], [Resident(0, device=dev)], N_rays=n)(scene)
+            assert scene.last_trace["pos"].numel() == 0 and scene.rays.pos.data_ptr() == pos.data_ptr()
+            assert scene.final_rays is True                  # restored after the evaluation
+        else:
+            out = rtt.ops.trace_sequential(scene.table(), pos, dirs, inten, None, want_record=True)
+            assert out["pos"].shape == (n, 3)
+            loss = rtt.ops.spot_size(out["records"].reshape(-1, 4), None)
+        loss.backward()
+        res.append((float(loss), [float(els[0].shape.surfaces[k].c.grad) for k in (0, 1)]))
+    (l1, g1), (l2, g2) = res
+    assert abs(l1 - l2) <= 1e-6 * abs(l2)
+    for a, b in zip(g1, g2):
+        assert abs(a - b) <= 1e-4 * abs(b), (g1, g2)
+
+
+@pytest.mark.gpu
 def test_spot_target_fused_equals_eager(rtt_ns, monkeypatch):
     import raytracetorch_b200 as rtt
     import scenes

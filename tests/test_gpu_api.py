@@ -329,6 +329,59 @@ def test_host_resident_bundle_is_streamed_and_equals_the_device_trace(rtt_ns):
         assert torch.equal(x, y)
 
 
+def test_adjoint_builds_and_compaction_agree(rtt_ns):
+    """The sequential adjoint has four routes to the same parameter gradients: with / without the block-level
+    compaction to rays that carry an upstream gradient (no ray gradients requested / requested), and the builds with /
+    without pose-gradient code (RTT_MODE_SCALAR_GRADS).  On a bundle where most rays are dead or masked out they must
+    agree to accumulation order, and so must the ray gradients of the two builds."""
+    import raytracetorch_b200 as rtt
+    n = 400_003
+    g = torch.Generator(device="cuda").manual_seed(11)
+    th = torch.rand(n, device="cuda", generator=g) * (2 * np.pi)
+    r = torch.sqrt(torch.rand(n, device="cuda", generator=g)) * 8.0
+    pos = torch.stack([r * torch.cos(th), r * torch.sin(th), torch.full_like(r, -10.0)], 1).contiguous()
+    dirs = torch.zeros(n, 3, device="cuda")
+    dirs[:, 2] = 1.0
+    inten = torch.ones(n, device="cuda")
+    lam = torch.tensor(scenes.C2_WAVELENGTHS, device="cuda")[torch.arange(n, device="cuda") % 3].contiguous()
+    els = scenes.c2_cylindrical(rtt_ns)
+    for el in els:
+        for s_ in getattr(el.shape, "surfaces", []):
+            if hasattr(s_, "c") and isinstance(s_.c, torch.nn.Parameter):
+                s_.c.requires_grad_(True)
+    scene = rtt.scene.SequentialScene(els).cuda()
+    scene.set_dispersion(rtt.Dispersion(scenes.C2_WAVELENGTHS, {
+        els[0].ior_glass: [1.5 * s_ for s_ in scenes.C2_GLASS_SCALE],
+        els[1].ior_glass: [1.6 * s_ for s_ in scenes.C2_GLASS_SCALE]}))
+    tab = scene.table()
+    assert rtt.ops.adjoint_hint(tab) == rtt.ops.MODE_SCALAR_GRADS
+    mode = rtt.ops.get_default_mode()
+    tf = tab.f.detach()
+    fwd = torch.ops.rtt_b200.trace_seq_fwd(pos, dirs, inten, lam, tf, tab.i, tab.lut, tab.lut_wavelengths, [], False, mode)
+    opos, _odir, oint, hitmask = fwd[:4]
+    keep = (torch.rand(n, device="cuda", generator=g) < 0.6).float()          # 40 % of the survivors masked out too
+    g_pos = torch.zeros_like(opos)
+    g_pos[:, :2] = 2.0 * (oint * keep)[:, None] * opos[:, :2]
+    g_int = (opos[:, :2] ** 2).sum(1)
+    live = float((g_pos != 0).any(1).float().mean())
+    assert 0.1 < live < 0.4
+
+    def run(need_rays, hint):
+        return torch.ops.rtt_b200.trace_seq_bwd(pos, dirs, inten, lam, hitmask, g_pos, None, g_int, None, tf, tab.i,
+                                                tab.lut, tab.lut_wavelengths, need_rays, True, mode | hint)
+
+    ref = run(True, 0)
+    assert float(ref[3].abs().sum()) > 0
+    for need_rays in (False, True):
+        for hint in (0, rtt.ops.MODE_SCALAR_GRADS):
+            out = run(need_rays, hint)
+            assert parity.grad_rel(out[3].cpu().numpy(), ref[3].cpu().numpy()) < 2e-5, (need_rays, hint)
+            assert parity.grad_rel(out[4].cpu().numpy(), ref[4].cpu().numpy()) < 2e-5
+            if need_rays:                                   # FAST arithmetic: the two builds may contract differently
+                for k in (0, 1, 2):
+                    assert parity.grad_rel(out[k].cpu().numpy(), ref[k].cpu().numpy()) < 1e-5, (k, hint)
+
+
 def test_host_resident_bundle_nonsequential_equals_the_device_trace(rtt_ns):
     """Scene.simulate on Rays in (pinned) host memory: H2D chunks pipelined with per-chunk bounce-loop launches
     (ops.trace_nonsequential_host).  Rays are independent and the entry runs EXACT arithmetic, so every per-ray output
