@@ -373,6 +373,61 @@ def test_seq_adjoint_scalar_grads_hint(runner_of, rtt_ns, name, variant):
     assert rtt.ops.adjoint_hint(tab) == (0 if any(m[C.I_FLAGS] & 3 for m in tab.i_host) else rtt.ops.MODE_SCALAR_GRADS)
 
 
+def _stack_of_singlets(rtt_ns, grads=()):
+    """21 weak singlets (3 rows each) + a sensor = RTT_MAX_ROWS = 64 table rows; the hit mask uses all 64 bits."""
+    E, G = rtt_ns.elements, rtt_ns.geom
+    els = [E.SingletLens(c1=0.004 * (1.0 + 0.1 * k), c2=-0.003, d=24.0, t=2.0, ior_glass=1.5 + 0.004 * k, ior_media=1.0,
+                         c1_grad=(k in grads), c2_grad=(k in grads), transform=scenes._T(rtt_ns, 4.0 * k))
+           for k in range(21)]
+    els.append(E.Sensor(G.Disk(radius=30.0, transform=scenes._T(rtt_ns, 100.0))))
+    return els
+
+
+@pytest.mark.parametrize("variant", ["exact", "fast"])
+def test_maximum_table_size(runner_of, ieee_oracle, rtt_ns, variant):
+    """A 64-row table (the C ABI's maximum): forward against the oracle (EXACT: bit for bit, the sensor bit is bit 63 of
+    the hit mask), adjoint against oracle autograd for the first and the last lens (rows beyond the 12 private
+    accumulator slots take the per-row warp reduction)."""
+    import raytracetorch_b200 as rtt
+    from raytracetorch_b200 import codes as C
+    hs = runner_of(variant)
+    els = _stack_of_singlets(rtt_ns, grads=(0, 9, 20))
+    tab = rtt.compile_elements(els)
+    assert tab.n_rows == C.MAX_ROWS == 64
+    rays = scenes.make_bundle(rtt_ns, ("coll", 9.0, -10.0, [0.01, -0.02, 0.0]), 4096, 3)
+    p, dd, inten = rays.pos.clone().requires_grad_(True), rays.dir.clone().requires_grad_(True), \
+        rays.intensity.clone().requires_grad_(True)
+    o = ieee_oracle.trace_sequential(tab.f, tab.i_host, p, dd, inten)
+    parity.golden_loss(o["pos"], o["dir"], o["intensity"]).backward()
+    surf = lambda k, j: els[k].shape.surfaces[j].c
+    ref = {(k, j): surf(k, j).grad.clone() for k in (0, 9, 20) for j in (0, 1)}
+    ref_gpos = p.grad.numpy().copy()
+    for k, j in ref:
+        surf(k, j).grad = None
+    tab = rtt.compile_elements(els)
+    tf, ti = tab.f.detach().numpy(), tab.i.numpy()
+    pn, dn, inn = rays.pos.numpy(), rays.dir.numpy(), rays.intensity.numpy()
+    h = hs.trace_seq(tf, ti, pn, dn, inn, sensor_specs=[None])
+    bits = parity.mask_bits(h["hitmask"], 64)
+    np.testing.assert_array_equal(bits, o["hit"].numpy())
+    assert bits[:, 63].mean() > 0.5 and bits[:, 0].all()
+    if variant == "exact":
+        for k in ("pos", "dir", "intensity"):
+            np.testing.assert_array_equal(h[k], o[k].detach().numpy(), err_msg=k)
+    else:
+        scale = float(np.abs(o["pos"].detach().numpy()).max())
+        assert parity.vec_rel(h["pos"], o["pos"].detach().numpy(), floor=scale).max() <= parity.TOL_POINT
+        assert parity.vec_rel(h["dir"], o["dir"].detach().numpy()).max() <= parity.TOL_POINT
+    gp, gd, gi = parity.golden_loss_grads(h["pos"], h["dir"], h["intensity"])
+    bwd = hs.trace_seq_bwd(tf, ti, pn, dn, inn, h["hitmask"], gp, gd, gi)
+    assert parity.grad_rel(bwd["g_pos"], ref_gpos) < parity.TOL_GRAD
+    tab.f.backward(torch.from_numpy(bwd["g_table"]))
+    for (k, j), g in ref.items():
+        assert parity.grad_rel(surf(k, j).grad.numpy(), g.numpy()) < parity.TOL_GRAD, (k, j)
+    lean = hs.trace_seq_bwd(tf, ti, pn, dn, inn, h["hitmask"], gp, gd, gi, hint=rtt.ops.MODE_SCALAR_GRADS)
+    assert parity.grad_rel(lean["g_table"][:, C.F_C:C.N_DIFF], bwd["g_table"][:, C.F_C:C.N_DIFF]) < 2e-5
+
+
 def test_nonseq_adjoint_matches_oracle_autograd(rtt_ns, run_exact, ieee_oracle):
     import raytracetorch_b200 as rtt
     d = parity.load("x2_nonsequential")
