@@ -244,6 +244,66 @@ def test_full_size_properties_sequential(rtt_ns, n):
                                   o["hit"].numpy())
 
 
+def test_full_size_properties_adjoint(rtt_ns):
+    """The adjoint at BASELINE config 3's size (1e7 rays per step): linearity in the upstream gradient, additivity over
+    ray chunks (rays are independent, the parameter gradient is a sum over rays), run-to-run agreement to accumulation
+    order, and oracle autograd on a random sub-sample (per-ray input gradients, parameter gradients of that sample)."""
+    import raytracetorch_b200 as rtt
+    n = 10_000_000
+    els = scenes.c1_singlet(rtt_ns, physical=True, grads=True)
+    scene = rtt.scene.SequentialScene(els).cuda()
+    g = torch.Generator(device="cuda").manual_seed(21)
+    th = torch.rand(n, device="cuda", generator=g) * (2 * np.pi)
+    r = torch.sqrt(torch.rand(n, device="cuda", generator=g)) * 5.0
+    pos = torch.stack([r * torch.cos(th), r * torch.sin(th), torch.full_like(r, -10.0)], 1).contiguous()
+    del th, r
+    dirs = torch.zeros_like(pos)
+    dirs[:, 2] = 1.0
+    inten = torch.ones(n, device="cuda")
+    tab = scene.table()
+    mode = rtt.ops.get_default_mode()
+    hint = rtt.ops.adjoint_hint(tab)
+    tf = tab.f.detach()
+    fwd = torch.ops.rtt_b200.trace_seq_fwd(pos, dirs, inten, None, tf, tab.i, None, None, [], False, mode)
+    opos, odir, oint, hm = fwd[:4]
+    g1 = torch.zeros_like(opos)
+    g1[:, :2] = 2.0 * oint[:, None] * opos[:, :2]
+    g2 = torch.randn(opos.shape, device="cuda", generator=g) * oint[:, None]
+    gi = (opos[:, :2] ** 2).sum(1)
+
+    def bwd(sl, gp, gint, need_rays=False):
+        return torch.ops.rtt_b200.trace_seq_bwd(pos[sl], dirs[sl], inten[sl], None, hm[sl], gp[sl].contiguous(), None,
+                                                None if gint is None else gint[sl], None, tf, tab.i, None, None,
+                                                need_rays, True, mode | hint)
+
+    full = slice(None)
+    a, b, ab = bwd(full, g1, gi)[3], bwd(full, g2, None)[3], bwd(full, g1 + g2, gi)[3]
+    assert float(a.abs().sum()) > 0 and float(b.abs().sum()) > 0
+    assert parity.grad_rel((a + b).cpu().numpy(), ab.cpu().numpy()) < 1e-4                 # linearity
+    again = bwd(full, g1, gi)[3]
+    assert parity.grad_rel(again.cpu().numpy(), a.cpu().numpy()) < 1e-5                     # accumulation order only
+    h = n // 2 + 12345
+    halves = bwd(slice(0, h), g1, gi)[3] + bwd(slice(h, n), g1, gi)[3]
+    assert parity.grad_rel(halves.cpu().numpy(), a.cpu().numpy()) < 1e-4                    # additivity over chunks
+    # oracle autograd on a random sub-sample
+    idx = torch.randint(0, n, (20000,), device="cuda", generator=g)
+    elc = scenes.c1_singlet(rtt_ns, physical=True, grads=True)
+    tabc = rtt.compile_elements(elc)
+    p, dd, ii = (t[idx].cpu().clone().requires_grad_(True) for t in (pos, dirs, inten))
+    o = O.trace_sequential(tabc.f, tabc.i_host, p, dd, ii)
+    (o["intensity"] * (o["pos"][:, :2] ** 2).sum(1)).sum().backward()
+    sub = torch.ops.rtt_b200.trace_seq_bwd(pos[idx], dirs[idx], inten[idx], None, hm[idx], g1[idx].contiguous(), None,
+                                           gi[idx], None, tf, tab.i, None, None, True, True, mode | hint)
+    assert parity.grad_rel(sub[0].cpu().numpy(), p.grad.numpy()) < parity.TOL_GRAD
+    assert parity.grad_rel(sub[1].cpu().numpy(), dd.grad.numpy()) < parity.TOL_GRAD
+    assert parity.grad_rel(sub[2].cpu().numpy(), ii.grad.numpy()) < parity.TOL_GRAD
+    tab.f.backward(sub[3])
+    for k in (0, 1):
+        ref = elc[0].shape.surfaces[k].c.grad.numpy()
+        got = els[0].shape.surfaces[k].c.grad.cpu().numpy()
+        assert parity.grad_rel(got, ref) < parity.TOL_GRAD, (k, got, ref)
+
+
 def test_full_size_nonsequential_properties(rtt_ns):
     """C5 at 2e7 rays: determinism, chunking invariance, first-bounce winners vs the oracle."""
     import raytracetorch_b200 as rtt
