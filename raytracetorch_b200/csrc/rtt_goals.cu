@@ -114,17 +114,29 @@ __global__ void __launch_bounds__(kThreads) k_spot_size_fwd(const float4* __rest
     const Centre c = centre_of(mom4, target_xy);
     float acc[3] = {0.0f, 0.0f, 0.0f};
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
-        const float4 r = __ldg(rec + i);
-        if (!(r.w > 0.0f)) continue;                                    // optim/goals.py:165
-        const float dx = r.x - c.cx, dy = r.y - c.cy;
-        const float wn = r.w / c.W;
-        const float q = (dx * dx + dy * dy) * wn;                       // :176-181
-        const float rms = sqrtf(q);
-        acc[0] += rms;
-        const float a = (q > 0.0f) ? 0.5f / rms : 0.0f;                 // d sqrt
-        acc[1] += a * (-2.0f * dx * wn);
-        acc[2] += a * (-2.0f * dy * wn);
+    // four records per trip, their loads issued together: the divisions and the square root of one record overlap the
+    // loads of the next ones (one load in flight per thread ran this pass at half the rate of k_spot_moments)
+    constexpr int kUnroll = 4;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < m; i0 += kUnroll * stride) {
+        float4 rr[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long i = i0 + u * stride;
+            rr[u] = (i < m) ? __ldg(rec + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const float4 r = rr[u];
+            if (!(r.w > 0.0f)) continue;                                // optim/goals.py:165
+            const float dx = r.x - c.cx, dy = r.y - c.cy;
+            const float wn = r.w / c.W;
+            const float q = (dx * dx + dy * dy) * wn;                   // :176-181
+            const float rms = sqrtf(q);
+            acc[0] += rms;
+            const float a = (q > 0.0f) ? 0.5f / rms : 0.0f;             // d sqrt
+            acc[1] += a * (-2.0f * dx * wn);
+            acc[2] += a * (-2.0f * dy * wn);
+        }
     }
     publish<3>(acc, work, out3);
 }
