@@ -231,7 +231,10 @@ class GraphedStep:
 
     last_error = None
 
-    def __init__(self, scene, goal, optimizer, warmup: int = 3):
+    def __init__(self, scene, goal, optimizer, warmup: int = 3, after_backward=None):
+        """``after_backward``: optional callable run between ``backward`` and ``optimizer.step`` — with a bundle sharded
+        over ranks, the one all-reduce of the parameter gradients (``dist.allreduce_scene_results``); NCCL collectives
+        are captured into the graph like kernels."""
         self.scene, self.goal, self.optimizer = scene, goal, optimizer
         dev = next(p for p in scene.parameters()).device
 
@@ -257,6 +260,8 @@ class GraphedStep:
                 optimizer.zero_grad(set_to_none=True)
                 loss = goal(scene)
                 loss.backward()
+                if after_backward is not None:
+                    after_backward()
                 optimizer.step()
                 del loss
                 drop_graph_refs()
@@ -269,6 +274,8 @@ class GraphedStep:
         with torch.cuda.graph(self.graph):
             self.loss = goal(scene)
             self.loss.backward()
+            if after_backward is not None:
+                after_backward()
             optimizer.step()
         self.launches_per_step = lib.launch_count() - before     # this library's kernels inside one replay
 
@@ -278,10 +285,10 @@ class GraphedStep:
         return self.loss
 
     @classmethod
-    def try_build(cls, scene, goal, optimizer, warmup: int = 3):
+    def try_build(cls, scene, goal, optimizer, warmup: int = 3, after_backward=None):
         cls.last_error = None
         try:
-            return cls(scene, goal, optimizer, warmup)
+            return cls(scene, goal, optimizer, warmup, after_backward)
         except Exception as exc:                             # capture refused: callers fall back to eager steps
             cls.last_error = f"{type(exc).__name__}: {exc}"
             torch.cuda.synchronize()
