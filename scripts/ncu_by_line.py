@@ -1,7 +1,12 @@
 #!/usr/bin/env python
 """Aggregate an ncu source page (SASS level) by CUDA source line.
 
-    python scripts/ncu_by_line.py <report.ncu-rep> <kernel mangled-name substring> [variant cubin] [top]
+    python scripts/ncu_by_line.py <report.ncu-rep> <kernel mangled-name substring> [variant cubin] [top] [--by-samples]
+
+The substring must select ONE function of the cubin: for a templated kernel pass the mangled instantiation
+(e.g. k_trace_seq_bwd_fastILi4ELb0), otherwise the address maps of several instantiations overwrite each other.
+--by-samples orders the lines by warp stall samples instead of executed instructions (where warps WAIT, e.g. the
+compaction pass of the adjoint that executed 3 % of the instructions and held 24 % of the samples).
 
 Joins `ncu --page source --csv` (per-SASS-address executed instructions and stall samples) with the
 `//## File ..., line N` annotations of `nvdisasm -g` on the cubin extracted from librtt_b200.so
@@ -14,6 +19,8 @@ import subprocess
 import sys
 import tempfile
 
+BY_SAMPLES = "--by-samples" in sys.argv
+sys.argv = [a for a in sys.argv if a != "--by-samples"]
 rep, kern = sys.argv[1], sys.argv[2]
 variant = sys.argv[3] if len(sys.argv) > 3 else "fast"
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 60
@@ -72,7 +79,7 @@ for r in rows:
     tot += ie
 srcs = {}
 print(f"total warp instructions {tot:.3e}")
-for key, (ie, smp) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for key, (ie, smp) in sorted(agg.items(), key=lambda kv: -kv[1][1 if BY_SAMPLES else 0])[:top]:
     f, ln = key
     if f not in srcs:
         p = os.path.join(ROOT, "raytracetorch_b200", "csrc", f)
