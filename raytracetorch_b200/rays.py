@@ -162,6 +162,30 @@ def source_state(device) -> torch.Tensor:
     return hit[1]
 
 
+_RANK_STRIDE = 1 << 40   # Philox counter offset between ranks: 1e12 rays per rank before two shards could overlap
+
+
+def _rank_first(n: int) -> int:
+    """Counter offset (``rtt_source_t.first``) of this rank's shard.  Ranks that share a seed — the usual DDP
+    setup — would otherwise generate identical rays and all-reduce world_size copies of one sample."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_rank() * _RANK_STRIDE
+    return 0
+
+
+_IDENT_POSE = {}
+
+
+def _identity_pose12(device) -> torch.Tensor:
+    device = torch.device(device)
+    hit = _IDENT_POSE.get(device)
+    if hit is None:
+        hit = _IDENT_POSE[device] = torch.tensor([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], dtype=torch.float32,
+                                                 device=device)
+    return hit
+
+
 class SourceRays(Rays):
     """Rays of a device ray source, generated on demand (see the module docstring).
 
@@ -256,7 +280,17 @@ class Bundle(nn.Module):
             state = source_state(dev)
             snap = state.clone()
             state[1:].add_(int(N))
-            spec = dict(kind=src[0], a=list(src[1]), width=0, height=0, intensity=1.0, wavelength=0.0, first=0)
+            spec = dict(kind=src[0], a=list(src[1]), width=0, height=0, intensity=1.0, wavelength=0.0,
+                        first=_rank_first(N))
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.transform.parameters()):
+                # The source pose is being optimised (rays/bundle.py:30-37 with geom/transform.py:245-276; the
+                # reference's tests/test_ideal.py:142-168 differentiates w.r.t. the source origin).  In-kernel
+                # generated rays have no autograd edge to the pose, so: same Philox samples, drawn in the LOCAL
+                # frame by the kernel (identity pose), then the pose applied with differentiable torch ops.  The
+                # trace's adjoint returns d/d pos, d/d dir of these rays and autograd chains them to rot_vec / trans.
+                local = SourceRays(spec, _identity_pose12(dev), snap, N, self.ray_id)
+                p, d = self.transform.transform_(local.pos, local.dir)
+                return Rays.initialize(p, d, ray_id=self.ray_id, device=self.device, dtype=self.dtype)
             return SourceRays(spec, self._pose12(dev), snap, N, self.ray_id)
         p, d = self.transform.transform_(self.sample_pos(N), self.sample_dir(N))
         return Rays.initialize(p, d, ray_id=self.ray_id, device=self.device, dtype=self.dtype)

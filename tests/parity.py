@@ -189,3 +189,15 @@ def self_hit_free(d, tf, ti, nbounces=None):
         o = O.trace_nonsequential(tf, ti, p, dd, inten, 1)
         p, dd, inten = o["pos"], o["dir"], o["intensity"]
     return ok
+
+
+# Fraction of each non-sequential fixture's rays that `self_hit_free` keeps, measured once on the committed
+# fixtures (oracle sweep, no kernel involved).  The tests pin these so that a change which silently drops rays
+# from the comparison fails instead of passing on a smaller subset.
+CLEAN_FRACTION = {"c5_nonsequential": 0.3277, "sim_benchmark": 0.9223, "x2_nonsequential": 0.2240}
+
+
+def assert_clean_fraction(name, clean):
+    want = CLEAN_FRACTION[name]
+    got = float(np.mean(clean))
+    assert abs(got - want) <= 0.002, f"{name}: self-hit-free fraction {got:.4f}, pinned {want:.4f}"

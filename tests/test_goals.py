@@ -278,3 +278,85 @@ def test_graphed_optimisation_step_follows_the_eager_loop(rtt_ns):
     # the loss is steep here (it falls 3x in five steps): 1e-5 parameter differences show up as ~1e-3 in the loss
     np.testing.assert_allclose(losses_g, losses_e[warm:], rtol=3e-3)
     assert len(set(losses_g)) == steps                      # fresh rays on every replay
+
+
+@pytest.mark.gpu
+def test_bundle_transform_gradients_reach_the_source_pose(rtt_ns):
+    """rays/bundle.py:30-37 + geom/transform.py:245-276: a Bundle whose pose is being optimised.  The
+    reference's tests/test_ideal.py:142-168 differentiates an image position w.r.t. the source origin; here the
+    device path must hand d loss / d trans, d rot_vec of the bundle to autograd (it used to drop them silently):
+    the same Philox samples are drawn in the local frame by the kernel and posed with differentiable torch ops.
+    Checked against oracle autograd on the same local samples, and against the analytic dZi/dZo of an ideal lens."""
+    import raytracetorch_b200 as rtt
+    import scenes
+    from oracle import trace_oracle as O
+    from raytracetorch_b200.rays import SourceRays
+    dev = torch.device("cuda", 0)
+    n = 30_000
+    tr = rtt.geom.RayTransformBundle(translation=[0.3, -0.2, -10.0], rotation=[0.01, -0.02, 0.0],
+                                     trans_grad=True, rot_grad=True).to(dev)
+    bundle = rtt.rays.CollimatedDisk(4.0, 2, device=dev, transform=tr)
+    torch.manual_seed(11)
+    state0 = rtt.rays.source_state(dev).clone()
+    rays = bundle.sample(n)
+    assert not isinstance(rays, SourceRays) and rays.pos.requires_grad and rays.dir.requires_grad
+    # with frozen pose parameters the in-kernel source is used, and it draws the same rays
+    tr_frozen = rtt.geom.RayTransformBundle(translation=[0.3, -0.2, -10.0], rotation=[0.01, -0.02, 0.0]).to(dev)
+    torch.manual_seed(11)
+    twin = rtt.rays.CollimatedDisk(4.0, 2, device=dev, transform=tr_frozen).sample(n)
+    assert isinstance(twin, SourceRays) and torch.equal(twin.state, state0)
+    np.testing.assert_allclose(twin.pos.cpu().numpy(), rays.pos.detach().cpu().numpy(), atol=1e-5)
+    np.testing.assert_allclose(twin.dir.cpu().numpy(), rays.dir.detach().cpu().numpy(), atol=2e-6)
+
+    els = scenes.c1_singlet(rtt_ns, physical=True, grads=True)
+    scene = rtt.scene.SequentialScene(els).to(dev)
+    scene.simulate(rays)
+    locs, wt, _ = els[1].getHitsTensors()
+    loss = (wt * ((locs[:, 0] - 0.05) ** 2 + locs[:, 1] ** 2)).sum() / wt.sum()
+    loss.backward()
+    assert tr.trans.grad is not None and tr.rot_vec.grad is not None
+
+    # oracle autograd on the same local samples (identity-pose twin), pose applied with the same torch ops
+    local = SourceRays(twin.source, torch.tensor([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.0], device=dev), state0, n, 2)
+    lp, ld = local.pos.cpu(), local.dir.cpu()
+    tr_c = rtt.geom.RayTransformBundle(translation=[0.3, -0.2, -10.0], rotation=[0.01, -0.02, 0.0],
+                                       trans_grad=True, rot_grad=True)
+    p, d = tr_c.transform_(lp, ld)
+    d = torch.nn.functional.normalize(d, p=2, dim=1)
+    els_c = scenes.c1_singlet(rtt_ns, physical=True, grads=True)
+    tab = rtt.scene.SequentialScene(els_c).table()
+    o = O.trace_sequential(tab.f, tab.i_host, p, d, torch.ones(n))
+    _m, hl, ww = o["sensor"][0]
+    loss_o = (ww * ((hl[:, 0] - 0.05) ** 2 + hl[:, 1] ** 2)).sum() / ww.sum()
+    loss_o.backward()
+    assert abs(float(loss.detach()) - float(loss_o.detach())) <= 1e-4 * abs(float(loss_o.detach()))
+    assert parity.grad_rel(tr.trans.grad.cpu().numpy(), tr_c.trans.grad.numpy()) < parity.TOL_GRAD
+    assert parity.grad_rel(tr.rot_vec.grad.cpu().numpy(), tr_c.rot_vec.grad.numpy()) < parity.TOL_GRAD
+    for k in (0, 1):
+        assert parity.grad_rel(els[0].shape.surfaces[k].c.grad.cpu().numpy(),
+                               els_c[0].shape.surfaces[k].c.grad.numpy()) < parity.TOL_GRAD
+
+
+@pytest.mark.gpu
+def test_source_origin_gradient_of_an_ideal_lens_is_the_axial_magnification(rtt_ns):
+    """tests/test_ideal.py:142-186 of the reference on the device path: a point source at z_o = -3f in front of
+    an ideal thin lens (f = 100) images at z_i = 1.5f; d z_i / d z_o = (z_i / z_o)^2 = 0.25.  The source origin is
+    the bundle's `trans` Parameter."""
+    import raytracetorch_b200 as rtt
+    dev = torch.device("cuda", 0)
+    tr = rtt.geom.RayTransformBundle(translation=[0.0, 0.0, -300.0], trans_grad=True).to(dev)
+    bundle = rtt.rays.PointSource(0.02, 0, device=dev, transform=tr)
+    torch.manual_seed(3)
+    rays = bundle.sample(4096)
+    lens = rtt.elements.IdealThinLens(focal=100.0).to(dev)
+    out_pos, out_dir, _ = lens(rays, surf_idx=0)
+    # axial crossing of each ray: the point on the ray closest to the z axis
+    txy = -(out_pos[:, 0] * out_dir[:, 0] + out_pos[:, 1] * out_dir[:, 1]) / \
+        (out_dir[:, 0] ** 2 + out_dir[:, 1] ** 2).clamp_min(1e-12)
+    zi = out_pos[:, 2] + txy * out_dir[:, 2]
+    off_axis = (out_dir[:, 0] ** 2 + out_dir[:, 1] ** 2) > 1e-8
+    zi_mean = zi[off_axis].mean()
+    zi_mean.backward()
+    assert abs(float(zi_mean.detach()) - 150.0) < 0.5
+    g = tr.trans.grad.cpu().numpy()
+    assert abs(g[2] - 0.25) < 2e-3, g

@@ -82,7 +82,7 @@ def test_nonseq_exact_matches_oracle(run_exact, ieee_oracle, name):
     hseq = h["seq"].astype(np.int64)
     hseq[hseq == 255] = -1
     clean = _self_hit_free(d, tf, ti)
-    assert clean.mean() > 0.1      # most c5 rays re-hit the surface they just left
+    parity.assert_clean_fraction(name, clean)      # most c5 rays re-hit the surface they just left
     np.testing.assert_array_equal(hseq[clean], o["seq"].numpy()[clean])
     np.testing.assert_array_equal(h["nb"][clean], o["nb"].numpy()[clean])
     np.testing.assert_array_equal(h["intensity"][clean], o["intensity"].numpy()[clean])
@@ -101,7 +101,7 @@ def test_nonseq_exact_matches_reference_on_stable_rays(run_exact, name):
     hseq = h["seq"].astype(np.int64)
     hseq[hseq == 255] = -1
     stable = parity.stable_nonseq_rows(d) & _self_hit_free(d, torch.from_numpy(d["table_f"]), d["table_i"].tolist())
-    assert stable.sum() > 100
+    parity.assert_clean_fraction(name, stable)          # every clean ray is also fp32/fp64-stable
     np.testing.assert_array_equal(hseq[stable], d["f32_seq"][stable])
     _assert_close_noise_aware(h, d, name, rows=stable)
 
@@ -429,36 +429,55 @@ def test_maximum_table_size(runner_of, ieee_oracle, rtt_ns, variant):
 
 
 def test_nonseq_adjoint_matches_oracle_autograd(rtt_ns, run_exact, ieee_oracle):
+    """Ray gradients on every ray whose hit sequence equals the oracle's; PARAMETER gradients at the same 1e-3 bar
+    as the sequential adjoint, on the bundle restricted to those rays (a parameter gradient sums over rays, so a ray
+    that took another path — fp32 noise at the t > 1e-6 rule, SURVEY 0.10 — must be left out of both sums)."""
     import raytracetorch_b200 as rtt
     d = parity.load("x2_nonsequential")
     els = scenes.x2_tilted_lenses(rtt_ns, grads=True)
     holder = torch.nn.Module()
     holder.elements = torch.nn.ModuleList(els)
-    tab = rtt.compile_elements(els)
     nb = 6
-    p, dd, inten = parity.inputs_t(d)
-    for t in (p, dd, inten):
-        t.requires_grad_(True)
-    o = O.trace_nonsequential(tab.f, tab.i_host, p, dd, inten, nb)
-    parity.golden_loss(o["pos"], o["dir"], o["intensity"]).backward()
-    ref = {k: v.grad.clone() for k, v in holder.named_parameters() if v.grad is not None}
-    for v in holder.parameters():
-        v.grad = None
-    tab = rtt.compile_elements(els)
-    tf, ti = tab.f.detach().numpy(), tab.i.numpy()
-    fwd = run_exact.trace_nonseq(tf, ti, d["in_pos"], d["in_dir"], d["in_intensity"], nb)
-    same = (np.where(fwd["seq"] == 255, -1, fwd["seq"].astype(np.int64)) == o["seq"].numpy()).all(1)
+
+    def run(idx):
+        """oracle autograd and kernel adjoint on rays `idx` -> (same-sequence mask, oracle ray grads, kernel bwd, ref)"""
+        for v in holder.parameters():
+            v.grad = None
+        tab = rtt.compile_elements(els)
+        p, dd, inten = (torch.from_numpy(d[k][idx].copy()).requires_grad_(True)
+                        for k in ("in_pos", "in_dir", "in_intensity"))
+        o = O.trace_nonsequential(tab.f, tab.i_host, p, dd, inten, nb)
+        parity.golden_loss(o["pos"], o["dir"], o["intensity"]).backward()
+        ref = {k: v.grad.clone() for k, v in holder.named_parameters() if v.grad is not None}
+        for v in holder.parameters():
+            v.grad = None
+        tab = rtt.compile_elements(els)
+        tf, ti = tab.f.detach().numpy(), tab.i.numpy()
+        fwd = run_exact.trace_nonseq(tf, ti, d["in_pos"][idx], d["in_dir"][idx], d["in_intensity"][idx], nb)
+        same = (np.where(fwd["seq"] == 255, -1, fwd["seq"].astype(np.int64)) == o["seq"].numpy()).all(1)
+        gp, gd, gi = parity.golden_loss_grads(fwd["pos"], fwd["dir"], fwd["intensity"])
+        bwd = run_exact.trace_nonseq_bwd(tf, ti, d["in_pos"][idx], d["in_dir"][idx], d["in_intensity"][idx],
+                                         fwd["seq"], gp, gd, gi)
+        tab.f.backward(torch.from_numpy(bwd["g_table"]))
+        got = {k: v.grad.clone() for k, v in holder.named_parameters() if v.grad is not None}
+        return same, p.grad.numpy(), dd.grad.numpy(), bwd, ref, got
+
+    idx = np.arange(d["in_pos"].shape[0])
+    same, gp_o, gd_o, bwd, _ref, _got = run(idx)
     assert same.mean() > 0.97
-    gp, gd, gi = parity.golden_loss_grads(fwd["pos"], fwd["dir"], fwd["intensity"])
-    bwd = run_exact.trace_nonseq_bwd(tf, ti, d["in_pos"], d["in_dir"], d["in_intensity"], fwd["seq"], gp, gd, gi)
-    assert parity.grad_rel(bwd["g_pos"][same], p.grad.numpy()[same]) < parity.TOL_GRAD
-    assert parity.grad_rel(bwd["g_dir"][same], dd.grad.numpy()[same]) < parity.TOL_GRAD
-    tab.f.backward(torch.from_numpy(bwd["g_table"]))
+    assert parity.grad_rel(bwd["g_pos"][same], gp_o[same]) < parity.TOL_GRAD
+    assert parity.grad_rel(bwd["g_dir"][same], gd_o[same]) < parity.TOL_GRAD
+    # parameter gradients: both sides on the rays that took the same path
+    for _ in range(3):
+        idx = idx[same]
+        same, gp_o, gd_o, bwd, ref, got = run(idx)
+        if same.all():
+            break
+    assert same.all() and idx.size > 0.95 * d["in_pos"].shape[0]
     checked = 0
-    for k, v in holder.named_parameters():
-        if k in ref and float(ref[k].norm()) > 0:
-            # a handful of noise-dominated rays take another path: looser than the sequential bar
-            assert parity.grad_rel(v.grad.numpy(), ref[k].numpy()) < 2e-2, k
+    for k in ref:
+        if float(ref[k].norm()) > 0:
+            assert parity.grad_rel(got[k].numpy(), ref[k].numpy()) < parity.TOL_GRAD, k
             checked += 1
     assert checked >= 5
 
@@ -677,7 +696,7 @@ def test_fresnel_kernels_take_the_oracles_branches(run_exact, run_fast, ieee_ora
     hseq[hseq == 255] = -1
     clean = parity.self_hit_free(dict(in_pos=pos, in_dir=dr, in_intensity=inten, nbounces=nb), tab.f.detach(),
                                  tab.i_host, nbounces=nb)
-    assert clean.mean() > 0.1
+    assert abs(clean.mean() - 0.7256) < 0.005, clean.mean()   # measured on this scene (both seeds): pinned
     np.testing.assert_array_equal(hseq[clean], on["seq"].numpy()[clean])
     assert parity.vec_rel(hn["pos"][clean], on["pos"].numpy()[clean]).max() <= parity.TOL_POINT
 
