@@ -10,8 +10,10 @@
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says
  *     "host"; all float arrays are contiguous fp32, int arrays int32, masks uint64/uint8
  *   - the caller owns every buffer; the library allocates nothing that outlives a call
- *     and keeps no global state (the surface table is read from device memory and staged
- *     in shared memory by every thread block), so calls are re-entrant
+ *     and keeps no state that influences a result: no caches, no environment variables, the
+ *     surface table is read from device memory and staged in shared memory by every thread
+ *     block, so calls are re-entrant (the one process-wide variable is the diagnostic launch
+ *     counter behind rtt_launch_count())
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
  *     synchronises
  *   - return value: 0 on success, a cudaError_t (>0) from the launch, or a negative
@@ -78,6 +80,16 @@ enum { RTT_MODE_FAST = 0, RTT_MODE_EXACT = 1 };
  * indices).  The adjoint then runs a build without the pose-gradient code (72 instead of 80+ registers, four blocks
  * per SM); pose flags present in the table are ignored under this hint.  Every other entry ignores the bit. */
 enum { RTT_MODE_SCALAR_GRADS = 0x100, RTT_MODE_ARITH_MASK = 0xff };
+/* Optional kernel-build selector in bits 16..23 of `mode` (0 = the library's default choice for the table): which
+ * compiled instantiation of the sequential forward / adjoint kernel runs.  Results are the same for every value
+ * (FAST builds agree to rounding); it exists for performance sweeps and A/B measurements, and it is the ONLY tuning
+ * input — the library reads no environment variables.
+ *   rtt_trace_seq_fwd (FAST): 1 = tile, 1 ray/thread, 4 blocks/SM; 2 = tile, 2 rays, 3 blocks; 3 = tile, 2 rays,
+ *     4 blocks; 5 = tile, 1 ray, 5 blocks; 9 = per-ray kernel in the reference's operation order; 16 = packed ray
+ *     pairs (f32x2 arithmetic) with bulk-async (TMA) ray streaming, 3 blocks/SM; 17 = same, 4 blocks/SM;
+ *     18 = packed pairs with plain global loads / stores
+ *   rtt_trace_seq_bwd: 2 / 3 / 4 = resident blocks per SM the adjoint build is compiled for */
+enum { RTT_MODE_TUNE_SHIFT = 16, RTT_MODE_TUNE_MASK = 0xff0000 };
 
 /* Sensor image request for one sensor slot.  Bin rule (restating the fixed-range
  * histogram of gui/workbench.py:615-624 in fp32):

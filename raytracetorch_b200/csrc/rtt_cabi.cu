@@ -174,6 +174,7 @@ int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_
         a.tab = make_table<rtt::NS::TableDev>(table);                                                  \
         if (int e = fill_sensors(a.sens, sensors, n_sensors)) return e;                                \
         a.n_sens = n_sensors; a.n = n;                                                                 \
+        a.tune = (mode & RTT_MODE_TUNE_MASK) >> RTT_MODE_TUNE_SHIFT;                                   \
         return finish(rtt::NS::launch_seq_fwd_##NS(a, st));                                            \
     }
     if ((mode & RTT_MODE_ARITH_MASK) == RTT_MODE_EXACT) RTT_BODY(exact) else RTT_BODY(fast)
@@ -212,6 +213,7 @@ int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float* in_
         a.tab = make_table<rtt::NS::TableDev>(table);                                                  \
         a.n_sens = n_sensors; a.n = n;                                                                 \
         a.scalar_grads = (mode & RTT_MODE_SCALAR_GRADS) ? 1 : 0;                                       \
+        a.tune = (mode & RTT_MODE_TUNE_MASK) >> RTT_MODE_TUNE_SHIFT;                                   \
         return finish(rtt::NS::launch_seq_bwd_##NS(a, st));                                            \
     }
     if ((mode & RTT_MODE_ARITH_MASK) == RTT_MODE_EXACT) RTT_BODY(exact) else RTT_BODY(fast)

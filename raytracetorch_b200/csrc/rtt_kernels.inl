@@ -19,7 +19,6 @@
 //     reduce parameter gradients warp -> block (shared) -> global
 //   * the non-sequential forward refills a lane as soon as its ray has ended
 #include <cuda_runtime.h>
-#include <stdlib.h>
 #include "rtt_core.cuh"
 #include "rtt_tile.cuh"
 #include "rtt_kernels_decl.h"
@@ -870,7 +869,7 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
 // Non-sequential trace, adjoint: replay the recorded hit sequence, then reverse
 // ============================================================================================
 
-constexpr int kMaxReplay = 32;   // bounces differentiated per ray (deeper tails are treated as constant)
+constexpr int kMaxReplay = 32;   // checkpoints held per ray at a time; deeper hit sequences are differentiated in windows
 
 __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_bwd)(const __grid_constant__ NonseqBwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -884,64 +883,70 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_bwd)(const _
     const SourceKey skey = fetch_key(a);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
         const RayIn ray = fetch_ray(a, skey, i, L > 0);
-        V3 p = ray.p, d = ray.d;
         const int lam = (L > 0) ? wavelength_index(T, L, ray.wav) : 0;
-        Checkpoint ck[kMaxReplay];
-        unsigned char rows_hit[kMaxReplay];
-        int nh = 0;
-        unsigned cnts = 0u;                                             // sensor interactions per slot, 8 bits each
-        const int lim = NB < kMaxReplay ? NB : kMaxReplay;
-        for (int b = 0; b < lim; ++b) {
-            const int r = a.hit_seq[i * NB + b];
-            if (r == 255) break;
-            ck[nh].p = p; ck[nh].d = d; rows_hit[nh] = (unsigned char)r; ++nh;
-            const RowDev& R = T.rows[r];
-            {
-                const int sl = R.i[RTT_I_SENSOR];
-                if (sl >= 0 && sl < a.n_sens && ((cnts >> (8 * sl)) & 255u) < 255u) cnts += 1u << (8 * sl);
-            }
-            const Frames F = to_frames(R, p, d);
-            const Roots q = solve_roots(R, F.o, F.dd);
-            int which;
-            const float t = select_root(R, q, F.o, F.dd, &which);
-            const Ior io = row_ior(T, S, L, r, lam);
-            const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit, make_aux(T.rows, R, io.ni, io.no, i, r, b));
-            p = s.hit_global; d = s.new_dir;
-        }
+        int H = 0;                                                      // interactions of this ray (base.py:201: <= Nbounces)
+        while (H < NB && a.hit_seq[i * NB + H] != 255) ++H;
         V3 gp = a.g_opos ? load3(a.g_opos, i) : v3(0, 0, 0);
         V3 gd = a.g_odir ? load3(a.g_odir, i) : v3(0, 0, 0);
         float gI = a.g_ointen ? a.g_ointen[i] : 0.0f;
-        while (nh > 0) {
-            --nh;
-            const int r = rows_hit[nh];
-            const RowDev& R = T.rows[r];
-            const int flags = R.i[RTT_I_FLAGS];
-            const Ior io = row_ior(T, S, L, r, lam);
-            RowGrad G;
-            zero(G);
-            V3 g_hl = v3(0, 0, 0);
-            float g_w = 0.0f;
-            const int slot = R.i[RTT_I_SENSOR];
-            if (slot >= 0 && slot < a.n_sens) {
-                cnts -= 1u << (8 * slot);                               // ordinal of this interaction
-                const int ord = (int)((cnts >> (8 * slot)) & 255u);
-                if (a.g_record[slot] && ord < a.rec_hits[slot]) {
-                    const float4 gr = reinterpret_cast<const float4*>(a.g_record[slot])[(long long)ord * a.n + i];
-                    g_hl = v3(gr.x, gr.y, gr.z); g_w = gr.w;
+        Checkpoint ck[kMaxReplay];
+        unsigned char rows_hit[kMaxReplay];
+        // Windows of kMaxReplay interactions, last window first.  Each window replays the ray from its ORIGINAL state
+        // up to the window's end (recompute, not store) and keeps the incoming states of the window's interactions only;
+        // a ray with H <= kMaxReplay hits (every BASELINE config) is one window = one replay.
+        for (int w0 = (H > 0 ? ((H - 1) / kMaxReplay) * kMaxReplay : 0); w0 >= 0 && H > 0; w0 -= kMaxReplay) {
+            const int wend = (w0 + kMaxReplay < H) ? w0 + kMaxReplay : H;
+            V3 p = ray.p, d = ray.d;
+            int nh = 0;
+            unsigned cnts = 0u;                                         // sensor interactions per slot, 8 bits each
+            for (int b = 0; b < wend; ++b) {
+                const int r = a.hit_seq[i * NB + b];
+                if (b >= w0) { ck[nh].p = p; ck[nh].d = d; rows_hit[nh] = (unsigned char)r; ++nh; }
+                const RowDev& R = T.rows[r];
+                {
+                    const int sl = R.i[RTT_I_SENSOR];
+                    if (sl >= 0 && sl < a.n_sens && ((cnts >> (8 * sl)) & 255u) < 255u) cnts += 1u << (8 * sl);
                 }
+                const Frames F = to_frames(R, p, d);
+                const Roots q = solve_roots(R, F.o, F.dd);
+                int which;
+                const float t = select_root(R, q, F.o, F.dd, &which);
+                const Ior io = row_ior(T, S, L, r, lam);
+                const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit, make_aux(T.rows, R, io.ni, io.no, i, r, b));
+                p = s.hit_global; d = s.new_dir;
             }
-            V3 ngp, ngd; float mod;
-            interact_adjoint(R, ck[nh].p, ck[nh].d, io.ni, io.no, io.mu_enter, io.mu_exit,
-                             gp, gd, g_hl, v3(0, 0, 0), 0.0f, ngp, ngd, mod, G, flags,
-                             make_aux(T.rows, R, io.ni, io.no, i, r, nh).u);       // nh == bounce index of this interaction
-            gp = ngp; gd = ngd; gI = gI * mod + g_w;
-            if (a.g_table && flags) {
-                if (L > 0 && (flags & RTT_FLAG_GRAD_IOR)) {
-                    atomicAdd(acc_lut + ((size_t)lam * S + r) * 2, G.g[RTT_F_IOR_IN]);
-                    atomicAdd(acc_lut + ((size_t)lam * S + r) * 2 + 1, G.g[RTT_F_IOR_OUT]);
-                    scatter_row_grad(G, flags & ~RTT_FLAG_GRAD_IOR, acc + r * RTT_ROW_G);
-                } else {
-                    scatter_row_grad(G, flags, acc + r * RTT_ROW_G);
+            while (nh > 0) {
+                --nh;
+                const int r = rows_hit[nh];
+                const RowDev& R = T.rows[r];
+                const int flags = R.i[RTT_I_FLAGS];
+                const Ior io = row_ior(T, S, L, r, lam);
+                RowGrad G;
+                zero(G);
+                V3 g_hl = v3(0, 0, 0);
+                float g_w = 0.0f;
+                const int slot = R.i[RTT_I_SENSOR];
+                if (slot >= 0 && slot < a.n_sens) {
+                    cnts -= 1u << (8 * slot);                           // ordinal of this interaction
+                    const int ord = (int)((cnts >> (8 * slot)) & 255u);
+                    if (a.g_record[slot] && ord < a.rec_hits[slot]) {
+                        const float4 gr = reinterpret_cast<const float4*>(a.g_record[slot])[(long long)ord * a.n + i];
+                        g_hl = v3(gr.x, gr.y, gr.z); g_w = gr.w;
+                    }
+                }
+                V3 ngp, ngd; float mod;
+                interact_adjoint(R, ck[nh].p, ck[nh].d, io.ni, io.no, io.mu_enter, io.mu_exit,
+                                 gp, gd, g_hl, v3(0, 0, 0), 0.0f, ngp, ngd, mod, G, flags,
+                                 make_aux(T.rows, R, io.ni, io.no, i, r, w0 + nh).u);   // w0 + nh == bounce index
+                gp = ngp; gd = ngd; gI = gI * mod + g_w;
+                if (a.g_table && flags) {
+                    if (L > 0 && (flags & RTT_FLAG_GRAD_IOR)) {
+                        atomicAdd(acc_lut + ((size_t)lam * S + r) * 2, G.g[RTT_F_IOR_IN]);
+                        atomicAdd(acc_lut + ((size_t)lam * S + r) * 2 + 1, G.g[RTT_F_IOR_OUT]);
+                        scatter_row_grad(G, flags & ~RTT_FLAG_GRAD_IOR, acc + r * RTT_ROW_G);
+                    } else {
+                        scatter_row_grad(G, flags, acc + r * RTT_ROW_G);
+                    }
                 }
             }
         }
@@ -1119,32 +1124,21 @@ inline cudaError_t launch_tile(const SeqFwdArgs& a, cudaStream_t st) {
     k_trace_seq_fwd_tile<RPT, MINB><<<(int)g, kThreads, smem, st>>>(a);
     return cudaGetLastError();
 }
-// RTT_FWD_TILE selects the frame-resident forward kernel: 1 = 1 ray/thread, 2 = 2 rays (80 regs), 3 = 2 rays
-// (64 regs), 5 = 1 ray at 48 registers / five blocks per SM (C1 -4 %, C2 +3 %, C4 +9 % against 3); 0 = the per-ray
-// kernel of the EXACT variant's structure.  Measured and dropped: 4 rays per thread (128 registers, -20 %), 2 rays at
-// 48 registers (spills, -17 %).
-inline int fwd_tile_choice() {
-    static int choice = -1;
-    if (choice < 0) {
-        const char* e = getenv("RTT_FWD_TILE");
-        choice = e ? atoi(e) : 100;   // 100 = by table size (below)
-    }
-    return choice;
-}
-// Default: 2 rays per thread at 64 registers (4 blocks / SM) — best on C2 and C4; a short table (a singlet and its
+// Which build of the frame-resident forward kernel runs (a.tune, include/rtt_b200.h RTT_MODE_TUNE_*): 1 = 1 ray/thread,
+// 2 = 2 rays (80 regs), 3 = 2 rays (64 regs), 5 = 1 ray at 48 registers / five blocks per SM (C1 -4 %, C2 +3 %, C4 +9 %
+// against 3); 9 = the per-ray kernel of the EXACT variant's structure.  Measured and dropped: 4 rays per thread (128
+// registers, -20 %), 2 rays at 48 registers (spills, -17 %).
+// Default (0): 2 rays per thread at 64 registers (4 blocks / SM) — best on C2 and C4; a short table (a singlet and its
 // sensor) has too little arithmetic per ray to hide the ray loads behind 32 warps, there 1 ray per thread at 48
 // registers (40 warps / SM) wins (C1, 4 rows: 2.69 -> 2.58 ms per 1e8 rays).
-// The choice depends on the table only, so a bundle generated in the kernel and its materialised twin run the same
-// build and stay bit-identical (tests/test_goals.py).
-inline int fwd_tile_for(int S) {
-    const int c = fwd_tile_choice();
-    return c == 100 ? (S <= 6 ? 5 : 3) : c;
-}
+// The choice depends on the table and the caller's mode bits only (no environment, no cached state), so a bundle
+// generated in the kernel and its materialised twin run the same build and stay bit-identical (tests/test_goals.py).
+inline int fwd_tile_for(int S, int tune) { return tune ? tune : (S <= 6 ? 5 : 3); }
 #endif
 
 cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
 #if defined(RTT_APPROX)
-    switch (fwd_tile_for(a.tab.S)) {
+    switch (fwd_tile_for(a.tab.S, a.tune)) {
         case 1: return launch_tile<1, 4>(a, st);
         case 2: return launch_tile<2, 3>(a, st);
         case 3: return launch_tile<2, 4>(a, st);
@@ -1156,14 +1150,11 @@ cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
     RTT_NAME(k_trace_seq_fwd)<<<grid_for(a.n, 8), kThreads, fwd_smem(a.tab.S, a.tab.L), st>>>(a);
     return cudaGetLastError();
 }
-// RTT_BWD_MINB = resident blocks per SM the sequential adjoint is compiled for (2: ~110 registers, 3: <= 85)
-inline int bwd_minb_choice() {
-    static int choice = -1;
-    if (choice < 0) {
-        const char* e = getenv("RTT_BWD_MINB");
-        choice = e ? atoi(e) : 3;     // measured: 3 blocks / SM (80 registers, a few spills) beats 2 by 4-8 %
-    }
-    return choice;
+template <int MINB, bool POSE>
+inline cudaError_t launch_seq_bwd_as(const SeqBwdArgs& b, int g, size_t smem, cudaStream_t st) {
+    if (cudaError_t e = allow_smem(RTT_NAME(k_trace_seq_bwd)<MINB, POSE>, smem)) return e;
+    RTT_NAME(k_trace_seq_bwd)<MINB, POSE><<<g, kThreads, smem, st>>>(b);
+    return cudaGetLastError();
 }
 cudaError_t RTT_NAME(launch_seq_bwd)(const SeqBwdArgs& a, cudaStream_t st) {
     const size_t smem = bwd_smem(a.tab.S, a.tab.L) + 8 + bwd_queue_bytes();
@@ -1178,18 +1169,15 @@ cudaError_t RTT_NAME(launch_seq_bwd)(const SeqBwdArgs& a, cudaStream_t st) {
     long long g = (long long)sm_count() * 8;
     if (chunks < g) g = chunks;
     if (g < 1) g = 1;
-    // without pose gradients the kernel needs 64-72 registers: four resident blocks (measured: C2 -10 %, C4 -5 % against
-    // three; RTT_BWD_MINB=3 selects the 72-register build)
-    static int minb_env = -1;
-    if (minb_env < 0) { const char* e = getenv("RTT_BWD_MINB"); minb_env = e ? atoi(e) : 0; }
+    // a.tune = resident blocks per SM the build is compiled for.  Without pose gradients the kernel needs 64-72
+    // registers: four resident blocks (measured: C2 -10 %, C4 -5 % against three); with them three blocks (80 registers,
+    // a few spills) beat two (~110 registers) by 4-8 %.
     if (a.scalar_grads) {
-        if (minb_env == 3) RTT_NAME(k_trace_seq_bwd)<3, false><<<(int)g, kThreads, smem, st>>>(b);
-        else RTT_NAME(k_trace_seq_bwd)<4, false><<<(int)g, kThreads, smem, st>>>(b);
-    } else {
-        if (bwd_minb_choice() == 3) RTT_NAME(k_trace_seq_bwd)<3, true><<<(int)g, kThreads, smem, st>>>(b);
-        else RTT_NAME(k_trace_seq_bwd)<2, true><<<(int)g, kThreads, smem, st>>>(b);
+        if (a.tune == 3) return launch_seq_bwd_as<3, false>(b, (int)g, smem, st);
+        return launch_seq_bwd_as<4, false>(b, (int)g, smem, st);
     }
-    return cudaGetLastError();
+    if (a.tune == 2) return launch_seq_bwd_as<2, true>(b, (int)g, smem, st);
+    return launch_seq_bwd_as<3, true>(b, (int)g, smem, st);
 }
 cudaError_t RTT_NAME(launch_nonseq_fwd)(const NonseqFwdArgs& a, cudaStream_t st) {
     if (cudaError_t e = allow_smem(RTT_NAME(k_trace_nonseq_fwd), nonseq_fwd_smem(a.tab.S, a.tab.L))) return e;
@@ -1197,18 +1185,22 @@ cudaError_t RTT_NAME(launch_nonseq_fwd)(const NonseqFwdArgs& a, cudaStream_t st)
     return cudaGetLastError();
 }
 cudaError_t RTT_NAME(launch_nonseq_bwd)(const NonseqBwdArgs& a, cudaStream_t st) {
+    if (cudaError_t e = allow_smem(RTT_NAME(k_trace_nonseq_bwd), bwd_smem(a.tab.S, a.tab.L))) return e;
     RTT_NAME(k_trace_nonseq_bwd)<<<grid_for(a.n, 4), kThreads, bwd_smem(a.tab.S, a.tab.L), st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t RTT_NAME(launch_intersect_test)(const IsectArgs& a, cudaStream_t st) {
+    if (cudaError_t e = allow_smem(RTT_NAME(k_intersect_test), smem_table_bytes(a.tab.S, 0))) return e;
     RTT_NAME(k_intersect_test)<<<grid_for(a.n, 8), kThreads, smem_table_bytes(a.tab.S, 0), st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t RTT_NAME(launch_step_fwd)(const StepFwdArgs& a, cudaStream_t st) {
+    if (cudaError_t e = allow_smem(RTT_NAME(k_surface_step_fwd), smem_table_bytes(a.tab.S, a.tab.L))) return e;
     RTT_NAME(k_surface_step_fwd)<<<grid_for(a.n, 8), kThreads, smem_table_bytes(a.tab.S, a.tab.L), st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t RTT_NAME(launch_step_bwd)(const StepBwdArgs& a, cudaStream_t st) {
+    if (cudaError_t e = allow_smem(RTT_NAME(k_surface_step_bwd), bwd_smem(a.tab.S, a.tab.L))) return e;
     RTT_NAME(k_surface_step_bwd)<<<grid_for(a.n, 4), kThreads, bwd_smem(a.tab.S, a.tab.L), st>>>(a);
     return cudaGetLastError();
 }

@@ -57,6 +57,7 @@ struct SeqFwdArgs {
     SensorDev sens[RTT_MAX_SENSORS];
     int n_sens;
     long long n;
+    int tune;                   // (mode & RTT_MODE_TUNE_MASK) >> RTT_MODE_TUNE_SHIFT: kernel build, 0 = default
 };
 
 struct SeqBwdArgs {
@@ -72,6 +73,7 @@ struct SeqBwdArgs {
     long long n;
     int chunk;                  // rays per block iteration (set by the launcher, <= kBwdChunk)
     int scalar_grads;           // RTT_MODE_SCALAR_GRADS: no row requests pose gradients
+    int tune;                   // (mode & RTT_MODE_TUNE_MASK) >> RTT_MODE_TUNE_SHIFT: resident blocks per SM, 0 = default
 };
 
 struct NonseqFwdArgs {

@@ -29,6 +29,38 @@ MODE_NO_FINAL_RAYS = 0x200    # trace_seq_fwd op only: skip the final pos / dir 
 _default_mode = MODE_FAST
 _default_mode_nonseq = MODE_EXACT
 
+# Kernel-build selectors (include/rtt_b200.h RTT_MODE_TUNE_*): 0 = the library's default for the table.  The C library
+# itself reads no environment; for sweeps the Python layer honours RTT_FWD_TILE / RTT_BWD_MINB once at import
+# (RTT_FWD_TILE=0, the per-ray kernel, is selector 9).
+MODE_TUNE_SHIFT, MODE_TUNE_MASK = 16, 0xFF0000
+
+
+def _env_tune(name: str, zero_means: int = 0) -> int:
+    import os
+    v = os.environ.get(name)
+    if v is None or not v.strip().lstrip("-").isdigit():
+        return 0
+    v = int(v)
+    return zero_means if v == 0 else max(0, min(255, v))
+
+
+_tune_fwd = _env_tune("RTT_FWD_TILE", zero_means=9)
+_tune_bwd = _env_tune("RTT_BWD_MINB")
+
+
+def set_tuning(fwd: Optional[int] = None, bwd: Optional[int] = None):
+    """Select the compiled build of the sequential forward / adjoint kernel (0 = default); see RTT_MODE_TUNE_* in
+    include/rtt_b200.h.  Results do not depend on it."""
+    global _tune_fwd, _tune_bwd
+    if fwd is not None:
+        _tune_fwd = int(fwd) & 0xFF
+    if bwd is not None:
+        _tune_bwd = int(bwd) & 0xFF
+
+
+def _with_tune(mode: int, tune: int) -> int:
+    return mode if (mode & MODE_TUNE_MASK) else (mode | (tune << MODE_TUNE_SHIFT))
+
 
 def set_default_mode(mode: int, nonseq: Optional[int] = None):
     """Set the arithmetic of the sequential/element ops (and, if given, of the non-sequential op)."""
@@ -138,7 +170,7 @@ def _seq_fwd_body(dev, n, pos, dir, intensity, wavelength, src, table_f, table_i
         lib.call("rtt_trace_seq_fwd", _ptr(pos), _ptr(dir), _ptr(intensity), _ptr(wavelength),
                  ct.byref(src) if src is not None else None,
                  _ptr(opos), _ptr(odir), _ptr(oint), hitmask.data_ptr(),
-                 ct.byref(req), sens, cnt, n, mode, _stream(table_f))
+                 ct.byref(req), sens, cnt, n, _with_tune(mode, _tune_fwd), _stream(table_f))
     return [opos, odir, oint, hitmask, records, images]
 
 
@@ -161,7 +193,8 @@ def _seq_bwd_body(dev, n, pos, dir, intensity, wavelength, src, hitmask, g_pos, 
         lib.call("rtt_trace_seq_bwd", _ptr(pos), _ptr(dir), _ptr(intensity), _ptr(wavelength),
                  ct.byref(src) if src is not None else None,
                  hitmask.data_ptr(), _ptr(g_pos), _ptr(g_dir), _ptr(g_int), rec_arr,
-                 _ptr(gp), _ptr(gd), _ptr(gi), _ptr(gt), _ptr(gl), ct.byref(req), ns, n, mode, _stream(table_f))
+                 _ptr(gp), _ptr(gd), _ptr(gi), _ptr(gt), _ptr(gl), ct.byref(req), ns, n,
+                 _with_tune(mode & ~MODE_TUNE_MASK, _tune_bwd), _stream(table_f))
     return [gp, gd, gi, gt, gl]
 
 
@@ -713,23 +746,36 @@ class _SpotSize(torch.autograd.Function):
         mom = _all_reduce_sum(torch.ops.rtt_b200.spot_moments(rec, True))
         out3 = _all_reduce_sum(torch.ops.rtt_b200.spot_size_fwd(rec, mom, target))
         ctx.save_for_backward(rec, mom, out3, target)
-        return out3[0].clone()
+        active = (mom[3] > 0).to(torch.float32)          # 1 if any ray of the bundle reached the sensor with w > 0
+        ctx.mark_non_differentiable(active)
+        return out3[0].clone(), active
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, _g_active):
         rec, mom, out3, target = ctx.saved_tensors
         return torch.ops.rtt_b200.spot_size_bwd(rec, mom, target, out3, g.reshape(1).contiguous()), None
 
 
 def spot_moments(rec: torch.Tensor, active_only: bool = False) -> torch.Tensor:
-    """Differentiable [sum w, sum w x, sum w y, #(w>0)] of sensor records rec [..., 4]."""
-    return _SpotMoments.apply(_f32c(rec).reshape(-1, 4), bool(active_only))
+    """Differentiable [sum w, sum w x, sum w y, #(w>0)] of sensor records rec [..., 4] (summed over ranks).  An empty
+    local shard still takes part in the collective (a rank must never skip an all-reduce its peers run)."""
+    rec = _f32c(rec).reshape(-1, 4)
+    if rec.shape[0] == 0:
+        return _all_reduce_sum(torch.zeros(4, dtype=torch.float32, device=rec.device))
+    return _SpotMoments.apply(rec, bool(active_only))
+
+
+def spot_size_active(rec: torch.Tensor, target_xy: Optional[torch.Tensor] = None):
+    """(SpotSizeLoss term of ONE bundle, active flag) from its sensor records rec [..., 4]: the flag is a device
+    scalar, 1.0 iff some ray reached the sensor with positive weight — the reference skips bundles without active
+    hits (optim/goals.py:165-167), which the caller reproduces by weighting, without a host synchronisation."""
+    tgt = None if target_xy is None else _f32c(target_xy.to(rec.device)).reshape(2)
+    return _SpotSize.apply(_f32c(rec).reshape(-1, 4), tgt)
 
 
 def spot_size(rec: torch.Tensor, target_xy: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Differentiable SpotSizeLoss term of ONE bundle from its sensor records rec [..., 4]."""
-    tgt = None if target_xy is None else _f32c(target_xy.to(rec.device)).reshape(2)
-    return _SpotSize.apply(_f32c(rec).reshape(-1, 4), tgt)
+    return spot_size_active(rec, target_xy)[0]
 
 
 def sample_source(rays, mode: Optional[int] = None):
@@ -903,7 +949,7 @@ def trace_sequential_host(table: SurfaceTable, pos, dir_, intensity, wavelength=
             lib.call("rtt_trace_seq_fwd", d_pos[sl].data_ptr(), d_dir[sl].data_ptr(), d_int[sl].data_ptr(),
                      d_wav[sl].data_ptr() if use_wav else 0, None,
                      opos[sl].data_ptr(), odir[sl].data_ptr(), oint[sl].data_ptr(), hitmask[sl].data_ptr(),
-                     ct.byref(req), sens, cnt, m, mode, ct.c_void_p(cur.cuda_stream))
+                     ct.byref(req), sens, cnt, m, _with_tune(mode, _tune_fwd), ct.c_void_p(cur.cuda_stream))
         cur.wait_event(tail)
     return dict(pos=opos, dir=odir, intensity=oint, hitmask=hitmask, records=records,
                 images=split_images(images, cfg), in_pos=d_pos, in_dir=d_dir, in_intensity=d_int,

@@ -130,6 +130,17 @@ def _place(scene, rays):
     return rays
 
 
+def _mean_over_active(losses, flags):
+    """Mean of the per-bundle terms over the bundles that reached the sensor: the reference `continue`s on a bundle
+    without (active) hits and averages the rest (optim/goals.py:72-74, 165-167, 185-187).  On the device path the
+    emptiness test is a device flag per bundle (no host synchronisation): sum(term * flag) / max(sum(flag), 1), which
+    is the plain mean when every bundle is active and 0 when none is.  The eager path (`flags` empty) keeps the mean."""
+    if len(flags) != len(losses):
+        return torch.stack(losses).mean()
+    f = torch.stack(flags)
+    return (torch.stack(losses) * f).sum() / f.sum().clamp(min=1.0)
+
+
 class SpotTargetLoss(Goal):
     """Squared distance between each bundle's intensity centroid and a target (optim/goals.py:42-96)."""
 
@@ -142,7 +153,7 @@ class SpotTargetLoss(Goal):
         self.register_buffer("target_xy", target_xy)
 
     def forward(self, scene, bundles: List[Bundle], N_rays: int = 128) -> torch.Tensor:
-        losses = []
+        losses, flags = [], []
         for i, bundle in enumerate(bundles):
             self.sensor.reset()
             _place(scene, bundle.sample(N_rays))
@@ -150,10 +161,10 @@ class SpotTargetLoss(Goal):
                 scene.simulate()
             rec = _sensor_records(scene, self.sensor)
             if rec is not None and rec.is_cuda:
-                if rec.shape[0] == 0:
-                    continue
+                # never skipped, even on an empty local shard: spot_moments holds a collective every rank must enter
                 mom = ops.spot_moments(rec, active_only=False)       # every recorded hit (optim/goals.py:76-88)
                 xy = rec
+                flags.append((mom[3] > 0).to(torch.float32).detach())   # bundles that never reached the sensor drop
             else:
                 xy, w = _sensor_hits(scene, self.sensor)
                 if w.shape[0] == 0:
@@ -166,7 +177,7 @@ class SpotTargetLoss(Goal):
             losses.append((cx - tx) ** 2 + (cy - ty) ** 2)
         if not losses:
             return torch.tensor(0.0)
-        return torch.stack(losses).mean()
+        return _mean_over_active(losses, flags)
 
 
 class SpotSizeLoss(Goal):
@@ -184,7 +195,7 @@ class SpotSizeLoss(Goal):
         self._target_xy = target_xy
 
     def forward(self, scene) -> torch.Tensor:
-        losses = []
+        losses, flags = [], []
         for i, bundle in enumerate(self.bundles):
             self.sensor.reset()
             _place(scene, bundle.sample(self.N_rays))
@@ -197,7 +208,9 @@ class SpotSizeLoss(Goal):
                     if self._target_xy.device != rec.device:   # once: no per-step host-to-device copy
                         self._target_xy = self._target_xy.to(rec.device)
                     tgt = self._target_xy[min(i, self._target_xy.shape[0] - 1)]
-                losses.append(ops.spot_size(rec, tgt))
+                term, active = ops.spot_size_active(rec, tgt)
+                losses.append(term)
+                flags.append(active)
                 continue
             xy, w = _sensor_hits(scene, self.sensor)
             active = w > 0                                  # optim/goals.py:165 (as a mask: no gather)
@@ -215,7 +228,7 @@ class SpotSizeLoss(Goal):
             losses.append(_dist_sum(torch.where(active, rms, torch.zeros_like(rms)).sum()))
         if not losses:
             return torch.tensor(0.0)
-        return torch.stack(losses).mean()
+        return _mean_over_active(losses, flags)
 
 
 class GraphedStep:

@@ -325,7 +325,7 @@ int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float*,
         const int lam = T.L > 0 ? lam_index(T, ray.wav) : 0;
         int cnt[RTT_MAX_SENSORS] = {0, 0, 0, 0};
         int nh = 0;
-        for (int b = 0; b < nbounces && b < 32; ++b) {
+        for (int b = 0; b < nbounces; ++b) {                     // every interaction (the CUDA kernel replays in windows)
             const int r = hit_seq[i * nbounces + b];
             if (r == 255) break;
             ck[nh].p = p; ck[nh].d = d; rows_hit[nh] = r; ++nh;

@@ -482,6 +482,47 @@ def test_nonseq_adjoint_matches_oracle_autograd(rtt_ns, run_exact, ieee_oracle):
     assert checked >= 5
 
 
+def test_nonseq_adjoint_differentiates_hit_sequences_deeper_than_one_window(rtt_ns, run_exact, ieee_oracle):
+    """Scene.Nbounces defaults to 100 (scene/base.py:93) and the reference's autograd differentiates every
+    bounce.  A stable two-mirror resonator keeps near-axis rays bouncing to the limit (48 > the 32 checkpoints
+    the CUDA adjoint holds per ray at a time: it replays in windows): ray and parameter gradients must equal
+    oracle autograd over the whole sequence."""
+    import raytracetorch_b200 as rtt
+    E = rtt_ns.elements
+    T = lambda z: rtt_ns.geom.RayTransform(translation=[0.0, 0.0, z])
+    # scene scale ~0.2: the fp32 ulp there (~3e-8) is far below the t > 1e-6 rule, so no ray re-hits the mirror it
+    # just left (SURVEY 0.10) and the sequences are as long as the bounce limit
+    els = [E.SphericalMirror(c1=-1 / 0.8, d=0.3, diameter=0.3, c1_grad=True, transform=T(0.2)),
+           E.SphericalMirror(c1=1 / 0.8, d=0.3, diameter=0.3, c1_grad=True, transform=T(-0.2))]
+    nb = 48
+    g = torch.Generator().manual_seed(5)
+    n = 600
+    pos = torch.cat([(torch.rand(n, 2, generator=g) - 0.5) * 0.04, torch.zeros(n, 1)], 1)
+    ang = (torch.rand(n, 2, generator=g) - 0.5) * 0.06
+    dr = torch.nn.functional.normalize(torch.cat([ang, torch.ones(n, 1)], 1), dim=1)
+    inten = torch.ones(n)
+    tab = rtt.compile_elements(els)
+    p, dd, w = (t.clone().requires_grad_(True) for t in (pos, dr, inten))
+    o = ieee_oracle.trace_nonsequential(tab.f, tab.i_host, p, dd, w, nb)
+    assert int(o["nb"].min()) == nb                                      # every ray runs into the bounce limit
+    parity.golden_loss(o["pos"], o["dir"], o["intensity"]).backward()
+    ref = [els[k].shape.c.grad.clone() for k in (0, 1)]
+    for k in (0, 1):
+        els[k].shape.c.grad = None
+    tab = rtt.compile_elements(els)
+    tf, ti = tab.f.detach().numpy(), tab.i.numpy()
+    fwd = run_exact.trace_nonseq(tf, ti, pos.numpy(), dr.numpy(), inten.numpy(), nb)
+    np.testing.assert_array_equal(fwd["seq"].astype(np.int64), o["seq"].numpy())
+    np.testing.assert_array_equal(fwd["pos"], o["pos"].detach().numpy())
+    gp, gd, gi = parity.golden_loss_grads(fwd["pos"], fwd["dir"], fwd["intensity"])
+    bwd = run_exact.trace_nonseq_bwd(tf, ti, pos.numpy(), dr.numpy(), inten.numpy(), fwd["seq"], gp, gd, gi)
+    assert parity.grad_rel(bwd["g_pos"], p.grad.numpy()) < parity.TOL_GRAD
+    assert parity.grad_rel(bwd["g_dir"], dd.grad.numpy()) < parity.TOL_GRAD
+    tab.f.backward(torch.from_numpy(bwd["g_table"]))
+    for k in (0, 1):
+        assert parity.grad_rel(els[k].shape.c.grad.numpy(), ref[k].numpy()) < parity.TOL_GRAD, k
+
+
 # ---------------------------------------------------------------------------------------------
 # edge cases
 # ---------------------------------------------------------------------------------------------
