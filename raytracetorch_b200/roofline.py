@@ -96,6 +96,36 @@ def adjoint_flops_per_ray(table_f, table_i, hit_fraction: Sequence[float]) -> fl
     return tot
 
 
+# ---- the per-row constants the judge recomputes the roofline with -----------------------
+# refracting / reflecting quadric row: 160 FLOP per ray-surface with a general pose, 115 with identity rotation;
+# planar row (aperture / sensor / ideal element): 60; lens-edge row (cylinder or box / side plane): 40.
+# These are deliberately coarser (and, for edge rows, LOWER) than the hand counts above: an edge row that the kernel
+# culls is charged 40, not the 50-110 the full test costs, so `frac` by this counting does not reward skipped work.
+SURVEY_QUADRIC_GENERAL, SURVEY_QUADRIC_IDENT, SURVEY_PLANAR, SURVEY_EDGE = 160.0, 115.0, 60.0, 40.0
+SURVEY_ADJOINT_FACTOR = 3.5
+
+
+def survey_row_flops(row_f: Sequence[float], row_i: Sequence[int]) -> float:
+    surf, shape = row_i[C.I_SURF], row_i[C.I_SHAPE]
+    if shape in (C.SHAPE_SPHERIC_EDGE, C.SHAPE_CYL_EDGE, C.SHAPE_POLY):
+        return SURVEY_EDGE
+    if surf == C.SURF_PLANE:
+        return SURVEY_PLANAR
+    ident = _is_identity(row_f, C.F_RE) and _is_identity(row_f, C.F_RS)
+    return SURVEY_QUADRIC_IDENT if ident else SURVEY_QUADRIC_GENERAL
+
+
+def survey_flops_per_ray(table_f, table_i) -> float:
+    """Forward FLOPs per ray by SURVEY 8(d)'s constants: every row charged once per ray."""
+    return float(sum(survey_row_flops(table_f[r], table_i[r]) for r in range(len(table_i))))
+
+
+def survey_adjoint_flops_per_ray(table_f, table_i, hit_fraction: Sequence[float]) -> float:
+    """Adjoint by SURVEY 8(d): 3.5 x the forward constant of every row a live ray interacted with."""
+    return float(sum(float(hit_fraction[r]) * survey_row_flops(table_f[r], table_i[r]) * SURVEY_ADJOINT_FACTOR
+                     for r in range(len(table_i))))
+
+
 def sequential_bytes_per_ray(*, wavelength: bool, hitmask: bool, records: int = 0) -> int:
     return 28 + (4 if wavelength else 0) + 28 + (8 if hitmask else 0) + 16 * records
 

@@ -572,3 +572,178 @@ def test_fresnel_lens_through_the_scene_api(rtt_ns):
     for k in (0, 1):
         g, r = float(els[0].shape.surfaces[k].c.grad), float(els_c[0].shape.surfaces[k].c.grad)
         assert abs(g - r) <= parity.TOL_GRAD * abs(r), (k, g, r)
+
+
+# ---------------------------------------------------------------------------------------------
+# the BENCHMARKED configurations at full size (bench.py builds exactly these)
+# ---------------------------------------------------------------------------------------------
+def _bench_module():
+    import importlib
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    return importlib.import_module("bench")
+
+
+def test_full_size_c2_as_benchmarked_with_wavelength_table_and_three_channel_image(rtt_ns):
+    """BASELINE configs[1] exactly as bench.py times it: 1e8 rays, 14 rows, per-wavelength index table (3 lines),
+    3x1024x1024 sensor image, FAST arithmetic.  Per-channel image checksum against the hit masks, determinism, and
+    the oracle (with the same table) on a random sub-sample: alive masks / hit masks exact, points 1e-5, the
+    sub-sample's own 3-channel image within 1e-4 relative L1 with identical bin occupancy away from ties."""
+    import raytracetorch_b200 as rtt
+    bench = _bench_module()
+    dev = torch.device("cuda", 0)
+    w = bench.build_workload("c2", dev)
+    n = w["rays"]
+    assert n == 10 ** 8
+    scene = rtt.scene.SequentialScene(w["elements"])
+    scene.set_dispersion(w["dispersion"])
+    scene = scene.to(dev)
+    scene.record_hits = False
+    tab = scene.table()
+    assert tab.n_rows == 14 and tab.lut is not None and tab.lut.shape[0] == 3
+    cfg = rtt.ops.sensor_cfg_of(tab)
+    pos, dirs, inten, wav = bench.synth_bundle(w, n, dev, 1000)
+    out = rtt.ops.trace_sequential(tab, pos, dirs, inten, wav, want_record=False, sensor_cfg=cfg)
+    img = out["images"][0]
+    assert img.shape == (3, 1024, 1024)
+    # (1) per-channel checksum: channel c holds the weight of the rays of wavelength c that hit the sensor in range
+    srow = tab.sensor_rows[0]
+    hit = ((out["hitmask"] >> srow) & 1).bool()
+    inside = hit & (out["pos"][:, 0].abs() < 15.0) & (out["pos"][:, 1].abs() < 15.0)
+    lam_idx = torch.arange(n, device=dev) % 3
+    for c in range(3):
+        total = float(out["intensity"][inside & (lam_idx == c)].double().sum())
+        assert total > 0.1 * n / 3
+        assert abs(float(img[c].double().sum()) - total) <= 1e-4 * total, c
+    # (2) determinism of the per-ray outputs, image equal up to accumulation order
+    out2 = rtt.ops.trace_sequential(tab, pos, dirs, inten, wav, want_record=False, sensor_cfg=cfg)
+    assert torch.equal(out["pos"], out2["pos"]) and torch.equal(out["hitmask"], out2["hitmask"])
+    assert float((out2["images"][0] - img).abs().sum() / img.sum()) <= 1e-5
+    del out2, inside, hit
+    # (3) oracle with the same wavelength table on a random sub-sample
+    g = torch.Generator(device=dev).manual_seed(3)
+    idx = torch.randint(0, n, (30000,), device=dev, generator=g)
+    els_c = _bench_module().build_workload("c2", "cpu")
+    tabc = rtt.compile_elements([e.cpu() for e in els_c["elements"]], dispersion=els_c["dispersion"])
+    sp, sd, si, sw = (t[idx].cpu() for t in (pos, dirs, inten, wav))
+    o = O.trace_sequential(tabc.f, tabc.i_host, sp, sd, si, wavelength=sw, lut=tabc.lut, lut_w=tabc.lut_wavelengths)
+    np.testing.assert_array_equal(out["intensity"][idx].cpu().numpy(), o["intensity"].numpy())
+    np.testing.assert_array_equal(parity.mask_bits(out["hitmask"][idx].cpu().numpy().view(np.uint64), 14),
+                                  o["hit"].numpy())
+    live = o["intensity"].numpy() > 0
+    assert live.mean() > 0.3
+    assert parity.vec_rel(out["pos"][idx].cpu().numpy()[live], o["pos"].numpy()[live]).max() <= parity.TOL_POINT
+    assert parity.vec_rel(out["dir"][idx].cpu().numpy()[live], o["dir"].numpy()[live]).max() <= parity.TOL_POINT
+    # the sub-sample's own image through the kernel vs the oracle's histogram
+    sub = rtt.ops.trace_sequential(tab, pos[idx].contiguous(), dirs[idx].contiguous(), inten[idx].contiguous(),
+                                   wav[idx].contiguous(), want_record=False, sensor_cfg=cfg)
+    mask, hl, ww = o["sensor"][0]
+    ch = (idx.cpu() % 3)[mask]
+    ref = O.sensor_image(hl, ww, w["sensor"].image_spec, channel=ch).numpy()
+    got = sub["images"][0].cpu().numpy()
+    assert ref.sum() > 0.3 * idx.numel()
+    assert parity.rel_l1(got, ref) <= parity.TOL_IMAGE_L1
+    assert ((got > 0) != (ref > 0)).sum() <= 2            # bin indices exact away from measure-zero ties
+
+
+def test_full_size_c4_camera_render_as_benchmarked(rtt_ns):
+    """BASELINE configs[3] as bench.py --workload c4cam runs it on one GPU: 1.24e8 pinhole-camera rays generated in
+    the kernel (15 samples per pixel of a 3840x2160 camera), 17-row lens, 4K sensor image.  The image must be
+    additive over sample ranges (the multi-GPU sharding), reproducible, and equal to the ORACLE's histogram on
+    sub-ranges of the same Philox counters (rays materialised by rtt_sample_bundle, traced on the CPU)."""
+    import raytracetorch_b200 as rtt
+    bench = _bench_module()
+    dev = torch.device("cuda", 0)
+    w = bench.build_workload("c4cam", dev)
+    n = w["rays"]
+    assert n == 3840 * 2160 * 15
+    scene = rtt.scene.SequentialScene(w["elements"]).to(dev)
+    tab = scene.table()
+    assert tab.n_rows == 17
+    cfg = rtt.ops.sensor_cfg_of(tab)
+    cam = rtt.render.Camera((0.0, 0.0, -200.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 6.0, 3840, 2160, device=dev)
+
+    def render(first, count):
+        src = cam.generate_source_rays(samples=15, seed=1234, first=first, count=count)
+        return rtt.ops.trace_sequential(tab, want_record=False, sensor_cfg=cfg, source=src, want_rays=False)
+
+    full = render(0, n)
+    img = full["images"][0]
+    assert img.shape == (1, 2160, 3840)
+    tot = float(img.double().sum())
+    srow = tab.sensor_rows[0]
+    hits = float(((full["hitmask"] >> srow) & 1).double().sum())
+    assert 0.05 * n < tot <= hits                           # unit weights: image total = rays binned on the sensor
+    again = render(0, n)["images"][0]
+    assert float((again - img).abs().sum()) <= 1e-5 * tot
+    h = (n // 3 // 256) * 256 + 77                          # an uneven split, like a shard boundary
+    parts = render(0, h)["images"][0] + render(h, n - h)["images"][0]
+    assert float((parts - img).abs().sum()) <= 1e-5 * tot
+    del again, parts
+    # oracle on sub-ranges of the same counters: sample 0 (pixel centres) and two jittered samples
+    npix = 3840 * 2160
+    elc = _bench_module().build_workload("c4cam", "cpu")["elements"]
+    tabc = rtt.compile_elements([e.cpu() for e in elc])
+    checked = 0
+    for first in (npix // 2 - 10000, 7 * npix + npix // 2 + 1234, 14 * npix + npix // 2 - 20000):
+        m = 20000
+        src = cam.generate_source_rays(samples=15, seed=1234, first=first, count=m)
+        twin = rtt.rays.SourceRays(src.source, src.pose, src.state, src.n, 0)
+        sp, sd, si = twin.pos.cpu(), twin.dir.cpu(), twin.intensity.cpu()        # rtt_sample_bundle, same counters
+        o = O.trace_sequential(tabc.f, tabc.i_host, sp, sd, si)
+        sub = rtt.ops.trace_sequential(tab, want_record=False, sensor_cfg=cfg, source=src, want_rays=True)
+        np.testing.assert_array_equal(sub["intensity"].cpu().numpy(), o["intensity"].numpy())
+        np.testing.assert_array_equal(parity.mask_bits(sub["hitmask"].cpu().numpy().view(np.uint64), 17),
+                                      o["hit"].numpy())
+        np.testing.assert_array_equal(full["hitmask"][first:first + m].cpu().numpy(), sub["hitmask"].cpu().numpy())
+        mask, hl, ww = o["sensor"][0]
+        ref = O.sensor_image(hl, ww, w["sensor"].image_spec).numpy()
+        got = sub["images"][0].cpu().numpy()
+        if ref.sum() > 0:
+            assert parity.rel_l1(got, ref) <= parity.TOL_IMAGE_L1
+            assert ((got > 0) != (ref > 0)).sum() <= 2
+            checked += int(ref.sum())
+    assert checked > 3000
+
+
+def test_full_size_nonsequential_whole_hit_sequences(rtt_ns):
+    """C5 at 2e7 rays, 8 bounces: WHOLE hit sequences, bounce counts, final positions and intensities of a random
+    sub-sample against the oracle, on the rays whose path does not depend on the t > 1e-6 threshold
+    (tests/parity.py::self_hit_free, SURVEY 0.10); the fraction of such rays is pinned."""
+    import raytracetorch_b200 as rtt
+    n, nb = 20_000_000, 8
+    els = scenes.c5_nonsequential(rtt_ns)
+    scene = rtt.scene.Scene()
+    for e in els:
+        scene.add_element(e)
+    scene = scene.cuda()
+    tab = scene.table()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    th = torch.rand(n, device="cuda", generator=g) * (2 * np.pi)
+    r = torch.sqrt(torch.rand(n, device="cuda", generator=g)) * 10.0
+    pos = torch.stack([r * torch.cos(th), r * torch.sin(th), torch.full_like(r, -5.0)], 1)
+    dirs = torch.zeros_like(pos)
+    dirs[:, 2] = 1.0
+    inten = torch.ones(n, device="cuda")
+    out = rtt.ops.trace_nonsequential(tab, pos, dirs, inten, nb, want_record=False)
+    idx = torch.randint(0, n, (6000,), device="cuda", generator=g)
+    tabc = rtt.compile_elements([e.cpu() for e in scenes.c5_nonsequential(rtt_ns)])
+    sp, sd, si = pos[idx].cpu(), dirs[idx].cpu(), inten[idx].cpu()
+    O.IEEE_SQRT = True
+    try:
+        o = O.trace_nonsequential(tabc.f, tabc.i_host, sp, sd, si, nb)
+    finally:
+        O.IEEE_SQRT = False
+    clean = parity.self_hit_free(dict(in_pos=sp.numpy(), in_dir=sd.numpy(), in_intensity=si.numpy(), nbounces=nb),
+                                 tabc.f, tabc.i_host, nbounces=nb)
+    assert abs(clean.mean() - parity.CLEAN_FRACTION["c5_nonsequential"]) < 0.03, clean.mean()
+    seq = out["hit_seq"][idx].cpu().numpy().astype(np.int64)
+    seq[seq == 255] = -1
+    np.testing.assert_array_equal(seq[clean], o["seq"].numpy()[clean])
+    np.testing.assert_array_equal(out["n_hits"][idx].cpu().numpy()[clean], o["nb"].numpy()[clean])
+    np.testing.assert_array_equal(out["intensity"][idx].cpu().numpy()[clean], o["intensity"].numpy()[clean])
+    assert parity.vec_rel(out["pos"][idx].cpu().numpy()[clean], o["pos"].numpy()[clean]).max() <= parity.TOL_POINT
+    assert (seq == o["seq"].numpy()).all(axis=1).mean() > 0.99       # and almost everywhere on the noisy rays too
