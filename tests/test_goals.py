@@ -296,12 +296,14 @@ def test_bundle_transform_gradients_reach_the_source_pose(rtt_ns):
     tr = rtt.geom.RayTransformBundle(translation=[0.3, -0.2, -10.0], rotation=[0.01, -0.02, 0.0],
                                      trans_grad=True, rot_grad=True).to(dev)
     bundle = rtt.rays.CollimatedDisk(4.0, 2, device=dev, transform=tr)
+    rtt.rays._SRC_STATE.clear()
     torch.manual_seed(11)
     state0 = rtt.rays.source_state(dev).clone()
     rays = bundle.sample(n)
     assert not isinstance(rays, SourceRays) and rays.pos.requires_grad and rays.dir.requires_grad
     # with frozen pose parameters the in-kernel source is used, and it draws the same rays
     tr_frozen = rtt.geom.RayTransformBundle(translation=[0.3, -0.2, -10.0], rotation=[0.01, -0.02, 0.0]).to(dev)
+    rtt.rays._SRC_STATE.clear()                      # re-key: the same seed again does not reset the device counter
     torch.manual_seed(11)
     twin = rtt.rays.CollimatedDisk(4.0, 2, device=dev, transform=tr_frozen).sample(n)
     assert isinstance(twin, SourceRays) and torch.equal(twin.state, state0)
