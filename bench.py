@@ -449,9 +449,15 @@ def run_gpu_arm(args):
     rank, world, local = rdist.init_from_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cores = rdist.bind_to_gpu_numa(local)       # before any pinned allocation: staging memory lands on the GPU's node
     lib = _cabi.load()
     w = build_workload(args.workload, dev)
     n = int(args.rays or w["rays"])
+    if args.scaling == "strong":
+        # fixed TOTAL work: the bundle of --rays (default: the workload's BASELINE size) is split over the ranks
+        lo, hi = rdist.shard_bounds(n, rank, world)
+        n = hi - lo
+    overlap = rdist.OverlappedReducer(dev) if (world > 1 and not args.no_overlap) else None
     if w["nonseq"]:
         scene = rtt.scene.Scene()
         for e in w["elements"]:
@@ -476,23 +482,27 @@ def run_gpu_arm(args):
     cfg = rtt.ops.sensor_cfg_of(table)
     img_numel = sum(int(cfg[k]) * int(cfg[k + 1]) * int(cfg[k + 2]) for k in range(0, len(cfg), rtt.ops.SENSOR_CFG))
 
+    def reduce_images(out):
+        """The one collective of a step: all-reduce of the sensor image(s).  Default: on a side stream, so that it
+        runs under the next step's trace (dist.OverlappedReducer; drained inside the timed region)."""
+        if world == 1:
+            return
+        if overlap is not None:
+            overlap.submit(out["images"])
+        else:
+            red = rdist.FlatReducer()
+            red.extend(out["images"])
+            red.reduce()
+
     def fwd_step():
         if camera_src is not None:
             out = rtt.ops.trace_sequential(table, want_record=False, sensor_cfg=cfg, source=camera_src, want_rays=False)
-            if world > 1:
-                red = rdist.FlatReducer()
-                red.extend(out["images"])
-                red.reduce()
-            return out
-        if w["nonseq"]:
+        elif w["nonseq"]:
             out = rtt.ops.trace_nonsequential(table, pos, dirs, inten, w["nbounces"], wav, want_record=False,
                                               sensor_cfg=cfg)
         else:
             out = rtt.ops.trace_sequential(table, pos, dirs, inten, wav, want_record=False, sensor_cfg=cfg)
-        if world > 1:
-            red = rdist.FlatReducer()
-            red.extend(out["images"])
-            red.reduce()
+        reduce_images(out)
         return out
 
     def barrier():
@@ -514,6 +524,8 @@ def run_gpu_arm(args):
     out = None
     for _ in range(max(args.warmup, 1)):
         out = fwd_step()
+    if overlap is not None:
+        overlap.drain()
     torch.cuda.synchronize()
     # interactions actually counted per ray
     if w["nonseq"]:
@@ -537,6 +549,8 @@ def run_gpu_arm(args):
     e0.record()
     for _ in range(args.steps):
         fwd_step()
+    if overlap is not None:
+        overlap.drain()                 # the last steps' reductions end inside the timed region
     e1.record()
     barrier()
     launches = lib.launch_count() - launches0
@@ -864,12 +878,16 @@ def run_gpu_arm(args):
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                    ms_per_step=ms_step, higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32",
                     data="synthetic",
                     config=dict(workload=w["desc"], rays_per_gpu=n, rows=S, tests_per_ray=tests_per_ray,
                                 alive_fraction=alive, l2="inputs larger than L2 (>= 1 GB per array)",
                                 mode="FAST (FMA contraction)" if not w["nonseq"] else "EXACT (reference rounding)",
-                                collective="all_reduce(sensor image) per step" if world > 1 else "none"),
+                                collective=("none" if world == 1 else
+                                            "all_reduce(sensor image) per step, " +
+                                            ("on a side stream under the next step's trace" if overlap is not None
+                                             else "on the trace stream")),
+                                numa_cores=(f"{numa_cores[0]}-{numa_cores[-1]} ({len(numa_cores)})" if numa_cores else None)),
                     clocks=clocks, gpu_launches=launches, roofline=roof)
         if fb:
             line["fwd_bwd"] = fb
@@ -1086,6 +1104,10 @@ def main():
                     help="--impl reference: skip the unmodified benchmarks/sim_benchmark.main() run")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --rays per GPU (default); strong: the workload's total ray count is split over the ranks")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N > 1: run the image all-reduce on the trace stream instead of a side stream")
+    ap.add_argument("--no-config4", action="store_true",
+                    help="default workload only: skip the extra BASELINE config-4 (camera render) measurement")
     ap.add_argument("--no-graph", action="store_true", help="c3: run the optimisation step eagerly (no CUDA graph)")
     ap.add_argument("--graph-multi", action="store_true",
                     help="c3 with several ranks: capture the step including its NCCL all-reduces (see run_c3)")

@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include "rtt_core.cuh"
 #include "rtt_tile.cuh"
+#include "rtt_pair.cuh"
 #include "rtt_kernels_decl.h"
 
 namespace rtt {
@@ -141,34 +142,41 @@ __device__ __forceinline__ SourceKey fetch_key(const Args& a) {
 //      shared-memory CAS.  The cache is flushed with one global atomic per occupied slot when
 //      the persistent block has finished its rays.
 // Zero weights (dead rays that still cross the sensor) add nothing and are skipped.
-constexpr int kImgLog = 12;
-constexpr int kImgSlots = 1 << kImgLog;   // 4096 (bin, partial sum) pairs = 32 KB per block
+constexpr int kImgLog = 12;                // default: 4096 (bin, partial sum) pairs = 32 KB per block
+constexpr int kImgSlots = 1 << kImgLog;
 constexpr int kImgProbes = 4;             // linear probes before falling through to a global atomic
 constexpr int kImgMaxFails = 256;         // spread-out image (the cache is full of other bins): stop probing, go global directly
 constexpr int kImgKeyBits = 28;           // key = sensor slot << 28 | flat bin index
 
-struct ImgCache {
-    int* tag;          // [kImgSlots], -1 = empty
-    float* val;        // [kImgSlots]
+// LOG = log2 of the slot count: the kernels that also stage ray tiles in shared memory carry a smaller cache
+template <int LOG>
+struct ImgCacheT {
+    int* tag;          // [1 << LOG], -1 = empty
+    float* val;        // [1 << LOG]
     int* fails;        // [1] probes that found no slot; the cache switches itself off beyond kImgMaxFails
 };
+typedef ImgCacheT<kImgLog> ImgCache;
 
-__host__ __device__ inline size_t img_cache_bytes() { return (size_t)kImgSlots * 8 + 16; }
+template <int LOG = kImgLog>
+__host__ __device__ constexpr size_t img_cache_bytes() { return ((size_t)1 << LOG) * 8 + 16; }
 
-__device__ __forceinline__ ImgCache img_cache_carve(unsigned char* base) {
-    ImgCache c;
+template <int LOG = kImgLog>
+__device__ __forceinline__ ImgCacheT<LOG> img_cache_carve(unsigned char* base) {
+    ImgCacheT<LOG> c;
     c.tag = reinterpret_cast<int*>(base);
-    c.val = reinterpret_cast<float*>(c.tag + kImgSlots);
-    c.fails = reinterpret_cast<int*>(c.val + kImgSlots);
+    c.val = reinterpret_cast<float*>(c.tag + (1 << LOG));
+    c.fails = reinterpret_cast<int*>(c.val + (1 << LOG));
     return c;
 }
 
-__device__ __forceinline__ void img_cache_init(ImgCache c) {
-    for (int idx = threadIdx.x; idx < kImgSlots; idx += blockDim.x) { c.tag[idx] = -1; c.val[idx] = 0.0f; }
+template <int LOG>
+__device__ __forceinline__ void img_cache_init(ImgCacheT<LOG> c) {
+    for (int idx = threadIdx.x; idx < (1 << LOG); idx += blockDim.x) { c.tag[idx] = -1; c.val[idx] = 0.0f; }
     if (threadIdx.x == 0) *c.fails = 0;
 }
 
-__device__ __forceinline__ void img_cache_add(ImgCache c, float* image, int slot, int bin, float w) {
+template <int LOG>
+__device__ __forceinline__ void img_cache_add(ImgCacheT<LOG> c, float* image, int slot, int bin, float w) {
     if (*reinterpret_cast<volatile int*>(c.fails) >= kImgMaxFails) {     // cache switched off: one RED per deposit
         atomicAdd(image + bin, w);
         return;
@@ -193,21 +201,22 @@ __device__ __forceinline__ void img_cache_add(ImgCache c, float* image, int slot
         }
     }
     if (*reinterpret_cast<volatile int*>(c.fails) < kImgMaxFails) {
-        int s = (int)(((unsigned)key * 2654435761u) >> (32 - kImgLog));
+        int s = (int)(((unsigned)key * 2654435761u) >> (32 - LOG));
 #pragma unroll 1
         for (int probe = 0; probe < kImgProbes; ++probe) {
             const int old = atomicCAS(c.tag + s, -1, key);
             if (old == -1 || old == key) { atomicAdd(c.val + s, sum); return; }
-            s = (s + 1) & (kImgSlots - 1);
+            s = (s + 1) & ((1 << LOG) - 1);
         }
         atomicAdd(c.fails, 1);
     }
     atomicAdd(image + bin, sum);
 }
 
-__device__ __forceinline__ void img_cache_flush(ImgCache c, const SensorDev* sens) {
+template <int LOG>
+__device__ __forceinline__ void img_cache_flush(ImgCacheT<LOG> c, const SensorDev* sens) {
     __syncthreads();
-    for (int idx = threadIdx.x; idx < kImgSlots; idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < (1 << LOG); idx += blockDim.x) {
         const int key = c.tag[idx];
         if (key >= 0 && c.val[idx] != 0.0f)
             atomicAdd(sens[key >> kImgKeyBits].image + (key & ((1 << kImgKeyBits) - 1)), c.val[idx]);
@@ -215,7 +224,8 @@ __device__ __forceinline__ void img_cache_flush(ImgCache c, const SensorDev* sen
 }
 
 // `ordinal` = how many times this ray has interacted with this sensor before, `n` = bundle size
-__device__ __forceinline__ void sensor_deposit(const SensorDev& sd, ImgCache c, int slot, long long i, V3 hl, float w,
+template <int LOG>
+__device__ __forceinline__ void sensor_deposit(const SensorDev& sd, ImgCacheT<LOG> c, int slot, long long i, V3 hl, float w,
                                                int lam, int ordinal = 0, long long n = 0) {
     if (sd.record && ordinal < sd.K) {
         float4* rec = reinterpret_cast<float4*>(sd.record);
@@ -235,9 +245,9 @@ __device__ __forceinline__ void sensor_deposit(const SensorDev& sd, ImgCache c, 
 // ============================================================================================
 
 // One row of the sequential walk for one ray (scene/sequential.py:19-34), kinds fixed by K.
-template <class K>
+template <class K, int LOG = kImgLog>
 __device__ __forceinline__ void seq_row(const SmemTable& T, int S, int L, int r, int lam, long long i,
-                                        const SeqFwdArgs& a, ImgCache cache, V3& p, V3& d, float& I,
+                                        const SeqFwdArgs& a, ImgCacheT<LOG> cache, V3& p, V3& d, float& I,
                                         unsigned long long& mask, unsigned long long bit) {
     Frames F; Roots q; float t; int which;
     if (!intersect<true, K>(T.rows, r, p, d, F, q, t, which)) return;
@@ -438,6 +448,332 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_tile(const __g
             }
         }
     }
+    img_cache_flush(cache, a.sens);
+}
+
+// ============================================================================================
+// Sequential trace, forward, FAST variant: packed ray pairs + bulk-async ray streaming
+// ============================================================================================
+// k_trace_seq_fwd_pair is the tile kernel's successor for Blackwell:
+//   * ARITHMETIC: the two rays of a thread are the two lanes of f32x2 operands (rtt_pair.cuh: FFMA2 / FMUL2 / FADD2):
+//     the FMA-pipe share of the per-row work issues once for both rays;
+//   * RAY I/O (STREAM = true): no thread touches global memory for rays.  A block's tile of 512 rays is a handful of
+//     CONTIGUOUS spans of the caller's AoS arrays (pos 6 KB, dir 6 KB, intensity 2 KB, wavelength 2 KB), so one elected
+//     thread moves them with 1-D bulk-async copies (cp.async.bulk = the TMA engine, SASS UBLKCP) into a two-slot
+//     shared-memory ring, completion signalled on an mbarrier (SYNCS); the threads read their rays from shared memory
+//     (stride-3 words: bank-conflict free), write the results back into the same slot, and the slot leaves as bulk
+//     stores.  The load of tile k+2 is issued when tile k has left its slot, i.e. a whole tile of arithmetic (~10 us)
+//     ahead of its use: the ray loads never sit on a dependency chain, and the address arithmetic of 17 strided
+//     LDG / STG per ray (the tile kernel's: 119 of its 137 global accesses) is gone from the issue stream.
+//     One __syncthreads per tile (results complete -> elected thread stores).
+// Rays generated in the kernel (rtt_source_t), unaligned caller buffers and the ragged last tile take the same
+// arithmetic with plain loads / stores (STREAM = false build, or the cooperative copy below).
+constexpr int kPairTile = 2 * kThreads;                                  // rays per block iteration
+constexpr int kSlotPos = 0, kSlotDir = kPairTile * 12, kSlotInt = kPairTile * 24, kSlotWav = kPairTile * 28,
+              kSlotMask = kPairTile * 32, kSlotBytes = kPairTile * 40;   // 20 KB per slot
+constexpr int kPairSlots = 2;
+
+// ---- bulk-async copy / mbarrier primitives (PTX ISA 8.x, sm_90+; SASS: UBLKCP, SYNCS) --------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a copy that never lands (a bug) must end the kernel with an error, not hang the GPU
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && spin > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst_smem, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, unsigned src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to shared memory -> visible to the async proxy (bulk stores read the slot)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// shared-memory layout of the pair kernel, all at compile-time offsets: [image cache | Xf[MAX_ROWS+1] | ray slots | mbarriers | table]
+template <int LOG, bool STREAM>
+struct PairLayout {
+    static constexpr size_t kOffXf = (img_cache_bytes<LOG>() + 15) / 16 * 16;
+    static constexpr size_t kOffSlots = (kOffXf + sizeof(Xf) * (RTT_MAX_ROWS + 1) + 127) / 128 * 128;
+    static constexpr size_t kOffBar = kOffSlots + (STREAM ? (size_t)kPairSlots * kSlotBytes : 0);
+    static constexpr size_t kOffTable = kOffBar + 16;
+    __host__ __device__ static size_t bytes(int S, int L) { return kOffTable + smem_table_bytes(S, L); }
+};
+
+// reference-order walk of an irregular ray (see seq_walk_generic), for the pair kernel's layout
+template <int LOG, bool STREAM>
+__device__ __noinline__ WalkState pair_walk_generic(const SeqFwdArgs& a, int lam, long long i, WalkState w) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = a.tab.S, L = a.tab.L;
+    SmemTable T = carve(smem_raw + PairLayout<LOG, STREAM>::kOffTable, S, L);
+    ImgCacheT<LOG> cache = img_cache_carve<LOG>(smem_raw);
+    unsigned long long bit = 1ull;
+    for (int r = 0; r < S; ++r, bit += bit) seq_row<KDyn, LOG>(T, S, L, r, lam, i, a, cache, w.p, w.d, w.I, w.mask, bit);
+    return w;
+}
+
+// ray `loc` of the tile staged in a slot
+__device__ __forceinline__ RayIn slot_ray(const unsigned char* slot, int loc, bool want_wav) {
+    const float* sp = reinterpret_cast<const float*>(slot + kSlotPos);
+    const float* sd = reinterpret_cast<const float*>(slot + kSlotDir);
+    RayIn r;
+    r.p = v3(sp[3 * loc], sp[3 * loc + 1], sp[3 * loc + 2]);
+    r.d = v3(sd[3 * loc], sd[3 * loc + 1], sd[3 * loc + 2]);
+    r.I = reinterpret_cast<const float*>(slot + kSlotInt)[loc];
+    r.wav = want_wav ? reinterpret_cast<const float*>(slot + kSlotWav)[loc] : 0.0f;
+    return r;
+}
+
+// sensor deposits of a pair: lane 0 / 1 = rays i0, i0 + kThreads
+template <int LOG>
+struct PairDeposit {
+    const SeqFwdArgs& a;
+    ImgCacheT<LOG> cache;
+    long long i0;
+    int lam_a, lam_b;
+    __device__ __forceinline__ void operator()(int lane, int slot, V3 hl, float w) const {
+        if (slot >= 0 && slot < a.n_sens)
+            sensor_deposit(a.sens[slot], cache, slot, i0 + (long long)lane * kThreads, hl, w, lane ? lam_b : lam_a);
+    }
+};
+
+// per-lane refractive-index ratios of row r (row values, or the wavelength table's)
+__device__ __forceinline__ void pair_ior(const SmemTable& T, int S, int L, int r, int lam_a, int lam_b, F2& mu_enter, F2& mu_exit) {
+    if (L > 0) {
+        const int ia = lam_a * S + r, ib = lam_b * S + r;
+        mu_enter = f2(T.mu_enter[ia], T.mu_enter[ib]); mu_exit = f2(T.mu_exit[ia], T.mu_exit[ib]);
+    } else {
+        mu_enter = bc(T.rows[r].f[D_MU_ENTER]); mu_exit = bc(T.rows[r].f[D_MU_EXIT]);
+    }
+}
+
+// a row kind without a packed form: the scalar twin per lane, with the specialised policy K
+template <class K, class DEP>
+__device__ __forceinline__ unsigned pair_row_generic(const SmemTable& T, int S, int L, int r, long long i0, int lam_a, int lam_b,
+                                                     P3& P, P3& D, F2& I, unsigned act, DEP& dep) {
+    const RowDev& R = T.rows[r];
+    F2 mu_enter = bc(0.0f), mu_exit = bc(0.0f);
+    PhysAux aux_a = no_aux(), aux_b = no_aux();
+    if (uses_ior<K>(R)) {
+        pair_ior(T, S, L, r, lam_a, lam_b, mu_enter, mu_exit);
+        if (K::phys(R) == RTT_PHYS_FRESNEL) {
+            const Ior qa = row_ior(T, S, L, r, lam_a), qb = row_ior(T, S, L, r, lam_b);
+            aux_a = make_aux<K>(T.rows, R, qa.ni, qa.no, i0, r, 0);
+            aux_b = make_aux<K>(T.rows, R, qb.ni, qb.no, i0 + kThreads, r, 0);
+        }
+    }
+    return pair_row_scalar<K>(T.rows, r, P, D, I, act, mu_enter, mu_exit, aux_a, aux_b, dep);
+}
+
+template <int MINB, bool STREAM, int LOG>
+__global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __grid_constant__ SeqFwdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef PairLayout<LOG, STREAM> LY;
+    const int S = a.tab.S, L = a.tab.L;
+    SmemTable T = carve(smem_raw + LY::kOffTable, S, L);
+    Xf* xf = reinterpret_cast<Xf*>(smem_raw + LY::kOffXf);
+    ImgCacheT<LOG> cache = img_cache_carve<LOG>(smem_raw);
+    const long long n_tiles = (a.n + kPairTile - 1) / kPairTile;
+    const unsigned bar0 = smem_u32(smem_raw + LY::kOffBar);
+    const unsigned slot0 = smem_u32(smem_raw + LY::kOffSlots);
+    const bool use_wav = L > 0;
+    const unsigned tile_bytes = (unsigned)(kPairTile * (use_wav ? 32 : 28));
+
+    // elected thread: issue the bulk loads of tile `t` (a FULL tile) into slot `s`
+    auto issue_load = [&](long long t, int s) {
+        const unsigned bar = bar0 + 8u * s, dst = slot0 + (unsigned)(s * kSlotBytes);
+        const long long base = t * kPairTile;
+        mbar_expect_tx(bar, tile_bytes);
+        bulk_g2s(dst + kSlotPos, a.pos + 3 * base, kPairTile * 12, bar);
+        bulk_g2s(dst + kSlotDir, a.dir + 3 * base, kPairTile * 12, bar);
+        bulk_g2s(dst + kSlotInt, a.inten + base, kPairTile * 4, bar);
+        if (use_wav) bulk_g2s(dst + kSlotWav, a.wav + base, kPairTile * 4, bar);
+    };
+    auto tile_is_full = [&](long long t) { return (t + 1) * kPairTile <= a.n; };
+
+    if (STREAM && threadIdx.x == 0) {
+        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
+        mbar_fence_init();
+        for (int k = 0; k < kPairSlots; ++k) {                          // prologue: the first two tiles of this block
+            const long long t = (long long)blockIdx.x + (long long)k * gridDim.x;
+            if (t < n_tiles && tile_is_full(t)) issue_load(t, k);
+        }
+    }
+    img_cache_init(cache);
+    stage_table(a.tab, T);
+    stage_tile(T, S, xf);
+    const SourceKey skey = fetch_key(a);
+
+    long long k = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+        const long long base = tile * kPairTile;
+        const long long i0 = base + threadIdx.x;
+        const int s = (int)(k & 1);
+        unsigned char* slot = smem_raw + LY::kOffSlots + (size_t)s * kSlotBytes;
+        const bool full = tile_is_full(tile);
+        const int cnt = full ? kPairTile : (int)(a.n - base);
+        if (STREAM) {
+            if (full) {
+                mbar_wait(bar0 + 8u * s, (unsigned)((k >> 1) & 1));
+            } else {                                                    // ragged last tile: cooperative plain copy
+                float* sp = reinterpret_cast<float*>(slot + kSlotPos);
+                float* sd = reinterpret_cast<float*>(slot + kSlotDir);
+                float* si = reinterpret_cast<float*>(slot + kSlotInt);
+                float* sw = reinterpret_cast<float*>(slot + kSlotWav);
+                for (int idx = threadIdx.x; idx < 3 * cnt; idx += kThreads) {
+                    sp[idx] = a.pos[3 * base + idx]; sd[idx] = a.dir[3 * base + idx];
+                }
+                for (int idx = threadIdx.x; idx < cnt; idx += kThreads) {
+                    si[idx] = a.inten[base + idx];
+                    if (use_wav) sw[idx] = a.wav[base + idx];
+                }
+                __syncthreads();
+            }
+        }
+        // ---- this thread's pair: rays i0 and i0 + kThreads ----
+        P3 P, D;
+        F2 I;
+        int lam[2];
+        bool act[2], odd[2];
+        {
+            V3 pin[2], din[2];
+            float Iin[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int loc = threadIdx.x + j * kThreads;
+                pin[j] = v3(0.0f, 0.0f, 0.0f); din[j] = v3(0.0f, 0.0f, 0.0f); Iin[j] = 0.0f; lam[j] = 0;
+                act[j] = false; odd[j] = false;
+                if (loc < cnt) {
+                    const RayIn ray = STREAM ? slot_ray(slot, loc, use_wav) : fetch_ray(a, skey, base + loc, use_wav);
+                    pin[j] = ray.p; din[j] = ray.d; Iin[j] = ray.I;
+                    lam[j] = use_wav ? wavelength_index(T, L, ray.wav) : 0;
+                    act[j] = finite_ray(ray.p, ray.d) && regular_dir(ray.d);
+                    odd[j] = !act[j];                                   // re-read below: un-normalised or non-finite ray
+                }
+            }
+            P = pack3(pin[0], pin[1]); D = pack3(din[0], din[1]); I = f2(Iin[0], Iin[1]);
+        }
+        const unsigned actb = (act[0] ? 1u : 0u) | (act[1] ? 2u : 0u);
+        unsigned long long mask_a = 0ull, mask_b = 0ull, bit = 1ull;
+        PairDeposit<LOG> dep{a, cache, i0, lam[0], lam[1]};
+        for (int r = 0; r < S; ++r, bit += bit) {
+            const int op = T.rows[r].i[DI_TILE_OP];
+            const int kind = xf[r].kind;                                // warp-uniform
+            const int run = xf[r].run;
+            if (kind) pair_apply_xf(xf[r], P, D);
+            if (run > 0) {                                              // lens-edge rows: skip them when no lane can hit
+                const bool away = pair_edge_culled(xf[r], P, D, act[0], act[1]);
+                if (__all_sync(kFull, away)) {
+                    r += run - 1; bit <<= (run - 1);
+                    continue;
+                }
+            }
+            unsigned hit;
+            switch (op) {                                               // warp-uniform
+                case 1: {
+                    F2 me, mx; pair_ior(T, S, L, r, lam[0], lam[1], me, mx);
+                    hit = pair_conic_face<true, RTT_SHAPE_SPHERIC_FACE>(T.rows, r, P, D, I, actb, me, mx, dep);
+                    break;
+                }
+                case 4: {
+                    F2 me, mx; pair_ior(T, S, L, r, lam[0], lam[1], me, mx);
+                    hit = pair_conic_face<false, RTT_SHAPE_CYL_FACE>(T.rows, r, P, D, I, actb, me, mx, dep);
+                    break;
+                }
+                case 7: hit = pair_plane<RTT_BOUND_DISK, RTT_PHYS_APERTURE, false>(T.rows, r, P, D, I, actb, dep); break;
+                case 8: hit = pair_plane<RTT_BOUND_DISK, RTT_PHYS_TRANSMIT, true>(T.rows, r, P, D, I, actb, dep); break;
+                case 9: hit = pair_plane<RTT_BOUND_RECT, RTT_PHYS_TRANSMIT, true>(T.rows, r, P, D, I, actb, dep); break;
+#define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR)                                         \
+                case OP: hit = pair_row_generic<KTile<SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR>>(T, S, L, r, i0, lam[0], lam[1], P, D, I, actb, dep); break;
+                RTT_PAIR_SCALAR_SPECS(RTT_X)
+#undef RTT_X
+                default: hit = pair_row_generic<KDyn>(T, S, L, r, i0, lam[0], lam[1], P, D, I, actb, dep); break;
+            }
+            if (hit & 1u) mask_a |= bit;
+            if (hit & 2u) mask_b |= bit;
+        }
+        if (xf[S].kind) pair_apply_xf(xf[S], P, D);
+        // ---- results ----
+        V3 po[2] = {lane_a(P), lane_b(P)}, dout[2] = {lane_a(D), lane_b(D)};
+        float Io[2] = {I.x, I.y};
+        unsigned long long mo[2] = {mask_a, mask_b};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int loc = threadIdx.x + j * kThreads;
+            if (odd[j]) {
+                // un-normalised direction: walk in the reference's order; NaN / inf ray: hits nothing, stays as it was
+                // (the slot still holds this ray's inputs: a thread only ever writes its own entries)
+                const RayIn ray = STREAM ? slot_ray(slot, loc, use_wav) : fetch_ray(a, skey, base + loc, use_wav);
+                WalkState w;
+                w.p = ray.p; w.d = ray.d; w.I = ray.I; w.mask = 0ull;
+                if (finite_ray(ray.p, ray.d)) w = pair_walk_generic<LOG, STREAM>(a, lam[j], base + loc, w);
+                po[j] = w.p; dout[j] = w.d; Io[j] = w.I; mo[j] = w.mask;
+            }
+            if (loc < cnt) {
+                if (STREAM) {
+                    float* sp = reinterpret_cast<float*>(slot + kSlotPos);
+                    float* sd = reinterpret_cast<float*>(slot + kSlotDir);
+                    sp[3 * loc] = po[j].x; sp[3 * loc + 1] = po[j].y; sp[3 * loc + 2] = po[j].z;
+                    sd[3 * loc] = dout[j].x; sd[3 * loc + 1] = dout[j].y; sd[3 * loc + 2] = dout[j].z;
+                    reinterpret_cast<float*>(slot + kSlotInt)[loc] = Io[j];
+                    reinterpret_cast<unsigned long long*>(slot + kSlotMask)[loc] = mo[j];
+                } else {
+                    const long long i = base + loc;
+                    if (a.opos) { store3(a.opos, i, po[j]); store3(a.odir, i, dout[j]); a.ointen[i] = Io[j]; }
+                    if (a.hitmask) a.hitmask[i] = mo[j];
+                }
+            }
+        }
+        if (STREAM) {
+            fence_async_smem();
+            __syncthreads();                                            // every result of the tile is in the slot
+            if (full) {
+                if (threadIdx.x == 0) {
+                    const unsigned src = slot0 + (unsigned)(s * kSlotBytes);
+                    if (a.opos) {
+                        bulk_s2g(a.opos + 3 * base, src + kSlotPos, kPairTile * 12);
+                        bulk_s2g(a.odir + 3 * base, src + kSlotDir, kPairTile * 12);
+                        bulk_s2g(a.ointen + base, src + kSlotInt, kPairTile * 4);
+                    }
+                    if (a.hitmask) bulk_s2g(a.hitmask + base, src + kSlotMask, kPairTile * 8);
+                    bulk_commit();
+                    const long long next = tile + (long long)kPairSlots * gridDim.x;
+                    if (next < n_tiles) {
+                        bulk_wait_read0();                              // the stores have read the slot: refill it
+                        if (tile_is_full(next)) issue_load(next, s);
+                    }
+                }
+            } else {
+                const float* sp = reinterpret_cast<const float*>(slot + kSlotPos);
+                const float* sd = reinterpret_cast<const float*>(slot + kSlotDir);
+                if (a.opos) {
+                    for (int idx = threadIdx.x; idx < 3 * cnt; idx += kThreads) {
+                        a.opos[3 * base + idx] = sp[idx]; a.odir[3 * base + idx] = sd[idx];
+                    }
+                    for (int idx = threadIdx.x; idx < cnt; idx += kThreads)
+                        a.ointen[base + idx] = reinterpret_cast<const float*>(slot + kSlotInt)[idx];
+                }
+                if (a.hitmask)
+                    for (int idx = threadIdx.x; idx < cnt; idx += kThreads)
+                        a.hitmask[base + idx] = reinterpret_cast<const unsigned long long*>(slot + kSlotMask)[idx];
+            }
+        }
+    }
+    if (STREAM && threadIdx.x == 0) bulk_wait_all0();                   // the slot must outlive the stores that read it
     img_cache_flush(cache, a.sens);
 }
 #endif  // RTT_APPROX
@@ -1134,6 +1470,31 @@ inline cudaError_t launch_tile(const SeqFwdArgs& a, cudaStream_t st) {
 // The choice depends on the table and the caller's mode bits only (no environment, no cached state), so a bundle
 // generated in the kernel and its materialised twin run the same build and stay bit-identical (tests/test_goals.py).
 inline int fwd_tile_for(int S, int tune) { return tune ? tune : (S <= 6 ? 5 : 3); }
+
+template <int MINB, bool STREAM, int LOG>
+inline cudaError_t launch_pair(const SeqFwdArgs& a, cudaStream_t st) {
+    const size_t smem = PairLayout<LOG, STREAM>::bytes(a.tab.S, a.tab.L);
+    if (cudaError_t e = allow_smem(k_trace_seq_fwd_pair<MINB, STREAM, LOG>, smem)) return e;
+    const long long tiles = (a.n + kPairTile - 1) / kPairTile;
+    // persistent blocks, one resident set (tiles are handed out round-robin: tile = block + k * grid); the plain build
+    // keeps the tile kernel's four waves (a block that lands on a busier SM costs 1/4 of a launch)
+    long long g = (long long)sm_count() * MINB * (STREAM ? 1 : 4);
+    if (tiles < g) g = tiles;
+    if (g < 1) g = 1;
+    k_trace_seq_fwd_pair<MINB, STREAM, LOG><<<(int)g, kThreads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+// bulk-async copies need 16-byte aligned global addresses; every full tile starts a multiple of 512 rays into the
+// arrays, so the base pointers decide.  Generated rays have no input to stream.
+inline bool pair_can_stream(const SeqFwdArgs& a) {
+    if (a.src.kind >= 0) return false;
+    auto ok = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (!ok(a.pos) || !ok(a.dir) || !ok(a.inten)) return false;
+    if (a.tab.L > 0 && !ok(a.wav)) return false;
+    if (a.opos && (!ok(a.opos) || !ok(a.odir) || !ok(a.ointen))) return false;
+    if (a.hitmask && !ok(a.hitmask)) return false;
+    return true;
+}
 #endif
 
 cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
@@ -1143,6 +1504,10 @@ cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
         case 2: return launch_tile<2, 3>(a, st);
         case 3: return launch_tile<2, 4>(a, st);
         case 5: return launch_tile<1, 5>(a, st);
+        case 16: return pair_can_stream(a) ? launch_pair<3, true, 11>(a, st) : launch_pair<3, false, 12>(a, st);
+        case 17: return launch_pair<4, false, 12>(a, st);
+        case 18: return launch_pair<3, false, 12>(a, st);
+        case 19: return pair_can_stream(a) ? launch_pair<2, true, 12>(a, st) : launch_pair<3, false, 12>(a, st);
         default: break;
     }
 #endif

@@ -103,6 +103,70 @@ class FlatReducer:
         return None
 
 
+class OverlappedReducer:
+    """All-reduce of per-step accumulators (sensor images) on a side stream, so that the collective of step k runs
+    under the trace of step k+1 instead of after it on the same stream.
+
+    ``submit(tensors)`` — call right after the kernels that produced them were enqueued on the current stream; the
+    side stream waits for that point, then runs ONE flat all-reduce (SUM, in place).  ``drain()`` makes the current
+    stream wait for every submitted reduction (call before reading the results / at the end of a timed region).
+    Each step must hand over FRESH tensors (the trace ops allocate their images per call), never a buffer a later
+    step writes while the reduction may still be in flight."""
+
+    def __init__(self, device, group=None):
+        self.group = group
+        self.stream = torch.cuda.Stream(device=device)
+        self.pending: List[Tuple[torch.cuda.Event, list]] = []
+
+    def submit(self, tensors: Iterable[Optional[torch.Tensor]]):
+        items = [t for t in tensors if t is not None]
+        if not items or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return
+        cur = torch.cuda.current_stream(self.stream.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            red = FlatReducer(self.group)
+            red.extend(items)
+            red.reduce()
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        for t in items:
+            t.record_stream(self.stream)
+        self.pending.append((done, items))
+        if len(self.pending) > 4:                       # bound the number of images kept alive
+            ev, _ = self.pending.pop(0)
+            cur.wait_event(ev)
+
+    def drain(self):
+        cur = torch.cuda.current_stream(self.stream.device)
+        for ev, _ in self.pending:
+            cur.wait_event(ev)
+        self.pending = []
+
+
+def bind_to_gpu_numa(local_rank: int) -> Optional[List[int]]:
+    """Pin this process to the CPU cores NVML reports as local to GPU ``local_rank`` (its NUMA node), BEFORE pinned
+    host buffers are allocated: first-touch then places the staging memory on that node and the H2D copies of several
+    ranks do not all cross one socket's memory controller.  Returns the core list, or None when NVML / affinity is
+    unavailable (nothing is changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(local_rank))
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cores = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return allowed
+    except Exception:
+        return None
+    return None
+
+
 def allreduce_scene_results(sensors: Sequence, params: Iterable[torch.nn.Parameter] = (), extra: Sequence = ()):
     """Sum sensor images, parameter gradients and extra accumulators (loss moments) over ranks
     with one collective.  Call after ``loss.backward()`` on every rank."""

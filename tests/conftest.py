@@ -38,12 +38,15 @@ _BACKENDS = ["host", pytest.param("gpu", marks=pytest.mark.gpu)]
 def _runner(backend, variant):
     if backend == "host":
         from hostsim import build
-        return build(variant)
+        return build({"pair_plain": "pair", "tile": "fast"}.get(variant, variant))
     import torch
     if not torch.cuda.is_available():
         pytest.fail("gpu test selected but no CUDA device is visible (there is no CPU fallback)")
     from gpusim import GpuSim
-    return GpuSim(1 if variant == "exact" else 0)
+    # mode word of the C ABI: arithmetic in bits 0..7 (0 FAST, 1 EXACT), kernel build in bits 16..23
+    # (include/rtt_b200.h RTT_MODE_TUNE_*): "pair" = packed ray pairs with bulk-async ray streaming, "pair_plain" =
+    # the same arithmetic with plain loads / stores, "tile" = the scalar frame-resident tile kernel
+    return GpuSim({"exact": 1, "fast": 0, "pair": 16 << 16, "pair_plain": 18 << 16, "tile": 3 << 16}[variant])
 
 
 @pytest.fixture(params=_BACKENDS)

@@ -20,7 +20,10 @@ from simcommon import SourceGoalMixin
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _BUILD = os.path.join(_HERE, "_build")
-_FLAGS = {"exact": ["-ffp-contract=off", "-mfma"], "fast": ["-ffp-contract=fast", "-mfma", "-DRTT_HOST_TILE", "-DRTT_TILE_LEAN"]}
+_FLAGS = {"exact": ["-ffp-contract=off", "-mfma"],
+          "fast": ["-ffp-contract=fast", "-mfma", "-DRTT_HOST_TILE", "-DRTT_TILE_LEAN"],
+          # mirror of k_trace_seq_fwd_pair (csrc/rtt_pair.cuh): packed two-ray arithmetic, lanes = fmaf on the host
+          "pair": ["-ffp-contract=fast", "-mfma", "-DRTT_HOST_TILE", "-DRTT_TILE_LEAN", "-DRTT_HOST_PAIR"]}
 _cache = {}
 
 
@@ -32,8 +35,9 @@ def build(variant: str = "exact") -> "HostSim":
     src = os.path.join(_HERE, "hostsim.cpp")
     core = os.path.join(_HERE, "..", "..", "raytracetorch_b200", "csrc", "rtt_core.cuh")
     tile = os.path.join(_HERE, "..", "..", "raytracetorch_b200", "csrc", "rtt_tile.cuh")
+    pair = os.path.join(_HERE, "..", "..", "raytracetorch_b200", "csrc", "rtt_pair.cuh")
     hdr = os.path.join(_HERE, "..", "..", "include", "rtt_b200.h")
-    newest = max(os.path.getmtime(p) for p in (src, core, tile, hdr, __file__))
+    newest = max(os.path.getmtime(p) for p in (src, core, tile, pair, hdr, __file__))
     if not os.path.exists(out) or os.path.getmtime(out) < newest:
         cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fno-fast-math", *_FLAGS[variant], src, "-o", out]
         subprocess.run(cmd, check=True)

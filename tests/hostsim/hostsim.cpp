@@ -14,6 +14,7 @@
 
 #include "../../raytracetorch_b200/csrc/rtt_core.cuh"
 #include "../../raytracetorch_b200/csrc/rtt_tile.cuh"
+#include "../../raytracetorch_b200/csrc/rtt_pair.cuh"
 
 using namespace rtt;
 
@@ -155,7 +156,73 @@ int rtt_trace_seq_fwd(const float* in_pos, const float* in_dir, const float* in_
         xf[r] = make_xf(r > 0 ? &T.rows[r - 1] : nullptr, r < T.S ? &T.rows[r] : nullptr);
     for (int r = 0; r < T.S; ++r) edge_run_at(T.rows.data(), T.S, xf.data(), r);
 #endif
+#ifdef RTT_HOST_PAIR
+    // mirror of k_trace_seq_fwd_pair: rays (i, i+1) are the two lanes of the packed arithmetic of rtt_pair.cuh; a ray
+    // the kernel would walk in the reference's order (non-finite / un-normalised direction) is handled by the scalar
+    // loop below, with its lane switched off in the pair
+    std::vector<char> done(n, 0);
+    struct HostDep {
+        const rtt_sensor_t* sensors; int n_sensors; int64_t i0; int lam[2];
+        void operator()(int lane, int slot, V3 hl, float w) const {
+            if (slot >= 0 && slot < n_sensors) deposit(sensors[slot], i0 + lane, hl, w, lam[lane]);
+        }
+    };
+    for (int64_t i0 = 0; i0 < n; i0 += 2) {
+        HostRay ray[2];
+        bool act[2] = {false, false};
+        int lam[2] = {0, 0};
+        for (int j = 0; j < 2; ++j) {
+            ray[j].p = v3(0, 0, 0); ray[j].d = v3(0, 0, 0); ray[j].I = 0.0f; ray[j].wav = 0.0f;
+            if (i0 + j >= n) continue;
+            ray[j] = fetch_ray(source, in_pos, in_dir, in_intensity, in_wavelength, T.L > 0, i0 + j);
+            lam[j] = T.L > 0 ? lam_index(T, ray[j].wav) : 0;
+            act[j] = finite_ray(ray[j].p, ray[j].d) && regular_dir(ray[j].d);
+            if (!act[j]) { ray[j].p = v3(0, 0, 0); ray[j].d = v3(0, 0, 0); ray[j].I = 0.0f; }
+        }
+        if (!act[0] && !act[1]) continue;
+        P3 P = pack3(ray[0].p, ray[1].p), D = pack3(ray[0].d, ray[1].d);
+        F2 I = f2(ray[0].I, ray[1].I);
+        const unsigned actb = (act[0] ? 1u : 0u) | (act[1] ? 2u : 0u);
+        uint64_t mask[2] = {0, 0};
+        HostDep dep{sensors, n_sensors, i0, {lam[0], lam[1]}};
+        for (int r = 0; r < T.S; ++r) {
+            pair_apply_xf(xf[r], P, D);
+            if (xf[r].run > 0 && pair_edge_culled(xf[r], P, D, act[0], act[1])) { r += xf[r].run - 1; continue; }
+            const RowDev& R = T.rows[r];
+            const Ior ia = row_ior(T, r, lam[0]), ib = row_ior(T, r, lam[1]);
+            const F2 me = f2(ia.mu_enter, ib.mu_enter), mx = f2(ia.mu_exit, ib.mu_exit);
+            unsigned hit;
+            switch (tile_opcode(R)) {
+                case 1: hit = pair_conic_face<true, RTT_SHAPE_SPHERIC_FACE>(T.rows.data(), r, P, D, I, actb, me, mx, dep); break;
+                case 4: hit = pair_conic_face<false, RTT_SHAPE_CYL_FACE>(T.rows.data(), r, P, D, I, actb, me, mx, dep); break;
+                case 7: hit = pair_plane<RTT_BOUND_DISK, RTT_PHYS_APERTURE, false>(T.rows.data(), r, P, D, I, actb, dep); break;
+                case 8: hit = pair_plane<RTT_BOUND_DISK, RTT_PHYS_TRANSMIT, true>(T.rows.data(), r, P, D, I, actb, dep); break;
+                case 9: hit = pair_plane<RTT_BOUND_RECT, RTT_PHYS_TRANSMIT, true>(T.rows.data(), r, P, D, I, actb, dep); break;
+                default:
+                    hit = pair_row_scalar<KDyn>(T.rows.data(), r, P, D, I, actb, me, mx,
+                                                make_aux(T.rows.data(), R, ia.ni, ia.no, i0, r, 0),
+                                                make_aux(T.rows.data(), R, ib.ni, ib.no, i0 + 1, r, 0), dep);
+                    break;
+            }
+            if (hit & 1u) mask[0] |= 1ull << r;
+            if (hit & 2u) mask[1] |= 1ull << r;
+        }
+        pair_apply_xf(xf[T.S], P, D);
+        const V3 po[2] = {lane_a(P), lane_b(P)}, dout[2] = {lane_a(D), lane_b(D)};
+        const float Io[2] = {I.x, I.y};
+        for (int j = 0; j < 2; ++j) {
+            if (!act[j]) continue;
+            const int64_t i = i0 + j;
+            if (out_pos) { store3(out_pos, i, po[j]); store3(out_dir, i, dout[j]); out_intensity[i] = Io[j]; }
+            if (hitmask) hitmask[i] = mask[j];
+            done[i] = 1;
+        }
+    }
+#endif
     for (int64_t i = 0; i < n; ++i) {
+#ifdef RTT_HOST_PAIR
+        if (done[i]) continue;
+#endif
         const HostRay ray = fetch_ray(source, in_pos, in_dir, in_intensity, in_wavelength, T.L > 0, i);
         V3 p = ray.p, d = ray.d;
         float I = ray.I;

@@ -52,7 +52,7 @@ def test_seq_exact_is_bit_identical_to_oracle(run_exact, ieee_oracle, name):
         np.testing.assert_array_equal(rec[mask.numpy(), 3], w.numpy())
 
 
-@pytest.mark.parametrize("variant", ["exact", "fast"])
+@pytest.mark.parametrize("variant", ["exact", "fast", "pair", "pair_plain", "tile"])
 @pytest.mark.parametrize("name", SEQ)
 def test_seq_matches_reference_within_tolerance(runner_of, name, variant):
     d = parity.load(name)
@@ -383,7 +383,7 @@ def _stack_of_singlets(rtt_ns, grads=()):
     return els
 
 
-@pytest.mark.parametrize("variant", ["exact", "fast"])
+@pytest.mark.parametrize("variant", ["exact", "fast", "pair"])
 def test_maximum_table_size(runner_of, ieee_oracle, rtt_ns, variant):
     """A 64-row table (the C ABI's maximum): forward against the oracle (EXACT: bit for bit, the sensor bit is bit 63 of
     the hit mask), adjoint against oracle autograd for the first and the last lens (rows beyond the 12 private
