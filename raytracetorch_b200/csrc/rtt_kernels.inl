@@ -37,8 +37,7 @@ struct SmemTable {
     RowDev* rows;        // [S]
     float* lut_ni;       // [L*S]
     float* lut_no;       // [L*S]
-    float* mu_enter;     // [L*S]   no/ni
-    float* mu_exit;      // [L*S]   ni/no
+    float2* mu;          // [L*S]   (no/ni, ni/no) = (mu_enter, mu_exit): one 8-byte load per lookup
     float* lut_w;        // [L]
 };
 
@@ -52,8 +51,7 @@ __device__ __forceinline__ SmemTable carve(unsigned char* base, int S, int L) {
     float* f = reinterpret_cast<float*>(base + sizeof(RowDev) * (size_t)S);
     T.lut_ni = f; f += (size_t)L * S;
     T.lut_no = f; f += (size_t)L * S;
-    T.mu_enter = f; f += (size_t)L * S;
-    T.mu_exit = f; f += (size_t)L * S;
+    T.mu = reinterpret_cast<float2*>(f); f += (size_t)2 * L * S;     // 8-byte aligned: 256 S + 8 L S bytes into the table
     T.lut_w = f;
     return T;
 }
@@ -68,7 +66,7 @@ __device__ __forceinline__ void stage_table(const TableDev& tab, SmemTable& T) {
     for (int idx = threadIdx.x; idx < L * S; idx += blockDim.x) {
         const float ni = tab.lut[2 * idx], no = tab.lut[2 * idx + 1];
         T.lut_ni[idx] = ni; T.lut_no[idx] = no;
-        T.mu_enter[idx] = no / ni; T.mu_exit[idx] = ni / no;
+        T.mu[idx] = make_float2(no / ni, ni / no);
     }
     for (int idx = threadIdx.x; idx < L; idx += blockDim.x) T.lut_w[idx] = tab.lut_w[idx];
     __syncthreads();
@@ -93,7 +91,8 @@ __device__ __forceinline__ Ior row_ior(const SmemTable& T, int S, int L, int r, 
     Ior q;
     if (L > 0) {
         const int idx = lam * S + r;
-        q.ni = T.lut_ni[idx]; q.no = T.lut_no[idx]; q.mu_enter = T.mu_enter[idx]; q.mu_exit = T.mu_exit[idx];
+        const float2 m = T.mu[idx];
+        q.ni = T.lut_ni[idx]; q.no = T.lut_no[idx]; q.mu_enter = m.x; q.mu_exit = m.y;
     } else {
         const RowDev& R = T.rows[r];
         q.ni = R.f[RTT_F_IOR_IN]; q.no = R.f[RTT_F_IOR_OUT]; q.mu_enter = R.f[D_MU_ENTER]; q.mu_exit = R.f[D_MU_EXIT];
@@ -321,7 +320,11 @@ __device__ __forceinline__ void stage_tile(SmemTable& T, int S, Xf* xf) {
     }
     __syncthreads();
     // runs of lens-edge rows that can be culled together (same element frame)
-    for (int r = threadIdx.x; r < S; r += blockDim.x) edge_run_at(T.rows, S, xf, r);
+    for (int r = threadIdx.x; r < S; r += blockDim.x) {
+        edge_run_at(T.rows, S, xf, r);
+        // one control word per row for the pair kernel's loop: opcode | frame-change kind << 8 | cull run << 16
+        xf[r].ctl = T.rows[r].i[DI_TILE_OP] | (xf[r].kind << 8) | (xf[r].run << 16);
+    }
     __syncthreads();
 }
 
@@ -551,13 +554,15 @@ struct PairDeposit {
     }
 };
 
-// per-lane refractive-index ratios of row r (row values, or the wavelength table's)
-__device__ __forceinline__ void pair_ior(const SmemTable& T, int S, int L, int r, int lam_a, int lam_b, F2& mu_enter, F2& mu_exit) {
+// per-lane refractive-index ratios of row r (row values, or the wavelength table's): one 8-byte shared-memory load per
+// lane; lamS = wavelength index * S, computed once per ray
+__device__ __forceinline__ void pair_ior(const SmemTable& T, int L, int r, int lamS_a, int lamS_b, F2& mu_enter, F2& mu_exit) {
     if (L > 0) {
-        const int ia = lam_a * S + r, ib = lam_b * S + r;
-        mu_enter = f2(T.mu_enter[ia], T.mu_enter[ib]); mu_exit = f2(T.mu_exit[ia], T.mu_exit[ib]);
+        const float2 ma = T.mu[lamS_a + r], mb = T.mu[lamS_b + r];
+        mu_enter = f2(ma.x, mb.x); mu_exit = f2(ma.y, mb.y);
     } else {
-        mu_enter = bc(T.rows[r].f[D_MU_ENTER]); mu_exit = bc(T.rows[r].f[D_MU_EXIT]);
+        const float2 m = *reinterpret_cast<const float2*>(T.rows[r].f + D_MU_ENTER);   // (D_MU_ENTER, D_MU_EXIT) adjacent, 8-byte aligned
+        mu_enter = bc(m.x); mu_exit = bc(m.y);
     }
 }
 
@@ -569,7 +574,7 @@ __device__ __forceinline__ unsigned pair_row_generic(const SmemTable& T, int S, 
     F2 mu_enter = bc(0.0f), mu_exit = bc(0.0f);
     PhysAux aux_a = no_aux(), aux_b = no_aux();
     if (uses_ior<K>(R)) {
-        pair_ior(T, S, L, r, lam_a, lam_b, mu_enter, mu_exit);
+        pair_ior(T, L, r, lam_a * S, lam_b * S, mu_enter, mu_exit);
         if (K::phys(R) == RTT_PHYS_FRESNEL) {
             const Ior qa = row_ior(T, S, L, r, lam_a), qb = row_ior(T, S, L, r, lam_b);
             aux_a = make_aux<K>(T.rows, R, qa.ni, qa.no, i0, r, 0);
@@ -587,30 +592,31 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
     SmemTable T = carve(smem_raw + LY::kOffTable, S, L);
     Xf* xf = reinterpret_cast<Xf*>(smem_raw + LY::kOffXf);
     ImgCacheT<LOG> cache = img_cache_carve<LOG>(smem_raw);
-    const long long n_tiles = (a.n + kPairTile - 1) / kPairTile;
+    // tiles are counted in int: a.n <= 2^40 rays = 2^31 tiles of 512
+    const int n_tiles = (int)((a.n + kPairTile - 1) / kPairTile);
+    const int n_full = (int)(a.n / kPairTile);                          // tiles [0, n_full) are full
     const unsigned bar0 = smem_u32(smem_raw + LY::kOffBar);
     const unsigned slot0 = smem_u32(smem_raw + LY::kOffSlots);
     const bool use_wav = L > 0;
     const unsigned tile_bytes = (unsigned)(kPairTile * (use_wav ? 32 : 28));
 
     // elected thread: issue the bulk loads of tile `t` (a FULL tile) into slot `s`
-    auto issue_load = [&](long long t, int s) {
+    auto issue_load = [&](int t, int s) {
         const unsigned bar = bar0 + 8u * s, dst = slot0 + (unsigned)(s * kSlotBytes);
-        const long long base = t * kPairTile;
+        const long long base = (long long)t * kPairTile;
         mbar_expect_tx(bar, tile_bytes);
         bulk_g2s(dst + kSlotPos, a.pos + 3 * base, kPairTile * 12, bar);
         bulk_g2s(dst + kSlotDir, a.dir + 3 * base, kPairTile * 12, bar);
         bulk_g2s(dst + kSlotInt, a.inten + base, kPairTile * 4, bar);
         if (use_wav) bulk_g2s(dst + kSlotWav, a.wav + base, kPairTile * 4, bar);
     };
-    auto tile_is_full = [&](long long t) { return (t + 1) * kPairTile <= a.n; };
 
     if (STREAM && threadIdx.x == 0) {
         mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
         mbar_fence_init();
         for (int k = 0; k < kPairSlots; ++k) {                          // prologue: the first two tiles of this block
             const long long t = (long long)blockIdx.x + (long long)k * gridDim.x;
-            if (t < n_tiles && tile_is_full(t)) issue_load(t, k);
+            if (t < n_full) issue_load((int)t, k);
         }
     }
     img_cache_init(cache);
@@ -618,18 +624,17 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
     stage_tile(T, S, xf);
     const SourceKey skey = fetch_key(a);
 
-    long long k = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
-        const long long base = tile * kPairTile;
-        const long long i0 = base + threadIdx.x;
-        const int s = (int)(k & 1);
+    unsigned k = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+        const int s = (int)(k & 1u);
         unsigned char* slot = smem_raw + LY::kOffSlots + (size_t)s * kSlotBytes;
-        const bool full = tile_is_full(tile);
-        const int cnt = full ? kPairTile : (int)(a.n - base);
+        const bool full = tile < n_full;
+        const int cnt = full ? kPairTile : (int)(a.n - (long long)tile * kPairTile);
         if (STREAM) {
             if (full) {
-                mbar_wait(bar0 + 8u * s, (unsigned)((k >> 1) & 1));
+                mbar_wait(bar0 + 8u * s, (k >> 1) & 1u);
             } else {                                                    // ragged last tile: cooperative plain copy
+                const long long base = (long long)tile * kPairTile;
                 float* sp = reinterpret_cast<float*>(slot + kSlotPos);
                 float* sd = reinterpret_cast<float*>(slot + kSlotDir);
                 float* si = reinterpret_cast<float*>(slot + kSlotInt);
@@ -644,10 +649,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
                 __syncthreads();
             }
         }
-        // ---- this thread's pair: rays i0 and i0 + kThreads ----
+        // ---- this thread's pair: rays base + threadIdx.x and base + threadIdx.x + kThreads ----
         P3 P, D;
         F2 I;
-        int lam[2];
+        int lamS[2];                                                    // wavelength index * S (offset into the index table)
         bool act[2], odd[2];
         {
             V3 pin[2], din[2];
@@ -655,12 +660,13 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int loc = threadIdx.x + j * kThreads;
-                pin[j] = v3(0.0f, 0.0f, 0.0f); din[j] = v3(0.0f, 0.0f, 0.0f); Iin[j] = 0.0f; lam[j] = 0;
+                pin[j] = v3(0.0f, 0.0f, 0.0f); din[j] = v3(0.0f, 0.0f, 0.0f); Iin[j] = 0.0f; lamS[j] = 0;
                 act[j] = false; odd[j] = false;
                 if (loc < cnt) {
-                    const RayIn ray = STREAM ? slot_ray(slot, loc, use_wav) : fetch_ray(a, skey, base + loc, use_wav);
+                    const RayIn ray = STREAM ? slot_ray(slot, loc, use_wav)
+                                             : fetch_ray(a, skey, (long long)tile * kPairTile + loc, use_wav);
                     pin[j] = ray.p; din[j] = ray.d; Iin[j] = ray.I;
-                    lam[j] = use_wav ? wavelength_index(T, L, ray.wav) : 0;
+                    lamS[j] = use_wav ? wavelength_index(T, L, ray.wav) * S : 0;
                     act[j] = finite_ray(ray.p, ray.d) && regular_dir(ray.d);
                     odd[j] = !act[j];                                   // re-read below: un-normalised or non-finite ray
                 }
@@ -668,29 +674,33 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
             P = pack3(pin[0], pin[1]); D = pack3(din[0], din[1]); I = f2(Iin[0], Iin[1]);
         }
         const unsigned actb = (act[0] ? 1u : 0u) | (act[1] ? 2u : 0u);
-        unsigned long long mask_a = 0ull, mask_b = 0ull, bit = 1ull;
-        PairDeposit<LOG> dep{a, cache, i0, lam[0], lam[1]};
-        for (int r = 0; r < S; ++r, bit += bit) {
-            const int op = T.rows[r].i[DI_TILE_OP];
-            const int kind = xf[r].kind;                                // warp-uniform
-            const int run = xf[r].run;
-            if (kind) pair_apply_xf(xf[r], P, D);
+        // hit masks: 32-bit words (row r -> bit r & 31 of the current word); the low words are set aside when the walk
+        // passes row 32.  A 64-bit mask per lane costs four extra integer instructions per row.
+        unsigned m_a = 0u, m_b = 0u, lo_a = 0u, lo_b = 0u;
+        bool upper = false;
+        const long long i0 = (long long)tile * kPairTile + threadIdx.x;
+        PairDeposit<LOG> dep{a, cache, i0, use_wav ? lamS[0] / S : 0, use_wav ? lamS[1] / S : 0};
+        for (int r = 0; r < S; ++r) {
+            if (r >= 32 && !upper) { lo_a = m_a; lo_b = m_b; m_a = 0u; m_b = 0u; upper = true; }
+            const int ctl = xf[r].ctl;                                  // warp-uniform: opcode | kind << 8 | run << 16
+            if (ctl & 0xff00) pair_apply_xf(xf[r], P, D);
+            const int run = ctl >> 16;
             if (run > 0) {                                              // lens-edge rows: skip them when no lane can hit
                 const bool away = pair_edge_culled(xf[r], P, D, act[0], act[1]);
                 if (__all_sync(kFull, away)) {
-                    r += run - 1; bit <<= (run - 1);
+                    r += run - 1;
                     continue;
                 }
             }
             unsigned hit;
-            switch (op) {                                               // warp-uniform
+            switch (ctl & 0xff) {                                       // warp-uniform
                 case 1: {
-                    F2 me, mx; pair_ior(T, S, L, r, lam[0], lam[1], me, mx);
+                    F2 me, mx; pair_ior(T, L, r, lamS[0], lamS[1], me, mx);
                     hit = pair_conic_face<true, RTT_SHAPE_SPHERIC_FACE>(T.rows, r, P, D, I, actb, me, mx, dep);
                     break;
                 }
                 case 4: {
-                    F2 me, mx; pair_ior(T, S, L, r, lam[0], lam[1], me, mx);
+                    F2 me, mx; pair_ior(T, L, r, lamS[0], lamS[1], me, mx);
                     hit = pair_conic_face<false, RTT_SHAPE_CYL_FACE>(T.rows, r, P, D, I, actb, me, mx, dep);
                     break;
                 }
@@ -698,29 +708,32 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
                 case 8: hit = pair_plane<RTT_BOUND_DISK, RTT_PHYS_TRANSMIT, true>(T.rows, r, P, D, I, actb, dep); break;
                 case 9: hit = pair_plane<RTT_BOUND_RECT, RTT_PHYS_TRANSMIT, true>(T.rows, r, P, D, I, actb, dep); break;
 #define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR)                                         \
-                case OP: hit = pair_row_generic<KTile<SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR>>(T, S, L, r, i0, lam[0], lam[1], P, D, I, actb, dep); break;
+                case OP: hit = pair_row_generic<KTile<SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR>>(T, S, L, r, i0, dep.lam_a, dep.lam_b, P, D, I, actb, dep); break;
                 RTT_PAIR_SCALAR_SPECS(RTT_X)
 #undef RTT_X
-                default: hit = pair_row_generic<KDyn>(T, S, L, r, i0, lam[0], lam[1], P, D, I, actb, dep); break;
+                default: hit = pair_row_generic<KDyn>(T, S, L, r, i0, dep.lam_a, dep.lam_b, P, D, I, actb, dep); break;
             }
-            if (hit & 1u) mask_a |= bit;
-            if (hit & 2u) mask_b |= bit;
+            const unsigned bit = 1u << (r & 31);
+            m_a |= bit & (0u - (hit & 1u));
+            m_b |= bit & (0u - (hit >> 1));
         }
         if (xf[S].kind) pair_apply_xf(xf[S], P, D);
+        if (!upper) { lo_a = m_a; lo_b = m_b; m_a = 0u; m_b = 0u; }
         // ---- results ----
         V3 po[2] = {lane_a(P), lane_b(P)}, dout[2] = {lane_a(D), lane_b(D)};
         float Io[2] = {I.x, I.y};
-        unsigned long long mo[2] = {mask_a, mask_b};
+        unsigned long long mo[2] = {((unsigned long long)m_a << 32) | lo_a, ((unsigned long long)m_b << 32) | lo_b};
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int loc = threadIdx.x + j * kThreads;
             if (odd[j]) {
                 // un-normalised direction: walk in the reference's order; NaN / inf ray: hits nothing, stays as it was
                 // (the slot still holds this ray's inputs: a thread only ever writes its own entries)
-                const RayIn ray = STREAM ? slot_ray(slot, loc, use_wav) : fetch_ray(a, skey, base + loc, use_wav);
+                const long long i = (long long)tile * kPairTile + loc;
+                const RayIn ray = STREAM ? slot_ray(slot, loc, use_wav) : fetch_ray(a, skey, i, use_wav);
                 WalkState w;
                 w.p = ray.p; w.d = ray.d; w.I = ray.I; w.mask = 0ull;
-                if (finite_ray(ray.p, ray.d)) w = pair_walk_generic<LOG, STREAM>(a, lam[j], base + loc, w);
+                if (finite_ray(ray.p, ray.d)) w = pair_walk_generic<LOG, STREAM>(a, j ? dep.lam_b : dep.lam_a, i, w);
                 po[j] = w.p; dout[j] = w.d; Io[j] = w.I; mo[j] = w.mask;
             }
             if (loc < cnt) {
@@ -732,7 +745,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
                     reinterpret_cast<float*>(slot + kSlotInt)[loc] = Io[j];
                     reinterpret_cast<unsigned long long*>(slot + kSlotMask)[loc] = mo[j];
                 } else {
-                    const long long i = base + loc;
+                    const long long i = (long long)tile * kPairTile + loc;
                     if (a.opos) { store3(a.opos, i, po[j]); store3(a.odir, i, dout[j]); a.ointen[i] = Io[j]; }
                     if (a.hitmask) a.hitmask[i] = mo[j];
                 }
@@ -741,6 +754,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
         if (STREAM) {
             fence_async_smem();
             __syncthreads();                                            // every result of the tile is in the slot
+            const long long base = (long long)tile * kPairTile;
             if (full) {
                 if (threadIdx.x == 0) {
                     const unsigned src = slot0 + (unsigned)(s * kSlotBytes);
@@ -751,10 +765,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
                     }
                     if (a.hitmask) bulk_s2g(a.hitmask + base, src + kSlotMask, kPairTile * 8);
                     bulk_commit();
-                    const long long next = tile + (long long)kPairSlots * gridDim.x;
+                    const long long next = (long long)tile + (long long)kPairSlots * gridDim.x;
                     if (next < n_tiles) {
                         bulk_wait_read0();                              // the stores have read the slot: refill it
-                        if (tile_is_full(next)) issue_load(next, s);
+                        if (next < n_full) issue_load((int)next, s);
                     }
                 }
             } else {
@@ -1469,7 +1483,7 @@ inline cudaError_t launch_tile(const SeqFwdArgs& a, cudaStream_t st) {
 // registers (40 warps / SM) wins (C1, 4 rows: 2.69 -> 2.58 ms per 1e8 rays).
 // The choice depends on the table and the caller's mode bits only (no environment, no cached state), so a bundle
 // generated in the kernel and its materialised twin run the same build and stay bit-identical (tests/test_goals.py).
-inline int fwd_tile_for(int S, int tune) { return tune ? tune : (S <= 6 ? 5 : 3); }
+inline int fwd_tile_for(int S, int tune) { return tune ? tune : (S <= 6 ? 5 : 3); }   // 0 is resolved by the caller (fwd_default_build)
 
 template <int MINB, bool STREAM, int LOG>
 inline cudaError_t launch_pair(const SeqFwdArgs& a, cudaStream_t st) {
@@ -1499,7 +1513,15 @@ inline bool pair_can_stream(const SeqFwdArgs& a) {
 
 cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
 #if defined(RTT_APPROX)
-    switch (fwd_tile_for(a.tab.S, a.tune)) {
+    // Default build (a.tune == 0).  Measured on B200 (profiles/r2_fwd_pair_ab.md): per ray, the packed-pair streaming
+    // kernel saves a fixed amount of issue slots (ray I/O through the copy engine, one packed chain instead of two) but
+    // runs ONE dependency chain per thread at 24 warps / SM, where the tile kernel runs two at 32 — so it wins on short
+    // tables, which are I/O- and issue-bound (C1 4 rows: -2 %, C2 14 rows of which 8 culled: -5 %), and loses on long
+    // ones, which are latency-bound (C4, 17 rows: +20 %).  The library sees the row count only (the table lives in device
+    // memory); the Python layer refines the choice from its host copy of the table (ops._fwd_build_hint).
+    int build = a.tune;
+    if (build == 0) build = (a.tab.S <= 14) ? 16 : fwd_tile_for(a.tab.S, 0);      // by the table only: see tests/test_goals.py
+    switch (build) {
         case 1: return launch_tile<1, 4>(a, st);
         case 2: return launch_tile<2, 3>(a, st);
         case 3: return launch_tile<2, 4>(a, st);

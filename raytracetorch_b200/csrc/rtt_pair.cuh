@@ -101,14 +101,16 @@ RTT_HD bool pair_edge_culled(const Xf& x, const P3& p, const P3& d, bool act_a, 
     const F2 zt = f2(d.z.x > 0.0f ? x.zhi : x.zlo, d.z.y > 0.0f ? x.zhi : x.zlo);
     const F2 rz = f2(rcp_(d.z.x), rcp_(d.z.y));
     const F2 te = fma2(mul2(sub2(zt, p.z), rz), bc(1.0001f), bc(1e-4f));
-    const F2 qx = fma2(te, d.x, p.x), qy = fma2(te, d.y, p.y);
     bool ia, ib;
     if (x.ctype == 2) {
-        ia = p.x.x > x.b[0] && p.x.x < x.b[1] && p.y.x > x.b[2] && p.y.x < x.b[3] &&
-             qx.x > x.b[0] && qx.x < x.b[1] && qy.x > x.b[2] && qy.x < x.b[3];
-        ib = p.x.y > x.b[0] && p.x.y < x.b[1] && p.y.y > x.b[2] && p.y.y < x.b[3] &&
-             qx.y > x.b[0] && qx.y < x.b[1] && qy.y > x.b[2] && qy.y < x.b[3];
+        // both ends of the segment strictly inside the rectangle: max(|p - c|, |q - c|) < half extent, per axis (the
+        // rectangle is already shrunk by 2e-3, far above the rounding of its centre / half-extent form)
+        const F2 ux = add2s(p.x, -x.q[0]), uy = add2s(p.y, -x.q[2]);
+        const F2 vx = fma2(te, d.x, ux), vy = fma2(te, d.y, uy);
+        ia = fmaxf(fabsf(ux.x), fabsf(vx.x)) < x.q[1] && fmaxf(fabsf(uy.x), fabsf(vy.x)) < x.q[3];
+        ib = fmaxf(fabsf(ux.y), fabsf(vx.y)) < x.q[1] && fmaxf(fabsf(uy.y), fabsf(vy.y)) < x.q[3];
     } else {
+        const F2 qx = fma2(te, d.x, p.x), qy = fma2(te, d.y, p.y);
         const F2 rp = fma2(p.x, p.x, mul2(p.y, p.y)), rq = fma2(qx, qx, mul2(qy, qy));
         ia = rp.x < x.b[0] && rq.x < x.b[0];
         ib = rp.y < x.b[0] && rq.y < x.b[0];
@@ -116,31 +118,33 @@ RTT_HD bool pair_edge_culled(const Xf& x, const P3& p, const P3& d, bool act_a, 
     return (da || ia) && (db || ib);
 }
 
-// ---- scalar twin of one row for one lane (rare cases and unpacked row kinds) ----------------------------
-// Returns true iff the lane interacted; state updated in place.  DEP: dep(lane, slot, hit_local, weight).
-template <class K, class DEP>
-RTT_HD bool lane_row(const RowDev* rows, int r, int lane, V3& p, V3& d, float& I, float mu_enter, float mu_exit,
-                     PhysAux aux, DEP& dep) {
-    float t;
-    if (!tile_test<K>(rows, r, p, d, t)) return false;
-    const RowDev& R = rows[r];
-    V3 np, nd, hl; float mod;
-    tile_interact<K>(R, p, d, t, mu_enter, mu_exit, np, nd, mod, hl, aux);
-    if (K::sensor(R)) dep(lane, R.i[RTT_I_SENSOR], hl, I);
-    p = np; d = nd; I = I * mod;
-    return true;
-}
-
+// ---- scalar twin of one row (rare cases and row kinds without a packed form): tile_test / tile_interact per lane ----
+// DEP: dep(lane, slot, hit_local, weight).
 template <class K, class DEP>
 RTT_HD unsigned pair_row_scalar(const RowDev* rows, int r, P3& P, P3& D, F2& I, unsigned act, F2 mu_enter, F2 mu_exit,
                                 PhysAux aux_a, PhysAux aux_b, DEP& dep) {
     V3 pa = lane_a(P), pb = lane_b(P), da = lane_a(D), db = lane_b(D);
+    // both tests first: two independent dependency chains for the scheduler, as in the tile kernel
+    float ta, tb;
+    const bool ha = tile_test<K>(rows, r, pa, da, ta) && (act & 1u);
+    const bool hb = tile_test<K>(rows, r, pb, db, tb) && (act & 2u);
+    if (!(ha || hb)) return 0u;
+    const RowDev& R = rows[r];
     float ia = I.x, ib = I.y;
-    unsigned hit = 0u;
-    if ((act & 1u) && lane_row<K>(rows, r, 0, pa, da, ia, mu_enter.x, mu_exit.x, aux_a, dep)) hit |= 1u;
-    if ((act & 2u) && lane_row<K>(rows, r, 1, pb, db, ib, mu_enter.y, mu_exit.y, aux_b, dep)) hit |= 2u;
-    if (hit) { P = pack3(pa, pb); D = pack3(da, db); I = f2(ia, ib); }
-    return hit;
+    if (ha) {
+        V3 np, nd, hl; float mod;
+        tile_interact<K>(R, pa, da, ta, mu_enter.x, mu_exit.x, np, nd, mod, hl, aux_a);
+        if (K::sensor(R)) dep(0, R.i[RTT_I_SENSOR], hl, ia);
+        pa = np; da = nd; ia = ia * mod;
+    }
+    if (hb) {
+        V3 np, nd, hl; float mod;
+        tile_interact<K>(R, pb, db, tb, mu_enter.y, mu_exit.y, np, nd, mod, hl, aux_b);
+        if (K::sensor(R)) dep(1, R.i[RTT_I_SENSOR], hl, ib);
+        pb = np; db = nd; ib = ib * mod;
+    }
+    P = pack3(pa, pb); D = pack3(da, db); I = f2(ia, ib);
+    return (ha ? 1u : 0u) | (hb ? 2u : 0u);
 }
 
 // ---- conic lens face, packed -----------------------------------------------------------------------------

@@ -71,7 +71,9 @@ struct Xf {
     float zlo, zhi;      // enclosure of the z range the edge rows accept (element frame)
     int32_t ctype;       // 1: z test only, 2: + rectangular cross-section b = (x0, x1, y0, y1), 3: + disc, b[0] = r^2
     float b[4];
-    int32_t pad[3];
+    float q[4];          // ctype 2: the rectangle b as centre / half extents (cx, hx, cy, hy) for the packed cull test
+    int32_t ctl;         // pair kernel: opcode | kind << 8 | run << 16 (set when the tile is staged)
+    int32_t pad[1];
 };
 
 struct FramePose { float R[9]; float T[3]; };
@@ -92,7 +94,7 @@ RTT_HD Xf make_xf(const RowDev* from, const RowDev* to) {
     const FramePose o = frame_pose(from), n = frame_pose(to);
     Xf x;
     x.run = 0; x.zlo = 0.0f; x.zhi = 0.0f; x.ctype = 0;
-    x.b[0] = x.b[1] = x.b[2] = x.b[3] = 0.0f; x.pad[0] = x.pad[1] = x.pad[2] = 0;
+    x.b[0] = x.b[1] = x.b[2] = x.b[3] = 0.0f; x.q[0] = x.q[1] = x.q[2] = x.q[3] = 0.0f; x.ctl = 0; x.pad[0] = 0;
     bool same_R = true, same_T = true, o_ident = true, n_ident = true;
     for (int a = 0; a < 9; ++a) {
         same_R = same_R && (o.R[a] == n.R[a]);
@@ -201,6 +203,8 @@ RTT_HD void edge_run_at(const RowDev* rows, int S, Xf* xf, int r) {
     }
     xf[r].run = run; xf[r].zlo = e.zlo; xf[r].zhi = e.zhi; xf[r].ctype = e.ctype;
     for (int a = 0; a < 4; ++a) xf[r].b[a] = e.b[a];
+    xf[r].q[0] = 0.5f * (e.b[0] + e.b[1]); xf[r].q[1] = 0.5f * (e.b[1] - e.b[0]);
+    xf[r].q[2] = 0.5f * (e.b[2] + e.b[3]); xf[r].q[3] = 0.5f * (e.b[3] - e.b[2]);
 }
 
 RTT_HD bool edge_culled(const Xf& x, V3 p, V3 d) {

@@ -62,6 +62,21 @@ def _with_tune(mode: int, tune: int) -> int:
     return mode if (mode & MODE_TUNE_MASK) else (mode | (tune << MODE_TUNE_SHIFT))
 
 
+def _fwd_build_hint(i_host) -> int:
+    """Kernel build of the sequential forward trace for rays that live in device memory, from the host copy of the
+    table's int block: the packed-pair streaming kernel (16) when the walk is SHORT — rows that are not lens-edge rows
+    plus one cull test per run of edge rows <= 10 — else 0 (the library's choice by row count).  Measured on B200:
+    profiles/r2_fwd_pair_ab.md (C1 / C2 gain 2-5 %, C4 with 15 effective rows loses 20 %)."""
+    edge = (C.SHAPE_SPHERIC_EDGE, C.SHAPE_CYL_EDGE)
+    eff, prev_edge = 0, False
+    for m in i_host:
+        is_edge = m[C.I_SHAPE] in edge
+        if not is_edge or not prev_edge:
+            eff += 1
+        prev_edge = is_edge
+    return 16 if eff <= 10 else (5 if len(i_host) <= 6 else 3)
+
+
 def set_default_mode(mode: int, nonseq: Optional[int] = None):
     """Set the arithmetic of the sequential/element ops (and, if given, of the non-sequential op)."""
     global _default_mode, _default_mode_nonseq
@@ -861,6 +876,10 @@ def trace_sequential(table: SurfaceTable, pos=None, dir_=None, intensity=None, w
     cfg = sensor_cfg_of(table) if sensor_cfg is None else list(sensor_cfg)
     mode = _default_mode if mode is None else mode
     hint = adjoint_hint(table)
+    if not _tune_fwd and not (mode & MODE_TUNE_MASK) and (mode & 0xFF) == MODE_FAST:
+        # the build depends on the TABLE only: rays generated in the kernel and their materialised twin run the same
+        # arithmetic and stay bit-identical (tests/test_goals.py)
+        mode |= _fwd_build_hint(table.i_host) << MODE_TUNE_SHIFT
     if source is not None:
         _need_cuda(table.f)
         opos, odir, oint, hitmask, records, images = _TraceSeqSrc.apply(
@@ -904,6 +923,8 @@ def trace_sequential_host(table: SurfaceTable, pos, dir_, intensity, wavelength=
     lib = _cabi.load()
     cfg = sensor_cfg_of(table) if sensor_cfg is None else list(sensor_cfg)
     mode = _default_mode if mode is None else mode
+    if not _tune_fwd and not (mode & MODE_TUNE_MASK) and (mode & 0xFF) == MODE_FAST:
+        mode |= _fwd_build_hint(table.i_host) << MODE_TUNE_SHIFT
     f32 = dict(dtype=torch.float32, device=dev)
     pos, dir_, intensity = (_f32c(t.detach()) for t in (pos, dir_, intensity))
     use_wav = table.lut is not None and wavelength is not None       # the kernel reads it only with an index table
