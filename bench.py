@@ -970,10 +970,11 @@ def run_c3(args):
     torch.manual_seed(100 + rank)
     loss_host = torch.empty(1).pin_memory()
     graphed = None
-    if (world == 1 or args.graph_multi) and not args.no_graph:
+    if (world == 1 or not args.no_graph_multi) and not args.no_graph:
         # the whole step (zero_grad, goal, backward, Adam) replays as ONE CUDA graph (optim.GraphedStep).  With several
-        # ranks the NCCL all-reduces can be captured with it (--graph-multi: 1.89 -> 1.33 ms per step at N=2), but a
-        # process that still holds the captured graph hung in destroy_process_group on this image, so it is opt-in
+        # ranks the NCCL all-reduces of the step are captured with it (N=2: 1.96 -> 1.37 ms per step, r2 box m1); the
+        # graph is released BEFORE the process group is destroyed (end of this function): a process that still held
+        # the captured NCCL work hung in destroy_process_group in round 1
         opt = torch.optim.Adam(params, lr=1e-5, capturable=True)
         sync = (lambda: rdist.allreduce_scene_results([], params)) if world > 1 else None
         graphed = rtt.optim.GraphedStep.try_build(scene, goal, opt, after_backward=sync)
@@ -1155,8 +1156,9 @@ def main():
     ap.add_argument("--no-config4", action="store_true",
                     help="default workload only: skip the extra BASELINE config-4 (camera render) measurement")
     ap.add_argument("--no-graph", action="store_true", help="c3: run the optimisation step eagerly (no CUDA graph)")
-    ap.add_argument("--graph-multi", action="store_true",
-                    help="c3 with several ranks: capture the step including its NCCL all-reduces (see run_c3)")
+    ap.add_argument("--no-graph-multi", action="store_true",
+                    help="c3 with several ranks: do NOT capture the NCCL all-reduces with the step (eager steps)")
+    ap.add_argument("--graph-multi", action="store_true", help="(default since r2; kept for old command lines)")
     args = ap.parse_args()
     args.rays = int(args.rays)
     if args.impl == "reference":
