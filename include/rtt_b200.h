@@ -275,6 +275,28 @@ int rtt_spot_size_fwd(const float* rec, int64_t m, const float* mom4, const floa
 int rtt_spot_size_bwd(const float* rec, int64_t m, const float* mom4, const float* target_xy, const float* out3,
                       const float* g_loss, float* g_rec, void* stream);
 
+/* Per-id sensor moments: Sensor.getSpotSizeParallel_xy (elements/sensor.py:87-176: isin + sort + searchsorted +
+ * scatter_add over the hit lists) as one pass per reduction over the dense records.
+ *   rec      : [m,4] sensor records (x, y, z, w), w == 0 = no hit (every sum below is weighted by w)
+ *   ids      : [m] int8 ray ids (rays/ray.py:17)
+ *   group_of : DEVICE int32 [256], group_of[id + 128] = index of `id` in the caller's query list, -1 = not queried
+ *   n_groups : K = number of queried ids, 1..256
+ *   work     : DEVICE scratch of RTT_SPOT_ID_WORK floats, zero before the first call (left zeroed), one per stream
+ * rtt_spot_id_moments:  out [K,4] = per group (sum w, sum w x, sum w y, #{w > 0})
+ * rtt_spot_id_size:     with centres [K,2] (centroids or targets) and norm order p >= 1:
+ *                       out [K,4] = (sum w (|dx|^p + |dy|^p), sum w p |dx|^(p-1) sgn dx, sum w p |dy|^(p-1) sgn dy, 0);
+ *                       the reference's result is out[k][0] / (2 max-or-one(sum w)), entries 1, 2 feed the adjoint
+ * rtt_spot_id_size_bwd: coef [K,8] = (cx, cy, a, bx, by, sW, 0, 0) per group ->
+ *                       g_rec[i] = (a w (p|dx|^(p-1) sgn dx - bx), a w (p|dy|^(p-1) sgn dy - by), 0,
+ *                                   a (|dx|^p + |dy|^p - bx dx - by dy - sW)), zero for ids that were not queried */
+enum { RTT_SPOT_ID_WORK = 296 * 256 * 4 + 4 };
+int rtt_spot_id_moments(const float* rec, const int8_t* ids, int64_t m, const int32_t* group_of, int32_t n_groups,
+                        float* out, float* work, void* stream);
+int rtt_spot_id_size(const float* rec, const int8_t* ids, int64_t m, const int32_t* group_of, int32_t n_groups,
+                     const float* centres, float norm_ord, float* out, float* work, void* stream);
+int rtt_spot_id_size_bwd(const float* rec, const int8_t* ids, int64_t m, const int32_t* group_of, int32_t n_groups,
+                         const float* coef, float norm_ord, float* g_rec, void* stream);
+
 /* Measurement helper (bench.py): launches a pure-FMA kernel (8 independent chains per thread,
  * 8 blocks of 256 threads per SM, `iters` x 64 FMAs per thread) on `stream` and returns the FLOPs
  * it executes (FMA = 2), or a negative code.  Timed with CUDA events by the caller, this is the

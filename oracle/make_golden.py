@@ -263,6 +263,31 @@ def _gen_goal_case(ns, prefix):
     return data
 
 
+def gen_spot_id_case(ns):
+    """Sensor.getSpotSizeParallel_xy (elements/sensor.py:87-176) of the UNMODIFIED reference on a multi-bundle
+    sequential trace: three bundles (ray ids 0, 1, 2; the goal fixture's samples) through the C1 singlet onto its
+    sensor, then per-id spot sizes for query ids [2, 0, 1] — centroid and fixed targets, norm orders 2 and 3 — and the
+    gradients of their sums w.r.t. the two curvatures.  (getSpotSizeID_xy raises in the reference at this snapshot —
+    a 0-dim centroid is indexed with [None, :] — so only the parallel method pins this path.)"""
+    data = {}
+    query = [2, 0, 1]
+    targets = torch.tensor([[0.05, -0.02], [0.0, 0.0], [-0.03, 0.04]])
+    data["query"], data["targets"] = np.array(query), targets.numpy()
+    for tag, tgt, p in (("centroid_p2", None, 2), ("target_p2", targets, 2), ("centroid_p3", None, 3)):
+        _scene, elements, bundles = goal_setup(ns)
+        sensor = elements[1]
+        seq = ns.scene.SequentialScene(elements)
+        torch.manual_seed(GOAL_SEED)
+        for b in bundles:
+            seq.simulate(b.sample(GOAL_RAYS))
+        res, wsum = sensor.getSpotSizeParallel_xy(query, target_xy=tgt, norm_ord=p)
+        res.sum().backward()
+        data[f"{tag}_result"], data[f"{tag}_intensity_sum"] = res.detach().numpy().copy(), wsum.detach().numpy().copy()
+        for k in (0, 1):
+            data[f"{tag}_g_c{k}"] = elements[0].shape.surfaces[k].c.grad.numpy().copy()
+    return data
+
+
 def main(argv):
     os.makedirs(OUT, exist_ok=True)
     ns = ref_namespace()
@@ -286,6 +311,10 @@ def main(argv):
         g = gen_goal_case(ns)
         np.savez_compressed(os.path.join(OUT, "extra_goals.npz"), **g)
         print("extras:", {k: float(v) for k, v in g.items() if k.endswith("_loss")})
+    if not wanted or "extras" in wanted or "spot_id" in wanted:
+        sid = gen_spot_id_case(ns)
+        np.savez_compressed(os.path.join(OUT, "extra_spot_id.npz"), **sid)
+        print("spot_id:", {k: v.tolist() for k, v in sid.items() if k.endswith("_result")})
     for name in GRAD_CASES:
         if wanted and name not in wanted:
             continue

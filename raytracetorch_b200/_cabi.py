@@ -42,6 +42,7 @@ class SourceReq(ct.Structure):
 
 
 SRC_DISK, SRC_LINE, SRC_FAN, SRC_POINT, SRC_CAMERA = 0, 1, 2, 3, 4
+SPOT_ID_WORK = 296 * 256 * 4 + 4     # floats of scratch per stream for the per-id reductions (RTT_SPOT_ID_WORK)
 SPOT_WORK = 4 * 1024 + 4
 
 
@@ -79,6 +80,9 @@ _SIGS = {
     "rtt_spot_moments_bwd": [_P, ct.c_int64, ct.c_int32, _P, _P, _P],
     "rtt_spot_size_fwd": [_P, ct.c_int64, _P, _P, _P, _P, _P],
     "rtt_spot_size_bwd": [_P, ct.c_int64, _P, _P, _P, _P, _P, _P],
+    "rtt_spot_id_moments": [_P, _P, ct.c_int64, _P, ct.c_int32, _P, _P, _P],
+    "rtt_spot_id_size": [_P, _P, ct.c_int64, _P, ct.c_int32, _P, ct.c_float, _P, _P, _P],
+    "rtt_spot_id_size_bwd": [_P, _P, ct.c_int64, _P, ct.c_int32, _P, ct.c_float, _P, _P],
 }
 # symbols every build of the CUDA library must export (tests/test_cabi.py checks them)
 EXPORTS = tuple(_SIGS) + ("rtt_version", "rtt_layout_query", "rtt_error_string", "rtt_launch_count")

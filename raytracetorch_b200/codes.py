@@ -62,4 +62,5 @@ MAX_BOUNCES = 255           # hit sequence is stored one byte per bounce
 
 # ray source kinds (rtt_source_t.kind) and the scratch size of the goal reductions
 SRC_DISK, SRC_LINE, SRC_FAN, SRC_POINT, SRC_CAMERA = 0, 1, 2, 3, 4
+SPOT_ID_WORK = 296 * 256 * 4 + 4    # floats of scratch per stream of the per-id reductions (RTT_SPOT_ID_WORK)
 SPOT_WORK = 4 * 1024 + 4

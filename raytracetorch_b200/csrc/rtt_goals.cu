@@ -170,6 +170,129 @@ __global__ void __launch_bounds__(kThreads) k_spot_size_bwd(const float4* __rest
     }
 }
 
+
+// ============================================================================================
+// Per-id sensor moments (elements/sensor.py:87-176, Sensor.getSpotSizeParallel_xy)
+// ============================================================================================
+// The reference filters the hit lists with isin, sorts the query ids, maps every hit to its group with searchsorted and
+// reduces with three scatter_adds (plus the boolean gathers of getHitsTensors).  Here: one pass over the dense records
+// [m,4] + int8 ids per reduction.  A 256-entry table (id + 128 -> group, -1 = not queried) lives in shared memory;
+// a thread keeps the running sums of the group it is in (ray ids come in runs: one bundle after the other) and
+// touches the block's shared accumulators only when the group changes; blocks publish their partials and the last
+// block folds them in a fixed order in double precision (deterministic, like the reductions above).
+constexpr int kIdBlocks = 296;                         // RTT_SPOT_ID_WORK = kIdBlocks * 256 * 4 + 4 floats
+
+// MODE 0: v = (w, w x, w y, [w > 0])                                   -> out[k] = per-group sums
+// MODE 1: v = (w (|dx|^p + |dy|^p), w p |dx|^(p-1) sgn dx, w p |dy|^(p-1) sgn dy, 0), d = xy - centre[k]
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) k_spot_id_sums(const float4* __restrict__ rec, const signed char* __restrict__ ids,
+                                                           long long m, const int* __restrict__ group_of, int K,
+                                                           const float* __restrict__ centres, float p,
+                                                           float* __restrict__ out, float* __restrict__ work) {
+    __shared__ int lut[256];
+    __shared__ float acc[256 * 4];
+    __shared__ bool last;
+    for (int idx = threadIdx.x; idx < 256; idx += kThreads) lut[idx] = group_of[idx];
+    for (int idx = threadIdx.x; idx < 4 * K; idx += kThreads) acc[idx] = 0.0f;
+    __syncthreads();
+    int cur = -1;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f, cx = 0.0f, cy = 0.0f;
+    auto flush = [&]() {
+        if (cur >= 0) {
+            if (a0 != 0.0f) atomicAdd(acc + 4 * cur, a0);
+            if (a1 != 0.0f) atomicAdd(acc + 4 * cur + 1, a1);
+            if (a2 != 0.0f) atomicAdd(acc + 4 * cur + 2, a2);
+            if (a3 != 0.0f) atomicAdd(acc + 4 * cur + 3, a3);
+        }
+        a0 = a1 = a2 = a3 = 0.0f;
+    };
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        const int g = lut[(int)ids[i] + 128];
+        if (g < 0) continue;
+        const float4 r = __ldg(rec + i);
+        if (r.w == 0.0f) continue;                                      // every sum is weighted by w
+        if (g != cur) {
+            flush();
+            cur = g;
+            if (MODE == 1) { cx = centres[2 * g]; cy = centres[2 * g + 1]; }
+        }
+        if (MODE == 0) {
+            a0 += r.w; a1 += r.w * r.x; a2 += r.w * r.y; a3 += (r.w > 0.0f) ? 1.0f : 0.0f;
+        } else {
+            const float dx = r.x - cx, dy = r.y - cy;
+            if (p == 2.0f) {
+                a0 += r.w * (dx * dx + dy * dy); a1 += r.w * 2.0f * dx; a2 += r.w * 2.0f * dy;
+            } else {
+                const float ax = fabsf(dx), ay = fabsf(dy);
+                const float px = powf(ax, p - 1.0f), py = powf(ay, p - 1.0f);
+                a0 += r.w * (px * ax + py * ay);
+                a1 += r.w * p * px * (dx > 0.0f ? 1.0f : (dx < 0.0f ? -1.0f : 0.0f));
+                a2 += r.w * p * py * (dy > 0.0f ? 1.0f : (dy < 0.0f ? -1.0f : 0.0f));
+            }
+        }
+    }
+    flush();
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 4 * K; idx += kThreads) work[(size_t)blockIdx.x * 4 * K + idx] = acc[idx];
+    __threadfence();
+    __syncthreads();
+    unsigned* ticket = reinterpret_cast<unsigned*>(work + (size_t)kIdBlocks * 256 * 4);
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int idx = threadIdx.x; idx < 4 * K; idx += kThreads) {
+        double v = 0.0;
+        for (int b = 0; b < (int)gridDim.x; ++b) v += (double)__ldcg(work + (size_t)b * 4 * K + idx);
+        out[idx] = (float)v;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;                // leave the workspace ready for the next launch
+}
+
+// coef[k] = (cx, cy, a, bx, by, sW, -, -):  g_rec = (a w (p |dx|^(p-1) sgn dx - bx), a w (p |dy|^(p-1) sgn dy - by), 0,
+//                                                    a ((|dx|^p + |dy|^p) - bx dx - by dy - sW))
+__global__ void __launch_bounds__(kThreads) k_spot_id_size_bwd(const float4* __restrict__ rec, const signed char* __restrict__ ids,
+                                                               long long m, const int* __restrict__ group_of, int K,
+                                                               const float* __restrict__ coef, float p,
+                                                               float4* __restrict__ g_rec) {
+    __shared__ int lut[256];
+    __shared__ float cf[256 * 8];
+    for (int idx = threadIdx.x; idx < 256; idx += kThreads) lut[idx] = group_of[idx];
+    for (int idx = threadIdx.x; idx < 8 * K; idx += kThreads) cf[idx] = coef[idx];
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        const int g = lut[(int)ids[i] + 128];
+        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g >= 0) {
+            const float4 r = __ldg(rec + i);
+            const float* c = cf + 8 * g;
+            const float dx = r.x - c[0], dy = r.y - c[1];
+            float sx, sy, pw;
+            if (p == 2.0f) { sx = 2.0f * dx; sy = 2.0f * dy; pw = dx * dx + dy * dy; }
+            else {
+                const float ax = fabsf(dx), ay = fabsf(dy);
+                const float px = powf(ax, p - 1.0f), py = powf(ay, p - 1.0f);
+                sx = p * px * (dx > 0.0f ? 1.0f : (dx < 0.0f ? -1.0f : 0.0f));
+                sy = p * py * (dy > 0.0f ? 1.0f : (dy < 0.0f ? -1.0f : 0.0f));
+                pw = px * ax + py * ay;
+            }
+            out.x = c[2] * r.w * (sx - c[3]);
+            out.y = c[2] * r.w * (sy - c[4]);
+            out.w = c[2] * (pw - c[3] * dx - c[4] * dy - c[5]);
+        }
+        g_rec[i] = out;
+    }
+}
+
+int grid_id(long long m) {
+    long long g = (m + kThreads - 1) / kThreads;
+    if (g > kIdBlocks) g = kIdBlocks;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
 int grid_for(long long m) {
     long long g = (m + kThreads - 1) / kThreads;
     if (g > kMaxBlocks) g = kMaxBlocks;
@@ -219,6 +342,42 @@ int rtt_spot_size_bwd(const float* rec, int64_t m, const float* mom4, const floa
     if (!rtt_internal_have_device()) return RTT_E_NO_DEVICE;
     k_spot_size_bwd<<<grid_for(m) * 4, kThreads, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(rec), m, mom4, target_xy, out3, g_loss, reinterpret_cast<float4*>(g_rec));
+    return rtt_internal_finish(cudaGetLastError());
+}
+
+int rtt_spot_id_moments(const float* rec, const int8_t* ids, int64_t m, const int32_t* group_of, int32_t n_groups,
+                        float* out, float* work, void* stream) {
+    if (m < 0 || !group_of || !out || !work || n_groups < 1 || n_groups > 256 || (m > 0 && (!rec || !ids))) return RTT_E_ARG;
+    if (m > 0 && bad_rec(rec)) return RTT_E_ALIGN;
+    if (!rtt_internal_have_device()) return RTT_E_NO_DEVICE;
+    k_spot_id_sums<0><<<grid_id(m), kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(rec), reinterpret_cast<const signed char*>(ids), m, group_of, n_groups, nullptr,
+        2.0f, out, work);
+    return rtt_internal_finish(cudaGetLastError());
+}
+
+int rtt_spot_id_size(const float* rec, const int8_t* ids, int64_t m, const int32_t* group_of, int32_t n_groups,
+                     const float* centres, float norm_ord, float* out, float* work, void* stream) {
+    if (m < 0 || !group_of || !centres || !out || !work || n_groups < 1 || n_groups > 256 || (m > 0 && (!rec || !ids)))
+        return RTT_E_ARG;
+    if (!(norm_ord >= 1.0f)) return RTT_E_ARG;
+    if (m > 0 && bad_rec(rec)) return RTT_E_ALIGN;
+    if (!rtt_internal_have_device()) return RTT_E_NO_DEVICE;
+    k_spot_id_sums<1><<<grid_id(m), kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(rec), reinterpret_cast<const signed char*>(ids), m, group_of, n_groups, centres,
+        norm_ord, out, work);
+    return rtt_internal_finish(cudaGetLastError());
+}
+
+int rtt_spot_id_size_bwd(const float* rec, const int8_t* ids, int64_t m, const int32_t* group_of, int32_t n_groups,
+                         const float* coef, float norm_ord, float* g_rec, void* stream) {
+    if (m == 0) return RTT_OK;
+    if (m < 0 || !ids || !group_of || !coef || n_groups < 1 || n_groups > 256 || !(norm_ord >= 1.0f)) return RTT_E_ARG;
+    if (bad_rec(rec) || bad_rec(g_rec)) return rec && g_rec ? RTT_E_ALIGN : RTT_E_ARG;
+    if (!rtt_internal_have_device()) return RTT_E_NO_DEVICE;
+    k_spot_id_size_bwd<<<grid_id(m) * 4, kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(rec), reinterpret_cast<const signed char*>(ids), m, group_of, n_groups, coef,
+        norm_ord, reinterpret_cast<float4*>(g_rec));
     return rtt_internal_finish(cudaGetLastError());
 }
 

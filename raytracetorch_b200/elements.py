@@ -498,6 +498,69 @@ class Sensor(Element):
         self._locs, self._w, self._ids, self._pending = [], [], [], []
         self.image = None
 
+    # ---- per-id spot sizes (elements/sensor.py:67-176) ----------------------------------------------------------
+    def _dense_records(self):
+        """(rec [M,4], ids [M]) of every pending fused-kernel trace when ALL recorded hits are still in their dense,
+        un-gathered form on a CUDA device (no boolean compaction, no host sync); None otherwise."""
+        if self._locs or not self._pending:
+            return None
+        recs, ids = [], []
+        for record, _hit, rid, overflow in self._pending:
+            if overflow is not None or not record.is_cuda:
+                return None
+            recs.append(record.reshape(-1, 4))
+            rid = rid() if callable(rid) else rid
+            ids.append(rid.reshape(-1))
+        return (recs[0], ids[0]) if len(recs) == 1 else (torch.cat(recs, 0), torch.cat(ids, 0))
+
+    def getSpotSizeParallel_xy(self, query_ids, target_xy=None, norm_ord=2):
+        """Per-ray-id spot sizes, all ids at once (elements/sensor.py:87-176): for each id in ``query_ids``
+        sum_i w_i (|x_i - cx|^p + |y_i - cy|^p) / (2 sum_i w_i) about the id's intensity centroid or its row of
+        ``target_xy`` [K,2] (given in the order of ``query_ids``).  Returns ``(spot_sizes [K], intensity_sum [K])``
+        like the reference: spot sizes in the order of ``query_ids``, the intensity sums in the order of the SORTED
+        ids (the reference un-sorts only its first output).
+
+        After a fused CUDA trace this is two reduction kernels over the dense sensor records (rtt_spot_id_*), no hit
+        lists are built; otherwise the same sums are taken with torch index_add on the hit lists."""
+        q = torch.as_tensor(query_ids).reshape(-1)
+        order = torch.argsort(q.to(torch.int64))
+        dense = self._dense_records()
+        if dense is not None:
+            from . import ops
+            rec, ids = dense
+            size, wsum = ops.spot_size_per_id(rec, ids, q, target_xy, norm_ord)
+            return size, wsum[order.to(wsum.device)]
+        locs, w, ids = self.getHitsTensors()
+        K = q.numel()
+        lut = torch.full((256,), -1, dtype=torch.int64, device=ids.device)
+        lut[q.to(torch.int64).to(ids.device) + 128] = torch.arange(K, device=ids.device)
+        grp = lut[ids.to(torch.int64) + 128]
+        keep = grp >= 0
+        xy, w, grp = locs[keep, :2], w[keep], grp[keep]
+        wsum = torch.zeros(K, dtype=w.dtype, device=w.device).index_add(0, grp, w)
+        safe = torch.where(wsum == 0, torch.ones_like(wsum), wsum)
+        if target_xy is None:
+            centres = torch.zeros(K, 2, dtype=xy.dtype, device=xy.device).index_add(0, grp, xy * w[:, None]) / safe[:, None]
+        else:
+            centres = torch.as_tensor(target_xy, dtype=xy.dtype, device=xy.device).reshape(K, 2)
+        moment = (w[:, None] * (xy - centres[grp]).abs() ** norm_ord).sum(1)
+        size = torch.zeros(K, dtype=xy.dtype, device=xy.device).index_add(0, grp, moment) / (2 * safe)
+        return size, wsum[order.to(wsum.device)]
+
+    def getSpotSizeID_xy(self, ray_id, target_xy=None, norm_ord=2):
+        """Per-axis weighted moment [2] of ONE ray id about its centroid / ``target_xy`` [2]:
+        sum_{i in id} w_i |xy_i - c|^p / sum_i w_i (elements/sensor.py:67-85).  The reference's method raises at this
+        snapshot (it indexes a 0-dim centroid with [None, :] and multiplies the un-masked intensities into the masked
+        hits); this is what its formula states once the id mask is applied consistently: centroid and moment over the
+        id's hits, normalised by the TOTAL recorded intensity as written there."""
+        locs, w, ids = self.getHitsTensors()
+        keep = ids == int(ray_id)
+        xy, wi = locs[keep, :2], w[keep]
+        total = w.sum()
+        c = (xy * wi[:, None]).sum(0) / total if target_xy is None else \
+            torch.as_tensor(target_xy, dtype=xy.dtype, device=xy.device).reshape(2)
+        return (wi[:, None] * (xy - c[None, :]).abs() ** norm_ord).sum(0) / total
+
     def getHitsTensors(self, ray_id=None):
         """(locs [M,3], intensities [M], ids [M]) over all recorded hits
         (elements/sensor.py:46-65)."""

@@ -792,6 +792,121 @@ def spot_size(rec: torch.Tensor, target_xy: Optional[torch.Tensor] = None) -> to
     """Differentiable SpotSizeLoss term of ONE bundle from its sensor records rec [..., 4]."""
     return spot_size_active(rec, target_xy)[0]
 
+# ---- per-id sensor moments (rtt_goals.cu k_spot_id_*) -------------------------------------------------------------
+_SPOT_ID_WORK = {}
+
+
+def _spot_id_work(dev) -> torch.Tensor:
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    w = _SPOT_ID_WORK.get(key)
+    if w is None:
+        w = _SPOT_ID_WORK[key] = torch.zeros(_cabi.SPOT_ID_WORK, dtype=torch.float32, device=dev)
+    return w
+
+
+@torch.library.custom_op("rtt_b200::spot_id_moments", mutates_args=())
+def _spot_id_moments(rec: torch.Tensor, ids: torch.Tensor, group_of: torch.Tensor, n_groups: int) -> torch.Tensor:
+    """rec [M,4], ids int8 [M], group_of int32 [256] -> [K,4] = (sum w, sum w x, sum w y, #(w > 0)) per queried id"""
+    _need_cuda(rec, ids, group_of)
+    out = torch.empty((n_groups, 4), dtype=torch.float32, device=rec.device)
+    with torch.cuda.device(rec.device):
+        _cabi.load().call("rtt_spot_id_moments", _ptr(rec), _ptr(ids), rec.shape[0], group_of.data_ptr(), n_groups,
+                          out.data_ptr(), _spot_id_work(rec.device).data_ptr(), _stream(rec))
+    return out
+
+
+@_spot_id_moments.register_fake
+def _(rec, ids, group_of, n_groups):
+    return rec.new_empty((n_groups, 4))
+
+
+@torch.library.custom_op("rtt_b200::spot_id_size", mutates_args=())
+def _spot_id_size(rec: torch.Tensor, ids: torch.Tensor, group_of: torch.Tensor, n_groups: int, centres: torch.Tensor,
+                  norm_ord: float) -> torch.Tensor:
+    """-> [K,4] = (sum w (|dx|^p + |dy|^p), sum w p|dx|^(p-1) sgn dx, sum w p|dy|^(p-1) sgn dy, 0)"""
+    _need_cuda(rec, ids, group_of, centres)
+    out = torch.empty((n_groups, 4), dtype=torch.float32, device=rec.device)
+    with torch.cuda.device(rec.device):
+        _cabi.load().call("rtt_spot_id_size", _ptr(rec), _ptr(ids), rec.shape[0], group_of.data_ptr(), n_groups,
+                          centres.data_ptr(), float(norm_ord), out.data_ptr(), _spot_id_work(rec.device).data_ptr(),
+                          _stream(rec))
+    return out
+
+
+@_spot_id_size.register_fake
+def _(rec, ids, group_of, n_groups, centres, norm_ord):
+    return rec.new_empty((n_groups, 4))
+
+
+@torch.library.custom_op("rtt_b200::spot_id_size_bwd", mutates_args=())
+def _spot_id_size_bwd(rec: torch.Tensor, ids: torch.Tensor, group_of: torch.Tensor, n_groups: int, coef: torch.Tensor,
+                      norm_ord: float) -> torch.Tensor:
+    _need_cuda(rec, ids, group_of, coef)
+    g = torch.empty_like(rec)
+    with torch.cuda.device(rec.device):
+        _cabi.load().call("rtt_spot_id_size_bwd", _ptr(rec), _ptr(ids), rec.shape[0], group_of.data_ptr(), n_groups,
+                          coef.data_ptr(), float(norm_ord), _ptr(g), _stream(rec))
+    return g
+
+
+@_spot_id_size_bwd.register_fake
+def _(rec, ids, group_of, n_groups, coef, norm_ord):
+    return torch.empty_like(rec)
+
+
+class _SpotSizePerId(torch.autograd.Function):
+    """Sensor.getSpotSizeParallel_xy (elements/sensor.py:87-176) on dense records: per queried ray id,
+    sum_i w_i (|x_i - cx|^p + |y_i - cy|^p) / (2 W), W = sum_i w_i (1 where no hit), c = the id's intensity centroid
+    or its target.  Two reduction launches forward, one elementwise launch backward; sums are global over ranks."""
+
+    @staticmethod
+    def forward(ctx, rec, ids, group_of, n_groups, targets, norm_ord):
+        mom = _all_reduce_sum(torch.ops.rtt_b200.spot_id_moments(rec, ids, group_of, n_groups))
+        W = mom[:, 0]
+        safe = torch.where(W == 0, torch.ones_like(W), W)                # safe_denom (sensor.py:124-125)
+        centres = (mom[:, 1:3] / safe[:, None]) if targets is None else targets
+        centres = centres.contiguous()
+        s4 = _all_reduce_sum(torch.ops.rtt_b200.spot_id_size(rec, ids, group_of, n_groups, centres, norm_ord))
+        ctx.save_for_backward(rec, ids, group_of, centres, s4, safe, W)
+        ctx.meta = (n_groups, float(norm_ord), targets is None)
+        ctx.mark_non_differentiable(W)
+        return s4[:, 0] / (2.0 * safe), W
+
+    @staticmethod
+    def backward(ctx, g_out, _g_w):
+        rec, ids, group_of, centres, s4, safe, W = ctx.saved_tensors
+        K, p, free_centre = ctx.meta
+        a = g_out / (2.0 * safe)
+        hit = (W != 0).to(a.dtype)
+        bx = s4[:, 1] / safe * hit if free_centre else torch.zeros_like(a)
+        by = s4[:, 2] / safe * hit if free_centre else torch.zeros_like(a)
+        sW = s4[:, 0] / safe * hit                                       # d/dW of S / (2W); no W-dependence where W was replaced by 1
+        z = torch.zeros_like(a)
+        coef = torch.stack([centres[:, 0], centres[:, 1], a, bx, by, sW, z, z], 1).contiguous()
+        return torch.ops.rtt_b200.spot_id_size_bwd(rec, ids, group_of, K, coef, p), None, None, None, None, None
+
+
+def _group_table(query_ids, device) -> torch.Tensor:
+    """int32 [256]: group_of[id + 128] = position of `id` in query_ids, -1 elsewhere (int8 ids, rays/ray.py:17)."""
+    q = torch.as_tensor(query_ids).to(torch.int64).reshape(-1).cpu()
+    if q.numel() < 1 or q.numel() > 256 or int(q.min()) < -128 or int(q.max()) > 127 or q.unique().numel() != q.numel():
+        raise ValueError("query_ids must be 1..256 distinct int8 ray ids")
+    lut = torch.full((256,), -1, dtype=torch.int32)
+    lut[q + 128] = torch.arange(q.numel(), dtype=torch.int32)
+    return lut.to(device)
+
+
+def spot_size_per_id(rec: torch.Tensor, ids: torch.Tensor, query_ids, target_xy: Optional[torch.Tensor] = None,
+                     norm_ord: float = 2):
+    """Differentiable per-id spot sizes of dense sensor records rec [M,4] with ray ids [M] int8:
+    (spot_size [K] in the order of ``query_ids``, intensity_sum [K] in the same order)."""
+    rec = _f32c(rec).reshape(-1, 4)
+    ids = ids.reshape(-1).to(torch.int8).contiguous()
+    lut = _group_table(query_ids, rec.device)
+    K = int((lut >= 0).sum())
+    tgt = None if target_xy is None else _f32c(torch.as_tensor(target_xy).to(rec.device)).reshape(K, 2)
+    return _SpotSizePerId.apply(rec, ids, lut, K, tgt, float(norm_ord))
+
 
 def sample_source(rays, mode: Optional[int] = None):
     """Materialise SourceRays: (pos, dir, intensity, wavelength) from rtt_sample_bundle."""

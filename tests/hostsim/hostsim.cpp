@@ -595,4 +595,63 @@ int rtt_spot_size_bwd(const float* rec, int64_t m, const float* mom4, const floa
     return 0;
 }
 
+
+// ---- per-id sensor moments (host mirror of csrc/rtt_goals.cu k_spot_id_*; same formulas, double accumulation) ----
+int rtt_spot_id_moments(const float* rec, const int8_t* ids, int64_t m, const int32_t* group_of, int32_t K,
+                        float* out, float*, void*) {
+    std::vector<double> acc(4 * (size_t)K, 0.0);
+    for (int64_t i = 0; i < m; ++i) {
+        const int g = group_of[(int)ids[i] + 128];
+        const float* r = rec + 4 * i;
+        if (g < 0 || r[3] == 0.0f) continue;
+        acc[4 * g] += r[3]; acc[4 * g + 1] += (double)(r[3] * r[0]); acc[4 * g + 2] += (double)(r[3] * r[1]);
+        acc[4 * g + 3] += r[3] > 0.0f ? 1.0 : 0.0;
+    }
+    for (size_t k = 0; k < acc.size(); ++k) out[k] = (float)acc[k];
+    return 0;
+}
+
+static inline void spot_id_terms(float dx, float dy, float p, float& pw, float& sx, float& sy) {
+    if (p == 2.0f) { sx = 2.0f * dx; sy = 2.0f * dy; pw = dx * dx + dy * dy; return; }
+    const float ax = std::fabs(dx), ay = std::fabs(dy);
+    const float px = std::pow(ax, p - 1.0f), py = std::pow(ay, p - 1.0f);
+    sx = p * px * (dx > 0.0f ? 1.0f : (dx < 0.0f ? -1.0f : 0.0f));
+    sy = p * py * (dy > 0.0f ? 1.0f : (dy < 0.0f ? -1.0f : 0.0f));
+    pw = px * ax + py * ay;
+}
+
+int rtt_spot_id_size(const float* rec, const int8_t* ids, int64_t m, const int32_t* group_of, int32_t K,
+                     const float* centres, float p, float* out, float*, void*) {
+    std::vector<double> acc(4 * (size_t)K, 0.0);
+    for (int64_t i = 0; i < m; ++i) {
+        const int g = group_of[(int)ids[i] + 128];
+        const float* r = rec + 4 * i;
+        if (g < 0 || r[3] == 0.0f) continue;
+        float pw, sx, sy;
+        spot_id_terms(r[0] - centres[2 * g], r[1] - centres[2 * g + 1], p, pw, sx, sy);
+        acc[4 * g] += (double)(r[3] * pw); acc[4 * g + 1] += (double)(r[3] * sx); acc[4 * g + 2] += (double)(r[3] * sy);
+    }
+    for (size_t k = 0; k < acc.size(); ++k) out[k] = (float)acc[k];
+    return 0;
+}
+
+int rtt_spot_id_size_bwd(const float* rec, const int8_t* ids, int64_t m, const int32_t* group_of, int32_t,
+                         const float* coef, float p, float* g_rec, void*) {
+    for (int64_t i = 0; i < m; ++i) {
+        const int g = group_of[(int)ids[i] + 128];
+        float* o = g_rec + 4 * i;
+        o[0] = o[1] = o[2] = o[3] = 0.0f;
+        if (g < 0) continue;
+        const float* r = rec + 4 * i;
+        const float* c = coef + 8 * g;
+        const float dx = r[0] - c[0], dy = r[1] - c[1];
+        float pw, sx, sy;
+        spot_id_terms(dx, dy, p, pw, sx, sy);
+        o[0] = c[2] * r[3] * (sx - c[3]);
+        o[1] = c[2] * r[3] * (sy - c[4]);
+        o[3] = c[2] * (pw - c[3] * dx - c[4] * dy - c[5]);
+    }
+    return 0;
+}
+
 }  // extern "C"

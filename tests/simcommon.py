@@ -89,3 +89,45 @@ class SourceGoalMixin:
                       self._pp(gl), self._pp(g), self._st())
         self._sync()
         return self._host(out), self._host(g)
+
+    # ---- per-id sensor moments ----
+    def spot_id(self, rec, ids, query, targets=None, p=2.0, g_out=None, repeat=1):
+        """(moments [K,4], sums [K,4], result [K], g_rec [M,4]) through rtt_spot_id_moments / _size / _size_bwd, with
+        the same host-side glue as raytracetorch_b200.ops._SpotSizePerId."""
+        rec_np = np.asarray(rec, np.float32)
+        K = len(query)
+        lut = np.full(256, -1, np.int32)
+        lut[np.asarray(query, np.int64) + 128] = np.arange(K, dtype=np.int32)
+        rec_d, ids_d, lut_d = self._a(rec_np), self._a(np.asarray(ids, np.int8)), self._a(lut)
+        mom, work = self._z((K, 4), np.float32), self._z(_cabi.SPOT_ID_WORK, np.float32)
+        for _ in range(repeat):          # the kernels must leave `work` reusable
+            self.lib.call("rtt_spot_id_moments", self._pp(rec_d), self._pp(ids_d), rec_np.shape[0], self._pp(lut_d), K,
+                          self._pp(mom), self._pp(work), self._st())
+        self._sync()
+        mom_h = self._host(mom)
+        W = mom_h[:, 0]
+        safe = np.where(W == 0, 1.0, W).astype(np.float32)
+        centres = (mom_h[:, 1:3] / safe[:, None]) if targets is None else np.asarray(targets, np.float32)
+        cen_d = self._a(np.ascontiguousarray(centres, np.float32))
+        s4 = self._z((K, 4), np.float32)
+        self.lib.call("rtt_spot_id_size", self._pp(rec_d), self._pp(ids_d), rec_np.shape[0], self._pp(lut_d), K,
+                      self._pp(cen_d), float(p), self._pp(s4), self._pp(work), self._st())
+        self._sync()
+        s4_h = self._host(s4)
+        result = s4_h[:, 0] / (2.0 * safe)
+        g_rec = None
+        if g_out is not None:
+            a = np.asarray(g_out, np.float32) / (2.0 * safe)
+            hit = (W != 0).astype(np.float32)
+            free = targets is None
+            bx = s4_h[:, 1] / safe * hit if free else np.zeros(K, np.float32)
+            by = s4_h[:, 2] / safe * hit if free else np.zeros(K, np.float32)
+            coef = np.stack([centres[:, 0], centres[:, 1], a, bx, by, s4_h[:, 0] / safe * hit, np.zeros(K), np.zeros(K)],
+                            1).astype(np.float32)
+            coef_d = self._a(np.ascontiguousarray(coef))
+            g = self._z(rec_np.shape, np.float32)
+            self.lib.call("rtt_spot_id_size_bwd", self._pp(rec_d), self._pp(ids_d), rec_np.shape[0], self._pp(lut_d), K,
+                          self._pp(coef_d), float(p), self._pp(g), self._st())
+            self._sync()
+            g_rec = self._host(g)
+        return mom_h, s4_h, result, g_rec

@@ -162,3 +162,116 @@ def test_spot_reductions_on_empty_and_all_dead_records(run_exact):
     np.testing.assert_array_equal(mom, np.zeros(4, np.float32))
     out3, g = run_exact.spot_size(dead, mom)
     assert out3[0] == 0 and np.all(g == 0) and np.all(np.isfinite(g))
+
+
+# ---------------------------------------------------------------------------------------------
+# per-id sensor moments: Sensor.getSpotSizeParallel_xy (elements/sensor.py:87-176)
+# ---------------------------------------------------------------------------------------------
+def _per_id_reference(rec, ids, query, targets, p):
+    """The reference's computation restated with torch index ops (differentiable): result [K] in query order."""
+    K = len(query)
+    lut = torch.full((256,), -1, dtype=torch.int64)
+    lut[torch.as_tensor(query) + 128] = torch.arange(K)
+    grp = lut[ids.long() + 128]
+    keep = grp >= 0
+    xy, w, grp = rec[keep, :2], rec[keep, 3], grp[keep]
+    W = torch.zeros(K, dtype=rec.dtype).index_add(0, grp, w)
+    safe = torch.where(W == 0, torch.ones_like(W), W)
+    if targets is None:
+        c = torch.zeros(K, 2, dtype=rec.dtype).index_add(0, grp, xy * w[:, None]) / safe[:, None]
+    else:
+        c = torch.as_tensor(targets, dtype=rec.dtype)
+    mom = (w[:, None] * (xy - c[grp]).abs() ** p).sum(1)
+    return torch.zeros(K, dtype=rec.dtype).index_add(0, grp, mom) / (2 * safe), W
+
+
+@pytest.mark.parametrize("p", [2.0, 3.0, 1.0])
+@pytest.mark.parametrize("targets", [None, [[0.1, -0.2], [0.0, 0.3], [1.0, 1.0], [0.0, 0.0]]])
+def test_spot_id_kernels_and_adjoint_match_torch_autograd(run_exact, targets, p):
+    """rtt_spot_id_moments / _size / _size_bwd against the same sums taken with torch index_add in float64 and its
+    autograd: ids in runs (bundles) and shuffled, an id that is not queried, a queried id without hits, dead records."""
+    g = torch.Generator().manual_seed(4)
+    m = 30_000
+    ids = torch.cat([torch.full((m // 3,), k, dtype=torch.int8) for k in (0, 1, 5)])
+    ids = torch.cat([ids, torch.randint(-3, 7, (5000,), generator=g, dtype=torch.int64).to(torch.int8)])
+    M = ids.numel()
+    rec = torch.randn(M, 4, generator=g, dtype=torch.float64) * 0.3
+    rec[:, 3] = torch.rand(M, generator=g, dtype=torch.float64)
+    rec[torch.rand(M, generator=g) < 0.3, 3] = 0.0                      # rays that never reached the sensor
+    rec = rec.float().double()                                           # the values the fp32 kernels see
+    query = [5, 0, 1, 100]                                               # 100: queried, never present
+    rec64 = rec.clone().requires_grad_(True)
+    want, W = _per_id_reference(rec64, ids, query, targets, p)
+    g_out = torch.tensor([1.0, -0.5, 2.0, 0.7], dtype=torch.float64)
+    (want * g_out).sum().backward()
+    mom, s4, got, g_rec = run_exact.spot_id(rec.float().numpy(), ids.numpy(), query, targets, p, g_out.numpy(), repeat=2)
+    np.testing.assert_allclose(mom[:, 0], W.detach().numpy(), rtol=2e-6)
+    assert mom[3, 0] == 0 and got[3] == 0
+    np.testing.assert_allclose(got, want.detach().numpy(), rtol=2e-5, atol=1e-9)
+    ref_g = rec64.grad.numpy().copy()
+    ref_g[:, 2] = 0.0
+    assert parity.grad_rel(g_rec, ref_g) < 2e-5
+    assert np.all(g_rec[~np.isin(ids.numpy(), query)] == 0)
+
+
+def test_sensor_per_id_spot_sizes_match_the_reference_fixture(rtt_ns):
+    """Sensor.getSpotSizeParallel_xy of this package (torch path: hit lists recorded on the CPU) against the
+    UNMODIFIED reference's results on the multi-bundle fixture (oracle/make_golden.py::gen_spot_id_case): spot sizes
+    in query order, intensity sums in sorted-id order, gradients to the lens curvatures through the oracle trace."""
+    import raytracetorch_b200 as rtt
+    import scenes
+    from oracle import trace_oracle as O
+    from oracle.make_golden import GOAL_RAYS
+    d = parity.load("extra_spot_id")
+    goals = parity.load("extra_goals")
+    query = d["query"].tolist()
+    for tag, tgt, p in (("centroid_p2", None, 2), ("target_p2", torch.from_numpy(d["targets"]), 2),
+                        ("centroid_p3", None, 3)):
+        els = scenes.c1_singlet(rtt_ns, physical=True, grads=True)
+        sensor = els[1]
+        tab = rtt.compile_elements(els)
+        for k in range(3):
+            pos, dr = torch.from_numpy(goals[f"bundle{k}_pos"]), torch.from_numpy(goals[f"bundle{k}_dir"])
+            o = O.trace_sequential(tab.f, tab.i_host, pos, dr, torch.ones(GOAL_RAYS))
+            mask, hl, w = o["sensor"][0]
+            sensor.record(hl, w, torch.full((int(mask.sum()),), k, dtype=torch.int8))
+        res, wsum = sensor.getSpotSizeParallel_xy(query, target_xy=tgt, norm_ord=p)
+        res.sum().backward()
+        np.testing.assert_allclose(res.detach().numpy(), d[f"{tag}_result"], rtol=2e-4)
+        np.testing.assert_allclose(wsum.detach().numpy(), d[f"{tag}_intensity_sum"], rtol=1e-6)
+        for k in (0, 1):
+            assert parity.grad_rel(els[0].shape.surfaces[k].c.grad.numpy(), d[f"{tag}_g_c{k}"]) < parity.TOL_GRAD, (tag, k)
+
+
+@pytest.mark.gpu
+def test_sensor_per_id_spot_sizes_fused_path_matches_the_reference_fixture(rtt_ns):
+    """The same fixture through the product path: three bundles traced by the fused CUDA kernel, per-id spot sizes by
+    rtt_spot_id_* on the dense records (no hit lists), gradients through the hand-written adjoints."""
+    import raytracetorch_b200 as rtt
+    import scenes
+    d = parity.load("extra_spot_id")
+    goals = parity.load("extra_goals")
+    query = d["query"].tolist()
+    dev = torch.device("cuda", 0)
+    for tag, tgt, p in (("centroid_p2", None, 2), ("target_p2", torch.from_numpy(d["targets"]), 2),
+                        ("centroid_p3", None, 3)):
+        els = scenes.c1_singlet(rtt_ns, physical=True, grads=True)
+        sensor = els[1]
+        scene = rtt.scene.SequentialScene(els).to(dev)
+        for k in range(3):
+            pos, dr = torch.from_numpy(goals[f"bundle{k}_pos"]).to(dev), torch.from_numpy(goals[f"bundle{k}_dir"]).to(dev)
+            n = pos.shape[0]
+            rays = rtt.rays.Rays._wrap(pos=pos, dir=dr, intensity=torch.ones(n, device=dev),
+                                       id=torch.full((n,), k, dtype=torch.int8, device=dev),
+                                       wavelength=torch.zeros(n, device=dev))
+            scene.simulate(rays)
+        assert sensor._dense_records() is not None                   # the fused path is the one that runs
+        res, wsum = sensor.getSpotSizeParallel_xy(query, target_xy=tgt, norm_ord=p)
+        res.sum().backward()
+        np.testing.assert_allclose(res.detach().cpu().numpy(), d[f"{tag}_result"], rtol=2e-4)
+        np.testing.assert_allclose(wsum.detach().cpu().numpy(), d[f"{tag}_intensity_sum"], rtol=1e-6)
+        for k in (0, 1):
+            g = els[0].shape.surfaces[k].c.grad.cpu().numpy()
+            assert parity.grad_rel(g, d[f"{tag}_g_c{k}"]) < parity.TOL_GRAD, (tag, k, g, d[f"{tag}_g_c{k}"])
+        locs, w, ids = sensor.getHitsTensors()                        # the lists are still available afterwards
+        assert locs.shape[0] == int(d[f"{tag}_intensity_sum"].sum())
