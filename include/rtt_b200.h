@@ -304,6 +304,17 @@ int rtt_spot_id_size_bwd(const float* rec, const int8_t* ids, int64_t m, const i
  * `scratch`: one device float (never written in practice). */
 int64_t rtt_probe_fp32(int32_t iters, float* scratch, void* stream);
 
+/* Renderer.render_3d (render/camera.py:191-257): per ray the nearest hit over all table rows (the caller passes the
+ * table of the renderable, non-aperture elements), the winner's global normal (Shape.forward, geom/shape.py:61-87) and
+ * the colour clamp(base_rgb[row] * (0.3 + 0.7 |n . light|), 0, 1); rays without a hit get `background`.
+ *   in_pos / in_dir : [n,3] pixel rays, or NULL with `source` = a CAMERA rtt_source_t (rays generated in the kernel)
+ *   base_rgb        : DEVICE [n_rows,3]; light_dir, background: HOST float[3] (light_dir normalised by the caller)
+ *   out_rgb         : [n,3];  out_row: [n] uint8 winning row, 255 = background, or NULL
+ * Always runs the EXACT arithmetic (the nearest-hit decision is the non-sequential search's, see rtt_trace_nonseq_fwd). */
+int rtt_render_shade(const float* in_pos, const float* in_dir, const rtt_source_t* source, const rtt_table_t* table,
+                     const float* base_rgb, const float* light_dir, const float* background,
+                     float* out_rgb, uint8_t* out_row, int64_t n, int32_t mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

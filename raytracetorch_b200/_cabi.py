@@ -80,6 +80,8 @@ _SIGS = {
     "rtt_spot_moments_bwd": [_P, ct.c_int64, ct.c_int32, _P, _P, _P],
     "rtt_spot_size_fwd": [_P, ct.c_int64, _P, _P, _P, _P, _P],
     "rtt_spot_size_bwd": [_P, ct.c_int64, _P, _P, _P, _P, _P, _P],
+    "rtt_render_shade": [_P, _P, _SRC, ct.POINTER(TableReq), _P, ct.POINTER(ct.c_float), ct.POINTER(ct.c_float), _P, _P,
+                         ct.c_int64, ct.c_int32, _P],
     "rtt_spot_id_moments": [_P, _P, ct.c_int64, _P, ct.c_int32, _P, _P, _P],
     "rtt_spot_id_size": [_P, _P, ct.c_int64, _P, ct.c_int32, _P, ct.c_float, _P, _P, _P],
     "rtt_spot_id_size_bwd": [_P, _P, ct.c_int64, _P, ct.c_int32, _P, ct.c_float, _P, _P],

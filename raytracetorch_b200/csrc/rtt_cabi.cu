@@ -387,4 +387,22 @@ int rtt_surface_step_bwd(const float* in_pos, const float* in_dir, const float* 
 #undef RTT_BODY
 }
 
+int rtt_render_shade(const float* in_pos, const float* in_dir, const rtt_source_t* source, const rtt_table_t* table,
+                     const float* base_rgb, const float* light_dir, const float* background,
+                     float* out_rgb, uint8_t* out_row, int64_t n, int32_t, void* stream) {
+    if (int e = check_table(table)) return e;
+    if (n == 0) return RTT_OK;
+    if (n < 0 || !base_rgb || !light_dir || !background || !out_rgb) return RTT_E_ARG;
+    if (!source && (!in_pos || !in_dir)) return RTT_E_ARG;
+    if (!have_device()) return RTT_E_NO_DEVICE;
+    rtt::exact::RenderArgs a;                          /* nearest-hit decisions: the reference's rounding (EXACT) */
+    if (int e = fill_source(a.src, source)) return e;
+    a.pos = in_pos; a.dir = in_dir;
+    a.tab = make_table<rtt::exact::TableDev>(table);
+    a.base_rgb = base_rgb;
+    for (int k = 0; k < 3; ++k) { a.light[k] = light_dir[k]; a.bg[k] = background[k]; }
+    a.rgb = out_rgb; a.win = out_row; a.n = n;
+    return finish(rtt::exact::launch_render_exact(a, (cudaStream_t)stream));
+}
+
 }  // extern "C"

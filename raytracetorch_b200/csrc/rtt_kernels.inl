@@ -1409,6 +1409,68 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_surface_step_bwd)(const _
     flush_block_grads(acc, S, a.g_table, acc_lut, L, a.g_lut);
 }
 
+
+// ============================================================================================
+// Renderer.render_3d (render/camera.py:191-257): nearest hit + normal + shading, one launch
+// ============================================================================================
+// The reference builds the [N, S] distance matrix of the renderable elements, takes the row-wise minimum, then — per
+// winning (element, surface) — gathers the pixel rays, re-runs the surface's forward for the normal and shades
+// (0.3 ambient + 0.7 |n . light|) x base colour (render/camera.py:259-301).  Here every pixel ray does its search,
+// recomputes the winner's geometry and writes its colour in the same thread; the pinhole camera's rays can be
+// generated in the kernel (rtt_source_t, kind CAMERA), so a render reads no ray input at all.
+__global__ void __launch_bounds__(kThreads) RTT_NAME(k_render_shade)(const __grid_constant__ RenderArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = a.tab.S;
+    SmemTable T = carve(smem_raw, S, 0);
+    TableDev tb = a.tab; tb.L = 0;
+    stage_table(tb, T);
+    for (int r = threadIdx.x; r < S; r += blockDim.x) {                 // rows of one element share the element-frame ray
+        bool same = r > 0 && T.rows[r].i[RTT_I_SHAPE] != RTT_SHAPE_NONE && T.rows[r - 1].i[RTT_I_SHAPE] != RTT_SHAPE_NONE;
+        for (int e = RTT_F_RE; same && e < RTT_F_TE + 3; ++e) same = T.rows[r].f[e] == T.rows[r - 1].f[e];
+        T.rows[r].f[D_SAME_ELEM] = same ? 1.0f : 0.0f;
+    }
+    __syncthreads();
+    const V3 light = v3(a.light[0], a.light[1], a.light[2]);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const SourceKey skey = fetch_key(a);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        V3 p, d;
+        if (a.src.kind >= 0) source_ray(a.src, skey, i, p, d);
+        else { p = load3(a.pos, i); d = load3(a.dir, i); }
+        float best = rtt_inf();
+        int win = -1;
+        bool poisoned = !finite_ray(p, d);
+        Frames Fs;
+        Fs.pe = Fs.de = Fs.den = Fs.o = Fs.dd = v3(0.0f, 0.0f, 0.0f); Fs.len = 0.0f;
+        for (int r = 0; r < S && !poisoned; ++r) {                      // min over rows, NaN anywhere => no hit (:236-237)
+            switch (T.rows[r].i[DI_OPCODE]) {                           // warp-uniform
+#define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR)                                            \
+                case OP: nonseq_probe<KStatic<SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR>>(T.rows, r, p, d, best, win, poisoned, Fs); break;
+                RTT_ROW_SPECS(RTT_X)
+#undef RTT_X
+                default: nonseq_probe<KDyn>(T.rows, r, p, d, best, win, poisoned, Fs); break;
+            }
+        }
+        V3 rgb = v3(a.bg[0], a.bg[1], a.bg[2]);
+        if (!poisoned && win >= 0) {
+            Frames F; Roots q; float t; int which;
+            intersect<false>(T.rows, win, p, d, F, q, t, which);        // Shape.forward of the winner (:249)
+            const RowDev& R = T.rows[win];
+            float nlen;
+            const V3 n = normal_global(R, normal_local(R, along(F.o, t, F.dd), &nlen));
+            const float shade = 0.3f + 0.7f * fabsf(dot(n, light));     // :296-299
+            const float* b = a.base_rgb + 3 * win;
+            rgb = v3(fminf(fmaxf(b[0] * shade, 0.0f), 1.0f), fminf(fmaxf(b[1] * shade, 0.0f), 1.0f),
+                     fminf(fmaxf(b[2] * shade, 0.0f), 1.0f));
+        } else {
+            win = 255;
+            rgb = v3(fminf(fmaxf(rgb.x, 0.0f), 1.0f), fminf(fmaxf(rgb.y, 0.0f), 1.0f), fminf(fmaxf(rgb.z, 0.0f), 1.0f));
+        }
+        store3(a.rgb, i, rgb);
+        if (a.win) a.win[i] = (unsigned char)win;
+    }
+}
+
 // ============================================================================================
 // Bundle.sample (rays/bundle.py:30-37): materialise the rays of a source
 // ============================================================================================
@@ -1589,6 +1651,12 @@ cudaError_t RTT_NAME(launch_step_fwd)(const StepFwdArgs& a, cudaStream_t st) {
 cudaError_t RTT_NAME(launch_step_bwd)(const StepBwdArgs& a, cudaStream_t st) {
     if (cudaError_t e = allow_smem(RTT_NAME(k_surface_step_bwd), bwd_smem(a.tab.S, a.tab.L))) return e;
     RTT_NAME(k_surface_step_bwd)<<<grid_for(a.n, 4), kThreads, bwd_smem(a.tab.S, a.tab.L), st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t RTT_NAME(launch_render)(const RenderArgs& a, cudaStream_t st) {
+    if (cudaError_t e = allow_smem(RTT_NAME(k_render_shade), smem_table_bytes(a.tab.S, 0))) return e;
+    RTT_NAME(k_render_shade)<<<grid_for(a.n, 8), kThreads, smem_table_bytes(a.tab.S, 0), st>>>(a);
     return cudaGetLastError();
 }
 

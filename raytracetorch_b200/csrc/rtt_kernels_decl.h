@@ -126,6 +126,18 @@ struct StepBwdArgs {
     long long n;
 };
 
+struct RenderArgs {                 // Renderer.render_3d: nearest hit of every ray + Lambert shading
+    SourceDev src;
+    const float *pos, *dir;
+    TableDev tab;
+    const float* base_rgb;          // [S,3] base colour of every table row
+    float light[3], bg[3];
+    float* rgb;                     // [n,3]
+    unsigned char* win;             // [n] winning row, 255 = background (optional)
+    long long n;
+};
+
+cudaError_t RTT_NAME(launch_render)(const RenderArgs& a, cudaStream_t st);
 cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st);
 cudaError_t RTT_NAME(launch_seq_bwd)(const SeqBwdArgs& a, cudaStream_t st);
 cudaError_t RTT_NAME(launch_nonseq_fwd)(const NonseqFwdArgs& a, cudaStream_t st);

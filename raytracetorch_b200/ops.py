@@ -792,6 +792,32 @@ def spot_size(rec: torch.Tensor, target_xy: Optional[torch.Tensor] = None) -> to
     """Differentiable SpotSizeLoss term of ONE bundle from its sensor records rec [..., 4]."""
     return spot_size_active(rec, target_xy)[0]
 
+@torch.library.custom_op("rtt_b200::render_shade", mutates_args=())
+def _render_shade(pos: Optional[torch.Tensor], dir: Optional[torch.Tensor], src_cfg: List[float],
+                  pose: Optional[torch.Tensor], state: Optional[torch.Tensor], n: int,
+                  table_f: torch.Tensor, table_i: torch.Tensor, base_rgb: torch.Tensor,
+                  light: List[float], background: List[float]) -> List[torch.Tensor]:
+    """Renderer.render_3d in one launch (rtt_render_shade) -> [rgb [n,3] f32, winning row [n] u8 (255 = background)];
+    rays from (pos, dir) or — pose/state given — generated in the kernel from the camera source ``src_cfg``."""
+    _need_cuda(table_f, table_i, base_rgb)
+    dev = table_f.device
+    rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    win = torch.empty(n, dtype=torch.uint8, device=dev)
+    src = _source_req(src_cfg, pose, state) if pose is not None else None
+    req = _table_req(table_f, table_i, None, None)
+    la, bg = (ct.c_float * 3)(*light), (ct.c_float * 3)(*background)
+    with torch.cuda.device(dev):
+        _cabi.load().call("rtt_render_shade", _ptr(pos), _ptr(dir), ct.byref(src) if src is not None else None,
+                          ct.byref(req), base_rgb.data_ptr(), la, bg, rgb.data_ptr(), win.data_ptr(), n, MODE_EXACT,
+                          _stream(table_f))
+    return [rgb, win]
+
+
+@_render_shade.register_fake
+def _(pos, dir, src_cfg, pose, state, n, table_f, table_i, base_rgb, light, background):
+    return [table_f.new_empty((n, 3)), table_f.new_empty(n, dtype=torch.uint8)]
+
+
 # ---- per-id sensor moments (rtt_goals.cu k_spot_id_*) -------------------------------------------------------------
 _SPOT_ID_WORK = {}
 

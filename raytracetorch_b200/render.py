@@ -115,28 +115,29 @@ class Renderer:
 
     def render_3d(self, camera) -> torch.Tensor:
         """[H, W, 3] image on the CPU: nearest hit of every pixel ray over the non-aperture elements, base colour by
-        surface physics, 0.3 ambient + 0.7 |n . light| shading, background elsewhere."""
+        surface physics, 0.3 ambient + 0.7 |n . light| shading, background elsewhere (render/camera.py:191-257).
+
+        ONE kernel launch (rtt_render_shade): the search over all rows, the winner's normal and the shading run in
+        the thread that owns the pixel ray; a CUDA camera's rays are generated in the kernel (no ray tensors at all)."""
         from . import ops
         from .table import compile_elements
         self.scene._build_index_maps()
-        rays = camera.generate_rays()
-        n = rays.batch_size[0]
-        dev = rays.pos.device
-        colors = self.bg_color.to(dev).expand(n, 3).clone()
+        n = camera.width * camera.height
+        dev = self.bg_color.device
         renderable = [el for el in self.scene.elements if not _is_aperture(el)]
         if not renderable:
-            return colors.reshape(camera.height, camera.width, 3).cpu()
+            return self.bg_color.expand(n, 3).clone().reshape(camera.height, camera.width, 3).cpu()
         with torch.no_grad():
             table = compile_elements(renderable, dispersion=getattr(self.scene, "dispersion", None))
-            out = ops.trace_nonsequential(table, rays.pos, rays.dir, torch.ones_like(rays.intensity), 1,
-                                          want_record=False, sensor_cfg=[])
-            win = out["hit_seq"][:, 0].long()
-            light = self.light_dir.to(dev)
-            rows_of = [(el, j) for el in renderable for j in range(len(el.shape))]
-            for r in torch.unique(win[win != 255]).tolist():
-                sel = win == r
-                el, j = rows_of[r]
-                normal = ops.step_row(table, rays.pos[sel], rays.dir[sel], r, mode=ops.MODE_EXACT)[5]
-                shade = 0.3 + 0.7 * torch.sum(normal * light, dim=1).abs()
-                colors[sel] = _base_color(el.surface_functions[j]).to(dev) * shade.unsqueeze(1)
-        return torch.clamp(colors.reshape(camera.height, camera.width, 3), 0.0, 1.0).cpu()
+            base = torch.stack([_base_color(el.surface_functions[j]) for el in renderable
+                                for j in range(len(el.shape))]).to(device=dev, dtype=torch.float32).contiguous()
+            light, bg = self.light_dir.cpu().tolist(), self.bg_color.cpu().tolist()
+            if torch.device(camera.device).type == "cuda":
+                src = camera.generate_source_rays(samples=1)
+                rgb, self.last_rows = torch.ops.rtt_b200.render_shade(
+                    None, None, ops.source_cfg_of(src), src.pose, src.state, n, table.f, table.i, base, light, bg)
+            else:
+                rays = camera.generate_rays().to(dev)
+                rgb, self.last_rows = torch.ops.rtt_b200.render_shade(
+                    rays.pos.contiguous(), rays.dir.contiguous(), [], None, None, n, table.f, table.i, base, light, bg)
+        return rgb.reshape(camera.height, camera.width, 3).cpu()

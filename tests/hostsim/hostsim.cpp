@@ -654,4 +654,41 @@ int rtt_spot_id_size_bwd(const float* rec, const int8_t* ids, int64_t m, const i
     return 0;
 }
 
+// Renderer.render_3d: host mirror of k_render_shade (nearest hit, winner's normal, Lambert shading)
+int rtt_render_shade(const float* in_pos, const float* in_dir, const rtt_source_t* source, const rtt_table_t* table,
+                     const float* base_rgb, const float* light_dir, const float* background,
+                     float* out_rgb, uint8_t* out_row, int64_t n, int32_t, void*) {
+    rtt_table_t tb = *table; tb.n_lut = 0;
+    const HostTable T = stage(&tb);
+    const V3 light = v3(light_dir[0], light_dir[1], light_dir[2]);
+    auto clamp01 = [](float v) { return std::fmin(std::fmax(v, 0.0f), 1.0f); };
+    for (int64_t i = 0; i < n; ++i) {
+        const HostRay ray = fetch_ray(source, in_pos, in_dir, nullptr, nullptr, false, i);
+        float best = rtt_inf();
+        int win = -1;
+        bool poisoned = !finite_ray(ray.p, ray.d);
+        for (int r = 0; r < T.S && !poisoned; ++r) {
+            Frames F; Roots q; float t; int which;
+            const bool valid = intersect<true>(T.rows.data(), r, ray.p, ray.d, F, q, t, which);
+            if (T.rows[r].i[RTT_I_SHAPE] == RTT_SHAPE_NONE && is_nan(t)) poisoned = true;
+            if (valid && t < best) { best = t; win = r; }
+        }
+        V3 rgb = v3(background[0], background[1], background[2]);
+        if (!poisoned && win >= 0) {
+            Frames F; Roots q; float t; int which;
+            intersect<false>(T.rows.data(), win, ray.p, ray.d, F, q, t, which);
+            const RowDev& R = T.rows[win];
+            float nlen;
+            const V3 nn = normal_global(R, normal_local(R, along(F.o, t, F.dd), &nlen));
+            const float shade = 0.3f + 0.7f * std::fabs(dot(nn, light));
+            rgb = v3(base_rgb[3 * win] * shade, base_rgb[3 * win + 1] * shade, base_rgb[3 * win + 2] * shade);
+        } else {
+            win = 255;
+        }
+        out_rgb[3 * i] = clamp01(rgb.x); out_rgb[3 * i + 1] = clamp01(rgb.y); out_rgb[3 * i + 2] = clamp01(rgb.z);
+        if (out_row) out_row[i] = (uint8_t)win;
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -194,10 +194,13 @@ def self_hit_free(d, tf, ti, nbounces=None):
 # Fraction of each non-sequential fixture's rays that `self_hit_free` keeps, measured once on the committed
 # fixtures (oracle sweep, no kernel involved).  The tests pin these so that a change which silently drops rays
 # from the comparison fails instead of passing on a smaller subset.
-CLEAN_FRACTION = {"c5_nonsequential": 0.3277, "sim_benchmark": 0.9223, "x2_nonsequential": 0.2240}
+CLEAN_FRACTION = {"c5_nonsequential": 0.3277, "sim_benchmark": 0.9223, "x2_nonsequential": 0.2240,
+                  "x5_light_pipe": 0.1093}
+# ... of which the reference's own fp32 and fp64 runs also agree on the whole hit sequence
+STABLE_CLEAN_FRACTION = dict(CLEAN_FRACTION, x5_light_pipe=0.1073)
 
 
-def assert_clean_fraction(name, clean):
-    want = CLEAN_FRACTION[name]
+def assert_clean_fraction(name, clean, stable=False):
+    want = (STABLE_CLEAN_FRACTION if stable else CLEAN_FRACTION)[name]
     got = float(np.mean(clean))
     assert abs(got - want) <= 0.002, f"{name}: self-hit-free fraction {got:.4f}, pinned {want:.4f}"

@@ -75,6 +75,14 @@ def c5_nonsequential(ns):
     return [mirror, lens, box, stop, sensor]
 
 
+# ---- light pipe: the four mirrored side planes of a Box4Side (geom/shape.py:213-276), tilted, + sensor ----------
+def x5_light_pipe(ns):
+    E, G, P = ns.elements, ns.geom, ns.phys
+    pipe = _adhoc(ns, G.Box4Side(6.0, 4.0, transform=_T(ns, 20.0, x=0.3, rot=[0.02, -0.03, 0.1])), P.Reflect)
+    sensor = E.Sensor(G.Disk(12.0, transform=_T(ns, 70.0)))
+    return [pipe, sensor]
+
+
 # ---- benchmark scene of the reference (benchmarks/sim_benchmark.py:56-88) ---------------
 def sim_benchmark_scene(ns):
     E, G = ns.elements, ns.geom
@@ -189,6 +197,7 @@ CASES = {
     "c5_nonsequential": (c5_nonsequential, {}, "nonseq", ("coll", 10.0, -5.0, None)),
     "sim_benchmark": (sim_benchmark_scene, {}, "nonseq", ("coll", 4.0, 0.0, None)),
     "x2_nonsequential": (x2_tilted_lenses, {}, "nonseq", ("coll", 10.0, -12.0, [0.02, 0.03, 0.0])),
+    "x5_light_pipe": (x5_light_pipe, {}, "nonseq", ("point", 0.25, (0.2, -0.1, 5.0))),
 }
 
 

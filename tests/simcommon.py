@@ -131,3 +131,16 @@ class SourceGoalMixin:
             self._sync()
             g_rec = self._host(g)
         return mom_h, s4_h, result, g_rec
+
+    # ---- Renderer.render_3d in one call ----
+    def render_shade(self, tf, ti, pos, dir_, base_rgb, light, background):
+        req, hold = self._table(tf, ti, None, None)
+        n = pos.shape[0]
+        pos_d, dir_d = self._a(np.asarray(pos, np.float32)), self._a(np.asarray(dir_, np.float32))
+        base_d = self._a(np.ascontiguousarray(base_rgb, np.float32))
+        rgb, row = self._z((n, 3), np.float32), self._z(n, np.uint8)
+        la, bg = (ct.c_float * 3)(*map(float, light)), (ct.c_float * 3)(*map(float, background))
+        self.lib.call("rtt_render_shade", self._pp(pos_d), self._pp(dir_d), None, ct.byref(req), self._pp(base_d), la, bg,
+                      self._pp(rgb), self._pp(row), n, 1, self._st())
+        self._sync()
+        return self._host(rgb), self._host(row)

@@ -362,3 +362,28 @@ def test_source_origin_gradient_of_an_ideal_lens_is_the_axial_magnification(rtt_
     assert abs(float(zi_mean.detach()) - 150.0) < 0.5
     g = tr.trans.grad.cpu().numpy()
     assert abs(g[2] - 0.25) < 2e-3, g
+
+
+def test_render_shade_entry_matches_the_reference_image(run_exact, rtt_ns):
+    """rtt_render_shade (nearest hit + normal + shading in one call) against the reference's own render_3d image
+    (fixture extra_render3d), on both back-ends: same winner surface, normal and colour per pixel; pixels whose
+    nearest hit is decided at a silhouette edge may differ."""
+    import raytracetorch_b200 as rtt
+    import scenes
+    from raytracetorch_b200 import render as RD
+    ns = types.SimpleNamespace(elements=rtt.elements, geom=rtt.geom, phys=rtt.phys, rays=rtt.rays, scene=rtt.scene,
+                               render=rtt.render)
+    scene, cam = scenes.render_setup(ns, device="cpu")
+    rays = cam.generate_rays()
+    renderable = [el for el in scene.elements if not RD._is_aperture(el)]
+    tab = rtt.compile_elements(renderable)
+    base = torch.stack([RD._base_color(el.surface_functions[j]) for el in renderable for j in range(len(el.shape))])
+    rd = RD.Renderer(scene)
+    rgb, row = run_exact.render_shade(tab.f.detach().numpy(), tab.i.numpy(), rays.pos.numpy(), rays.dir.numpy(),
+                                      base.numpy(), rd.light_dir.tolist(), rd.bg_color.tolist())
+    ref = parity.load("extra_render3d")["image"]
+    img = rgb.reshape(ref.shape)
+    diff = np.abs(img - ref).max(axis=2)
+    assert (diff > 1e-4).mean() <= 0.005, f"{(diff > 1e-4).sum()} pixels differ"
+    hit = row.reshape(ref.shape[:2]) != 255
+    assert hit.sum() > 800 and np.array_equal(hit, np.abs(ref - 1.0).sum(-1) > 0) or (hit != (np.abs(ref - 1.0).sum(-1) > 0)).mean() < 0.005
