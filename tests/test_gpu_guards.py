@@ -1,0 +1,92 @@
+"""Out-of-bounds guard tests (compute-sanitizer is closed on this GPU pool): every output buffer of a launch is carved
+out of one arena between guard zones filled with a sentinel; after the launch the guard zones must be untouched and the
+results must equal an un-guarded launch.  Sizes straddle the 512-ray tile of the streaming kernel (bulk-async copies of
+whole tiles, cooperative copy of the ragged last one); an unaligned carve makes the library fall back to plain stores."""
+import ctypes as ct
+
+import numpy as np
+import pytest
+import torch
+
+import parity
+
+pytestmark = pytest.mark.gpu
+GUARD = 4096
+SENTINEL = 0xA5
+
+
+class Arena:
+    def __init__(self, nbytes_list, misalign=0):
+        self.spans = []
+        off = GUARD + misalign
+        for nb in nbytes_list:
+            self.spans.append((off, nb))
+            off += (nb + 15) // 16 * 16 + GUARD + misalign
+        self.buf = torch.full((off + GUARD,), SENTINEL, dtype=torch.uint8, device="cuda")
+
+    def view(self, k, dtype):
+        off, nb = self.spans[k]
+        return self.buf[off:off + nb].view(dtype)
+
+    def guards_intact(self):
+        keep = torch.ones(self.buf.numel(), dtype=torch.bool, device="cuda")
+        for off, nb in self.spans:
+            keep[off:off + nb] = False
+        return bool((self.buf[keep] == SENTINEL).all())
+
+
+@pytest.mark.parametrize("misalign", [0, 4])
+@pytest.mark.parametrize("tune", [16, 18, 3, 5, 9])
+@pytest.mark.parametrize("n", [1, 511, 512, 513, 1536, 20011])
+def test_sequential_forward_stays_inside_its_output_buffers(n, tune, misalign):
+    from raytracetorch_b200 import _cabi
+    from gpusim import GpuSim, _dev, _p
+    d = parity.load("c2_cylindrical")
+    sim = GpuSim(tune << 16)
+    reps = (n + d["in_pos"].shape[0] - 1) // d["in_pos"].shape[0]
+    pos = np.tile(d["in_pos"], (reps, 1))[:n]
+    dr = np.tile(d["in_dir"], (reps, 1))[:n]
+    inten = np.tile(d["in_intensity"], reps)[:n]
+    want = sim.trace_seq(d["table_f"], d["table_i"], pos, dr, inten)
+    arena = Arena([12 * n, 12 * n, 4 * n, 8 * n], misalign=misalign)
+    op, od, oi, mask = (arena.view(k, t) for k, t in enumerate((torch.float32, torch.float32, torch.float32, torch.int64)))
+    req, hold = sim._table(d["table_f"], d["table_i"], None, None)
+    p_, d_, i_ = _dev(pos), _dev(dr), _dev(inten)
+    sim.lib.call("rtt_trace_seq_fwd", _p(p_), _p(d_), _p(i_), 0, None, op.data_ptr(), od.data_ptr(), oi.data_ptr(),
+                 mask.data_ptr(), ct.byref(req), None, 0, n, sim.mode, sim._stream())
+    torch.cuda.synchronize()
+    assert arena.guards_intact(), "a kernel wrote outside its output buffers"
+    np.testing.assert_array_equal(oi.cpu().numpy(), want["intensity"])
+    np.testing.assert_array_equal(op.cpu().numpy().reshape(n, 3), want["pos"])
+    np.testing.assert_array_equal(mask.cpu().numpy().view(np.uint64), want["hitmask"])
+
+
+@pytest.mark.parametrize("n", [1, 4095, 4097, 70001])
+def test_sequential_adjoint_stays_inside_its_output_buffers(n):
+    from raytracetorch_b200 import codes as C
+    from gpusim import GpuSim, _dev, _p
+    d = parity.load("grad_c2_cylindrical")
+    sim = GpuSim(0)
+    reps = (n + d["in_pos"].shape[0] - 1) // d["in_pos"].shape[0]
+    pos = np.tile(d["in_pos"], (reps, 1))[:n]
+    dr = np.tile(d["in_dir"], (reps, 1))[:n]
+    inten = np.tile(d["in_intensity"], reps)[:n]
+    fwd = sim.trace_seq(d["table_f"], d["table_i"], pos, dr, inten)
+    gp, gd, gi = parity.golden_loss_grads(fwd["pos"], fwd["dir"], fwd["intensity"])
+    want = sim.trace_seq_bwd(d["table_f"], d["table_i"], pos, dr, inten, fwd["hitmask"], gp, gd, gi)
+    S = d["table_f"].shape[0]
+    arena = Arena([12 * n, 12 * n, 4 * n, 4 * S * C.ROW_G])
+    o = [arena.view(k, torch.float32) for k in range(4)]
+    for t in o:
+        t.zero_()
+    req, hold = sim._table(d["table_f"], d["table_i"], None, None)
+    args = [_dev(x) for x in (pos, dr, inten)]
+    mask = _dev(np.asarray(fwd["hitmask"]).view(np.int64), torch.int64)
+    g = [_dev(x) for x in (gp, gd, gi)]
+    sim.lib.call("rtt_trace_seq_bwd", _p(args[0]), _p(args[1]), _p(args[2]), 0, None, _p(mask), _p(g[0]), _p(g[1]),
+                 _p(g[2]), None, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), o[3].data_ptr(), 0, ct.byref(req), 0, n,
+                 sim.mode, sim._stream())
+    torch.cuda.synchronize()
+    assert arena.guards_intact(), "the adjoint wrote outside its output buffers"
+    assert parity.grad_rel(o[0].cpu().numpy().reshape(n, 3), want["g_pos"]) < 1e-6
+    assert parity.grad_rel(o[3].cpu().numpy().reshape(S, C.ROW_G), want["g_table"]) < 1e-4
