@@ -580,6 +580,25 @@ def run_gpu_arm(args):
         kt.append(a.elapsed_time(b))
         del images
     k_ms = float(np.median(kt))
+    nonseq_fast = None
+    if w["nonseq"]:
+        # the same launch with the opt-in FAST arithmetic (RTT_MODE_NONSEQ_FAST): not the parity configuration — rays
+        # within rounding of a self-intersection take other paths than the reference's — reported beside the line
+        ft = []
+        fmode = rtt.ops.MODE_FAST | rtt.ops.MODE_NONSEQ_FAST
+        for _ in range(max(3, args.steps // 2)):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            o_f = torch.ops.rtt_b200.trace_nonseq_fwd(pos, dirs, inten, wav, table.f, table.i, table.lut,
+                                                      table.lut_wavelengths, cfg, False, w["nbounces"], fmode)
+            b.record()
+            torch.cuda.synchronize()
+            ft.append(a.elapsed_time(b))
+        f_ms = float(np.median(ft))
+        f_tests = S * min(float(o_f[4].float().mean().item()) + 1.0, w["nbounces"])
+        nonseq_fast = dict(kernel_ms=f_ms, value=n * f_tests / (f_ms / 1e3), unit=UNIT, tests_per_ray=f_tests,
+                           mode="FAST arithmetic, explicit opt-in (RTT_MODE_NONSEQ_FAST); parity is defined for EXACT")
+        del o_f
     clocks = sampler.stop()          # sampled under load: warm-up + timed steps + the per-launch timing above
     peaks = {}
     try:
@@ -941,6 +960,8 @@ def run_gpu_arm(args):
             line["cpu_baseline"] = cpu
         if config4:
             line["config4"] = config4
+        if nonseq_fast:
+            line["nonseq_fast"] = nonseq_fast
         emit(line)
     if world > 1:
         tdist.barrier()

@@ -90,6 +90,8 @@ enum { RTT_MODE_SCALAR_GRADS = 0x100, RTT_MODE_ARITH_MASK = 0xff };
  *     18 = packed pairs with plain global loads / stores
  *   rtt_trace_seq_bwd: 2 / 3 / 4 = resident blocks per SM the adjoint build is compiled for */
 enum { RTT_MODE_TUNE_SHIFT = 16, RTT_MODE_TUNE_MASK = 0xff0000 };
+/* rtt_trace_nonseq_fwd / _bwd only: run the FAST arithmetic (see there); every other entry ignores the bit. */
+enum { RTT_MODE_NONSEQ_FAST = 0x400 };
 
 /* Sensor image request for one sensor slot.  Bin rule (restating the fixed-range
  * histogram of gui/workbench.py:615-624 in fp32):
@@ -199,10 +201,12 @@ int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float* in_
  *   n_hits      : [n] uint8 number of executed bounces (may be NULL)
  * Sensors: every sensor interaction is accumulated into the image; `record` keeps the first
  * `record_hits` interactions per ray and `count` their total number.
- * `mode` is accepted for symmetry but ignored: the non-sequential trace (and its adjoint) always
- * run the EXACT arithmetic.  Whether a ray re-hits the surface it is leaving is decided by the
- * reference's t > 1e-6 rule at the fp32 ulp of scene-scale coordinates, i.e. by its exact rounding
- * sequence; FMA contraction or approximate division change hit sequences on ~20 % of the rays. */
+ * The arithmetic bits of `mode` are ignored: the non-sequential trace (and its adjoint) run the EXACT arithmetic.
+ * Whether a ray re-hits the surface it is leaving is decided by the reference's t > 1e-6 rule at the fp32 ulp of
+ * scene-scale coordinates, i.e. by its exact rounding sequence; FMA contraction or approximate division change hit
+ * sequences on ~20 % of the rays.  A caller who accepts that noise (the hit sequences of rays that do NOT depend on
+ * the threshold are unchanged, see tests) opts in to the FAST arithmetic (MUFU division / square root, FMA
+ * contraction: ~1.4x the throughput) with RTT_MODE_NONSEQ_FAST; trace and adjoint must use the same setting. */
 int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* in_intensity,
                          const float* in_wavelength, const rtt_source_t* source,
                          float* out_pos, float* out_dir, float* out_intensity,

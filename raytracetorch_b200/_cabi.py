@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "librtt_b200.so")
 
 MODE_FAST, MODE_EXACT = 0, 1
 MODE_SCALAR_GRADS = 0x100   # hint for rtt_trace_seq_bwd (include/rtt_b200.h): no row requests pose gradients
+MODE_NONSEQ_FAST = 0x400    # rtt_trace_nonseq_fwd / _bwd: explicit opt-in to the FAST arithmetic
 
 
 class RttLibraryMissing(RuntimeError):

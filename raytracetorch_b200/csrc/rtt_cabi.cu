@@ -248,8 +248,8 @@ int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* 
         a.n_sens = n_sensors; a.nbounces = nbounces; a.n = n;                                          \
         return finish(rtt::NS::launch_nonseq_fwd_##NS(a, st));                                         \
     }
-    (void)mode;   /* one arithmetic only: see include/rtt_b200.h */
-    RTT_BODY(exact)
+    /* EXACT unless the caller opts in to the FAST arithmetic explicitly: see include/rtt_b200.h */
+    if (mode & RTT_MODE_NONSEQ_FAST) RTT_BODY(fast) else RTT_BODY(exact)
 #undef RTT_BODY
 }
 
@@ -289,8 +289,8 @@ int rtt_trace_nonseq_bwd(const float* in_pos, const float* in_dir, const float* 
         a.n_sens = n_sensors; a.nbounces = nbounces; a.n = n;                                          \
         return finish(rtt::NS::launch_nonseq_bwd_##NS(a, st));                                         \
     }
-    (void)mode;   /* one arithmetic only: see include/rtt_b200.h */
-    RTT_BODY(exact)
+    /* EXACT unless the caller opts in to the FAST arithmetic explicitly: see include/rtt_b200.h */
+    if (mode & RTT_MODE_NONSEQ_FAST) RTT_BODY(fast) else RTT_BODY(exact)
 #undef RTT_BODY
 }
 

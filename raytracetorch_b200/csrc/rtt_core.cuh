@@ -82,6 +82,11 @@ enum {
 // Subset of RTT_ROW_SPECS that also gets a specialised ADJOINT (code size: the reverse sweep is ~3x
 // the forward interaction).  Absorbing rows (inked edges, box faces) kill the ray, so live-ray
 // gradients rarely cross them; they and every other kind use the generic adjoint.
+#if defined(RTT_EXPERIMENT_ADJ_MIN)
+#define RTT_ROW_SPECS_ADJ(X)                                                                            \
+    X(1, RTT_SURF_QUADRIC, RTT_BOUND_HALF, RTT_SHAPE_SPHERIC_FACE, RTT_PHYS_SNELL, 3, 0)                           \
+    X(13, RTT_SURF_PLANE, RTT_BOUND_DISK, RTT_SHAPE_NONE, RTT_PHYS_TRANSMIT, 3, 1)
+#else
 #define RTT_ROW_SPECS_ADJ(X)                                                                            \
     X(1, RTT_SURF_QUADRIC, RTT_BOUND_HALF, RTT_SHAPE_SPHERIC_FACE, RTT_PHYS_SNELL, 3, 0)                           \
     X(2, RTT_SURF_QUADRIC, RTT_BOUND_HALF, RTT_SHAPE_SPHERIC_FACE, RTT_PHYS_SNELL, 2, 0)                           \
@@ -90,6 +95,7 @@ enum {
     X(12, RTT_SURF_PLANE, RTT_BOUND_DISK, RTT_SHAPE_NONE, RTT_PHYS_APERTURE, 3, 0)                                 \
     X(13, RTT_SURF_PLANE, RTT_BOUND_DISK, RTT_SHAPE_NONE, RTT_PHYS_TRANSMIT, 3, 1)                                 \
     X(14, RTT_SURF_PLANE, RTT_BOUND_RECT, RTT_SHAPE_NONE, RTT_PHYS_TRANSMIT, 3, 1)
+#endif
 
 // ---- row-kind policies -----------------------------------------------------------------------
 // Every per-row function below is a template over a policy K that answers "what kind of row is

@@ -887,6 +887,27 @@ __device__ __forceinline__ void reverse_row(const SmemTable& T, int S, int L, in
     gI = gI * mod + g_w;
 }
 
+// The generic (KDyn) replay / reverse steps handle every row kind the table format can express and are ~9 k instructions
+// of code between them, eight times the specialised lens-face + stop + sensor paths that the BASELINE scenes execute.
+// Inlined into the row switches they pushed the kernel to 12.8 k instructions (200 KB) and the hot paths apart: 45 % of
+// the adjoint's stall samples on C3 were `no_instruction` (instruction fetch).  Out of line, by value, they cost a call
+// only when a row really needs them.
+struct ReplayOut { V3 p, d; };
+__device__ __noinline__ ReplayOut replay_row_generic(SmemTable T, int S, int L, int r, int lam, long long i, V3 p, V3 d) {
+    replay_row<KDyn>(T, S, L, r, lam, i, p, d);
+    ReplayOut o; o.p = p; o.d = d;
+    return o;
+}
+struct ReverseOut { V3 gp, gd; float gI; RowGrad G; };
+__device__ __noinline__ ReverseOut reverse_row_generic(SmemTable T, int S, int L, int r, int lam, long long i,
+                                                       const SeqBwdArgs& a, Checkpoint ck, V3 gp, V3 gd, float gI, int flags) {
+    ReverseOut o;
+    zero(o.G);
+    reverse_row<KDyn>(T, S, L, r, lam, i, a, ck, gp, gd, gI, o.G, flags);
+    o.gp = gp; o.gd = gd; o.gI = gI;
+    return o;
+}
+
 // Rays per block iteration of the sequential adjoint.  When no input-ray gradients are requested, a ray whose
 // upstream gradients (final position / direction, sensor-record xyz) are all zero contributes nothing to any
 // parameter gradient — every term of the reverse sweep is linear in them — so the block first compacts the
@@ -1017,7 +1038,7 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
                     case OP: replay_row<KStatic<SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR>>(T, S, L, r, lam, i, p, d); break;
                     RTT_ROW_SPECS_ADJ(RTT_X)
 #undef RTT_X
-                    default: replay_row<KDyn>(T, S, L, r, lam, i, p, d); break;
+                    default: { const ReplayOut o = replay_row_generic(T, S, L, r, lam, i, p, d); p = o.p; d = o.d; break; }
                 }
             }
         }
@@ -1045,7 +1066,11 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
                     case OP: reverse_row<KStatic<SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR>>(T, S, L, r, lam, i, a, ck[nh], gp, gd, gI, G, flags); break;
                     RTT_ROW_SPECS_ADJ(RTT_X)
 #undef RTT_X
-                    default: reverse_row<KDyn>(T, S, L, r, lam, i, a, ck[nh], gp, gd, gI, G, flags); break;
+                    default: {
+                        const ReverseOut o = reverse_row_generic(T, S, L, r, lam, i, a, ck[nh], gp, gd, gI, flags);
+                        gp = o.gp; gd = o.gd; gI = o.gI; G = o.G;
+                        break;
+                    }
                 }
             }
             const int slot = (int)R.f[D_ACC_SLOT];
@@ -1199,13 +1224,15 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
                 p = s.hit_global; d = s.new_dir; I = I * s.mod;
                 if (a.hit_seq) a.hit_seq[i * NB + nb] = (unsigned char)win;
                 ++nb;
-                done = nb >= NB;
+                // retire in THIS trip when the ray is over (bounce limit, absorbed, blown up): an absorbed ray used to
+                // hold its lane for one more, idle trip of the warp loop before it was written back and replaced
+                done = (nb >= NB) || !(I > 0.0f) || !finite_ray(p, d);
             }
         }
         if (done) {
             for (int s = 0; s < a.n_sens; ++s)
                 if (a.sens[s].count) a.sens[s].count[i] = (unsigned char)((cnts >> (8 * s)) & 255u);
-            if (a.hit_seq) for (int b = nb; b < NB; ++b) a.hit_seq[i * NB + b] = 255;
+            // (the tail of hit_seq is pre-filled with 255 by the launcher: one memset instead of byte stores per ray)
             if (a.n_hits) a.n_hits[i] = (unsigned char)nb;
             if (a.opos) { store3(a.opos, i, p); store3(a.odir, i, d); a.ointen[i] = I; }
             have = false;
@@ -1630,6 +1657,8 @@ cudaError_t RTT_NAME(launch_seq_bwd)(const SeqBwdArgs& a, cudaStream_t st) {
 }
 cudaError_t RTT_NAME(launch_nonseq_fwd)(const NonseqFwdArgs& a, cudaStream_t st) {
     if (cudaError_t e = allow_smem(RTT_NAME(k_trace_nonseq_fwd), nonseq_fwd_smem(a.tab.S, a.tab.L))) return e;
+    if (a.hit_seq && a.nbounces > 0)
+        if (cudaError_t e = cudaMemsetAsync(a.hit_seq, 0xFF, (size_t)a.n * a.nbounces, st)) return e;
     RTT_NAME(k_trace_nonseq_fwd)<<<grid_for(a.n, 8), kThreads, nonseq_fwd_smem(a.tab.S, a.tab.L), st>>>(a);
     return cudaGetLastError();
 }

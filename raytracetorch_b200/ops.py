@@ -20,6 +20,7 @@ from .table import SurfaceTable, compile_elements
 
 MODE_FAST, MODE_EXACT = _cabi.MODE_FAST, _cabi.MODE_EXACT
 MODE_SCALAR_GRADS = _cabi.MODE_SCALAR_GRADS
+MODE_NONSEQ_FAST = _cabi.MODE_NONSEQ_FAST
 MODE_NO_FINAL_RAYS = 0x200    # trace_seq_fwd op only: skip the final pos / dir / intensity outputs (goal evaluations)
 # Arithmetic defaults.  Sequential traces: FAST (FMA contraction; masks verified identical to
 # the reference on every fixture, points within 1e-5).  Non-sequential traces: EXACT — the
@@ -1122,6 +1123,10 @@ def trace_nonsequential(table: SurfaceTable, pos, dir_, intensity, nbounces: int
                         want_record=True, sensor_cfg: Optional[List[float]] = None, mode: Optional[int] = None,
                         record_depth: int = 1, source=None, want_rays: bool = True):
     """Fused Scene.simulate bounce loop (scene/base.py:129-235).
+
+    Arithmetic: EXACT (the reference's rounding; default).  ``mode=MODE_FAST | MODE_NONSEQ_FAST`` opts in to the FAST
+    arithmetic: hit sequences of rays that do not depend on the t > 1e-6 threshold are unchanged, the others — which
+    are decided by fp32 rounding in the reference itself — may take another path.
 
     Returns dict(pos, dir, intensity, hit_seq [N,B] uint8 (255 = none), n_hits [N] uint8,
     records [n_sensors, K, N, 4] (the k-th interaction of ray i with the sensor, K = record_depth),

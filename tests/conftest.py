@@ -38,7 +38,7 @@ _BACKENDS = ["host", pytest.param("gpu", marks=pytest.mark.gpu)]
 def _runner(backend, variant):
     if backend == "host":
         from hostsim import build
-        return build({"pair_plain": "pair", "tile": "fast"}.get(variant, variant))
+        return build({"pair_plain": "pair", "tile": "fast", "nonseq_fast": "fast"}.get(variant, variant))
     import torch
     if not torch.cuda.is_available():
         pytest.fail("gpu test selected but no CUDA device is visible (there is no CPU fallback)")
@@ -46,7 +46,9 @@ def _runner(backend, variant):
     # mode word of the C ABI: arithmetic in bits 0..7 (0 FAST, 1 EXACT), kernel build in bits 16..23
     # (include/rtt_b200.h RTT_MODE_TUNE_*): "pair" = packed ray pairs with bulk-async ray streaming, "pair_plain" =
     # the same arithmetic with plain loads / stores, "tile" = the scalar frame-resident tile kernel
-    return GpuSim({"exact": 1, "fast": 0, "pair": 16 << 16, "pair_plain": 18 << 16, "tile": 3 << 16}[variant])
+    # "nonseq_fast": the explicit opt-in of the non-sequential entries to the FAST arithmetic (RTT_MODE_NONSEQ_FAST)
+    return GpuSim({"exact": 1, "fast": 0, "pair": 16 << 16, "pair_plain": 18 << 16, "tile": 3 << 16,
+                   "nonseq_fast": 0x400}[variant])
 
 
 @pytest.fixture(params=_BACKENDS)
