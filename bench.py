@@ -864,8 +864,17 @@ def run_gpu_arm(args):
         g1.record()
         barrier()
         e_ms = max_over_ranks(max(g0.elapsed_time(g1), 1e3 * (time.perf_counter() - t0)) / args.e2e_steps)
+        # per-rank host->device rate (this rank's own clock): at N >= 4 the ranks share the host's memory system
+        my_gbs = h2d / (max(g0.elapsed_time(g1), 1e-3) / args.e2e_steps / 1e3) / 1e9
+        rates = [my_gbs]
+        if world > 1:
+            t_r = torch.tensor([my_gbs], device=dev, dtype=torch.float64)
+            gl = [torch.zeros_like(t_r) for _ in range(world)]
+            tdist.all_gather(gl, t_r)
+            rates = [float(x.item()) for x in gl]
         e2e = dict(value=world * n * tests_per_ray / (e_ms / 1e3), unit=UNIT, h2d_bytes_per_step=h2d,
                    d2h_bytes_per_step=img_numel * 4, ms_per_step=e_ms, steps=args.e2e_steps,
+                   h2d_gb_per_s_per_rank=[round(r, 1) for r in rates],
                    api="SequentialScene.simulate(rays)" if not w["nonseq"] else "Scene.simulate()")
 
     # ---- CPU baseline on rank 0, N=1 only --------------------------------------------------------------
