@@ -471,9 +471,15 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_tile(const __g
 //     One __syncthreads per tile (results complete -> elected thread stores).
 // Rays generated in the kernel (rtt_source_t), unaligned caller buffers and the ragged last tile take the same
 // arithmetic with plain loads / stores (STREAM = false build, or the cooperative copy below).
-constexpr int kPairTile = 2 * kThreads;                                  // rays per block iteration
-constexpr int kSlotPos = 0, kSlotDir = kPairTile * 12, kSlotInt = kPairTile * 24, kSlotWav = kPairTile * 28,
-              kSlotMask = kPairTile * 32, kSlotBytes = kPairTile * 40;   // 20 KB per slot
+// NP = ray pairs per thread.  Shipped: 1 (512-ray tiles, 80 registers, 3 blocks / SM).  NP = 2 (1024-ray tiles, two
+// independent packed chains per thread, 112 registers, 2 blocks / SM) measured slower on every workload — C2 4.28 vs
+// 3.92, C1 2.75 vs 2.51, C4 8.19 vs 6.92 ms per 1e8 rays (profiles/r2_fwd_pair_ab.md) — and is not instantiated.
+template <int NP>
+struct PairGeom {
+    static constexpr int kTile = NP * 2 * kThreads;                     // rays per block iteration
+    static constexpr int kPos = 0, kDir = kTile * 12, kInt = kTile * 24, kWav = kTile * 28, kMask = kTile * 32,
+                         kBytes = kTile * 40;                           // 20 KB per slot and pair
+};
 constexpr int kPairSlots = 2;
 
 // ---- bulk-async copy / mbarrier primitives (PTX ISA 8.x, sm_90+; SASS: UBLKCP, SYNCS) --------------------
@@ -508,21 +514,21 @@ __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // shared-memory layout of the pair kernel, all at compile-time offsets: [image cache | Xf[MAX_ROWS+1] | ray slots | mbarriers | table]
-template <int LOG, bool STREAM>
+template <int LOG, bool STREAM, int NP = 1>
 struct PairLayout {
     static constexpr size_t kOffXf = (img_cache_bytes<LOG>() + 15) / 16 * 16;
     static constexpr size_t kOffSlots = (kOffXf + sizeof(Xf) * (RTT_MAX_ROWS + 1) + 127) / 128 * 128;
-    static constexpr size_t kOffBar = kOffSlots + (STREAM ? (size_t)kPairSlots * kSlotBytes : 0);
+    static constexpr size_t kOffBar = kOffSlots + (STREAM ? (size_t)kPairSlots * PairGeom<NP>::kBytes : 0);
     static constexpr size_t kOffTable = kOffBar + 16;
     __host__ __device__ static size_t bytes(int S, int L) { return kOffTable + smem_table_bytes(S, L); }
 };
 
 // reference-order walk of an irregular ray (see seq_walk_generic), for the pair kernel's layout
-template <int LOG, bool STREAM>
+template <int LOG, bool STREAM, int NP>
 __device__ __noinline__ WalkState pair_walk_generic(const SeqFwdArgs& a, int lam, long long i, WalkState w) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.tab.S, L = a.tab.L;
-    SmemTable T = carve(smem_raw + PairLayout<LOG, STREAM>::kOffTable, S, L);
+    SmemTable T = carve(smem_raw + PairLayout<LOG, STREAM, NP>::kOffTable, S, L);
     ImgCacheT<LOG> cache = img_cache_carve<LOG>(smem_raw);
     unsigned long long bit = 1ull;
     for (int r = 0; r < S; ++r, bit += bit) seq_row<KDyn, LOG>(T, S, L, r, lam, i, a, cache, w.p, w.d, w.I, w.mask, bit);
@@ -530,14 +536,16 @@ __device__ __noinline__ WalkState pair_walk_generic(const SeqFwdArgs& a, int lam
 }
 
 // ray `loc` of the tile staged in a slot
+template <int NP>
 __device__ __forceinline__ RayIn slot_ray(const unsigned char* slot, int loc, bool want_wav) {
-    const float* sp = reinterpret_cast<const float*>(slot + kSlotPos);
-    const float* sd = reinterpret_cast<const float*>(slot + kSlotDir);
+    typedef PairGeom<NP> GE;
+    const float* sp = reinterpret_cast<const float*>(slot + GE::kPos);
+    const float* sd = reinterpret_cast<const float*>(slot + GE::kDir);
     RayIn r;
     r.p = v3(sp[3 * loc], sp[3 * loc + 1], sp[3 * loc + 2]);
     r.d = v3(sd[3 * loc], sd[3 * loc + 1], sd[3 * loc + 2]);
-    r.I = reinterpret_cast<const float*>(slot + kSlotInt)[loc];
-    r.wav = want_wav ? reinterpret_cast<const float*>(slot + kSlotWav)[loc] : 0.0f;
+    r.I = reinterpret_cast<const float*>(slot + GE::kInt)[loc];
+    r.wav = want_wav ? reinterpret_cast<const float*>(slot + GE::kWav)[loc] : 0.0f;
     return r;
 }
 
@@ -584,31 +592,32 @@ __device__ __forceinline__ unsigned pair_row_generic(const SmemTable& T, int S, 
     return pair_row_scalar<K>(T.rows, r, P, D, I, act, mu_enter, mu_exit, aux_a, aux_b, dep);
 }
 
-template <int MINB, bool STREAM, int LOG>
+template <int MINB, bool STREAM, int LOG, int NP>
 __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __grid_constant__ SeqFwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    typedef PairLayout<LOG, STREAM> LY;
+    typedef PairLayout<LOG, STREAM, NP> LY;
+    typedef PairGeom<NP> GE;
     const int S = a.tab.S, L = a.tab.L;
     SmemTable T = carve(smem_raw + LY::kOffTable, S, L);
     Xf* xf = reinterpret_cast<Xf*>(smem_raw + LY::kOffXf);
     ImgCacheT<LOG> cache = img_cache_carve<LOG>(smem_raw);
     // tiles are counted in int: a.n <= 2^40 rays = 2^31 tiles of 512
-    const int n_tiles = (int)((a.n + kPairTile - 1) / kPairTile);
-    const int n_full = (int)(a.n / kPairTile);                          // tiles [0, n_full) are full
+    const int n_tiles = (int)((a.n + GE::kTile - 1) / GE::kTile);
+    const int n_full = (int)(a.n / GE::kTile);                          // tiles [0, n_full) are full
     const unsigned bar0 = smem_u32(smem_raw + LY::kOffBar);
     const unsigned slot0 = smem_u32(smem_raw + LY::kOffSlots);
     const bool use_wav = L > 0;
-    const unsigned tile_bytes = (unsigned)(kPairTile * (use_wav ? 32 : 28));
+    const unsigned tile_bytes = (unsigned)(GE::kTile * (use_wav ? 32 : 28));
 
     // elected thread: issue the bulk loads of tile `t` (a FULL tile) into slot `s`
     auto issue_load = [&](int t, int s) {
-        const unsigned bar = bar0 + 8u * s, dst = slot0 + (unsigned)(s * kSlotBytes);
-        const long long base = (long long)t * kPairTile;
+        const unsigned bar = bar0 + 8u * s, dst = slot0 + (unsigned)(s * GE::kBytes);
+        const long long base = (long long)t * GE::kTile;
         mbar_expect_tx(bar, tile_bytes);
-        bulk_g2s(dst + kSlotPos, a.pos + 3 * base, kPairTile * 12, bar);
-        bulk_g2s(dst + kSlotDir, a.dir + 3 * base, kPairTile * 12, bar);
-        bulk_g2s(dst + kSlotInt, a.inten + base, kPairTile * 4, bar);
-        if (use_wav) bulk_g2s(dst + kSlotWav, a.wav + base, kPairTile * 4, bar);
+        bulk_g2s(dst + GE::kPos, a.pos + 3 * base, GE::kTile * 12, bar);
+        bulk_g2s(dst + GE::kDir, a.dir + 3 * base, GE::kTile * 12, bar);
+        bulk_g2s(dst + GE::kInt, a.inten + base, GE::kTile * 4, bar);
+        if (use_wav) bulk_g2s(dst + GE::kWav, a.wav + base, GE::kTile * 4, bar);
     };
 
     if (STREAM && threadIdx.x == 0) {
@@ -627,18 +636,18 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
     unsigned k = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
         const int s = (int)(k & 1u);
-        unsigned char* slot = smem_raw + LY::kOffSlots + (size_t)s * kSlotBytes;
+        unsigned char* slot = smem_raw + LY::kOffSlots + (size_t)s * GE::kBytes;
         const bool full = tile < n_full;
-        const int cnt = full ? kPairTile : (int)(a.n - (long long)tile * kPairTile);
+        const int cnt = full ? GE::kTile : (int)(a.n - (long long)tile * GE::kTile);
         if (STREAM) {
             if (full) {
                 mbar_wait(bar0 + 8u * s, (k >> 1) & 1u);
             } else {                                                    // ragged last tile: cooperative plain copy
-                const long long base = (long long)tile * kPairTile;
-                float* sp = reinterpret_cast<float*>(slot + kSlotPos);
-                float* sd = reinterpret_cast<float*>(slot + kSlotDir);
-                float* si = reinterpret_cast<float*>(slot + kSlotInt);
-                float* sw = reinterpret_cast<float*>(slot + kSlotWav);
+                const long long base = (long long)tile * GE::kTile;
+                float* sp = reinterpret_cast<float*>(slot + GE::kPos);
+                float* sd = reinterpret_cast<float*>(slot + GE::kDir);
+                float* si = reinterpret_cast<float*>(slot + GE::kInt);
+                float* sw = reinterpret_cast<float*>(slot + GE::kWav);
                 for (int idx = threadIdx.x; idx < 3 * cnt; idx += kThreads) {
                     sp[idx] = a.pos[3 * base + idx]; sd[idx] = a.dir[3 * base + idx];
                 }
@@ -649,121 +658,177 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
                 __syncthreads();
             }
         }
-        // ---- this thread's pair: rays base + threadIdx.x and base + threadIdx.x + kThreads ----
-        P3 P, D;
-        F2 I;
-        int lamS[2];                                                    // wavelength index * S (offset into the index table)
-        bool act[2], odd[2];
-        {
+        // ---- this thread's pairs: pair q = rays base + threadIdx.x + (2q) * kThreads and + (2q + 1) * kThreads ----
+        P3 P[NP], D[NP];
+        F2 I[NP];
+        int lamS[NP][2];                                                // wavelength index * S (offset into the index table)
+        unsigned actb[NP], oddb = 0u;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
             V3 pin[2], din[2];
             float Iin[2];
+            actb[q] = 0u;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int loc = threadIdx.x + j * kThreads;
-                pin[j] = v3(0.0f, 0.0f, 0.0f); din[j] = v3(0.0f, 0.0f, 0.0f); Iin[j] = 0.0f; lamS[j] = 0;
-                act[j] = false; odd[j] = false;
+                const int loc = threadIdx.x + (2 * q + j) * kThreads;
+                pin[j] = v3(0.0f, 0.0f, 0.0f); din[j] = v3(0.0f, 0.0f, 0.0f); Iin[j] = 0.0f; lamS[q][j] = 0;
                 if (loc < cnt) {
-                    const RayIn ray = STREAM ? slot_ray(slot, loc, use_wav)
-                                             : fetch_ray(a, skey, (long long)tile * kPairTile + loc, use_wav);
+                    const RayIn ray = STREAM ? slot_ray<NP>(slot, loc, use_wav)
+                                             : fetch_ray(a, skey, (long long)tile * GE::kTile + loc, use_wav);
                     pin[j] = ray.p; din[j] = ray.d; Iin[j] = ray.I;
-                    lamS[j] = use_wav ? wavelength_index(T, L, ray.wav) * S : 0;
-                    act[j] = finite_ray(ray.p, ray.d) && regular_dir(ray.d);
-                    odd[j] = !act[j];                                   // re-read below: un-normalised or non-finite ray
+                    lamS[q][j] = use_wav ? wavelength_index(T, L, ray.wav) * S : 0;
+                    if (finite_ray(ray.p, ray.d) && regular_dir(ray.d)) actb[q] |= 1u << j;
+                    else oddb |= 1u << (2 * q + j);                     // re-read below: un-normalised or non-finite ray
                 }
             }
-            P = pack3(pin[0], pin[1]); D = pack3(din[0], din[1]); I = f2(Iin[0], Iin[1]);
+            P[q] = pack3(pin[0], pin[1]); D[q] = pack3(din[0], din[1]); I[q] = f2(Iin[0], Iin[1]);
         }
-        const unsigned actb = (act[0] ? 1u : 0u) | (act[1] ? 2u : 0u);
         // hit masks: 32-bit words (row r -> bit r & 31 of the current word); the low words are set aside when the walk
         // passes row 32.  A 64-bit mask per lane costs four extra integer instructions per row.
-        unsigned m_a = 0u, m_b = 0u, lo_a = 0u, lo_b = 0u;
+        unsigned m_a[NP], m_b[NP], lo_a[NP], lo_b[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) { m_a[q] = m_b[q] = lo_a[q] = lo_b[q] = 0u; }
         bool upper = false;
-        const long long i0 = (long long)tile * kPairTile + threadIdx.x;
-        PairDeposit<LOG> dep{a, cache, i0, use_wav ? lamS[0] / S : 0, use_wav ? lamS[1] / S : 0};
+        const long long i0 = (long long)tile * GE::kTile + threadIdx.x;
         for (int r = 0; r < S; ++r) {
-            if (r >= 32 && !upper) { lo_a = m_a; lo_b = m_b; m_a = 0u; m_b = 0u; upper = true; }
+            if (r >= 32 && !upper) {
+#pragma unroll
+                for (int q = 0; q < NP; ++q) { lo_a[q] = m_a[q]; lo_b[q] = m_b[q]; m_a[q] = 0u; m_b[q] = 0u; }
+                upper = true;
+            }
             const int ctl = xf[r].ctl;                                  // warp-uniform: opcode | kind << 8 | run << 16
-            if (ctl & 0xff00) pair_apply_xf(xf[r], P, D);
+            if (ctl & 0xff00) {
+#pragma unroll
+                for (int q = 0; q < NP; ++q) pair_apply_xf(xf[r], P[q], D[q]);
+            }
             const int run = ctl >> 16;
             if (run > 0) {                                              // lens-edge rows: skip them when no lane can hit
-                const bool away = pair_edge_culled(xf[r], P, D, act[0], act[1]);
+                bool away = true;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) away = away && pair_edge_culled(xf[r], P[q], D[q], actb[q] & 1u, actb[q] & 2u);
                 if (__all_sync(kFull, away)) {
                     r += run - 1;
                     continue;
                 }
             }
-            unsigned hit;
+            unsigned hit[NP];
+            F2 me[NP], mx[NP];
             switch (ctl & 0xff) {                                       // warp-uniform
-                case 1: {
-                    F2 me, mx; pair_ior(T, L, r, lamS[0], lamS[1], me, mx);
-                    hit = pair_conic_face<true, RTT_SHAPE_SPHERIC_FACE>(T.rows, r, P, D, I, actb, me, mx, dep);
+                case 1:
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) pair_ior(T, L, r, lamS[q][0], lamS[q][1], me[q], mx[q]);
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        PairDeposit<LOG> dep{a, cache, i0 + (long long)(2 * q) * kThreads, 0, 0};
+                        hit[q] = pair_conic_face<true, RTT_SHAPE_SPHERIC_FACE>(T.rows, r, P[q], D[q], I[q], actb[q], me[q], mx[q], dep);
+                    }
                     break;
-                }
-                case 4: {
-                    F2 me, mx; pair_ior(T, L, r, lamS[0], lamS[1], me, mx);
-                    hit = pair_conic_face<false, RTT_SHAPE_CYL_FACE>(T.rows, r, P, D, I, actb, me, mx, dep);
+                case 4:
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) pair_ior(T, L, r, lamS[q][0], lamS[q][1], me[q], mx[q]);
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        PairDeposit<LOG> dep{a, cache, i0 + (long long)(2 * q) * kThreads, 0, 0};
+                        hit[q] = pair_conic_face<false, RTT_SHAPE_CYL_FACE>(T.rows, r, P[q], D[q], I[q], actb[q], me[q], mx[q], dep);
+                    }
                     break;
-                }
-                case 7: hit = pair_plane<RTT_BOUND_DISK, RTT_PHYS_APERTURE, false>(T.rows, r, P, D, I, actb, dep); break;
-                case 8: hit = pair_plane<RTT_BOUND_DISK, RTT_PHYS_TRANSMIT, true>(T.rows, r, P, D, I, actb, dep); break;
-                case 9: hit = pair_plane<RTT_BOUND_RECT, RTT_PHYS_TRANSMIT, true>(T.rows, r, P, D, I, actb, dep); break;
-#define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR)                                         \
-                case OP: hit = pair_row_generic<KTile<SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR>>(T, S, L, r, i0, dep.lam_a, dep.lam_b, P, D, I, actb, dep); break;
+#define RTT_PLANE_CASE(OP, BOUND, PHYS, SENSOR)                                                                         \
+                case OP:                                                                                                    \
+                    _Pragma("unroll") for (int q = 0; q < NP; ++q) {                                                        \
+                        PairDeposit<LOG> dep{a, cache, i0 + (long long)(2 * q) * kThreads,                                  \
+                                             use_wav ? lamS[q][0] / S : 0, use_wav ? lamS[q][1] / S : 0};                   \
+                        hit[q] = pair_plane<BOUND, PHYS, SENSOR>(T.rows, r, P[q], D[q], I[q], actb[q], dep);                \
+                    }                                                                                                       \
+                    break;
+                RTT_PLANE_CASE(7, RTT_BOUND_DISK, RTT_PHYS_APERTURE, false)
+                RTT_PLANE_CASE(8, RTT_BOUND_DISK, RTT_PHYS_TRANSMIT, true)
+                RTT_PLANE_CASE(9, RTT_BOUND_RECT, RTT_PHYS_TRANSMIT, true)
+#undef RTT_PLANE_CASE
+#define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR)                                                           \
+                case OP:                                                                                                    \
+                    _Pragma("unroll") for (int q = 0; q < NP; ++q) {                                                        \
+                        const int la = use_wav ? lamS[q][0] / S : 0, lb = use_wav ? lamS[q][1] / S : 0;                     \
+                        PairDeposit<LOG> dep{a, cache, i0 + (long long)(2 * q) * kThreads, la, lb};                         \
+                        hit[q] = pair_row_generic<KTile<SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR>>(                       \
+                            T, S, L, r, i0 + (long long)(2 * q) * kThreads, la, lb, P[q], D[q], I[q], actb[q], dep);        \
+                    }                                                                                                       \
+                    break;
                 RTT_PAIR_SCALAR_SPECS(RTT_X)
 #undef RTT_X
-                default: hit = pair_row_generic<KDyn>(T, S, L, r, i0, dep.lam_a, dep.lam_b, P, D, I, actb, dep); break;
+                default:
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        const int la = use_wav ? lamS[q][0] / S : 0, lb = use_wav ? lamS[q][1] / S : 0;
+                        PairDeposit<LOG> dep{a, cache, i0 + (long long)(2 * q) * kThreads, la, lb};
+                        hit[q] = pair_row_generic<KDyn>(T, S, L, r, i0 + (long long)(2 * q) * kThreads, la, lb, P[q], D[q], I[q],
+                                                        actb[q], dep);
+                    }
+                    break;
             }
             const unsigned bit = 1u << (r & 31);
-            m_a |= bit & (0u - (hit & 1u));
-            m_b |= bit & (0u - (hit >> 1));
-        }
-        if (xf[S].kind) pair_apply_xf(xf[S], P, D);
-        if (!upper) { lo_a = m_a; lo_b = m_b; m_a = 0u; m_b = 0u; }
-        // ---- results ----
-        V3 po[2] = {lane_a(P), lane_b(P)}, dout[2] = {lane_a(D), lane_b(D)};
-        float Io[2] = {I.x, I.y};
-        unsigned long long mo[2] = {((unsigned long long)m_a << 32) | lo_a, ((unsigned long long)m_b << 32) | lo_b};
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int loc = threadIdx.x + j * kThreads;
-            if (odd[j]) {
-                // un-normalised direction: walk in the reference's order; NaN / inf ray: hits nothing, stays as it was
-                // (the slot still holds this ray's inputs: a thread only ever writes its own entries)
-                const long long i = (long long)tile * kPairTile + loc;
-                const RayIn ray = STREAM ? slot_ray(slot, loc, use_wav) : fetch_ray(a, skey, i, use_wav);
-                WalkState w;
-                w.p = ray.p; w.d = ray.d; w.I = ray.I; w.mask = 0ull;
-                if (finite_ray(ray.p, ray.d)) w = pair_walk_generic<LOG, STREAM>(a, j ? dep.lam_b : dep.lam_a, i, w);
-                po[j] = w.p; dout[j] = w.d; Io[j] = w.I; mo[j] = w.mask;
+            for (int q = 0; q < NP; ++q) {
+                m_a[q] |= bit & (0u - (hit[q] & 1u));
+                m_b[q] |= bit & (0u - (hit[q] >> 1));
             }
-            if (loc < cnt) {
-                if (STREAM) {
-                    float* sp = reinterpret_cast<float*>(slot + kSlotPos);
-                    float* sd = reinterpret_cast<float*>(slot + kSlotDir);
-                    sp[3 * loc] = po[j].x; sp[3 * loc + 1] = po[j].y; sp[3 * loc + 2] = po[j].z;
-                    sd[3 * loc] = dout[j].x; sd[3 * loc + 1] = dout[j].y; sd[3 * loc + 2] = dout[j].z;
-                    reinterpret_cast<float*>(slot + kSlotInt)[loc] = Io[j];
-                    reinterpret_cast<unsigned long long*>(slot + kSlotMask)[loc] = mo[j];
-                } else {
-                    const long long i = (long long)tile * kPairTile + loc;
-                    if (a.opos) { store3(a.opos, i, po[j]); store3(a.odir, i, dout[j]); a.ointen[i] = Io[j]; }
-                    if (a.hitmask) a.hitmask[i] = mo[j];
+        }
+        if (xf[S].kind) {
+#pragma unroll
+            for (int q = 0; q < NP; ++q) pair_apply_xf(xf[S], P[q], D[q]);
+        }
+        if (!upper) {
+#pragma unroll
+            for (int q = 0; q < NP; ++q) { lo_a[q] = m_a[q]; lo_b[q] = m_b[q]; m_a[q] = 0u; m_b[q] = 0u; }
+        }
+        // ---- results ----
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            V3 po[2] = {lane_a(P[q]), lane_b(P[q])}, dout[2] = {lane_a(D[q]), lane_b(D[q])};
+            float Io[2] = {I[q].x, I[q].y};
+            unsigned long long mo[2] = {((unsigned long long)m_a[q] << 32) | lo_a[q], ((unsigned long long)m_b[q] << 32) | lo_b[q]};
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int loc = threadIdx.x + (2 * q + j) * kThreads;
+                if ((oddb >> (2 * q + j)) & 1u) {
+                    // un-normalised direction: walk in the reference's order; NaN / inf ray: hits nothing, stays as it was
+                    // (the slot still holds this ray's inputs: a thread only ever writes its own entries)
+                    const long long i = (long long)tile * GE::kTile + loc;
+                    const RayIn ray = STREAM ? slot_ray<NP>(slot, loc, use_wav) : fetch_ray(a, skey, i, use_wav);
+                    WalkState w;
+                    w.p = ray.p; w.d = ray.d; w.I = ray.I; w.mask = 0ull;
+                    if (finite_ray(ray.p, ray.d))
+                        w = pair_walk_generic<LOG, STREAM, NP>(a, use_wav ? lamS[q][j] / S : 0, i, w);
+                    po[j] = w.p; dout[j] = w.d; Io[j] = w.I; mo[j] = w.mask;
+                }
+                if (loc < cnt) {
+                    if (STREAM) {
+                        float* sp = reinterpret_cast<float*>(slot + GE::kPos);
+                        float* sd = reinterpret_cast<float*>(slot + GE::kDir);
+                        sp[3 * loc] = po[j].x; sp[3 * loc + 1] = po[j].y; sp[3 * loc + 2] = po[j].z;
+                        sd[3 * loc] = dout[j].x; sd[3 * loc + 1] = dout[j].y; sd[3 * loc + 2] = dout[j].z;
+                        reinterpret_cast<float*>(slot + GE::kInt)[loc] = Io[j];
+                        reinterpret_cast<unsigned long long*>(slot + GE::kMask)[loc] = mo[j];
+                    } else {
+                        const long long i = (long long)tile * GE::kTile + loc;
+                        if (a.opos) { store3(a.opos, i, po[j]); store3(a.odir, i, dout[j]); a.ointen[i] = Io[j]; }
+                        if (a.hitmask) a.hitmask[i] = mo[j];
+                    }
                 }
             }
         }
         if (STREAM) {
             fence_async_smem();
             __syncthreads();                                            // every result of the tile is in the slot
-            const long long base = (long long)tile * kPairTile;
+            const long long base = (long long)tile * GE::kTile;
             if (full) {
                 if (threadIdx.x == 0) {
-                    const unsigned src = slot0 + (unsigned)(s * kSlotBytes);
+                    const unsigned src = slot0 + (unsigned)(s * GE::kBytes);
                     if (a.opos) {
-                        bulk_s2g(a.opos + 3 * base, src + kSlotPos, kPairTile * 12);
-                        bulk_s2g(a.odir + 3 * base, src + kSlotDir, kPairTile * 12);
-                        bulk_s2g(a.ointen + base, src + kSlotInt, kPairTile * 4);
+                        bulk_s2g(a.opos + 3 * base, src + GE::kPos, GE::kTile * 12);
+                        bulk_s2g(a.odir + 3 * base, src + GE::kDir, GE::kTile * 12);
+                        bulk_s2g(a.ointen + base, src + GE::kInt, GE::kTile * 4);
                     }
-                    if (a.hitmask) bulk_s2g(a.hitmask + base, src + kSlotMask, kPairTile * 8);
+                    if (a.hitmask) bulk_s2g(a.hitmask + base, src + GE::kMask, GE::kTile * 8);
                     bulk_commit();
                     const long long next = (long long)tile + (long long)kPairSlots * gridDim.x;
                     if (next < n_tiles) {
@@ -772,18 +837,18 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
                     }
                 }
             } else {
-                const float* sp = reinterpret_cast<const float*>(slot + kSlotPos);
-                const float* sd = reinterpret_cast<const float*>(slot + kSlotDir);
+                const float* sp = reinterpret_cast<const float*>(slot + GE::kPos);
+                const float* sd = reinterpret_cast<const float*>(slot + GE::kDir);
                 if (a.opos) {
                     for (int idx = threadIdx.x; idx < 3 * cnt; idx += kThreads) {
                         a.opos[3 * base + idx] = sp[idx]; a.odir[3 * base + idx] = sd[idx];
                     }
                     for (int idx = threadIdx.x; idx < cnt; idx += kThreads)
-                        a.ointen[base + idx] = reinterpret_cast<const float*>(slot + kSlotInt)[idx];
+                        a.ointen[base + idx] = reinterpret_cast<const float*>(slot + GE::kInt)[idx];
                 }
                 if (a.hitmask)
                     for (int idx = threadIdx.x; idx < cnt; idx += kThreads)
-                        a.hitmask[base + idx] = reinterpret_cast<const unsigned long long*>(slot + kSlotMask)[idx];
+                        a.hitmask[base + idx] = reinterpret_cast<const unsigned long long*>(slot + GE::kMask)[idx];
             }
         }
     }
@@ -1574,17 +1639,17 @@ inline cudaError_t launch_tile(const SeqFwdArgs& a, cudaStream_t st) {
 // generated in the kernel and its materialised twin run the same build and stay bit-identical (tests/test_goals.py).
 inline int fwd_tile_for(int S, int tune) { return tune ? tune : (S <= 6 ? 5 : 3); }   // 0 is resolved by the caller (fwd_default_build)
 
-template <int MINB, bool STREAM, int LOG>
+template <int MINB, bool STREAM, int LOG, int NP = 1>
 inline cudaError_t launch_pair(const SeqFwdArgs& a, cudaStream_t st) {
-    const size_t smem = PairLayout<LOG, STREAM>::bytes(a.tab.S, a.tab.L);
-    if (cudaError_t e = allow_smem(k_trace_seq_fwd_pair<MINB, STREAM, LOG>, smem)) return e;
-    const long long tiles = (a.n + kPairTile - 1) / kPairTile;
+    const size_t smem = PairLayout<LOG, STREAM, NP>::bytes(a.tab.S, a.tab.L);
+    if (cudaError_t e = allow_smem(k_trace_seq_fwd_pair<MINB, STREAM, LOG, NP>, smem)) return e;
+    const long long tiles = (a.n + PairGeom<NP>::kTile - 1) / PairGeom<NP>::kTile;
     // persistent blocks, one resident set (tiles are handed out round-robin: tile = block + k * grid); the plain build
     // keeps the tile kernel's four waves (a block that lands on a busier SM costs 1/4 of a launch)
     long long g = (long long)sm_count() * MINB * (STREAM ? 1 : 4);
     if (tiles < g) g = tiles;
     if (g < 1) g = 1;
-    k_trace_seq_fwd_pair<MINB, STREAM, LOG><<<(int)g, kThreads, smem, st>>>(a);
+    k_trace_seq_fwd_pair<MINB, STREAM, LOG, NP><<<(int)g, kThreads, smem, st>>>(a);
     return cudaGetLastError();
 }
 // bulk-async copies need 16-byte aligned global addresses; every full tile starts a multiple of 512 rays into the

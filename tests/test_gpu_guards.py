@@ -37,7 +37,7 @@ class Arena:
 
 @pytest.mark.parametrize("misalign", [0, 4])
 @pytest.mark.parametrize("tune", [16, 18, 3, 5, 9])
-@pytest.mark.parametrize("n", [1, 511, 512, 513, 1536, 20011])
+@pytest.mark.parametrize("n", [1, 511, 512, 513, 1024, 1536, 20011])
 def test_sequential_forward_stays_inside_its_output_buffers(n, tune, misalign):
     from raytracetorch_b200 import _cabi
     from gpusim import GpuSim, _dev, _p
