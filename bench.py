@@ -1103,23 +1103,47 @@ def run_c3(args):
     _attach_profile_evidence(roof, "c3", n)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import trace_oracle as O          # CPU baseline only
         n_cpu = min(args.cpu_rays, 1_000_000)
         torch.set_num_threads(os.cpu_count() or 1)
-        els_c = build_workload("c3", "cpu")["elements"]
-        tabc = rtt.compile_elements(els_c)
         pos, dirs, inten, _ = synth_bundle(w, n_cpu, "cpu", 5)
-        t0 = time.perf_counter()
-        o = O.trace_sequential(tabc.f, tabc.i_host, pos, dirs, inten)
-        m, hl, ww = o["sensor"][0]
-        act = ww > 0
-        xy, ww = hl[act, :2], ww[act]
-        W = ww.sum()
-        cx, cy = (xy[:, 0] * ww).sum() / W, (xy[:, 1] * ww).sum() / W
-        torch.sqrt(((xy[:, 0] - cx) ** 2 + (xy[:, 1] - cy) ** 2) * (ww / W)).sum().backward()
-        tc = time.perf_counter() - t0
-        cpu = dict(value=n_cpu * S / tc, unit=UNIT, cores=os.cpu_count(), kind="port",
-                   sample=f"one forward+backward step of {n_cpu} rays ({tc:.1f} s), eager torch oracle + autograd")
+
+        def spot_size(xy, ww):
+            act = ww > 0
+            xy, ww = xy[act, :2], ww[act]
+            W = ww.sum()
+            cx, cy = (xy[:, 0] * ww).sum() / W, (xy[:, 1] * ww).sum() / W
+            return torch.sqrt(((xy[:, 0] - cx) ** 2 + (xy[:, 1] - cy) ** 2) * (ww / W)).sum()
+
+        def port_step():
+            from oracle import trace_oracle as O      # CPU baseline only
+            els_c = build_workload("c3", "cpu")["elements"]
+            tabc = rtt.compile_elements(els_c)
+            t0 = time.perf_counter()
+            o = O.trace_sequential(tabc.f, tabc.i_host, pos, dirs, inten)
+            _m, hl, ww = o["sensor"][0]
+            spot_size(hl, ww).backward()
+            return time.perf_counter() - t0
+
+        R = None if args.port_only else _reference_modules()
+        if R is not None:
+            # the UNMODIFIED reference: SequentialScene.simulate + the spot-size loss on its sensor lists + backward()
+            import scenes
+            els_r = scenes.c1_singlet(R, physical=True, grads=True)
+            t0 = time.perf_counter()
+            R.scene.SequentialScene(els_r).simulate(R.rays.Rays.initialize(pos, dirs, intensities=inten))
+            locs, ww, _ids = els_r[1].getHitsTensors()
+            spot_size(locs, ww).backward()
+            tc = time.perf_counter() - t0
+            cpu = dict(value=n_cpu * S / tc, unit=UNIT, cores=os.cpu_count(), kind="reference",
+                       sample=f"one forward+backward step of {n_cpu} rays ({tc:.1f} s): the unmodified reference's "
+                              f"SequentialScene.simulate, the spot-size loss on its sensor hit lists, autograd backward")
+            tp = port_step()
+            cpu["port"] = dict(value=n_cpu * S / tp, unit=UNIT, cores=os.cpu_count(),
+                               what="oracle/trace_oracle.py + autograd on the same sample")
+        else:
+            tc = port_step()
+            cpu = dict(value=n_cpu * S / tc, unit=UNIT, cores=os.cpu_count(), kind="port",
+                       sample=f"one forward+backward step of {n_cpu} rays ({tc:.1f} s), eager torch oracle + autograd")
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
