@@ -10,9 +10,9 @@ REP=$OUT/prof_${NAME}_$TAG
 ncu --set full --clock-control none --import-source on -k regex:$KREGEX -s $SKIP -c 1 -f -o $REP $CMD > $OUT/ncu_full_${NAME}_$TAG.log 2>&1
 echo "ncu full $NAME exit $?"
 python scripts/ncu_summary.py $REP.ncu-rep > $OUT/sum_${NAME}_$TAG.txt 2>&1
-python scripts/ncu_by_func.py $REP.ncu-rep $KSUB fast > $OUT/func_${NAME}_$TAG.txt 2>&1
-python scripts/ncu_by_line.py $REP.ncu-rep $KSUB fast 60 --by-samples > $OUT/samples_${NAME}_$TAG.txt 2>&1
-python scripts/ncu_by_line.py $REP.ncu-rep $KSUB fast 60 > $OUT/lines_${NAME}_$TAG.txt 2>&1
+python scripts/ncu_by_func.py $REP.ncu-rep $KSUB ${VARIANT:-fast} > $OUT/func_${NAME}_$TAG.txt 2>&1
+python scripts/ncu_by_line.py $REP.ncu-rep $KSUB ${VARIANT:-fast} 60 --by-samples > $OUT/samples_${NAME}_$TAG.txt 2>&1
+python scripts/ncu_by_line.py $REP.ncu-rep $KSUB ${VARIANT:-fast} 60 > $OUT/lines_${NAME}_$TAG.txt 2>&1
 ncu -i $REP.ncu-rep --page raw --csv 2>/dev/null | python -c "
 import csv,sys
 rows=list(csv.reader(sys.stdin)); h=rows[0]

@@ -428,6 +428,50 @@ def test_maximum_table_size(runner_of, ieee_oracle, rtt_ns, variant):
     assert parity.grad_rel(lean["g_table"][:, C.F_C:C.N_DIFF], bwd["g_table"][:, C.F_C:C.N_DIFF]) < 2e-5
 
 
+@pytest.mark.parametrize("variant", ["exact", "fast"])
+def test_maximum_rows_times_maximum_wavelengths(runner_of, rtt_ns, variant):
+    """The advertised limits together: 64 rows x 8 sample wavelengths (table + index tables + block accumulators need
+    more than the 48 KB default of dynamic shared memory: every launcher opts in).  Forward and adjoint against the
+    oracle with the same index table."""
+    import raytracetorch_b200 as rtt
+    from raytracetorch_b200 import codes as C
+    hs = runner_of(variant)
+    els = _stack_of_singlets(rtt_ns, grads=(0, 20))
+    lams = [400.0 + 50.0 * l for l in range(C.MAX_WAVELENGTHS)]
+    disp = rtt.Dispersion(lams, {els[k].ior_glass: [float(els[k].ior_glass) * (1.0 + 0.002 * (l - 3)) for l in range(len(lams))]
+                                 for k in (0, 7, 20)})
+    tab = rtt.compile_elements(els, dispersion=disp)
+    assert tab.n_rows == C.MAX_ROWS and tab.lut.shape[0] == C.MAX_WAVELENGTHS
+    n = 4096
+    rays = scenes.make_bundle(rtt_ns, ("coll", 9.0, -10.0, [0.01, -0.02, 0.0]), n, 3)
+    wav = torch.tensor(lams)[torch.arange(n) % len(lams)].contiguous()
+    p, dd, inten = (t.clone().requires_grad_(True) for t in (rays.pos, rays.dir, rays.intensity))
+    O.IEEE_SQRT = True
+    try:
+        o = O.trace_sequential(tab.f, tab.i_host, p, dd, inten, wavelength=wav, lut=tab.lut, lut_w=tab.lut_wavelengths)
+    finally:
+        O.IEEE_SQRT = False
+    parity.golden_loss(o["pos"], o["dir"], o["intensity"]).backward()
+    surf = lambda k, j: els[k].shape.surfaces[j].c
+    ref = {(k, j): surf(k, j).grad.clone() for k in (0, 20) for j in (0, 1)}
+    for k, j in ref:
+        surf(k, j).grad = None
+    tab = rtt.compile_elements(els, dispersion=disp)
+    tf, ti = tab.f.detach().numpy(), tab.i.numpy()
+    lut, lut_w = tab.lut.detach().numpy(), tab.lut_wavelengths.numpy()
+    pn, dn, inn = rays.pos.numpy(), rays.dir.numpy(), rays.intensity.numpy()
+    h = hs.trace_seq(tf, ti, pn, dn, inn, wav=wav.numpy(), lut=lut, lut_w=lut_w)
+    np.testing.assert_array_equal(parity.mask_bits(h["hitmask"], 64), o["hit"].numpy())
+    scale = float(np.abs(o["pos"].detach().numpy()).max())
+    assert parity.vec_rel(h["pos"], o["pos"].detach().numpy(), floor=scale).max() <= parity.TOL_POINT
+    gp, gd, gi = parity.golden_loss_grads(h["pos"], h["dir"], h["intensity"])
+    bwd = hs.trace_seq_bwd(tf, ti, pn, dn, inn, h["hitmask"], gp, gd, gi, wav=wav.numpy(), lut=lut, lut_w=lut_w)
+    assert parity.grad_rel(bwd["g_pos"], p.grad.numpy()) < parity.TOL_GRAD
+    tab.f.backward(torch.from_numpy(bwd["g_table"]))
+    for (k, j), g in ref.items():
+        assert parity.grad_rel(surf(k, j).grad.numpy(), g.numpy()) < parity.TOL_GRAD, (k, j)
+
+
 def test_nonseq_adjoint_matches_oracle_autograd(rtt_ns, run_exact, ieee_oracle):
     """Ray gradients on every ray whose hit sequence equals the oracle's; PARAMETER gradients at the same 1e-3 bar
     as the sequential adjoint, on the bundle restricted to those rays (a parameter gradient sums over rays, so a ray
