@@ -971,10 +971,43 @@ def run_gpu_arm(args):
             line["config4"] = config4
         if nonseq_fast:
             line["nonseq_fast"] = nonseq_fast
+        if getattr(args, "return_line", False):
+            return line
+        if args.workload == "c2" and world == 1 and not args.no_other_configs and not args.rays:
+            # the other BASELINE configurations, compact (device-timed forward / optimisation step only), so that the
+            # driver's record of the default run carries a number for every config; full lines: --workload <name>
+            pos = dirs = inten = wav = None
+            torch.cuda.empty_cache()
+            line["other_configs"] = other_config_lines(args)
         emit(line)
     if world > 1:
         tdist.barrier()
         tdist.destroy_process_group()
+
+
+def other_config_lines(args):
+    """Compact lines of C1, C3, C4 and C5 at their BASELINE sizes on this GPU (5 timed steps each, no CPU / e2e legs)."""
+    import copy
+    out = {}
+    for wl in ("c1", "c3", "c4", "c5"):
+        sub = copy.copy(args)
+        sub.workload, sub.steps, sub.warmup = wl, 5, 3
+        sub.no_cpu = sub.no_e2e = sub.no_bwd = sub.no_config4 = sub.no_other_configs = True
+        sub.return_line = True
+        try:
+            ln = run_c3(sub) if wl == "c3" else run_gpu_arm(sub)
+            r = ln["roofline"]
+            out[wl] = dict(workload=ln["config"]["workload"], value=ln["value"], unit=ln["unit"], ms_per_step=ln["ms_per_step"],
+                           steps=ln["steps"], rays_per_gpu=ln["config"].get("rays_per_gpu"), rows=ln["config"].get("rows"),
+                           roofline=dict(bound=r["bound"], frac=r["frac"], frac_reference_work=r.get("frac_reference_work"),
+                                         kernel=r.get("kernel"), kernel_ms=r.get("kernel_ms")),
+                           clocks=ln.get("clocks"), gpu_launches=ln.get("gpu_launches"))
+            if ln.get("nonseq_fast"):
+                out[wl]["nonseq_fast"] = ln["nonseq_fast"]
+        except Exception as exc:                                         # an extra figure must not cost the bench line
+            out[wl] = dict(error=f"{type(exc).__name__}: {exc}")
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_c3(args):
@@ -1158,6 +1191,9 @@ def run_c3(args):
                                   "reference's own GPU flow), so a step has no host input; the loss scalar is read back"))
         if cpu:
             line["cpu_baseline"] = cpu
+        if getattr(args, "return_line", False):
+            graphed = None
+            return line
         emit(line)
     if world > 1:
         graphed = None                     # a captured graph holds NCCL work: release it before the group goes away
@@ -1207,6 +1243,8 @@ def main():
                     help="weak: --rays per GPU (default); strong: the workload's total ray count is split over the ranks")
     ap.add_argument("--no-overlap", action="store_true",
                     help="N > 1: run the image all-reduce on the trace stream instead of a side stream")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="default workload at N = 1 only: skip the compact lines of C1 / C3 / C4 / C5 (other_configs key)")
     ap.add_argument("--no-config4", action="store_true",
                     help="default workload only: skip the extra BASELINE config-4 (camera render) measurement")
     ap.add_argument("--no-graph", action="store_true", help="c3: run the optimisation step eagerly (no CUDA graph)")

@@ -13,7 +13,8 @@ import os
 from typing import Optional, Sequence
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librtt_b200.so")
+# RTT_B200_LIB: an alternative build of librtt_b200.so (A/B experiments, scripts/gpu_ab_lib.sh); default = the in-tree library
+LIB_PATH = os.environ.get("RTT_B200_LIB") or os.path.join(_HERE, "librtt_b200.so")
 
 MODE_FAST, MODE_EXACT = 0, 1
 MODE_SCALAR_GRADS = 0x100   # hint for rtt_trace_seq_bwd (include/rtt_b200.h): no row requests pose gradients

@@ -214,6 +214,9 @@ RTT_HD void prepare_row(RowDev& R) {
         R.i[RTT_I_PHYS] == PHYS && ident == IDENT && (R.i[RTT_I_SENSOR] >= 0) == (SENSOR != 0)) op = OP;
     RTT_ROW_SPECS(RTT_X)
 #undef RTT_X
+#if defined(RTT_EXPERIMENT_GENERIC_ROWS)
+    op = 0;                                                             // A/B build: every row on the generic path
+#endif
     R.i[DI_OPCODE] = op;
 }
 

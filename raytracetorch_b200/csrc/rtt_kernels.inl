@@ -984,7 +984,9 @@ __host__ __device__ inline size_t bwd_queue_bytes() { return sizeof(unsigned sho
 
 // POSE = false: the caller guarantees that no row requests pose gradients (RTT_MODE_SCALAR_GRADS); the pose-gradient
 // outer products and their 24 accumulator registers per row are compiled out.
-template <int MINB, bool POSE>
+// CK = checkpoints a thread can hold = rows of the table rounded up (24 or RTT_MAX_ROWS): a 64-entry frame reserved 1.9 KB of
+// local memory per thread for scenes that never hit more than 17 rows.
+template <int MINB, bool POSE, int CK>
 __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(const __grid_constant__ SeqBwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.tab.S, L = a.tab.L;
@@ -1090,7 +1092,7 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
             if (L > 0) lam = wavelength_index(T, L, ray.wav);
         }
         // ---- forward replay over the recorded interactions (row loop is warp-uniform) ----
-        Checkpoint ck[RTT_MAX_ROWS];
+        Checkpoint ck[CK];
         int nh = 0;
         for (int r = 0; r < S; ++r) {
             const bool hit = (mask >> r) & 1ull;
@@ -1691,11 +1693,16 @@ cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
     RTT_NAME(k_trace_seq_fwd)<<<grid_for(a.n, 8), kThreads, fwd_smem(a.tab.S, a.tab.L), st>>>(a);
     return cudaGetLastError();
 }
+template <int MINB, bool POSE, int CK>
+inline cudaError_t launch_seq_bwd_ck(const SeqBwdArgs& b, int g, size_t smem, cudaStream_t st) {
+    if (cudaError_t e = allow_smem(RTT_NAME(k_trace_seq_bwd)<MINB, POSE, CK>, smem)) return e;
+    RTT_NAME(k_trace_seq_bwd)<MINB, POSE, CK><<<g, kThreads, smem, st>>>(b);
+    return cudaGetLastError();
+}
 template <int MINB, bool POSE>
 inline cudaError_t launch_seq_bwd_as(const SeqBwdArgs& b, int g, size_t smem, cudaStream_t st) {
-    if (cudaError_t e = allow_smem(RTT_NAME(k_trace_seq_bwd)<MINB, POSE>, smem)) return e;
-    RTT_NAME(k_trace_seq_bwd)<MINB, POSE><<<g, kThreads, smem, st>>>(b);
-    return cudaGetLastError();
+    return b.tab.S <= 24 ? launch_seq_bwd_ck<MINB, POSE, 24>(b, g, smem, st)
+                         : launch_seq_bwd_ck<MINB, POSE, RTT_MAX_ROWS>(b, g, smem, st);
 }
 cudaError_t RTT_NAME(launch_seq_bwd)(const SeqBwdArgs& a, cudaStream_t st) {
     const size_t smem = bwd_smem(a.tab.S, a.tab.L) + 8 + bwd_queue_bytes();

@@ -56,6 +56,9 @@ RTT_HD int tile_opcode(const RowDev& R) {
     // specialised HALF-bounded conics assume the usual, non-inverted bound (lean root selection); an inverted one
     // takes the generic path
     if (R.i[RTT_I_BOUND] == RTT_BOUND_HALF && R.i[RTT_I_INVERT] != 0) op = 0;
+#if defined(RTT_EXPERIMENT_GENERIC_ROWS)
+    op = 0;
+#endif
     return op;
 }
 

@@ -4,7 +4,7 @@ set -u
 TAG="${1:-all}"; WLS="${2:-c2 c1 c4 c4cam c5 c3}"
 OUT=gpurun_out; mkdir -p $OUT
 for wl in $WLS; do
-  timeout 600 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu --no-e2e --no-config4 > $OUT/bench_${wl}_$TAG.json 2> $OUT/bench_${wl}_$TAG.err
+  timeout 600 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu --no-e2e --no-config4 --no-other-configs > $OUT/bench_${wl}_$TAG.json 2> $OUT/bench_${wl}_$TAG.err
   echo "$wl exit $? $(python - <<PY
 import json
 try:

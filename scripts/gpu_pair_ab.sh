@@ -8,7 +8,7 @@ timeout 900 python -m pytest tests/test_kernel_parity.py -m gpu -q -x -k "seq_ma
 tail -5 $OUT/pytest_pair_$TAG.log
 for wl in $WLS; do
   for t in $TUNES; do
-    RTT_FWD_TILE=$t timeout 300 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu --no-e2e --no-bwd > $OUT/ab_${wl}_t${t}_$TAG.json 2> $OUT/ab_${wl}_t${t}_$TAG.err
+    RTT_FWD_TILE=$t timeout 300 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu --no-e2e --no-bwd --no-config4 --no-other-configs > $OUT/ab_${wl}_t${t}_$TAG.json 2> $OUT/ab_${wl}_t${t}_$TAG.err
     echo "$wl tune $t exit $? $(python -c "import json,sys; d=json.load(open('$OUT/ab_${wl}_t${t}_$TAG.json')); r=d['roofline']; print('ms_per_step', round(d['ms_per_step'],3), 'kernel_ms', round(r['kernel_ms'],3), 'frac', round(r['frac'],3), 'clk', d['clocks'].get('sm_mhz'))" 2>&1 | tail -1)"
   done
 done

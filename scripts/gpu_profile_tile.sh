@@ -5,7 +5,7 @@ set -u
 TAG="$1"; WL="$2"; TILE="$3"; RAYS="${4:-20000000}"; KEEP="${5:-0}"; KSUB="${6:-k_trace_seq_fwd}"
 OUT=gpurun_out; mkdir -p $OUT
 export RTT_FWD_TILE=$TILE
-CMD="python bench.py --workload $WL --rays $RAYS --steps 2 --warmup 1 --no-e2e --no-cpu --no-bwd --no-config4"
+CMD="python bench.py --workload $WL --rays $RAYS --steps 2 --warmup 1 --no-e2e --no-cpu --no-bwd --no-config4 --no-other-configs"
 $CMD > $OUT/plain_${WL}_t${TILE}_$TAG.log 2>&1 || { echo "plain run failed"; tail -20 $OUT/plain_${WL}_t${TILE}_$TAG.log; exit 1; }
 REP=$OUT/prof_${WL}_t${TILE}_$TAG
 ncu --set full --clock-control none --import-source on -k regex:k_trace_seq_fwd -s 3 -c 1 -f -o $REP $CMD > $OUT/ncu_full_${WL}_t${TILE}_$TAG.log 2>&1
