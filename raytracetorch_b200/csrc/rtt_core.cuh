@@ -37,6 +37,14 @@ RTT_HD float rcp_(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r)
 RTT_HD float sqrt_(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 RTT_HD float div_(float a, float b) { return a * rcp_(b); }
 RTT_HD float rsqrt_(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#elif defined(RTT_OUTLINE_IEEE) && defined(__CUDA_ARCH__)
+// EXACT device build with the IEEE division / square root sequences (~15 instructions + a slow-path call each, at
+// ~60 sites of the non-sequential kernel) behind ONE out-of-line copy each: smaller code for the instruction cache.
+__device__ __noinline__ float rtt_ieee_div(float a, float b) { return a / b; }
+__device__ __noinline__ float rtt_ieee_sqrt(float x) { return sqrtf(x); }
+RTT_HD float rcp_(float x) { return rtt_ieee_div(1.0f, x); }
+RTT_HD float sqrt_(float x) { return rtt_ieee_sqrt(x); }
+RTT_HD float div_(float a, float b) { return rtt_ieee_div(a, b); }
 #else
 RTT_HD float rcp_(float x) { return 1.0f / x; }
 RTT_HD float sqrt_(float x) { return sqrtf(x); }
@@ -178,7 +186,7 @@ RTT_HD V3 div3(V3 v, float s) {
     const float r = rcp_(s);
     return v3(v.x * r, v.y * r, v.z * r);
 #else
-    return v3(v.x / s, v.y / s, v.z / s);
+    return v3(div_(v.x, s), div_(v.y, s), div_(v.z, s));
 #endif
 }
 
