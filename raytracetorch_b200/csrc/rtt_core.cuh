@@ -763,19 +763,8 @@ RTT_HD void source_ray(const SRC& s, SourceKey k, long long i, V3& p, V3& d) {
         default: {                                                      // RTT_SRC_CAMERA: render/camera.py:39-72
             const long long npix = (long long)s.width * s.height;
             const long long g = (long long)ctr;
-            long long smp;
-            int px, py;
-            if (ctr <= 0xffffffffull && npix <= 0x7fffffffll) {
-                // renders below 2^32 rays (every BASELINE size): 32-bit divisions, a fraction of the 64-bit ones' cost
-                const unsigned g32 = (unsigned)ctr, np32 = (unsigned)npix;
-                const unsigned sm32 = g32 / np32, pix32 = g32 - sm32 * np32;
-                const unsigned py32 = pix32 / (unsigned)s.width;
-                smp = sm32; py = (int)py32; px = (int)(pix32 - py32 * (unsigned)s.width);
-            } else {
-                const long long pix = g % npix;
-                smp = g / npix;
-                px = (int)(pix % s.width); py = (int)(pix / s.width);
-            }
+            const long long pix = g % npix, smp = g / npix;
+            const int px = (int)(pix % s.width), py = (int)(pix / s.width);
             float x = linspace_at(-s.a[0], s.a[0], s.width, px);
             float y = linspace_at(s.a[1], -s.a[1], s.height, py);
             if (smp > 0) {                                              // extension: jittered sub-pixel samples
