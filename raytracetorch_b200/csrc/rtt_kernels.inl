@@ -123,6 +123,23 @@ __device__ __forceinline__ RayIn fetch_ray(const Args& a, SourceKey key, long lo
     }
     return r;
 }
+// GEN fixed at compile time: the kernel build for rays in memory carries no ray-source code (Philox, sincosf, acosf,
+// camera pixel math — several hundred instructions per fetch site) and the build for generated rays no ray loads.
+// The dead half was never executed, but it changed the register allocation and the layout of the hot loop: a cold edit
+// inside source_ray moved the tile kernel by 6 % on C4 (profiles/r2_fwd_pair_ab.md).
+template <bool GEN, class Args>
+__device__ __forceinline__ RayIn fetch_ray_t(const Args& a, SourceKey key, long long i, bool want_wav) {
+    RayIn r;
+    if (GEN) {
+        source_ray(a.src, key, i, r.p, r.d);
+        r.I = a.src.intensity; r.wav = a.src.wavelength;
+    } else {
+        r.p = load3(a.pos, i); r.d = load3(a.dir, i);
+        r.I = a.inten[i];
+        r.wav = want_wav ? a.wav[i] : 0.0f;
+    }
+    return r;
+}
 template <class Args>
 __device__ __forceinline__ SourceKey fetch_key(const Args& a) {
     SourceKey k; k.key = 0ull; k.base = 0ull;
@@ -372,7 +389,7 @@ __device__ __forceinline__ void tile_row(const SmemTable& T, int S, int L, int r
     }
 }
 
-template <int RPT, int MINB>
+template <int RPT, int MINB, bool GEN>
 __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_tile(const __grid_constant__ SeqFwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.tab.S, L = a.tab.L;
@@ -382,7 +399,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_tile(const __g
     img_cache_init(cache);
     stage_table(a.tab, T);
     stage_tile(T, S, xf);
-    const SourceKey skey = fetch_key(a);
+    SourceKey skey; skey.key = 0ull; skey.base = 0ull;
+    if (GEN) skey = source_key(a.src);
     const long long tile = (long long)kThreads * RPT;
     for (long long base = (long long)blockIdx.x * tile; base < a.n; base += (long long)gridDim.x * tile) {
         const long long i0 = base + threadIdx.x;
@@ -397,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_tile(const __g
             p[j] = v3(0.0f, 0.0f, 0.0f); d[j] = v3(0.0f, 0.0f, 0.0f); I[j] = 0.0f; lam[j] = 0; mask[j] = 0ull;
             act[j] = false; odd[j] = false;
             if (i < a.n) {
-                const RayIn ray = fetch_ray(a, skey, i, L > 0);
+                const RayIn ray = fetch_ray_t<GEN>(a, skey, i, L > 0);
                 p[j] = ray.p; d[j] = ray.d; I[j] = ray.I;
                 lam[j] = (L > 0) ? wavelength_index(T, L, ray.wav) : 0;
                 act[j] = finite_ray(ray.p, ray.d) && regular_dir(ray.d);
@@ -439,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_tile(const __g
             const long long i = i0 + (long long)j * kThreads;
             if (odd[j]) {
                 // un-normalised direction: walk in the reference's order; NaN / inf ray: hits nothing, stays as it was
-                const RayIn ray = fetch_ray(a, skey, i, L > 0);
+                const RayIn ray = fetch_ray_t<GEN>(a, skey, i, L > 0);
                 WalkState w;
                 w.p = ray.p; w.d = ray.d; w.I = ray.I; w.mask = 0ull;
                 if (finite_ray(ray.p, ray.d)) w = seq_walk_generic(a, lam[j], i, w);
@@ -592,7 +610,7 @@ __device__ __forceinline__ unsigned pair_row_generic(const SmemTable& T, int S, 
     return pair_row_scalar<K>(T.rows, r, P, D, I, act, mu_enter, mu_exit, aux_a, aux_b, dep);
 }
 
-template <int MINB, bool STREAM, int LOG, int NP>
+template <int MINB, bool STREAM, int LOG, int NP, bool GEN>
 __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __grid_constant__ SeqFwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef PairLayout<LOG, STREAM, NP> LY;
@@ -631,7 +649,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
     img_cache_init(cache);
     stage_table(a.tab, T);
     stage_tile(T, S, xf);
-    const SourceKey skey = fetch_key(a);
+    SourceKey skey; skey.key = 0ull; skey.base = 0ull;
+    if (GEN) skey = source_key(a.src);
 
     unsigned k = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
@@ -674,7 +693,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
                 pin[j] = v3(0.0f, 0.0f, 0.0f); din[j] = v3(0.0f, 0.0f, 0.0f); Iin[j] = 0.0f; lamS[q][j] = 0;
                 if (loc < cnt) {
                     const RayIn ray = STREAM ? slot_ray<NP>(slot, loc, use_wav)
-                                             : fetch_ray(a, skey, (long long)tile * GE::kTile + loc, use_wav);
+                                             : fetch_ray_t<GEN>(a, skey, (long long)tile * GE::kTile + loc, use_wav);
                     pin[j] = ray.p; din[j] = ray.d; Iin[j] = ray.I;
                     lamS[q][j] = use_wav ? wavelength_index(T, L, ray.wav) * S : 0;
                     if (finite_ray(ray.p, ray.d) && regular_dir(ray.d)) actb[q] |= 1u << j;
@@ -793,7 +812,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
                     // un-normalised direction: walk in the reference's order; NaN / inf ray: hits nothing, stays as it was
                     // (the slot still holds this ray's inputs: a thread only ever writes its own entries)
                     const long long i = (long long)tile * GE::kTile + loc;
-                    const RayIn ray = STREAM ? slot_ray<NP>(slot, loc, use_wav) : fetch_ray(a, skey, i, use_wav);
+                    const RayIn ray = STREAM ? slot_ray<NP>(slot, loc, use_wav) : fetch_ray_t<GEN>(a, skey, i, use_wav);
                     WalkState w;
                     w.p = ray.p; w.d = ray.d; w.I = ray.I; w.mask = 0ull;
                     if (finite_ray(ray.p, ray.d))
@@ -1617,18 +1636,22 @@ inline cudaError_t allow_smem(Kern kern, size_t bytes) {
 }
 
 #if defined(RTT_APPROX)
-template <int RPT, int MINB>
-inline cudaError_t launch_tile(const SeqFwdArgs& a, cudaStream_t st) {
+template <int RPT, int MINB, bool GEN>
+inline cudaError_t launch_tile_g(const SeqFwdArgs& a, cudaStream_t st) {
     const size_t smem = tile_smem_bytes(a.tab.S, a.tab.L);
-    if (cudaError_t e = allow_smem(k_trace_seq_fwd_tile<RPT, MINB>, smem)) return e;
+    if (cudaError_t e = allow_smem(k_trace_seq_fwd_tile<RPT, MINB, GEN>, smem)) return e;
     const long long tiles = (a.n + (long long)kThreads * RPT - 1) / ((long long)kThreads * RPT);
     // several waves of grid-striding blocks: a block that lands on a busier SM costs 1/kWaves of a launch
     constexpr int kWaves = 4;
     long long g = (long long)sm_count() * MINB * kWaves;
     if (tiles < g) g = tiles;
     if (g < 1) g = 1;
-    k_trace_seq_fwd_tile<RPT, MINB><<<(int)g, kThreads, smem, st>>>(a);
+    k_trace_seq_fwd_tile<RPT, MINB, GEN><<<(int)g, kThreads, smem, st>>>(a);
     return cudaGetLastError();
+}
+template <int RPT, int MINB>
+inline cudaError_t launch_tile(const SeqFwdArgs& a, cudaStream_t st) {
+    return a.src.kind >= 0 ? launch_tile_g<RPT, MINB, true>(a, st) : launch_tile_g<RPT, MINB, false>(a, st);
 }
 // Which build of the frame-resident forward kernel runs (a.tune, include/rtt_b200.h RTT_MODE_TUNE_*): 1 = 1 ray/thread,
 // 2 = 2 rays (80 regs), 3 = 2 rays (64 regs), 5 = 1 ray at 48 registers / five blocks per SM (C1 -4 %, C2 +3 %, C4 +9 %
@@ -1641,18 +1664,23 @@ inline cudaError_t launch_tile(const SeqFwdArgs& a, cudaStream_t st) {
 // generated in the kernel and its materialised twin run the same build and stay bit-identical (tests/test_goals.py).
 inline int fwd_tile_for(int S, int tune) { return tune ? tune : (S <= 6 ? 5 : 3); }   // 0 is resolved by the caller (fwd_default_build)
 
-template <int MINB, bool STREAM, int LOG, int NP = 1>
-inline cudaError_t launch_pair(const SeqFwdArgs& a, cudaStream_t st) {
+template <int MINB, bool STREAM, int LOG, int NP, bool GEN>
+inline cudaError_t launch_pair_g(const SeqFwdArgs& a, cudaStream_t st) {
     const size_t smem = PairLayout<LOG, STREAM, NP>::bytes(a.tab.S, a.tab.L);
-    if (cudaError_t e = allow_smem(k_trace_seq_fwd_pair<MINB, STREAM, LOG, NP>, smem)) return e;
+    if (cudaError_t e = allow_smem(k_trace_seq_fwd_pair<MINB, STREAM, LOG, NP, GEN>, smem)) return e;
     const long long tiles = (a.n + PairGeom<NP>::kTile - 1) / PairGeom<NP>::kTile;
     // persistent blocks, one resident set (tiles are handed out round-robin: tile = block + k * grid); the plain build
     // keeps the tile kernel's four waves (a block that lands on a busier SM costs 1/4 of a launch)
     long long g = (long long)sm_count() * MINB * (STREAM ? 1 : 4);
     if (tiles < g) g = tiles;
     if (g < 1) g = 1;
-    k_trace_seq_fwd_pair<MINB, STREAM, LOG, NP><<<(int)g, kThreads, smem, st>>>(a);
+    k_trace_seq_fwd_pair<MINB, STREAM, LOG, NP, GEN><<<(int)g, kThreads, smem, st>>>(a);
     return cudaGetLastError();
+}
+template <int MINB, bool STREAM, int LOG, int NP = 1>
+inline cudaError_t launch_pair(const SeqFwdArgs& a, cudaStream_t st) {
+    if (STREAM) return launch_pair_g<MINB, STREAM, LOG, NP, false>(a, st);            // streams rays from memory by construction
+    return a.src.kind >= 0 ? launch_pair_g<MINB, false, LOG, NP, true>(a, st) : launch_pair_g<MINB, false, LOG, NP, false>(a, st);
 }
 // bulk-async copies need 16-byte aligned global addresses; every full tile starts a multiple of 512 rays into the
 // arrays, so the base pointers decide.  Generated rays have no input to stream.
