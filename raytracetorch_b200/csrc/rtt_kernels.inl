@@ -22,6 +22,7 @@
 #include "rtt_core.cuh"
 #include "rtt_tile.cuh"
 #include "rtt_pair.cuh"
+#include "rtt_lean.cuh"
 #include "rtt_kernels_decl.h"
 
 namespace rtt {
@@ -1005,7 +1006,10 @@ __host__ __device__ inline size_t bwd_queue_bytes() { return sizeof(unsigned sho
 // outer products and their 24 accumulator registers per row are compiled out.
 // CK = checkpoints a thread can hold = rows of the table rounded up (24 or RTT_MAX_ROWS): a 64-entry frame reserved 1.9 KB of
 // local memory per thread for scenes that never hit more than 17 rows.
-template <int MINB, bool POSE, int CK>
+// LEAN (FAST build, POSE = false, no input-ray gradients): rays whose every interaction is a lens face, a stop or a sensor
+// take the frame-resident replay / reverse steps of rtt_lean.cuh; the rest of the queue runs the general code below.
+// GEN: 0 = rays from memory or from the ray source (run-time test), 1 = memory only, 2 = generated only (see fetch_ray_t).
+template <int MINB, bool POSE, int CK, bool LEAN, int GEN>
 __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(const __grid_constant__ SeqBwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.tab.S, L = a.tab.L;
@@ -1016,6 +1020,12 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
     unsigned short* queue = reinterpret_cast<unsigned short*>(qcount + 2);
     for (int idx = threadIdx.x; idx < S * RTT_ROW_G + L * S * 2; idx += blockDim.x) acc[idx] = 0.0f;
     stage_table(a.tab, T);
+#if defined(RTT_APPROX)
+    // lean path: frame changes between the rows (rtt_tile.cuh) behind the queue, then the mask of lean rows (two words)
+    Xf* xf = reinterpret_cast<Xf*>(reinterpret_cast<unsigned char*>(queue) + bwd_queue_bytes());
+    unsigned* lean_words = reinterpret_cast<unsigned*>(xf + (S + 1));
+    if (LEAN) stage_tile(T, S, xf);
+#endif
 
     // Private gradient accumulators: rows whose requested gradients are scalars only (c, k, radius, indices —
     // the usual lens-design variables) add into per-thread slots (local memory, L1) ray after ray and are reduced
@@ -1029,14 +1039,39 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
                                      !(L > 0 && (fl & RTT_FLAG_GRAD_IOR));
             T.rows[r].f[D_ACC_SLOT] = (a.g_table && scalar_only && used < kAccRows) ? (float)(used++) : -1.0f;
         }
+#if defined(RTT_APPROX)
+        if (LEAN) {
+            // a row is lean when it has a lean step (rtt_lean.cuh) and its requested gradients — pose requests are
+            // ignored in this build — all go to private slots
+            unsigned long long lean = 0ull;
+            for (int r = 0; r < S; ++r) {
+                const int fl = a.g_table ? (T.rows[r].i[RTT_I_FLAGS] & ~(RTT_FLAG_GRAD_POSE_E | RTT_FLAG_GRAD_POSE_S)) : 0;
+                if (lean_tile_op(T.rows[r].i[DI_TILE_OP]) && (fl == 0 || T.rows[r].f[D_ACC_SLOT] >= 0.0f)) lean |= 1ull << r;
+            }
+            lean_words[0] = (unsigned)lean; lean_words[1] = (unsigned)(lean >> 32);
+            // the lean walk visits only the rows that matter to a lean ray: lean rows and frame changes.
+            // word = row | tile opcode << 8 | frame-change kind << 16 | lean << 24
+            int nw = 0;
+            for (int r = 0; r < S; ++r) {
+                const unsigned is_lean = (unsigned)((lean >> r) & 1ull);
+                if (is_lean || xf[r].kind != 0)
+                    lean_words[3 + nw++] = (unsigned)r | ((unsigned)T.rows[r].i[DI_TILE_OP] << 8) | ((unsigned)xf[r].kind << 16) | (is_lean << 24);
+            }
+            lean_words[2] = (unsigned)nw;
+        }
+#endif
     }
     __syncthreads();
+#if defined(RTT_APPROX)
+    const unsigned long long lean_rows = LEAN ? (((unsigned long long)lean_words[1] << 32) | lean_words[0]) : 0ull;
+#endif
     float pacc[kAccRows * kAccPerRow];
 #pragma unroll
     for (int e = 0; e < kAccRows * kAccPerRow; ++e) pacc[e] = 0.0f;
 
     const bool compact = !a.g_pos && !a.g_dir && !a.g_inten;
-    const SourceKey skey = fetch_key(a);
+    SourceKey skey; skey.key = 0ull; skey.base = 0ull;
+    if (GEN == 2 || (GEN == 0 && a.src.kind >= 0)) skey = source_key(a.src);
     const int chunk = a.chunk;
     for (long long base = (long long)blockIdx.x * chunk; base < a.n; base += (long long)gridDim.x * chunk) {
       int count = (int)((a.n - base) < (long long)chunk ? (a.n - base) : (long long)chunk);
@@ -1106,13 +1141,98 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
         int lam = 0;
         if (live) {
             mask = a.hitmask[i];
-            const RayIn ray = fetch_ray(a, skey, i, L > 0);
+            const RayIn ray = GEN == 0 ? fetch_ray(a, skey, i, L > 0) : fetch_ray_t<GEN == 2>(a, skey, i, L > 0);
             p = ray.p; d = ray.d;
             if (L > 0) lam = wavelength_index(T, L, ray.wav);
         }
-        // ---- forward replay over the recorded interactions (row loop is warp-uniform) ----
         Checkpoint ck[CK];
         int nh = 0;
+#if defined(RTT_APPROX)
+        if (LEAN) {
+            // ---- lean rays: frame-resident replay + reverse (rtt_lean.cuh); 7 words per interaction in the same frame ----
+            constexpr int kLeanHits = CK * 6 / kLeanCkWords;
+            const bool lean_ray = live && mask != 0ull && (mask & ~lean_rows) == 0ull && __popcll(mask) <= kLeanHits &&
+                                  finite_ray(p, d) && regular_dir(d);
+            if (__any_sync(kFull, lean_ray)) {
+                float* ckw = reinterpret_cast<float*>(ck);
+                const unsigned m_lo = lean_ray ? (unsigned)mask : 0u, m_hi = lean_ray ? (unsigned)(mask >> 32) : 0u;
+                const int nwalk = (int)lean_words[2];
+                const int lamS = lam * S;
+                V3 lp = p, ld = d;
+                for (int k = 0; k < nwalk; ++k) {
+                    const unsigned w = lean_words[3 + k];                // warp-uniform
+                    const int r = (int)(w & 0xffu);
+                    if (w & 0xff0000u) apply_xf(xf[r], lp, ld);
+                    if (((((r & 32) ? m_hi : m_lo) >> (r & 31)) & 1u) && (w >> 24)) {
+                        const RowDev& R = T.rows[r];
+                        const int op = (int)((w >> 8) & 0xffu);
+                        LeanCk c;
+                        if (op == 1 || op == 4) {
+                            const float2 m = (L > 0) ? T.mu[lamS + r] : *reinterpret_cast<const float2*>(R.f + D_MU_ENTER);
+                            if (op == 1) lean_face_replay<true>(R, m.x, m.y, lp, ld, c);
+                            else lean_face_replay<false>(R, m.x, m.y, lp, ld, c);
+                        } else {
+                            lean_plane_replay(R, op, lp, ld, c);
+                        }
+                        lean_ck_store(ckw + kLeanCkWords * nh, c);
+                        ++nh;
+                    }
+                }
+                V3 gp = v3(0, 0, 0), gd = v3(0, 0, 0);
+                if (lean_ray) {
+                    if (a.g_opos) gp = load3(a.g_opos, i);
+                    if (a.g_odir) gd = load3(a.g_odir, i);
+                }
+                lean_xf_transpose(xf[S], gp, gd);                        // global frame -> frame of the last row
+                for (int k = nwalk - 1; k >= 0; --k) {
+                    const unsigned w = lean_words[3 + k];
+                    const int r = (int)(w & 0xffu);
+                    if (((((r & 32) ? m_hi : m_lo) >> (r & 31)) & 1u) && (w >> 24)) {
+                        --nh;
+                        const LeanCk c = lean_ck_load(ckw + kLeanCkWords * nh);
+                        const RowDev& R = T.rows[r];
+                        const int op = (int)((w >> 8) & 0xffu);
+                        if (op == 1 || op == 4) {
+                            const int flags = a.g_table ? R.i[RTT_I_FLAGS] : 0;
+                            const int slot = (int)R.f[D_ACC_SLOT];
+                            // the private slots are read before the arithmetic and written after it: the local-memory
+                            // round trip hides behind the reverse step
+                            float* pa = pacc + (slot >= 0 ? slot : 0) * kAccPerRow;
+                            float g5[kAccPerRow] = {pa[0], pa[1], 0.0f, pa[3], pa[4]};
+                            float mu_enter, mu_exit, ni, no;
+                            if (L > 0) {
+                                const float2 m = T.mu[lamS + r];
+                                mu_enter = m.x; mu_exit = m.y; ni = T.lut_ni[lamS + r]; no = T.lut_no[lamS + r];
+                            } else {
+                                mu_enter = R.f[D_MU_ENTER]; mu_exit = R.f[D_MU_EXIT]; ni = R.f[RTT_F_IOR_IN]; no = R.f[RTT_F_IOR_OUT];
+                            }
+                            if (op == 1) lean_face_reverse<true>(R, mu_enter, mu_exit, ni, no, c, gp, gd, flags, g5);
+                            else lean_face_reverse<false>(R, mu_enter, mu_exit, ni, no, c, gp, gd, flags, g5);
+                            if (slot >= 0) {
+                                if (flags & RTT_FLAG_GRAD_CK) { pa[0] = g5[0]; pa[1] = g5[1]; }
+                                if (flags & RTT_FLAG_GRAD_IOR) { pa[3] = g5[3]; pa[4] = g5[4]; }
+                            }
+                        } else {
+                            V3 g_hl = v3(0, 0, 0);
+                            if (op != 7) {
+                                const int slot = R.i[RTT_I_SENSOR];
+                                if (slot >= 0 && slot < a.n_sens && a.g_record[slot]) {
+                                    const float4 gr = reinterpret_cast<const float4*>(a.g_record[slot])[i];
+                                    g_hl = v3(gr.x, gr.y, gr.z);
+                                }
+                            }
+                            lean_plane_reverse(R, op, c, g_hl, gp, gd);
+                        }
+                    }
+                    if (((w >> 16) & 0xffu) == 2u) lean_xf_transpose(xf[r], gp, gd);   // frame of row r -> frame of row r - 1
+                }
+                nh = 0;
+            }
+            if (lean_ray) mask = 0ull;                                   // done: the general loops below skip this lane
+            if (!__any_sync(kFull, mask != 0ull)) continue;
+        }
+#endif
+        // ---- forward replay over the recorded interactions (row loop is warp-uniform) ----
         for (int r = 0; r < S; ++r) {
             const bool hit = (mask >> r) & 1ull;
             if (__ballot_sync(kFull, hit) == 0u) continue;
@@ -1721,19 +1841,26 @@ cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
     RTT_NAME(k_trace_seq_fwd)<<<grid_for(a.n, 8), kThreads, fwd_smem(a.tab.S, a.tab.L), st>>>(a);
     return cudaGetLastError();
 }
-template <int MINB, bool POSE, int CK>
+template <int MINB, bool POSE, int CK, bool LEAN, int GEN>
 inline cudaError_t launch_seq_bwd_ck(const SeqBwdArgs& b, int g, size_t smem, cudaStream_t st) {
-    if (cudaError_t e = allow_smem(RTT_NAME(k_trace_seq_bwd)<MINB, POSE, CK>, smem)) return e;
-    RTT_NAME(k_trace_seq_bwd)<MINB, POSE, CK><<<g, kThreads, smem, st>>>(b);
+    if (cudaError_t e = allow_smem(RTT_NAME(k_trace_seq_bwd)<MINB, POSE, CK, LEAN, GEN>, smem)) return e;
+    RTT_NAME(k_trace_seq_bwd)<MINB, POSE, CK, LEAN, GEN><<<g, kThreads, smem, st>>>(b);
     return cudaGetLastError();
 }
 template <int MINB, bool POSE>
 inline cudaError_t launch_seq_bwd_as(const SeqBwdArgs& b, int g, size_t smem, cudaStream_t st) {
-    return b.tab.S <= 24 ? launch_seq_bwd_ck<MINB, POSE, 24>(b, g, smem, st)
-                         : launch_seq_bwd_ck<MINB, POSE, RTT_MAX_ROWS>(b, g, smem, st);
+    return b.tab.S <= 24 ? launch_seq_bwd_ck<MINB, POSE, 24, false, 0>(b, g, smem, st)
+                         : launch_seq_bwd_ck<MINB, POSE, RTT_MAX_ROWS, false, 0>(b, g, smem, st);
 }
+#if defined(RTT_APPROX)
+template <int GEN>
+inline cudaError_t launch_seq_bwd_lean(const SeqBwdArgs& b, int g, size_t smem, cudaStream_t st) {
+    return b.tab.S <= 24 ? launch_seq_bwd_ck<4, false, 24, true, GEN>(b, g, smem, st)
+                         : launch_seq_bwd_ck<4, false, RTT_MAX_ROWS, true, GEN>(b, g, smem, st);
+}
+#endif
 cudaError_t RTT_NAME(launch_seq_bwd)(const SeqBwdArgs& a, cudaStream_t st) {
-    const size_t smem = bwd_smem(a.tab.S, a.tab.L) + 8 + bwd_queue_bytes();
+    size_t smem = bwd_smem(a.tab.S, a.tab.L) + 8 + bwd_queue_bytes();
     // chunk: as large as the queue allows, but small launches still spread over every resident block slot
     const long long slots = (long long)(sm_count() > 0 ? sm_count() : 1) * 4 * 2;
     long long chunk = ((a.n + slots - 1) / slots + kThreads - 1) / kThreads * kThreads;
@@ -1745,14 +1872,21 @@ cudaError_t RTT_NAME(launch_seq_bwd)(const SeqBwdArgs& a, cudaStream_t st) {
     long long g = (long long)sm_count() * 8;
     if (chunks < g) g = chunks;
     if (g < 1) g = 1;
-    // a.tune = resident blocks per SM the build is compiled for.  Without pose gradients the kernel needs 64-72
+    // a.tune & 7 = resident blocks per SM the build is compiled for.  Without pose gradients the kernel needs 64-72
     // registers: four resident blocks (measured: C2 -10 %, C4 -5 % against three); with them three blocks (80 registers,
-    // a few spills) beat two (~110 registers) by 4-8 %.
+    // a few spills) beat two (~110 registers) by 4-8 %.  a.tune & 8: no lean path (every ray through the general code).
+    const int minb = a.tune & 7;
     if (a.scalar_grads) {
-        if (a.tune == 3) return launch_seq_bwd_as<3, false>(b, (int)g, smem, st);
+#if defined(RTT_APPROX)
+        if (!(a.tune & 8) && minb != 3 && !a.g_pos && !a.g_dir && !a.g_inten) {
+            smem += sizeof(Xf) * (size_t)(a.tab.S + 1) + sizeof(unsigned) * (size_t)(a.tab.S + 4);   // frame changes, lean mask, walk list
+            return a.src.kind >= 0 ? launch_seq_bwd_lean<2>(b, (int)g, smem, st) : launch_seq_bwd_lean<1>(b, (int)g, smem, st);
+        }
+#endif
+        if (minb == 3) return launch_seq_bwd_as<3, false>(b, (int)g, smem, st);
         return launch_seq_bwd_as<4, false>(b, (int)g, smem, st);
     }
-    if (a.tune == 2) return launch_seq_bwd_as<2, true>(b, (int)g, smem, st);
+    if (minb == 2) return launch_seq_bwd_as<2, true>(b, (int)g, smem, st);
     return launch_seq_bwd_as<3, true>(b, (int)g, smem, st);
 }
 cudaError_t RTT_NAME(launch_nonseq_fwd)(const NonseqFwdArgs& a, cudaStream_t st) {

@@ -97,7 +97,7 @@ class GpuSim(SourceGoalMixin):
                     sensors=[(self._np(r), self._np(i), self._np(c)) for r, i, c in keep])
 
     def trace_seq_bwd(self, tf, ti, pos, dir_, inten, mask, g_pos, g_dir, g_int, wav=None, lut=None, lut_w=None,
-                      g_records=None, hint=0):
+                      g_records=None, hint=0, need_rays=True):
         pos, dir_, inten, wav = _dev(pos), _dev(dir_), _dev(inten), _dev(wav)
         g_pos, g_dir, g_int = _dev(g_pos), _dev(g_dir), _dev(g_int)
         mask = _dev(np.asarray(mask).view(np.int64), torch.int64)
@@ -110,7 +110,8 @@ class GpuSim(SourceGoalMixin):
         ns = len(g_records)
         rec_arr = (ct.c_void_p * ns)(*[_p(g) or None for g in g_records]) if ns else None
         self.lib.call("rtt_trace_seq_bwd", _p(pos), _p(dir_), _p(inten), _p(wav), None, _p(mask),
-                      _p(g_pos), _p(g_dir), _p(g_int), rec_arr, _p(gp), _p(gd), _p(gi), _p(gt), _p(gl),
+                      _p(g_pos), _p(g_dir), _p(g_int), rec_arr,
+                      _p(gp) if need_rays else 0, _p(gd) if need_rays else 0, _p(gi) if need_rays else 0, _p(gt), _p(gl),
                       ct.byref(req), ns, n, self.mode | hint, self._stream())
         torch.cuda.synchronize()
         return dict(g_pos=self._np(gp), g_dir=self._np(gd), g_intensity=self._np(gi), g_table=self._np(gt),

@@ -36,8 +36,9 @@ def build(variant: str = "exact") -> "HostSim":
     core = os.path.join(_HERE, "..", "..", "raytracetorch_b200", "csrc", "rtt_core.cuh")
     tile = os.path.join(_HERE, "..", "..", "raytracetorch_b200", "csrc", "rtt_tile.cuh")
     pair = os.path.join(_HERE, "..", "..", "raytracetorch_b200", "csrc", "rtt_pair.cuh")
+    lean = os.path.join(_HERE, "..", "..", "raytracetorch_b200", "csrc", "rtt_lean.cuh")
     hdr = os.path.join(_HERE, "..", "..", "include", "rtt_b200.h")
-    newest = max(os.path.getmtime(p) for p in (src, core, tile, pair, hdr, __file__))
+    newest = max(os.path.getmtime(p) for p in (src, core, tile, pair, lean, hdr, __file__))
     if not os.path.exists(out) or os.path.getmtime(out) < newest:
         cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fno-fast-math", *_FLAGS[variant], src, "-o", out]
         subprocess.run(cmd, check=True)
@@ -106,7 +107,7 @@ class HostSim(SourceGoalMixin):
         return dict(pos=op, dir=od, intensity=oi, hitmask=mask, sensors=keep)
 
     def trace_seq_bwd(self, tf, ti, pos, dir_, inten, mask, g_pos, g_dir, g_int, wav=None, lut=None, lut_w=None,
-                      g_records=None, hint=0):
+                      g_records=None, hint=0, need_rays=True):
         pos, dir_, inten, wav = _f32(pos), _f32(dir_), _f32(inten), _f32(wav)
         g_pos, g_dir, g_int = _f32(g_pos), _f32(g_dir), _f32(g_int)
         n = pos.shape[0]
@@ -118,7 +119,8 @@ class HostSim(SourceGoalMixin):
         ns = len(g_records)
         rec_arr = (ct.c_void_p * max(ns, 1))(*[_p(g) or None for g in g_records]) if ns else None
         self.lib.call("rtt_trace_seq_bwd", _p(pos), _p(dir_), _p(inten), _p(wav), None, _p(mask),
-                      _p(g_pos), _p(g_dir), _p(g_int), rec_arr, _p(gp), _p(gd), _p(gi), _p(gt), _p(gl),
+                      _p(g_pos), _p(g_dir), _p(g_int), rec_arr,
+                      _p(gp) if need_rays else 0, _p(gd) if need_rays else 0, _p(gi) if need_rays else 0, _p(gt), _p(gl),
                       ct.byref(req), ns, n, hint, None)
         return dict(g_pos=gp, g_dir=gd, g_intensity=gi, g_table=gt, g_lut=gl)
 

@@ -15,6 +15,7 @@
 #include "../../raytracetorch_b200/csrc/rtt_core.cuh"
 #include "../../raytracetorch_b200/csrc/rtt_tile.cuh"
 #include "../../raytracetorch_b200/csrc/rtt_pair.cuh"
+#include "../../raytracetorch_b200/csrc/rtt_lean.cuh"
 
 using namespace rtt;
 
@@ -285,12 +286,88 @@ int rtt_trace_seq_bwd(const float* in_pos, const float* in_dir, const float*,
     // RTT_MODE_SCALAR_GRADS: pose-gradient requests are ignored (include/rtt_b200.h)
     const int flag_mask = (mode & RTT_MODE_SCALAR_GRADS) ? ~(RTT_FLAG_GRAD_POSE_E | RTT_FLAG_GRAD_POSE_S) : ~0;
     std::vector<Ck> ck(RTT_MAX_ROWS);
+#ifdef RTT_HOST_TILE
+    // mirror of the LEAN path of k_trace_seq_bwd (FAST build, scalar gradients, no input-ray gradients; mode tune bit 8
+    // switches it off): rays whose every interaction is a lean row take the frame-resident steps of rtt_lean.cuh
+    const bool lean_on = (mode & RTT_MODE_SCALAR_GRADS) && !g_in_pos && !g_in_dir && !g_in_intensity &&
+                         !(((mode & RTT_MODE_TUNE_MASK) >> RTT_MODE_TUNE_SHIFT) & 8);
+    std::vector<Xf> xf(T.S + 1);
+    std::vector<int> tile_op(T.S, 0);
+    uint64_t lean_rows = 0;
+    if (lean_on) {
+        for (int r = 0; r <= T.S; ++r)
+            xf[r] = make_xf(r > 0 ? &T.rows[r - 1] : nullptr, r < T.S ? &T.rows[r] : nullptr);
+        int used = 0;                                                    // private gradient slots, as in the kernel
+        for (int r = 0; r < T.S; ++r) {
+            tile_op[r] = tile_opcode(T.rows[r]);
+            const int fl_all = T.rows[r].i[RTT_I_FLAGS];
+            const bool scalar_only = fl_all != 0 && !(fl_all & (RTT_FLAG_GRAD_POSE_E | RTT_FLAG_GRAD_POSE_S)) &&
+                                     !(T.L > 0 && (fl_all & RTT_FLAG_GRAD_IOR));
+            const bool slot = g_table && scalar_only && used < 12;
+            if (slot) ++used;
+            const int fl = g_table ? (fl_all & flag_mask) : 0;
+            if (lean_tile_op(tile_op[r]) && (fl == 0 || slot)) lean_rows |= 1ull << r;
+        }
+    }
+    std::vector<float> ckw(RTT_MAX_ROWS * 6);
+#endif
     for (int64_t i = 0; i < n; ++i) {
         const HostRay ray = fetch_ray(source, in_pos, in_dir, nullptr, in_wavelength, T.L > 0, i);
         V3 p = ray.p, d = ray.d;
         const int lam = T.L > 0 ? lam_index(T, ray.wav) : 0;
         const uint64_t mask = hitmask[i];
         int nh = 0;
+#ifdef RTT_HOST_TILE
+        const int cap = (T.S <= 24 ? 24 : RTT_MAX_ROWS) * 6 / kLeanCkWords;
+        if (lean_on && mask != 0 && (mask & ~lean_rows) == 0 && __builtin_popcountll(mask) <= cap && finite_ray(p, d) &&
+            regular_dir(d)) {
+            V3 lp = p, ld = d;
+            for (int r = 0; r < T.S; ++r) {
+                apply_xf(xf[r], lp, ld);
+                if (!((mask >> r) & 1ull)) continue;
+                const RowDev& R = T.rows[r];
+                const Ior io = row_ior(T, r, lam);
+                LeanCk c;
+                if (tile_op[r] == 1) lean_face_replay<true>(R, io.mu_enter, io.mu_exit, lp, ld, c);
+                else if (tile_op[r] == 4) lean_face_replay<false>(R, io.mu_enter, io.mu_exit, lp, ld, c);
+                else lean_plane_replay(R, tile_op[r], lp, ld, c);
+                lean_ck_store(ckw.data() + kLeanCkWords * nh, c);
+                ++nh;
+            }
+            V3 gp = g_out_pos ? load3(g_out_pos, i) : v3(0, 0, 0);
+            V3 gd = g_out_dir ? load3(g_out_dir, i) : v3(0, 0, 0);
+            lean_xf_transpose(xf[T.S], gp, gd);
+            for (int r = T.S - 1; r >= 0; --r) {
+                if ((mask >> r) & 1ull) {
+                    --nh;
+                    const LeanCk c = lean_ck_load(ckw.data() + kLeanCkWords * nh);
+                    const RowDev& R = T.rows[r];
+                    if (tile_op[r] == 1 || tile_op[r] == 4) {
+                        const int flags = g_table ? R.i[RTT_I_FLAGS] : 0;
+                        const Ior io = row_ior(T, r, lam);
+                        float g5[5] = {0, 0, 0, 0, 0};
+                        if (tile_op[r] == 1) lean_face_reverse<true>(R, io.mu_enter, io.mu_exit, io.ni, io.no, c, gp, gd, flags, g5);
+                        else lean_face_reverse<false>(R, io.mu_enter, io.mu_exit, io.ni, io.no, c, gp, gd, flags, g5);
+                        if (g_table) {
+                            float* row = g_table + (size_t)r * RTT_ROW_G;
+                            if (flags & RTT_FLAG_GRAD_CK) { row[RTT_F_C] += g5[0]; row[RTT_F_K] += g5[1]; }
+                            if (flags & RTT_FLAG_GRAD_IOR) { row[RTT_F_IOR_IN] += g5[3]; row[RTT_F_IOR_OUT] += g5[4]; }
+                        }
+                    } else {
+                        V3 g_hl = v3(0, 0, 0);
+                        const int slot = R.i[RTT_I_SENSOR];
+                        if (tile_op[r] != 7 && slot >= 0 && slot < n_sensors && g_record && g_record[slot]) {
+                            const float* gr = g_record[slot] + 4 * i;
+                            g_hl = v3(gr[0], gr[1], gr[2]);
+                        }
+                        lean_plane_reverse(R, tile_op[r], c, g_hl, gp, gd);
+                    }
+                }
+                lean_xf_transpose(xf[r], gp, gd);
+            }
+            continue;
+        }
+#endif
         for (int r = 0; r < T.S; ++r) {
             if (!((mask >> r) & 1ull)) continue;
             ck[nh].p = p; ck[nh].d = d; ++nh;

@@ -373,6 +373,146 @@ def test_seq_adjoint_scalar_grads_hint(runner_of, rtt_ns, name, variant):
     assert rtt.ops.adjoint_hint(tab) == (0 if any(m[C.I_FLAGS] & 3 for m in tab.i_host) else rtt.ops.MODE_SCALAR_GRADS)
 
 
+NO_LEAN = 8 << 16          # include/rtt_b200.h: rtt_trace_seq_bwd tune bit 8 = every ray through the general adjoint
+
+
+@pytest.mark.parametrize("name", parity.golden_names(grads=True))
+def test_seq_adjoint_lean_path(runner_of, rtt_ns, name):
+    """The frame-resident lean adjoint (csrc/rtt_lean.cuh: lens faces, stops, sensors; FAST build, scalar gradients, no
+    input-ray gradients) against (a) the general adjoint on the same launch arguments and (b) the reference's own
+    autograd for every curvature / conic / index Parameter, within north_star's 1e-3."""
+    import raytracetorch_b200 as rtt
+    from raytracetorch_b200 import codes as C
+    hs = runner_of("fast")
+    builder, kw, _ = scenes.GRAD_CASES[name]
+    d = parity.load(name)
+    els = builder(rtt_ns, **kw)
+    holder = torch.nn.Module()
+    holder.elements = torch.nn.ModuleList(els)
+    tab = rtt.compile_elements(els)
+    tf, ti = tab.f.detach().numpy(), tab.i.numpy()
+    fwd = hs.trace_seq(tf, ti, d["in_pos"], d["in_dir"], d["in_intensity"])
+    gp, gd, gi = parity.golden_loss_grads(fwd["pos"], fwd["dir"], fwd["intensity"])
+    args = (tf, ti, d["in_pos"], d["in_dir"], d["in_intensity"], fwd["hitmask"], gp, gd, gi)
+    hint = rtt.ops.MODE_SCALAR_GRADS
+    lean = hs.trace_seq_bwd(*args, hint=hint, need_rays=False)
+    general = hs.trace_seq_bwd(*args, hint=hint | NO_LEAN, need_rays=False)
+    scalar = slice(C.F_C, C.N_DIFF)
+    assert not lean["g_table"][:, :C.F_C].any()
+    ref_t = general["g_table"][:, scalar]
+    if np.abs(ref_t).sum() > 0:
+        assert parity.grad_rel(lean["g_table"][:, scalar], ref_t) < 2e-4
+    # chain to the Parameters; compare the scalar ones with the reference's autograd (fp64 run)
+    tab.f.backward(torch.from_numpy(lean["g_table"]))
+    params = dict(holder.named_parameters())
+    checked = 0
+    for k in [k[len("f32_gp::"):] for k in d.files if k.startswith("f32_gp::")]:
+        if k.rsplit(".", 1)[-1] in ("trans", "rot_vec"):                 # pose gradients: not this build's business
+            continue
+        ref = d["f64_gp::" + k]
+        if np.linalg.norm(ref) == 0:
+            continue
+        g = params[k].grad
+        g = np.zeros_like(ref) if g is None else g.numpy()
+        assert parity.grad_rel(g, ref) < parity.TOL_GRAD, (k, g, ref)
+        checked += 1
+    assert checked > 0, "no scalar parameter of this fixture was checked"
+    if name in ("grad_c2_cylindrical", "grad_c3_singlet", "grad_c3_singlet_ref_order", "grad_c4_camera_lens"):
+        # lens faces + stop + sensor: the lean path ran (another summation order than the general code)
+        assert not np.array_equal(lean["g_table"], general["g_table"])
+
+
+def test_seq_adjoint_lean_path_records_and_wavelengths(runner_of, rtt_ns):
+    """Lean adjoint fed through the sensor record (what SpotSizeLoss differentiates) on C2 with the wavelength table:
+    same curvature gradients as the general adjoint and as oracle autograd."""
+    import raytracetorch_b200 as rtt
+    from raytracetorch_b200 import codes as C
+    hs = runner_of("fast")
+    d = parity.load("grad_c2_cylindrical")
+    els = scenes.c2_cylindrical(rtt_ns, grads=True)
+    disp = rtt.Dispersion(scenes.C2_WAVELENGTHS, {
+        els[0].ior_glass: [1.5 * s for s in scenes.C2_GLASS_SCALE],
+        els[1].ior_glass: [1.6 * s for s in scenes.C2_GLASS_SCALE]})
+    tab = rtt.compile_elements(els, dispersion=disp)
+    n = d["in_pos"].shape[0]
+    has_lut = tab.lut is not None and tab.lut.numel() > 0
+    wav = np.asarray(scenes.C2_WAVELENGTHS, np.float32)[np.arange(n) % 3] if has_lut else None
+    lut = tab.lut.detach().numpy() if has_lut else None
+    lut_w = tab.lut_wavelengths.numpy() if has_lut else None
+    p, dd, inten = (t.clone().requires_grad_(True) for t in parity.inputs_t(d))
+    o = O.trace_sequential(tab.f, tab.i_host, p, dd, inten, **(dict(wavelength=torch.from_numpy(wav), lut=tab.lut,
+                                                                    lut_w=tab.lut_wavelengths) if has_lut else {}))
+    mask, hl, w = o["sensor"][0]
+    ((w * ((hl[:, 0] - 0.3) ** 2 + hl[:, 1] ** 2 + 0.5 * hl[:, 0] * hl[:, 1])).sum() / w.sum()).backward()
+    surfs = [s for e in els[:2] for s in e.shape.surfaces[:2]]
+    ref = [s.c.grad.clone() for s in surfs if s.c.grad is not None]
+    assert ref
+    for s in surfs:
+        s.c.grad = None
+    tab = rtt.compile_elements(els, dispersion=disp)
+    assert has_lut
+    tf, ti = tab.f.detach().numpy(), tab.i.numpy()
+    fwd = hs.trace_seq(tf, ti, d["in_pos"], d["in_dir"], d["in_intensity"], wav=wav, lut=lut, lut_w=lut_w,
+                       sensor_specs=[None])
+    rec = torch.from_numpy(fwd["sensors"][0][0]).requires_grad_(True)
+    m = torch.from_numpy(parity.mask_bits(fwd["hitmask"], tf.shape[0])[:, tab.sensor_rows[0]])
+    ww = rec[:, 3] * m
+    ((ww * ((rec[:, 0] - 0.3) ** 2 + rec[:, 1] ** 2 + 0.5 * rec[:, 0] * rec[:, 1])).sum() / ww.sum()).backward()
+    args = (tf, ti, d["in_pos"], d["in_dir"], d["in_intensity"], fwd["hitmask"], None, None, None)
+    kw = dict(wav=wav, lut=lut, lut_w=lut_w, g_records=[rec.grad.numpy()], need_rays=False)
+    lean = hs.trace_seq_bwd(*args, hint=rtt.ops.MODE_SCALAR_GRADS, **kw)
+    general = hs.trace_seq_bwd(*args, hint=rtt.ops.MODE_SCALAR_GRADS | NO_LEAN, **kw)
+    scalar = slice(C.F_C, C.N_DIFF)
+    assert np.abs(general["g_table"][:, scalar]).sum() > 0
+    assert parity.grad_rel(lean["g_table"][:, scalar], general["g_table"][:, scalar]) < 2e-4
+    tab.f.backward(torch.from_numpy(lean["g_table"]))
+    got = [s.c.grad for s in surfs if s.c.grad is not None]
+    for g, r in zip(got, ref):
+        assert parity.grad_rel(g.numpy(), r.numpy()) < parity.TOL_GRAD
+
+
+def test_seq_adjoint_lean_path_flat_face(runner_of, rtt_ns):
+    """C2 with all four curvatures trainable: the back face of the second lens is FLAT (c = 0), so the forward pass takes
+    the A ~ 0 branch t = -C / B and the reference's autograd sends no gradient through A (dA/dc ~ 1 there).  The lean
+    reverse step restates exactly that: same curvature gradients as the general adjoint (which differentiates the
+    reference's expressions term by term)."""
+    import raytracetorch_b200 as rtt
+    from raytracetorch_b200 import codes as C
+    hs = runner_of("fast")
+    n = 30_000
+    g = torch.Generator().manual_seed(5)
+    th = torch.rand(n, generator=g) * (2 * np.pi)
+    r = torch.sqrt(torch.rand(n, generator=g)) * 8.0
+    pos = torch.stack([r * torch.cos(th), r * torch.sin(th), torch.full_like(r, -10.0)], 1).contiguous().numpy()
+    dirs = np.zeros((n, 3), np.float32)
+    dirs[:, 2] = 1.0
+    inten = np.ones(n, np.float32)
+    lam = np.asarray(scenes.C2_WAVELENGTHS, np.float32)[np.arange(n) % 3]
+    els = scenes.c2_cylindrical(rtt_ns)
+    for el in els:
+        for s_ in getattr(el.shape, "surfaces", []):
+            if hasattr(s_, "c") and isinstance(s_.c, torch.nn.Parameter):
+                s_.c.requires_grad_(True)
+    disp = rtt.Dispersion(scenes.C2_WAVELENGTHS, {
+        els[0].ior_glass: [1.5 * s_ for s_ in scenes.C2_GLASS_SCALE],
+        els[1].ior_glass: [1.6 * s_ for s_ in scenes.C2_GLASS_SCALE]})
+    tab = rtt.compile_elements(els, dispersion=disp)
+    tf, ti = tab.f.detach().numpy(), tab.i.numpy()
+    face_rows = [r_ for r_ in range(tf.shape[0]) if ti[r_, C.I_FLAGS] & C.FLAG_GRAD_CK]
+    assert len(face_rows) == 4 and any(tf[r_, C.F_C] == 0.0 for r_ in face_rows)
+    kw = dict(wav=lam, lut=tab.lut.detach().numpy(), lut_w=tab.lut_wavelengths.numpy())
+    fwd = hs.trace_seq(tf, ti, pos, dirs, inten, **kw)
+    g_pos = np.zeros_like(fwd["pos"])
+    g_pos[:, :2] = 2.0 * fwd["intensity"][:, None] * fwd["pos"][:, :2]
+    args = (tf, ti, pos, dirs, inten, fwd["hitmask"], g_pos, None, None)
+    lean = hs.trace_seq_bwd(*args, hint=rtt.ops.MODE_SCALAR_GRADS, need_rays=False, **kw)
+    general = hs.trace_seq_bwd(*args, hint=rtt.ops.MODE_SCALAR_GRADS | NO_LEAN, need_rays=False, **kw)
+    for r_ in face_rows:
+        assert general["g_table"][r_, C.F_C] != 0.0
+        assert parity.grad_rel(lean["g_table"][r_, C.F_C], general["g_table"][r_, C.F_C]) < 2e-5, r_
+    assert not np.array_equal(lean["g_table"], general["g_table"])
+
+
 def _stack_of_singlets(rtt_ns, grads=()):
     """21 weak singlets (3 rows each) + a sensor = RTT_MAX_ROWS = 64 table rows; the hit mask uses all 64 bits."""
     E, G = rtt_ns.elements, rtt_ns.geom
