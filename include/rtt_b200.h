@@ -84,11 +84,15 @@ enum { RTT_MODE_SCALAR_GRADS = 0x100, RTT_MODE_ARITH_MASK = 0xff };
  * compiled instantiation of the sequential forward / adjoint kernel runs.  Results are the same for every value
  * (FAST builds agree to rounding); it exists for performance sweeps and A/B measurements, and it is the ONLY tuning
  * input — the library reads no environment variables.
- *   rtt_trace_seq_fwd (FAST): 1 = tile, 1 ray/thread, 4 blocks/SM; 2 = tile, 2 rays, 3 blocks; 3 = tile, 2 rays,
- *     4 blocks; 5 = tile, 1 ray, 5 blocks; 9 = per-ray kernel in the reference's operation order; 16 = packed ray
- *     pairs (f32x2 arithmetic) with bulk-async (TMA) ray streaming, 3 blocks/SM; 17 = same, 4 blocks/SM;
- *     18 = packed pairs with plain global loads / stores
- *   rtt_trace_seq_bwd: 2 / 3 / 4 = resident blocks per SM the adjoint build is compiled for */
+ *   rtt_trace_seq_fwd (FAST): 0 / 7 = tile kernel, 2 rays/thread, one block of 1024 threads per SM (default);
+ *     6 = 7 with a barrier per tile; 8 = two blocks of 512; 1 = tile, 1 ray/thread, 4 blocks of 256 per SM; 2 = tile,
+ *     2 rays, 3 blocks; 3 = tile, 2 rays, 4 blocks; 5 = tile, 1 ray, 5 blocks; 9 = per-ray kernel in the reference's
+ *     operation order; 16 = packed ray pairs (f32x2 arithmetic) with bulk-async (TMA) ray streaming, 3 blocks/SM;
+ *     17 = same, 4 blocks/SM; 18 = packed pairs with plain global loads / stores
+ *   rtt_trace_seq_bwd: low 3 bits 2 / 3 / 4 = resident blocks per SM the adjoint build is compiled for; bit 8 (value 8) =
+ *     no lean path (every ray through the general adjoint, csrc/rtt_lean.cuh)
+ *   rtt_trace_nonseq_fwd: 0 = one block of 1024 threads per SM (EXACT: with a barrier per bounce trip); 7 = 256-thread
+ *     blocks running free (the round-1 kernel); 1, 3..6 = other barrier placements (A/B) */
 enum { RTT_MODE_TUNE_SHIFT = 16, RTT_MODE_TUNE_MASK = 0xff0000 };
 /* rtt_trace_nonseq_fwd / _bwd only: run the FAST arithmetic (see there); every other entry ignores the bit. */
 enum { RTT_MODE_NONSEQ_FAST = 0x400 };

@@ -246,6 +246,7 @@ int rtt_trace_nonseq_fwd(const float* in_pos, const float* in_dir, const float* 
         a.tab = make_table<rtt::NS::TableDev>(table);                                                  \
         if (int e = fill_sensors(a.sens, sensors, n_sensors)) return e;                                \
         a.n_sens = n_sensors; a.nbounces = nbounces; a.n = n;                                          \
+        a.tune = (mode & RTT_MODE_TUNE_MASK) >> RTT_MODE_TUNE_SHIFT;                                   \
         return finish(rtt::NS::launch_nonseq_fwd_##NS(a, st));                                         \
     }
     /* EXACT unless the caller opts in to the FAST arithmetic explicitly: see include/rtt_b200.h */

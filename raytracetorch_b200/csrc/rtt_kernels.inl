@@ -360,7 +360,7 @@ __device__ __noinline__ WalkState seq_walk_generic(const SeqFwdArgs& a, int lam,
     return w;
 }
 
-template <class K, int RPT>
+template <class K, int RPT, int BLK = kThreads>
 __device__ __forceinline__ void tile_row(const SmemTable& T, int S, int L, int r, const SeqFwdArgs& a, ImgCache cache,
                                          long long i0, V3 (&p)[RPT], V3 (&d)[RPT], float (&I)[RPT],
                                          unsigned long long (&mask)[RPT], const int (&lam)[RPT],
@@ -378,11 +378,11 @@ __device__ __forceinline__ void tile_row(const SmemTable& T, int S, int L, int r
             if (uses_ior<K>(R)) io = row_ior(T, S, L, r, lam[j]);
             V3 np, nd, hl; float mod;
             tile_interact<K>(R, p[j], d[j], t[j], io.mu_enter, io.mu_exit, np, nd, mod, hl,
-                             make_aux<K>(T.rows, R, io.ni, io.no, i0 + (long long)j * kThreads, r, 0));
+                             make_aux<K>(T.rows, R, io.ni, io.no, i0 + (long long)j * BLK, r, 0));
             if (K::sensor(R)) {
                 const int slot = R.i[RTT_I_SENSOR];
                 if (slot >= 0 && slot < a.n_sens)
-                    sensor_deposit(a.sens[slot], cache, slot, i0 + (long long)j * kThreads, hl, I[j], lam[j]);
+                    sensor_deposit(a.sens[slot], cache, slot, i0 + (long long)j * BLK, hl, I[j], lam[j]);
             }
             p[j] = np; d[j] = nd; I[j] = I[j] * mod;
             mask[j] |= bit;
@@ -390,8 +390,12 @@ __device__ __forceinline__ void tile_row(const SmemTable& T, int S, int L, int r
     }
 }
 
-template <int RPT, int MINB, bool GEN>
-__global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_tile(const __grid_constant__ SeqFwdArgs a) {
+// BLK = threads per block; SYNC: the warps of a block start every tile together (one barrier per iteration of the block's
+// grid-stride loop, whose trip count is block-uniform).  With 1024-thread blocks the eight warps of an SM sub-partition
+// then fetch the same instructions at the same time: the build for rays generated in the kernel waits on instruction
+// fetch for 40 % of its stall samples (profiles/r2_forward_kernels.md, c4cam).
+template <int RPT, int MINB, bool GEN, int BLK = kThreads, bool SYNC = false>
+__global__ void __launch_bounds__(BLK, MINB) k_trace_seq_fwd_tile(const __grid_constant__ SeqFwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.tab.S, L = a.tab.L;
     SmemTable T = carve(smem_raw + kTileOffTable, S, L);
@@ -402,8 +406,9 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_tile(const __g
     stage_tile(T, S, xf);
     SourceKey skey; skey.key = 0ull; skey.base = 0ull;
     if (GEN) skey = source_key(a.src);
-    const long long tile = (long long)kThreads * RPT;
+    const long long tile = (long long)BLK * RPT;
     for (long long base = (long long)blockIdx.x * tile; base < a.n; base += (long long)gridDim.x * tile) {
+        if (SYNC) __syncthreads();
         const long long i0 = base + threadIdx.x;
         V3 p[RPT], d[RPT];
         float I[RPT];
@@ -412,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_tile(const __g
         bool act[RPT], odd[RPT];
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
-            const long long i = i0 + (long long)j * kThreads;
+            const long long i = i0 + (long long)j * BLK;
             p[j] = v3(0.0f, 0.0f, 0.0f); d[j] = v3(0.0f, 0.0f, 0.0f); I[j] = 0.0f; lam[j] = 0; mask[j] = 0ull;
             act[j] = false; odd[j] = false;
             if (i < a.n) {
@@ -443,10 +448,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_tile(const __g
             }
             switch (op) {                                               // warp-uniform
 #define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR)                                         \
-                case OP: tile_row<KTile<SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR>, RPT>(T, S, L, r, a, cache, i0, p, d, I, mask, lam, act, bit); break;
+                case OP: tile_row<KTile<SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR>, RPT, BLK>(T, S, L, r, a, cache, i0, p, d, I, mask, lam, act, bit); break;
                 RTT_TILE_SPECS(RTT_X)
 #undef RTT_X
-                default: tile_row<KDyn, RPT>(T, S, L, r, a, cache, i0, p, d, I, mask, lam, act, bit); break;
+                default: tile_row<KDyn, RPT, BLK>(T, S, L, r, a, cache, i0, p, d, I, mask, lam, act, bit); break;
             }
         }
         if (xf[S].kind) {
@@ -455,7 +460,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_tile(const __g
         }
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
-            const long long i = i0 + (long long)j * kThreads;
+            const long long i = i0 + (long long)j * BLK;
             if (odd[j]) {
                 // un-normalised direction: walk in the reference's order; NaN / inf ray: hits nothing, stays as it was
                 const RayIn ray = fetch_ray_t<GEN>(a, skey, i, L > 0);
@@ -493,9 +498,9 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_tile(const __g
 // NP = ray pairs per thread.  Shipped: 1 (512-ray tiles, 80 registers, 3 blocks / SM).  NP = 2 (1024-ray tiles, two
 // independent packed chains per thread, 112 registers, 2 blocks / SM) measured slower on every workload — C2 4.28 vs
 // 3.92, C1 2.75 vs 2.51, C4 8.19 vs 6.92 ms per 1e8 rays (profiles/r2_fwd_pair_ab.md) — and is not instantiated.
-template <int NP>
+template <int NP, int BLK = kThreads>
 struct PairGeom {
-    static constexpr int kTile = NP * 2 * kThreads;                     // rays per block iteration
+    static constexpr int kTile = NP * 2 * BLK;                     // rays per block iteration
     static constexpr int kPos = 0, kDir = kTile * 12, kInt = kTile * 24, kWav = kTile * 28, kMask = kTile * 32,
                          kBytes = kTile * 40;                           // 20 KB per slot and pair
 };
@@ -533,21 +538,21 @@ __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // shared-memory layout of the pair kernel, all at compile-time offsets: [image cache | Xf[MAX_ROWS+1] | ray slots | mbarriers | table]
-template <int LOG, bool STREAM, int NP = 1>
+template <int LOG, bool STREAM, int NP = 1, int BLK = kThreads>
 struct PairLayout {
     static constexpr size_t kOffXf = (img_cache_bytes<LOG>() + 15) / 16 * 16;
     static constexpr size_t kOffSlots = (kOffXf + sizeof(Xf) * (RTT_MAX_ROWS + 1) + 127) / 128 * 128;
-    static constexpr size_t kOffBar = kOffSlots + (STREAM ? (size_t)kPairSlots * PairGeom<NP>::kBytes : 0);
+    static constexpr size_t kOffBar = kOffSlots + (STREAM ? (size_t)kPairSlots * PairGeom<NP, BLK>::kBytes : 0);
     static constexpr size_t kOffTable = kOffBar + 16;
     __host__ __device__ static size_t bytes(int S, int L) { return kOffTable + smem_table_bytes(S, L); }
 };
 
 // reference-order walk of an irregular ray (see seq_walk_generic), for the pair kernel's layout
-template <int LOG, bool STREAM, int NP>
+template <int LOG, bool STREAM, int NP, int BLK>
 __device__ __noinline__ WalkState pair_walk_generic(const SeqFwdArgs& a, int lam, long long i, WalkState w) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.tab.S, L = a.tab.L;
-    SmemTable T = carve(smem_raw + PairLayout<LOG, STREAM, NP>::kOffTable, S, L);
+    SmemTable T = carve(smem_raw + PairLayout<LOG, STREAM, NP, BLK>::kOffTable, S, L);
     ImgCacheT<LOG> cache = img_cache_carve<LOG>(smem_raw);
     unsigned long long bit = 1ull;
     for (int r = 0; r < S; ++r, bit += bit) seq_row<KDyn, LOG>(T, S, L, r, lam, i, a, cache, w.p, w.d, w.I, w.mask, bit);
@@ -555,9 +560,9 @@ __device__ __noinline__ WalkState pair_walk_generic(const SeqFwdArgs& a, int lam
 }
 
 // ray `loc` of the tile staged in a slot
-template <int NP>
+template <int NP, int BLK>
 __device__ __forceinline__ RayIn slot_ray(const unsigned char* slot, int loc, bool want_wav) {
-    typedef PairGeom<NP> GE;
+    typedef PairGeom<NP, BLK> GE;
     const float* sp = reinterpret_cast<const float*>(slot + GE::kPos);
     const float* sd = reinterpret_cast<const float*>(slot + GE::kDir);
     RayIn r;
@@ -569,7 +574,7 @@ __device__ __forceinline__ RayIn slot_ray(const unsigned char* slot, int loc, bo
 }
 
 // sensor deposits of a pair: lane 0 / 1 = rays i0, i0 + kThreads
-template <int LOG>
+template <int LOG, int BLK = kThreads>
 struct PairDeposit {
     const SeqFwdArgs& a;
     ImgCacheT<LOG> cache;
@@ -577,7 +582,7 @@ struct PairDeposit {
     int lam_a, lam_b;
     __device__ __forceinline__ void operator()(int lane, int slot, V3 hl, float w) const {
         if (slot >= 0 && slot < a.n_sens)
-            sensor_deposit(a.sens[slot], cache, slot, i0 + (long long)lane * kThreads, hl, w, lane ? lam_b : lam_a);
+            sensor_deposit(a.sens[slot], cache, slot, i0 + (long long)lane * BLK, hl, w, lane ? lam_b : lam_a);
     }
 };
 
@@ -594,7 +599,7 @@ __device__ __forceinline__ void pair_ior(const SmemTable& T, int L, int r, int l
 }
 
 // a row kind without a packed form: the scalar twin per lane, with the specialised policy K
-template <class K, class DEP>
+template <class K, int BLK, class DEP>
 __device__ __forceinline__ unsigned pair_row_generic(const SmemTable& T, int S, int L, int r, long long i0, int lam_a, int lam_b,
                                                      P3& P, P3& D, F2& I, unsigned act, DEP& dep) {
     const RowDev& R = T.rows[r];
@@ -605,17 +610,17 @@ __device__ __forceinline__ unsigned pair_row_generic(const SmemTable& T, int S, 
         if (K::phys(R) == RTT_PHYS_FRESNEL) {
             const Ior qa = row_ior(T, S, L, r, lam_a), qb = row_ior(T, S, L, r, lam_b);
             aux_a = make_aux<K>(T.rows, R, qa.ni, qa.no, i0, r, 0);
-            aux_b = make_aux<K>(T.rows, R, qb.ni, qb.no, i0 + kThreads, r, 0);
+            aux_b = make_aux<K>(T.rows, R, qb.ni, qb.no, i0 + BLK, r, 0);
         }
     }
     return pair_row_scalar<K>(T.rows, r, P, D, I, act, mu_enter, mu_exit, aux_a, aux_b, dep);
 }
 
-template <int MINB, bool STREAM, int LOG, int NP, bool GEN>
-__global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __grid_constant__ SeqFwdArgs a) {
+template <int MINB, bool STREAM, int LOG, int NP, bool GEN, int BLK = kThreads>
+__global__ void __launch_bounds__(BLK, MINB) k_trace_seq_fwd_pair(const __grid_constant__ SeqFwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    typedef PairLayout<LOG, STREAM, NP> LY;
-    typedef PairGeom<NP> GE;
+    typedef PairLayout<LOG, STREAM, NP, BLK> LY;
+    typedef PairGeom<NP, BLK> GE;
     const int S = a.tab.S, L = a.tab.L;
     SmemTable T = carve(smem_raw + LY::kOffTable, S, L);
     Xf* xf = reinterpret_cast<Xf*>(smem_raw + LY::kOffXf);
@@ -668,17 +673,17 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
                 float* sd = reinterpret_cast<float*>(slot + GE::kDir);
                 float* si = reinterpret_cast<float*>(slot + GE::kInt);
                 float* sw = reinterpret_cast<float*>(slot + GE::kWav);
-                for (int idx = threadIdx.x; idx < 3 * cnt; idx += kThreads) {
+                for (int idx = threadIdx.x; idx < 3 * cnt; idx += BLK) {
                     sp[idx] = a.pos[3 * base + idx]; sd[idx] = a.dir[3 * base + idx];
                 }
-                for (int idx = threadIdx.x; idx < cnt; idx += kThreads) {
+                for (int idx = threadIdx.x; idx < cnt; idx += BLK) {
                     si[idx] = a.inten[base + idx];
                     if (use_wav) sw[idx] = a.wav[base + idx];
                 }
                 __syncthreads();
             }
         }
-        // ---- this thread's pairs: pair q = rays base + threadIdx.x + (2q) * kThreads and + (2q + 1) * kThreads ----
+        // ---- this thread's pairs: pair q = rays base + threadIdx.x + (2q) * BLK and + (2q + 1) * BLK ----
         P3 P[NP], D[NP];
         F2 I[NP];
         int lamS[NP][2];                                                // wavelength index * S (offset into the index table)
@@ -690,10 +695,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
             actb[q] = 0u;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int loc = threadIdx.x + (2 * q + j) * kThreads;
+                const int loc = threadIdx.x + (2 * q + j) * BLK;
                 pin[j] = v3(0.0f, 0.0f, 0.0f); din[j] = v3(0.0f, 0.0f, 0.0f); Iin[j] = 0.0f; lamS[q][j] = 0;
                 if (loc < cnt) {
-                    const RayIn ray = STREAM ? slot_ray<NP>(slot, loc, use_wav)
+                    const RayIn ray = STREAM ? slot_ray<NP, BLK>(slot, loc, use_wav)
                                              : fetch_ray_t<GEN>(a, skey, (long long)tile * GE::kTile + loc, use_wav);
                     pin[j] = ray.p; din[j] = ray.d; Iin[j] = ray.I;
                     lamS[q][j] = use_wav ? wavelength_index(T, L, ray.wav) * S : 0;
@@ -739,7 +744,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
                     for (int q = 0; q < NP; ++q) pair_ior(T, L, r, lamS[q][0], lamS[q][1], me[q], mx[q]);
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
-                        PairDeposit<LOG> dep{a, cache, i0 + (long long)(2 * q) * kThreads, 0, 0};
+                        PairDeposit<LOG, BLK> dep{a, cache, i0 + (long long)(2 * q) * BLK, 0, 0};
                         hit[q] = pair_conic_face<true, RTT_SHAPE_SPHERIC_FACE>(T.rows, r, P[q], D[q], I[q], actb[q], me[q], mx[q], dep);
                     }
                     break;
@@ -748,14 +753,14 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
                     for (int q = 0; q < NP; ++q) pair_ior(T, L, r, lamS[q][0], lamS[q][1], me[q], mx[q]);
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
-                        PairDeposit<LOG> dep{a, cache, i0 + (long long)(2 * q) * kThreads, 0, 0};
+                        PairDeposit<LOG, BLK> dep{a, cache, i0 + (long long)(2 * q) * BLK, 0, 0};
                         hit[q] = pair_conic_face<false, RTT_SHAPE_CYL_FACE>(T.rows, r, P[q], D[q], I[q], actb[q], me[q], mx[q], dep);
                     }
                     break;
 #define RTT_PLANE_CASE(OP, BOUND, PHYS, SENSOR)                                                                         \
                 case OP:                                                                                                    \
                     _Pragma("unroll") for (int q = 0; q < NP; ++q) {                                                        \
-                        PairDeposit<LOG> dep{a, cache, i0 + (long long)(2 * q) * kThreads,                                  \
+                        PairDeposit<LOG, BLK> dep{a, cache, i0 + (long long)(2 * q) * BLK,                                  \
                                              use_wav ? lamS[q][0] / S : 0, use_wav ? lamS[q][1] / S : 0};                   \
                         hit[q] = pair_plane<BOUND, PHYS, SENSOR>(T.rows, r, P[q], D[q], I[q], actb[q], dep);                \
                     }                                                                                                       \
@@ -768,9 +773,9 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
                 case OP:                                                                                                    \
                     _Pragma("unroll") for (int q = 0; q < NP; ++q) {                                                        \
                         const int la = use_wav ? lamS[q][0] / S : 0, lb = use_wav ? lamS[q][1] / S : 0;                     \
-                        PairDeposit<LOG> dep{a, cache, i0 + (long long)(2 * q) * kThreads, la, lb};                         \
-                        hit[q] = pair_row_generic<KTile<SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR>>(                       \
-                            T, S, L, r, i0 + (long long)(2 * q) * kThreads, la, lb, P[q], D[q], I[q], actb[q], dep);        \
+                        PairDeposit<LOG, BLK> dep{a, cache, i0 + (long long)(2 * q) * BLK, la, lb};                         \
+                        hit[q] = pair_row_generic<KTile<SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR>, BLK>(                       \
+                            T, S, L, r, i0 + (long long)(2 * q) * BLK, la, lb, P[q], D[q], I[q], actb[q], dep);        \
                     }                                                                                                       \
                     break;
                 RTT_PAIR_SCALAR_SPECS(RTT_X)
@@ -779,8 +784,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
                         const int la = use_wav ? lamS[q][0] / S : 0, lb = use_wav ? lamS[q][1] / S : 0;
-                        PairDeposit<LOG> dep{a, cache, i0 + (long long)(2 * q) * kThreads, la, lb};
-                        hit[q] = pair_row_generic<KDyn>(T, S, L, r, i0 + (long long)(2 * q) * kThreads, la, lb, P[q], D[q], I[q],
+                        PairDeposit<LOG, BLK> dep{a, cache, i0 + (long long)(2 * q) * BLK, la, lb};
+                        hit[q] = pair_row_generic<KDyn, BLK>(T, S, L, r, i0 + (long long)(2 * q) * BLK, la, lb, P[q], D[q], I[q],
                                                         actb[q], dep);
                     }
                     break;
@@ -808,16 +813,16 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
             unsigned long long mo[2] = {((unsigned long long)m_a[q] << 32) | lo_a[q], ((unsigned long long)m_b[q] << 32) | lo_b[q]};
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int loc = threadIdx.x + (2 * q + j) * kThreads;
+                const int loc = threadIdx.x + (2 * q + j) * BLK;
                 if ((oddb >> (2 * q + j)) & 1u) {
                     // un-normalised direction: walk in the reference's order; NaN / inf ray: hits nothing, stays as it was
                     // (the slot still holds this ray's inputs: a thread only ever writes its own entries)
                     const long long i = (long long)tile * GE::kTile + loc;
-                    const RayIn ray = STREAM ? slot_ray<NP>(slot, loc, use_wav) : fetch_ray_t<GEN>(a, skey, i, use_wav);
+                    const RayIn ray = STREAM ? slot_ray<NP, BLK>(slot, loc, use_wav) : fetch_ray_t<GEN>(a, skey, i, use_wav);
                     WalkState w;
                     w.p = ray.p; w.d = ray.d; w.I = ray.I; w.mask = 0ull;
                     if (finite_ray(ray.p, ray.d))
-                        w = pair_walk_generic<LOG, STREAM, NP>(a, use_wav ? lamS[q][j] / S : 0, i, w);
+                        w = pair_walk_generic<LOG, STREAM, NP, BLK>(a, use_wav ? lamS[q][j] / S : 0, i, w);
                     po[j] = w.p; dout[j] = w.d; Io[j] = w.I; mo[j] = w.mask;
                 }
                 if (loc < cnt) {
@@ -860,14 +865,14 @@ __global__ void __launch_bounds__(kThreads, MINB) k_trace_seq_fwd_pair(const __g
                 const float* sp = reinterpret_cast<const float*>(slot + GE::kPos);
                 const float* sd = reinterpret_cast<const float*>(slot + GE::kDir);
                 if (a.opos) {
-                    for (int idx = threadIdx.x; idx < 3 * cnt; idx += kThreads) {
+                    for (int idx = threadIdx.x; idx < 3 * cnt; idx += BLK) {
                         a.opos[3 * base + idx] = sp[idx]; a.odir[3 * base + idx] = sd[idx];
                     }
-                    for (int idx = threadIdx.x; idx < cnt; idx += kThreads)
+                    for (int idx = threadIdx.x; idx < cnt; idx += BLK)
                         a.ointen[base + idx] = reinterpret_cast<const float*>(slot + GE::kInt)[idx];
                 }
                 if (a.hitmask)
-                    for (int idx = threadIdx.x; idx < cnt; idx += kThreads)
+                    for (int idx = threadIdx.x; idx < cnt; idx += BLK)
                         a.hitmask[base + idx] = reinterpret_cast<const unsigned long long*>(slot + GE::kMask)[idx];
             }
         }
@@ -999,8 +1004,8 @@ __device__ __noinline__ ReverseOut reverse_row_generic(SmemTable T, int S, int L
 // chunk to the rays that matter (dead rays of an intensity-weighted loss, rays that missed everything) and
 // runs the replay + reverse sweep on full warps of those.
 constexpr int kAccRows = 12, kAccPerRow = 5;      // private gradient slots: rows x (c, k, radius, ior_in, ior_out)
-constexpr int kBwdChunk = 16 * kThreads;   // large enough that the compacted chunk still fills whole blocks of warps
-__host__ __device__ inline size_t bwd_queue_bytes() { return sizeof(unsigned short) * kBwdChunk + 16; }
+constexpr int kBwdChunkIters = 16;         // chunk = 16 rays per thread: large enough that the compacted chunk still fills whole blocks of warps
+__host__ __device__ inline size_t bwd_queue_bytes(int threads) { return sizeof(unsigned short) * kBwdChunkIters * threads + 16; }
 
 // POSE = false: the caller guarantees that no row requests pose gradients (RTT_MODE_SCALAR_GRADS); the pose-gradient
 // outer products and their 24 accumulator registers per row are compiled out.
@@ -1009,8 +1014,9 @@ __host__ __device__ inline size_t bwd_queue_bytes() { return sizeof(unsigned sho
 // LEAN (FAST build, POSE = false, no input-ray gradients): rays whose every interaction is a lens face, a stop or a sensor
 // take the frame-resident replay / reverse steps of rtt_lean.cuh; the rest of the queue runs the general code below.
 // GEN: 0 = rays from memory or from the ray source (run-time test), 1 = memory only, 2 = generated only (see fetch_ray_t).
-template <int MINB, bool POSE, int CK, bool LEAN, int GEN>
-__global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(const __grid_constant__ SeqBwdArgs a) {
+// BLK = threads per block (256, or one block of 1024 per SM: see the block-size A/B of the forward kernels).
+template <int MINB, bool POSE, int CK, bool LEAN, int GEN, int BLK = BLK>
+__global__ void __launch_bounds__(BLK, MINB) RTT_NAME(k_trace_seq_bwd)(const __grid_constant__ SeqBwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.tab.S, L = a.tab.L;
     SmemTable T = carve(smem_raw, S, L);
@@ -1022,7 +1028,7 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
     stage_table(a.tab, T);
 #if defined(RTT_APPROX)
     // lean path: frame changes between the rows (rtt_tile.cuh) behind the queue, then the mask of lean rows (two words)
-    Xf* xf = reinterpret_cast<Xf*>(reinterpret_cast<unsigned char*>(queue) + bwd_queue_bytes());
+    Xf* xf = reinterpret_cast<Xf*>(reinterpret_cast<unsigned char*>(queue) + bwd_queue_bytes(BLK));
     unsigned* lean_words = reinterpret_cast<unsigned*>(xf + (S + 1));
     if (LEAN) stage_tile(T, S, xf);
 #endif
@@ -1084,14 +1090,14 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
         unsigned needs = 0u;
         constexpr int kGroup = 4;
 #pragma unroll
-        for (int k0 = 0; k0 < kBwdChunk / kThreads; k0 += kGroup) {
+        for (int k0 = 0; k0 < kBwdChunkIters; k0 += kGroup) {
             unsigned long long hm[kGroup];
             V3 ga[kGroup], gb[kGroup];
             float4 gr[kGroup];
             bool ok[kGroup];
 #pragma unroll
             for (int j = 0; j < kGroup; ++j) {
-                const int loc = (k0 + j) * kThreads + threadIdx.x;
+                const int loc = (k0 + j) * BLK + threadIdx.x;
                 ok[j] = loc < count;
                 const long long i = base + (ok[j] ? loc : 0);
                 hm[j] = a.hitmask[i];
@@ -1106,7 +1112,7 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
                             gb[j].x != 0.0f || gb[j].y != 0.0f || gb[j].z != 0.0f ||
                             gr[j].x != 0.0f || gr[j].y != 0.0f || gr[j].z != 0.0f;
                 if (ok[j] && hm[j] != 0ull && !need) {                   // further sensors (rare): dependent loads
-                    const long long i = base + (k0 + j) * kThreads + threadIdx.x;
+                    const long long i = base + (k0 + j) * BLK + threadIdx.x;
                     for (int sl = 1; sl < a.n_sens; ++sl)
                         if (a.g_record[sl]) {
                             const float4 g2 = reinterpret_cast<const float4*>(a.g_record[sl])[i];
@@ -1118,7 +1124,7 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
             }
         }
         // pass 2: append them to the block's queue (warp-aggregated)
-        for (int k = 0; k < chunk / kThreads; ++k) {
+        for (int k = 0; k < chunk / BLK; ++k) {
             const bool need = (needs >> k) & 1u;
             const unsigned votes = __ballot_sync(kFull, need);
             if (votes) {
@@ -1126,13 +1132,13 @@ __global__ void __launch_bounds__(kThreads, MINB) RTT_NAME(k_trace_seq_bwd)(cons
                 int pos = 0;
                 if (lane == lead) pos = atomicAdd(qcount, __popc(votes));
                 pos = __shfl_sync(kFull, pos, lead);
-                if (need) queue[pos + __popc(votes & ((1u << lane) - 1u))] = (unsigned short)(k * kThreads + threadIdx.x);
+                if (need) queue[pos + __popc(votes & ((1u << lane) - 1u))] = (unsigned short)(k * BLK + threadIdx.x);
             }
         }
         __syncthreads();
         count = *qcount;
       }
-      for (int q0 = 0; q0 < count; q0 += kThreads) {
+      for (int q0 = 0; q0 < count; q0 += BLK) {
         const int q = q0 + threadIdx.x;
         const bool live = q < count;
         const long long i = base + (live ? (compact ? (int)queue[q] : q) : 0);
@@ -1439,6 +1445,115 @@ __global__ void __launch_bounds__(kThreads) RTT_NAME(k_trace_nonseq_fwd)(const _
             for (int s = 0; s < a.n_sens; ++s)
                 if (a.sens[s].count) a.sens[s].count[i] = (unsigned char)((cnts >> (8 * s)) & 255u);
             // (the tail of hit_seq is pre-filled with 255 by the launcher: one memset instead of byte stores per ray)
+            if (a.n_hits) a.n_hits[i] = (unsigned char)nb;
+            if (a.opos) { store3(a.opos, i, p); store3(a.odir, i, d); a.ointen[i] = I; }
+            have = false;
+            i += stride;
+        }
+    }
+    img_cache_flush(cache, a.sens);
+}
+
+// Lock-step build of the non-sequential forward (A/B: RTT_MODE_TUNE 1..5 of rtt_trace_nonseq_fwd).  The kernel above is
+// bound by instruction FETCH (ncu: `no_instruction` is half of its stall samples): the row loop of one search runs through
+// ~6 specialised bodies of several hundred instructions each, far more than an SM sub-partition's L0 instruction cache
+// holds, and the resident warps sit in different bodies, so every warp streams its code from the L1.5 cache by itself.
+// Here the warps of a block start every trip (SYNC >= 1) — or every row of the search (SYNC == 2) — together, so the
+// warps of a sub-partition fetch the same lines at the same time.  Same per-ray arithmetic and results.
+template <int BLOCK, int SYNC>
+__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) RTT_NAME(k_trace_nonseq_fwd_ls)(const __grid_constant__ NonseqFwdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemTable T = carve(smem_raw, a.tab.S, a.tab.L);
+    unsigned char* after = smem_raw + ((smem_table_bytes(a.tab.S, a.tab.L) + 15) / 16) * 16;
+    ImgCache cache = img_cache_carve(after);
+    NsCull* cull = reinterpret_cast<NsCull*>(after + ((img_cache_bytes() + 15) / 16) * 16);
+    img_cache_init(cache);
+    stage_table(a.tab, T);
+    const int S = a.tab.S, L = a.tab.L, NB = a.nbounces;
+    for (int r = threadIdx.x; r < S; r += blockDim.x) {
+        cull[r] = box_cull_info(T.rows, S, r);
+        bool same = r > 0 && T.rows[r].i[RTT_I_SHAPE] != RTT_SHAPE_NONE && T.rows[r - 1].i[RTT_I_SHAPE] != RTT_SHAPE_NONE;
+        for (int e = RTT_F_RE; same && e < RTT_F_TE + 3; ++e) same = T.rows[r].f[e] == T.rows[r - 1].f[e];
+        T.rows[r].f[D_SAME_ELEM] = same ? 1.0f : 0.0f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < S; r += blockDim.x) {
+        if (cull[r].run != 6) continue;
+        for (int f = 0; f < 6; ++f) {
+            RowDev& B = T.rows[r + f];
+            B.f[RTT_F_C] = cull[r].ex; B.f[RTT_F_K] = cull[r].ey; B.f[RTT_F_RADIUS] = cull[r].ez;
+            B.f[D_SB0SQ] = cull[r].r2;
+        }
+    }
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const SourceKey skey = fetch_key(a);
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool have = false;
+    V3 p = v3(0, 0, 0), d = v3(0, 0, 0);
+    float I = 0.0f;
+    int lam = 0, nb = 0;
+    unsigned cnts = 0u;
+    while (true) {
+        if (!have && i < a.n) {
+            const RayIn ray = fetch_ray(a, skey, i, L > 0);
+            p = ray.p; d = ray.d; I = ray.I;
+            lam = (L > 0) ? wavelength_index(T, L, ray.wav) : 0;
+            cnts = 0u; nb = 0;
+            have = true;
+        }
+        if (SYNC == 0) { if (!__any_sync(kFull, have)) break; }         // (A/B: the block size alone, warps run free)
+        else if (!__syncthreads_or(have ? 1 : 0)) break;                // every warp of the block starts the trip together
+        bool done = !have || (nb >= NB) || !(I > 0.0f) || !finite_ray(p, d);
+        float best = rtt_inf();
+        int win = -1;
+        bool poisoned = false;
+        Frames Fs;
+        Fs.pe = Fs.de = Fs.den = Fs.o = Fs.dd = v3(0.0f, 0.0f, 0.0f); Fs.len = 0.0f;
+        int skip_to = 0;
+        for (int r = 0; r < S; ++r) {
+            if (SYNC == 2 || (SYNC == 3 && (r & 3) == 0 && r > 0) || (SYNC == 5 && r * 2 == (S & ~1))) __syncthreads();
+            if (r < skip_to) continue;
+            if (cull[r].run > 0) {
+                const bool missed = done || sphere_missed(cull[r], p, d);
+                if (__all_sync(kFull, missed)) { skip_to = r + cull[r].run; continue; }
+            }
+            if (!done) {
+                switch (T.rows[r].i[DI_OPCODE]) {                       // warp-uniform
+#define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR)                                            \
+                    case OP: nonseq_probe<KStatic<SURF, BOUND, SHAPE, PHYS, IDENT, SENSOR>>(T.rows, r, p, d, best, win, poisoned, Fs); break;
+                    RTT_ROW_SPECS(RTT_X)
+#undef RTT_X
+                    default: nonseq_probe<KDyn>(T.rows, r, p, d, best, win, poisoned, Fs); break;
+                }
+            }
+        }
+        if (SYNC == 4 || SYNC == 5) __syncthreads();
+        if (!done) {
+            if (poisoned || win < 0) {
+                done = true;
+            } else {
+                Frames F; Roots q; float t; int which;
+                intersect<false>(T.rows, win, p, d, F, q, t, which);
+                const RowDev& R = T.rows[win];
+                const Ior io = row_ior(T, S, L, win, lam);
+                const Step s = interact(R, F, t, p, d, io.mu_enter, io.mu_exit,
+                                        make_aux(T.rows, R, io.ni, io.no, i, win, nb));
+                const int slot = R.i[RTT_I_SENSOR];
+                if (slot >= 0 && slot < a.n_sens) {
+                    const unsigned c = (cnts >> (8 * slot)) & 255u;
+                    sensor_deposit(a.sens[slot], cache, slot, i, s.hit_local, I, lam, (int)c, a.n);
+                    if (c < 255u) cnts += 1u << (8 * slot);
+                }
+                p = s.hit_global; d = s.new_dir; I = I * s.mod;
+                if (a.hit_seq) a.hit_seq[i * NB + nb] = (unsigned char)win;
+                ++nb;
+                done = (nb >= NB) || !(I > 0.0f) || !finite_ray(p, d);
+            }
+        }
+        if (have && done) {
+            for (int s = 0; s < a.n_sens; ++s)
+                if (a.sens[s].count) a.sens[s].count[i] = (unsigned char)((cnts >> (8 * s)) & 255u);
             if (a.n_hits) a.n_hits[i] = (unsigned char)nb;
             if (a.opos) { store3(a.opos, i, p); store3(a.odir, i, d); a.ointen[i] = I; }
             have = false;
@@ -1756,51 +1871,52 @@ inline cudaError_t allow_smem(Kern kern, size_t bytes) {
 }
 
 #if defined(RTT_APPROX)
-template <int RPT, int MINB, bool GEN>
+template <int RPT, int MINB, bool GEN, int BLK = kThreads, bool SYNC = false>
 inline cudaError_t launch_tile_g(const SeqFwdArgs& a, cudaStream_t st) {
     const size_t smem = tile_smem_bytes(a.tab.S, a.tab.L);
-    if (cudaError_t e = allow_smem(k_trace_seq_fwd_tile<RPT, MINB, GEN>, smem)) return e;
-    const long long tiles = (a.n + (long long)kThreads * RPT - 1) / ((long long)kThreads * RPT);
+    if (cudaError_t e = allow_smem(k_trace_seq_fwd_tile<RPT, MINB, GEN, BLK, SYNC>, smem)) return e;
+    const long long tiles = (a.n + (long long)BLK * RPT - 1) / ((long long)BLK * RPT);
     // several waves of grid-striding blocks: a block that lands on a busier SM costs 1/kWaves of a launch
     constexpr int kWaves = 4;
     long long g = (long long)sm_count() * MINB * kWaves;
     if (tiles < g) g = tiles;
     if (g < 1) g = 1;
-    k_trace_seq_fwd_tile<RPT, MINB, GEN><<<(int)g, kThreads, smem, st>>>(a);
+    k_trace_seq_fwd_tile<RPT, MINB, GEN, BLK, SYNC><<<(int)g, BLK, smem, st>>>(a);
     return cudaGetLastError();
 }
 template <int RPT, int MINB>
 inline cudaError_t launch_tile(const SeqFwdArgs& a, cudaStream_t st) {
     return a.src.kind >= 0 ? launch_tile_g<RPT, MINB, true>(a, st) : launch_tile_g<RPT, MINB, false>(a, st);
 }
-// Which build of the frame-resident forward kernel runs (a.tune, include/rtt_b200.h RTT_MODE_TUNE_*): 1 = 1 ray/thread,
-// 2 = 2 rays (80 regs), 3 = 2 rays (64 regs), 5 = 1 ray at 48 registers / five blocks per SM (C1 -4 %, C2 +3 %, C4 +9 %
-// against 3); 9 = the per-ray kernel of the EXACT variant's structure.  Measured and dropped: 4 rays per thread (128
-// registers, -20 %), 2 rays at 48 registers (spills, -17 %).
-// Default (0): 2 rays per thread at 64 registers (4 blocks / SM) — best on C2 and C4; a short table (a singlet and its
-// sensor) has too little arithmetic per ray to hide the ray loads behind 32 warps, there 1 ray per thread at 48
-// registers (40 warps / SM) wins (C1, 4 rows: 2.69 -> 2.58 ms per 1e8 rays).
-// The choice depends on the table and the caller's mode bits only (no environment, no cached state), so a bundle
-// generated in the kernel and its materialised twin run the same build and stay bit-identical (tests/test_goals.py).
-inline int fwd_tile_for(int S, int tune) { return tune ? tune : (S <= 6 ? 5 : 3); }   // 0 is resolved by the caller (fwd_default_build)
+// large blocks: RPT rays per thread, MINB blocks of BLK threads per SM, lock-step (SYNC) or free-running
+template <int RPT, int MINB, int BLK, bool SYNC>
+inline cudaError_t launch_tile_big(const SeqFwdArgs& a, cudaStream_t st) {
+    return a.src.kind >= 0 ? launch_tile_g<RPT, MINB, true, BLK, SYNC>(a, st) : launch_tile_g<RPT, MINB, false, BLK, SYNC>(a, st);
+}
+// Builds of the frame-resident forward kernel (a.tune, include/rtt_b200.h RTT_MODE_TUNE_*), 256-thread blocks: 1 = 1 ray
+// per thread, 2 = 2 rays (80 regs), 3 = 2 rays (64 regs, 4 blocks / SM), 5 = 1 ray at 48 registers / five blocks per SM;
+// large blocks: 7 = 2 rays, one block of 1024 threads per SM (the default), 6 = 7 with a barrier per tile, 8 = two blocks of
+// 512; 9 = the per-ray kernel of the EXACT variant's structure.  Measured and dropped: 4 rays per thread (128 registers,
+// -20 %), 2 rays at 48 registers (spills, -17 %), 3 rays in a 768-thread block (80 registers: C2 4.21, c4cam 9.63), 1 ray in
+// a 1024-thread block (C2 4.15), the packed-pair kernel in one block of 768 threads (C2 3.82, C1 2.83, C4 6.91).
 
-template <int MINB, bool STREAM, int LOG, int NP, bool GEN>
+template <int MINB, bool STREAM, int LOG, int NP, bool GEN, int BLK = kThreads>
 inline cudaError_t launch_pair_g(const SeqFwdArgs& a, cudaStream_t st) {
-    const size_t smem = PairLayout<LOG, STREAM, NP>::bytes(a.tab.S, a.tab.L);
-    if (cudaError_t e = allow_smem(k_trace_seq_fwd_pair<MINB, STREAM, LOG, NP, GEN>, smem)) return e;
-    const long long tiles = (a.n + PairGeom<NP>::kTile - 1) / PairGeom<NP>::kTile;
+    const size_t smem = PairLayout<LOG, STREAM, NP, BLK>::bytes(a.tab.S, a.tab.L);
+    if (cudaError_t e = allow_smem(k_trace_seq_fwd_pair<MINB, STREAM, LOG, NP, GEN, BLK>, smem)) return e;
+    const long long tiles = (a.n + PairGeom<NP, BLK>::kTile - 1) / PairGeom<NP, BLK>::kTile;
     // persistent blocks, one resident set (tiles are handed out round-robin: tile = block + k * grid); the plain build
     // keeps the tile kernel's four waves (a block that lands on a busier SM costs 1/4 of a launch)
     long long g = (long long)sm_count() * MINB * (STREAM ? 1 : 4);
     if (tiles < g) g = tiles;
     if (g < 1) g = 1;
-    k_trace_seq_fwd_pair<MINB, STREAM, LOG, NP, GEN><<<(int)g, kThreads, smem, st>>>(a);
+    k_trace_seq_fwd_pair<MINB, STREAM, LOG, NP, GEN, BLK><<<(int)g, BLK, smem, st>>>(a);
     return cudaGetLastError();
 }
-template <int MINB, bool STREAM, int LOG, int NP = 1>
+template <int MINB, bool STREAM, int LOG, int NP = 1, int BLK = kThreads>
 inline cudaError_t launch_pair(const SeqFwdArgs& a, cudaStream_t st) {
-    if (STREAM) return launch_pair_g<MINB, STREAM, LOG, NP, false>(a, st);            // streams rays from memory by construction
-    return a.src.kind >= 0 ? launch_pair_g<MINB, false, LOG, NP, true>(a, st) : launch_pair_g<MINB, false, LOG, NP, false>(a, st);
+    if (STREAM) return launch_pair_g<MINB, STREAM, LOG, NP, false, BLK>(a, st);       // streams rays from memory by construction
+    return a.src.kind >= 0 ? launch_pair_g<MINB, false, LOG, NP, true, BLK>(a, st) : launch_pair_g<MINB, false, LOG, NP, false, BLK>(a, st);
 }
 // bulk-async copies need 16-byte aligned global addresses; every full tile starts a multiple of 512 rays into the
 // arrays, so the base pointers decide.  Generated rays have no input to stream.
@@ -1817,19 +1933,24 @@ inline bool pair_can_stream(const SeqFwdArgs& a) {
 
 cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
 #if defined(RTT_APPROX)
-    // Default build (a.tune == 0).  Measured on B200 (profiles/r2_fwd_pair_ab.md): per ray, the packed-pair streaming
-    // kernel saves a fixed amount of issue slots (ray I/O through the copy engine, one packed chain instead of two) but
-    // runs ONE dependency chain per thread at 24 warps / SM, where the tile kernel runs two at 32 — so it wins on short
-    // tables, which are I/O- and issue-bound (C1 4 rows: -2 %, C2 14 rows of which 8 culled: -5 %), and loses on long
-    // ones, which are latency-bound (C4, 17 rows: +20 %).  The library sees the row count only (the table lives in device
-    // memory); the Python layer refines the choice from its host copy of the table (ops._fwd_build_hint).
+    // Default build (a.tune == 0): the frame-resident tile kernel with 2 rays per thread in ONE block of 1024 threads per
+    // SM (64 registers).  Same-box A/B on B200 (profiles/r2_block_size_ab.md, ms per 1e8 rays, C2 / C1 / C4 / c4cam):
+    // 3.65 / 2.35 / 5.47 / 7.27 against 4.00 / 2.46 / 5.81 / 7.77 for the same kernel in four blocks of 256 threads and
+    // 3.92 / 2.51 / 6.92 / 9.44 for the packed-pair streaming kernel (16).  What the large block buys: the table staging,
+    // image-cache set-up and flush of a block are shared by four times as many threads, and the 32 warps of an SM start
+    // together and run the same code at nearly the same time, which the instruction caches like (the same effect, much
+    // larger, in the non-sequential kernel).  One default for every table: a bundle generated in the kernel and its
+    // materialised twin run the same build and stay bit-identical (tests/test_goals.py).
     int build = a.tune;
-    if (build == 0) build = (a.tab.S <= 14) ? 16 : fwd_tile_for(a.tab.S, 0);      // by the table only: see tests/test_goals.py
+    if (build == 0) build = 7;
     switch (build) {
         case 1: return launch_tile<1, 4>(a, st);
         case 2: return launch_tile<2, 3>(a, st);
         case 3: return launch_tile<2, 4>(a, st);
         case 5: return launch_tile<1, 5>(a, st);
+        case 6: return launch_tile_big<2, 1, 1024, true>(a, st);
+        case 7: return launch_tile_big<2, 1, 1024, false>(a, st);
+        case 8: return launch_tile_big<2, 2, 512, false>(a, st);
         case 16: return pair_can_stream(a) ? launch_pair<3, true, 11>(a, st) : launch_pair<3, false, 12>(a, st);
         case 17: return launch_pair<4, false, 12>(a, st);
         case 18: return launch_pair<3, false, 12>(a, st);
@@ -1841,58 +1962,91 @@ cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
     RTT_NAME(k_trace_seq_fwd)<<<grid_for(a.n, 8), kThreads, fwd_smem(a.tab.S, a.tab.L), st>>>(a);
     return cudaGetLastError();
 }
-template <int MINB, bool POSE, int CK, bool LEAN, int GEN>
-inline cudaError_t launch_seq_bwd_ck(const SeqBwdArgs& b, int g, size_t smem, cudaStream_t st) {
-    if (cudaError_t e = allow_smem(RTT_NAME(k_trace_seq_bwd)<MINB, POSE, CK, LEAN, GEN>, smem)) return e;
-    RTT_NAME(k_trace_seq_bwd)<MINB, POSE, CK, LEAN, GEN><<<g, kThreads, smem, st>>>(b);
-    return cudaGetLastError();
-}
-template <int MINB, bool POSE>
-inline cudaError_t launch_seq_bwd_as(const SeqBwdArgs& b, int g, size_t smem, cudaStream_t st) {
-    return b.tab.S <= 24 ? launch_seq_bwd_ck<MINB, POSE, 24, false, 0>(b, g, smem, st)
-                         : launch_seq_bwd_ck<MINB, POSE, RTT_MAX_ROWS, false, 0>(b, g, smem, st);
-}
-#if defined(RTT_APPROX)
-template <int GEN>
-inline cudaError_t launch_seq_bwd_lean(const SeqBwdArgs& b, int g, size_t smem, cudaStream_t st) {
-    return b.tab.S <= 24 ? launch_seq_bwd_ck<4, false, 24, true, GEN>(b, g, smem, st)
-                         : launch_seq_bwd_ck<4, false, RTT_MAX_ROWS, true, GEN>(b, g, smem, st);
-}
-#endif
-cudaError_t RTT_NAME(launch_seq_bwd)(const SeqBwdArgs& a, cudaStream_t st) {
-    size_t smem = bwd_smem(a.tab.S, a.tab.L) + 8 + bwd_queue_bytes();
+template <int MINB, bool POSE, int CK, bool LEAN, int GEN, int BLK = kThreads>
+inline cudaError_t launch_seq_bwd_ck(const SeqBwdArgs& a, cudaStream_t st) {
+    size_t smem = bwd_smem(a.tab.S, a.tab.L) + 8 + bwd_queue_bytes(BLK);
+    if (LEAN) smem += sizeof(Xf) * (size_t)(a.tab.S + 1) + sizeof(unsigned) * (size_t)(a.tab.S + 4);   // frame changes, lean mask, walk list
     // chunk: as large as the queue allows, but small launches still spread over every resident block slot
-    const long long slots = (long long)(sm_count() > 0 ? sm_count() : 1) * 4 * 2;
-    long long chunk = ((a.n + slots - 1) / slots + kThreads - 1) / kThreads * kThreads;
-    if (chunk < 4 * kThreads) chunk = 4 * kThreads;
-    if (chunk > kBwdChunk) chunk = kBwdChunk;
+    const int sms = sm_count() > 0 ? sm_count() : 1;
+    const long long slots = (long long)sms * (BLK == kThreads ? 8 : 2 * MINB);
+    long long chunk = ((a.n + slots - 1) / slots + BLK - 1) / BLK * BLK;
+    if (chunk < 4 * BLK) chunk = 4 * BLK;
+    if (chunk > kBwdChunkIters * BLK) chunk = kBwdChunkIters * BLK;
     SeqBwdArgs b = a;
     b.chunk = (int)chunk;
     const long long chunks = (a.n + chunk - 1) / chunk;
-    long long g = (long long)sm_count() * 8;
+    long long g = slots;
     if (chunks < g) g = chunks;
     if (g < 1) g = 1;
+    if (cudaError_t e = allow_smem(RTT_NAME(k_trace_seq_bwd)<MINB, POSE, CK, LEAN, GEN, BLK>, smem)) return e;
+    RTT_NAME(k_trace_seq_bwd)<MINB, POSE, CK, LEAN, GEN, BLK><<<(int)g, BLK, smem, st>>>(b);
+    return cudaGetLastError();
+}
+template <int MINB, bool POSE>
+inline cudaError_t launch_seq_bwd_as(const SeqBwdArgs& a, cudaStream_t st) {
+    return a.tab.S <= 24 ? launch_seq_bwd_ck<MINB, POSE, 24, false, 0>(a, st)
+                         : launch_seq_bwd_ck<MINB, POSE, RTT_MAX_ROWS, false, 0>(a, st);
+}
+#if defined(RTT_APPROX)
+template <int GEN, int MINB, int BLK>
+inline cudaError_t launch_seq_bwd_lean(const SeqBwdArgs& a, cudaStream_t st) {
+    return a.tab.S <= 24 ? launch_seq_bwd_ck<MINB, false, 24, true, GEN, BLK>(a, st)
+                         : launch_seq_bwd_ck<MINB, false, RTT_MAX_ROWS, true, GEN, BLK>(a, st);
+}
+#endif
+cudaError_t RTT_NAME(launch_seq_bwd)(const SeqBwdArgs& a, cudaStream_t st) {
     // a.tune & 7 = resident blocks per SM the build is compiled for.  Without pose gradients the kernel needs 64-72
     // registers: four resident blocks (measured: C2 -10 %, C4 -5 % against three); with them three blocks (80 registers,
     // a few spills) beat two (~110 registers) by 4-8 %.  a.tune & 8: no lean path (every ray through the general code).
+    // a.tune & 16: the lean build in four blocks of 256 threads instead of one block of 1024 per SM (A/B).
     const int minb = a.tune & 7;
     if (a.scalar_grads) {
 #if defined(RTT_APPROX)
         if (!(a.tune & 8) && minb != 3 && !a.g_pos && !a.g_dir && !a.g_inten) {
-            smem += sizeof(Xf) * (size_t)(a.tab.S + 1) + sizeof(unsigned) * (size_t)(a.tab.S + 4);   // frame changes, lean mask, walk list
-            return a.src.kind >= 0 ? launch_seq_bwd_lean<2>(b, (int)g, smem, st) : launch_seq_bwd_lean<1>(b, (int)g, smem, st);
+            if (a.tune & 16)
+                return a.src.kind >= 0 ? launch_seq_bwd_lean<2, 4, kThreads>(a, st) : launch_seq_bwd_lean<1, 4, kThreads>(a, st);
+            return a.src.kind >= 0 ? launch_seq_bwd_lean<2, 1, 1024>(a, st) : launch_seq_bwd_lean<1, 1, 1024>(a, st);
         }
 #endif
-        if (minb == 3) return launch_seq_bwd_as<3, false>(b, (int)g, smem, st);
-        return launch_seq_bwd_as<4, false>(b, (int)g, smem, st);
+        if (minb == 3) return launch_seq_bwd_as<3, false>(a, st);
+        return launch_seq_bwd_as<4, false>(a, st);
     }
-    if (minb == 2) return launch_seq_bwd_as<2, true>(b, (int)g, smem, st);
-    return launch_seq_bwd_as<3, true>(b, (int)g, smem, st);
+    if (minb == 2) return launch_seq_bwd_as<2, true>(a, st);
+    return launch_seq_bwd_as<3, true>(a, st);
 }
 cudaError_t RTT_NAME(launch_nonseq_fwd)(const NonseqFwdArgs& a, cudaStream_t st) {
     if (cudaError_t e = allow_smem(RTT_NAME(k_trace_nonseq_fwd), nonseq_fwd_smem(a.tab.S, a.tab.L))) return e;
     if (a.hit_seq && a.nbounces > 0)
         if (cudaError_t e = cudaMemsetAsync(a.hit_seq, 0xFF, (size_t)a.n * a.nbounces, st)) return e;
+    // Default: the lock-step build, one block of 1024 threads per SM with one barrier per trip (C5: 67.6 -> 56.0 ms EXACT,
+    // 48.8 -> 44.0 FAST; barriers inside the search cost more than they save: profiles/r2_nonseq_lockstep.md).
+    // a.tune (A/B): 7 = the free-running kernel of 256-thread blocks; 1 = 256 threads with the barrier; 3 / 4 / 5 = extra
+    // barriers (every 4th row / before the interaction / both halves of the search); 6 = 1024 threads, no barrier.
+    if (a.tune != 7) {
+        const size_t smem = nonseq_fwd_smem(a.tab.S, a.tab.L);
+        const int sms = sm_count() > 0 ? sm_count() : 1;
+#define RTT_LS(BLOCK, SYNC, WAVES)                                                                                  \
+        {                                                                                                           \
+            if (cudaError_t e = allow_smem(RTT_NAME(k_trace_nonseq_fwd_ls)<BLOCK, SYNC>, smem)) return e;           \
+            long long g = (long long)sms * (1024 / BLOCK) * WAVES;                                                  \
+            const long long tiles = (a.n + BLOCK - 1) / BLOCK;                                                      \
+            if (tiles < g) g = tiles;                                                                               \
+            RTT_NAME(k_trace_nonseq_fwd_ls)<BLOCK, SYNC><<<(int)(g < 1 ? 1 : g), BLOCK, smem, st>>>(a);             \
+            return cudaGetLastError();                                                                              \
+        }
+        if (a.tune == 1) RTT_LS(256, 1, 2)
+        if (a.tune == 3) RTT_LS(1024, 3, 1)
+        if (a.tune == 4) RTT_LS(1024, 4, 1)
+        if (a.tune == 5) RTT_LS(1024, 5, 1)
+#if defined(RTT_APPROX)
+        if (a.tune == 2) RTT_LS(1024, 1, 1)
+        RTT_LS(1024, 0, 1)                 // FAST arithmetic: the large block alone (43.0 ms; with the barrier 44.1)
+#else
+        if (a.tune == 6) RTT_LS(1024, 0, 1)
+        RTT_LS(1024, 1, 1)                 // EXACT: 56.0 ms with the barrier, 64.9 without
+#endif
+#undef RTT_LS
+    }
     RTT_NAME(k_trace_nonseq_fwd)<<<grid_for(a.n, 8), kThreads, nonseq_fwd_smem(a.tab.S, a.tab.L), st>>>(a);
     return cudaGetLastError();
 }

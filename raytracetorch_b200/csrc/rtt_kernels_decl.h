@@ -85,6 +85,7 @@ struct NonseqFwdArgs {
     SensorDev sens[RTT_MAX_SENSORS];
     int n_sens, nbounces;
     long long n;
+    int tune;                   // (mode & RTT_MODE_TUNE_MASK) >> RTT_MODE_TUNE_SHIFT: kernel build, 0 = default
 };
 
 struct NonseqBwdArgs {

@@ -47,6 +47,7 @@ def _env_tune(name: str, zero_means: int = 0) -> int:
 
 _tune_fwd = _env_tune("RTT_FWD_TILE", zero_means=9)
 _tune_bwd = _env_tune("RTT_BWD_MINB")
+_tune_nonseq = _env_tune("RTT_NS_TUNE")
 
 
 def set_tuning(fwd: Optional[int] = None, bwd: Optional[int] = None):
@@ -64,18 +65,11 @@ def _with_tune(mode: int, tune: int) -> int:
 
 
 def _fwd_build_hint(i_host) -> int:
-    """Kernel build of the sequential forward trace for rays that live in device memory, from the host copy of the
-    table's int block: the packed-pair streaming kernel (16) when the walk is SHORT — rows that are not lens-edge rows
-    plus one cull test per run of edge rows <= 10 — else 0 (the library's choice by row count).  Measured on B200:
-    profiles/r2_fwd_pair_ab.md (C1 / C2 gain 2-5 %, C4 with 15 effective rows loses 20 %)."""
-    edge = (C.SHAPE_SPHERIC_EDGE, C.SHAPE_CYL_EDGE)
-    eff, prev_edge = 0, False
-    for m in i_host:
-        is_edge = m[C.I_SHAPE] in edge
-        if not is_edge or not prev_edge:
-            eff += 1
-        prev_edge = is_edge
-    return 16 if eff <= 10 else (5 if len(i_host) <= 6 else 3)
+    """Kernel build of the sequential forward trace chosen from the host copy of the table: 0 = the library's default
+    (since the block-size A/B of round 2 — profiles/r2_block_size_ab.md — one build wins on every BASELINE table: the
+    tile kernel with 2 rays per thread in one 1024-thread block per SM; the packed-pair streaming kernel (16) that short
+    walks used to get stays selectable with ``set_tuning(fwd=16)`` / ``RTT_FWD_TILE=16``)."""
+    return 0
 
 
 def set_default_mode(mode: int, nonseq: Optional[int] = None):
@@ -235,7 +229,7 @@ def _nonseq_fwd_body(dev, n, pos, dir, intensity, wavelength, src, table_f, tabl
         lib.call("rtt_trace_nonseq_fwd", _ptr(pos), _ptr(dir), _ptr(intensity), _ptr(wavelength),
                  ct.byref(src) if src is not None else None,
                  _ptr(opos), _ptr(odir), _ptr(oint), seq.data_ptr(), nh.data_ptr(),
-                 ct.byref(req), sens, cnt, nbounces, n, mode, _stream(table_f))
+                 ct.byref(req), sens, cnt, nbounces, n, _with_tune(mode, _tune_nonseq), _stream(table_f))
     return [opos, odir, oint, seq, nh, records, images, counts]
 
 
