@@ -84,13 +84,14 @@ enum { RTT_MODE_SCALAR_GRADS = 0x100, RTT_MODE_ARITH_MASK = 0xff };
  * compiled instantiation of the sequential forward / adjoint kernel runs.  Results are the same for every value
  * (FAST builds agree to rounding); it exists for performance sweeps and A/B measurements, and it is the ONLY tuning
  * input — the library reads no environment variables.
- *   rtt_trace_seq_fwd (FAST): 0 / 7 = tile kernel, 2 rays/thread, one block of 1024 threads per SM (default);
- *     6 = 7 with a barrier per tile; 8 = two blocks of 512; 1 = tile, 1 ray/thread, 4 blocks of 256 per SM; 2 = tile,
+ *   rtt_trace_seq_fwd (FAST): 0 / 12 = tile kernel, 2 rays/thread, one persistent block of 1024 threads per SM
+ *     (default); 7 / 13 = the same in four / two waves of blocks; 6 = 7 with a barrier per tile; 8 = two blocks of 512; 1 = tile, 1 ray/thread, 4 blocks of 256 per SM; 2 = tile,
  *     2 rays, 3 blocks; 3 = tile, 2 rays, 4 blocks; 5 = tile, 1 ray, 5 blocks; 9 = per-ray kernel in the reference's
  *     operation order; 16 = packed ray pairs (f32x2 arithmetic) with bulk-async (TMA) ray streaming, 3 blocks/SM;
  *     17 = same, 4 blocks/SM; 18 = packed pairs with plain global loads / stores
  *   rtt_trace_seq_bwd: low 3 bits 2 / 3 / 4 = resident blocks per SM the adjoint build is compiled for; bit 8 (value 8) =
- *     no lean path (every ray through the general adjoint, csrc/rtt_lean.cuh)
+ *     no lean path (every ray through the general adjoint, csrc/rtt_lean.cuh); bit 16 = the lean build in 256-thread
+ *     blocks whatever the launch size (default: one 1024-thread block per SM from 2^25 rays on)
  *   rtt_trace_nonseq_fwd: 0 = one block of 1024 threads per SM (EXACT: with a barrier per bounce trip); 7 = 256-thread
  *     blocks running free (the round-1 kernel); 1, 3..6 = other barrier placements (A/B) */
 enum { RTT_MODE_TUNE_SHIFT = 16, RTT_MODE_TUNE_MASK = 0xff0000 };

@@ -1015,7 +1015,7 @@ __host__ __device__ inline size_t bwd_queue_bytes(int threads) { return sizeof(u
 // take the frame-resident replay / reverse steps of rtt_lean.cuh; the rest of the queue runs the general code below.
 // GEN: 0 = rays from memory or from the ray source (run-time test), 1 = memory only, 2 = generated only (see fetch_ray_t).
 // BLK = threads per block (256, or one block of 1024 per SM: see the block-size A/B of the forward kernels).
-template <int MINB, bool POSE, int CK, bool LEAN, int GEN, int BLK = BLK>
+template <int MINB, bool POSE, int CK, bool LEAN, int GEN, int BLK = kThreads>
 __global__ void __launch_bounds__(BLK, MINB) RTT_NAME(k_trace_seq_bwd)(const __grid_constant__ SeqBwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.tab.S, L = a.tab.L;
@@ -1871,13 +1871,12 @@ inline cudaError_t allow_smem(Kern kern, size_t bytes) {
 }
 
 #if defined(RTT_APPROX)
-template <int RPT, int MINB, bool GEN, int BLK = kThreads, bool SYNC = false>
+template <int RPT, int MINB, bool GEN, int BLK = kThreads, bool SYNC = false, int kWaves = 4>
 inline cudaError_t launch_tile_g(const SeqFwdArgs& a, cudaStream_t st) {
     const size_t smem = tile_smem_bytes(a.tab.S, a.tab.L);
     if (cudaError_t e = allow_smem(k_trace_seq_fwd_tile<RPT, MINB, GEN, BLK, SYNC>, smem)) return e;
     const long long tiles = (a.n + (long long)BLK * RPT - 1) / ((long long)BLK * RPT);
     // several waves of grid-striding blocks: a block that lands on a busier SM costs 1/kWaves of a launch
-    constexpr int kWaves = 4;
     long long g = (long long)sm_count() * MINB * kWaves;
     if (tiles < g) g = tiles;
     if (g < 1) g = 1;
@@ -1889,14 +1888,14 @@ inline cudaError_t launch_tile(const SeqFwdArgs& a, cudaStream_t st) {
     return a.src.kind >= 0 ? launch_tile_g<RPT, MINB, true>(a, st) : launch_tile_g<RPT, MINB, false>(a, st);
 }
 // large blocks: RPT rays per thread, MINB blocks of BLK threads per SM, lock-step (SYNC) or free-running
-template <int RPT, int MINB, int BLK, bool SYNC>
+template <int RPT, int MINB, int BLK, bool SYNC, int WAVES = 4>
 inline cudaError_t launch_tile_big(const SeqFwdArgs& a, cudaStream_t st) {
-    return a.src.kind >= 0 ? launch_tile_g<RPT, MINB, true, BLK, SYNC>(a, st) : launch_tile_g<RPT, MINB, false, BLK, SYNC>(a, st);
+    return a.src.kind >= 0 ? launch_tile_g<RPT, MINB, true, BLK, SYNC, WAVES>(a, st) : launch_tile_g<RPT, MINB, false, BLK, SYNC, WAVES>(a, st);
 }
 // Builds of the frame-resident forward kernel (a.tune, include/rtt_b200.h RTT_MODE_TUNE_*), 256-thread blocks: 1 = 1 ray
 // per thread, 2 = 2 rays (80 regs), 3 = 2 rays (64 regs, 4 blocks / SM), 5 = 1 ray at 48 registers / five blocks per SM;
-// large blocks: 7 = 2 rays, one block of 1024 threads per SM (the default), 6 = 7 with a barrier per tile, 8 = two blocks of
-// 512; 9 = the per-ray kernel of the EXACT variant's structure.  Measured and dropped: 4 rays per thread (128 registers,
+// large blocks: 12 = 2 rays, one persistent block of 1024 threads per SM (the default), 7 / 13 = the same in four / two waves
+// of blocks, 6 = 7 with a barrier per tile, 8 = two blocks of 512; 9 = the per-ray kernel of the EXACT variant's structure.  Measured and dropped: 4 rays per thread (128 registers,
 // -20 %), 2 rays at 48 registers (spills, -17 %), 3 rays in a 768-thread block (80 registers: C2 4.21, c4cam 9.63), 1 ray in
 // a 1024-thread block (C2 4.15), the packed-pair kernel in one block of 768 threads (C2 3.82, C1 2.83, C4 6.91).
 
@@ -1941,8 +1940,10 @@ cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
     // together and run the same code at nearly the same time, which the instruction caches like (the same effect, much
     // larger, in the non-sequential kernel).  One default for every table: a bundle generated in the kernel and its
     // materialised twin run the same build and stay bit-identical (tests/test_goals.py).
+    // The blocks are persistent (one wave: a 1024-thread block sets up its table, frame changes and image cache once per
+    // launch; with four waves C3's forward at 1e7 rays paid 4 % of a step for it: 1.054 -> 1.011 ms, C2 3.656 -> 3.624).
     int build = a.tune;
-    if (build == 0) build = 7;
+    if (build == 0) build = 12;
     switch (build) {
         case 1: return launch_tile<1, 4>(a, st);
         case 2: return launch_tile<2, 3>(a, st);
@@ -1951,6 +1952,8 @@ cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
         case 6: return launch_tile_big<2, 1, 1024, true>(a, st);
         case 7: return launch_tile_big<2, 1, 1024, false>(a, st);
         case 8: return launch_tile_big<2, 2, 512, false>(a, st);
+        case 12: return launch_tile_big<2, 1, 1024, false, 1>(a, st);
+        case 13: return launch_tile_big<2, 1, 1024, false, 2>(a, st);
         case 16: return pair_can_stream(a) ? launch_pair<3, true, 11>(a, st) : launch_pair<3, false, 12>(a, st);
         case 17: return launch_pair<4, false, 12>(a, st);
         case 18: return launch_pair<3, false, 12>(a, st);
@@ -1967,9 +1970,11 @@ inline cudaError_t launch_seq_bwd_ck(const SeqBwdArgs& a, cudaStream_t st) {
     size_t smem = bwd_smem(a.tab.S, a.tab.L) + 8 + bwd_queue_bytes(BLK);
     if (LEAN) smem += sizeof(Xf) * (size_t)(a.tab.S + 1) + sizeof(unsigned) * (size_t)(a.tab.S + 4);   // frame changes, lean mask, walk list
     // chunk: as large as the queue allows, but small launches still spread over every resident block slot
+    // (large blocks: one persistent block per SM; ~16 chunks per block keep the tail of the launch short)
     const int sms = sm_count() > 0 ? sm_count() : 1;
-    const long long slots = (long long)sms * (BLK == kThreads ? 8 : 2 * MINB);
-    long long chunk = ((a.n + slots - 1) / slots + BLK - 1) / BLK * BLK;
+    const long long slots = (long long)sms * (BLK == kThreads ? 8 : MINB);
+    const long long parts = BLK == kThreads ? slots : slots * 16;
+    long long chunk = ((a.n + parts - 1) / parts + BLK - 1) / BLK * BLK;
     if (chunk < 4 * BLK) chunk = 4 * BLK;
     if (chunk > kBwdChunkIters * BLK) chunk = kBwdChunkIters * BLK;
     SeqBwdArgs b = a;
@@ -2003,7 +2008,9 @@ cudaError_t RTT_NAME(launch_seq_bwd)(const SeqBwdArgs& a, cudaStream_t st) {
     if (a.scalar_grads) {
 #if defined(RTT_APPROX)
         if (!(a.tune & 8) && minb != 3 && !a.g_pos && !a.g_dir && !a.g_inten) {
-            if (a.tune & 16)
+            // one 1024-thread block per SM from ~3e7 rays on (C2, 1e8 rays: 3.31 -> 3.19 ms, C4 12.55 -> 12.12); below, the
+            // chunks of a large block are too few to balance the SMs (C3, 1e7 rays: 0.526 ms in 256-thread blocks, 0.548 in one)
+            if ((a.tune & 16) || a.n < (1ll << 25))
                 return a.src.kind >= 0 ? launch_seq_bwd_lean<2, 4, kThreads>(a, st) : launch_seq_bwd_lean<1, 4, kThreads>(a, st);
             return a.src.kind >= 0 ? launch_seq_bwd_lean<2, 1, 1024>(a, st) : launch_seq_bwd_lean<1, 1, 1024>(a, st);
         }

@@ -76,10 +76,15 @@ def test_camera_source_matches_generate_rays(run_exact):
     assert 0 < dev <= 0.51 * px * 1.01
 
 
+@pytest.mark.parametrize("variant", ["exact", "fast"])
 @pytest.mark.parametrize("name", ["c1_singlet_physical", "c2_cylindrical"])
-def test_trace_from_source_equals_trace_of_its_rays(run_fast, name):
-    """The trace kernels generate the rays of a source in registers: same outputs, bit for bit, as tracing
-    the bundle materialised by rtt_sample_bundle — forward and adjoint."""
+def test_trace_from_source_equals_trace_of_its_rays(runner_of, name, variant):
+    """The trace kernels generate the rays of a source in registers: same rays, bit for bit, as the bundle materialised
+    by rtt_sample_bundle, hence the same trace — forward and adjoint.  EXACT: every output bit for bit.  FAST: the builds
+    for generated rays and for rays in memory are separate instantiations (the ray-source code is compiled out of the
+    latter), and the compiler contracts their multiply-adds independently: masks and intensities equal, points and
+    directions to rounding (2e-6 relative)."""
+    run_fast = runner_of(variant)
     d = parity.load(name)
     n = 5000
     pose = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, -10.0], np.float32)
@@ -87,14 +92,22 @@ def test_trace_from_source_equals_trace_of_its_rays(run_fast, name):
     rays = run_fast.sample(src, n)
     a = run_fast.trace_seq(d["table_f"], d["table_i"], rays["pos"], rays["dir"], rays["intensity"], sensor_specs=[None])
     b = run_fast.trace_seq_src(d["table_f"], d["table_i"], src, n, sensor_specs=[None])
-    for k in ("pos", "dir", "intensity", "hitmask"):
+    for k in ("intensity", "hitmask"):
         np.testing.assert_array_equal(a[k], b[k])
-    np.testing.assert_array_equal(a["sensors"][0][0], b["sensors"][0][0])
+    if variant == "exact":
+        for k in ("pos", "dir"):
+            np.testing.assert_array_equal(a[k], b[k])
+        np.testing.assert_array_equal(a["sensors"][0][0], b["sensors"][0][0])
+    else:
+        scale = float(np.abs(a["pos"]).max())
+        assert parity.vec_rel(b["pos"], a["pos"], floor=scale).max() <= 2e-6
+        assert parity.vec_rel(b["dir"], a["dir"]).max() <= 2e-6
+        np.testing.assert_allclose(b["sensors"][0][0], a["sensors"][0][0], rtol=0, atol=2e-6 * scale)
     assert (a["hitmask"] != 0).mean() > 0.5
     # records only: no final-ray outputs
     c = run_fast.trace_seq_src(d["table_f"], d["table_i"], src, n, sensor_specs=[None], want_rays=False)
     assert c["pos"] is None
-    np.testing.assert_array_equal(c["sensors"][0][0], a["sensors"][0][0])
+    np.testing.assert_array_equal(c["sensors"][0][0], b["sensors"][0][0])      # same build, with and without ray outputs
     g_rec = np.random.default_rng(0).standard_normal((n, 4)).astype(np.float32)
     ti = d["table_i"].copy()
     ti[:, C.I_FLAGS] = C.FLAG_GRAD_CK | C.FLAG_GRAD_POSE_S | C.FLAG_GRAD_IOR        # ask for parameter gradients
