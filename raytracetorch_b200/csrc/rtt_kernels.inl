@@ -880,6 +880,7 @@ __global__ void __launch_bounds__(BLK, MINB) k_trace_seq_fwd_pair(const __grid_c
     if (STREAM && threadIdx.x == 0) bulk_wait_all0();                   // the slot must outlive the stores that read it
     img_cache_flush(cache, a.sens);
 }
+
 #endif  // RTT_APPROX
 
 // ============================================================================================
@@ -1897,7 +1898,11 @@ inline cudaError_t launch_tile_big(const SeqFwdArgs& a, cudaStream_t st) {
 // large blocks: 12 = 2 rays, one persistent block of 1024 threads per SM (the default), 7 / 13 = the same in four / two waves
 // of blocks, 6 = 7 with a barrier per tile, 8 = two blocks of 512; 9 = the per-ray kernel of the EXACT variant's structure.  Measured and dropped: 4 rays per thread (128 registers,
 // -20 %), 2 rays at 48 registers (spills, -17 %), 3 rays in a 768-thread block (80 registers: C2 4.21, c4cam 9.63), 1 ray in
-// a 1024-thread block (C2 4.15), the packed-pair kernel in one block of 768 threads (C2 3.82, C1 2.83, C4 6.91).
+// a 1024-thread block (C2 4.15), the packed-pair kernel in one block of 768 threads (C2 3.82, C1 2.83, C4 6.91), 2 rays in
+// one block of 896 / 768 threads with 72 / 80 registers and no spills (C2 3.88 / 4.12 against 3.63 at 1024 threads and 64
+// registers with 84 bytes of spills: resident warps beat registers), and the default build with the pair kernel's bulk-async
+// ray streaming (2048-ray tiles in a two-slot ring, 2 x 80 KB: correct, but the block-wide barrier per tile that hands the
+// slot to the elected thread stalls 32 warps at once — C2 3.84, C1 2.90, C4 5.74 against 3.63 / 2.30 / 5.43).
 
 template <int MINB, bool STREAM, int LOG, int NP, bool GEN, int BLK = kThreads>
 inline cudaError_t launch_pair_g(const SeqFwdArgs& a, cudaStream_t st) {

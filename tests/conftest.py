@@ -47,6 +47,8 @@ def _runner(backend, variant):
     # (include/rtt_b200.h RTT_MODE_TUNE_*): "pair" = packed ray pairs with bulk-async ray streaming, "pair_plain" =
     # the same arithmetic with plain loads / stores, "tile" = the scalar frame-resident tile kernel
     # "nonseq_fast": the explicit opt-in of the non-sequential entries to the FAST arithmetic (RTT_MODE_NONSEQ_FAST)
+    # "fast" = the default build (tile kernel, one persistent 1024-thread block per SM); "tile" = the same kernel in
+    # 256-thread blocks
     return GpuSim({"exact": 1, "fast": 0, "pair": 16 << 16, "pair_plain": 18 << 16, "tile": 3 << 16,
                    "nonseq_fast": 0x400}[variant])
 

@@ -36,8 +36,8 @@ class Arena:
 
 
 @pytest.mark.parametrize("misalign", [0, 4])
-@pytest.mark.parametrize("tune", [16, 18, 3, 5, 9])
-@pytest.mark.parametrize("n", [1, 511, 512, 513, 1024, 1536, 20011])
+@pytest.mark.parametrize("tune", [0, 12, 7, 8, 16, 18, 3, 5, 9])         # 0 / 12: the default (one 1024-thread block per SM)
+@pytest.mark.parametrize("n", [1, 511, 512, 513, 1024, 1536, 2047, 2048, 2049, 20011])
 def test_sequential_forward_stays_inside_its_output_buffers(n, tune, misalign):
     from raytracetorch_b200 import _cabi
     from gpusim import GpuSim, _dev, _p
@@ -94,3 +94,55 @@ def test_sequential_adjoint_stays_inside_its_output_buffers(n, rtt_ns):
     assert arena.guards_intact(), "the adjoint wrote outside its output buffers"
     assert parity.grad_rel(o[0].cpu().numpy().reshape(n, 3), want["g_pos"]) < 1e-6
     assert parity.grad_rel(o[3].cpu().numpy().reshape(S, C.ROW_G), want["g_table"]) < 1e-4
+
+
+@pytest.mark.parametrize("n", [1, 4095, 4097, 70001, (1 << 25) + 12345])
+def test_lean_adjoint_stays_inside_its_gradient_table(n, rtt_ns):
+    """The lean adjoint path (csrc/rtt_lean.cuh; scalar gradients, no ray-gradient outputs) in both launch shapes — four
+    256-thread blocks per SM below 2^25 rays, one 1024-thread block per SM from there on: the gradient table sits between
+    guard zones, and equals the general adjoint's (tune bit 8) to summation order."""
+    import raytracetorch_b200 as rtt
+    import scenes
+    from raytracetorch_b200 import codes as C
+    from gpusim import GpuSim, _dev, _p
+    els = scenes.c2_cylindrical(rtt_ns)
+    for el in els:
+        for s_ in getattr(el.shape, "surfaces", []):
+            if hasattr(s_, "c") and isinstance(s_.c, torch.nn.Parameter):
+                s_.c.requires_grad_(True)
+    tab = rtt.compile_elements(els)
+    tf, ti = tab.f.detach().numpy(), tab.i.numpy()
+    assert rtt.ops.adjoint_hint(tab) == rtt.ops.MODE_SCALAR_GRADS
+    S = tf.shape[0]
+    g = torch.Generator(device="cuda").manual_seed(11)
+    th = torch.rand(n, device="cuda", generator=g) * (2 * np.pi)
+    r = torch.sqrt(torch.rand(n, device="cuda", generator=g)) * 8.0
+    pos = torch.stack([r * torch.cos(th), r * torch.sin(th), torch.full_like(r, -10.0)], 1).contiguous()
+    del th, r
+    dirs = torch.zeros_like(pos)
+    dirs[:, 2] = 1.0
+    inten = torch.ones(n, device="cuda")
+    sim = GpuSim(0)
+    req, hold = sim._table(tf, ti, None, None)
+    opos, odir, oint = torch.empty_like(pos), torch.empty_like(dirs), torch.empty_like(inten)
+    mask = torch.zeros(n, dtype=torch.int64, device="cuda")
+    sim.lib.call("rtt_trace_seq_fwd", _p(pos), _p(dirs), _p(inten), 0, None, _p(opos), _p(odir), _p(oint), _p(mask),
+                 ct.byref(req), None, 0, n, sim.mode, sim._stream())
+    g_pos = torch.zeros_like(opos)
+    g_pos[:, :2] = 2.0 * oint[:, None] * opos[:, :2]
+    del odir
+    out = {}
+    for name, extra in (("lean", 0), ("general", 8 << 16)):
+        arena = Arena([4 * S * C.ROW_G])
+        gt = arena.view(0, torch.float32)
+        gt.zero_()
+        sim.lib.call("rtt_trace_seq_bwd", _p(pos), _p(dirs), _p(inten), 0, None, _p(mask), _p(g_pos), 0, 0, None,
+                     0, 0, 0, gt.data_ptr(), 0, ct.byref(req), 0, n, sim.mode | rtt.ops.MODE_SCALAR_GRADS | extra,
+                     sim._stream())
+        torch.cuda.synchronize()
+        assert arena.guards_intact(), f"the {name} adjoint wrote outside its gradient table"
+        out[name] = gt.cpu().numpy().reshape(S, C.ROW_G).copy()
+    if n > 1000:
+        assert np.abs(out["general"][:, C.F_C]).sum() > 0
+        assert parity.grad_rel(out["lean"][:, C.F_C:C.N_DIFF], out["general"][:, C.F_C:C.N_DIFF]) < 1e-4
+    assert not out["lean"][:, :C.F_C].any()
