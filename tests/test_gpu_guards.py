@@ -146,3 +146,46 @@ def test_lean_adjoint_stays_inside_its_gradient_table(n, rtt_ns):
         assert np.abs(out["general"][:, C.F_C]).sum() > 0
         assert parity.grad_rel(out["lean"][:, C.F_C:C.N_DIFF], out["general"][:, C.F_C:C.N_DIFF]) < 1e-4
     assert not out["lean"][:, :C.F_C].any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c5_nonsequential", "x2_nonsequential"])
+def test_nonsequential_forward_builds_agree_bit_for_bit(name):
+    """The non-sequential forward in EXACT arithmetic: the default (one 1024-thread block per SM, a barrier per bounce
+    trip), the free-running 256-thread kernel of round 1 (tune 7) and the other barrier placements (1, 3..6) run the same
+    per-ray arithmetic — every output equal bit for bit, sensor images to accumulation order."""
+    from gpusim import GpuSim
+    d = parity.load(name)
+    nb = int(d["nbounces"])
+    reps = 40                                                # enough rays for several trips of every block
+    pos, dr, inten = (np.tile(d[k], (reps,) + (1,) * (d[k].ndim - 1)) for k in ("in_pos", "in_dir", "in_intensity"))
+    spec = [(64, 64, -5.0, 5.0, -5.0, 5.0, 1)]
+    ref = GpuSim(1 | (7 << 16)).trace_nonseq(d["table_f"], d["table_i"], pos, dr, inten, nb, sensor_specs=spec)
+    assert (ref["nb"] > 0).mean() > 0.3
+    for tune in (0, 1, 3, 4, 5, 6):
+        out = GpuSim(1 | (tune << 16)).trace_nonseq(d["table_f"], d["table_i"], pos, dr, inten, nb, sensor_specs=spec)
+        for k in ("pos", "dir", "intensity", "seq", "nb"):
+            np.testing.assert_array_equal(out[k], ref[k], err_msg=f"tune {tune}: {k}")
+        np.testing.assert_array_equal(out["sensors"][0][0], ref["sensors"][0][0])
+        img, img_ref = out["sensors"][0][1], ref["sensors"][0][1]
+        assert np.abs(img - img_ref).sum() <= 1e-5 * max(np.abs(img_ref).sum(), 1.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c2_cylindrical", "c4_camera_lens", "c1_singlet_physical"])
+def test_sequential_forward_builds_agree(name):
+    """FAST builds of the sequential forward against each other: the default (tile kernel, one persistent 1024-thread
+    block per SM), the same kernel in 256- and 512-thread blocks, with a barrier per tile, and the packed-pair kernels —
+    identical hit masks and intensities, points and directions to rounding (north_star: 1e-5; measured <= 2e-6)."""
+    from gpusim import GpuSim
+    d = parity.load(name)
+    reps = 7
+    pos, dr, inten = (np.tile(d[k], (reps,) + (1,) * (d[k].ndim - 1)) for k in ("in_pos", "in_dir", "in_intensity"))
+    ref = GpuSim(3 << 16).trace_seq(d["table_f"], d["table_i"], pos, dr, inten)
+    scale = float(np.abs(ref["pos"][np.isfinite(ref["pos"]).all(1)]).max())
+    for tune in (0, 12, 7, 13, 6, 8, 5, 16, 18):
+        out = GpuSim(tune << 16).trace_seq(d["table_f"], d["table_i"], pos, dr, inten)
+        np.testing.assert_array_equal(out["hitmask"], ref["hitmask"], err_msg=f"tune {tune}")
+        np.testing.assert_array_equal(out["intensity"], ref["intensity"], err_msg=f"tune {tune}")
+        assert parity.vec_rel(out["pos"], ref["pos"], floor=scale).max() <= 2e-6, tune
+        assert parity.vec_rel(out["dir"], ref["dir"]).max() <= 2e-6, tune
