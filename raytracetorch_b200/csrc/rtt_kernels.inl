@@ -415,13 +415,25 @@ __global__ void __launch_bounds__(BLK, MINB) k_trace_seq_fwd_tile(const __grid_c
         unsigned long long mask[RPT];
         int lam[RPT];
         bool act[RPT], odd[RPT];
+        // Rays in memory: the loads of ALL of this thread's rays are issued before the first value is consumed (one DRAM
+        // round trip per tile instead of RPT: written as "load ray, look up its wavelength, load the next ray" the compiler
+        // keeps that order, and the warps of a persistent block reach the top of a tile together, so nobody hides it).
+        // A ray beyond the bundle reads the last ray's data (a valid address, no branch) and is switched off below.
+        RayIn rin[RPT];
+        if (!GEN) {
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+                const long long i = i0 + (long long)j * BLK;
+                rin[j] = fetch_ray_t<false>(a, skey, i < a.n ? i : a.n - 1, L > 0);
+            }
+        }
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
             const long long i = i0 + (long long)j * BLK;
             p[j] = v3(0.0f, 0.0f, 0.0f); d[j] = v3(0.0f, 0.0f, 0.0f); I[j] = 0.0f; lam[j] = 0; mask[j] = 0ull;
             act[j] = false; odd[j] = false;
             if (i < a.n) {
-                const RayIn ray = fetch_ray_t<GEN>(a, skey, i, L > 0);
+                const RayIn ray = GEN ? fetch_ray_t<true>(a, skey, i, L > 0) : rin[j];
                 p[j] = ray.p; d[j] = ray.d; I[j] = ray.I;
                 lam[j] = (L > 0) ? wavelength_index(T, L, ray.wav) : 0;
                 act[j] = finite_ray(ray.p, ray.d) && regular_dir(ray.d);
