@@ -79,7 +79,17 @@ __device__ __forceinline__ void stage_table(const TableDev& tab, SmemTable& T) {
 __device__ __forceinline__ int wavelength_index(const SmemTable& T, int L, float w) {
     int best = 0;
     float bd = fabsf(w - T.lut_w[0]);
-    for (int l = 1; l < L; ++l) {
+    // straight-line for up to four sample wavelengths (the usual F / d / C triple): the rolled loop unrolls into an
+    // eight-wide body plus remainder chains that a three-entry table only jumps through
+#pragma unroll
+    for (int l = 1; l < 4; ++l) {
+        if (l < L) {
+            const float dd = fabsf(w - T.lut_w[l]);
+            if (dd < bd) { bd = dd; best = l; }
+        }
+    }
+#pragma unroll 1
+    for (int l = 4; l < L; ++l) {
         const float dd = fabsf(w - T.lut_w[l]);
         if (dd < bd) { bd = dd; best = l; }
     }
