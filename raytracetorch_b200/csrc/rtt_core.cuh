@@ -251,7 +251,7 @@ RTT_HD bool surface_in_bounds(const RowDev& R, V3 h) {
         case RTT_BOUND_DISK:                                            // :60-64
             return (h.x * h.x + h.y * h.y) <= R.f[D_SB0SQ];
         case RTT_BOUND_RECT:                                            // :77-82
-            return (fabsf(h.x) <= sb[0]) && (fabsf(h.y) <= sb[1]);
+            return (fabsf(h.x) <= sb[0]) & (fabsf(h.y) <= sb[1]);
         case RTT_BOUND_ELLIPSE: {                                       // :98-106
             const float u = h.x * sb[2] - h.y * sb[3];
             const float v = h.x * sb[3] + h.y * sb[2];
@@ -261,7 +261,7 @@ RTT_HD bool surface_in_bounds(const RowDev& R, V3 h) {
         case RTT_BOUND_HALF:                                            // :123-127, :171-174
             return fabsf(h.z * R.f[RTT_F_C]) < 1.000001f;
         case RTT_BOUND_HALF_DISK:                                       // :151-159
-            return (fabsf(h.z * R.f[RTT_F_C]) < 1.000001f) && ((h.x * h.x + h.y * h.y) <= R.f[D_SB0SQ]);
+            return (fabsf(h.z * R.f[RTT_F_C]) < 1.000001f) & ((h.x * h.x + h.y * h.y) <= R.f[D_SB0SQ]);
         case RTT_BOUND_NAPPE:                                           // :208-217 (slope in the c slot)
             return (h.z * R.f[RTT_F_C]) >= -1e-6f;
         default:
@@ -378,20 +378,20 @@ RTT_HD float select_root(const RowDev& R, const Roots& q, V3 o, V3 d, int* which
     float t1 = q.t1, t2 = q.t2;
     if (K::bound(R) == RTT_BOUND_NONE) {
         if (t1 <= 1e-6f) t1 = inf;
-        if (q.n == 2 && t2 <= 1e-6f) t2 = inf;
+        if ((q.n == 2) & (t2 <= 1e-6f)) t2 = inf;
     } else {
         const bool inv = R.i[RTT_I_INVERT] != 0;
         bool k1 = surface_in_bounds<K>(R, along(o, t1, d));
         if (inv) k1 = !k1;
-        if (t1 <= 1e-6f || !k1) t1 = inf;
+        if ((t1 <= 1e-6f) | !k1) t1 = inf;
         if (q.n == 2) {
             bool k2 = surface_in_bounds<K>(R, along(o, t2, d));
             if (inv) k2 = !k2;
-            if (t2 <= 1e-6f || !k2) t2 = inf;
+            if ((t2 <= 1e-6f) | !k2) t2 = inf;
         }
     }
     if (q.n == 1) { *which = 0; return t1; }
-    if (is_nan(t1) || is_nan(t2)) { *which = 0; return rtt_nan(); }
+    if (is_nan(t1) | is_nan(t2)) { *which = 0; return rtt_nan(); }
     if (t2 < t1) { *which = 1; return t2; }
     *which = 0;
     return t1;
@@ -413,15 +413,16 @@ RTT_HD bool shape_in_bounds(const RowDev* rows, int r, V3 h) {
         case RTT_SHAPE_SPHERIC_FACE:                                    // geom/spherics.py:40-46
             return (h.x * h.x + h.y * h.y) <= R.f[D_HB0SQ];
         case RTT_SHAPE_SPHERIC_EDGE:                                    // geom/spherics.py:34-39
-            return (h.z >= hb[0]) && (h.z <= hb[1]);
+            return (h.z >= hb[0]) & (h.z <= hb[1]);
         case RTT_SHAPE_CYL_FACE:
         case RTT_SHAPE_CYL_EDGE: {                                      // geom/cylindrics.py:23-55
-            const bool ap = (h.x <= hb[1]) && (h.x >= hb[0]) && (h.y <= hb[3]) && (h.y >= hb[2]);   // slack pre-added
+            // `&`, not `&&`: four compares on one predicate chain instead of four short-circuit branches
+            const bool ap = (h.x <= hb[1]) & (h.x >= hb[0]) & (h.y <= hb[3]) & (h.y >= hb[2]);       // slack pre-added
             if (K::shape(R) == RTT_SHAPE_CYL_FACE) return ap;
             if (!ap) return false;                                      // outside the aperture: the sag tests cannot save it
             const float zf = sag_at(hb[4], h.y, hb[5]);
             const float zb = sag_at(hb[6], h.y, hb[7]);
-            return (h.z >= zf + 1e-4f) && (h.z <= zb - 1e-4f) && ap;
+            return (h.z >= zf + 1e-4f) & (h.z <= zb - 1e-4f) & ap;
         }
         case RTT_SHAPE_POLY: {                                          // geom/shape.py:122-132
             const int first = R.i[RTT_I_POLY_FIRST], cnt = R.i[RTT_I_POLY_COUNT];
@@ -658,7 +659,7 @@ RTT_HD Step interact(const RowDev& R, const Frames& F, float t, V3 p, V3 d, floa
 RTT_HD bool sensor_bin(float x, float y, float x0, float y0, float sx, float sy, int W, int H, int* ix, int* iy) {
     const float fx = floorf((x - x0) * sx);
     const float fy = floorf((y - y0) * sy);
-    if (!(fx >= 0.0f && fx < (float)W && fy >= 0.0f && fy < (float)H)) return false;
+    if (!((fx >= 0.0f) & (fx < (float)W) & (fy >= 0.0f) & (fy < (float)H))) return false;
     *ix = (int)fx; *iy = (int)fy;
     return true;
 }

@@ -19,6 +19,7 @@
 //     reduce parameter gradients warp -> block (shared) -> global
 //   * the non-sequential forward refills a lane as soon as its ray has ended
 #include <cuda_runtime.h>
+#include <type_traits>
 #include "rtt_core.cuh"
 #include "rtt_tile.cuh"
 #include "rtt_pair.cuh"
@@ -370,11 +371,11 @@ __device__ __noinline__ WalkState seq_walk_generic(const SeqFwdArgs& a, int lam,
     return w;
 }
 
-template <class K, int RPT, int BLK = kThreads>
+template <class K, int RPT, int BLK = kThreads, class M = unsigned long long>
 __device__ __forceinline__ void tile_row(const SmemTable& T, int S, int L, int r, const SeqFwdArgs& a, ImgCache cache,
                                          long long i0, V3 (&p)[RPT], V3 (&d)[RPT], float (&I)[RPT],
-                                         unsigned long long (&mask)[RPT], const int (&lam)[RPT],
-                                         const bool (&act)[RPT], unsigned long long bit) {
+                                         M (&mask)[RPT], const int (&lam)[RPT],
+                                         const bool (&act)[RPT], M bit) {
     const RowDev& R = T.rows[r];
     float t[RPT];
     bool hit[RPT];
@@ -404,8 +405,12 @@ __device__ __forceinline__ void tile_row(const SmemTable& T, int S, int L, int r
 // grid-stride loop, whose trip count is block-uniform).  With 1024-thread blocks the eight warps of an SM sub-partition
 // then fetch the same instructions at the same time: the build for rays generated in the kernel waits on instruction
 // fetch for 40 % of its stall samples (profiles/r2_forward_kernels.md, c4cam).
-template <int RPT, int MINB, bool GEN, int BLK = kThreads, bool SYNC = false>
+// NARROW: tables of at most 32 rows keep the hit mask and the row bit in ONE register each (the walk updates them at
+// every row and every hit; the 64-bit words of the general build cost two instructions each time and three more registers
+// of the 64 a 1024-thread block has).  The launcher picks it by a.tab.S; results are the same bits.
+template <int RPT, int MINB, bool GEN, int BLK = kThreads, bool SYNC = false, bool NARROW = false>
 __global__ void __launch_bounds__(BLK, MINB) k_trace_seq_fwd_tile(const __grid_constant__ SeqFwdArgs a) {
+    typedef typename std::conditional<NARROW, unsigned, unsigned long long>::type mask_t;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.tab.S, L = a.tab.L;
     SmemTable T = carve(smem_raw + kTileOffTable, S, L);
@@ -420,9 +425,11 @@ __global__ void __launch_bounds__(BLK, MINB) k_trace_seq_fwd_tile(const __grid_c
     for (long long base = (long long)blockIdx.x * tile; base < a.n; base += (long long)gridDim.x * tile) {
         if (SYNC) __syncthreads();
         const long long i0 = base + threadIdx.x;
-        V3 p[RPT], d[RPT];
+        const long long rest = a.n - base;
+        const int left = rest < tile ? (int)rest : (int)tile;            // rays of this tile (block-uniform): the per-ray
+        V3 p[RPT], d[RPT];                                               // bounds tests below are 32-bit compares against it
         float I[RPT];
-        unsigned long long mask[RPT];
+        mask_t mask[RPT];
         int lam[RPT];
         bool act[RPT], odd[RPT];
         // Rays in memory: the loads of ALL of this thread's rays are issued before the first value is consumed (one DRAM
@@ -433,47 +440,46 @@ __global__ void __launch_bounds__(BLK, MINB) k_trace_seq_fwd_tile(const __grid_c
         if (!GEN) {
 #pragma unroll
             for (int j = 0; j < RPT; ++j) {
-                const long long i = i0 + (long long)j * BLK;
-                rin[j] = fetch_ray_t<false>(a, skey, i < a.n ? i : a.n - 1, L > 0);
+                const int loc = (int)threadIdx.x + j * BLK;
+                rin[j] = fetch_ray_t<false>(a, skey, base + (loc < left ? loc : left - 1), L > 0);
             }
         }
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
             const long long i = i0 + (long long)j * BLK;
-            p[j] = v3(0.0f, 0.0f, 0.0f); d[j] = v3(0.0f, 0.0f, 0.0f); I[j] = 0.0f; lam[j] = 0; mask[j] = 0ull;
+            p[j] = v3(0.0f, 0.0f, 0.0f); d[j] = v3(0.0f, 0.0f, 0.0f); I[j] = 0.0f; lam[j] = 0; mask[j] = 0;
             act[j] = false; odd[j] = false;
-            if (i < a.n) {
+            if ((int)threadIdx.x + j * BLK < left) {
                 const RayIn ray = GEN ? fetch_ray_t<true>(a, skey, i, L > 0) : rin[j];
                 p[j] = ray.p; d[j] = ray.d; I[j] = ray.I;
                 lam[j] = (L > 0) ? wavelength_index(T, L, ray.wav) : 0;
-                act[j] = finite_ray(ray.p, ray.d) && regular_dir(ray.d);
+                act[j] = finite_ray(ray.p, ray.d) & regular_dir(ray.d);
                 odd[j] = !act[j];                                       // re-read below: un-normalised or non-finite ray
             }
         }
-        unsigned long long bit = 1ull;
+        mask_t bit = 1;
         for (int r = 0; r < S; ++r, bit += bit) {
-            const int op = T.rows[r].i[DI_TILE_OP];
-            const int kind = xf[r].kind;                                // warp-uniform
-            const int run = xf[r].run;
-            if (kind) {
+            const int ctl = xf[r].ctl;                                  // warp-uniform: opcode | frame-change kind << 8 | cull run << 16
+            if (ctl & 0xff00) {
 #pragma unroll
-                for (int j = 0; j < RPT; ++j) apply_xf(xf[r], p[j], d[j]);
+                for (int j = 0; j < RPT; ++j) apply_xf_kind(xf[r], ctl & 0x0200, p[j], d[j]);
             }
-            if (run > 0) {                                              // lens-edge rows: skip them when no lane can hit
+            if (ctl >= 0x10000) {                                       // lens-edge rows: skip them when no lane can hit
                 bool away = true;
 #pragma unroll
-                for (int j = 0; j < RPT; ++j) away = away && (!act[j] || edge_culled(xf[r], p[j], d[j]));
+                for (int j = 0; j < RPT; ++j) away = away & (!act[j] | edge_culled(xf[r], p[j], d[j]));
                 if (__all_sync(kFull, away)) {
-                    r += run - 1; bit <<= (run - 1);
+                    const int skip = (ctl >> 16) - 1;
+                    r += skip; bit <<= skip;
                     continue;
                 }
             }
-            switch (op) {                                               // warp-uniform
+            switch (ctl & 0xff) {                                       // warp-uniform
 #define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR)                                         \
-                case OP: tile_row<KTile<SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR>, RPT, BLK>(T, S, L, r, a, cache, i0, p, d, I, mask, lam, act, bit); break;
+                case OP: tile_row<KTile<SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR>, RPT, BLK, mask_t>(T, S, L, r, a, cache, i0, p, d, I, mask, lam, act, bit); break;
                 RTT_TILE_SPECS(RTT_X)
 #undef RTT_X
-                default: tile_row<KDyn, RPT, BLK>(T, S, L, r, a, cache, i0, p, d, I, mask, lam, act, bit); break;
+                default: tile_row<KDyn, RPT, BLK, mask_t>(T, S, L, r, a, cache, i0, p, d, I, mask, lam, act, bit); break;
             }
         }
         if (xf[S].kind) {
@@ -489,11 +495,11 @@ __global__ void __launch_bounds__(BLK, MINB) k_trace_seq_fwd_tile(const __grid_c
                 WalkState w;
                 w.p = ray.p; w.d = ray.d; w.I = ray.I; w.mask = 0ull;
                 if (finite_ray(ray.p, ray.d)) w = seq_walk_generic(a, lam[j], i, w);
-                p[j] = w.p; d[j] = w.d; I[j] = w.I; mask[j] = w.mask;
+                p[j] = w.p; d[j] = w.d; I[j] = w.I; mask[j] = (mask_t)w.mask;
             }
-            if (i < a.n) {
+            if ((int)threadIdx.x + j * BLK < left) {
                 if (a.opos) { store3(a.opos, i, p[j]); store3(a.odir, i, d[j]); a.ointen[i] = I[j]; }
-                if (a.hitmask) a.hitmask[i] = mask[j];
+                if (a.hitmask) a.hitmask[i] = (unsigned long long)mask[j];
             }
         }
     }
@@ -1894,16 +1900,16 @@ inline cudaError_t allow_smem(Kern kern, size_t bytes) {
 }
 
 #if defined(RTT_APPROX)
-template <int RPT, int MINB, bool GEN, int BLK = kThreads, bool SYNC = false, int kWaves = 4>
+template <int RPT, int MINB, bool GEN, int BLK = kThreads, bool SYNC = false, int kWaves = 4, bool NARROW = false>
 inline cudaError_t launch_tile_g(const SeqFwdArgs& a, cudaStream_t st) {
     const size_t smem = tile_smem_bytes(a.tab.S, a.tab.L);
-    if (cudaError_t e = allow_smem(k_trace_seq_fwd_tile<RPT, MINB, GEN, BLK, SYNC>, smem)) return e;
+    if (cudaError_t e = allow_smem(k_trace_seq_fwd_tile<RPT, MINB, GEN, BLK, SYNC, NARROW>, smem)) return e;
     const long long tiles = (a.n + (long long)BLK * RPT - 1) / ((long long)BLK * RPT);
     // several waves of grid-striding blocks: a block that lands on a busier SM costs 1/kWaves of a launch
     long long g = (long long)sm_count() * MINB * kWaves;
     if (tiles < g) g = tiles;
     if (g < 1) g = 1;
-    k_trace_seq_fwd_tile<RPT, MINB, GEN, BLK, SYNC><<<(int)g, BLK, smem, st>>>(a);
+    k_trace_seq_fwd_tile<RPT, MINB, GEN, BLK, SYNC, NARROW><<<(int)g, BLK, smem, st>>>(a);
     return cudaGetLastError();
 }
 template <int RPT, int MINB>
@@ -1911,9 +1917,9 @@ inline cudaError_t launch_tile(const SeqFwdArgs& a, cudaStream_t st) {
     return a.src.kind >= 0 ? launch_tile_g<RPT, MINB, true>(a, st) : launch_tile_g<RPT, MINB, false>(a, st);
 }
 // large blocks: RPT rays per thread, MINB blocks of BLK threads per SM, lock-step (SYNC) or free-running
-template <int RPT, int MINB, int BLK, bool SYNC, int WAVES = 4>
+template <int RPT, int MINB, int BLK, bool SYNC, int WAVES = 4, bool NARROW = false>
 inline cudaError_t launch_tile_big(const SeqFwdArgs& a, cudaStream_t st) {
-    return a.src.kind >= 0 ? launch_tile_g<RPT, MINB, true, BLK, SYNC, WAVES>(a, st) : launch_tile_g<RPT, MINB, false, BLK, SYNC, WAVES>(a, st);
+    return a.src.kind >= 0 ? launch_tile_g<RPT, MINB, true, BLK, SYNC, WAVES, NARROW>(a, st) : launch_tile_g<RPT, MINB, false, BLK, SYNC, WAVES, NARROW>(a, st);
 }
 // Builds of the frame-resident forward kernel (a.tune, include/rtt_b200.h RTT_MODE_TUNE_*), 256-thread blocks: 1 = 1 ray
 // per thread, 2 = 2 rays (80 regs), 3 = 2 rays (64 regs, 4 blocks / SM), 5 = 1 ray at 48 registers / five blocks per SM;
@@ -1979,7 +1985,7 @@ cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
         case 6: return launch_tile_big<2, 1, 1024, true>(a, st);
         case 7: return launch_tile_big<2, 1, 1024, false>(a, st);
         case 8: return launch_tile_big<2, 2, 512, false>(a, st);
-        case 12: return launch_tile_big<2, 1, 1024, false, 1>(a, st);
+        case 12: return a.tab.S <= 32 ? launch_tile_big<2, 1, 1024, false, 1, true>(a, st) : launch_tile_big<2, 1, 1024, false, 1>(a, st);
         case 13: return launch_tile_big<2, 1, 1024, false, 2>(a, st);
         case 16: return pair_can_stream(a) ? launch_pair<3, true, 11>(a, st) : launch_pair<3, false, 12>(a, st);
         case 17: return launch_pair<4, false, 12>(a, st);

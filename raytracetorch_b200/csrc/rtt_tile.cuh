@@ -133,6 +133,14 @@ RTT_HD void apply_xf(const Xf& x, V3& p, V3& d) {
     d = mul_R(d, x.M);
 }
 
+// the same with the kind taken from the row's control word (kind != 0; general = kind is 2)
+RTT_HD void apply_xf_kind(const Xf& x, bool general, V3& p, V3& d) {
+    const V3 c = ld3(x.c);
+    if (!general) { p = p + c; return; }
+    p = mul_R(p, x.M) + c;
+    d = mul_R(d, x.M);
+}
+
 // ---- lens-edge culling ---------------------------------------------------------------------------
 // The edge rows of a lens (the cylinder of a spherical lens, geom/spherics.py:34-39; the four side planes
 // of a cylindrical lens, geom/cylindrics.py:38-55) accept a hit only if its element-frame z lies between
@@ -211,16 +219,17 @@ RTT_HD void edge_run_at(const RowDev* rows, int S, Xf* xf, int r) {
 }
 
 RTT_HD bool edge_culled(const Xf& x, V3 p, V3 d) {
-    if ((p.z > x.zhi && d.z >= 0.0f) || (p.z < x.zlo && d.z <= 0.0f)) return true;          // (z)
+    // bitwise `&` / `|` on the compares throughout: predicate chains, no short-circuit branches (per-lane data)
+    if (((p.z > x.zhi) & (d.z >= 0.0f)) | ((p.z < x.zlo) & (d.z <= 0.0f))) return true;       // (z)
     if (x.ctype < 2 || d.z == 0.0f) return false;
     // (xy): time at which the ray leaves the z enclosure, stretched a little (a longer segment is conservative)
     const float zt = d.z > 0.0f ? x.zhi : x.zlo;
     const float te = fmaf(div_(zt - p.z, d.z), 1.0001f, 1e-4f);
     const float qx = fmaf(te, d.x, p.x), qy = fmaf(te, d.y, p.y);
     if (x.ctype == 2)
-        return p.x > x.b[0] && p.x < x.b[1] && p.y > x.b[2] && p.y < x.b[3] &&
-               qx > x.b[0] && qx < x.b[1] && qy > x.b[2] && qy < x.b[3];
-    return (p.x * p.x + p.y * p.y) < x.b[0] && (qx * qx + qy * qy) < x.b[0];
+        return (p.x > x.b[0]) & (p.x < x.b[1]) & (p.y > x.b[2]) & (p.y < x.b[3]) &
+               (qx > x.b[0]) & (qx < x.b[1]) & (qy > x.b[2]) & (qy < x.b[3]);
+    return ((p.x * p.x + p.y * p.y) < x.b[0]) & ((qx * qx + qy * qy) < x.b[0]);
 }
 
 // ---- box culling (non-sequential search) ----------------------------------------------------------
@@ -304,7 +313,7 @@ RTT_HD bool finite_ray(V3 p, V3 d) {
 // |d|^2 close enough to 1 (or exactly 0) for the per-row renormalisation to be the identity to 1e-6
 RTT_HD bool regular_dir(V3 d) {
     const float l2 = fma3(d.x, d.x, d.y, d.y, d.z, d.z);
-    return (l2 == 0.0f) || (fabsf(l2 - 1.0f) <= 4e-6f);
+    return (l2 == 0.0f) | (fabsf(l2 - 1.0f) <= 4e-6f);
 }
 
 // ---- lean root selection for lens faces (RTT_TILE_LEAN: FAST builds) ------------------------------
@@ -329,17 +338,17 @@ RTT_HD bool conic_half_hit(const RowDev& R, V3 o, V3 d, float& t) {
     if (fabsf(A) < 1e-6f) {                                             // flat face / ray along a generator
         const float Bs = (fabsf(B) < 1e-6f) ? 1e-6f : B;
         t = div_(-Cq, Bs);
-        return (t > 1e-6f) && (fabsf(fmaf(t, d.z, o.z) * c) < 1.000001f);
+        return (t > 1e-6f) & (fabsf(fmaf(t, d.z, o.z) * c) < 1.000001f);
     }
     const float disc = B * B - (4.0f * A) * Cq;
     const float sq = sqrt_(fabsf(disc));
     const float inv = rcp_(2.0f * A);
     const float r1 = (-B - sq) * inv, r2 = (-B + sq) * inv;
     const float lo = fminf(r1, r2), hi = fmaxf(r1, r2);
-    const bool oklo = (lo > 1e-6f) && (fabsf(fmaf(lo, d.z, o.z) * c) < 1.000001f);
-    const bool okhi = (hi > 1e-6f) && (fabsf(fmaf(hi, d.z, o.z) * c) < 1.000001f);
+    const bool oklo = (lo > 1e-6f) & (fabsf(fmaf(lo, d.z, o.z) * c) < 1.000001f);
+    const bool okhi = (hi > 1e-6f) & (fabsf(fmaf(hi, d.z, o.z) * c) < 1.000001f);
     t = oklo ? lo : hi;
-    return (disc >= 0.0f) && (oklo || okhi);
+    return (disc >= 0.0f) & (oklo | okhi);
 }
 
 // ---- one row ------------------------------------------------------------------------------------
