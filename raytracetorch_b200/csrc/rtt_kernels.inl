@@ -354,6 +354,7 @@ __device__ __forceinline__ void stage_tile(SmemTable& T, int S, Xf* xf) {
         // one control word per row for the pair kernel's loop: opcode | frame-change kind << 8 | cull run << 16
         xf[r].ctl = T.rows[r].i[DI_TILE_OP] | (xf[r].kind << 8) | (xf[r].run << 16);
     }
+    if (threadIdx.x == 0) xf[S].ctl = -1;                              // ends the tile kernel's walk (no row count in its loop)
     __syncthreads();
 }
 
@@ -425,9 +426,7 @@ __global__ void __launch_bounds__(BLK, MINB) k_trace_seq_fwd_tile(const __grid_c
     for (long long base = (long long)blockIdx.x * tile; base < a.n; base += (long long)gridDim.x * tile) {
         if (SYNC) __syncthreads();
         const long long i0 = base + threadIdx.x;
-        const long long rest = a.n - base;
-        const int left = rest < tile ? (int)rest : (int)tile;            // rays of this tile (block-uniform): the per-ray
-        V3 p[RPT], d[RPT];                                               // bounds tests below are 32-bit compares against it
+        V3 p[RPT], d[RPT];
         float I[RPT];
         mask_t mask[RPT];
         int lam[RPT];
@@ -440,8 +439,8 @@ __global__ void __launch_bounds__(BLK, MINB) k_trace_seq_fwd_tile(const __grid_c
         if (!GEN) {
 #pragma unroll
             for (int j = 0; j < RPT; ++j) {
-                const int loc = (int)threadIdx.x + j * BLK;
-                rin[j] = fetch_ray_t<false>(a, skey, base + (loc < left ? loc : left - 1), L > 0);
+                const long long i = i0 + (long long)j * BLK;
+                rin[j] = fetch_ray_t<false>(a, skey, i < a.n ? i : a.n - 1, L > 0);
             }
         }
 #pragma unroll
@@ -449,17 +448,20 @@ __global__ void __launch_bounds__(BLK, MINB) k_trace_seq_fwd_tile(const __grid_c
             const long long i = i0 + (long long)j * BLK;
             p[j] = v3(0.0f, 0.0f, 0.0f); d[j] = v3(0.0f, 0.0f, 0.0f); I[j] = 0.0f; lam[j] = 0; mask[j] = 0;
             act[j] = false; odd[j] = false;
-            if ((int)threadIdx.x + j * BLK < left) {
+            if (i < a.n) {
                 const RayIn ray = GEN ? fetch_ray_t<true>(a, skey, i, L > 0) : rin[j];
                 p[j] = ray.p; d[j] = ray.d; I[j] = ray.I;
                 lam[j] = (L > 0) ? wavelength_index(T, L, ray.wav) : 0;
-                act[j] = finite_ray(ray.p, ray.d) & regular_dir(ray.d);
+                act[j] = finite_ray(ray.p, ray.d) && regular_dir(ray.d);
                 odd[j] = !act[j];                                       // re-read below: un-normalised or non-finite ray
             }
         }
+        // The walk reads ONE control word per row (warp-uniform: opcode | frame-change kind << 8 | cull run << 16), fetched a
+        // row ahead so that its shared-memory latency runs under the previous row's arithmetic; xf[S].ctl = -1 ends it.
         mask_t bit = 1;
-        for (int r = 0; r < S; ++r, bit += bit) {
-            const int ctl = xf[r].ctl;                                  // warp-uniform: opcode | frame-change kind << 8 | cull run << 16
+        int next = xf[0].ctl;
+        for (int r = 0; next >= 0; ++r, bit += bit) {
+            const int ctl = next;
             if (ctl & 0xff00) {
 #pragma unroll
                 for (int j = 0; j < RPT; ++j) apply_xf_kind(xf[r], ctl & 0x0200, p[j], d[j]);
@@ -471,9 +473,11 @@ __global__ void __launch_bounds__(BLK, MINB) k_trace_seq_fwd_tile(const __grid_c
                 if (__all_sync(kFull, away)) {
                     const int skip = (ctl >> 16) - 1;
                     r += skip; bit <<= skip;
+                    next = xf[r + 1].ctl;
                     continue;
                 }
             }
+            next = xf[r + 1].ctl;
             switch (ctl & 0xff) {                                       // warp-uniform
 #define RTT_X(OP, SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR)                                         \
                 case OP: tile_row<KTile<SURF, BOUND, SHAPE, PHYS, RS_IDENT, SENSOR>, RPT, BLK, mask_t>(T, S, L, r, a, cache, i0, p, d, I, mask, lam, act, bit); break;
@@ -497,7 +501,7 @@ __global__ void __launch_bounds__(BLK, MINB) k_trace_seq_fwd_tile(const __grid_c
                 if (finite_ray(ray.p, ray.d)) w = seq_walk_generic(a, lam[j], i, w);
                 p[j] = w.p; d[j] = w.d; I[j] = w.I; mask[j] = (mask_t)w.mask;
             }
-            if ((int)threadIdx.x + j * BLK < left) {
+            if (i < a.n) {
                 if (a.opos) { store3(a.opos, i, p[j]); store3(a.odir, i, d[j]); a.ointen[i] = I[j]; }
                 if (a.hitmask) a.hitmask[i] = (unsigned long long)mask[j];
             }

@@ -85,7 +85,7 @@ RTT_HD void lean_face_replay(const RowDev& R, float mu_enter, float mu_exit, V3&
         const float inv = rcp_(2.0f * A);
         const float r1 = (-B - sq) * inv, r2 = (-B + sq) * inv;
         const float lo = fminf(r1, r2), hi = fmaxf(r1, r2);
-        const bool oklo = (lo > 1e-6f) && (fabsf(fmaf(lo, d.z, o.z) * c) < 1.000001f);
+        const bool oklo = (lo > 1e-6f) & (fabsf(fmaf(lo, d.z, o.z) * c) < 1.000001f);
         t = oklo ? lo : hi;
     }
     const V3 h = along(o, t, d);

@@ -313,7 +313,7 @@ RTT_HD bool finite_ray(V3 p, V3 d) {
 // |d|^2 close enough to 1 (or exactly 0) for the per-row renormalisation to be the identity to 1e-6
 RTT_HD bool regular_dir(V3 d) {
     const float l2 = fma3(d.x, d.x, d.y, d.y, d.z, d.z);
-    return (l2 == 0.0f) | (fabsf(l2 - 1.0f) <= 4e-6f);
+    return (l2 == 0.0f) || (fabsf(l2 - 1.0f) <= 4e-6f);
 }
 
 // ---- lean root selection for lens faces (RTT_TILE_LEAN: FAST builds) ------------------------------
