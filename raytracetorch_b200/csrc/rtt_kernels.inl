@@ -409,11 +409,14 @@ __device__ __forceinline__ void tile_row(const SmemTable& T, int S, int L, int r
 // NARROW: tables of at most 32 rows keep the hit mask and the row bit in ONE register each (the walk updates them at
 // every row and every hit; the 64-bit words of the general build cost two instructions each time and three more registers
 // of the 64 a 1024-thread block has).  The launcher picks it by a.tab.S; results are the same bits.
-template <int RPT, int MINB, bool GEN, int BLK = kThreads, bool SYNC = false, bool NARROW = false>
+// LUT: -1 = the wavelength table is tested at run time (L > 0) at every use — every refracting hit, every ray load;
+// 0 / 1 = the launcher has looked: no table / a table, and the tests fold at compile time.
+template <int RPT, int MINB, bool GEN, int BLK = kThreads, bool SYNC = false, bool NARROW = false, int LUT = -1>
 __global__ void __launch_bounds__(BLK, MINB) k_trace_seq_fwd_tile(const __grid_constant__ SeqFwdArgs a) {
     typedef typename std::conditional<NARROW, unsigned, unsigned long long>::type mask_t;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int S = a.tab.S, L = a.tab.L;
+    const int S = a.tab.S, L = (LUT == 0) ? 0 : a.tab.L;
+    if (LUT == 1) __builtin_assume(L > 0);
     SmemTable T = carve(smem_raw + kTileOffTable, S, L);
     Xf* xf = reinterpret_cast<Xf*>(smem_raw + kTileOffXf);
     ImgCache cache = img_cache_carve(smem_raw);
@@ -1904,16 +1907,16 @@ inline cudaError_t allow_smem(Kern kern, size_t bytes) {
 }
 
 #if defined(RTT_APPROX)
-template <int RPT, int MINB, bool GEN, int BLK = kThreads, bool SYNC = false, int kWaves = 4, bool NARROW = false>
+template <int RPT, int MINB, bool GEN, int BLK = kThreads, bool SYNC = false, int kWaves = 4, bool NARROW = false, int LUT = -1>
 inline cudaError_t launch_tile_g(const SeqFwdArgs& a, cudaStream_t st) {
     const size_t smem = tile_smem_bytes(a.tab.S, a.tab.L);
-    if (cudaError_t e = allow_smem(k_trace_seq_fwd_tile<RPT, MINB, GEN, BLK, SYNC, NARROW>, smem)) return e;
+    if (cudaError_t e = allow_smem(k_trace_seq_fwd_tile<RPT, MINB, GEN, BLK, SYNC, NARROW, LUT>, smem)) return e;
     const long long tiles = (a.n + (long long)BLK * RPT - 1) / ((long long)BLK * RPT);
     // several waves of grid-striding blocks: a block that lands on a busier SM costs 1/kWaves of a launch
     long long g = (long long)sm_count() * MINB * kWaves;
     if (tiles < g) g = tiles;
     if (g < 1) g = 1;
-    k_trace_seq_fwd_tile<RPT, MINB, GEN, BLK, SYNC, NARROW><<<(int)g, BLK, smem, st>>>(a);
+    k_trace_seq_fwd_tile<RPT, MINB, GEN, BLK, SYNC, NARROW, LUT><<<(int)g, BLK, smem, st>>>(a);
     return cudaGetLastError();
 }
 template <int RPT, int MINB>
@@ -1921,9 +1924,9 @@ inline cudaError_t launch_tile(const SeqFwdArgs& a, cudaStream_t st) {
     return a.src.kind >= 0 ? launch_tile_g<RPT, MINB, true>(a, st) : launch_tile_g<RPT, MINB, false>(a, st);
 }
 // large blocks: RPT rays per thread, MINB blocks of BLK threads per SM, lock-step (SYNC) or free-running
-template <int RPT, int MINB, int BLK, bool SYNC, int WAVES = 4, bool NARROW = false>
+template <int RPT, int MINB, int BLK, bool SYNC, int WAVES = 4, bool NARROW = false, int LUT = -1>
 inline cudaError_t launch_tile_big(const SeqFwdArgs& a, cudaStream_t st) {
-    return a.src.kind >= 0 ? launch_tile_g<RPT, MINB, true, BLK, SYNC, WAVES, NARROW>(a, st) : launch_tile_g<RPT, MINB, false, BLK, SYNC, WAVES, NARROW>(a, st);
+    return a.src.kind >= 0 ? launch_tile_g<RPT, MINB, true, BLK, SYNC, WAVES, NARROW, LUT>(a, st) : launch_tile_g<RPT, MINB, false, BLK, SYNC, WAVES, NARROW, LUT>(a, st);
 }
 // Builds of the frame-resident forward kernel (a.tune, include/rtt_b200.h RTT_MODE_TUNE_*), 256-thread blocks: 1 = 1 ray
 // per thread, 2 = 2 rays (80 regs), 3 = 2 rays (64 regs, 4 blocks / SM), 5 = 1 ray at 48 registers / five blocks per SM;
@@ -1989,7 +1992,9 @@ cudaError_t RTT_NAME(launch_seq_fwd)(const SeqFwdArgs& a, cudaStream_t st) {
         case 6: return launch_tile_big<2, 1, 1024, true>(a, st);
         case 7: return launch_tile_big<2, 1, 1024, false>(a, st);
         case 8: return launch_tile_big<2, 2, 512, false>(a, st);
-        case 12: return a.tab.S <= 32 ? launch_tile_big<2, 1, 1024, false, 1, true>(a, st) : launch_tile_big<2, 1, 1024, false, 1>(a, st);
+        case 12:
+            if (a.tab.S > 32) return launch_tile_big<2, 1, 1024, false, 1>(a, st);
+            return a.tab.L > 0 ? launch_tile_big<2, 1, 1024, false, 1, true, 1>(a, st) : launch_tile_big<2, 1, 1024, false, 1, true, 0>(a, st);
         case 13: return launch_tile_big<2, 1, 1024, false, 2>(a, st);
         case 16: return pair_can_stream(a) ? launch_pair<3, true, 11>(a, st) : launch_pair<3, false, 12>(a, st);
         case 17: return launch_pair<4, false, 12>(a, st);
