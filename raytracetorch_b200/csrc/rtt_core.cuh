@@ -529,18 +529,22 @@ RTT_HD V3 normal_local(const RowDev& R, V3 h, float* len_out) {
             const float ny = tc * h.y;
             const float nz = tc1k * h.z - 2.0f;
 #if defined(RTT_APPROX) && defined(__CUDA_ARCH__)
-            // FAST: one rsqrt instead of sqrt + add + rcp (drops the reference's +1e-8 on a length of ~2: 5e-9 relative)
-            const float l2 = fma3(nx, nx, ny, ny, nz, nz);
-            if (l2 > 1e-30f) {
+            // FAST: one rsqrt instead of sqrt + add + rcp (drops the reference's +1e-8 on a length of ~2: 5e-9 relative).
+            // The squared length is clamped like the lean adjoint's (rtt_lean.cuh) instead of branching to the slow form
+            // below: a conic's gradient (2cx, 2cy, 2c(1+k)z - 2) vanishes only at the centre of the quadric, never on it,
+            // and the branch cost five predicated-off instructions at every hit.
+            {
+                const float l2 = fmaxf(fma3(nx, nx, ny, ny, nz, nz), 1e-30f);
                 const float inv = rsqrt_(l2);
                 *len_out = l2 * inv;
                 return v3(-nx * inv, -ny * inv, -nz * inv);
             }
-#endif
+#else
             const float len = norm3(nx, ny, nz);
             const float den = len + 1e-8f;
             *len_out = len;
             return -div3(v3(nx, ny, nz), den);
+#endif
         }
     }
 }
