@@ -569,6 +569,52 @@ def test_maximum_table_size(runner_of, ieee_oracle, rtt_ns, variant):
 
 
 @pytest.mark.parametrize("variant", ["exact", "fast"])
+@pytest.mark.parametrize("n_lenses,with_stop,lut", [(10, True, False), (10, True, True), (11, False, False), (11, False, True)])
+def test_table_size_either_side_of_32_rows(runner_of, ieee_oracle, rtt_ns, variant, n_lenses, with_stop, lut):
+    """The default FAST forward build keeps the hit mask in 32 bits for tables of at most 32 rows and fixes the presence
+    of the wavelength table at compile time (csrc/rtt_kernels.inl, NARROW / LUT): 32 rows (10 singlets + inverted stop +
+    sensor; the sensor bit is bit 31) and 34 rows (11 singlets + sensor, the first size on the 64-bit build), each with and
+    without a wavelength table, forward against the oracle.  EXACT: bit for bit."""
+    import raytracetorch_b200 as rtt
+    E, G = rtt_ns.elements, rtt_ns.geom
+    hs = runner_of(variant)
+    els = [E.SingletLens(c1=0.004 * (1.0 + 0.1 * k), c2=-0.003, d=24.0, t=2.0, ior_glass=1.5 + 0.004 * k, ior_media=1.0,
+                         transform=scenes._T(rtt_ns, 4.0 * k)) for k in range(n_lenses)]
+    if with_stop:
+        els.append(E.CircularAperture(8.0, invert=True, transform=scenes._T(rtt_ns, 4.0 * n_lenses + 2.0)))
+    els.append(E.Sensor(G.Disk(radius=30.0, transform=scenes._T(rtt_ns, 100.0))))
+    kw_c, kw_o, kw_h = {}, {}, {}
+    n = 4096
+    rays = scenes.make_bundle(rtt_ns, ("coll", 9.0, -10.0, [0.01, -0.02, 0.0]), n, 3)
+    if lut:
+        lams = [450.0, 550.0, 650.0]
+        kw_c = dict(dispersion=rtt.Dispersion(lams, {els[k].ior_glass: [float(els[k].ior_glass) * (1.0 + 0.003 * (l - 1))
+                                                                       for l in range(3)] for k in (0, n_lenses - 1)}))
+    tab = rtt.compile_elements(els, **kw_c)
+    S = 3 * n_lenses + (1 if with_stop else 0) + 1
+    assert tab.n_rows == S and S in (32, 34)
+    if lut:
+        wav = torch.tensor(lams)[torch.arange(n) % 3].contiguous()
+        kw_o = dict(wavelength=wav, lut=tab.lut, lut_w=tab.lut_wavelengths)
+        kw_h = dict(wav=wav.numpy(), lut=tab.lut.detach().numpy(), lut_w=tab.lut_wavelengths.numpy())
+    o = ieee_oracle.trace_sequential(tab.f, tab.i_host, rays.pos, rays.dir, rays.intensity, **kw_o)
+    h = hs.trace_seq(tab.f.detach().numpy(), tab.i.numpy(), rays.pos.numpy(), rays.dir.numpy(), rays.intensity.numpy(),
+                     sensor_specs=[None], **kw_h)
+    bits = parity.mask_bits(h["hitmask"], S)
+    np.testing.assert_array_equal(bits, o["hit"].numpy())
+    assert bits[:, S - 1].mean() > 0.5 and bits[:, 0].all()              # the last row's bit (31 / 33) is in use
+    assert (h["hitmask"] >> np.uint64(S)).max() == 0                      # and nothing above it
+    if variant == "exact":
+        for k in ("pos", "dir", "intensity"):
+            np.testing.assert_array_equal(h[k], o[k].detach().numpy(), err_msg=k)
+    else:
+        scale = float(np.abs(o["pos"].detach().numpy()).max())
+        assert parity.vec_rel(h["pos"], o["pos"].detach().numpy(), floor=scale).max() <= parity.TOL_POINT
+        assert parity.vec_rel(h["dir"], o["dir"].detach().numpy()).max() <= parity.TOL_POINT
+        np.testing.assert_allclose(h["intensity"], o["intensity"].detach().numpy(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("variant", ["exact", "fast"])
 def test_maximum_rows_times_maximum_wavelengths(runner_of, rtt_ns, variant):
     """The advertised limits together: 64 rows x 8 sample wavelengths (table + index tables + block accumulators need
     more than the 48 KB default of dynamic shared memory: every launcher opts in).  Forward and adjoint against the
